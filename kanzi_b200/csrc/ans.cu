@@ -1,0 +1,795 @@
+// ans.cu — rANS order-0 / order-1 encode and decode kernels (sm_100a).
+//
+// Replaces K/entropy/ANSRangeEncoder.java and ANSRangeDecoder.java with the
+// same bitstream: per chunk a 3-bit logRange, per-context alphabet + frequencies (encodeHeader :211-252),
+// varint(byte count), four 32-bit states, bytes.  The unit of parallel work is what the format fixes:
+// one chunk (16 KiB for order 0, 4 MiB for order 1) = one coupled 4-state stream.  Four lanes run the
+// four states; the shared read/write cursor is resolved per step with a warp ballot (the reference's
+// st0..st3 / st3..st0 order becomes a popcount of the lower lanes' renormalisation flags).
+// Order 0 keeps all per-chunk tables in shared memory (32 chunks per CTA); order 1 tables (512 KiB per
+// chunk) live in global memory and stay L2-resident.
+//
+// HBM traffic per chunk (algorithmic): encode reads n bytes twice (histogram + code) and writes the
+// coded bytes; decode reads coded bytes once and writes n bytes.  Both are bound by the dependent
+// table-lookup chain of the rANS recurrence, not by bandwidth.
+#include "kzg_common.cuh"
+#include "kzg_entropy.cuh"
+
+#define ANS_TOP (1 << 15)
+
+// ---- EntropyUtils.normalizeFrequencies (K/entropy/EntropyUtils.java:141-250), one thread ------------------
+// freqs: 256 counts (in/out), alphabet: out.  Order-sensitive, restated literally (tie-breaks matter).
+__device__ int ans_normalize(u32* freqs, u8* alphabet, int totalFreq, int scale) {
+  if (totalFreq == 0) return 0;
+  int alphabetSize = 0;
+  if (totalFreq == scale) {
+    for (int i = 0; i < 256; i++)
+      if (freqs[i] != 0) alphabet[alphabetSize++] = (u8)i;
+    return alphabetSize;
+  }
+  int sumScaledFreq = 0, sumFreq = 0, idxMax = 0;
+  const bool small = ((u64)totalFreq * (u64)scale) < 0x7FFFFFFFull;
+  for (int i = 0; i < 256; i++) {
+    const int f = (int)freqs[i];
+    if (f == 0) continue;
+    int scaledFreq;
+    if (small) {
+      const u32 sf = (u32)f * (u32)scale;
+      scaledFreq = (sf <= (u32)totalFreq) ? 1 : (int)((sf + ((u32)totalFreq >> 1)) / (u32)totalFreq);
+    } else {
+      const u64 sf = (u64)f * (u64)scale;
+      scaledFreq = (sf <= (u64)totalFreq) ? 1 : (int)((sf + ((u64)totalFreq >> 1)) / (u64)totalFreq);
+    }
+    alphabet[alphabetSize++] = (u8)i;
+    sumScaledFreq += scaledFreq;
+    freqs[i] = (u32)scaledFreq;
+    sumFreq += f;
+    if (scaledFreq > (int)freqs[idxMax]) idxMax = i;
+    if (sumFreq >= totalFreq) break;
+  }
+  if (alphabetSize == 0) return 0;
+  if (alphabetSize == 1) { freqs[alphabet[0]] = (u32)scale; return 1; }
+  if (sumScaledFreq == scale) return alphabetSize;
+  int delta = sumScaledFreq - scale;
+  const int errThr = (int)freqs[idxMax] >> 4;
+  if (abs(delta) <= errThr) { freqs[idxMax] -= delta; return alphabetSize; }
+  if (delta < 0) { delta += errThr; freqs[idxMax] += errThr; }
+  else { delta -= errThr; freqs[idxMax] -= errThr; }
+  const int inc = (delta > 0) ? -1 : 1;
+  delta = abs(delta);
+  int round = 0;
+  while ((++round < 6) && (delta > 0)) {
+    int adjustments = 0;
+    for (int i = 0; i < alphabetSize; i++) {
+      const int idx = alphabet[i];
+      if ((int)freqs[idx] <= 2) continue;
+      freqs[idx] += inc;
+      adjustments++;
+      delta--;
+      if (delta == 0) break;
+    }
+    if (adjustments == 0) break;
+  }
+  freqs[idxMax] = (u32)max((int)freqs[idxMax] - delta, 1);
+  return alphabetSize;
+}
+
+// EntropyUtils.encodeAlphabet (K/entropy/EntropyUtils.java:38-75)
+__device__ void ans_encode_alphabet(BitWriterD& bw, const u8* alphabet, int count) {
+  if (count == 0) { bw.write(0, 1); bw.write(1, 1); return; }
+  if (count == 256) { bw.write(0, 1); bw.write(0, 1); return; }
+  bw.write(1, 1);
+  const int lastMask = alphabet[count - 1] >> 3;
+  bw.write((u32)lastMask, 5);
+  int k = 0;
+  for (int i = 0; i <= lastMask; i++) {
+    u32 m = 0;
+    while (k < count && (alphabet[k] >> 3) == i) { m |= 1u << (alphabet[k] & 7); k++; }
+    bw.write(m, 8);
+  }
+}
+
+// ANSRangeEncoder.encodeHeader (K/entropy/ANSRangeEncoder.java:211-252)
+__device__ void ans_encode_header(BitWriterD& bw, int alphabetSize, const u8* alphabet, const u32* freqs, int lr) {
+  ans_encode_alphabet(bw, alphabet, alphabetSize);
+  if (alphabetSize <= 1) return;
+  const int chkSize = (alphabetSize >= 64) ? 8 : 6;
+  int llr = 3;
+  while ((1 << llr) <= lr) llr++;
+  for (int i = 1; i < alphabetSize; i += chkSize) {
+    int mx = (int)freqs[alphabet[i]] - 1;
+    int logMax = 0;
+    const int endj = (i + chkSize < alphabetSize) ? i + chkSize : alphabetSize;
+    for (int j = i + 1; j < endj; j++) mx = max(mx, (int)freqs[alphabet[j]] - 1);
+    while ((1 << logMax) <= mx) logMax++;
+    bw.write((u32)logMax, llr);
+    if (logMax == 0) continue;
+    for (int j = i; j < endj; j++) bw.write(freqs[alphabet[j]] - 1, logMax);
+  }
+}
+
+// ANSRangeEncoder.Symbol.reset (K/entropy/ANSRangeEncoder.java:473-496) packed into two words:
+//   a = invFreq (32 bits);  b = bias (13+ bits) | cmplFreq << 14 | (invShift - 32) << 28
+// xMax is recomputed as freq << (31 - lr) with freq = scale - cmplFreq.
+__device__ __forceinline__ void ans_symbol_reset(u32& a, u32& b, int cumFreq, int freq, int lr) {
+  if (freq >= (1 << lr)) freq = (1 << lr) - 1;
+  const u32 cmpl = (u32)((1 << lr) - freq);
+  if (freq < 2) {
+    a = 0xFFFFFFFFu;
+    b = (u32)(cumFreq + (1 << lr) - 1) | (cmpl << 14) | (0u << 28);
+  } else {
+    int shift = 0;
+    while (freq > (1 << shift)) shift++;
+    a = (u32)((((1ull << (shift + 31)) + (u64)freq - 1) / (u64)freq) & 0xFFFFFFFFull);
+    b = (u32)cumFreq | (cmpl << 14) | ((u32)(shift - 1) << 28);
+  }
+}
+
+// ANSRangeEncoder.encodeSymbol (:315-328) minus the byte emission
+__device__ __forceinline__ u32 ans_enc_step(u32 st, u32 a, u32 b) {
+  const u32 q = __umulhi(st, a) >> (b >> 28);
+  return st + (b & 0x3FFF) + q * ((b >> 14) & 0x3FFF);
+}
+
+// ================================================================================================================
+// order 0 encode: grid (ceil(maxChunks/32), nBlocks), 128 threads; group of 4 lanes = one chunk
+// ================================================================================================================
+#define A0_GROUPS 32
+struct A0EncSmem {
+  u32 freq[A0_GROUPS][256];
+  u32 symA[A0_GROUPS][256];
+  u32 symB[A0_GROUPS][256];
+  u8 alpha[A0_GROUPS][256];
+};
+
+__global__ void __launch_bounds__(128) ans0_encode_kernel(const KzgBlock* __restrict__ blocks, KzgEntParams P) {
+  extern __shared__ __align__(16) u8 smem_raw[];
+  A0EncSmem& S = *reinterpret_cast<A0EncSmem*>(smem_raw);
+  const int g = threadIdx.x >> 2, j = threadIdx.x & 3;
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * A0_GROUPS + g;
+  const KzgBlock& B = blocks[b];
+  const int len = (B.status == 0 && B.entropy == P.entropy) ? B.curLen : 0;
+  const u8* __restrict__ data = B.cur;
+  const int chunkSize = P.chunkSize;
+  const int lr = 12;
+  const i64 gidx = (i64)b * P.maxChunks + c;
+  const bool rawAll = (len <= 32);          // ANSRangeEncoder.encode :267-270: count <= 32 -> raw bytes
+  const int start = c * chunkSize;
+  const bool active = (!rawAll) && (c < P.maxChunks) && (start < len);
+  const int end = active ? min(start + chunkSize, len) : 0;
+  u8* hdr = P.hdrBuf + gidx * (i64)P.hdrStride;
+  u8* pay = P.payBuf + gidx * (i64)P.payStride;
+  const int bufLen = P.payStride - 16;      // scratch emulating `this.buffer` (filled from its end)
+  KzgSeg* segs = P.segs + (i64)b * P.segsPerBlock + 1 + (i64)c * 2;
+
+  if (rawAll && c == 0 && j == 0 && len > 0) {
+    // whole call stored raw: one segment pointing at the data itself
+    segs[0] = KzgSeg{data, 0, 0, (u64)len * 8};
+    segs[1] = KzgSeg{nullptr, 0, 0, 0};
+  } else if (!active && c < P.maxChunks && j == 0) {
+    segs[0] = KzgSeg{nullptr, 0, 0, 0};
+    segs[1] = KzgSeg{nullptr, 0, 0, 0};
+  }
+
+  // ---- histogram (Global.computeHistogramOrder0 :274-330) ----
+  for (int k = j; k < 256; k += 4) S.freq[g][k] = 0;
+  __syncwarp();
+  if (active) {
+    for (int i = start + j; i < end; i += 4) atomicAdd(&S.freq[g][data[i]], 1u);
+  }
+  __syncwarp();
+
+  // ---- statistics + header (rebuildStatistics :419-449, updateFrequencies :171-200), lane 0 of the group ----
+  int alphabetSize = 0;
+  i64 hdrBits = 0;
+  if (active && j == 0) {
+    BitWriterD bw(hdr);
+    bw.write((u32)(lr - 8), 3);
+    alphabetSize = ans_normalize(S.freq[g], S.alpha[g], end - start, 1 << lr);
+    if (alphabetSize > 0) {
+      int sum = 0;
+      for (int k = 0; k < alphabetSize; k++) {
+        const int s = S.alpha[g][k];
+        const int f = (int)S.freq[g][s];
+        ans_symbol_reset(S.symA[g][s], S.symB[g][s], sum, f, lr);
+        sum += f;
+      }
+    }
+    ans_encode_header(bw, alphabetSize, S.alpha[g], S.freq[g], lr);
+    if (alphabetSize <= 1) {     // chunk skipped after its header (:296-299)
+      bw.flush();
+      segs[0] = KzgSeg{hdr, 0, 0, (u64)bw.bits()};
+      segs[1] = KzgSeg{nullptr, 0, 0, 0};
+    } else {
+      hdrBits = bw.bits();
+      bw.flush();
+    }
+  }
+  alphabetSize = __shfl_sync(0xFFFFFFFFu, alphabetSize, (threadIdx.x & 31) & ~3);
+  __syncwarp();
+  const bool coding = active && (alphabetSize > 1);
+
+  // ---- encodeChunk (:337-407): backwards, 4 interleaved states ----
+  const int end4 = start + ((end - start) & -4);
+  int n = bufLen - 1;
+  if (coding) {
+    const int tail = end - end4;
+    if (j == 0) for (int i = end - 1; i >= end4; i--) pay[n - (end - 1 - i)] = data[i];
+    n -= tail;
+  }
+  int steps = coding ? ((end4 - start) >> 2) : 0;
+  int maxSteps = steps;
+  for (int o = 16; o > 0; o >>= 1) maxSteps = max(maxSteps, __shfl_xor_sync(0xFFFFFFFFu, maxSteps, o));
+  u32 st = ANS_TOP;
+  int idx = n;
+  const int gshift = (threadIdx.x & 31) & ~3;
+  const u32 lowerMask = (1u << j) - 1;
+  for (int s = 0; s < maxSteps; s++) {
+    const bool on = s < steps;
+    u32 a = 0, bb = 0;
+    bool x = false;
+    if (on) {
+      const int i = end4 - 1 - 4 * s;
+      const int sym = data[i - j];
+      a = S.symA[g][sym]; bb = S.symB[g][sym];
+      const u32 xMax = ((u32)(1 << lr) - ((bb >> 14) & 0x3FFF)) << (31 - lr);
+      x = (st >= xMax);
+    }
+    const u32 m = (__ballot_sync(0xFFFFFFFFu, x) >> gshift) & 0xFu;
+    if (on) {
+      if (x) {
+        const int pos = idx - 2 * __popc(m & lowerMask);
+        pay[pos] = (u8)st;
+        pay[pos - 1] = (u8)(st >> 8);
+        st >>= 16;
+      }
+      idx -= 2 * __popc(m);
+      st = ans_enc_step(st, a, bb);
+    }
+  }
+  // gather the four final states in lane 0 of the group
+  const u32 s1 = __shfl_sync(0xFFFFFFFFu, st, gshift + 1);
+  const u32 s2 = __shfl_sync(0xFFFFFFFFu, st, gshift + 2);
+  const u32 s3 = __shfl_sync(0xFFFFFFFFu, st, gshift + 3);
+  if (coding && j == 0) {
+    n = idx + 1;
+    BitWriterD bw(hdr);
+    // continue the header bit string: re-open at hdrBits (bytes already flushed; keep partial byte)
+    bw.nbytes = hdrBits >> 3; bw.nacc = (int)(hdrBits & 7);
+    bw.acc = (bw.nacc > 0) ? ((u64)hdr[bw.nbytes] >> (8 - bw.nacc)) : 0;
+    write_varint(bw, bufLen - n);
+    bw.write(st, 32); bw.write(s1, 32); bw.write(s2, 32); bw.write(s3, 32);
+    bw.flush();
+    segs[0] = KzgSeg{hdr, 0, 0, (u64)bw.bits()};
+    segs[1] = KzgSeg{pay + n, 0, 0, (u64)(bufLen - n) * 8};
+  }
+}
+
+// ================================================================================================================
+// chunk scan for decode (order 0 and 1): one thread per block walks the chunk headers to find where each
+// chunk starts (the only serial part of decoding: chunk k+1 starts where chunk k's byte count says).
+// ================================================================================================================
+__device__ int ans_skip_alphabet(BitReaderD& br) {   // EntropyUtils.decodeAlphabet sizes only
+  if (br.read(1) == 0) return (br.read(1) == 1) ? 0 : 256;
+  const int lastMask = (int)br.read(5);
+  int count = 0;
+  for (int i = 0; i <= lastMask; i++) count += __popc(br.read(8));
+  return count;
+}
+
+__global__ void ans_scan_kernel(KzgBlock* __restrict__ blocks, int nBlocks, KzgEntParams P, int order) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nBlocks) return;
+  KzgBlock& B = blocks[b];
+  if (B.status != 0 || B.entropy != P.entropy) return;
+  const int len = B.preLen;
+  KzgChunkInfo* ci = P.chunks + (i64)b * P.maxChunks;
+  if (len <= 32) {   // raw (ANSRangeDecoder.decode :193-196)
+    B.entBits = (i64)len * 8;
+    if ((i64)len * 8 > B.srcBits) B.status = -KZG_ERR_PROCESS_BLOCK;
+    return;
+  }
+  BitReaderD br(P.stream, (u64)B.srcBit, (u64)(B.srcBit + B.srcBits));
+  const int nChunks = (len + P.chunkSize - 1) / P.chunkSize;
+  const int dim = 255 * order + 1;
+  for (int c = 0; c < nChunks; c++) {
+    KzgChunkInfo info;
+    info.hdrBit = (i64)br.pos;
+    const int lr = 8 + (int)br.read(3);
+    int llr = 3;
+    while ((1 << llr) <= lr) llr++;
+    int res = 0;
+    for (int k = 0; k < dim; k++) {
+      const int alphabetSize = ans_skip_alphabet(br);
+      if (alphabetSize == 0) continue;
+      const int chkSize = (alphabetSize >= 64) ? 8 : 6;
+      for (int i = 1; i < alphabetSize; i += chkSize) {
+        const int logMax = (int)br.read(llr);
+        const int endj = (i + chkSize < alphabetSize) ? i + chkSize : alphabetSize;
+        br.pos += (u64)(logMax * (endj - i));
+      }
+      res += alphabetSize;
+      if (br.overrun()) break;
+    }
+    info.alphabetSize = res;
+    info.sz = 0; info.payBit = 0;
+    if (res == 0 || br.overrun()) { B.status = -KZG_ERR_PROCESS_BLOCK; return; }   // decode returns early (:218-219)
+    if (!(order == 0 && res == 1)) {
+      const i32 sz = read_varint(br);
+      if (sz < 0 || sz >= (1 << 27)) { B.status = -KZG_ERR_PROCESS_BLOCK; return; }
+      info.st[0] = br.read(32); info.st[1] = br.read(32); info.st[2] = br.read(32); info.st[3] = br.read(32);
+      info.sz = sz;
+      info.payBit = (i64)br.pos;
+      br.pos += (u64)sz * 8;
+    }
+    if (br.overrun()) { B.status = -KZG_ERR_PROCESS_BLOCK; return; }
+    ci[c] = info;
+  }
+  B.entBits = (i64)br.pos - B.srcBit;
+}
+
+// 16 bits at byte offset `off` of a payload that starts at absolute bit `payBit`; bytes at or beyond `sz`
+// read as zero (ANSRangeDecoder zero-fills its buffer, :372-375)
+__device__ __forceinline__ u32 ans_pay16(const u8* __restrict__ stream, i64 payBit, int off, int sz) {
+  const u64 pos = (u64)payBit + (u64)off * 8;
+  const u8* p = stream + (pos >> 3);
+  const int sh = (int)(pos & 7);
+  const u32 w = ((u32)p[0] << 16) | ((u32)p[1] << 8) | (u32)p[2];
+  u32 v = (w >> (8 - sh)) & 0xFFFFu;
+  if (off + 2 > sz) v = (off >= sz) ? 0 : (v & 0xFF00u);
+  return v;
+}
+__device__ __forceinline__ u32 ans_pay8(const u8* __restrict__ stream, i64 payBit, int off) {
+  return get_bits(stream, (u64)payBit + (u64)off * 8, 8);
+}
+
+// ANSRangeDecoder.decodeHeader (:452-544) for one context: fills freq[256] (0 for absent symbols).
+// Returns alphabetSize, or -1 on an invalid header.
+__device__ int ans_decode_ctx_header(BitReaderD& br, int lr, int llr, u16* freq, u8* alphabet, bool& cleared) {
+  int alphabetSize = 0;
+  if (br.read(1) == 0) {
+    if (br.read(1) == 1) return 0;
+    alphabetSize = 256;
+    for (int i = 0; i < 256; i++) alphabet[i] = (u8)i;
+  } else {
+    const int lastMask = (int)br.read(5);
+    for (int i = 0; i <= lastMask; i++) {
+      const u32 mask = br.read(8);
+      for (int jj = 0; jj < 8; jj++)
+        if (mask & (1u << jj)) alphabet[alphabetSize++] = (u8)((i << 3) + jj);
+    }
+  }
+  if (alphabetSize == 0) return 0;
+  const int scale = 1 << lr;
+  if (alphabetSize != 256) { for (int i = 0; i < 256; i++) freq[i] = 0; cleared = true; }
+  const int chkSize = (alphabetSize >= 64) ? 8 : 6;
+  int sum = 0;
+  for (int i = 1; i < alphabetSize; i += chkSize) {
+    const int logMax = (int)br.read(llr);
+    if ((1 << logMax) > scale) return -1;
+    const int endj = (i + chkSize < alphabetSize) ? i + chkSize : alphabetSize;
+    for (int jj = i; jj < endj; jj++) {
+      const int f = (logMax == 0) ? 1 : (int)(1 + br.read(logMax));
+      if (f <= 0 || f >= scale) return -1;
+      freq[alphabet[jj]] = (u16)f;
+      sum += f;
+    }
+  }
+  if (scale <= sum) return -1;
+  freq[alphabet[0]] = (u16)(scale - sum);   // scale - sum may be 1<<lr when alphabetSize == 1 (stored mod 2^16: lr <= 15)
+  return alphabetSize;
+}
+
+// ================================================================================================================
+// order 0 decode: grid (ceil(maxChunks/32), nBlocks), 128 threads; group of 4 lanes = one chunk
+// ================================================================================================================
+struct A0DecSmem {
+  u8 f2s[A0_GROUPS][4096];
+  u32 sym[A0_GROUPS][256];      // freq | cumFreq << 16
+  u16 freq[A0_GROUPS][256];
+  u8 alpha[A0_GROUPS][256];
+};
+
+__global__ void __launch_bounds__(128) ans0_decode_kernel(KzgBlock* __restrict__ blocks, KzgEntParams P) {
+  extern __shared__ __align__(16) u8 smem_raw[];
+  A0DecSmem& S = *reinterpret_cast<A0DecSmem*>(smem_raw);
+  const int g = threadIdx.x >> 2, j = threadIdx.x & 3;
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * A0_GROUPS + g;
+  KzgBlock& B = blocks[b];
+  const bool blockOk = (B.status == 0 && B.entropy == P.entropy);
+  const int len = blockOk ? B.preLen : 0;
+  u8* __restrict__ out = B.cur;
+  const u8* __restrict__ stream = P.stream;
+  const int chunkSize = P.chunkSize;
+  const int start = c * chunkSize;
+
+  if (len <= 32) {   // raw
+    if (blockOk && c == 0 && j == 0) for (int i = 0; i < len; i++) out[i] = (u8)get_bits(stream, (u64)B.srcBit + 8ull * i, 8);
+    return;          // whole CTA shares (b): uniform exit for every warp
+  }
+  const bool active = (c < P.maxChunks) && (start < len);
+  const int end = active ? min(start + chunkSize, len) : 0;
+  KzgChunkInfo info;
+  info.alphabetSize = 0;
+  if (active) info = P.chunks[(i64)b * P.maxChunks + c];
+
+  // ---- header -> tables ----
+  int lr = 12;
+  int bad = 0;
+  if (active && j == 0) {
+    BitReaderD br(stream, (u64)info.hdrBit, (u64)(B.srcBit + B.srcBits));
+    lr = 8 + (int)br.read(3);
+    int llr = 3;
+    while ((1 << llr) <= lr) llr++;
+    bool cleared = false;
+    if (lr > 12) bad = 1;     // order-0 tables are sized for the reference's logRange 12 (ANSRangeEncoder :40)
+    else {
+      const int as = ans_decode_ctx_header(br, lr, llr, S.freq[g], S.alpha[g], cleared);
+      if (as <= 0) bad = 1;
+      else {
+        int sum = 0;
+        for (int i = 0; i < 256; i++) {
+          const int f = S.freq[g][i];
+          if (f == 0 && as != 256) continue;
+          if (as == 256 && f == 0) { bad = 1; break; }
+          const int fe = (f >= (1 << lr)) ? (1 << lr) - 1 : f;
+          S.sym[g][i] = (u32)fe | ((u32)sum << 16);
+          sum += f;
+        }
+      }
+    }
+  }
+  const int gl = (threadIdx.x & 31) & ~3;
+  lr = __shfl_sync(0xFFFFFFFFu, lr, gl);
+  bad = __shfl_sync(0xFFFFFFFFu, bad, gl);
+  __syncwarp();
+  const bool single = active && (info.alphabetSize == 1);
+  const bool coding = active && !single && !bad;
+  if (coding) {   // f2s fill, 4 lanes interleaved over symbols
+    for (int s = j; s < 256; s += 4) {
+      const u32 f = S.freq[g][s];
+      if (f == 0) continue;
+      const u32 cum = S.sym[g][s] >> 16;
+      for (u32 k = 0; k < f; k++) S.f2s[g][cum + k] = (u8)s;
+    }
+  }
+  if (single) {     // shortcut for chunks with only one symbol (:221-224)
+    const u8 v = S.alpha[g][0];
+    for (int i = start + j; i < end; i += 4) out[i] = v;
+  }
+  __syncwarp();
+
+  // ---- decodeChunkV2 (:357-440) ----
+  const int end4 = start + ((end - start) & -4);
+  int steps = coding ? ((end4 - start) >> 2) : 0;
+  int maxSteps = steps;
+  for (int o = 16; o > 0; o >>= 1) maxSteps = max(maxSteps, __shfl_xor_sync(0xFFFFFFFFu, maxSteps, o));
+  i32 st = coding ? (i32)info.st[3 - j] : 0;     // lane j decodes symbol i+j with state st(3-j) (:392-405)
+  const int mask = (1 << lr) - 1;
+  int cursor = 0;
+  const u32 lowerMask = (1u << j) - 1;
+  const i64 payBit = info.payBit;
+  const int sz = info.sz;
+  for (int s = 0; s < maxSteps; s++) {
+    const bool on = s < steps;
+    bool need = false;
+    if (on) {
+      const int slot = st & mask;
+      const int sym = S.f2s[g][slot];
+      const u32 fc = S.sym[g][sym];
+      out[start + 4 * s + j] = (u8)sym;
+      st = (i32)((fc & 0xFFFFu) * ((u32)st >> lr) + (u32)slot - (fc >> 16));
+      need = st < ANS_TOP;
+    }
+    const u32 m = (__ballot_sync(0xFFFFFFFFu, need) >> gl) & 0xFu;
+    if (on) {
+      if (need) {
+        const int off = cursor + 2 * __popc(m & lowerMask);
+        st = (i32)(((u32)st << 16) | ans_pay16(stream, payBit, off, sz));
+      }
+      cursor += 2 * __popc(m);
+    }
+  }
+  if (coding) {
+    const int tail = end - end4;
+    if (j == 0) {
+      for (int i = 0; i < tail; i++) out[end4 + i] = (cursor + i < sz) ? (u8)ans_pay8(stream, payBit, cursor + i) : 0;
+      if (cursor + tail != sz) atomicExch(&B.status, -KZG_ERR_PROCESS_BLOCK);   // decodeChunkV2 returns n == sz
+    }
+  }
+  if (active && bad && j == 0) atomicExch(&B.status, -KZG_ERR_PROCESS_BLOCK);
+}
+
+// ================================================================================================================
+// order 1: one warp per chunk (4 MiB), 4 lanes code, lane 0 builds the 256-context tables in global memory
+// ================================================================================================================
+// per-chunk global scratch (encode): symA[256][256], symB[256][256], freq[256][257] (u32), alpha[256]
+// per-chunk global scratch (decode): f2s[256][2048] (u8), sym[256][256] (u32), freq[256] (u16), alpha[256]
+
+__global__ void __launch_bounds__(32) ans1_encode_kernel(const KzgBlock* __restrict__ blocks, KzgEntParams P) {
+  const int lane = threadIdx.x;
+  const int b = blockIdx.y;
+  const int c = blockIdx.x;
+  const KzgBlock& B = blocks[b];
+  const int len = (B.status == 0 && B.entropy == P.entropy) ? B.curLen : 0;
+  const u8* __restrict__ data = B.cur;
+  const int chunkSize = P.chunkSize;     // 4 MiB
+  const int lr = 11;
+  const i64 gidx = (i64)b * P.maxChunks + c;
+  KzgSeg* segs = P.segs + (i64)b * P.segsPerBlock + 1 + (i64)c * 2;
+  if (len <= 32) {
+    if (lane == 0) {
+      segs[0] = (c == 0 && len > 0) ? KzgSeg{data, 0, 0, (u64)len * 8} : KzgSeg{nullptr, 0, 0, 0};
+      segs[1] = KzgSeg{nullptr, 0, 0, 0};
+    }
+    return;
+  }
+  const int start = c * chunkSize;
+  if (start >= len) {
+    if (lane == 0) { segs[0] = KzgSeg{nullptr, 0, 0, 0}; segs[1] = KzgSeg{nullptr, 0, 0, 0}; }
+    return;
+  }
+  const int end = min(start + chunkSize, len);
+  u8* hdr = P.hdrBuf + gidx * (i64)P.hdrStride;
+  u8* pay = P.payBuf + gidx * (i64)P.payStride;
+  const int bufLen = P.payStride - 16;
+  u32* tab = P.tabBuf + gidx * (i64)P.tabStride;       // u32 units
+  u32* symA = tab;                       // [256][256]
+  u32* symB = tab + 65536;               // [256][256]
+  u32* freq = tab + 2 * 65536;           // [256][257]
+  u8* alpha = (u8*)(tab + 2 * 65536 + 256 * 257);
+
+  // ---- order-1 histogram: first byte of each quarter in context 0 (rebuildStatistics :430-446) ----
+  for (int k = lane; k < 256 * 257; k += 32) freq[k] = 0;
+  for (int k = lane; k < 2 * 65536; k += 32) tab[k] = 0;   // Symbol objects are re-created per encode() call (:277-282): zero = "new Symbol()"
+  __syncwarp();
+  {
+    const int quarter = (end - start) >> 2;
+    if (quarter == 0) {
+      if (lane == 0) {
+        int prv = 0;
+        for (int i = start; i < end; i++) { freq[prv * 257 + data[i]]++; freq[prv * 257 + 256]++; prv = data[i]; }
+      }
+    } else {
+      // four quarters, each walked by 8 lanes over contiguous sub-ranges
+      const int q = lane >> 3, t = lane & 7;
+      const int qs = start + q * quarter;
+      const int per = (quarter + 7) >> 3;
+      const int s0 = qs + t * per, e0 = min(s0 + per, qs + quarter);
+      for (int i = s0; i < e0; i++) {
+        const int prv = (i == qs) ? 0 : data[i - 1];
+        atomicAdd(&freq[prv * 257 + data[i]], 1u);
+        atomicAdd(&freq[prv * 257 + 256], 1u);
+      }
+    }
+  }
+  __syncwarp();
+  __threadfence_block();
+
+  i64 hdrBits = 0;
+  if (lane == 0) {
+    BitWriterD bw(hdr);
+    bw.write((u32)(lr - 8), 3);
+    for (int k = 0; k < 256; k++) {
+      u32* f = freq + k * 257;
+      const int alphabetSize = ans_normalize(f, alpha, (int)f[256], 1 << lr);
+      if (alphabetSize > 0) {
+        int sum = 0;
+        for (int i = 0; i < alphabetSize; i++) {
+          const int s = alpha[i];
+          ans_symbol_reset(symA[k * 256 + s], symB[k * 256 + s], sum, (int)f[s], lr);
+          sum += (int)f[s];
+        }
+      }
+      ans_encode_header(bw, alphabetSize, alpha, f, lr);
+    }
+    hdrBits = bw.bits();
+    bw.flush();
+  }
+  __syncwarp();
+  __threadfence_block();
+
+  // ---- encodeChunk order 1 (:359-390): state q codes quarter q backwards; lanes 0..3 ----
+  const int end4 = start + ((end - start) & -4);
+  int n = bufLen - 1;
+  const int tail = end - end4;
+  if (lane == 0) for (int i = end - 1; i >= end4; i--) pay[n - (end - 1 - i)] = data[i];
+  n -= tail;
+  const int quarter = (end4 - start) >> 2;
+  const int j = lane;          // lanes >= 4 idle in the coding loop
+  u32 st = ANS_TOP;
+  int idx = n;
+  const u32 lowerMask = (1u << (j & 3)) - 1;
+  // Java: i_q = start + (q+1)*quarter - 2, prv_q = block[i_q + 1]; loop while i0 >= start (quarter-1 steps), then "last symbols" in ctx 0
+  int iq = start + (j + 1) * quarter - 2;
+  int prv = 0;
+  if (j < 4) {
+    const int pi = iq + 1;     // may be start-1 when quarter == 0 (degenerate chunk < 4 bytes, SURVEY E-8): pi >= 0 since start > 0 there
+    prv = (pi >= 0) ? data[pi] : 0;
+  }
+  const int steps = (quarter > 0) ? quarter - 1 : 0;
+  for (int s = 0; s <= steps; s++) {
+    u32 a = 0, bb = 0;
+    bool x = false;
+    const bool on = j < 4;
+    int cur = 0;
+    if (on) {
+      const bool last = (s == steps);      // last symbols: symbols[0][prv] (:386-389)
+      cur = last ? 0 : data[iq];
+      a = symA[cur * 256 + prv]; bb = symB[cur * 256 + prv];
+      // uninitialised Symbol (all zero) reproduces Java's default object: xMax 0, bias 0, cmplFreq 0, invFreq 0, invShift 0
+      const bool zeroSym = (a == 0 && bb == 0);
+      const u32 xMax = zeroSym ? 0u : (((u32)(1 << lr) - ((bb >> 14) & 0x3FFF)) << (31 - lr));
+      x = ((i32)st >= (i32)xMax);
+    }
+    const u32 m = __ballot_sync(0xFFFFFFFFu, x) & 0xFu;
+    if (on) {
+      if (x) {
+        const int pos = idx - 2 * __popc(m & lowerMask);
+        pay[pos] = (u8)st;
+        pay[pos - 1] = (u8)(st >> 8);
+        st = (u32)((i32)st >> 16);
+      }
+      idx -= 2 * __popc(m);
+      if (!(a == 0 && bb == 0)) st = ans_enc_step(st, a, bb);
+      prv = cur;
+      iq--;
+    }
+  }
+  const u32 s1 = __shfl_sync(0xFFFFFFFFu, st, 1);
+  const u32 s2 = __shfl_sync(0xFFFFFFFFu, st, 2);
+  const u32 s3 = __shfl_sync(0xFFFFFFFFu, st, 3);
+  if (lane == 0) {
+    n = idx + 1;
+    BitWriterD bw(hdr);
+    bw.nbytes = hdrBits >> 3; bw.nacc = (int)(hdrBits & 7);
+    bw.acc = (bw.nacc > 0) ? ((u64)hdr[bw.nbytes] >> (8 - bw.nacc)) : 0;
+    write_varint(bw, bufLen - n);
+    bw.write(st, 32); bw.write(s1, 32); bw.write(s2, 32); bw.write(s3, 32);
+    bw.flush();
+    segs[0] = KzgSeg{hdr, 0, 0, (u64)bw.bits()};
+    segs[1] = KzgSeg{pay + n, 0, 0, (u64)(bufLen - n) * 8};
+  }
+}
+
+__global__ void __launch_bounds__(32) ans1_decode_kernel(KzgBlock* __restrict__ blocks, KzgEntParams P) {
+  const int lane = threadIdx.x;
+  const int b = blockIdx.y;
+  const int c = blockIdx.x;
+  KzgBlock& B = blocks[b];
+  const bool blockOk = (B.status == 0 && B.entropy == P.entropy);
+  const int len = blockOk ? B.preLen : 0;
+  u8* __restrict__ out = B.cur;
+  const u8* __restrict__ stream = P.stream;
+  if (len <= 32) {
+    if (blockOk && c == 0 && lane == 0) for (int i = 0; i < len; i++) out[i] = (u8)get_bits(stream, (u64)B.srcBit + 8ull * i, 8);
+    return;
+  }
+  const int chunkSize = P.chunkSize;
+  const int start = c * chunkSize;
+  if (start >= len) return;
+  const int end = min(start + chunkSize, len);
+  const i64 gidx = (i64)b * P.maxChunks + c;
+  const KzgChunkInfo info = P.chunks[gidx];
+  u32* tab = P.tabBuf + gidx * (i64)P.tabStride;
+  u32* sym = tab;                               // [256][256] freq | cum << 16
+  u8* f2s = (u8*)(tab + 65536);                 // [256][2048]  (logRange <= 11 for order 1)
+  u16* freq = (u16*)(f2s + 256 * 2048);         // [256] scratch for one context
+  u8* alpha = (u8*)(freq + 256);
+  u8* declared = alpha + 256;                   // [256] context has a table
+
+  int lr = 11, bad = 0;
+  if (lane == 0) {
+    BitReaderD br(stream, (u64)info.hdrBit, (u64)(B.srcBit + B.srcBits));
+    lr = 8 + (int)br.read(3);
+    int llr = 3;
+    while ((1 << llr) <= lr) llr++;
+    if (lr > 11) bad = 1;   // order-1 tables sized for the reference's logRange 11 (ANSRangeEncoder :112,135)
+    for (int k = 0; k < 256 && !bad; k++) {
+      declared[k] = 0;
+      for (int i = 0; i < 256; i++) freq[i] = 0;   // frequencies persist across chunks in Java only when the alphabet is full; a full alphabet overwrites all 256
+      bool cleared = false;
+      const int as = ans_decode_ctx_header(br, lr, llr, freq, alpha, cleared);
+      if (as < 0) { bad = 1; break; }
+      if (as == 0) continue;
+      declared[k] = 1;
+      int sum = 0;
+      for (int i = 0; i < 256; i++) {
+        const int f = freq[i];
+        if (f == 0) continue;
+        for (int t = f - 1; t >= 0; t--) f2s[k * 2048 + sum + t] = (u8)i;
+        const int fe = (f >= (1 << lr)) ? (1 << lr) - 1 : f;
+        sym[k * 256 + i] = (u32)fe | ((u32)sum << 16);
+        sum += f;
+      }
+    }
+  }
+  lr = __shfl_sync(0xFFFFFFFFu, lr, 0);
+  bad = __shfl_sync(0xFFFFFFFFu, bad, 0);
+  __syncwarp();
+  __threadfence_block();
+  if (bad) { if (lane == 0) atomicExch(&B.status, -KZG_ERR_PROCESS_BLOCK); return; }
+
+  // ---- decodeChunkV2 order 1 (:406-432): lane j walks quarter j with state st_j; read order st3, st2, st1, st0 ----
+  const int end4 = start + ((end - start) & -4);
+  const int quarter = (end4 - start) >> 2;
+  const int j = lane;
+  i32 st = (j < 4) ? (i32)info.st[j] : 0;
+  const int mask = (1 << lr) - 1;
+  int cursor = 0;
+  int prv = 0;
+  int pos = start + j * quarter;
+  // lanes with a higher state index read first: "before" = flags of lanes above me within 0..3
+  const u32 upperMask = (j < 4) ? (0xFu & ~((2u << j) - 1)) : 0u;
+  const i64 payBit = info.payBit;
+  const int sz = info.sz;
+  int undeclared = 0;
+  for (int s = 0; s < quarter; s++) {
+    bool need = false;
+    if (j < 4) {
+      const int slot = st & mask;
+      if (!declared[prv]) undeclared = 1;
+      const int cur = f2s[prv * 2048 + slot];
+      const u32 fc = sym[prv * 256 + cur];
+      out[pos] = (u8)cur;
+      st = (i32)((fc & 0xFFFFu) * ((u32)st >> lr) + (u32)slot - (fc >> 16));
+      need = st < ANS_TOP;
+      prv = cur;
+      pos++;
+    }
+    const u32 m = __ballot_sync(0xFFFFFFFFu, need) & 0xFu;
+    if (j < 4) {
+      if (need) {
+        const int off = cursor + 2 * __popc(m & upperMask);
+        st = (i32)(((u32)st << 16) | ans_pay16(stream, payBit, off, sz));
+      }
+      cursor += 2 * __popc(m);
+    }
+  }
+  undeclared = __any_sync(0xFFFFFFFFu, undeclared);
+  if (lane == 0) {
+    const int tail = end - end4;
+    for (int i = 0; i < tail; i++) out[end4 + i] = (cursor + i < sz) ? (u8)ans_pay8(stream, payBit, cursor + i) : 0;
+    if (cursor + tail != sz || undeclared) atomicExch(&B.status, -KZG_ERR_PROCESS_BLOCK);
+  }
+}
+
+// ================================================================================================================
+// host launchers
+// ================================================================================================================
+int kzg_ans_encode_launch(cudaStream_t s, const KzgBlock* d_blocks, int nBlocks, const KzgEntParams& P, int order) {
+  if (order == 0) {
+    static bool attr = false;
+    if (!attr) { CUDA_TRY(cudaFuncSetAttribute(ans0_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(A0EncSmem))); attr = true; }
+    dim3 grid((P.maxChunks + A0_GROUPS - 1) / A0_GROUPS, nBlocks);
+    ans0_encode_kernel<<<grid, 128, sizeof(A0EncSmem), s>>>(d_blocks, P);
+  } else {
+    dim3 grid(P.maxChunks, nBlocks);
+    ans1_encode_kernel<<<grid, 32, 0, s>>>(d_blocks, P);
+  }
+  CUDA_TRY(cudaGetLastError());
+  kzg_count_launch(1);
+  return 0;
+}
+
+int kzg_ans_decode_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, const KzgEntParams& P, int order) {
+  ans_scan_kernel<<<(nBlocks + 31) / 32, 32, 0, s>>>(d_blocks, nBlocks, P, order);
+  CUDA_TRY(cudaGetLastError());
+  if (order == 0) {
+    static bool attr = false;
+    if (!attr) { CUDA_TRY(cudaFuncSetAttribute(ans0_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(A0DecSmem))); attr = true; }
+    dim3 grid((P.maxChunks + A0_GROUPS - 1) / A0_GROUPS, nBlocks);
+    ans0_decode_kernel<<<grid, 128, sizeof(A0DecSmem), s>>>(d_blocks, P);
+  } else {
+    dim3 grid(P.maxChunks, nBlocks);
+    ans1_decode_kernel<<<grid, 32, 0, s>>>(d_blocks, P);
+  }
+  CUDA_TRY(cudaGetLastError());
+  kzg_count_launch(2);
+  return 0;
+}
+
+size_t kzg_ans1_enc_tab_u32() { return 2 * 65536 + 256 * 257 + 64 + 16; }
+size_t kzg_ans1_dec_tab_u32() { return 65536 + (256 * 2048) / 4 + 128 + 64 + 64 + 16; }

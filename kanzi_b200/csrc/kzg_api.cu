@@ -1,0 +1,760 @@
+// kzg_api.cu — C ABI of libkanzi_b200 (include/kzg.h): per-thread workspace, the Sequence / block /
+// stream host logic that surrounds the kernels, and the batched whole-chain entries.
+//
+// Host logic mirrors, for the calling Java code's benefit:
+//   K/transform/Sequence.java:56-127,137-207   (stage order, skip flags, slice rotation)
+//   K/transform/TransformFactory.java:240-351   (which codec an id names, nbFunctions)
+//   K/io/CompressedOutputStream.java:236-313,733-1054 and CompressedInputStream.java:359-515,1025-1378
+//   (stream header, block records) for kzg_compress / kzg_decompress.
+// No CPU codec exists here: every byte of transform / entropy work runs in the CUDA kernels.
+#include "kzg_common.cuh"
+#include "kzg_entropy.cuh"
+#include "kzg_transforms.cuh"
+#include "kzg_container.cuh"
+#include "kzg_stages.cuh"
+#include <stdarg.h>
+#include <vector>
+#include <algorithm>
+
+// ---- per-thread workspace --------------------------------------------------------------------------------
+struct Workspace {
+  bool init = false;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  u8* dArena = nullptr; size_t dCap = 0, dOff = 0;
+  u8* hPinned = nullptr; size_t hCap = 0, hOff = 0;
+  i64 launches = 0;
+  char err[512] = {0};
+};
+static thread_local Workspace W;
+
+void kzg_set_error(const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt);
+  vsnprintf(W.err, sizeof(W.err), fmt, ap);
+  va_end(ap);
+}
+void kzg_count_launch(int n) { W.launches += n; }
+
+static int ws_init() {
+  if (W.init) return 0;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    kzg_set_error("no CUDA device: %s (libkanzi_b200 has no CPU fallback)", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    cudaGetLastError();
+    return -KZG_ERR_NO_DEVICE;
+  }
+  if (W.device >= n) W.device = 0;
+  CUDA_TRY(cudaSetDevice(W.device));
+  CUDA_TRY(cudaStreamCreateWithFlags(&W.stream, cudaStreamNonBlocking));
+  W.init = true;
+  return 0;
+}
+
+static int ws_reserve(size_t dBytes, size_t hBytes) {
+  if (dBytes > W.dCap) {
+    if (W.dArena) { CUDA_TRY(cudaStreamSynchronize(W.stream)); cudaFree(W.dArena); W.dArena = nullptr; W.dCap = 0; }
+    const size_t want = dBytes + dBytes / 8 + (1 << 20);
+    cudaError_t e = cudaMalloc((void**)&W.dArena, want);
+    if (e != cudaSuccess) { kzg_set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); cudaGetLastError(); return -KZG_ERR_CREATE_CODEC; }
+    W.dCap = want;
+  }
+  if (hBytes > W.hCap) {
+    if (W.hPinned) { CUDA_TRY(cudaStreamSynchronize(W.stream)); cudaFreeHost(W.hPinned); W.hPinned = nullptr; W.hCap = 0; }
+    const size_t want = hBytes + hBytes / 8 + (1 << 16);
+    cudaError_t e = cudaMallocHost((void**)&W.hPinned, want);
+    if (e != cudaSuccess) { kzg_set_error("cudaMallocHost(%zu) failed: %s", want, cudaGetErrorString(e)); cudaGetLastError(); return -KZG_ERR_CREATE_CODEC; }
+    W.hCap = want;
+  }
+  W.dOff = 0; W.hOff = 0;
+  return 0;
+}
+static inline size_t rnd(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+template <typename T> static T* dalloc(size_t count) {
+  const size_t bytes = rnd(count * sizeof(T));
+  if (W.dOff + bytes > W.dCap) { kzg_set_error("internal: device arena exhausted (%zu + %zu > %zu)", W.dOff, bytes, W.dCap); return nullptr; }
+  T* p = (T*)(W.dArena + W.dOff); W.dOff += bytes; return p;
+}
+template <typename T> static T* halloc(size_t count) {
+  const size_t bytes = rnd(count * sizeof(T));
+  if (W.hOff + bytes > W.hCap) { kzg_set_error("internal: pinned arena exhausted"); return nullptr; }
+  T* p = (T*)(W.hPinned + W.hOff); W.hOff += bytes; return p;
+}
+#define NN(p) do { if ((p) == nullptr) return -KZG_ERR_CREATE_CODEC; } while (0)
+
+// ---- ids / sizes (TransformFactory, getMaxEncodedLength of each codec) --------------------------------------
+static bool xf_known(int t) {
+  switch (t) { case KZG_T_NONE: case KZG_T_LZ: case KZG_T_LZX: case KZG_T_ROLZ: case KZG_T_BWT: case KZG_T_RANK: case KZG_T_MTFT:
+               case KZG_T_SRT: case KZG_T_ZRLT: return true; default: return false; }
+}
+static bool ent_known(int e) {
+  switch (e) { case KZG_E_NONE: case KZG_E_HUFFMAN: case KZG_E_ANS0: case KZG_E_ANS1: case KZG_E_FPAQ: return true; default: return false; }
+}
+static i32 xf_max_len(int t, i32 n) {
+  switch (t) {
+    case KZG_T_LZ: case KZG_T_LZX: return ((n <= 1024) ? n + 16 : n + (n / 64)) + 2;   // LZCodec.java:961-964
+    case KZG_T_ROLZ: return (n <= 512) ? n + 64 : n;                                  // ROLZCodec.java:1001-1003
+    case KZG_T_BWT: return n + 33;                                                    // BWTBlockCodec.java:222-224
+    case KZG_T_SRT: return n + 1024;                                                  // SRT.java:364-366
+    default: return n;                                                                // Null / SBRT / ZRLT
+  }
+}
+// TransformFactory.newFunction (:240-270): ids of the Sequence's functions
+static int seq_functions(const i32* transforms, int nT, int* out) {
+  int slots[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < nT && i < 8; i++) slots[i] = transforms[i];
+  int nbtr = 0;
+  for (int i = 0; i < 8; i++) if (slots[i] != KZG_T_NONE) nbtr++;
+  if (nbtr == 0) nbtr = 1;
+  int k = 0;
+  for (int i = 0; i < nbtr; i++) if (slots[i] != KZG_T_NONE || i == 0) out[k++] = slots[i];
+  return k;
+}
+static i32 seq_max_len(const int* fn, int nf, i32 n) {      // Sequence.getMaxEncodedLength (:219-230)
+  i32 req = n;
+  for (int i = 0; i < nf; i++) req = std::max(req, xf_max_len(fn[i], req));
+  return req;
+}
+static int ent_chunk_size(int e) {
+  switch (e) { case KZG_E_HUFFMAN: case KZG_E_ANS0: return 16384; case KZG_E_ANS1: case KZG_E_FPAQ: return 4 << 20; default: return 1 << 30; }
+}
+static int ent_segs_per_chunk(int e) { return e == KZG_E_HUFFMAN ? 6 : 2; }
+
+// ---- batch state ------------------------------------------------------------------------------------------
+struct Batch {
+  int nBlocks = 0;
+  KzgBlock* hBlocks = nullptr;     // pinned
+  KzgBlock* dBlocks = nullptr;
+  int* dResult = nullptr;
+  u8* dEnabled = nullptr; u8* hEnabled = nullptr;
+  int* dDstLimit = nullptr; int* hDstLimit = nullptr;
+  i32 maxLen = 0;                  // largest block length at any stage
+};
+
+static int batch_upload(Batch& bt) {
+  CUDA_TRY(cudaMemcpyAsync(bt.dBlocks, bt.hBlocks, sizeof(KzgBlock) * bt.nBlocks, cudaMemcpyHostToDevice, W.stream));
+  return 0;
+}
+static int batch_download(Batch& bt) {
+  CUDA_TRY(cudaMemcpyAsync(bt.hBlocks, bt.dBlocks, sizeof(KzgBlock) * bt.nBlocks, cudaMemcpyDeviceToHost, W.stream));
+  CUDA_TRY(cudaStreamSynchronize(W.stream));
+  return 0;
+}
+
+// scratch the transform stages of a chain need, per block of at most `maxLen` bytes
+struct XfScratch { size_t perBlock = 0; int tk = 0, m = 0, ml = 0; size_t hashInts = 0; size_t aux32 = 0; };
+static XfScratch xf_scratch_size(const int* fn, int nf, i32 maxLen, bool forward) {
+  XfScratch s;
+  for (int i = 0; i < nf; i++) {
+    if (fn[i] == KZG_T_LZ || fn[i] == KZG_T_LZX) {
+      if (forward) {
+        s.tk = (int)rnd(std::max(maxLen / 5, 256) + 16, 16); s.m = (int)rnd((size_t)maxLen + 16, 16); s.ml = (int)rnd((size_t)maxLen / 2 + 64, 16);
+        s.perBlock = std::max(s.perBlock, (size_t)s.tk + s.m + s.ml);
+        const bool smemTable = (fn[i] == KZG_T_LZ) && (maxLen <= (1 << 24));
+        if (!smemTable) s.hashInts = std::max(s.hashInts, (size_t)((fn[i] == KZG_T_LZX) ? (1 << 19) : (1 << 16)));
+      }
+    }
+    kzg_stage_scratch(fn[i], maxLen, forward, &s.perBlock, &s.hashInts, &s.aux32);
+  }
+  s.perBlock = rnd(s.perBlock, 256);
+  return s;
+}
+
+static int run_transform_stage(Batch& bt, int type, int stage, bool forward, const XfScratch& xs, u8* dScratch, i32* dHash, i32* dAux32, int flags) {
+  KzgXfParams P;
+  P.result = bt.dResult; P.enabled = bt.dEnabled; P.dstLimit = bt.dDstLimit;
+  P.scratch = dScratch; P.scratchStride = (i64)xs.perBlock; P.tkStride = xs.tk; P.mStride = xs.m; P.mLenStride = xs.ml;
+  P.hashBuf = dHash; P.aux32 = dAux32; P.aux32Stride = (i64)xs.aux32; P.flags = flags;
+  int r = 0;
+  switch (type) {
+    case KZG_T_LZ: case KZG_T_LZX:
+      if (forward) r = kzg_lz_forward_launch(W.stream, bt.dBlocks, bt.nBlocks, P, type == KZG_T_LZX, (type == KZG_T_LZ) && (bt.maxLen <= (1 << 24)));
+      else r = kzg_lz_inverse_launch(W.stream, bt.dBlocks, bt.nBlocks, P);
+      break;
+    default:
+      r = kzg_stage_launch(W.stream, type, forward, bt.dBlocks, bt.nBlocks, P, bt.maxLen);
+      break;
+  }
+  if (r < 0) return r;
+  return kzg_commit_launch(W.stream, bt.dBlocks, bt.nBlocks, bt.dResult, bt.dEnabled, stage, forward ? 1 : 0);
+}
+
+// entropy-stage scratch for encoding blocks of at most maxPost bytes
+struct EntScratch { int maxChunks = 0, spc = 0, segsPerBlock = 0; size_t hdrStride = 0, payStride = 0, tabStride = 0; };
+static EntScratch ent_scratch_size(int entropy, i32 maxPost, bool encode) {
+  EntScratch e;
+  const int cs = ent_chunk_size(entropy);
+  e.maxChunks = std::max(1, (int)(((i64)maxPost + cs - 1) / cs));
+  e.spc = ent_segs_per_chunk(entropy);
+  e.segsPerBlock = 1 + e.spc * e.maxChunks;
+  switch (entropy) {
+    case KZG_E_ANS0: e.hdrStride = 512; e.payStride = encode ? 2 * 16384 + 16 + 16 : 0; break;
+    case KZG_E_HUFFMAN: e.hdrStride = 1024; e.payStride = encode ? 4 * 6160 + 16 : 0; break;
+    case KZG_E_ANS1:
+      e.hdrStride = 256 * 480 + 64;
+      e.payStride = encode ? (size_t)std::max(std::min(cs + (cs >> 3), 2 * maxPost), 65536) + 16 + 16 : 0;
+      e.tabStride = encode ? kzg_ans1_enc_tab_u32() : kzg_ans1_dec_tab_u32();
+      break;
+    case KZG_E_FPAQ:
+      e.hdrStride = 64; e.payStride = encode ? (size_t)cs + (cs >> 3) + 64 : 0;
+      break;
+    default: break;
+  }
+  if (!encode) e.hdrStride = 0;
+  return e;
+}
+
+static int run_entropy_encode(Batch& bt, int entropy, const EntScratch& es, u8* dHdr, u8* dPay, u32* dTab, KzgSeg* dSegs) {
+  if (entropy == KZG_E_NONE) return 0;
+  KzgEntParams P;
+  memset(&P, 0, sizeof(P));
+  P.entropy = entropy; P.chunkSize = ent_chunk_size(entropy); P.maxChunks = es.maxChunks;
+  P.hdrBuf = dHdr; P.hdrStride = (int)es.hdrStride; P.payBuf = dPay; P.payStride = (int)es.payStride;
+  P.tabBuf = dTab; P.tabStride = (i64)es.tabStride; P.segs = dSegs; P.segsPerBlock = es.segsPerBlock;
+  switch (entropy) {
+    case KZG_E_ANS0: return kzg_ans_encode_launch(W.stream, bt.dBlocks, bt.nBlocks, P, 0);
+    case KZG_E_ANS1: return kzg_ans_encode_launch(W.stream, bt.dBlocks, bt.nBlocks, P, 1);
+    case KZG_E_HUFFMAN: return kzg_huff_encode_launch(W.stream, bt.dBlocks, bt.nBlocks, P);
+    case KZG_E_FPAQ: return kzg_fpaq_encode_launch(W.stream, bt.dBlocks, bt.nBlocks, P);
+    default: return -KZG_ERR_INVALID_CODEC;
+  }
+}
+
+static int run_entropy_decode(Batch& bt, int entropy, const EntScratch& es, const u8* dStream, KzgChunkInfo* dChunks, u32* dTab) {
+  if (entropy == KZG_E_NONE) return kzg_rawbits_launch(W.stream, bt.dBlocks, bt.nBlocks, dStream);
+  KzgEntParams P;
+  memset(&P, 0, sizeof(P));
+  P.entropy = entropy; P.chunkSize = ent_chunk_size(entropy); P.maxChunks = es.maxChunks;
+  P.stream = dStream; P.chunks = dChunks; P.tabBuf = dTab; P.tabStride = (i64)es.tabStride;
+  switch (entropy) {
+    case KZG_E_ANS0: return kzg_ans_decode_launch(W.stream, bt.dBlocks, bt.nBlocks, P, 0);
+    case KZG_E_ANS1: return kzg_ans_decode_launch(W.stream, bt.dBlocks, bt.nBlocks, P, 1);
+    case KZG_E_HUFFMAN: return kzg_huff_decode_launch(W.stream, bt.dBlocks, bt.nBlocks, P);
+    case KZG_E_FPAQ: return kzg_fpaq_decode_launch(W.stream, bt.dBlocks, bt.nBlocks, P);
+    default: return -KZG_ERR_INVALID_CODEC;
+  }
+}
+
+// ============================================================================================================
+// library entry points
+// ============================================================================================================
+extern "C" {
+
+int kzg_abi_version(void) { return 1; }
+int kzg_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
+int kzg_set_device(int device) {
+  if (W.init && W.device != device) {
+    cudaStreamSynchronize(W.stream);
+    if (W.dArena) cudaFree(W.dArena);
+    if (W.hPinned) cudaFreeHost(W.hPinned);
+    cudaStreamDestroy(W.stream);
+    W = Workspace();
+  }
+  W.device = device;
+  return ws_init();
+}
+const char* kzg_last_error(void) { return W.err; }
+int64_t kzg_launch_count(int reset) { const i64 v = W.launches; if (reset) W.launches = 0; return v; }
+void* kzg_stream(void) { if (ws_init() < 0) return nullptr; return (void*)W.stream; }
+int32_t kzg_transform_max_encoded_len(int type, int32_t n) { return xf_known(type) ? xf_max_len(type, n) : -KZG_ERR_INVALID_CODEC; }
+int64_t kzg_compress_bound(int64_t n, int32_t blockSize) {
+  const i64 nb = (n + blockSize - 1) / std::max(blockSize, 1);
+  return n + nb * 16 + 64 + n / 64;
+}
+
+// ---- one ByteTransform call -------------------------------------------------------------------------------------
+static int transform_call(int type, bool forward, kzg_ctx* ctx, const uint8_t* src, int32_t srcLen, uint8_t* dst, int32_t dstLen,
+                          int32_t dstCap, int32_t* srcUsed, int32_t* dstUsed) {
+  *srcUsed = 0; *dstUsed = 0;
+  if (!xf_known(type)) return -KZG_ERR_INVALID_CODEC;
+  if (srcLen == 0) return 1;                                   // every codec: `if (input.length == 0) return true`
+  if (srcLen < 0 || dstLen < 0 || dstCap < 0 || dstLen > dstCap || src == nullptr || dst == nullptr) return 0;
+  int r = ws_init(); if (r < 0) return r;
+  // host-evaluated slice preconditions (the parts of each codec's guard block that depend on lengths only)
+  const int pre = kzg_stage_precheck(type, forward, ctx, srcLen, dstLen, dstCap);
+  if (pre <= 0) return pre;
+  const int fn[1] = {type};
+  const i32 maxLen = std::max(srcLen, dstCap);
+  XfScratch xs = xf_scratch_size(fn, 1, maxLen, forward);
+  const size_t cap = rnd((size_t)maxLen + 64);
+  size_t need = 2 * cap + xs.perBlock + (xs.hashInts + xs.aux32) * 4 + 8192;
+  r = ws_reserve(need, sizeof(KzgBlock) + 4096); if (r < 0) return r;
+  Batch bt; bt.nBlocks = 1; bt.maxLen = maxLen;
+  bt.hBlocks = halloc<KzgBlock>(1); NN(bt.hBlocks);
+  bt.dBlocks = dalloc<KzgBlock>(1); NN(bt.dBlocks);
+  bt.dResult = dalloc<int>(2); NN(bt.dResult);
+  bt.dEnabled = dalloc<u8>(16); NN(bt.dEnabled);
+  bt.dDstLimit = dalloc<int>(4); NN(bt.dDstLimit);
+  u8* dA = dalloc<u8>(cap); NN(dA);
+  u8* dB = dalloc<u8>(cap); NN(dB);
+  u8* dScratch = dalloc<u8>(xs.perBlock + 16); NN(dScratch);
+  i32* dHash = dalloc<i32>(xs.hashInts + 4); NN(dHash);
+  i32* dAux = dalloc<i32>(xs.aux32 + 4); NN(dAux);
+  KzgBlock& B = bt.hBlocks[0];
+  memset(&B, 0, sizeof(B));
+  B.cur = dA; B.alt = dB; B.curLen = srcLen; B.cap = forward ? dstLen : dstCap; B.origLen = srcLen; B.skipFlags = 0xFF;
+  B.dataType = ctx ? ctx->dataType : 0; B.aux0 = nullptr; B.aux1 = dA; B.stagesLeft = 2;
+  u8 en = 1; int lim = forward ? dstLen : dstCap;
+  CUDA_TRY(cudaMemsetAsync(dA + srcLen, 0, cap - srcLen, W.stream));
+  CUDA_TRY(cudaMemcpyAsync(dA, src, srcLen, cudaMemcpyHostToDevice, W.stream));
+  CUDA_TRY(cudaMemcpyAsync(bt.dEnabled, &en, 1, cudaMemcpyHostToDevice, W.stream));
+  CUDA_TRY(cudaMemcpyAsync(bt.dDstLimit, &lim, sizeof(int), cudaMemcpyHostToDevice, W.stream));
+  r = batch_upload(bt); if (r < 0) return r;
+  const int flags = ctx ? ctx->flags : 0;
+  // (commit's inverse branch flags a failed inverse as a block error; here a false result is reported as 0)
+  r = run_transform_stage(bt, type, 0, forward, xs, dScratch, dHash, dAux, flags | (ctx ? 0 : 0)); if (r < 0) return r;
+  int hres[2] = {0, 0};
+  CUDA_TRY(cudaMemcpyAsync(hres, bt.dResult, sizeof(hres), cudaMemcpyDeviceToHost, W.stream));
+  r = batch_download(bt); if (r < 0) return r;
+  if (ctx) ctx->dataType = B.dataType;
+  if (B.status != 0 && !(B.status == -KZG_ERR_PROCESS_BLOCK && !forward && hres[0] == 0)) return B.status;
+  if (hres[0] == 1) {
+    if (hres[1] > dstCap) { kzg_set_error("transform output %d exceeds dst capacity %d", hres[1], dstCap); return -KZG_ERR_PROCESS_BLOCK; }
+    CUDA_TRY(cudaMemcpy(dst, B.cur, hres[1], cudaMemcpyDeviceToHost));
+    *srcUsed = srcLen; *dstUsed = hres[1];
+    return 1;
+  }
+  return 0;
+}
+
+int kzg_transform_forward(int type, kzg_ctx* ctx, const uint8_t* src, int32_t srcLen, uint8_t* dst, int32_t dstLen, int32_t dstCap,
+                          int32_t* srcUsed, int32_t* dstUsed) {
+  return transform_call(type, true, ctx, src, srcLen, dst, dstLen, dstCap, srcUsed, dstUsed);
+}
+int kzg_transform_inverse(int type, kzg_ctx* ctx, const uint8_t* src, int32_t srcLen, uint8_t* dst, int32_t dstLen, int32_t dstCap,
+                          int32_t* srcUsed, int32_t* dstUsed) {
+  return transform_call(type, false, ctx, src, srcLen, dst, dstLen, dstCap, srcUsed, dstUsed);
+}
+
+int kzg_bwt_forward(const uint8_t* src, int32_t n, uint8_t* dst, int32_t* primaryIndexes8) {
+  int r = ws_init(); if (r < 0) return r;
+  return kzg_bwt_raw(W.stream, true, src, n, dst, primaryIndexes8);
+}
+int kzg_bwt_inverse(const uint8_t* src, int32_t n, uint8_t* dst, const int32_t* primaryIndexes8) {
+  int r = ws_init(); if (r < 0) return r;
+  return kzg_bwt_raw(W.stream, false, src, n, dst, (int32_t*)primaryIndexes8);
+}
+
+// ---- one EntropyEncoder.encode (+dispose) / EntropyDecoder.decode call --------------------------------------------
+int64_t kzg_entropy_encode(int type, kzg_ctx* ctx, const uint8_t* src, int32_t n, uint8_t* out, int64_t outCap, int64_t* outBits) {
+  if (outBits) *outBits = 0;
+  if (!ent_known(type)) return -KZG_ERR_INVALID_CODEC;
+  if (n < 0 || src == nullptr || out == nullptr) return -1;          // Java: encode returns -1 on bad arguments
+  int r = ws_init(); if (r < 0) return r;
+  if (n == 0 && type != KZG_E_FPAQ) return 0;
+  EntScratch es = ent_scratch_size(type, n, true);
+  const size_t cap = rnd((size_t)n + 64);
+  const size_t outBytes = rnd((size_t)n + n / 4 + 4096);
+  const size_t need = cap + outBytes + (size_t)es.maxChunks * (es.hdrStride + es.payStride + es.tabStride * 4) +
+                      (size_t)es.segsPerBlock * sizeof(KzgSeg) + 65536;
+  r = ws_reserve(need, sizeof(KzgBlock) + 4096); if (r < 0) return r;
+  Batch bt; bt.nBlocks = 1; bt.maxLen = n;
+  bt.hBlocks = halloc<KzgBlock>(1); NN(bt.hBlocks);
+  bt.dBlocks = dalloc<KzgBlock>(1); NN(bt.dBlocks);
+  u8* dIn = dalloc<u8>(cap); NN(dIn);
+  u8* dOut = dalloc<u8>(outBytes); NN(dOut);
+  u8* dHdr = dalloc<u8>((size_t)es.maxChunks * es.hdrStride + 16); NN(dHdr);
+  u8* dPay = dalloc<u8>((size_t)es.maxChunks * es.payStride + 16); NN(dPay);
+  u32* dTab = dalloc<u32>((size_t)es.maxChunks * es.tabStride + 4); NN(dTab);
+  KzgSeg* dSegs = dalloc<KzgSeg>(es.segsPerBlock); NN(dSegs);
+  u8* dHdrBytes = dalloc<u8>(16); NN(dHdrBytes);
+  i64* dTotal = dalloc<i64>(2); NN(dTotal);
+  KzgBlock& B = bt.hBlocks[0];
+  memset(&B, 0, sizeof(B));
+  B.cur = dIn; B.alt = nullptr; B.curLen = n; B.cap = (i32)cap; B.origLen = n; B.entropy = type; B.srcBit = 0;
+  CUDA_TRY(cudaMemsetAsync(dIn + n, 0, cap - n, W.stream));
+  CUDA_TRY(cudaMemcpyAsync(dIn, src, n, cudaMemcpyHostToDevice, W.stream));
+  CUDA_TRY(cudaMemsetAsync(dOut, 0, outBytes, W.stream));
+  CUDA_TRY(cudaMemsetAsync(dSegs, 0, sizeof(KzgSeg) * es.segsPerBlock, W.stream));
+  r = batch_upload(bt); if (r < 0) return r;
+  r = run_entropy_encode(bt, type, es, dHdr, dPay, dTab, dSegs); if (r < 0) return r;
+  r = kzg_assemble_launch(W.stream, bt.dBlocks, 1, dSegs, es.segsPerBlock, dHdrBytes, 1, 0, dOut, 0, dTotal, (i64)outBytes - 8); if (r < 0) return r;
+  r = batch_download(bt); if (r < 0) return r;
+  if (B.status != 0) return B.status;
+  const i64 bits = B.entBits;
+  const i64 bytes = (bits + 7) >> 3;
+  if (bytes > outCap || bytes > (i64)outBytes - 8) { kzg_set_error("entropy output (%lld bytes) exceeds capacity", (long long)bytes); return -KZG_ERR_PROCESS_BLOCK; }
+  CUDA_TRY(cudaMemcpy(out, dOut, (size_t)bytes, cudaMemcpyDeviceToHost));
+  if (outBits) *outBits = bits;
+  return n;
+}
+
+int32_t kzg_entropy_decode(int type, kzg_ctx* ctx, const uint8_t* in, int64_t inBits, int64_t* bitsUsed, uint8_t* dst, int32_t n) {
+  if (bitsUsed) *bitsUsed = 0;
+  if (!ent_known(type)) return -KZG_ERR_INVALID_CODEC;
+  if (n < 0 || in == nullptr || dst == nullptr || inBits < 0) return -1;
+  int r = ws_init(); if (r < 0) return r;
+  if (n == 0) return 0;
+  EntScratch es = ent_scratch_size(type, n, false);
+  const size_t inBytes = (size_t)((inBits + 7) >> 3);
+  const size_t inCap = rnd(inBytes + 64);
+  const size_t cap = rnd((size_t)n + 64);
+  const size_t need = inCap + cap + (size_t)es.maxChunks * (sizeof(KzgChunkInfo) + es.tabStride * 4) + 65536;
+  r = ws_reserve(need, sizeof(KzgBlock) + 4096); if (r < 0) return r;
+  Batch bt; bt.nBlocks = 1; bt.maxLen = n;
+  bt.hBlocks = halloc<KzgBlock>(1); NN(bt.hBlocks);
+  bt.dBlocks = dalloc<KzgBlock>(1); NN(bt.dBlocks);
+  u8* dIn = dalloc<u8>(inCap); NN(dIn);
+  u8* dOut = dalloc<u8>(cap); NN(dOut);
+  KzgChunkInfo* dChunks = dalloc<KzgChunkInfo>(es.maxChunks); NN(dChunks);
+  u32* dTab = dalloc<u32>((size_t)es.maxChunks * es.tabStride + 4); NN(dTab);
+  KzgBlock& B = bt.hBlocks[0];
+  memset(&B, 0, sizeof(B));
+  B.cur = dOut; B.curLen = n; B.cap = (i32)cap; B.preLen = n; B.entropy = type; B.srcBit = 0; B.srcBits = inBits;
+  CUDA_TRY(cudaMemsetAsync(dIn + inBytes, 0, inCap - inBytes, W.stream));
+  CUDA_TRY(cudaMemcpyAsync(dIn, in, inBytes, cudaMemcpyHostToDevice, W.stream));
+  r = batch_upload(bt); if (r < 0) return r;
+  r = run_entropy_decode(bt, type, es, dIn, dChunks, dTab); if (r < 0) return r;
+  r = batch_download(bt); if (r < 0) return r;
+  if (B.status != 0) return 0;        // the Java decoders signal corrupt input by a short count / exception
+  CUDA_TRY(cudaMemcpy(dst, dOut, n, cudaMemcpyDeviceToHost));
+  if (bitsUsed) *bitsUsed = B.entBits;
+  return n;
+}
+
+// ---- whole streams ------------------------------------------------------------------------------------------------
+// stream header, COS:236-313 (checksum kind 0).  Returns header byte count (whole bytes: 160 + 16*szMask bits).
+static int stream_header(u8* h, int entropy, u64 transformType, i32 blockSize, i64 inputSize) {
+  u64 acc = 0; int nacc = 0, nb = 0;
+  auto put = [&](u64 v, int n) {
+    for (int i = n - 1; i >= 0; i--) { acc = (acc << 1) | ((v >> i) & 1); if (++nacc == 8) { h[nb++] = (u8)acc; acc = 0; nacc = 0; } }
+  };
+  put(0x4B414E5A, 32); put(7, 4); put(0, 2); put((u64)entropy, 5); put(transformType, 48); put((u64)((u32)blockSize >> 4), 28);
+  int szMask = 0;
+  if (inputSize != 0 && inputSize < (1LL << 48)) {
+    if (inputSize >= (1LL << 32)) szMask = 3;
+    else {
+      i64 isz = inputSize;
+      if (isz > (1LL << 30)) { isz >>= 4; szMask++; }
+      int lg = 0; while ((2LL << lg) <= isz) lg++;
+      szMask += (lg >> 4) + 1;
+    }
+  }
+  put((u64)szMask, 2);
+  if (szMask > 0) put((u64)inputSize, 16 * szMask);
+  put(0, 15);
+  const u32 HASH = 0x1E35A7BDu;
+  u32 c = HASH * (0x01030507u * 7u);
+  c = kzg_mix32(c, HASH, 0);
+  c = kzg_mix32(c, HASH, (u32)entropy);
+  c = kzg_mix32(c, HASH, (u32)(transformType >> 32));
+  c = kzg_mix32(c, HASH, (u32)transformType);
+  c = kzg_mix32(c, HASH, (u32)blockSize);
+  if (szMask > 0) { c = kzg_mix32(c, HASH, (u32)((u64)inputSize >> 32)); c = kzg_mix32(c, HASH, (u32)inputSize); }
+  c = (c >> 23) ^ (c >> 3);
+  put(c & 0xFFFFFF, 24);
+  return nb;
+}
+
+int64_t kzg_compress_dev(const uint8_t* d_in, int64_t n, const int32_t* transforms, int32_t nTransforms, int32_t entropy,
+                         int32_t blockSize, int32_t flags, uint8_t* d_out, int64_t outCap, float* timing3) {
+  if (n < 0 || nTransforms < 0 || nTransforms > 8 || !ent_known(entropy)) return -KZG_ERR_INVALID_PARAM;
+  if (blockSize > (1 << 30) || blockSize < 1024 || (blockSize & -16) != blockSize) return -KZG_ERR_BLOCK_SIZE;    // COS:165-174
+  for (int i = 0; i < nTransforms; i++) if (!xf_known(transforms[i])) return -KZG_ERR_INVALID_CODEC;
+  int r = ws_init(); if (r < 0) return r;
+  int fn[8]; const int nf = seq_functions(transforms, nTransforms, fn);
+  u64 transformType = 0;
+  for (int i = 0; i < nTransforms && i < 8; i++) transformType |= ((u64)transforms[i] << (42 - 6 * i));
+  const int nBlocks = (int)((n + blockSize - 1) / blockSize);
+  const i32 maxBlock = (i32)std::min<i64>(n, blockSize);
+  const i32 required = seq_max_len(fn, nf, maxBlock);
+  const size_t cap = rnd((size_t)required + 64);
+  bool anyXf = false; for (int i = 0; i < nf; i++) if (fn[i] != KZG_T_NONE) anyXf = true;
+  XfScratch xs = xf_scratch_size(fn, nf, required, true);
+  EntScratch es = ent_scratch_size(entropy, required, true);
+  const size_t nb = (size_t)std::max(nBlocks, 1);
+  size_t need = nb * (sizeof(KzgBlock) + 64) + (anyXf ? nb * cap * (nf >= 2 ? 2 : 1) : 0) + nb * xs.perBlock + (nb * (xs.hashInts + xs.aux32)) * 4 +
+                nb * (size_t)es.maxChunks * (es.hdrStride + es.payStride + es.tabStride * 4) + nb * (size_t)es.segsPerBlock * sizeof(KzgSeg) + (1 << 20);
+  r = ws_reserve(need, nb * (sizeof(KzgBlock) + 16) + 4096); if (r < 0) return r;
+  u8 hdr[64];
+  const int hdrLen = stream_header(hdr, entropy, transformType, blockSize, n);
+  if (outCap < hdrLen + 2) return -KZG_ERR_WRITE_FILE;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  if (timing3) for (int i = 0; i < 4; i++) CUDA_TRY(cudaEventCreate(&ev[i]));
+  CUDA_TRY(cudaMemsetAsync(d_out, 0, (size_t)outCap, W.stream));
+  CUDA_TRY(cudaMemcpyAsync(d_out, hdr, hdrLen, cudaMemcpyHostToDevice, W.stream));
+  i64 totalBits = (i64)hdrLen * 8 + 8;
+  if (nBlocks > 0) {
+    Batch bt; bt.nBlocks = nBlocks; bt.maxLen = required;
+    bt.hBlocks = halloc<KzgBlock>(nb); NN(bt.hBlocks);
+    bt.hEnabled = halloc<u8>(nb); NN(bt.hEnabled);
+    bt.dBlocks = dalloc<KzgBlock>(nb); NN(bt.dBlocks);
+    bt.dResult = dalloc<int>(2 * nb); NN(bt.dResult);
+    bt.dEnabled = dalloc<u8>(nb); NN(bt.dEnabled);
+    bt.dDstLimit = dalloc<int>(nb); NN(bt.dDstLimit);
+    u8* dA = anyXf ? dalloc<u8>(nb * cap) : nullptr; if (anyXf) NN(dA);
+    u8* dB = (anyXf && nf >= 2) ? dalloc<u8>(nb * cap) : nullptr; if (anyXf && nf >= 2) NN(dB);
+    u8* dScratch = dalloc<u8>(nb * xs.perBlock + 16); NN(dScratch);
+    i32* dHash = dalloc<i32>(nb * xs.hashInts + 4); NN(dHash);
+    i32* dAux = dalloc<i32>(nb * xs.aux32 + 4); NN(dAux);
+    u8* dHdr = dalloc<u8>(nb * es.maxChunks * es.hdrStride + 16); NN(dHdr);
+    u8* dPay = dalloc<u8>(nb * es.maxChunks * es.payStride + 16); NN(dPay);
+    u32* dTab = dalloc<u32>(nb * es.maxChunks * es.tabStride + 4); NN(dTab);
+    KzgSeg* dSegs = dalloc<KzgSeg>(nb * es.segsPerBlock); NN(dSegs);
+    u8* dHdrBytes = dalloc<u8>(nb * 8 + 16); NN(dHdrBytes);
+    i64* dTotal = dalloc<i64>(2); NN(dTotal);
+    for (int b = 0; b < nBlocks; b++) {
+      KzgBlock& B = bt.hBlocks[b];
+      memset(&B, 0, sizeof(B));
+      const i64 off = (i64)b * blockSize;
+      const i32 len = (i32)std::min<i64>(blockSize, n - off);
+      B.cur = (u8*)d_in + off; B.aux0 = B.cur;
+      B.alt = dA ? dA + (size_t)b * cap : nullptr; B.aux1 = dB ? dB + (size_t)b * cap : B.alt;
+      B.curLen = len; B.cap = (i32)cap - 64; B.origLen = len; B.skipFlags = 0xFF; B.entropy = entropy;
+      const bool small = len <= 15;                             // COS:764-767: raw copy block
+      if (small) { B.mode = 0x80; B.entropy = KZG_E_NONE; }
+      bt.hEnabled[b] = small ? 0 : 1;
+    }
+    CUDA_TRY(cudaMemcpyAsync(bt.dEnabled, bt.hEnabled, nb, cudaMemcpyHostToDevice, W.stream));
+    CUDA_TRY(cudaMemsetAsync(bt.dDstLimit, 0x7F, nb * sizeof(int), W.stream));
+    CUDA_TRY(cudaMemsetAsync(dSegs, 0, sizeof(KzgSeg) * nb * es.segsPerBlock, W.stream));
+    r = batch_upload(bt); if (r < 0) return r;
+    if (timing3) CUDA_TRY(cudaEventRecord(ev[0], W.stream));
+    // ctx["dataType"] from the block's magic number (COS:795-804)
+    r = kzg_magic_launch(W.stream, bt.dBlocks, nBlocks); if (r < 0) return r;
+    // Sequence.forward: a NONE-only chain is a copy that always succeeds (NullTransform) -> skip bit 7 cleared
+    for (int i = 0; i < nf; i++) {
+      if (fn[i] == KZG_T_NONE) { r = kzg_null_forward_launch(W.stream, bt.dBlocks, nBlocks, bt.dEnabled, i); if (r < 0) return r; continue; }
+      r = run_transform_stage(bt, fn[i], i, true, xs, dScratch, dHash, dAux, flags); if (r < 0) return r;
+    }
+    if (timing3) CUDA_TRY(cudaEventRecord(ev[1], W.stream));
+    r = run_entropy_encode(bt, entropy, es, dHdr, dPay, dTab, dSegs); if (r < 0) return r;
+    if (timing3) CUDA_TRY(cudaEventRecord(ev[2], W.stream));
+    r = kzg_assemble_launch(W.stream, bt.dBlocks, nBlocks, dSegs, es.segsPerBlock, dHdrBytes, nf, 1, d_out, (i64)hdrLen * 8, dTotal, outCap - 8);
+    if (r < 0) return r;
+    if (timing3) CUDA_TRY(cudaEventRecord(ev[3], W.stream));
+    CUDA_TRY(cudaMemcpyAsync(&totalBits, dTotal, sizeof(i64), cudaMemcpyDeviceToHost, W.stream));
+    r = batch_download(bt); if (r < 0) return r;
+    for (int b = 0; b < nBlocks; b++)
+      if (bt.hBlocks[b].status != 0) { kzg_set_error("block %d failed with status %d", b + 1, bt.hBlocks[b].status); return bt.hBlocks[b].status; }
+    if (totalBits < 0) return -KZG_ERR_PROCESS_BLOCK;
+    if (timing3) {
+      for (int i = 0; i < 3; i++) CUDA_TRY(cudaEventElapsedTime(&timing3[i], ev[i], ev[i + 1]));
+      for (int i = 0; i < 4; i++) cudaEventDestroy(ev[i]);
+    }
+  } else {
+    CUDA_TRY(cudaStreamSynchronize(W.stream));
+    if (timing3) { timing3[0] = timing3[1] = timing3[2] = 0; for (int i = 0; i < 4; i++) cudaEventDestroy(ev[i]); }
+  }
+  const i64 bytes = (totalBits + 7) >> 3;
+  if (bytes > outCap - 8) { kzg_set_error("compressed stream (%lld bytes) exceeds capacity %lld", (long long)bytes, (long long)outCap); return -KZG_ERR_WRITE_FILE; }
+  return bytes;
+}
+
+// ---- decode side: the host walks the container (CIS:359-515, 1025-1095, 1127-1167), the device does the rest -------
+struct HostBits {
+  const u8* p; u64 nbits; u64 pos = 0; bool bad = false;
+  u64 read(int n) {
+    if (pos + (u64)n > nbits) { bad = true; pos += n; return 0; }
+    u64 v = 0;
+    for (int i = 0; i < n; i++, pos++) v = (v << 1) | ((p[pos >> 3] >> (7 - (pos & 7))) & 1);
+    return v;
+  }
+};
+
+int64_t kzg_decompress_dev(const uint8_t* d_in, int64_t nBytes, const uint8_t* h_in, int32_t flags, uint8_t* d_out, int64_t outCap,
+                           float* timing3) {
+  int r = ws_init(); if (r < 0) return r;
+  if (nBytes < 20 || h_in == nullptr) return -KZG_ERR_INVALID_FILE;
+  HostBits hb{h_in, (u64)nBytes * 8};
+  if ((u32)hb.read(32) != 0x4B414E5Au) { kzg_set_error("Invalid stream type"); return -KZG_ERR_INVALID_FILE; }
+  const int bsVersion = (int)hb.read(4);
+  if (bsVersion != 7) { kzg_set_error("bitstream version %d not supported (7 only)", bsVersion); return -KZG_ERR_STREAM_VERSION; }
+  const int chkSize = (int)hb.read(2);
+  if (chkSize != 0) { kzg_set_error("block checksums not supported"); return -KZG_ERR_INVALID_PARAM; }
+  const int entropy = (int)hb.read(5);
+  const u64 transformType = hb.read(48);
+  const i32 blockSize = (i32)(hb.read(28) << 4);
+  if (blockSize < 1024 || blockSize > (1 << 30)) return -KZG_ERR_BLOCK_SIZE;
+  const int szMask = (int)hb.read(2);
+  i64 outputSize = 0;
+  if (szMask != 0) outputSize = (i64)hb.read(16 * szMask);
+  hb.read(15);
+  const u32 cksum1 = (u32)hb.read(24);
+  {
+    const u32 HASH = 0x1E35A7BDu;
+    u32 c = HASH * (0x01030507u * (u32)bsVersion);
+    c = kzg_mix32(c, HASH, (u32)chkSize); c = kzg_mix32(c, HASH, (u32)entropy);
+    c = kzg_mix32(c, HASH, (u32)(transformType >> 32)); c = kzg_mix32(c, HASH, (u32)transformType);
+    c = kzg_mix32(c, HASH, (u32)blockSize);
+    if (szMask > 0) { c = kzg_mix32(c, HASH, (u32)((u64)outputSize >> 32)); c = kzg_mix32(c, HASH, (u32)outputSize); }
+    c = (c >> 23) ^ (c >> 3);
+    if (cksum1 != (c & 0xFFFFFF) || hb.bad) { kzg_set_error("Invalid bitstream, checksum mismatch"); return -KZG_ERR_CRC_CHECK; }
+  }
+  if (!ent_known(entropy)) return -KZG_ERR_INVALID_CODEC;
+  i32 tr[8]; for (int i = 0; i < 8; i++) tr[i] = (i32)((transformType >> (42 - 6 * i)) & 63);
+  for (int i = 0; i < 8; i++) if (!xf_known(tr[i])) { kzg_set_error("transform id %d not supported", tr[i]); return -KZG_ERR_INVALID_CODEC; }
+  int fn[8]; const int nf = seq_functions(tr, 8, fn);
+
+  // walk the block records
+  struct Rec { i64 payBit, payBits; i32 preLen; int skipFlags; int entropy; bool rawCopy; };
+  std::vector<Rec> recs;
+  const i32 maxTransformLength = std::min(std::max(blockSize + blockSize / 2, 2048), 1 << 30);
+  while (true) {
+    const int lr = (int)hb.read(5) + 3;
+    const i64 written = (i64)hb.read(lr);
+    if (hb.bad) { kzg_set_error("truncated stream"); return -KZG_ERR_READ_FILE; }
+    if (written == 0) break;
+    if (written < 8) return -KZG_ERR_BLOCK_SIZE;
+    const u64 blockStart = hb.pos;
+    const int mode = (int)hb.read(8);
+    int skipFlags = 0; bool hasSkip = false, transformedCopy = false;
+    const bool copyBlock = (mode & 0x80) != 0;
+    if (copyBlock) {
+      if (mode & 0x10) { transformedCopy = true; if (nf > 4) hasSkip = true; else skipFlags = ((mode << 4) | 0x0F) & 0xFF; }
+    } else if (mode & 0x10) hasSkip = true;
+    else skipFlags = ((mode << 4) | 0x0F) & 0xFF;
+    const int dataSize = 1 + ((mode >> 5) & 0x03);
+    const int headerSize = 1 + (hasSkip ? 1 : 0) + dataSize + 1;
+    if (written < (i64)headerSize * 8) return -KZG_ERR_BLOCK_SIZE;
+    if (hasSkip) skipFlags = (int)hb.read(8);
+    u32 pre = 0;
+    for (int i = 0; i < dataSize; i++) pre = (pre << 8) | (u32)hb.read(8);
+    const u32 hck = (u32)hb.read(8);
+    const u32 HASH = 0x1E35A7BDu;
+    u32 c = HASH * 0x01030507u;
+    c = kzg_mix32(c, HASH, (u32)(mode & 0xFF)); c = kzg_mix32(c, HASH, (u32)(skipFlags & 0xFF)); c = kzg_mix32(c, HASH, pre);
+    c = kzg_mix32(c, HASH, (u32)((u64)written >> 32)); c = kzg_mix32(c, HASH, (u32)written);
+    c = (c >> 23) ^ (c >> 3);
+    if (hb.bad || hck != (c & 0xFF)) { kzg_set_error("Invalid bitstream, block header checksum mismatch"); return -KZG_ERR_CRC_CHECK; }
+    if ((i32)pre < 0 || (i32)pre > maxTransformLength) { kzg_set_error("Invalid compressed block length: %d", (i32)pre); return -KZG_ERR_READ_FILE; }
+    if (((written + 7) >> 3) > (i64)pre + headerSize) return -KZG_ERR_BLOCK_SIZE;
+    if (pre == 0) break;                                         // "last block is empty" (CIS:1223-1227)
+    Rec rc;
+    rc.payBit = (i64)hb.pos; rc.payBits = written - (i64)headerSize * 8; rc.preLen = (i32)pre;
+    rc.rawCopy = copyBlock && !transformedCopy;
+    rc.skipFlags = rc.rawCopy ? 0xFF : (skipFlags & 0xFF);
+    rc.entropy = copyBlock ? KZG_E_NONE : entropy;
+    recs.push_back(rc);
+    hb.pos = blockStart + (u64)written;
+    if (hb.pos > hb.nbits) { kzg_set_error("truncated stream"); return -KZG_ERR_READ_FILE; }
+  }
+  const int nBlocks = (int)recs.size();
+  if (nBlocks == 0) return 0;
+  if ((i64)nBlocks * blockSize > outCap + blockSize) { kzg_set_error("output capacity too small"); return -KZG_ERR_WRITE_FILE; }
+
+  i32 maxPre = 0; for (auto& rc : recs) maxPre = std::max(maxPre, rc.preLen);
+  const i32 blkBuf = std::max(blockSize + 512, blockSize + (blockSize >> 4));      // CIS:694-695
+  const i32 maxLen = std::max(std::max(blockSize, maxPre + 512), blkBuf);
+  const size_t cap = rnd((size_t)maxLen + 64);
+  XfScratch xs = xf_scratch_size(fn, nf, maxLen, false);
+  EntScratch es = ent_scratch_size(entropy, maxPre, false);
+  const size_t nb = (size_t)nBlocks;
+  size_t need = nb * (sizeof(KzgBlock) + 64) + nb * cap * 2 + nb * xs.perBlock + nb * (xs.hashInts + xs.aux32) * 4 +
+                nb * (size_t)es.maxChunks * (sizeof(KzgChunkInfo) + es.tabStride * 4) + nf * nb + (1 << 20);
+  r = ws_reserve(need, nb * (sizeof(KzgBlock) + 16 + nf) + 4096); if (r < 0) return r;
+  Batch bt; bt.nBlocks = nBlocks; bt.maxLen = maxLen;
+  bt.hBlocks = halloc<KzgBlock>(nb); NN(bt.hBlocks);
+  bt.hEnabled = halloc<u8>(nb * nf + 16); NN(bt.hEnabled);
+  bt.hDstLimit = halloc<int>(nb); NN(bt.hDstLimit);
+  bt.dBlocks = dalloc<KzgBlock>(nb); NN(bt.dBlocks);
+  bt.dResult = dalloc<int>(2 * nb); NN(bt.dResult);
+  u8* dEnabledAll = dalloc<u8>(nb * nf + 16); NN(dEnabledAll);
+  bt.dDstLimit = dalloc<int>(nb); NN(bt.dDstLimit);
+  u8* dE = dalloc<u8>(nb * cap); NN(dE);
+  u8* dF = dalloc<u8>(nb * cap); NN(dF);
+  u8* dScratch = dalloc<u8>(nb * xs.perBlock + 16); NN(dScratch);
+  i32* dHash = dalloc<i32>(nb * xs.hashInts + 4); NN(dHash);
+  i32* dAux = dalloc<i32>(nb * xs.aux32 + 4); NN(dAux);
+  KzgChunkInfo* dChunks = dalloc<KzgChunkInfo>(nb * es.maxChunks + 1); NN(dChunks);
+  u32* dTab = dalloc<u32>(nb * es.maxChunks * es.tabStride + 4); NN(dTab);
+  bool anyNone = false, anyEnt = false;
+  for (int b = 0; b < nBlocks; b++) {
+    const Rec& rc = recs[b];
+    KzgBlock& B = bt.hBlocks[b];
+    memset(&B, 0, sizeof(B));
+    int k = 0;     // inverse stages this block runs (Sequence.inverse :160-166 skips flagged transforms)
+    for (int i = 0; i < nf; i++) {
+      const bool runs = (rc.skipFlags != 0xFF) && ((rc.skipFlags & (1 << (7 - i))) == 0) && fn[i] != KZG_T_NONE;
+      bt.hEnabled[(size_t)i * nb + b] = runs ? 1 : 0;
+      if (runs) k++;
+    }
+    u8* dest = d_out + (size_t)b * blockSize;
+    B.aux0 = dest; B.stagesLeft = k;
+    B.cur = (k == 0) ? dest : dE + (size_t)b * cap;
+    B.alt = (k == 1) ? dest : dF + (size_t)b * cap;
+    B.aux1 = dF + (size_t)b * cap;
+    B.curLen = rc.preLen; B.preLen = rc.preLen; B.cap = (i32)cap - 64; B.skipFlags = rc.skipFlags;
+    B.entropy = rc.entropy; B.srcBit = rc.payBit; B.srcBits = rc.payBits;
+    if (k == 0 && rc.preLen > blockSize) { kzg_set_error("Block %d incorrectly decompressed", b + 1); return -KZG_ERR_PROCESS_BLOCK; }
+    bt.hDstLimit[b] = blkBuf;
+    if (rc.entropy == KZG_E_NONE) anyNone = true; else anyEnt = true;
+  }
+  CUDA_TRY(cudaMemcpyAsync(dEnabledAll, bt.hEnabled, nb * nf, cudaMemcpyHostToDevice, W.stream));
+  CUDA_TRY(cudaMemcpyAsync(bt.dDstLimit, bt.hDstLimit, nb * sizeof(int), cudaMemcpyHostToDevice, W.stream));
+  r = batch_upload(bt); if (r < 0) return r;
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  if (timing3) { for (int i = 0; i < 3; i++) CUDA_TRY(cudaEventCreate(&ev[i])); CUDA_TRY(cudaEventRecord(ev[0], W.stream)); }
+  if (anyEnt) { r = run_entropy_decode(bt, entropy, es, d_in, dChunks, dTab); if (r < 0) return r; }
+  if (anyNone) { r = run_entropy_decode(bt, KZG_E_NONE, es, d_in, dChunks, dTab); if (r < 0) return r; }
+  if (timing3) CUDA_TRY(cudaEventRecord(ev[1], W.stream));
+  for (int i = nf - 1; i >= 0; i--) {
+    if (fn[i] == KZG_T_NONE) continue;
+    bt.dEnabled = dEnabledAll + (size_t)i * nb;
+    r = run_transform_stage(bt, fn[i], i, false, xs, dScratch, dHash, dAux, flags); if (r < 0) return r;
+  }
+  if (timing3) CUDA_TRY(cudaEventRecord(ev[2], W.stream));
+  r = batch_download(bt); if (r < 0) return r;
+  if (timing3) {
+    CUDA_TRY(cudaEventElapsedTime(&timing3[1], ev[0], ev[1])); CUDA_TRY(cudaEventElapsedTime(&timing3[0], ev[1], ev[2])); timing3[2] = 0;
+    for (int i = 0; i < 3; i++) cudaEventDestroy(ev[i]);
+  }
+  i64 total = 0;
+  for (int b = 0; b < nBlocks; b++) {
+    const KzgBlock& B = bt.hBlocks[b];
+    if (B.status != 0) { kzg_set_error("block %d failed with status %d", b + 1, B.status); return B.status; }
+    if (B.curLen > blockSize) { kzg_set_error("Block %d incorrectly decompressed", b + 1); return -KZG_ERR_PROCESS_BLOCK; }
+    if (b + 1 < nBlocks && B.curLen != blockSize) { kzg_set_error("short block %d (%d bytes) inside the stream", b + 1, B.curLen); return -KZG_ERR_PROCESS_BLOCK; }
+    if (B.cur != d_out + (size_t)b * blockSize) { kzg_set_error("internal: block %d did not land in place", b + 1); return -KZG_ERR_UNKNOWN; }
+    total += B.curLen;
+  }
+  if (total > outCap) return -KZG_ERR_WRITE_FILE;
+  return total;
+}
+
+// ---- host-buffer forms: H2D, the device path, D2H ---------------------------------------------------------------------
+int64_t kzg_compress(const uint8_t* in, int64_t n, const int32_t* transforms, int32_t nTransforms, int32_t entropy, int32_t blockSize,
+                     int32_t flags, uint8_t* out, int64_t outCap) {
+  int r = ws_init(); if (r < 0) return r;
+  if (n < 0 || (n > 0 && in == nullptr) || out == nullptr) return -KZG_ERR_INVALID_PARAM;
+  const i64 bound = std::min<i64>(outCap, kzg_compress_bound(n, blockSize)) + 16;
+  u8* dIn = nullptr; u8* dOut = nullptr;
+  const size_t inCap = rnd((size_t)n + 64);
+  if (cudaMalloc((void**)&dIn, inCap) != cudaSuccess || cudaMalloc((void**)&dOut, rnd((size_t)bound + 64)) != cudaSuccess) {
+    cudaGetLastError(); if (dIn) cudaFree(dIn); kzg_set_error("cudaMalloc failed for stream buffers"); return -KZG_ERR_CREATE_CODEC;
+  }
+  i64 res;
+  do {
+    if (cudaMemsetAsync(dIn + n, 0, inCap - n, W.stream) != cudaSuccess) { res = -KZG_ERR_PROCESS_BLOCK; break; }
+    if (n > 0 && cudaMemcpyAsync(dIn, in, (size_t)n, cudaMemcpyHostToDevice, W.stream) != cudaSuccess) { res = -KZG_ERR_PROCESS_BLOCK; break; }
+    res = kzg_compress_dev(dIn, n, transforms, nTransforms, entropy, blockSize, flags, dOut, bound, nullptr);
+    if (res < 0) break;
+    if (res > outCap) { res = -KZG_ERR_WRITE_FILE; break; }
+    if (cudaMemcpy(out, dOut, (size_t)res, cudaMemcpyDeviceToHost) != cudaSuccess) { res = -KZG_ERR_PROCESS_BLOCK; break; }
+  } while (0);
+  cudaFree(dIn); cudaFree(dOut);
+  return res;
+}
+
+int64_t kzg_decompress(const uint8_t* in, int64_t nBytes, int32_t flags, uint8_t* out, int64_t outCap) {
+  int r = ws_init(); if (r < 0) return r;
+  if (in == nullptr || out == nullptr || nBytes < 0 || outCap < 0) return -KZG_ERR_INVALID_PARAM;
+  u8* dIn = nullptr; u8* dOut = nullptr;
+  const size_t inCap = rnd((size_t)nBytes + 64);
+  // room for whole blocks: the last block may be short but kernels address by block
+  if (cudaMalloc((void**)&dIn, inCap) != cudaSuccess || cudaMalloc((void**)&dOut, rnd((size_t)outCap + 64)) != cudaSuccess) {
+    cudaGetLastError(); if (dIn) cudaFree(dIn); kzg_set_error("cudaMalloc failed for stream buffers"); return -KZG_ERR_CREATE_CODEC;
+  }
+  i64 res;
+  do {
+    if (cudaMemsetAsync(dIn + nBytes, 0, inCap - nBytes, W.stream) != cudaSuccess) { res = -KZG_ERR_PROCESS_BLOCK; break; }
+    if (cudaMemcpyAsync(dIn, in, (size_t)nBytes, cudaMemcpyHostToDevice, W.stream) != cudaSuccess) { res = -KZG_ERR_PROCESS_BLOCK; break; }
+    res = kzg_decompress_dev(dIn, nBytes, in, flags, dOut, outCap, nullptr);
+    if (res < 0) break;
+    if (cudaMemcpy(out, dOut, (size_t)res, cudaMemcpyDeviceToHost) != cudaSuccess) { res = -KZG_ERR_PROCESS_BLOCK; break; }
+  } while (0);
+  cudaFree(dIn); cudaFree(dOut);
+  return res;
+}
+
+}  // extern "C"

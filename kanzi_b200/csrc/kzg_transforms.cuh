@@ -1,0 +1,19 @@
+// kzg_transforms.cuh — parameter block shared by the transform-stage kernels (lz.cu, rolz.cu, bwt.cu,
+// sbrt.cu, srt.cu, zrlt.cu) and the Sequence bookkeeping (container.cu).
+#pragma once
+#include "kzg_common.cuh"
+
+struct KzgXfParams {
+  int* result;            // [2 * nBlocks]: {boolean result of forward()/inverse(), bytes produced}
+  const u8* enabled;      // [nBlocks]: stage runs for this block (preconditions / skip flags, host-evaluated)
+  const int* dstLimit;    // [nBlocks]: dst.array.length (inverse) or dst slice length (forward) as Java sees it
+  u8* scratch; i64 scratchStride;      // per-block scratch area
+  int tkStride, mStride, mLenStride;   // LZ: sub-buffer capacities inside the scratch area
+  i32* hashBuf;                        // LZ/ROLZ: global hash / match tables
+  i32* aux32; i64 aux32Stride;         // BWT etc.: per-block 32-bit scratch (u32 units)
+  int flags;
+};
+
+int kzg_lz_forward_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, const KzgXfParams& P, bool extra, bool smemTable);
+int kzg_lz_inverse_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, const KzgXfParams& P);
+void kzg_count_launch(int n);
