@@ -161,7 +161,7 @@ def bwt_inverse(data, primary_indexes):
 def entropy_encode(kind, data, ctx=None):
     """EntropyEncoder.encode + dispose -> (payload bytes, bit length)."""
     a, p = _u8(data)
-    cap = len(a) + len(a) // 4 + 8192
+    cap = 2 * len(a) + (300 << 10)
     out = np.zeros(cap, dtype=np.uint8)
     bits = C.c_int64(0)
     c = _ctx(ctx)

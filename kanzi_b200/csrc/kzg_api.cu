@@ -341,10 +341,10 @@ int64_t kzg_entropy_encode(int type, kzg_ctx* ctx, const uint8_t* src, int32_t n
   if (!ent_known(type)) return -KZG_ERR_INVALID_CODEC;
   if (n < 0 || src == nullptr || out == nullptr) return -1;          // Java: encode returns -1 on bad arguments
   int r = ws_init(); if (r < 0) return r;
-  if (n == 0 && type != KZG_E_FPAQ) return 0;
+  if (n == 0) return 0;
   EntScratch es = ent_scratch_size(type, n, true);
   const size_t cap = rnd((size_t)n + 64);
-  const size_t outBytes = rnd((size_t)n + n / 4 + 4096);
+  const size_t outBytes = rnd(2 * (size_t)n + (256 << 10));     // ANS1 on noise: 256 context headers + up to 2 bytes per symbol
   const size_t need = cap + outBytes + (size_t)es.maxChunks * (es.hdrStride + es.payStride + es.tabStride * 4) +
                       (size_t)es.segsPerBlock * sizeof(KzgSeg) + 65536;
   r = ws_reserve(need, sizeof(KzgBlock) + 4096); if (r < 0) return r;
