@@ -14,6 +14,7 @@
 // table-lookup chain of the rANS recurrence, not by bandwidth.
 #include "kzg_common.cuh"
 #include "kzg_entropy.cuh"
+#include "ans_scan.cuh"
 
 #define ANS_TOP (1 << 15)
 
@@ -149,11 +150,12 @@ __global__ void __launch_bounds__(128) ans0_encode_kernel(const KzgBlock* __rest
   const int b = blockIdx.y;
   const int c = blockIdx.x * A0_GROUPS + g;
   const KzgBlock& B = blocks[b];
-  const int len = (B.status == 0 && B.entropy == P.entropy) ? B.curLen : 0;
+  if (!(B.status == 0 && B.entropy == P.entropy)) return;     // not this launch's codec (segments stay as the caller zeroed them)
+  const int len = B.curLen;
   const u8* __restrict__ data = B.cur;
   const int chunkSize = P.chunkSize;
   const int lr = 12;
-  const i64 gidx = (i64)b * P.maxChunks + c;
+  const i64 gidx = (P.slotBase ? (i64)P.slotBase[b] : (i64)b * P.maxChunks) + c;
   const bool rawAll = (len <= 32);          // ANSRangeEncoder.encode :267-270: count <= 32 -> raw bytes
   const int start = c * chunkSize;
   const bool active = (!rawAll) && (c < P.maxChunks) && (start < len);
@@ -270,62 +272,14 @@ __global__ void __launch_bounds__(128) ans0_encode_kernel(const KzgBlock* __rest
 // chunk scan for decode (order 0 and 1): one thread per block walks the chunk headers to find where each
 // chunk starts (the only serial part of decoding: chunk k+1 starts where chunk k's byte count says).
 // ================================================================================================================
-__device__ int ans_skip_alphabet(BitReaderD& br) {   // EntropyUtils.decodeAlphabet sizes only
-  if (br.read(1) == 0) return (br.read(1) == 1) ? 0 : 256;
-  const int lastMask = (int)br.read(5);
-  int count = 0;
-  for (int i = 0; i <= lastMask; i++) count += __popc(br.read(8));
-  return count;
-}
-
 __global__ void ans_scan_kernel(KzgBlock* __restrict__ blocks, int nBlocks, KzgEntParams P, int order) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nBlocks) return;
   KzgBlock& B = blocks[b];
   if (B.status != 0 || B.entropy != P.entropy) return;
-  const int len = B.preLen;
-  KzgChunkInfo* ci = P.chunks + (i64)b * P.maxChunks;
-  if (len <= 32) {   // raw (ANSRangeDecoder.decode :193-196)
-    B.entBits = (i64)len * 8;
-    if ((i64)len * 8 > B.srcBits) B.status = -KZG_ERR_PROCESS_BLOCK;
-    return;
-  }
   BitReaderD br(P.stream, (u64)B.srcBit, (u64)(B.srcBit + B.srcBits));
-  const int nChunks = (len + P.chunkSize - 1) / P.chunkSize;
-  const int dim = 255 * order + 1;
-  for (int c = 0; c < nChunks; c++) {
-    KzgChunkInfo info;
-    info.hdrBit = (i64)br.pos;
-    const int lr = 8 + (int)br.read(3);
-    int llr = 3;
-    while ((1 << llr) <= lr) llr++;
-    int res = 0;
-    for (int k = 0; k < dim; k++) {
-      const int alphabetSize = ans_skip_alphabet(br);
-      if (alphabetSize == 0) continue;
-      const int chkSize = (alphabetSize >= 64) ? 8 : 6;
-      for (int i = 1; i < alphabetSize; i += chkSize) {
-        const int logMax = (int)br.read(llr);
-        const int endj = (i + chkSize < alphabetSize) ? i + chkSize : alphabetSize;
-        br.pos += (u64)(logMax * (endj - i));
-      }
-      res += alphabetSize;
-      if (br.overrun()) break;
-    }
-    info.alphabetSize = res;
-    info.sz = 0; info.payBit = 0;
-    if (res == 0 || br.overrun()) { B.status = -KZG_ERR_PROCESS_BLOCK; return; }   // decode returns early (:218-219)
-    if (!(order == 0 && res == 1)) {
-      const i32 sz = read_varint(br);
-      if (sz < 0 || sz >= (1 << 27)) { B.status = -KZG_ERR_PROCESS_BLOCK; return; }
-      info.st[0] = br.read(32); info.st[1] = br.read(32); info.st[2] = br.read(32); info.st[3] = br.read(32);
-      info.sz = sz;
-      info.payBit = (i64)br.pos;
-      br.pos += (u64)sz * 8;
-    }
-    if (br.overrun()) { B.status = -KZG_ERR_PROCESS_BLOCK; return; }
-    ci[c] = info;
-  }
+  const int r = ans_scan_stream(br, B.preLen, P.chunkSize, order, P.chunks + (i64)b * P.maxChunks);
+  if (r < 0) { B.status = r; return; }
   B.entBits = (i64)br.pos - B.srcBit;
 }
 
@@ -513,11 +467,12 @@ __global__ void __launch_bounds__(32) ans1_encode_kernel(const KzgBlock* __restr
   const int b = blockIdx.y;
   const int c = blockIdx.x;
   const KzgBlock& B = blocks[b];
-  const int len = (B.status == 0 && B.entropy == P.entropy) ? B.curLen : 0;
+  if (!(B.status == 0 && B.entropy == P.entropy)) return;
+  const int len = B.curLen;
   const u8* __restrict__ data = B.cur;
   const int chunkSize = P.chunkSize;     // 4 MiB
   const int lr = 11;
-  const i64 gidx = (i64)b * P.maxChunks + c;
+  const i64 gidx = (P.slotBase ? (i64)P.slotBase[b] : (i64)b * P.maxChunks) + c;
   KzgSeg* segs = P.segs + (i64)b * P.segsPerBlock + 1 + (i64)c * 2;
   if (len <= 32) {
     if (lane == 0) {
@@ -673,7 +628,7 @@ __global__ void __launch_bounds__(32) ans1_decode_kernel(KzgBlock* __restrict__ 
   const int end = min(start + chunkSize, len);
   const i64 gidx = (i64)b * P.maxChunks + c;
   const KzgChunkInfo info = P.chunks[gidx];
-  u32* tab = P.tabBuf + gidx * (i64)P.tabStride;
+  u32* tab = P.tabBuf + ((P.slotBase ? (i64)P.slotBase[b] : (i64)b * P.maxChunks) + c) * (i64)P.tabStride;
   u32* sym = tab;                               // [256][256] freq | cum << 16
   u8* f2s = (u8*)(tab + 65536);                 // [256][2048]  (logRange <= 11 for order 1)
   u16* freq = (u16*)(f2s + 256 * 2048);         // [256] scratch for one context
@@ -774,9 +729,11 @@ int kzg_ans_encode_launch(cudaStream_t s, const KzgBlock* d_blocks, int nBlocks,
   return 0;
 }
 
-int kzg_ans_decode_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, const KzgEntParams& P, int order) {
-  ans_scan_kernel<<<(nBlocks + 31) / 32, 32, 0, s>>>(d_blocks, nBlocks, P, order);
-  CUDA_TRY(cudaGetLastError());
+int kzg_ans_decode_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, const KzgEntParams& P, int order, bool withScan) {
+  if (withScan) {
+    ans_scan_kernel<<<(nBlocks + 31) / 32, 32, 0, s>>>(d_blocks, nBlocks, P, order);
+    CUDA_TRY(cudaGetLastError());
+  }
   if (order == 0) {
     static bool attr = false;
     if (!attr) { CUDA_TRY(cudaFuncSetAttribute(ans0_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(A0DecSmem))); attr = true; }

@@ -191,6 +191,14 @@ __global__ void __launch_bounds__(256) kzg_bitcopy_kernel(const KzgSeg* __restri
   }
 }
 
+int kzg_bitcopy_launch(cudaStream_t s, const KzgSeg* segs, i64 nSegs) {
+  if (nSegs <= 0) return 0;
+  kzg_bitcopy_kernel<<<(unsigned)nSegs, 256, 0, s>>>(segs, (u32*)nullptr);
+  CUDA_TRY(cudaGetLastError());
+  kzg_count_launch(1);
+  return 0;
+}
+
 // ---- host launchers ------------------------------------------------------------------------------------------
 int kzg_commit_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, const int* result, const u8* enabled, int stage, int forward) {
   kzg_commit_kernel<<<(nBlocks + 127) / 128, 128, 0, s>>>(d_blocks, nBlocks, result, enabled, stage, forward);

@@ -302,7 +302,7 @@ static int transform_call(int type, bool forward, kzg_ctx* ctx, const uint8_t* s
   r = batch_upload(bt); if (r < 0) return r;
   const int flags = ctx ? ctx->flags : 0;
   // (commit's inverse branch flags a failed inverse as a block error; here a false result is reported as 0)
-  r = run_transform_stage(bt, type, 0, forward, xs, dScratch, dHash, dAux, flags | (ctx ? 0 : 0)); if (r < 0) return r;
+  r = run_transform_stage(bt, type, 0, forward, xs, dScratch, dHash, dAux, flags & ~KZG_FLAG_BWT_ASREF); if (r < 0) return r;   // the slice guards were evaluated by kzg_stage_precheck
   int hres[2] = {0, 0};
   CUDA_TRY(cudaMemcpyAsync(hres, bt.dResult, sizeof(hres), cudaMemcpyDeviceToHost, W.stream));
   r = batch_download(bt); if (r < 0) return r;

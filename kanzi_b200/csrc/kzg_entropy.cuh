@@ -20,6 +20,7 @@ struct KzgEntParams {
   u8* hdrBuf; int hdrStride;
   u8* payBuf; int payStride;
   u32* tabBuf; i64 tabStride;     // u32 units (order-1 tables)
+  const int* slotBase;            // optional: first scratch slot of block b (default b * maxChunks); lets sparse users (ROLZ) pack slots
   KzgSeg* segs; int segsPerBlock;  // block b, chunk c, k-th segment: segs[b*segsPerBlock + 1 + c*segsPerChunk + k] (slot 0 = raw copy)
   // decode side
   const u8* stream;               // compressed stream (device), >= 16 bytes of slack after the end
@@ -29,7 +30,7 @@ struct KzgEntParams {
 void kzg_count_launch(int n);
 
 int kzg_ans_encode_launch(cudaStream_t s, const KzgBlock* d_blocks, int nBlocks, const KzgEntParams& P, int order);
-int kzg_ans_decode_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, const KzgEntParams& P, int order);
+int kzg_ans_decode_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, const KzgEntParams& P, int order, bool withScan = true);
 size_t kzg_ans1_enc_tab_u32();
 size_t kzg_ans1_dec_tab_u32();
 
@@ -38,3 +39,4 @@ int kzg_huff_decode_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
 
 int kzg_fpaq_encode_launch(cudaStream_t s, const KzgBlock* d_blocks, int nBlocks, const KzgEntParams& P);
 int kzg_fpaq_decode_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, const KzgEntParams& P);
+int kzg_bitcopy_launch(cudaStream_t s, const KzgSeg* segs, i64 nSegs);

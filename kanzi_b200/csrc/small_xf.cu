@@ -1,0 +1,462 @@
+// small_xf.cu — ZRLT, SBRT (RANK / MTFT) and SRT kernels (sm_100a).
+//
+// Replaces K/transform/ZRLT.java, SBRT.java, SRT.java.
+// ZRLT is a scan: one warp per block walks 32-byte tiles, classifies bytes with ballots (zero runs,
+// 0xFF escapes), sizes each lane's output, prefix-sums the sizes and scatters — run lengths and escape
+// parity are carried across tiles in registers.
+// SBRT / SRT are list-update state machines (the output at i depends on the list after i-1): one warp
+// per block keeps the 256-entry list in shared memory; the search for the insertion rank is a ballot
+// over 32 candidates per step and the shift of the displaced entries is lane-parallel.
+#include "kzg_common.cuh"
+#include "kzg_transforms.cuh"
+#include "kzg_xf_kernels.cuh"
+
+__device__ __forceinline__ u32 warp_excl_scan(u32 v, int lane, u32& total) {
+  u32 incl = v;
+  for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+  total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+  return incl - v;
+}
+
+// ================================================================================================================
+// ZRLT.forward (ZRLT.java:54-136)
+// ================================================================================================================
+__global__ void __launch_bounds__(32) zrlt_forward_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P) {
+  const int lane = threadIdx.x, b = blockIdx.x;
+  KzgBlock& B = blocks[b];
+  int* res = P.result + 2 * b;
+  if (lane == 0) { res[0] = 0; res[1] = 0; }
+  if (B.status != 0 || !P.enabled[b]) return;
+  const int count = B.curLen;
+  const u8* __restrict__ src = B.cur;
+  u8* __restrict__ dst = B.alt;
+  const int dstEnd = count;                 // "do not expand"
+  u32 dstIdx = 0;
+  u32 carry = 0;                            // zeros pending from earlier tiles
+  bool fail = false;
+  const u32 lowMask = (1u << lane) - 1;
+  for (int base = 0; base < count; base += 32) {
+    const int i = base + lane;
+    const bool valid = i < count;
+    const int v = valid ? src[i] : 1;
+    const bool z = valid && (v == 0);
+    const u32 zmask = __ballot_sync(0xFFFFFFFFu, z);
+    const u32 vmask = __ballot_sync(0xFFFFFFFFu, valid);
+    // zeros directly below this lane (plus the carry when they reach the start of the tile)
+    const u32 nzBelow = ~zmask & lowMask;
+    u32 run;
+    if (nzBelow == 0) run = (u32)lane + carry;
+    else run = (u32)(lane - 1 - (31 - __clz(nzBelow)));
+    u32 size = 0; int lg = 0;
+    if (valid && !z) {
+      if (run > 0) lg = ilog2(run + 1);
+      size = (u32)lg + ((v >= 0xFE) ? 2u : 1u);
+    }
+    u32 total;
+    const u32 off = warp_excl_scan(size, lane, total);
+    if (valid && !z) {
+      u32 o = dstIdx + off;
+      if (run > 0) {
+        if ((i64)o >= (i64)dstEnd - lg) fail = true;        // :76
+        else { const u32 rl = run + 1; for (int k = lg - 1; k >= 0; k--) dst[o++] = (u8)((rl >> k) & 1); }
+      }
+      if (!fail) {
+        if (v >= 0xFE) {
+          if ((i64)o >= (i64)dstEnd - 1) fail = true;       // :94
+          else { dst[o] = 0xFF; dst[o + 1] = (u8)(v - 0xFE); }
+        } else {
+          if ((i64)o >= (i64)dstEnd) fail = true;           // :111
+          else dst[o] = (u8)(v + 1);
+        }
+      }
+    }
+    if (__any_sync(0xFFFFFFFFu, fail)) { fail = true; break; }
+    dstIdx += total;
+    // trailing zeros of this tile
+    const u32 nzAll = ~zmask & vmask;
+    if (nzAll == 0) carry += __popc(vmask);
+    else carry = (u32)__popc(vmask) - 1 - (31 - __clz(nzAll));
+  }
+  if (!fail && carry > 0) {                 // input ends inside a zero run
+    const u32 rl = carry + 1;
+    const int lg = ilog2(rl);
+    if ((i64)dstIdx >= (i64)dstEnd - lg) fail = true;
+    else if (lane == 0) { for (int k = lg - 1; k >= 0; k--) dst[dstIdx + (lg - 1 - k)] = (u8)((rl >> k) & 1); }
+    dstIdx += lg;
+  }
+  if (lane == 0 && !fail) { res[0] = 1; res[1] = (int)dstIdx; }
+}
+
+// ================================================================================================================
+// ZRLT.inverse (ZRLT.java:146-233)
+// ================================================================================================================
+__global__ void __launch_bounds__(32) zrlt_inverse_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P) {
+  const int lane = threadIdx.x, b = blockIdx.x;
+  KzgBlock& B = blocks[b];
+  int* res = P.result + 2 * b;
+  if (lane == 0) { res[0] = 0; res[1] = 0; }
+  if (B.status != 0 || !P.enabled[b]) return;
+  const int count = B.curLen;
+  const u8* __restrict__ src = B.cur;
+  u8* __restrict__ dst = B.alt;
+  const i64 dstEnd = min(P.dstLimit[b], B.cap);
+  i64 dstIdx = 0;
+  u64 carryVal = 1;          // run length accumulated by the digit sequence in progress (1 = none)
+  bool pendingEsc = false;   // the previous tile ended with an unpaired 0xFF
+  bool fail = false;
+  const u32 lowMask = (1u << lane) - 1;
+  for (int base = 0; base < count; base += 32) {
+    const int i = base + lane;
+    const bool valid = i < count;
+    const int v = valid ? src[i] : 2;
+    const u32 vmask = __ballot_sync(0xFFFFFFFFu, valid);
+    const u32 ffmask = __ballot_sync(0xFFFFFFFFu, valid && v == 0xFF);
+    // escapes pair up with their payload: byte is a payload iff the 0xFF run directly below it has odd length
+    const u32 nonFFBelow = ~ffmask & lowMask;
+    bool payload;
+    if (nonFFBelow == 0) payload = (((lane & 1) != 0) != pendingEsc);
+    else payload = (((lane - 1 - (31 - __clz(nonFFBelow))) & 1) != 0);
+    payload = payload && valid;
+    const bool digit = valid && !payload && v <= 1;
+    const bool esc = valid && !payload && v == 0xFF;
+    const u32 dmask = __ballot_sync(0xFFFFFFFFu, digit);
+    const u32 onemask = __ballot_sync(0xFFFFFFFFu, digit && v == 1);
+    // digits directly below this lane
+    const u32 ndBelow = ~dmask & lowMask;
+    int k; bool reachesStart;
+    if (ndBelow == 0) { k = lane; reachesStart = true; }
+    else { k = lane - 1 - (31 - __clz(ndBelow)); reachesStart = false; }
+    u64 zeros = 0;
+    const bool closer = valid && !digit && !payload;          // literal or escape: closes a digit run if one precedes it
+    if (closer) {
+      const u32 bits = (k > 0) ? (__brev((onemask >> (lane - k)) & ((k == 32) ? 0xFFFFFFFFu : ((1u << k) - 1))) >> (32 - k)) : 0u;
+      const u64 base1 = reachesStart ? carryVal : 1ull;
+      const u64 value = (k >= 40 || base1 > (1ull << 40)) ? (1ull << 62) : ((base1 << k) | (u64)bits);
+      zeros = value - 1;
+    }
+    const bool lit = closer && !esc;
+    if (zeros >= (u64)dstEnd) { fail = true; zeros = 0; }
+    if (__any_sync(0xFFFFFFFFu, fail)) { fail = true; break; }
+    u32 size = (u32)zeros + ((lit || payload) ? 1u : 0u);
+    u32 total;
+    const u32 off = warp_excl_scan(size, lane, total);
+    // bounds: a run followed by its closer needs dstIdx + run < dstEnd (:172); every byte needs dstIdx < dstEnd
+    const i64 o = dstIdx + off;
+    if (closer && zeros > 0 && o + (i64)zeros >= dstEnd) fail = true;
+    if ((lit || payload) && o + (i64)zeros >= dstEnd) fail = true;
+    if (__any_sync(0xFFFFFFFFu, fail)) { fail = true; break; }
+    if (zeros > 0 && zeros <= 64) for (u32 t = 0; t < (u32)zeros; t++) dst[o + t] = 0;
+    if (lit) dst[o + zeros] = (u8)(v - 1);
+    else if (payload) dst[o] = (u8)(0xFE + v);
+    // long runs: the whole warp fills them
+    u32 longMask = __ballot_sync(0xFFFFFFFFu, zeros > 64);
+    while (longMask) {
+      const int l = __ffs(longMask) - 1;
+      longMask &= longMask - 1;
+      const i64 o2 = __shfl_sync(0xFFFFFFFFu, o, l);
+      const u32 z2 = __shfl_sync(0xFFFFFFFFu, (u32)zeros, l);
+      for (u32 t = lane; t < z2; t += 32) dst[o2 + t] = 0;
+    }
+    dstIdx += total;
+    // carries
+    const int nv = __popc(vmask);
+    const u32 ndAll = ~dmask & vmask;
+    if (ndAll == 0) {           // the whole tile is digits
+      const u32 bits = __brev(onemask & vmask) >> (32 - nv);
+      carryVal = (carryVal > (1ull << 40)) ? (1ull << 62) : ((carryVal << nv) | (u64)bits);
+    } else {
+      const int top = 31 - __clz(ndAll);            // highest non-digit lane
+      const int t = nv - 1 - top;                   // trailing digits
+      carryVal = (t > 0) ? ((1ull << t) | (u64)(__brev((onemask >> (top + 1)) & ((1u << t) - 1)) >> (32 - t))) : 1ull;
+    }
+    pendingEsc = (__shfl_sync(0xFFFFFFFFu, (int)esc, nv - 1) != 0);
+  }
+  if (!fail && carryVal > 1) {      // trailing zeros (:221-229)
+    const u64 zeros = carryVal - 1;
+    if (dstIdx + (i64)zeros > dstEnd || zeros > (1ull << 31)) fail = true;
+    else { for (u64 t = lane; t < zeros; t += 32) dst[dstIdx + t] = 0; dstIdx += (i64)zeros; }
+  }
+  if (lane == 0 && !fail) { res[0] = 1; res[1] = (int)dstIdx; }
+}
+
+// ================================================================================================================
+// list machinery shared by SBRT and SRT: entries [lo, hi) move up one slot (to [lo+1, hi+1))
+// ================================================================================================================
+template <bool WITH_Q, bool WITH_S2R>
+__device__ __forceinline__ void list_shift_up(u8* r2s, i32* qr, u8* s2r, int lo, int hi, int lane) {
+  for (int top = hi - 1; top >= lo; top -= 32) {
+    const int k = top - lane;
+    u8 sym = 0; i32 q = 0;
+    const bool on = k >= lo;
+    if (on) { sym = r2s[k]; if (WITH_Q) q = qr[k]; }
+    __syncwarp();
+    if (on) { r2s[k + 1] = sym; if (WITH_Q) qr[k + 1] = q; if (WITH_S2R) s2r[sym] = (u8)(k + 1); }
+    __syncwarp();
+  }
+}
+
+// ================================================================================================================
+// SBRT forward / inverse (SBRT.java:87-151, 154-214); mode 1 = MTF, 2 = RANK, 3 = TIMESTAMP
+// ================================================================================================================
+struct SbrtSmem { i32 qr[256]; i32 p[256]; u8 r2s[256]; u8 s2r[256]; };
+
+template <bool FORWARD>
+__global__ void __launch_bounds__(32) sbrt_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P, int mode) {
+  __shared__ SbrtSmem S;
+  const int lane = threadIdx.x, b = blockIdx.x;
+  KzgBlock& B = blocks[b];
+  int* res = P.result + 2 * b;
+  if (lane == 0) { res[0] = 0; res[1] = 0; }
+  if (B.status != 0 || !P.enabled[b]) return;
+  const int count = B.curLen;
+  const u8* __restrict__ src = B.cur;
+  u8* __restrict__ dst = B.alt;
+  if (count > B.cap) return;
+  const int m1 = (mode == 3) ? 0 : -1, m2 = (mode == 1) ? 0 : -1, s = (mode == 2) ? 1 : 0;
+  for (int i = lane; i < 256; i += 32) { S.qr[i] = 0; S.p[i] = 0; S.r2s[i] = (u8)i; S.s2r[i] = (u8)i; }
+  __syncwarp();
+  for (int base = 0; base < count; base += 32) {
+    const int nIn = min(32, count - base);
+    const int mine = (lane < nIn) ? src[base + lane] : 0;     // one coalesced load per 32 symbols
+    int outv = 0;
+    for (int t = 0; t < nIn; t++) {
+      const int i = base + t;
+      const int in = __shfl_sync(0xFFFFFFFFu, mine, t);
+      int r, c;
+      if (FORWARD) { c = in; r = S.s2r[c]; if (lane == t) outv = r; }
+      else { r = in; c = S.r2s[r]; if (lane == t) outv = c; }
+      const int qc = ((i & m1) + (S.p[c] & m2)) >> s;
+      __syncwarp();
+      if (lane == 0) S.p[c] = i;
+      // new rank: just above the highest entry below r whose q is greater than qc (:138-142)
+      int rn = 0;
+      for (int top = r - 1; top >= 0; top -= 32) {
+        const int k = top - lane;
+        const bool gt = (k >= 0) && (S.qr[k] > qc);
+        const u32 m = __ballot_sync(0xFFFFFFFFu, gt);
+        if (m) { rn = top - (__ffs(m) - 1) + 1; break; }
+      }
+      if (rn < r) list_shift_up<true, FORWARD>(S.r2s, S.qr, S.s2r, rn, r, lane);
+      if (lane == 0) { S.r2s[rn] = (u8)c; S.qr[rn] = qc; if (FORWARD) S.s2r[c] = (u8)rn; }
+      __syncwarp();
+    }
+    if (lane < nIn) dst[base + lane] = (u8)outv;
+  }
+  if (lane == 0) { res[0] = 1; res[1] = count; }
+}
+
+// ================================================================================================================
+// SRT (SRT.java:73-168 forward, 178-257 inverse)
+// ================================================================================================================
+struct SrtSmem { i32 freqs[256]; i32 buckets[256]; i32 bucketEnds[256]; i32 firstPos[256]; u8 r2s[256]; u8 s2r[256]; u8 symbols[256]; int nbSymbols; int hdrLen; };
+
+// SRT.preprocess (:266-302): present symbols ordered by (freq desc, symbol asc) — a strict total order, so any sort gives it
+__device__ void srt_preprocess(SrtSmem& S, int lane) {
+  if (lane == 0) {
+    int n = 0;
+    for (int i = 0; i < 256; i++) if (S.freqs[i] > 0) S.symbols[n++] = (u8)i;
+    S.nbSymbols = n;
+    for (int i = 1; i < n; i++) {           // insertion sort
+      const int t = S.symbols[i];
+      int k = i - 1;
+      while (k >= 0 && ((S.freqs[S.symbols[k]] < S.freqs[t]) || ((S.freqs[t] == S.freqs[S.symbols[k]]) && (t < S.symbols[k])))) {
+        S.symbols[k + 1] = S.symbols[k]; k--;
+      }
+      S.symbols[k + 1] = (u8)t;
+    }
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(32) srt_forward_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P) {
+  __shared__ SrtSmem S;
+  const int lane = threadIdx.x, b = blockIdx.x;
+  KzgBlock& B = blocks[b];
+  int* res = P.result + 2 * b;
+  if (lane == 0) { res[0] = 0; res[1] = 0; }
+  if (B.status != 0 || !P.enabled[b]) return;
+  const int count = B.curLen;
+  const u8* __restrict__ src = B.cur;
+  u8* __restrict__ dst = B.alt;
+  if (count + 1024 > B.cap) return;
+  for (int i = lane; i < 256; i += 32) { S.freqs[i] = 0; S.firstPos[i] = 0x7FFFFFFF; S.r2s[i] = 0; S.s2r[i] = 0; }
+  __syncwarp();
+  for (int i = lane; i < count; i += 32) { const int c = src[i]; atomicAdd(&S.freqs[c], 1); atomicMin(&S.firstPos[c], i); }
+  __syncwarp();
+  // first symbols in order of appearance (:92-106): rank of firstPos among present symbols
+  for (int c = lane; c < 256; c += 32) {
+    if (S.freqs[c] == 0) continue;
+    int rk = 0;
+    for (int o = 0; o < 256; o++) if (S.firstPos[o] < S.firstPos[c]) rk++;
+    S.r2s[rk] = (u8)c; S.s2r[c] = (u8)rk;
+  }
+  __syncwarp();
+  srt_preprocess(S, lane);
+  if (lane == 0) {
+    int bucketPos = 0;
+    for (int i = 0; i < S.nbSymbols; i++) { const int c = S.symbols[i]; S.buckets[c] = bucketPos; bucketPos += S.freqs[c]; }
+    int k = 0;                              // encodeHeader (:312-325)
+    for (int i = 0; i < 256; i++) {
+      u32 f = (u32)S.freqs[i];
+      while (f >= 128) { dst[k++] = (u8)(0x80 | f); f >>= 7; }
+      dst[k++] = (u8)f;
+    }
+    S.hdrLen = k;
+  }
+  __syncwarp();
+  const int hdr = S.hdrLen;
+  u8* __restrict__ out = dst + hdr;
+  // encoding (:139-164): MTF rank at the head of every run, zeros for the rest of the run, bucketed by symbol
+  int i = 0;
+  while (i < count) {
+    const int c = src[i];
+    const int r = S.s2r[c];
+    int p = S.buckets[c];
+    __syncwarp();
+    if (lane == 0) out[p] = (u8)r;
+    p++;
+    if (r != 0) {
+      list_shift_up<false, true>(S.r2s, nullptr, S.s2r, 0, r, lane);
+      if (lane == 0) { S.r2s[0] = (u8)c; S.s2r[c] = 0; }
+      __syncwarp();
+    }
+    i++;
+    // rest of the run
+    while (i < count) {
+      const int k = i + lane;
+      const bool same = (k < count) && (src[k] == c);
+      const u32 m = __ballot_sync(0xFFFFFFFFu, !same);
+      const int n = m ? (__ffs(m) - 1) : 32;
+      if (lane < n) out[p + lane] = 0;
+      p += n; i += n;
+      if (m) break;
+    }
+    if (lane == 0) S.buckets[c] = p;
+    __syncwarp();
+  }
+  if (lane == 0) { res[0] = 1; res[1] = hdr + count; }
+}
+
+__global__ void __launch_bounds__(32) srt_inverse_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P) {
+  __shared__ SrtSmem S;
+  const int lane = threadIdx.x, b = blockIdx.x;
+  KzgBlock& B = blocks[b];
+  int* res = P.result + 2 * b;
+  if (lane == 0) { res[0] = 0; res[1] = 0; }
+  if (B.status != 0 || !P.enabled[b]) return;
+  const int length = B.curLen;
+  const u8* __restrict__ src = B.cur;
+  u8* __restrict__ dst = B.alt;
+  if (lane == 0) {                          // decodeHeader (:335-353)
+    int k = 0; bool bad = false;
+    for (int i = 0; i < 256; i++) {
+      if (k >= length) { bad = true; break; }
+      int val = src[k++];
+      int r = val & 0x7F, shift = 7;
+      while (val >= 128) {
+        if (k >= length) { bad = true; break; }
+        val = src[k++];
+        r |= ((val & 0x7F) << shift);
+        if (shift > 21) break;
+        shift += 7;
+      }
+      S.freqs[i] = r;
+    }
+    S.hdrLen = bad ? -1 : k;
+  }
+  __syncwarp();
+  const int hdr = S.hdrLen;
+  if (hdr < 0) return;
+  const int count = length - hdr;
+  if (count > min(P.dstLimit[b], B.cap) || count < 0) return;
+  const u8* __restrict__ in = src + hdr;
+  for (int i = lane; i < 256; i += 32) { S.r2s[i] = 0; S.buckets[i] = 0; S.bucketEnds[i] = 0; if (S.freqs[i] < 0) S.freqs[i] = 0; }
+  __syncwarp();
+  srt_preprocess(S, lane);
+  int bad = 0;
+  if (lane == 0) {
+    int bucketPos = 0;
+    for (int i = 0; i < S.nbSymbols; i++) {
+      const int c = S.symbols[i];
+      if ((hdr + bucketPos < 0) || (hdr + bucketPos >= length)) { bad = 1; break; }   // :206-207
+      S.r2s[in[bucketPos]] = (u8)c;
+      S.buckets[c] = bucketPos + 1;
+      bucketPos += S.freqs[c];
+      S.bucketEnds[c] = bucketPos;
+    }
+  }
+  bad = __shfl_sync(0xFFFFFFFFu, bad, 0);
+  __syncwarp();
+  if (bad) return;
+  int nbSymbols = S.nbSymbols;
+  int c = S.r2s[0];
+  for (int base = 0; base < count; base += 32) {
+    const int nOut = min(32, count - base);
+    int outv = 0;
+    for (int t = 0; t < nOut; t++) {
+      if (lane == t) outv = c;
+      const int bk = S.buckets[c], be = S.bucketEnds[c];
+      if (bk < be) {
+        if (bk >= count) { bad = 1; break; }
+        const int r = in[bk];
+        __syncwarp();
+        if (lane == 0) S.buckets[c] = bk + 1;
+        if (r != 0) {
+          // for (s < r) r2s[s] = r2s[s+1]; r2s[r] = c   (entries (0, r] move down one slot)
+          for (int lo = 0; lo < r; lo += 32) {
+            const int k = lo + lane;
+            u8 v = 0;
+            if (k < r) v = S.r2s[k + 1];
+            __syncwarp();
+            if (k < r) S.r2s[k] = v;
+            __syncwarp();
+          }
+          if (lane == 0) S.r2s[r] = (u8)c;
+          __syncwarp();
+          c = S.r2s[0];
+        }
+        __syncwarp();
+      } else {
+        if (nbSymbols == 1) continue;
+        nbSymbols--;
+        for (int lo = 0; lo < nbSymbols; lo += 32) {
+          const int k = lo + lane;
+          u8 v = 0;
+          if (k < nbSymbols) v = S.r2s[k + 1];
+          __syncwarp();
+          if (k < nbSymbols) S.r2s[k] = v;
+          __syncwarp();
+        }
+        c = S.r2s[0];
+      }
+    }
+    if (bad) break;
+    if (lane < nOut) dst[base + lane] = (u8)outv;
+  }
+  if (lane == 0 && !bad) { res[0] = 1; res[1] = count; }
+}
+
+// ---- launchers -------------------------------------------------------------------------------------------------------
+void kzg_small_scratch(int, i32, bool, size_t*, size_t*) {}
+
+int kzg_zrlt_launch(cudaStream_t s, bool forward, KzgBlock* d_blocks, int nBlocks, const KzgXfParams& P) {
+  if (forward) zrlt_forward_kernel<<<nBlocks, 32, 0, s>>>(d_blocks, P);
+  else zrlt_inverse_kernel<<<nBlocks, 32, 0, s>>>(d_blocks, P);
+  CUDA_TRY(cudaGetLastError());
+  kzg_count_launch(1);
+  return 0;
+}
+int kzg_sbrt_launch(cudaStream_t s, bool forward, int mode, KzgBlock* d_blocks, int nBlocks, const KzgXfParams& P) {
+  if (forward) sbrt_kernel<true><<<nBlocks, 32, 0, s>>>(d_blocks, P, mode);
+  else sbrt_kernel<false><<<nBlocks, 32, 0, s>>>(d_blocks, P, mode);
+  CUDA_TRY(cudaGetLastError());
+  kzg_count_launch(1);
+  return 0;
+}
+int kzg_srt_launch(cudaStream_t s, bool forward, KzgBlock* d_blocks, int nBlocks, const KzgXfParams& P) {
+  if (forward) srt_forward_kernel<<<nBlocks, 32, 0, s>>>(d_blocks, P);
+  else srt_inverse_kernel<<<nBlocks, 32, 0, s>>>(d_blocks, P);
+  CUDA_TRY(cudaGetLastError());
+  kzg_count_launch(1);
+  return 0;
+}

@@ -125,7 +125,12 @@ int kzg_stage_precheck(int type, bool forward, const kzg_ctx* ctx, i32 srcLen, i
     case KZG_T_BWT:
       if (forward) {                                                                     // BWTBlockCodec.java:82-96
         if (dstLen > dstCap || dstLen < srcLen + 33) return 0;
-        if (asref) return 0;     // BWT.java:152-156 as written: dst.index(header) + dst.length > dst.array.length is always true here
+        if (asref) {             // BWT.java:152-156 as written: dst.index (= header size) + dst.length > dst.array.length
+          int lg = 0; while ((2 << lg) <= srcLen) lg++;
+          if ((srcLen & (srcLen - 1)) != 0) lg++;
+          const int hdr = 1 + ((srcLen < 256) ? 1 : 8) * ((lg + 7) >> 3);
+          if (hdr + dstLen > dstCap) return 0;
+        }
       } else {
         if (asref) return 0;     // BWT.java:211 as written: count > src.length - src.index once the header is consumed
       }
