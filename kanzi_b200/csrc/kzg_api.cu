@@ -465,7 +465,7 @@ int64_t kzg_compress_dev(const uint8_t* d_in, int64_t n, const int32_t* transfor
   const size_t nb = (size_t)std::max(nBlocks, 1);
   size_t need = nb * (sizeof(KzgBlock) + 64) + (anyXf ? nb * cap * (nf >= 2 ? 2 : 1) : 0) + nb * xs.perBlock + (nb * (xs.hashInts + xs.aux32)) * 4 +
                 nb * (size_t)es.maxChunks * (es.hdrStride + es.payStride + es.tabStride * 4) + nb * (size_t)es.segsPerBlock * sizeof(KzgSeg) + (1 << 20);
-  r = ws_reserve(need, nb * (sizeof(KzgBlock) + 16) + 4096); if (r < 0) return r;
+  r = ws_reserve(need, nb * (sizeof(KzgBlock) + 32) + 8192); if (r < 0) return r;
   u8 hdr[64];
   const int hdrLen = stream_header(hdr, entropy, transformType, blockSize, n);
   if (outCap < hdrLen + 2) return -KZG_ERR_WRITE_FILE;
@@ -478,6 +478,7 @@ int64_t kzg_compress_dev(const uint8_t* d_in, int64_t n, const int32_t* transfor
     Batch bt; bt.nBlocks = nBlocks; bt.maxLen = required;
     bt.hBlocks = halloc<KzgBlock>(nb); NN(bt.hBlocks);
     bt.hEnabled = halloc<u8>(nb); NN(bt.hEnabled);
+    bt.hDstLimit = halloc<int>(nb); NN(bt.hDstLimit);
     bt.dBlocks = dalloc<KzgBlock>(nb); NN(bt.dBlocks);
     bt.dResult = dalloc<int>(2 * nb); NN(bt.dResult);
     bt.dEnabled = dalloc<u8>(nb); NN(bt.dEnabled);
@@ -502,11 +503,14 @@ int64_t kzg_compress_dev(const uint8_t* d_in, int64_t n, const int32_t* transfor
       B.alt = dA ? dA + (size_t)b * cap : nullptr; B.aux1 = dB ? dB + (size_t)b * cap : B.alt;
       B.curLen = len; B.cap = (i32)cap - 64; B.origLen = len; B.skipFlags = 0xFF; B.entropy = entropy;
       const bool small = len <= 15;                             // COS:764-767: raw copy block
-      if (small) { B.mode = 0x80; B.entropy = KZG_E_NONE; }
+      if (small) { B.mode = 0x80; B.entropy = KZG_E_NONE; B.skipFlags = 0x7F; }   // NONE&NONE copy block: its NullTransform "succeeds" (COS:764-767, 792-817)
       bt.hEnabled[b] = small ? 0 : 1;
+      // dst slice length of the transform stage: EncodingTask grows `buffer` to the Sequence's requiredSize and never shrinks it
+      // (COS:806-811), so with the blocks of one stream handled in order every block after the first sees the full-block size
+      bt.hDstLimit[b] = (b == 0) ? seq_max_len(fn, nf, len) : required;
     }
     CUDA_TRY(cudaMemcpyAsync(bt.dEnabled, bt.hEnabled, nb, cudaMemcpyHostToDevice, W.stream));
-    CUDA_TRY(cudaMemsetAsync(bt.dDstLimit, 0x7F, nb * sizeof(int), W.stream));
+    CUDA_TRY(cudaMemcpyAsync(bt.dDstLimit, bt.hDstLimit, nb * sizeof(int), cudaMemcpyHostToDevice, W.stream));
     CUDA_TRY(cudaMemsetAsync(dSegs, 0, sizeof(KzgSeg) * nb * es.segsPerBlock, W.stream));
     r = batch_upload(bt); if (r < 0) return r;
     if (timing3) CUDA_TRY(cudaEventRecord(ev[0], W.stream));

@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(32) rolz_parse_kernel(KzgBlock* __restrict__ b
   if (B.status != 0 || !P.enabled[b]) return;
   const int count = B.curLen;
   if (count < 64 || count > (1 << 30)) return;                 // MIN_BLOCK_SIZE / MAX_BLOCK_SIZE (:207-212)
-  if (((count <= 512) ? count + 64 : count) > B.cap) return;    // output.length - output.index < getMaxEncodedLength(count)
+  if (((count <= 512) ? count + 64 : count) > min(B.cap, P.dstLimit[b])) return;    // output.length - output.index < getMaxEncodedLength(count)
   if (count - 4 > RZ_CHUNK) { if (lane == 0) atomicExch(&B.status, -KZG_ERR_BLOCK_SIZE); return; }
   const u8* __restrict__ src = B.cur;
   u8* __restrict__ dst = B.alt;
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(256) rolz_layout_kernel(KzgBlock* __restrict__
   const int count = B.curLen;
   const i64 bytes = (tb == ~0ull) ? -1 : (i64)((tb + 7) >> 3);
   // dstIdx + buf.length > dst.length (:629-633) / dstIdx + 4 > dst.length (:642-646) -> false
-  const bool fits = (bytes >= 0) && (bytes + 4 <= (i64)B.cap) && (bytes + 4 <= (i64)((count <= 512) ? count + 64 : count));
+  const bool fits = (bytes >= 0) && (bytes + 4 <= (i64)min(B.cap, P.dstLimit[b]));      // dst slice length as the Java call sees it
   if (!fits) {
     for (int i = threadIdx.x; i < 4 * segsPerVb; i += blockDim.x) S[i].nBits = 0;
     if (threadIdx.x == 0) { res[0] = 0; res[1] = 0; if (tb == ~0ull) atomicExch(&B.status, -KZG_ERR_PROCESS_BLOCK); }
@@ -343,18 +343,28 @@ __global__ void rolz_scan_kernel(KzgBlock* __restrict__ blocks, int nBlocks, Kzg
   u8* bufs[4] = {sc + R.L.lit, sc + R.L.tk, sc + R.L.len, sc + R.L.midx};
   const int lens[4] = {litLen, tkLen, mLenLen, mIdxLen};
   const int litOrder = flags & 1;
-  BitReaderD br(nullptr, 8ull * (u64)(uintptr_t)src + 8ull * 21, 8ull * (u64)(uintptr_t)src + 8ull * (u64)count);
+  // positions are scanned relative to `src`; the decode kernels address the stream from address 0 (P.stream == nullptr),
+  // so the block's base address (in bits) is added afterwards
+  const u64 absBase = 8ull * (u64)(uintptr_t)src;
+  BitReaderD br(src, 8ull * 21, 8ull * (u64)count);
   for (int k = 0; k < 4; k++) {
     KzgBlock& V = vb[k];
-    V.cur = bufs[k]; V.curLen = lens[k]; V.preLen = lens[k]; V.status = 0;
-    V.entropy = (k == 0) ? (litOrder ? RZ_E_LIT1 : RZ_E_LIT0) : RZ_E_M;
-    V.srcBit = (i64)br.pos; V.srcBits = (i64)(br.end - br.pos);
+    const u64 pos0 = br.pos;
     const int chunkSize = (k == 0) ? (litOrder ? (4 << 20) : 16384) : 32768;
-    const int r = ans_scan_stream(br, lens[k], chunkSize, (k == 0) ? litOrder : 0, R.chunks + (i64)(4 * b + k) * R.maxChunks);
+    KzgChunkInfo* ci = R.chunks + (i64)(4 * b + k) * R.maxChunks;
+    const int r = ans_scan_stream(br, lens[k], chunkSize, (k == 0) ? litOrder : 0, ci);
     if (r < 0) { B.status = r; return; }
-    V.entBits = (i64)br.pos - V.srcBit;
+    if (lens[k] > 32) {
+      const int nChunks = (lens[k] + chunkSize - 1) / chunkSize;
+      for (int c = 0; c < nChunks; c++) { ci[c].hdrBit += (i64)absBase; ci[c].payBit += (i64)absBase; }
+    }
+    V.cur = bufs[k]; V.curLen = lens[k]; V.preLen = lens[k];
+    V.entropy = (k == 0) ? (litOrder ? RZ_E_LIT1 : RZ_E_LIT0) : RZ_E_M;
+    V.srcBit = (i64)(absBase + pos0); V.srcBits = (i64)(br.end - pos0);
+    V.entBits = (i64)(br.pos - pos0);
   }
-  const u64 used = br.pos - 8ull * (u64)(uintptr_t)src;
+  for (int k = 0; k < 4; k++) vb[k].status = 0;      // published only once every stream scanned cleanly
+  const u64 used = br.pos;
   I.endByte = (i32)((used + 7) >> 3);
   I.szBlock = szBlock; I.flags = flags; I.litLen = litLen; I.tkLen = tkLen; I.mLenLen = mLenLen; I.mIdxLen = mIdxLen;
   I.ok = 1;

@@ -11,6 +11,23 @@ from kanzi_b200 import synth
 CASES = corpus.small_cases()
 only = set(sys.argv[1:])
 fails = 0
+FAMILIES = ["NONE", "HUFFMAN", "ANS0", "ANS1", "FPAQ", "LZ", "LZX", "ROLZ", "ZRLT", "RANK", "MTFT", "SRT", "BWT", "STREAM"]
+if not only:
+    import subprocess
+    tot = 0
+    for fam in FAMILIES:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), fam], capture_output=True, text=True)
+        out = r.stdout
+        sys.stdout.write("".join(l + "\n" for l in out.splitlines() if not l.startswith("FAILURES:")))
+        if r.returncode != 0 and "FAILURES:" not in out:
+            print(f"FAIL family {fam} crashed rc={r.returncode}: {r.stderr[-500:]}")
+            tot += 1
+        for l in out.splitlines():
+            if l.startswith("FAILURES:"):
+                tot += int(l.split()[1])
+        sys.stdout.flush()
+    print("FAILURES:", tot)
+    sys.exit(0)
 
 def fd(a, b):
     n = min(len(a), len(b))
