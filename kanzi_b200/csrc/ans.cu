@@ -481,11 +481,11 @@ __global__ void __launch_bounds__(32) ans1_encode_kernel(const KzgBlock* __restr
     }
     return;
   }
-  const int start = c * chunkSize;
-  if (start >= len) {
+  if ((i64)c * chunkSize >= (i64)len) {          // (64-bit: the grid may be far wider than this block's chunk count)
     if (lane == 0) { segs[0] = KzgSeg{nullptr, 0, 0, 0}; segs[1] = KzgSeg{nullptr, 0, 0, 0}; }
     return;
   }
+  const int start = c * chunkSize;
   const int end = min(start + chunkSize, len);
   u8* hdr = P.hdrBuf + gidx * (i64)P.hdrStride;
   u8* pay = P.payBuf + gidx * (i64)P.payStride;
@@ -623,8 +623,8 @@ __global__ void __launch_bounds__(32) ans1_decode_kernel(KzgBlock* __restrict__ 
     return;
   }
   const int chunkSize = P.chunkSize;
+  if ((i64)c * chunkSize >= (i64)len) return;
   const int start = c * chunkSize;
-  if (start >= len) return;
   const int end = min(start + chunkSize, len);
   const i64 gidx = (i64)b * P.maxChunks + c;
   const KzgChunkInfo info = P.chunks[gidx];

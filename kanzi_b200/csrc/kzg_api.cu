@@ -13,6 +13,7 @@
 #include "kzg_container.cuh"
 #include "kzg_stages.cuh"
 #include <stdarg.h>
+#include <stdlib.h>
 #include <vector>
 #include <algorithm>
 
@@ -152,6 +153,9 @@ static XfScratch xf_scratch_size(const int* fn, int nf, i32 maxLen, bool forward
         s.perBlock = std::max(s.perBlock, (size_t)s.tk + s.m + s.ml);
         const bool smemTable = (fn[i] == KZG_T_LZ) && (maxLen <= (1 << 24));
         if (!smemTable) s.hashInts = std::max(s.hashInts, (size_t)((fn[i] == KZG_T_LZX) ? (1 << 19) : (1 << 16)));
+        kzg_lzf_scratch(maxLen, &s.perBlock);
+      } else {
+        kzg_lzi_scratch(maxLen, &s.perBlock, &s.aux32);
       }
     }
     kzg_stage_scratch(fn[i], maxLen, forward, &s.perBlock, &s.hashInts, &s.aux32);
@@ -168,8 +172,12 @@ static int run_transform_stage(Batch& bt, int type, int stage, bool forward, con
   int r = 0;
   switch (type) {
     case KZG_T_LZ: case KZG_T_LZX:
-      if (forward) r = kzg_lz_forward_launch(W.stream, bt.dBlocks, bt.nBlocks, P, type == KZG_T_LZX, (type == KZG_T_LZ) && (bt.maxLen <= (1 << 24)));
-      else r = kzg_lz_inverse_launch(W.stream, bt.dBlocks, bt.nBlocks, P);
+      if (forward) {
+        static const bool v1 = getenv("KZG_LZ_V1") != nullptr;      // developer switch: the first-generation single-kernel walker
+        if (v1) r = kzg_lz_forward_launch(W.stream, bt.dBlocks, bt.nBlocks, P, type == KZG_T_LZX, (type == KZG_T_LZ) && (bt.maxLen <= (1 << 24)));
+        else r = kzg_lz_forward2_launch(W.stream, bt.dBlocks, bt.nBlocks, P, type == KZG_T_LZX, bt.maxLen);
+      }
+      else r = kzg_lz_inverse_launch(W.stream, bt.dBlocks, bt.nBlocks, P, bt.maxLen);
       break;
     default:
       r = kzg_stage_launch(W.stream, type, forward, bt.dBlocks, bt.nBlocks, P, bt.maxLen);

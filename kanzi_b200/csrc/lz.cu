@@ -10,8 +10,7 @@
 // -t LZ: 2^16-entry table of 24-bit positions in shared memory (192 KiB: one block per SM);
 // -t LZX or blocks > 16 MiB: 32-bit table in global memory (L2-resident).
 //
-// Inverse: one warp per block; the token stream is parsed redundantly, copies are lane-parallel
-// (dst[i] = dst[ref + i % dist] reproduces the reference's forward byte copy, LZCodec.java:737-748).
+// The inverse lives in lz_inverse.cu (token parse + pointer jumping).
 #include "kzg_common.cuh"
 #include "kzg_transforms.cuh"
 
@@ -303,86 +302,6 @@ __global__ void __launch_bounds__(32) lz_forward_kernel(KzgBlock* __restrict__ b
   }
 }
 
-// ================================================================================================================
-// inverse: LZXCodec.inverseV6 (LZCodec.java:626-756).  One warp per block; B.cur -> B.alt (capacity B.cap).
-// ================================================================================================================
-__device__ __forceinline__ int lz_read_length(const u8* __restrict__ a, int& index) {   // LZCodec.java:241-258
-  int res = a[index++];
-  if (res < 254) return res;
-  if (res == 254) { res += (a[index] << 8); res += a[index + 1]; index += 2; return res; }
-  res += (a[index] << 16); res += (a[index + 1] << 8); res += a[index + 2];
-  index += 3;
-  return res;
-}
-
-__global__ void __launch_bounds__(32) lz_inverse_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P) {
-  const int lane = threadIdx.x;
-  const int b = blockIdx.x;
-  KzgBlock& B = blocks[b];
-  int* res = P.result + 2 * b;
-  if (lane == 0) { res[0] = 0; res[1] = 0; }
-  if (B.status != 0 || !P.enabled[b]) return;
-  const int count = B.curLen;
-  const u8* __restrict__ src = B.cur;
-  u8* __restrict__ dst = B.alt;
-  const int dstEnd = P.dstLimit[b];        // output.array.length as the Java call sees it
-  if (count < 13) return;
-  const i32 tkLen = (i32)ld32u(src), mIdxLen = (i32)ld32u(src + 4), mLenLen = (i32)ld32u(src + 8);
-  if ((tkLen < 0) || (mIdxLen < 0) || (mLenLen < 0)) return;
-  if ((tkLen < 13) || (tkLen > count) || (mIdxLen > count - tkLen) || (mLenLen > count - tkLen - mIdxLen)) return;
-  int tkIdx = tkLen;
-  int mIdx = tkIdx + mIdxLen;
-  int mLenIdx = mIdx + mLenLen;
-  const int srcEnd = tkIdx - 13;
-  const int litEnd = tkIdx;
-  const int maxDist = ((src[12] & 1) == 0) ? LZ_MAX_DISTANCE1 : LZ_MAX_DISTANCE2;
-  const int minMatch = ((src[12] >> 1) & 0x07) + 2;
-  int srcIdx = 13, dstIdx = 0;
-  int repd0 = count, repd1 = count;
-  // reads past the block (only possible on corrupt input) stay inside the padded buffer: every index is checked
-  bool fail = false;
-  while (true) {
-    if (tkIdx >= count) { fail = true; break; }
-    const int token = src[tkIdx++];
-    if (token >= 32) {
-      int litLen;
-      if (token >= 0xE0) { if (srcIdx + 4 > count) { fail = true; break; } litLen = 7 + lz_read_length(src, srcIdx); }
-      else litLen = token >> 5;
-      if ((litLen > dstEnd - dstIdx) || (litLen > litEnd - srcIdx)) { fail = true; break; }
-      warp_copy(dst + dstIdx, src + srcIdx, litLen, lane);
-      srcIdx += litLen;
-      dstIdx += litLen;
-      if (srcIdx >= srcEnd) break;
-    }
-    int mLen, dist;
-    const int f = token & 0x18;
-    if (f == 0) {
-      mLen = token & 0x03;
-      if (mLen == 3) { if (mLenIdx + 4 > count + 8) { fail = true; break; } mLen += minMatch + lz_read_length(src, mLenIdx); }
-      else mLen += minMatch;
-      dist = ((token & 0x04) == 0) ? repd0 : repd1;
-    } else {
-      mLen = token & 0x07;
-      if (mLen == 7) { if (mLenIdx + 4 > count + 8) { fail = true; break; } mLen += minMatch + lz_read_length(src, mLenIdx); }
-      else mLen += minMatch;
-      if (mIdx + 3 > count + 8) { fail = true; break; }
-      dist = src[mIdx++];
-      if (f == 0x18) { dist = (dist << 8) | src[mIdx++]; dist = (dist << 8) | src[mIdx++]; }
-      else if (f == 0x10) { dist = (dist << 8) | src[mIdx++]; }
-    }
-    repd1 = repd0; repd0 = dist;
-    const int mEnd = dstIdx + mLen;
-    const int ref = dstIdx - dist;
-    if ((ref < 0) || (dist > maxDist) || (mEnd > dstEnd) || (dist <= 0)) { fail = true; break; }
-    __syncwarp();      // literal bytes just written may be the source of this match
-    for (int i = lane; i < mLen; i += 32) dst[dstIdx + i] = dst[ref + (i % dist)];
-    __syncwarp();
-    dstIdx = mEnd;
-  }
-  if (fail) return;     // res[0] = 0: inverse returned false
-  if (lane == 0) { res[1] = dstIdx; res[0] = (srcIdx == srcEnd + 13) ? 1 : 0; }
-}
-
 int kzg_lz_forward_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, const KzgXfParams& P, bool extra, bool smemTable) {
   if (!extra && smemTable) {
     static bool attr = false;
@@ -399,9 +318,3 @@ int kzg_lz_forward_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, const
   return 0;
 }
 
-int kzg_lz_inverse_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, const KzgXfParams& P) {
-  lz_inverse_kernel<<<nBlocks, 32, 0, s>>>(d_blocks, P);
-  CUDA_TRY(cudaGetLastError());
-  kzg_count_launch(1);
-  return 0;
-}
