@@ -175,7 +175,11 @@ static int run_transform_stage(Batch& bt, int type, int stage, bool forward, con
       if (forward) {
         static const bool v1 = getenv("KZG_LZ_V1") != nullptr;      // developer switch: the first-generation single-kernel walker
         if (v1) r = kzg_lz_forward_launch(W.stream, bt.dBlocks, bt.nBlocks, P, type == KZG_T_LZX, (type == KZG_T_LZ) && (bt.maxLen <= (1 << 24)));
-        else r = kzg_lz_forward2_launch(W.stream, bt.dBlocks, bt.nBlocks, P, type == KZG_T_LZX, bt.maxLen);
+        else {
+          static const char* dbgEnv = getenv("KZG_DEBUG");          // developer aid: bit 0 stats printf, bits 1-2 disable walker shortcuts
+          if (dbgEnv) P.flags |= (atoi(dbgEnv) << 12);
+          r = kzg_lz_forward2_launch(W.stream, bt.dBlocks, bt.nBlocks, P, type == KZG_T_LZX, bt.maxLen);
+        }
       }
       else r = kzg_lz_inverse_launch(W.stream, bt.dBlocks, bt.nBlocks, P, bt.maxLen);
       break;

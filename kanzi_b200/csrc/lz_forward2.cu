@@ -240,9 +240,38 @@ __device__ __forceinline__ int lzf_emit_length(u8* block, int idx, int length, i
   return idx + 4;
 }
 
+#define LZF_LOOKAHEAD 1024
+struct LzfShared { volatile int pos; volatile int rep0; volatile int rep1; volatile int done; };
+
+__device__ __forceinline__ void lzf_prefetch(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// warp 1 of the CTA: runs ahead of the walker and pulls into L1 what the walker is about to touch — the sequential
+// streams (src, len0, prev), the two repeat-offset streams and the candidate lines src[prev[q]]
+__device__ void lzf_prefetch_warp(const LzfBlock& L, const u8* __restrict__ src, LzfShared& S, int lane) {
+  int pf = 0;
+  const int n = L.n;
+  while (!S.done) {
+    const int pos = S.pos;
+    const int target = min(pos + LZF_LOOKAHEAD, n);
+    if (pf < pos) pf = pos;
+    if (pf >= target) { __nanosleep(200); continue; }
+    const int r0 = S.rep0, r1 = S.rep1;
+    for (; pf < target; pf += 32) {
+      const int q = pf + lane;
+      if (q >= n) break;
+      const int l0 = L.len0[q];
+      if ((q & 31) == 0 && q + 128 < n) lzf_prefetch(src + q + 128);
+      if (l0 > 0) { const u32 pv = L.prev[q]; lzf_prefetch(src + pv); }
+      else if ((q & 31) == 0 && q + 64 < n) lzf_prefetch(L.prev + q + 64);
+      if (lane == 0) { if (q + 1 - r0 > 0) lzf_prefetch(src + q + 1 - r0 + 32); if (q + 1 - r1 > 0) lzf_prefetch(src + q + 1 - r1 + 32); }
+    }
+  }
+}
+
 template <bool EXTRA>
-__global__ void __launch_bounds__(32) lzf_walk_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P, LzfBlock* __restrict__ lb) {
-  const int lane = threadIdx.x, b = blockIdx.x;
+__global__ void __launch_bounds__(64) lzf_walk_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P, LzfBlock* __restrict__ lb) {
+  __shared__ LzfShared S;
+  const int lane = threadIdx.x & 31, b = blockIdx.x;
   const LzfBlock L = lb[b];
   if (L.n <= 0) return;
   KzgBlock& B = blocks[b];
@@ -250,6 +279,10 @@ __global__ void __launch_bounds__(32) lzf_walk_kernel(KzgBlock* __restrict__ blo
   const u8* __restrict__ src = B.cur;
   u8* __restrict__ dst = B.alt;
   const int count = L.count, srcEnd = L.srcEnd, maxDist = L.maxDist, minMatch = L.minMatch;
+  if (threadIdx.x == 0) { S.pos = 0; S.rep0 = count; S.rep1 = count; S.done = 0; }
+  __syncthreads();
+  if (threadIdx.x >= 32) { lzf_prefetch_warp(L, src, S, lane); return; }
+
   const u8 flagByte = (u8)(((maxDist == LZ_MAX_DISTANCE1) ? 0 : 1) | (((minMatch - 2) & 0x07) << 1));
   u8* tkBuf = L.tk; u8* mBuf = L.m; u8* mLenBuf = L.ml;
   int srcIdx = 0, anchor = 0, dstIdx = 13;
@@ -257,9 +290,13 @@ __global__ void __launch_bounds__(32) lzf_walk_kernel(KzgBlock* __restrict__ blo
   int repd0 = count, repd1 = count;
   int repIdx = 0, srcInc = 0;
   int lastSkip = -1;                         // highest position ever jumped over (may since have been re-inserted)
-  bool overflow = false;
+  bool overflow = false, giveUp = false;
+  const int dbg = P.flags >> 12;
+  long long t0 = clock64(); int nIter = 0, nEv = 0, nSlow = 0, nFmw = 0;
 
   while (srcIdx < srcEnd) {
+    nIter++;
+    if (lane == 0) { S.pos = srcIdx; S.rep0 = repd0; S.rep1 = repd1; }
     // ---- evaluate the next 32 visit positions, assuming the ones before each are misses ----
     const u32 stepExtra = (u32)((srcInc + lane) >> 6);
     u32 exIncl = stepExtra;
@@ -267,20 +304,29 @@ __global__ void __launch_bounds__(32) lzf_walk_kernel(KzgBlock* __restrict__ blo
     const int p = srcIdx + lane + (int)(exIncl - stepExtra);
     const bool valid = p < srcEnd;
     bool hit = false, slow = false;
+    int l0 = 0, pv = 0, repSmall = 0, repRef = 0;
     if (valid) {
       const int p1 = p + 1;
       const int minRef = max(p - maxDist, 0);
       const int maxM = min(srcEnd - p1, LZ_MAX_MATCH);
       const int rA = (lane == 0 && repIdx) ? repd1 : repd0, rB = (lane == 0 && repIdx) ? repd0 : repd1;
-      const u32 cur1 = lzf_ld32(src + p1);
-      int repLen = 0;
-      int ref = p1 - rA;
-      if (ref > minRef && lzf_ld32(src + ref) == cur1) repLen = lzf_find_match(src, p1, ref, maxM, 8);
-      else { ref = p1 - rB; if (ref > minRef && lzf_ld32(src + ref) == cur1) repLen = lzf_find_match(src, p1, ref, maxM, 8); }
-      if (repLen >= minMatch) hit = true;
+      const int refA = p1 - rA, refB = p1 - rB;
+      // independent loads first
+      const u64 n8 = lzf_ld64(src + p1);
+      const u64 a8 = (refA > minRef) ? lzf_ld64(src + refA) : ~n8;
+      const u64 b8 = (refB > minRef) ? lzf_ld64(src + refB) : ~n8;
+      l0 = L.len0[p];
+      pv = (int)L.prev[p];
+      // the reference tries repd[repIdx] first and only falls to the other one when the 4-byte pre-check fails (:374-387)
+      u64 diff; 
+      if ((u32)(a8 ^ n8) == 0) { diff = a8 ^ n8; repRef = refA; }
+      else if ((u32)(b8 ^ n8) == 0) { diff = b8 ^ n8; repRef = refB; }
+      else { diff = 1; repRef = 0; }
+      if (repRef > 0) repSmall = (maxM < 8) ? 0 : ((diff == 0) ? 8 : ((__ffsll((long long)diff) - 1) >> 3));
+      if (repSmall >= minMatch) hit = true;
       else {
-        const int l0 = L.len0[p];
-        if (lastSkip >= 0) { const int q = (int)L.prev[p]; if (q > 0 && q <= lastSkip) slow = true; }
+        if (lastSkip >= 0 && pv > 0 && pv <= lastSkip) slow = true;
+        if (((srcInc + 31) >> 6) > 0 && pv > srcIdx) slow = true;      // may be a position this very batch jumps over
         if (!slow && l0 >= minMatch) hit = true;
       }
     }
@@ -290,17 +336,17 @@ __global__ void __launch_bounds__(32) lzf_walk_kernel(KzgBlock* __restrict__ blo
     const int nMiss = stopMask ? min(__ffs(stopMask) - 1, nValid) : nValid;
     // ---- commit the misses: positions jumped over by the acceleration are recorded (they are never inserted) ----
     if (nMiss > 0) {
-      if (lane < nMiss && stepExtra > 0) {
-        for (u32 k = 1; k <= stepExtra; k++) { const int q = p + (int)k; if (q <= srcEnd) atomicOr(&L.skipped[q >> 5], 1u << (q & 31)); }
-      }
-      const int lastP = __shfl_sync(0xFFFFFFFFu, p, nMiss - 1);
       const int lastEx = __shfl_sync(0xFFFFFFFFu, (int)stepExtra, nMiss - 1);
-      if (lastEx > 0 || ((srcInc + nMiss - 1) >> 6) > 0) {
+      if (lastEx > 0) {
+        if (lane < nMiss && stepExtra > 0) {
+          for (u32 k = 1; k <= stepExtra; k++) { const int q = p + (int)k; if (q <= srcEnd) atomicOr(&L.skipped[q >> 5], 1u << (q & 31)); }
+        }
         int mx = (lane < nMiss && stepExtra > 0) ? p + (int)stepExtra : -1;
         for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
         lastSkip = max(lastSkip, min(mx, srcEnd));
         __threadfence_block();
       }
+      const int lastP = __shfl_sync(0xFFFFFFFFu, p, nMiss - 1);
       srcIdx = lastP + 1 + lastEx;
       srcInc += nMiss;
       repIdx = 0;
@@ -308,26 +354,38 @@ __global__ void __launch_bounds__(32) lzf_walk_kernel(KzgBlock* __restrict__ blo
     }
     if (!stopMask || nMiss >= nValid) continue;
     if (srcIdx >= srcEnd) break;
-    // ---- one iteration of the reference loop at srcIdx (:366-566), exact ----
+    // ---- one iteration of the reference loop at srcIdx (:366-566), exact; lane `f` already holds this position's loads ----
+    nEv++;
+    const int f = nMiss;
+    const int evL0 = __shfl_sync(0xFFFFFFFFu, l0, f);
+    const int evPv = __shfl_sync(0xFFFFFFFFu, pv, f);
+    const int evRepSmall = __shfl_sync(0xFFFFFFFFu, repSmall, f);
+    const int evRepRef = __shfl_sync(0xFFFFFFFFu, repRef, f);
+    const bool evSlow = (__shfl_sync(0xFFFFFFFFu, (int)slow, f) != 0);
+    // lane f+1 holds position srcIdx + 1 when lane f's step is 1
+    const int nextOk = (f + 1 < 32) && (((validMask >> (f + 1)) & 1u) != 0) && (__shfl_sync(0xFFFFFFFFu, (int)stepExtra, f) == 0);
+    const int nxL0 = __shfl_sync(0xFFFFFFFFu, l0, (f + 1) & 31);
+    const int nxPv = __shfl_sync(0xFFFFFFFFu, pv, (f + 1) & 31);
     int bestLen = 0;
-    const int ref0 = lzf_cand(L, srcIdx, lastSkip);
     const int srcIdx1 = srcIdx + 1;
-    int ref = srcIdx1 - (repIdx ? repd1 : repd0);
     const int minRef = max(srcIdx - maxDist, 0);
-    const u32 cur1 = lzf_ld32(src + srcIdx1);
-    if ((ref > minRef) && (lzf_ld32(src + ref) == cur1)) {
-      bestLen = lzf_find_match_warp(src, srcIdx1, ref, min(srcEnd - srcIdx1, LZ_MAX_MATCH), lane);
-    } else {
-      ref = srcIdx1 - (repIdx ? repd0 : repd1);
-      if ((ref > minRef) && (lzf_ld32(src + ref) == cur1))
-        bestLen = lzf_find_match_warp(src, srcIdx1, ref, min(srcEnd - srcIdx1, LZ_MAX_MATCH), lane);
-    }
+    int ref = evRepRef;
+    if (ref > 0) bestLen = (evRepSmall < 8) ? evRepSmall : lzf_find_match_warp(src, srcIdx1, ref, min(srcEnd - srcIdx1, LZ_MAX_MATCH), lane);
     if (bestLen < minMatch) {
+      // check match at position in hash table (:389-395): table content = first entry of the prev chain that was inserted
+      int ref0 = evPv;
+      bool firstHop = true;
+      if (evSlow) { nSlow++; const int q = lzf_cand(L, srcIdx, lastSkip); firstHop = (q == evPv); ref0 = q; }
       ref = ref0;
-      if ((ref > minRef) && (lzf_ld32(src + ref) == lzf_ld32(src + srcIdx))) {
-        const int l0 = (ref == (int)L.prev[srcIdx]) ? (int)L.len0[srcIdx] : 255;
-        bestLen = (l0 < 255) ? l0 : lzf_find_match_warp(src, srcIdx, ref, min(srcEnd - srcIdx, LZ_MAX_MATCH), lane);
-      }
+      int hl;
+      if (firstHop) {
+        // len0 already is ((ref > minRef) && 4-byte check) ? findMatch(srcIdx, ref) : 0, capped at 255
+        hl = (evL0 < 255) ? evL0 : lzf_find_match_warp(src, srcIdx, ref, min(srcEnd - srcIdx, LZ_MAX_MATCH), lane);
+      } else if ((ref > minRef) && (lzf_ld32(src + ref) == lzf_ld32(src + srcIdx))) {
+        hl = lzf_find_match_warp(src, srcIdx, ref, min(srcEnd - srcIdx, LZ_MAX_MATCH), lane);
+      } else hl = 0;
+      // (when the hash candidate fails its pre-check the reference keeps the too-short repeat result: a miss either way)
+      bestLen = (hl >= minMatch) ? hl : 0;
       if (bestLen < minMatch) {       // no good match
         const int ex = srcInc >> 6;
         if (ex > 0) {
@@ -343,10 +401,19 @@ __global__ void __launch_bounds__(32) lzf_walk_kernel(KzgBlock* __restrict__ blo
       }
       if ((ref != srcIdx - repd0) && (ref != srcIdx - repd1)) {
         // check if better match at next position (:405-422); the table lookup there happens before srcIdx1 is inserted
-        const int ref1 = lzf_cand(L, srcIdx1, lastSkip);
-        if ((ref1 > minRef + 1) && (lzf_ld32(src + ref1 + bestLen - 3) == lzf_ld32(src + srcIdx1 + bestLen - 3))) {
-          const int bestLen1 = lzf_find_match_warp(src, srcIdx1, ref1, min(srcEnd - srcIdx1, LZ_MAX_MATCH), lane);
-          if (bestLen1 >= bestLen) { ref = ref1; bestLen = bestLen1; srcIdx = srcIdx1; }
+        int ref1; bool hop1 = false; int l01 = 255;
+        if (!(dbg & 2) && nextOk && !(lastSkip >= 0 && nxPv > 0 && nxPv <= lastSkip)) { ref1 = nxPv; hop1 = true; l01 = nxL0; }
+        else ref1 = lzf_cand(L, srcIdx1, lastSkip);
+        if (ref1 > minRef + 1) {
+          bool sw = false; int bestLen1 = 0;
+          if (hop1 && l01 < 255 && l01 != bestLen) {
+            // len0 is findMatch(srcIdx1, ref1) (or 0 when its 4-byte pre-check fails, which also means < 4 <= bestLen)
+            if (l01 > bestLen) { sw = true; bestLen1 = l01; }
+          } else if (lzf_ld32(src + ref1 + bestLen - 3) == lzf_ld32(src + srcIdx1 + bestLen - 3)) {
+            bestLen1 = lzf_find_match_warp(src, srcIdx1, ref1, min(srcEnd - srcIdx1, LZ_MAX_MATCH), lane);
+            sw = (bestLen1 >= bestLen);
+          }
+          if (sw) { ref = ref1; bestLen = bestLen1; srcIdx = srcIdx1; }
         }
         if (EXTRA) {
           const int srcIdx2 = srcIdx1 + 1;
@@ -357,9 +424,24 @@ __global__ void __launch_bounds__(32) lzf_walk_kernel(KzgBlock* __restrict__ blo
           }
         }
       }
-      // extend backwards (:446-450)
+      // extend backwards (:446-450), 8 bytes per step
       const int visited = srcIdx;
-      while ((srcIdx > anchor) && (ref > minRef) && (src[srcIdx - 1] == src[ref - 1])) { bestLen++; ref--; srcIdx--; }
+      while (true) {
+        const int room = min(srcIdx - anchor, ref - minRef);
+        if (room <= 0) break;
+        const bool wide = !(dbg & 4) && (srcIdx >= 8) && (ref >= 8);
+        int e;
+        if (wide) {
+          const u64 d = lzf_ld64(src + srcIdx - 8) ^ lzf_ld64(src + ref - 8);
+          e = (d == 0) ? 8 : (__clzll((long long)d) >> 3);      // equal bytes counted from the end (highest byte = position - 1)
+        } else {
+          e = (src[srcIdx - 1] == src[ref - 1]) ? 1 : 0;
+        }
+        const int lim = wide ? 8 : 1;
+        const int take = min(e, room);
+        bestLen += take; ref -= take; srcIdx -= take;
+        if (take < lim) break;
+      }
       if (bestLen > LZ_MAX_MATCH) { ref += (bestLen - LZ_MAX_MATCH); srcIdx += (bestLen - LZ_MAX_MATCH); bestLen = LZ_MAX_MATCH; }
       // the match interior is inserted again (:553-565): positions jumped over earlier inside it become table entries
       if (lastSkip > srcIdx && srcIdx < visited) {
@@ -405,7 +487,7 @@ __global__ void __launch_bounds__(32) lzf_walk_kernel(KzgBlock* __restrict__ blo
       tkIdx++;
     } else {
       if (litLen >= 7) {
-        if (litLen >= (1 << 24)) return;                      // forward returns false (:523-524)
+        if (litLen >= (1 << 24)) { giveUp = true; break; }     // forward returns false (:523-524)
         if (lane == 0) tkBuf[tkIdx] = (u8)((7 << 5) | token);
         tkIdx++;
         dstIdx = lzf_emit_length(dst, dstIdx, litLen - 7, lane);
@@ -420,6 +502,9 @@ __global__ void __launch_bounds__(32) lzf_walk_kernel(KzgBlock* __restrict__ blo
     anchor = srcIdx + bestLen;
     srcIdx = anchor;
   }
+  if (lane == 0) S.done = 1;
+  if ((dbg & 1) && lane == 0) printf("lzf block %d count %d: iters %d events %d slow %d tokens %d cycles %lld\n", b, count, nIter, nEv, nSlow, tkIdx, clock64() - t0);
+  if (giveUp) return;
   if (overflow) { if (lane == 0) atomicExch(&B.status, -KZG_ERR_PROCESS_BLOCK); return; }
 
   // emit last literals (:568-596)
@@ -506,8 +591,8 @@ int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
   }
   lzf_prev_kernel<<<dim3(gx, nBlocks), 256, 0, s>>>(dlb, pass == 1 ? 1 : 0);
   lzf_cand_kernel<<<dim3(gx, nBlocks), 256, 0, s>>>(d_blocks, dlb);
-  if (extra) lzf_walk_kernel<true><<<nBlocks, 32, 0, s>>>(d_blocks, P, dlb);
-  else lzf_walk_kernel<false><<<nBlocks, 32, 0, s>>>(d_blocks, P, dlb);
+  if (extra) lzf_walk_kernel<true><<<nBlocks, 64, 0, s>>>(d_blocks, P, dlb);
+  else lzf_walk_kernel<false><<<nBlocks, 64, 0, s>>>(d_blocks, P, dlb);
   CUDA_TRY(cudaGetLastError());
   kzg_count_launch(5 + 3 * pass);
   return 0;
