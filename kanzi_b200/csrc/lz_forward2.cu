@@ -38,7 +38,19 @@ struct LzfBlock {                 // per-block scratch pointers (device)
   u8* tk; u8* m; u8* ml;          // token / distance / match-length side buffers
   i32 n;                          // positions that take part (srcEnd + 1), 0 = block does not run
   i32 count, srcEnd, maxDist, minMatch, tkCap, mCap, mlCap;
+  // segment-parallel parse (phase 2/3/4)
+  u32* A;                         // skipped-position bitmap every segment assumes for positions before its own start
+  u32* Kn;                        // skipped-position bitmap of the stitched parse (next round's assumption)
+  u32* D;                         // skipped positions each speculative segment found inside its own range
+  uint4* specEv;                  // per-segment match logs {start, length, distance, -}
+  uint4* patchEv;                 // matches the stitcher had to find itself
+  struct LzfSeg* seg;             // per-segment end state
+  struct LzfRange* rng;           // final match list as ranges of the two logs
+  i32 segLen, nSeg, evStride, patchCap, nRng, aMax, active, needSerial;
 };
+struct LzfState { i32 srcIdx, anchor, srcInc, repd0, repd1, repIdx, lastSkip, overLo, overHi; };
+struct LzfSeg { LzfState entry; LzfState end; LzfState trueEntry; i32 nEv; i32 fail; i32 haveTrue; i32 pad; };
+struct LzfRange { const uint4* ev; i32 count; i32 pad; };
 
 __device__ __forceinline__ u64 lzf_ld64(const u8* __restrict__ p) {
   const uintptr_t a = (uintptr_t)p;
@@ -87,7 +99,7 @@ __device__ __forceinline__ int lzf_find_match_warp(const u8* __restrict__ src, i
 }
 
 // ---- phase 1a: per-block setup + hashes ----------------------------------------------------------------------------------------
-__global__ void lzf_setup_kernel(const KzgBlock* __restrict__ blocks, int nBlocks, KzgXfParams P, LzfBlock* __restrict__ lb) {
+__global__ void lzf_setup_kernel(const KzgBlock* __restrict__ blocks, int nBlocks, KzgXfParams P, LzfBlock* __restrict__ lb, int segLen, int forceSerial) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nBlocks) return;
   const KzgBlock& B = blocks[b];
@@ -105,6 +117,8 @@ __global__ void lzf_setup_kernel(const KzgBlock* __restrict__ blocks, int nBlock
   L.minMatch = mm;
   L.tkCap = max(count / 5, 256);                                         // tkBuf is never grown (:324-333)
   L.n = L.srcEnd + 2;                                                    // positions 0..srcEnd+1 can be visited or looked up (lazy steps)
+  L.segLen = segLen; L.nSeg = max(1, (L.srcEnd + segLen - 1) / segLen);
+  L.nRng = 0; L.aMax = -1; L.active = forceSerial ? 0 : 1; L.needSerial = forceSerial;
 }
 
 template <bool EXTRA>
@@ -116,7 +130,7 @@ __global__ void lzf_hash_kernel(const KzgBlock* __restrict__ blocks, LzfBlock* _
     const u64 v = (lzf_ld64(src + p) << 24) * LZ_HASH_SEED;             // LZCodec.java:904-911
     L.hash[p] = (u32)(v >> (EXTRA ? (64 - 19) : (64 - 16)));
   }
-  if (blockIdx.x == 0) for (int i = threadIdx.x; i < (n + 31) / 32 + 1; i += blockDim.x) L.skipped[i] = 0;
+  if (blockIdx.x == 0) for (int i = threadIdx.x; i < (n + 31) / 32 + 2; i += blockDim.x) { L.skipped[i] = 0; L.A[i] = 0; }
 }
 
 // ---- phase 1b: stable LSD radix sort of positions by hash (8-bit digits) -----------------------------------------------------------
@@ -273,7 +287,7 @@ __global__ void __launch_bounds__(64) lzf_walk_kernel(KzgBlock* __restrict__ blo
   __shared__ LzfShared S;
   const int lane = threadIdx.x & 31, b = blockIdx.x;
   const LzfBlock L = lb[b];
-  if (L.n <= 0) return;
+  if (L.n <= 0 || !L.needSerial) return;
   KzgBlock& B = blocks[b];
   int* res = P.result + 2 * b;
   const u8* __restrict__ src = B.cur;
@@ -538,9 +552,603 @@ __global__ void __launch_bounds__(64) lzf_walk_kernel(KzgBlock* __restrict__ blo
   if (lane == 0) { res[1] = dstIdx; res[0] = (dstIdx <= count - (count / 100)) ? 1 : 0; }
 }
 
+// ====================================================================================================================================
+// Segment-parallel parse.  The walk above is one warp per block: ~10 cycles per dependent instruction and a few hundred
+// instructions per match make it latency-bound at a few MB/s per block.  The parse state of the reference is tiny
+// (srcIdx, anchor, srcInc, repd[2], repIdx) and greedy LZ parses re-synchronise quickly, so:
+//   spec    one warp per 32 KiB segment parses from a fresh state at the segment start and logs its matches.  Table
+//           content for positions before the segment comes from the assumed bitmap A, inside the segment from the
+//           segment's own bitmap D.
+//   stitch  one warp per block walks the segments in order.  Segment 0 is exact.  For the next ones it parses from the
+//           true state until it emits a match the segment's log also holds, with the same previous distance and the same
+//           skipped positions in between; from there the reference and the speculative parse are in the same state, so
+//           the rest of the log is adopted.  The stitcher keeps the exact skipped bitmap Kn of what it produced.
+//   check   if Kn == A the assumption every segment made was the truth and the stitched parse is the reference's parse
+//           (induction over positions: the first differing decision would need a table lookup that resolves differently,
+//           i.e. a consulted position whose bit differs).  Otherwise A := Kn and the block runs another round; the
+//           correct prefix grows every round.  Blocks that do not settle fall back to the serial walk above.
+//   emit    tokens, distances, lengths and literals are a pure function of the match list: one CTA per block writes them
+//           with prefix sums.
+#define LZF_WARMUP 2048
+struct LzfNoSync { __device__ __forceinline__ bool operator()(int, int, int, const LzfState&) const { return false; } };
+
+template <bool EXTRA, class OnMatch>
+__device__ __forceinline__ void lzf_core(const LzfBlock& L, const u8* __restrict__ src, LzfState& st, const int stopAt,
+                                         const u32* __restrict__ A, const int aHi, const int ownStart,
+                                         u32* D, const int dWriteBegin, const int dWriteEnd, uint4* __restrict__ ev, int& nEv, const int evCap,
+                                         int& fail, const int lane, OnMatch& onMatch) {
+  const int srcEnd = L.srcEnd, maxDist = L.maxDist, minMatch = L.minMatch;
+  const int limit = min(srcEnd, stopAt);
+  int srcIdx = st.srcIdx, anchor = st.anchor, srcInc = st.srcInc, repd0 = st.repd0, repd1 = st.repd1, repIdx = st.repIdx;
+  int lastSkip = st.lastSkip;               // highest own position ever jumped over
+  int overLo = st.overLo, overHi = st.overHi;
+
+  // is position q (q > 0) absent from the reference's table?
+  auto skippedAt = [&](int q) -> bool {
+    if (q >= ownStart) return (q <= lastSkip) && (((__ldcg(D + (q >> 5)) >> (q & 31)) & 1u) != 0);
+    return (q <= aHi) && (((__ldg(A + (q >> 5)) >> (q & 31)) & 1u) != 0);
+  };
+  auto cand = [&](int x) -> int {           // table content for position x: first inserted entry of the prev chain
+    int q = (int)L.prev[x];
+    while (q > 0 && skippedAt(q)) q = (int)L.prev[q];
+    return q;
+  };
+  auto markSkipped = [&](int lo, int hi) {  // called by one lane: positions lo..hi were jumped over
+    hi = min(min(hi, srcEnd), dWriteEnd - 1);
+    lo = max(lo, dWriteBegin);
+    if (lo > hi) return;
+    const int w0 = lo >> 5, w1 = hi >> 5;
+    for (int w = w0; w <= w1; w++) {
+      u32 mask = 0xFFFFFFFFu;
+      if (w == w0) mask &= 0xFFFFFFFFu << (lo & 31);
+      if (w == w1) mask &= 0xFFFFFFFFu >> (31 - (hi & 31));
+      atomicOr(&D[w], mask);
+    }
+  };
+
+  while (srcIdx < limit) {
+    // ---- evaluate the next 32 visit positions, assuming the ones before each are misses ----
+    const u32 stepExtra = (u32)((srcInc + lane) >> 6);
+    u32 exIncl = stepExtra;
+    if (srcInc + 31 >= 64) {
+      for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(0xFFFFFFFFu, exIncl, o); if (lane >= o) exIncl += t; }
+    }
+    const int p = srcIdx + lane + (int)(exIncl - stepExtra);
+    const bool valid = p < limit;
+    bool hit = false;
+    int l0 = 0, pv = 0, repSmall = 0, repRef = 0;
+    int cnd = -1;                             // table content for p (first inserted entry of its prev chain); -1: resolve after the commit
+    if (valid) {
+      const int p1 = p + 1;
+      const int minRef = max(p - maxDist, 0);
+      const int maxM = min(srcEnd - p1, LZ_MAX_MATCH);
+      const int rA = (lane == 0 && repIdx) ? repd1 : repd0, rB = (lane == 0 && repIdx) ? repd0 : repd1;
+      const int refA = p1 - rA, refB = p1 - rB;
+      const u64 n8 = lzf_ld64(src + p1);
+      const u64 a8 = (refA > minRef) ? lzf_ld64(src + refA) : ~n8;
+      const u64 b8 = (refB > minRef) ? lzf_ld64(src + refB) : ~n8;
+      l0 = L.len0[p];
+      pv = (int)L.prev[p];
+      // the reference tries repd[repIdx] first and only falls to the other one when the 4-byte pre-check fails (:374-387)
+      u64 diff;
+      if ((u32)(a8 ^ n8) == 0) { diff = a8 ^ n8; repRef = refA; }
+      else if ((u32)(b8 ^ n8) == 0) { diff = b8 ^ n8; repRef = refB; }
+      else { diff = 1; repRef = 0; }
+      if (repRef > 0) repSmall = (maxM < 8) ? 0 : ((diff == 0) ? 8 : ((__ffsll((long long)diff) - 1) >> 3));
+      // every lane walks its own chain past jumped-over entries; an entry this very batch may jump over is left for later
+      const bool inBatch = ((srcInc + 31) >> 6) > 0;
+      int q = pv;
+      bool unsure = false;
+      while (q > 0) {
+        if (inBatch && q > srcIdx) { unsure = true; break; }
+        if (!skippedAt(q)) break;
+        q = (int)L.prev[q];
+      }
+      bool tableHit;
+      if (unsure) tableHit = true;
+      else {
+        cnd = q;
+        if (q == pv) tableHit = (l0 >= minMatch);
+        else tableHit = (q > minRef) && (lzf_ld32(src + q) == lzf_ld32(src + p));     // the exact length is found at the event
+      }
+      hit = (repSmall >= minMatch) || tableHit;
+    }
+    const u32 stopMask = __ballot_sync(0xFFFFFFFFu, hit);
+    const u32 validMask = __ballot_sync(0xFFFFFFFFu, valid);
+    const int nValid = __popc(validMask);
+    const int nMiss = stopMask ? min(__ffs(stopMask) - 1, nValid) : nValid;
+    // ---- commit the misses: positions jumped over by the acceleration are recorded (they are never inserted) ----
+    if (nMiss > 0) {
+      const int lastEx = __shfl_sync(0xFFFFFFFFu, (int)stepExtra, nMiss - 1);
+      if (lastEx > 0) {
+        const bool mine = lane < nMiss && stepExtra > 0;
+        if (mine) markSkipped(p + 1, p + (int)stepExtra);
+        int mx = mine ? min(p + (int)stepExtra, srcEnd) : -1;
+        for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+        if (mx >= dWriteEnd) {          // only the last visit of a segment can jump across its end
+          int lo = (mine && min(p + (int)stepExtra, srcEnd) >= dWriteEnd) ? max(p + 1, dWriteEnd) : 0x7FFFFFFF;
+          for (int o = 16; o > 0; o >>= 1) lo = min(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, o));
+          overLo = (overHi < 0) ? lo : min(overLo, lo); overHi = max(overHi, mx);
+        }
+        lastSkip = max(lastSkip, min(mx, dWriteEnd - 1));
+        __threadfence_block();
+      }
+      const int lastP = __shfl_sync(0xFFFFFFFFu, p, nMiss - 1);
+      srcIdx = lastP + 1 + lastEx;
+      srcInc += nMiss;
+      repIdx = 0;
+      __syncwarp();
+    }
+    if (!stopMask || nMiss >= nValid) continue;
+    if (srcIdx >= limit) break;
+    // ---- one iteration of the reference loop at srcIdx (:366-566), exact; lane `f` already holds this position's loads ----
+    const int f = nMiss;
+    const int evL0 = __shfl_sync(0xFFFFFFFFu, l0, f);
+    const int evPv = __shfl_sync(0xFFFFFFFFu, pv, f);
+    const int evRepSmall = __shfl_sync(0xFFFFFFFFu, repSmall, f);
+    const int evRepRef = __shfl_sync(0xFFFFFFFFu, repRef, f);
+    const int evCnd = __shfl_sync(0xFFFFFFFFu, cnd, f);
+    // lane f+1 holds position srcIdx + 1 when lane f's step is 1
+    const int nextOk = (f + 1 < 32) && (((validMask >> (f + 1)) & 1u) != 0) && (__shfl_sync(0xFFFFFFFFu, (int)stepExtra, f) == 0);
+    const int nxL0 = __shfl_sync(0xFFFFFFFFu, l0, (f + 1) & 31);
+    const int nxPv = __shfl_sync(0xFFFFFFFFu, pv, (f + 1) & 31);
+    const int nxCnd = __shfl_sync(0xFFFFFFFFu, cnd, (f + 1) & 31);
+    int bestLen = 0;
+    const int srcIdx1 = srcIdx + 1;
+    const int minRef = max(srcIdx - maxDist, 0);
+    int ref = evRepRef;
+    if (ref > 0) bestLen = (evRepSmall < 8) ? evRepSmall : lzf_find_match_warp(src, srcIdx1, ref, min(srcEnd - srcIdx1, LZ_MAX_MATCH), lane);
+    if (bestLen < minMatch) {
+      // check match at position in hash table (:389-395): table content = first entry of the prev chain that was inserted
+      const int ref0 = (evCnd >= 0) ? evCnd : cand(srcIdx);
+      const bool firstHop = (ref0 == evPv);
+      ref = ref0;
+      int hl;
+      if (firstHop) {
+        // len0 already is ((ref > minRef) && 4-byte check) ? findMatch(srcIdx, ref) : 0, capped at 255
+        hl = (evL0 < 255) ? evL0 : lzf_find_match_warp(src, srcIdx, ref, min(srcEnd - srcIdx, LZ_MAX_MATCH), lane);
+      } else if ((ref > minRef) && (lzf_ld32(src + ref) == lzf_ld32(src + srcIdx))) {
+        hl = lzf_find_match_warp(src, srcIdx, ref, min(srcEnd - srcIdx, LZ_MAX_MATCH), lane);
+      } else hl = 0;
+      // (when the hash candidate fails its pre-check the reference keeps the too-short repeat result: a miss either way)
+      bestLen = (hl >= minMatch) ? hl : 0;
+      if (bestLen < minMatch) {       // no good match
+        const int ex = srcInc >> 6;
+        if (ex > 0) {
+          if (lane == 0) markSkipped(srcIdx + 1, srcIdx + ex);
+          const int mx = min(srcIdx + ex, srcEnd);
+          if (mx >= dWriteEnd) { const int lo = max(srcIdx + 1, dWriteEnd); overLo = (overHi < 0) ? lo : min(overLo, lo); overHi = max(overHi, mx); }
+          lastSkip = max(lastSkip, min(mx, dWriteEnd - 1));
+          __threadfence_block();
+          __syncwarp();
+        }
+        srcIdx = srcIdx1 + ex;
+        srcInc++;
+        repIdx = 0;
+        continue;
+      }
+      if ((ref != srcIdx - repd0) && (ref != srcIdx - repd1)) {
+        // check if better match at next position (:405-422); the table lookup there happens before srcIdx1 is inserted
+        int ref1; bool hop1 = false; int l01 = 255;
+        if (nextOk && nxCnd >= 0) { ref1 = nxCnd; hop1 = (nxCnd == nxPv); if (hop1) l01 = nxL0; }
+        else ref1 = cand(srcIdx1);
+        if (ref1 > minRef + 1) {
+          bool sw = false; int bestLen1 = 0;
+          if (hop1 && l01 < 255 && l01 != bestLen) {
+            // len0 is findMatch(srcIdx1, ref1) (or 0 when its 4-byte pre-check fails, which also means < 4 <= bestLen)
+            if (l01 > bestLen) { sw = true; bestLen1 = l01; }
+          } else if (lzf_ld32(src + ref1 + bestLen - 3) == lzf_ld32(src + srcIdx1 + bestLen - 3)) {
+            bestLen1 = lzf_find_match_warp(src, srcIdx1, ref1, min(srcEnd - srcIdx1, LZ_MAX_MATCH), lane);
+            sw = (bestLen1 >= bestLen);
+          }
+          if (sw) { ref = ref1; bestLen = bestLen1; srcIdx = srcIdx1; }
+        }
+        if (EXTRA) {
+          const int srcIdx2 = srcIdx1 + 1;
+          const int ref2 = cand(srcIdx2);
+          if ((ref2 > minRef + 2) && (lzf_ld32(src + ref2 + bestLen - 3) == lzf_ld32(src + srcIdx2 + bestLen - 3))) {
+            const int bestLen2 = lzf_find_match_warp(src, srcIdx2, ref2, min(srcEnd - srcIdx2, LZ_MAX_MATCH), lane);
+            if (bestLen2 >= bestLen) { ref = ref2; bestLen = bestLen2; srcIdx = srcIdx2; }
+          }
+        }
+      }
+      // extend backwards (:446-450), 8 bytes per step
+      const int visited = srcIdx;
+      while (true) {
+        const int room = min(srcIdx - anchor, ref - minRef);
+        if (room <= 0) break;
+        const bool wide = (srcIdx >= 8) && (ref >= 8);
+        int e;
+        if (wide) {
+          const u64 d = lzf_ld64(src + srcIdx - 8) ^ lzf_ld64(src + ref - 8);
+          e = (d == 0) ? 8 : (__clzll((long long)d) >> 3);      // equal bytes counted from the end (highest byte = position - 1)
+        } else {
+          e = (src[srcIdx - 1] == src[ref - 1]) ? 1 : 0;
+        }
+        const int lim = wide ? 8 : 1;
+        const int take = min(e, room);
+        bestLen += take; ref -= take; srcIdx -= take;
+        if (take < lim) break;
+      }
+      if (bestLen > LZ_MAX_MATCH) { ref += (bestLen - LZ_MAX_MATCH); srcIdx += (bestLen - LZ_MAX_MATCH); bestLen = LZ_MAX_MATCH; }
+      // the match interior is inserted again (:553-565): positions jumped over earlier inside it become table entries
+      if (lastSkip > srcIdx && srcIdx < visited) {
+        const int hi = min(visited, lastSkip);
+        for (int q = max(srcIdx + 1, ownStart) + lane; q <= hi; q += 32) atomicAnd(&D[q >> 5], ~(1u << (q & 31)));
+        __threadfence_block();
+        __syncwarp();
+      }
+    } else {
+      if ((bestLen >= LZ_MAX_MATCH) || (src[srcIdx] != src[ref - 1])) srcIdx++;
+      else { bestLen++; ref--; }
+    }
+    // log the match (:467-538 turn it into a token; lzf_emit_kernel does that from the log)
+    srcInc = 0;
+    const int dist = srcIdx - ref;
+    repd1 = repd0; repd0 = dist; repIdx = 1;
+    if (nEv >= evCap) { fail = 1; break; }
+    if (lane == 0) ev[nEv] = make_uint4((u32)srcIdx, (u32)bestLen, (u32)dist, 0u);
+    nEv++;
+    const int start = srcIdx;
+    anchor = srcIdx + bestLen;
+    srcIdx = anchor;
+    st.srcIdx = srcIdx; st.anchor = anchor; st.srcInc = 0; st.repd0 = repd0; st.repd1 = repd1; st.repIdx = 1;
+    st.lastSkip = lastSkip; st.overLo = overLo; st.overHi = overHi;
+    if (onMatch(start, bestLen, dist, st)) return;
+  }
+  st.srcIdx = srcIdx; st.anchor = anchor; st.srcInc = srcInc; st.repd0 = repd0; st.repd1 = repd1; st.repIdx = repIdx;
+  st.lastSkip = lastSkip; st.overLo = overLo; st.overHi = overHi;
+}
+
+__device__ __forceinline__ int lzf_seg_end(const LzfBlock& L, int s) { return (s + 1 >= L.nSeg) ? L.srcEnd : (s + 1) * L.segLen; }
+
+// (re)start of a round: clear the per-round bitmaps of the blocks still running
+__global__ void lzf_round_init_kernel(LzfBlock* __restrict__ lb, int first) {
+  const LzfBlock& L = lb[blockIdx.y];
+  if (L.n <= 0 || !L.active) return;
+  if (first) for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L.nSeg; i += gridDim.x * blockDim.x) L.seg[i].haveTrue = 0;
+  const int nW = (L.n + 31) / 32 + 2;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nW; i += gridDim.x * blockDim.x) { L.D[i] = 0; L.Kn[i] = 0; }
+}
+
+template <bool EXTRA>
+__global__ void __launch_bounds__(32) lzf_spec_kernel(const KzgBlock* __restrict__ blocks, LzfBlock* __restrict__ lb) {
+  const int b = blockIdx.y, s = blockIdx.x, lane = threadIdx.x;
+  const LzfBlock L = lb[b];
+  if (L.n <= 0 || !L.active || s >= L.nSeg) return;
+  const u8* __restrict__ src = blocks[b].cur;
+  const int segStart = s * L.segLen, segEnd = lzf_seg_end(L, s);
+  LzfState st;
+  st.srcIdx = segStart; st.anchor = segStart; st.srcInc = 0; st.repd0 = L.count; st.repd1 = L.count; st.repIdx = 0;
+  st.lastSkip = -1; st.overLo = 0; st.overHi = -1;
+  int nEv = 0, fail = 0;
+  LzfNoSync ns;
+  const int dEnd = (s + 1 >= L.nSeg) ? 0x7FFFFFFF : segEnd;
+  uint4* ev = L.specEv + (size_t)s * L.evStride;
+  if (s > 0 && L.seg[s].haveTrue) {
+    // a previous round's stitch walked up to this segment: start from the state it arrived in, with the positions its last
+    // visit before the segment jumped over (they are part of A by now)
+    const LzfState te = L.seg[s].trueEntry;
+    st.srcIdx = te.srcIdx; st.anchor = te.anchor; st.srcInc = te.srcInc; st.repd0 = te.repd0; st.repd1 = te.repd1; st.repIdx = te.repIdx;
+    const int hi = min(st.srcIdx, segEnd);
+    if (hi > segStart) {
+      bool any = false;
+      for (int w = (segStart >> 5) + lane; w <= ((hi - 1) >> 5); w += 32) {
+        u32 mask = 0xFFFFFFFFu;
+        if (w == ((hi - 1) >> 5) && (hi & 31)) mask &= (1u << (hi & 31)) - 1;
+        const u32 v = L.A[w] & mask;
+        if (v) { atomicOr(&L.D[w], v); any = true; }
+      }
+      if (__ballot_sync(0xFFFFFFFFu, any)) st.lastSkip = hi - 1;
+      __threadfence_block(); __syncwarp();
+    }
+  } else if (s > 0) {
+    // warm-up: parse the tail of the previous segment so that the state at the segment start is, most of the time,
+    // already the reference's (greedy parses re-synchronise within a few matches); nothing of it is kept but the state
+    st.srcIdx = st.anchor = max(segStart - LZF_WARMUP, 0);
+    lzf_core<EXTRA>(L, src, st, segStart, L.A, min(L.aMax, segStart - 1), segStart, L.D, segStart, dEnd, ev, nEv, L.evStride, fail, lane, ns);
+    nEv = 0;
+  }
+  const LzfState entry = st;
+  lzf_core<EXTRA>(L, src, st, segEnd, L.A, min(L.aMax, segStart - 1), segStart, L.D, segStart, dEnd, ev, nEv, L.evStride, fail, lane, ns);
+  if (lane == 0) { LzfSeg& S = L.seg[s]; S.entry = entry; S.end = st; S.nEv = nEv; S.fail = fail; }
+}
+
+// D == Kn on bit positions [lo, hi)?
+__device__ __forceinline__ bool lzf_bits_equal(const u32* D, const u32* Kn, int lo, int hi, int lane) {
+  if (hi <= lo) return true;
+  const int w0 = lo >> 5, w1 = (hi - 1) >> 5;
+  bool diff = false;
+  for (int w = w0 + lane; w <= w1; w += 32) {
+    u32 mask = 0xFFFFFFFFu;
+    if (w == w0) mask &= 0xFFFFFFFFu << (lo & 31);
+    if (w == w1 && (hi & 31)) mask &= (1u << (hi & 31)) - 1;
+    if ((__ldcg(D + w) ^ __ldcg(Kn + w)) & mask) diff = true;
+  }
+  return __ballot_sync(0xFFFFFFFFu, diff) == 0;
+}
+// Kn[lo, hi) := D[lo, hi)
+__device__ __forceinline__ void lzf_bits_copy(const u32* D, u32* Kn, int lo, int hi, int lane) {
+  if (hi <= lo) return;
+  const int w0 = lo >> 5, w1 = (hi - 1) >> 5;
+  for (int w = w0 + lane; w <= w1; w += 32) {
+    u32 mask = 0xFFFFFFFFu;
+    if (w == w0) mask &= 0xFFFFFFFFu << (lo & 31);
+    if (w == w1 && (hi & 31)) mask &= (1u << (hi & 31)) - 1;
+    const u32 v = (__ldcg(Kn + w) & ~mask) | (__ldcg(D + w) & mask);
+    __stcg(Kn + w, v);
+  }
+  __threadfence_block();
+  __syncwarp();
+}
+
+struct LzfSync {           // stitcher side of the re-synchronisation test
+  const uint4* spec; int nSpec; int j; int entryRepd0; int segStart, segEnd; const u32* D; const u32* Kn; int lane;
+  bool synced; bool dead;
+  __device__ __forceinline__ bool operator()(int start, int len, int dist, const LzfState& st) {
+    if (dead || start + len >= segEnd) return false;
+    // advance to the first logged match at or after `start`
+    while (j < nSpec) {
+      const int k = j + lane;
+      const u32 x = (k < nSpec) ? spec[k].x : 0xFFFFFFFFu;
+      const u32 m = __ballot_sync(0xFFFFFFFFu, x >= (u32)start);
+      if (m == 0) { j += 32; continue; }
+      j += __ffs(m) - 1;
+      break;
+    }
+    if (j >= nSpec) { dead = true; return false; }
+    const uint4 e = spec[j];
+    if ((int)e.x != start || (int)e.y != len || (int)e.z != dist) return false;
+    const int rp1 = (j > 0) ? (int)spec[j - 1].z : entryRepd0;
+    if (rp1 != st.repd1) return false;
+    if (st.overHi >= 0 || !lzf_bits_equal(D, Kn, segStart, start + len, lane)) { dead = true; return false; }
+    synced = true;
+    return true;
+  }
+};
+
+template <bool EXTRA>
+__global__ void __launch_bounds__(32) lzf_stitch_kernel(const KzgBlock* __restrict__ blocks, LzfBlock* __restrict__ lb, int dbg) {
+  const int b = blockIdx.x, lane = threadIdx.x;
+  const LzfBlock L = lb[b];
+  if (L.n <= 0 || !L.active) return;
+  const u8* __restrict__ src = blocks[b].cur;
+  int nR = 0, nPatch = 0, fail = 0;
+  int nSync = 0, nDead = 0, nOver = 0, nEnd = 0, nAtOnce = 0; long long t0 = clock64();
+  auto addRange = [&](const uint4* p, int cnt) { if (cnt > 0) { if (lane == 0) { L.rng[nR].ev = p; L.rng[nR].count = cnt; } nR++; } };
+  auto applyOver = [&](const LzfState& e) {          // positions a segment jumped over beyond its own end
+    if (e.overHi >= 0 && lane == 0) for (int q = e.overLo; q <= e.overHi; q++) atomicOr(&L.Kn[q >> 5], 1u << (q & 31));
+    __threadfence_block(); __syncwarp();
+  };
+  // segment 0 started from the reference's initial state: exact as it stands
+  LzfState st = L.seg[0].end;
+  fail |= L.seg[0].fail;
+  addRange(L.specEv, L.seg[0].nEv);
+  if (st.lastSkip >= 0) lzf_bits_copy(L.D, L.Kn, 0, lzf_seg_end(L, 0) + ((L.nSeg == 1) ? 2 : 0), lane);
+  applyOver(st);
+  st.lastSkip = max(st.lastSkip, st.overHi); st.overLo = 0; st.overHi = -1;
+  for (int s = 1; s < L.nSeg; s++) {
+    const int segStart = s * L.segLen, segEnd = lzf_seg_end(L, s);
+    LzfSeg& S = L.seg[s];
+    if (lane == 0) { S.trueEntry = st; S.haveTrue = 1; }
+    if (st.srcIdx >= segEnd) { nOver++; continue; }    // a match ran over the whole segment
+    LzfSync sy;
+    sy.spec = L.specEv + (size_t)s * L.evStride; sy.nSpec = S.nEv; sy.j = 0; sy.entryRepd0 = S.entry.repd0;
+    sy.segStart = segStart; sy.segEnd = segEnd; sy.D = L.D; sy.Kn = L.Kn; sy.lane = lane; sy.synced = false;
+    sy.dead = (S.fail != 0);
+    const LzfState& en = S.entry;
+    const bool atOnce = !sy.dead && st.srcIdx == en.srcIdx && st.anchor == en.anchor && st.srcInc == en.srcInc && st.repd0 == en.repd0 &&
+                        st.repd1 == en.repd1 && st.repIdx == en.repIdx && lzf_bits_equal(L.D, L.Kn, segStart, st.srcIdx, lane);
+    if (atOnce) {                                      // the warm-up already was in the reference's state at the segment start
+      nAtOnce++;
+      sy.synced = true; sy.j = -1;
+      if (S.nEv > 0) {                                 // a first match that reaches back over the segment start re-inserts what it covers
+        const uint4 e0 = sy.spec[0];
+        const int hi = min(segStart, (int)(e0.x + e0.y)) - 1;
+        if ((int)e0.x < segStart && st.lastSkip > (int)e0.x) {
+          for (int q = (int)e0.x + 1 + lane; q <= hi; q += 32) atomicAnd(&L.Kn[q >> 5], ~(1u << (q & 31)));
+          __threadfence_block(); __syncwarp();
+        }
+      }
+    } else {
+      const int from = nPatch;
+      lzf_core<EXTRA>(L, src, st, segEnd, L.A, -1, 0, L.Kn, 0, 0x7FFFFFFF, L.patchEv, nPatch, L.patchCap, fail, lane, sy);
+      addRange(L.patchEv + from, nPatch - from);
+      if (fail) break;
+      if (sy.dead) nDead++; else if (!sy.synced) nEnd++;
+    }
+    if (sy.synced) {
+      nSync++;
+      addRange(sy.spec + sy.j + 1, S.nEv - sy.j - 1);
+      if (S.end.lastSkip >= segStart)                  // (nothing to merge when the segment never jumped)
+        lzf_bits_copy(L.D, L.Kn, atOnce ? segStart : st.anchor, segEnd + ((s + 1 >= L.nSeg) ? 2 : 0), lane);
+      const int ls = st.lastSkip;
+      st = S.end;
+      applyOver(st);
+      st.lastSkip = max(max(ls, st.lastSkip), st.overHi); st.overLo = 0; st.overHi = -1;
+    }
+  }
+  if (lane == 0) { lb[b].nRng = nR; if (fail) lb[b].needSerial = 1; }
+  if ((dbg & 1) && lane == 0) printf("lzf stitch block %d: %d segs, %d synced (%d at once), %d dead, %d unsynced, %d covered, %d own matches, fail %d, %lld cycles\n", b, L.nSeg, nSync, nAtOnce, nDead, nEnd, nOver, nPatch, fail, clock64() - t0);
+}
+
+// Kn == A ?  (one CTA per block).  Not equal: A := Kn for the next round, or the serial walk after the last one.
+__global__ void __launch_bounds__(1024) lzf_check_kernel(LzfBlock* __restrict__ lb, int lastRound, int* __restrict__ nActive) {
+  __shared__ int sDiff, sMax;
+  LzfBlock& L = lb[blockIdx.x];
+  if (L.n <= 0 || !L.active) return;
+  if (threadIdx.x == 0) { sDiff = 0; sMax = -1; }
+  __syncthreads();
+  const int nW = (L.n + 31) / 32 + 1;
+  int diff = 0, mx = -1;
+  for (int i = threadIdx.x; i < nW; i += blockDim.x) {
+    const u32 k = L.Kn[i], a = L.A[i];
+    if (k != a) diff = 1;
+    if (k) mx = i * 32 + 31 - __clz(k);
+  }
+  if (diff) sDiff = 1;
+  if (mx >= 0) atomicMax(&sMax, mx);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (L.needSerial) { L.active = 0; }
+    else if (!sDiff) { L.active = 0; }
+    else if (lastRound) { L.active = 0; L.needSerial = 1; }
+    else { u32* t = L.A; L.A = L.Kn; L.Kn = t; L.aMax = sMax; atomicAdd(nActive, 1); }
+    if (L.needSerial) atomicAdd(nActive + 1, 1);
+  }
+}
+
+// ---- phase 4: tokens from the match list (:467-538, :568-596) ----------------------------------------------------------------------
+__device__ __forceinline__ int lzf_len_size(int length) { return (length < 254) ? 1 : ((length < 65536 + 254) ? 3 : 4); }
+__device__ __forceinline__ void lzf_put_length(u8* p, int length) {      // emitLength (:211-231)
+  if (length < 254) { p[0] = (u8)length; return; }
+  if (length < 65536 + 254) { length -= 254; p[0] = 254; p[1] = (u8)(length >> 8); p[2] = (u8)length; return; }
+  length -= 255; p[0] = 255; p[1] = (u8)(length >> 16); p[2] = (u8)(length >> 8); p[3] = (u8)length;
+}
+#define LZF_ET 1024
+#define LZF_MAX_RNG 1100
+__global__ void __launch_bounds__(LZF_ET) lzf_emit_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P, LzfBlock* __restrict__ lb) {
+  __shared__ int rngStart[LZF_MAX_RNG + 1];
+  __shared__ uint4 tileEv[LZF_ET + 2];                  // [0], [1]: the two matches before the tile
+  __shared__ u32 wsA[32], wsB[32];
+  __shared__ int qSrc[LZF_ET], qDst[LZF_ET], qLen[LZF_ET];
+  __shared__ int qN, sErr, sGiveUp, sLastEnd;
+  __shared__ u32 carryLit, carryM, carryML, totA, totB;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const LzfBlock L = lb[b];
+  if (L.n <= 0 || L.needSerial) return;
+  KzgBlock& B = blocks[b];
+  int* res = P.result + 2 * b;
+  const u8* __restrict__ src = B.cur;
+  u8* __restrict__ dst = B.alt;
+  const int count = L.count, minMatch = L.minMatch, cap = B.cap;
+  const int nR = min(L.nRng, LZF_MAX_RNG);
+  for (int r = tid; r < nR; r += LZF_ET) rngStart[r + 1] = L.rng[r].count;
+  __syncthreads();
+  if (tid == 0) {
+    int acc = 0;
+    rngStart[0] = 0;
+    for (int r = 1; r <= nR; r++) { acc += rngStart[r]; rngStart[r] = acc; }
+    carryLit = 13; carryM = 0; carryML = 0; sErr = 0x7FFFFFFF; sGiveUp = 0x7FFFFFFF; sLastEnd = 0;
+    tileEv[0] = make_uint4(0, 0, (u32)count, 0); tileEv[1] = make_uint4(0, 0, (u32)count, 0);
+  }
+  __syncthreads();
+  const int m = rngStart[nR];
+  u8* tkBuf = L.tk; u8* mBuf = L.m; u8* mLenBuf = L.ml;
+  for (int base = 0; base < m; base += LZF_ET) {
+    const int i = base + tid;
+    const bool on = i < m;
+    uint4 e = make_uint4(0, 0, 0, 0);
+    if (on) {
+      int lo = 0, hi = nR - 1;                          // last range whose start <= i
+      while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (rngStart[mid] <= i) lo = mid; else hi = mid - 1; }
+      e = L.rng[lo].ev[i - rngStart[lo]];
+      if (i == m - 1) sLastEnd = (int)(e.x + e.y);
+    }
+    tileEv[tid + 2] = e;
+    if (tid == 0) qN = 0;
+    __syncthreads();
+    const uint4 p1 = tileEv[tid + 1], p2 = tileEv[tid];
+    int litLen = 0, token = 0, nd = 0, mlSize = 0, mlExt = 0, leSize = 0;
+    const int dist = (int)e.z;
+    if (on) {
+      litLen = (int)e.x - (int)(p1.x + p1.y);
+      int th;
+      if (dist == (int)p1.z) { token = 0x00; th = 3; }
+      else if (dist == (int)p2.z) { token = 0x04; th = 3; }
+      else { nd = 1 + (dist >= 256 ? 1 : 0) + (dist >= 65536 ? 1 : 0); token = nd << 3; th = 7; }
+      const int mLen = (int)e.y - minMatch;
+      if (mLen >= th) { token += th; mlExt = mLen - th; mlSize = lzf_len_size(mlExt); } else token += mLen;
+      if (litLen >= 7) { token |= (7 << 5); leSize = lzf_len_size(litLen - 7); } else token |= (litLen << 5);
+    }
+    // exclusive offsets inside the tile: literal area, and (distance bytes | length bytes) packed
+    const u32 vA = (u32)(leSize + litLen), vB = ((u32)nd << 16) | (u32)mlSize;
+    u32 iA = vA, iB = vB;
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 tA = __shfl_up_sync(0xFFFFFFFFu, iA, o), tB = __shfl_up_sync(0xFFFFFFFFu, iB, o);
+      if (lane >= o) { iA += tA; iB += tB; }
+    }
+    if (lane == 31) { wsA[warp] = iA; wsB[warp] = iB; }
+    __syncthreads();
+    if (warp == 0) {
+      const u32 a = wsA[lane], bb = wsB[lane];
+      u32 ia = a, ib = bb;
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 tA = __shfl_up_sync(0xFFFFFFFFu, ia, o), tB = __shfl_up_sync(0xFFFFFFFFu, ib, o);
+        if (lane >= o) { ia += tA; ib += tB; }
+      }
+      wsA[lane] = ia - a; wsB[lane] = ib - bb;
+      if (lane == 31) { totA = ia; totB = ib; }
+    }
+    __syncthreads();
+    const u32 offLit = carryLit + wsA[warp] + iA - vA;
+    const u32 offB = wsB[warp] + iB - vB;
+    const u32 offM = carryM + (offB >> 16), offML = carryML + (offB & 0xFFFFu);
+    if (on) {
+      if (litLen >= (1 << 24)) atomicMin(&sGiveUp, i);
+      if (i >= L.tkCap || (long long)offLit + leSize + litLen > (long long)cap || (nd && (int)offM + 3 > L.mCap) || (mlSize && (int)offML + 4 > L.mlCap)) atomicMin(&sErr, i);
+      else {
+        tkBuf[i] = (u8)token;
+        if (nd) { u8* q = mBuf + offM; int k = 0; if (nd == 3) q[k++] = (u8)(dist >> 16); if (nd >= 2) q[k++] = (u8)(dist >> 8); q[k] = (u8)dist; }
+        if (mlSize) lzf_put_length(mLenBuf + offML, mlExt);
+        if (leSize) lzf_put_length(dst + offLit, litLen - 7);
+        const int ls = (int)(p1.x + p1.y), ld = (int)offLit + leSize;
+        if (litLen <= 16) { for (int k = 0; k < litLen; k++) dst[ld + k] = src[ls + k]; }
+        else { const int q = atomicAdd(&qN, 1); qSrc[q] = ls; qDst[q] = ld; qLen[q] = litLen; }
+      }
+    }
+    __syncthreads();
+    {                                                   // long literal runs: one warp per run
+      const int n = qN;
+      for (int q = warp; q < n; q += LZF_ET / 32) {
+        const int ls = qSrc[q], ld = qDst[q], len = qLen[q];
+        for (int k = lane; k < len; k += 32) dst[ld + k] = src[ls + k];
+      }
+    }
+    if (tid == 0) {
+      carryLit += totA; carryM += (totB >> 16); carryML += (totB & 0xFFFFu);
+      tileEv[0] = tileEv[LZF_ET]; tileEv[1] = tileEv[LZF_ET + 1];
+    }
+    __syncthreads();
+  }
+  // (error ordering follows the serial loop: the first offending match decides)
+  const int errIdx = sErr, gvIdx = sGiveUp;
+  if (gvIdx != 0x7FFFFFFF && gvIdx <= errIdx) return;                                    // forward returns false (:523-524)
+  if (errIdx != 0x7FFFFFFF) { if (tid == 0) atomicExch(&B.status, -KZG_ERR_PROCESS_BLOCK); return; }
+  // last literals (:568-596)
+  const int prevEnd = sLastEnd;
+  const int litLen = count - prevEnd;
+  int dstIdx = (int)carryLit; const int mIdx = (int)carryM, mLenIdx = (int)carryML;
+  int tkIdx = m;
+  if (dstIdx + litLen + tkIdx + mIdx + mLenIdx >= count) return;                         // forward returns false
+  if (tkIdx >= L.tkCap) { if (tid == 0) atomicExch(&B.status, -KZG_ERR_PROCESS_BLOCK); return; }
+  if (litLen >= 7) {
+    if (tid == 0) { tkBuf[tkIdx] = (u8)(7 << 5); lzf_put_length(dst + dstIdx, litLen - 7); }
+    dstIdx += lzf_len_size(litLen - 7);
+  } else if (tid == 0) tkBuf[tkIdx] = (u8)(litLen << 5);
+  tkIdx++;
+  __syncthreads();
+  for (int i = tid; i < litLen; i += LZF_ET) dst[dstIdx + i] = src[prevEnd + i];
+  dstIdx += litLen;
+  if (tid == 0) {
+    const u32 a = (u32)dstIdx, t = (u32)tkIdx, mm = (u32)mIdx;
+    dst[0] = (u8)a; dst[1] = (u8)(a >> 8); dst[2] = (u8)(a >> 16); dst[3] = (u8)(a >> 24);
+    dst[4] = (u8)t; dst[5] = (u8)(t >> 8); dst[6] = (u8)(t >> 16); dst[7] = (u8)(t >> 24);
+    dst[8] = (u8)mm; dst[9] = (u8)(mm >> 8); dst[10] = (u8)(mm >> 16); dst[11] = (u8)(mm >> 24);
+    dst[12] = (u8)(((L.maxDist == LZ_MAX_DISTANCE1) ? 0 : 1) | (((minMatch - 2) & 0x07) << 1));
+  }
+  for (int i = tid; i < tkIdx; i += LZF_ET) dst[dstIdx + i] = tkBuf[i];
+  dstIdx += tkIdx;
+  for (int i = tid; i < mIdx; i += LZF_ET) dst[dstIdx + i] = mBuf[i];
+  dstIdx += mIdx;
+  for (int i = tid; i < mLenIdx; i += LZF_ET) dst[dstIdx + i] = mLenBuf[i];
+  dstIdx += mLenIdx;
+  if (tid == 0) { res[1] = dstIdx; res[0] = (dstIdx <= count - (count / 100)) ? 1 : 0; }
+}
+
 // ---- host ------------------------------------------------------------------------------------------------------------------------------
 static size_t lzf_al(size_t v) { return (v + 255) / 256 * 256; }
-struct LzfSizes { size_t hash, sa, prev, len0, skipped, hist, tk, m, ml, total; };
+struct LzfSizes { size_t hash, sa, prev, len0, skipped, hist, tk, m, ml, spec, patch, seg, rng, total; int segLen, maxSeg, evStride, patchCap; };
 static LzfSizes lzf_sizes(i32 maxLen) {
   LzfSizes z;
   const size_t n = (size_t)maxLen + 64;
@@ -548,15 +1156,21 @@ static LzfSizes lzf_sizes(i32 maxLen) {
   z.hash = lzf_al(4 * n); z.sa = lzf_al(4 * n); z.prev = lzf_al(4 * n); z.len0 = lzf_al(n); z.skipped = lzf_al(n / 8 + 64);
   z.hist = lzf_al(4 * 256 * nT);
   z.tk = lzf_al(std::max<size_t>(n / 5, 256) + 64); z.m = lzf_al(n + 64); z.ml = lzf_al(n / 2 + 64);
-  z.total = z.hash + 2 * z.sa + z.prev + z.len0 + z.skipped + 2 * z.hist + z.tk + z.m + z.ml + 1024;
+  z.segLen = std::max(32768, (int)((n / 512 + 4095) / 4096 * 4096));
+  z.maxSeg = (int)((n + z.segLen - 1) / z.segLen);
+  z.evStride = z.segLen / 4 + 16;
+  z.patchCap = (int)(n / 4 + 64);
+  z.spec = lzf_al((size_t)z.maxSeg * z.evStride * sizeof(uint4)); z.patch = lzf_al((size_t)z.patchCap * sizeof(uint4));
+  z.seg = lzf_al((size_t)z.maxSeg * sizeof(LzfSeg)); z.rng = lzf_al((size_t)(2 * z.maxSeg + 4) * sizeof(LzfRange));
+  z.total = z.hash + 2 * z.sa + z.prev + z.len0 + 4 * z.skipped + 2 * z.hist + z.tk + z.m + z.ml + z.spec + z.patch + z.seg + z.rng + 1024;
   return z;
 }
-void kzg_lzf_scratch(i32 maxLen, size_t* perBlockBytes) { *perBlockBytes = std::max(*perBlockBytes, lzf_sizes(maxLen).total + sizeof(LzfBlock) + 256); }
+void kzg_lzf_scratch(i32 maxLen, size_t* perBlockBytes) { *perBlockBytes = std::max(*perBlockBytes, lzf_sizes(maxLen).total + sizeof(LzfBlock) + 256 + 1024); }
 
 int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, const KzgXfParams& P, bool extra, i32 maxLen) {
   const LzfSizes z = lzf_sizes(maxLen);
   const size_t nb = (size_t)nBlocks;
-  if (nb * (z.total + 256) > nb * (size_t)P.scratchStride) { kzg_set_error("lz forward: scratch pool too small"); return -KZG_ERR_CREATE_CODEC; }
+  if (nb * (z.total + 256) + 1024 > nb * (size_t)P.scratchStride) { kzg_set_error("lz forward: scratch pool too small"); return -KZG_ERR_CREATE_CODEC; }
   // flat pool: [LzfBlock descriptors][per-block areas]
   LzfBlock* dlb = (LzfBlock*)P.scratch;
   u8* base = P.scratch + lzf_al(nb * sizeof(LzfBlock));
@@ -569,10 +1183,15 @@ int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
     L.len0 = o; o += z.len0; L.skipped = (u32*)o; o += z.skipped; L.hist = (u32*)o; o += z.hist; L.offs = (u32*)o; o += z.hist;
     L.tk = o; o += z.tk; L.m = o; o += z.m; L.ml = o; o += z.ml;
     L.mCap = (i32)z.m - 16; L.mlCap = (i32)z.ml - 16;
+    L.A = (u32*)o; o += z.skipped; L.Kn = (u32*)o; o += z.skipped; L.D = (u32*)o; o += z.skipped;
+    L.specEv = (uint4*)o; o += z.spec; L.patchEv = (uint4*)o; o += z.patch;
+    L.seg = (LzfSeg*)o; o += z.seg; L.rng = (LzfRange*)o; o += z.rng;
+    L.evStride = z.evStride; L.patchCap = z.patchCap;
   }
   CUDA_TRY(cudaMemcpyAsync(dlb, hl.data(), sizeof(LzfBlock) * nb, cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaStreamSynchronize(s));          // hl is stack-owned
-  lzf_setup_kernel<<<(nBlocks + 63) / 64, 64, 0, s>>>(d_blocks, nBlocks, P, dlb);
+  const int dbg = P.flags >> 12;
+  lzf_setup_kernel<<<(nBlocks + 63) / 64, 64, 0, s>>>(d_blocks, nBlocks, P, dlb, z.segLen, (dbg & 8) ? 1 : 0);
   const int gx = std::max(1, std::min((maxLen + 255) / 256, 8 * KZG_SM_COUNT));
   if (extra) lzf_hash_kernel<true><<<dim3(gx, nBlocks), 256, 0, s>>>(d_blocks, dlb);
   else lzf_hash_kernel<false><<<dim3(gx, nBlocks), 256, 0, s>>>(d_blocks, dlb);
@@ -591,9 +1210,35 @@ int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
   }
   lzf_prev_kernel<<<dim3(gx, nBlocks), 256, 0, s>>>(dlb, pass == 1 ? 1 : 0);
   lzf_cand_kernel<<<dim3(gx, nBlocks), 256, 0, s>>>(d_blocks, dlb);
-  if (extra) lzf_walk_kernel<true><<<nBlocks, 64, 0, s>>>(d_blocks, P, dlb);
-  else lzf_walk_kernel<false><<<nBlocks, 64, 0, s>>>(d_blocks, P, dlb);
+  int launches = 5 + 3 * pass;
+  // phase 2/3: speculative segments + stitch, repeated until the assumed skipped-position bitmap is the produced one
+  int* dCnt = (int*)(base + nb * z.total);
+  int hCnt[2] = {0, (dbg & 8) ? nBlocks : 0};
+  int rounds = 0;
+  if (!(dbg & 8)) {
+    const int maxRounds = 4;
+    for (int round = 0; round < maxRounds; round++) {
+      rounds++;
+      CUDA_TRY(cudaMemsetAsync(dCnt, 0, 2 * sizeof(int), s));
+      lzf_round_init_kernel<<<dim3(std::min(gx, 64), nBlocks), 256, 0, s>>>(dlb, round == 0 ? 1 : 0);
+      if (extra) { lzf_spec_kernel<true><<<dim3(z.maxSeg, nBlocks), 32, 0, s>>>(d_blocks, dlb); lzf_stitch_kernel<true><<<nBlocks, 32, 0, s>>>(d_blocks, dlb, dbg); }
+      else { lzf_spec_kernel<false><<<dim3(z.maxSeg, nBlocks), 32, 0, s>>>(d_blocks, dlb); lzf_stitch_kernel<false><<<nBlocks, 32, 0, s>>>(d_blocks, dlb, dbg); }
+      lzf_check_kernel<<<nBlocks, 1024, 0, s>>>(dlb, round == maxRounds - 1 ? 1 : 0, dCnt);
+      launches += 4;
+      CUDA_TRY(cudaMemcpyAsync(hCnt, dCnt, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+      CUDA_TRY(cudaStreamSynchronize(s));
+      if (hCnt[0] == 0) break;
+    }
+  }
+  if (dbg & 1) fprintf(stderr, "lzf: %d blocks, %d rounds, %d serial\n", nBlocks, rounds, hCnt[1]);
+  if (hCnt[1] > 0) {
+    if (extra) lzf_walk_kernel<true><<<nBlocks, 64, 0, s>>>(d_blocks, P, dlb);
+    else lzf_walk_kernel<false><<<nBlocks, 64, 0, s>>>(d_blocks, P, dlb);
+    launches++;
+  }
+  lzf_emit_kernel<<<nBlocks, LZF_ET, 0, s>>>(d_blocks, P, dlb);
+  launches++;
   CUDA_TRY(cudaGetLastError());
-  kzg_count_launch(5 + 3 * pass);
+  kzg_count_launch(launches);
   return 0;
 }
