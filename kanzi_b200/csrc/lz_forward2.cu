@@ -42,6 +42,7 @@ struct LzfBlock {                 // per-block scratch pointers (device)
   u32* A;                         // skipped-position bitmap every segment assumes for positions before its own start
   u32* Kn;                        // skipped-position bitmap of the stitched parse (next round's assumption)
   u32* D;                         // skipped positions each speculative segment found inside its own range
+  u32* C;                         // positions before a segment whose assumed state a lookup of that segment depended on
   uint4* specEv;                  // per-segment match logs {start, length, distance, -}
   uint4* patchEv;                 // matches the stitcher had to find itself
   struct LzfSeg* seg;             // per-segment end state
@@ -134,7 +135,14 @@ __global__ void lzf_hash_kernel(const KzgBlock* __restrict__ blocks, LzfBlock* _
 }
 
 // ---- phase 1b: stable LSD radix sort of positions by hash (8-bit digits) -----------------------------------------------------------
-__global__ void __launch_bounds__(32 * LZF_WARPS) lzf_hist_kernel(LzfBlock* __restrict__ lb, int shift, int first) {
+// sort key of position s: a digit of its hash, or (second sort) of a 16-bit fingerprint of its first 4 bytes
+#define LZF_NOCAND 0x80000000u
+__device__ __forceinline__ u32 lzf_fp(const u8* __restrict__ src, u32 s) { return (lzf_ld32(src + s) * 0x9E3779B1u) >> 16; }
+__device__ __forceinline__ int lzf_digit(const LzfBlock& L, const u8* __restrict__ src, u32 s, int shift, int useFp) {
+  return (int)(((useFp ? lzf_fp(src, s) : L.hash[s]) >> shift) & 255);
+}
+// pass k reads identity (k == 0), sa (k odd) or sa2 (k even) and writes sa (k even) or sa2 (k odd)
+__global__ void __launch_bounds__(32 * LZF_WARPS) lzf_hist_kernel(const KzgBlock* __restrict__ blocks, LzfBlock* __restrict__ lb, int shift, int k, int useFp) {
   __shared__ u32 cnt[LZF_WARPS][256];
   const LzfBlock& L = lb[blockIdx.y];
   const int n = L.n;
@@ -145,9 +153,11 @@ __global__ void __launch_bounds__(32 * LZF_WARPS) lzf_hist_kernel(LzfBlock* __re
   for (int i = lane; i < 256; i += 32) cnt[warp][i] = 0;
   __syncwarp();
   const int beg = tile * LZF_WT, end = min(beg + LZF_WT, n);
+  const u8* __restrict__ src = blocks[blockIdx.y].cur;
+  const u32* __restrict__ in = (k & 1) ? L.sa : L.sa2;
   for (int i = beg + lane; i < end; i += 32) {
-    const u32 s = first ? (u32)i : L.sa[i];
-    atomicAdd(&cnt[warp][(L.hash[s] >> shift) & 255], 1u);
+    const u32 s = (k == 0) ? (u32)i : in[i];
+    atomicAdd(&cnt[warp][lzf_digit(L, src, s, shift, useFp)], 1u);
   }
   __syncwarp();
   for (int d = lane; d < 256; d += 32) L.hist[(size_t)d * nT + tile] = cnt[warp][d];
@@ -181,7 +191,7 @@ __global__ void __launch_bounds__(1024) lzf_scan_kernel(LzfBlock* __restrict__ l
     __syncthreads();
   }
 }
-__global__ void __launch_bounds__(32 * LZF_WARPS) lzf_scatter_kernel(LzfBlock* __restrict__ lb, int shift, int first) {
+__global__ void __launch_bounds__(32 * LZF_WARPS) lzf_scatter_kernel(const KzgBlock* __restrict__ blocks, LzfBlock* __restrict__ lb, int shift, int k, int useFp) {
   __shared__ u32 pos[LZF_WARPS][256];
   const LzfBlock& L = lb[blockIdx.y];
   const int n = L.n;
@@ -193,12 +203,14 @@ __global__ void __launch_bounds__(32 * LZF_WARPS) lzf_scatter_kernel(LzfBlock* _
   __syncwarp();
   const int beg = tile * LZF_WT, end = min(beg + LZF_WT, n);
   const u32 lower = (1u << lane) - 1;
-  u32* __restrict__ out = first ? L.sa : L.sa2;       // pass 1 writes sa (from identity), pass 2 writes sa2 (from sa)
+  const u8* __restrict__ src = blocks[blockIdx.y].cur;
+  const u32* __restrict__ in = (k & 1) ? L.sa : L.sa2;
+  u32* __restrict__ out = (k & 1) ? L.sa2 : L.sa;
   for (int base = beg; base < end; base += 32) {
     const int i = base + lane;
     const bool on = i < end;
     u32 s = 0; int d = 256 + lane;
-    if (on) { s = first ? (u32)i : L.sa[i]; d = (int)((L.hash[s] >> shift) & 255); }
+    if (on) { s = (k == 0) ? (u32)i : in[i]; d = lzf_digit(L, src, s, shift, useFp); }
     const u32 peers = __match_any_sync(0xFFFFFFFFu, d);
     if (on) out[pos[warp][d] + __popc(peers & lower)] = s;
     __syncwarp();
@@ -207,10 +219,10 @@ __global__ void __launch_bounds__(32 * LZF_WARPS) lzf_scatter_kernel(LzfBlock* _
   }
 }
 // sorted[i-1] precedes sorted[i] in (hash, position) order: same hash -> it is the previous occurrence
-__global__ void lzf_prev_kernel(LzfBlock* __restrict__ lb, int extraPass) {
+__global__ void lzf_prev_kernel(LzfBlock* __restrict__ lb, int lastPass) {
   const LzfBlock& L = lb[blockIdx.y];
   const int n = L.n;
-  const u32* __restrict__ sorted = extraPass ? L.sa : L.sa2;
+  const u32* __restrict__ sorted = (lastPass & 1) ? L.sa2 : L.sa;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const u32 s = sorted[i];
     u32 pv = 0;
@@ -233,13 +245,29 @@ __global__ void lzf_cand_kernel(const KzgBlock* __restrict__ blocks, LzfBlock* _
   }
 }
 
+// After the second sort (fingerprint, hash, position): a position whose predecessor differs in hash or fingerprint has no
+// earlier occurrence of its first 4 bytes among the positions with its hash, so no table content can ever pass the 4-byte
+// pre-check there (:389-395, :405-422 need bestLen >= 4).  Those positions never need the table: flag them in prev[].
+__global__ void lzf_flag_kernel(const KzgBlock* __restrict__ blocks, LzfBlock* __restrict__ lb, int lastPass) {
+  const LzfBlock& L = lb[blockIdx.y];
+  const int n = L.n;
+  const u8* __restrict__ src = blocks[blockIdx.y].cur;
+  const u32* __restrict__ sorted = (lastPass & 1) ? L.sa2 : L.sa;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const u32 s = sorted[i];
+    bool has = false;
+    if (i > 0) { const u32 q = sorted[i - 1]; has = (L.hash[q] == L.hash[s]) && (lzf_fp(src, q) == lzf_fp(src, s)); }
+    if (!has) L.prev[s] |= LZF_NOCAND;
+  }
+}
+
 // ---- phase 2: the walk -----------------------------------------------------------------------------------------------------------------
 // (bitmap words are updated with atomics, which act at L2: read them with ld.global.cg so no stale L1 line is used)
 __device__ __forceinline__ bool lzf_is_skipped(const u32* sk, int q) { return (__ldcg(sk + (q >> 5)) >> (q & 31)) & 1u; }
 // the reference's table content for position x: most recent inserted position with x's hash
 __device__ __forceinline__ int lzf_cand(const LzfBlock& L, int x, int lastSkip) {
-  int q = (int)L.prev[x];
-  while (q > 0 && q <= lastSkip && lzf_is_skipped(L.skipped, q)) q = (int)L.prev[q];
+  int q = (int)(L.prev[x] & ~LZF_NOCAND);
+  while (q > 0 && q <= lastSkip && lzf_is_skipped(L.skipped, q)) q = (int)(L.prev[q] & ~LZF_NOCAND);
   return q;
 }
 __device__ __forceinline__ int lzf_emit_length(u8* block, int idx, int length, int lane) {   // emitLength (:211-231)
@@ -275,7 +303,7 @@ __device__ void lzf_prefetch_warp(const LzfBlock& L, const u8* __restrict__ src,
       if (q >= n) break;
       const int l0 = L.len0[q];
       if ((q & 31) == 0 && q + 128 < n) lzf_prefetch(src + q + 128);
-      if (l0 > 0) { const u32 pv = L.prev[q]; lzf_prefetch(src + pv); }
+      if (l0 > 0) { const u32 pv = L.prev[q] & ~LZF_NOCAND; lzf_prefetch(src + pv); }
       else if ((q & 31) == 0 && q + 64 < n) lzf_prefetch(L.prev + q + 64);
       if (lane == 0) { if (q + 1 - r0 > 0) lzf_prefetch(src + q + 1 - r0 + 32); if (q + 1 - r1 > 0) lzf_prefetch(src + q + 1 - r1 + 32); }
     }
@@ -330,7 +358,7 @@ __global__ void __launch_bounds__(64) lzf_walk_kernel(KzgBlock* __restrict__ blo
       const u64 a8 = (refA > minRef) ? lzf_ld64(src + refA) : ~n8;
       const u64 b8 = (refB > minRef) ? lzf_ld64(src + refB) : ~n8;
       l0 = L.len0[p];
-      pv = (int)L.prev[p];
+      pv = (int)(L.prev[p] & ~LZF_NOCAND);
       // the reference tries repd[repIdx] first and only falls to the other one when the 4-byte pre-check fails (:374-387)
       u64 diff; 
       if ((u32)(a8 ^ n8) == 0) { diff = a8 ^ n8; repRef = refA; }
@@ -575,7 +603,7 @@ struct LzfNoSync { __device__ __forceinline__ bool operator()(int, int, int, con
 template <bool EXTRA, class OnMatch>
 __device__ __forceinline__ void lzf_core(const LzfBlock& L, const u8* __restrict__ src, LzfState& st, const int stopAt,
                                          const u32* __restrict__ A, const int aHi, const int ownStart,
-                                         u32* D, const int dWriteBegin, const int dWriteEnd, uint4* __restrict__ ev, int& nEv, const int evCap,
+                                         u32* D, u32* C, const int dWriteBegin, const int dWriteEnd, uint4* __restrict__ ev, int& nEv, const int evCap,
                                          int& fail, const int lane, OnMatch& onMatch) {
   const int srcEnd = L.srcEnd, maxDist = L.maxDist, minMatch = L.minMatch;
   const int limit = min(srcEnd, stopAt);
@@ -589,8 +617,16 @@ __device__ __forceinline__ void lzf_core(const LzfBlock& L, const u8* __restrict
     return (q <= aHi) && (((__ldg(A + (q >> 5)) >> (q & 31)) & 1u) != 0);
   };
   auto cand = [&](int x) -> int {           // table content for position x: first inserted entry of the prev chain
-    int q = (int)L.prev[x];
-    while (q > 0 && skippedAt(q)) q = (int)L.prev[q];
+    const u32 r = L.prev[x];
+    if (r & LZF_NOCAND) return 0;             // no earlier occurrence of these 4 bytes: whatever the table holds fails the pre-check
+    int q = (int)r;
+    bool marked = false;
+    while (q > 0) {
+      if (q < ownStart && !marked) { atomicOr(&C[q >> 5], 1u << (q & 31)); marked = true; }   // (all lanes, same address)
+      const int nq = (int)(L.prev[q] & ~LZF_NOCAND);
+      if (!skippedAt(q)) break;
+      q = nq;
+    }
     return q;
   };
   auto markSkipped = [&](int lo, int hi) {  // called by one lane: positions lo..hi were jumped over
@@ -618,6 +654,7 @@ __device__ __forceinline__ void lzf_core(const LzfBlock& L, const u8* __restrict
     bool hit = false;
     int l0 = 0, pv = 0, repSmall = 0, repRef = 0;
     int cnd = -1;                             // table content for p (first inserted entry of its prev chain); -1: resolve after the commit
+    int cq = 0;                               // first chain entry before the segment: the lookup's result hangs on the assumed bitmap from there on
     if (valid) {
       const int p1 = p + 1;
       const int minRef = max(p - maxDist, 0);
@@ -628,7 +665,8 @@ __device__ __forceinline__ void lzf_core(const LzfBlock& L, const u8* __restrict
       const u64 a8 = (refA > minRef) ? lzf_ld64(src + refA) : ~n8;
       const u64 b8 = (refB > minRef) ? lzf_ld64(src + refB) : ~n8;
       l0 = L.len0[p];
-      pv = (int)L.prev[p];
+      const u32 pvRaw = L.prev[p];
+      pv = (int)(pvRaw & ~LZF_NOCAND);
       // the reference tries repd[repIdx] first and only falls to the other one when the 4-byte pre-check fails (:374-387)
       u64 diff;
       if ((u32)(a8 ^ n8) == 0) { diff = a8 ^ n8; repRef = refA; }
@@ -637,15 +675,18 @@ __device__ __forceinline__ void lzf_core(const LzfBlock& L, const u8* __restrict
       if (repRef > 0) repSmall = (maxM < 8) ? 0 : ((diff == 0) ? 8 : ((__ffsll((long long)diff) - 1) >> 3));
       // every lane walks its own chain past jumped-over entries; an entry this very batch may jump over is left for later
       const bool inBatch = ((srcInc + 31) >> 6) > 0;
-      int q = pv;
+      int q = (pvRaw & LZF_NOCAND) ? 0 : pv;  // flagged: nothing the table can hold passes the 4-byte pre-check
       bool unsure = false;
       while (q > 0) {
         if (inBatch && q > srcIdx) { unsure = true; break; }
+        if (q < ownStart && cq == 0) cq = q;
+        const int nq = (int)(L.prev[q] & ~LZF_NOCAND);
         if (!skippedAt(q)) break;
-        q = (int)L.prev[q];
+        q = nq;
       }
       bool tableHit;
       if (unsure) tableHit = true;
+      else if (pvRaw & LZF_NOCAND) { cnd = 0; tableHit = false; }
       else {
         cnd = q;
         if (q == pv) tableHit = (l0 >= minMatch);
@@ -657,6 +698,7 @@ __device__ __forceinline__ void lzf_core(const LzfBlock& L, const u8* __restrict
     const u32 validMask = __ballot_sync(0xFFFFFFFFu, valid);
     const int nValid = __popc(validMask);
     const int nMiss = stopMask ? min(__ffs(stopMask) - 1, nValid) : nValid;
+    if (cq > 0 && lane <= nMiss + 1) atomicOr(&C[cq >> 5], 1u << (cq & 31));   // lookups that (may) really happen: misses, the event, its lazy step
     // ---- commit the misses: positions jumped over by the acceleration are recorded (they are never inserted) ----
     if (nMiss > 0) {
       const int lastEx = __shfl_sync(0xFFFFFFFFu, (int)stepExtra, nMiss - 1);
@@ -808,7 +850,7 @@ __global__ void lzf_round_init_kernel(LzfBlock* __restrict__ lb, int first) {
   if (L.n <= 0 || !L.active) return;
   if (first) for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L.nSeg; i += gridDim.x * blockDim.x) L.seg[i].haveTrue = 0;
   const int nW = (L.n + 31) / 32 + 2;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nW; i += gridDim.x * blockDim.x) { L.D[i] = 0; L.Kn[i] = 0; }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nW; i += gridDim.x * blockDim.x) { L.D[i] = 0; L.Kn[i] = 0; L.C[i] = 0; }
 }
 
 template <bool EXTRA>
@@ -846,11 +888,11 @@ __global__ void __launch_bounds__(32) lzf_spec_kernel(const KzgBlock* __restrict
     // warm-up: parse the tail of the previous segment so that the state at the segment start is, most of the time,
     // already the reference's (greedy parses re-synchronise within a few matches); nothing of it is kept but the state
     st.srcIdx = st.anchor = max(segStart - LZF_WARMUP, 0);
-    lzf_core<EXTRA>(L, src, st, segStart, L.A, min(L.aMax, segStart - 1), segStart, L.D, segStart, dEnd, ev, nEv, L.evStride, fail, lane, ns);
+    lzf_core<EXTRA>(L, src, st, segStart, L.A, min(L.aMax, segStart - 1), segStart, L.D, L.C, segStart, dEnd, ev, nEv, L.evStride, fail, lane, ns);
     nEv = 0;
   }
   const LzfState entry = st;
-  lzf_core<EXTRA>(L, src, st, segEnd, L.A, min(L.aMax, segStart - 1), segStart, L.D, segStart, dEnd, ev, nEv, L.evStride, fail, lane, ns);
+  lzf_core<EXTRA>(L, src, st, segEnd, L.A, min(L.aMax, segStart - 1), segStart, L.D, L.C, segStart, dEnd, ev, nEv, L.evStride, fail, lane, ns);
   if (lane == 0) { LzfSeg& S = L.seg[s]; S.entry = entry; S.end = st; S.nEv = nEv; S.fail = fail; }
 }
 
@@ -952,7 +994,7 @@ __global__ void __launch_bounds__(32) lzf_stitch_kernel(const KzgBlock* __restri
       }
     } else {
       const int from = nPatch;
-      lzf_core<EXTRA>(L, src, st, segEnd, L.A, -1, 0, L.Kn, 0, 0x7FFFFFFF, L.patchEv, nPatch, L.patchCap, fail, lane, sy);
+      lzf_core<EXTRA>(L, src, st, segEnd, L.A, -1, 0, L.Kn, nullptr, 0, 0x7FFFFFFF, L.patchEv, nPatch, L.patchCap, fail, lane, sy);
       addRange(L.patchEv + from, nPatch - from);
       if (fail) break;
       if (sy.dead) nDead++; else if (!sy.synced) nEnd++;
@@ -972,7 +1014,15 @@ __global__ void __launch_bounds__(32) lzf_stitch_kernel(const KzgBlock* __restri
   if ((dbg & 1) && lane == 0) printf("lzf stitch block %d: %d segs, %d synced (%d at once), %d dead, %d unsynced, %d covered, %d own matches, fail %d, %lld cycles\n", b, L.nSeg, nSync, nAtOnce, nDead, nEnd, nOver, nPatch, fail, clock64() - t0);
 }
 
-// Kn == A ?  (one CTA per block).  Not equal: A := Kn for the next round, or the serial walk after the last one.
+// Did any lookup depend on a position whose assumed state (A) is not the produced one (Kn)?  (one CTA per block)
+// A lookup that entered the assumed range at chain entry q resolved to the first entry from q on that A does not mark;
+// it would have found the same thing under Kn iff that resolution is the same.  If so for every such q, parsing with Kn
+// assumed reproduces this very parse, so Kn is the fixed point and the parse is the reference's.  Otherwise A := Kn for
+// the next round, or the serial walk after the last one.
+__device__ __forceinline__ int lzf_resolve(const LzfBlock& L, const u32* __restrict__ X, int q) {
+  while (q > 0 && ((X[q >> 5] >> (q & 31)) & 1u)) q = (int)(L.prev[q] & ~LZF_NOCAND);
+  return q;
+}
 __global__ void __launch_bounds__(1024) lzf_check_kernel(LzfBlock* __restrict__ lb, int lastRound, int* __restrict__ nActive) {
   __shared__ int sDiff, sMax;
   LzfBlock& L = lb[blockIdx.x];
@@ -980,15 +1030,32 @@ __global__ void __launch_bounds__(1024) lzf_check_kernel(LzfBlock* __restrict__ 
   if (threadIdx.x == 0) { sDiff = 0; sMax = -1; }
   __syncthreads();
   const int nW = (L.n + 31) / 32 + 1;
-  int diff = 0, mx = -1;
+  int same = 1, mx = -1;
   for (int i = threadIdx.x; i < nW; i += blockDim.x) {
     const u32 k = L.Kn[i], a = L.A[i];
-    if (k != a) diff = 1;
+    if (k != a) same = 0;
     if (k) mx = i * 32 + 31 - __clz(k);
   }
-  if (diff) sDiff = 1;
+  if (!same) sDiff = 1;
   if (mx >= 0) atomicMax(&sMax, mx);
   __syncthreads();
+  const int differ = sDiff;
+  __syncthreads();
+  if (differ) {                      // bitmaps differ somewhere: does it matter to any lookup?
+    if (threadIdx.x == 0) sDiff = 0;
+    __syncthreads();
+    int bad = 0;
+    for (int i = threadIdx.x; i < nW && !bad; i += blockDim.x) {
+      u32 c = L.C[i];
+      while (c) {
+        const int q = i * 32 + __ffs(c) - 1;
+        c &= c - 1;
+        if (lzf_resolve(L, L.A, q) != lzf_resolve(L, L.Kn, q)) { bad = 1; break; }
+      }
+    }
+    if (bad) sDiff = 1;
+    __syncthreads();
+  }
   if (threadIdx.x == 0) {
     if (L.needSerial) { L.active = 0; }
     else if (!sDiff) { L.active = 0; }
@@ -1162,7 +1229,7 @@ static LzfSizes lzf_sizes(i32 maxLen) {
   z.patchCap = (int)(n / 4 + 64);
   z.spec = lzf_al((size_t)z.maxSeg * z.evStride * sizeof(uint4)); z.patch = lzf_al((size_t)z.patchCap * sizeof(uint4));
   z.seg = lzf_al((size_t)z.maxSeg * sizeof(LzfSeg)); z.rng = lzf_al((size_t)(2 * z.maxSeg + 4) * sizeof(LzfRange));
-  z.total = z.hash + 2 * z.sa + z.prev + z.len0 + 4 * z.skipped + 2 * z.hist + z.tk + z.m + z.ml + z.spec + z.patch + z.seg + z.rng + 1024;
+  z.total = z.hash + 2 * z.sa + z.prev + z.len0 + 5 * z.skipped + 2 * z.hist + z.tk + z.m + z.ml + z.spec + z.patch + z.seg + z.rng + 1024;
   return z;
 }
 void kzg_lzf_scratch(i32 maxLen, size_t* perBlockBytes) { *perBlockBytes = std::max(*perBlockBytes, lzf_sizes(maxLen).total + sizeof(LzfBlock) + 256 + 1024); }
@@ -1183,7 +1250,7 @@ int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
     L.len0 = o; o += z.len0; L.skipped = (u32*)o; o += z.skipped; L.hist = (u32*)o; o += z.hist; L.offs = (u32*)o; o += z.hist;
     L.tk = o; o += z.tk; L.m = o; o += z.m; L.ml = o; o += z.ml;
     L.mCap = (i32)z.m - 16; L.mlCap = (i32)z.ml - 16;
-    L.A = (u32*)o; o += z.skipped; L.Kn = (u32*)o; o += z.skipped; L.D = (u32*)o; o += z.skipped;
+    L.A = (u32*)o; o += z.skipped; L.Kn = (u32*)o; o += z.skipped; L.D = (u32*)o; o += z.skipped; L.C = (u32*)o; o += z.skipped;
     L.specEv = (uint4*)o; o += z.spec; L.patchEv = (uint4*)o; o += z.patch;
     L.seg = (LzfSeg*)o; o += z.seg; L.rng = (LzfRange*)o; o += z.rng;
     L.evStride = z.evStride; L.patchCap = z.patchCap;
@@ -1200,17 +1267,19 @@ int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
   const int bits = extra ? 19 : 16;
   int pass = 0;
   for (int shift = 0; shift < bits; shift += 8, pass++) {
-    // pass 0: identity -> sa; later passes ping-pong sa -> sa2 -> (swap by kernel argument is not possible) so copy back
-    lzf_hist_kernel<<<gridT, 32 * LZF_WARPS, 0, s>>>(dlb, shift, pass == 0 ? 1 : 0);
+    lzf_hist_kernel<<<gridT, 32 * LZF_WARPS, 0, s>>>(d_blocks, dlb, shift, pass, 0);
     lzf_scan_kernel<<<nBlocks, 1024, 0, s>>>(dlb);
-    lzf_scatter_kernel<<<gridT, 32 * LZF_WARPS, 0, s>>>(dlb, shift, pass == 0 ? 1 : 0);
-    if (pass >= 1 && shift + 8 < bits) {       // a third pass (19-bit hash) reads sa again: move sa2 back
-      for (int b = 0; b < nBlocks; b++) CUDA_TRY(cudaMemcpyAsync(hl[b].sa, hl[b].sa2, z.sa, cudaMemcpyDeviceToDevice, s));
-    }
+    lzf_scatter_kernel<<<gridT, 32 * LZF_WARPS, 0, s>>>(d_blocks, dlb, shift, pass, 0);
   }
-  lzf_prev_kernel<<<dim3(gx, nBlocks), 256, 0, s>>>(dlb, pass == 1 ? 1 : 0);
+  lzf_prev_kernel<<<dim3(gx, nBlocks), 256, 0, s>>>(dlb, pass - 1);
   lzf_cand_kernel<<<dim3(gx, nBlocks), 256, 0, s>>>(d_blocks, dlb);
-  int launches = 5 + 3 * pass;
+  for (int shift = 0; shift < 16; shift += 8, pass++) {   // second sort key: the 4-byte fingerprint
+    lzf_hist_kernel<<<gridT, 32 * LZF_WARPS, 0, s>>>(d_blocks, dlb, shift, pass, 1);
+    lzf_scan_kernel<<<nBlocks, 1024, 0, s>>>(dlb);
+    lzf_scatter_kernel<<<gridT, 32 * LZF_WARPS, 0, s>>>(d_blocks, dlb, shift, pass, 1);
+  }
+  lzf_flag_kernel<<<dim3(gx, nBlocks), 256, 0, s>>>(d_blocks, dlb, pass - 1);
+  int launches = 6 + 3 * pass;
   // phase 2/3: speculative segments + stitch, repeated until the assumed skipped-position bitmap is the produced one
   int* dCnt = (int*)(base + nb * z.total);
   int hCnt[2] = {0, (dbg & 8) ? nBlocks : 0};
