@@ -39,14 +39,53 @@ __device__ __forceinline__ u32 lzi_apply(u32 sel, u32 f0, u32 f1) {      // g.se
 }
 
 // ---- pass 1: token parse -----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) lzi_tokens_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P, LziTok* __restrict__ toks, i64 tokStride,
-                                                       LziHdr* __restrict__ hdrs) {
-  const int lane = threadIdx.x, b = blockIdx.x;
+// One CTA per block, 1024 tokens per tile.  Everything is a prefix sum over tokens except two cursor chains whose steps
+// are data dependent: the extended literal lengths (a record at the head of each literal run of 7+ bytes, so the place
+// of a record depends on every length before it) and the extended match lengths (1, 3 or 4 byte records in their own
+// stream).  Tile loop 1 gathers, for every extended-literal token, the literal bytes of the ordinary tokens before it;
+// then one thread chases the literal records (a short dependent-load chain, one step per record) while a warp decodes
+// the match-length records 32 at a time; tile loop 2 derives lengths, cursors, the repeat-offset state (a scan over
+// composable maps) and output offsets for all tokens.
+#define LZI_TT 1024
+struct LziShared {
+  u32 wsA[32], wsB[32];
+  u32 wm0[32], wm1[32], ws0[32], ws1[32];
+  u32 carryK, carryL, carryM, carryD, carryOut, rep0, rep1, totA, totB;
+  int nExtL, nExtM, nExtLValid, nExtMValid, lastIdx, fail;
+};
+
+// exclusive scan of two values over the CTA (1024 threads); totals left in S.totA / S.totB
+__device__ __forceinline__ void lzi_cta_scan2(u32 vA, u32 vB, u32& offA, u32& offB, LziShared& S, int lane, int warp) {
+  u32 iA = vA, iB = vB;
+  for (int o = 1; o < 32; o <<= 1) {
+    const u32 tA = __shfl_up_sync(0xFFFFFFFFu, iA, o), tB = __shfl_up_sync(0xFFFFFFFFu, iB, o);
+    if (lane >= o) { iA += tA; iB += tB; }
+  }
+  __syncthreads();                                   // previous users of wsA/wsB are done
+  if (lane == 31) { S.wsA[warp] = iA; S.wsB[warp] = iB; }
+  __syncthreads();
+  if (warp == 0) {
+    const u32 a = S.wsA[lane], bb = S.wsB[lane];
+    u32 ia = a, ib = bb;
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 tA = __shfl_up_sync(0xFFFFFFFFu, ia, o), tB = __shfl_up_sync(0xFFFFFFFFu, ib, o);
+      if (lane >= o) { ia += tA; ib += tB; }
+    }
+    S.wsA[lane] = ia - a; S.wsB[lane] = ib - bb;
+    if (lane == 31) { S.totA = ia; S.totB = ib; }
+  }
+  __syncthreads();
+  offA = S.wsA[warp] + iA - vA; offB = S.wsB[warp] + iB - vB;
+}
+
+__global__ void __launch_bounds__(LZI_TT) lzi_tokens_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P, LziTok* __restrict__ toks, i64 tokStride,
+                                                           LziHdr* __restrict__ hdrs, u32* __restrict__ extPool) {
+  __shared__ LziShared S;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.x;
   KzgBlock& B = blocks[b];
   int* res = P.result + 2 * b;
   LziHdr& H = hdrs[b];
-  if (lane == 0) { res[0] = 0; res[1] = 0; H.nTok = 0; H.outLen = 0; H.ok = 0; for (int i = 0; i < 8; i++) H.done[i] = 0; }
-  __syncwarp();
+  if (tid == 0) { res[0] = 0; res[1] = 0; H.nTok = 0; H.outLen = 0; H.ok = 0; for (int i = 0; i < 8; i++) H.done[i] = 0; }
   if (B.status != 0 || !P.enabled[b]) return;
   const int count = B.curLen;
   const u8* __restrict__ src = B.cur;
@@ -56,100 +95,150 @@ __global__ void __launch_bounds__(32) lzi_tokens_kernel(KzgBlock* __restrict__ b
   const i32 tkLen = le32(0), mIdxLen = le32(4), mLenLen = le32(8);
   if ((tkLen < 0) || (mIdxLen < 0) || (mLenLen < 0)) return;
   if ((tkLen < 13) || (tkLen > count) || (mIdxLen > count - tkLen) || (mLenLen > count - tkLen - mIdxLen)) return;
-  const int tkBase = tkLen;                 // tokens start where the literal area ends
-  int mIdx = tkBase + mIdxLen;              // NB: Java names: tkIdx = A, mIdx = tkIdx + mIdxLen (B), mLenIdx = mIdx + mLenLen (C)
-  // (the header's second field is the token byte count, the third the distance byte count)
+  // (Java names: the first header field is where the tokens start, the second the token byte count, the third the distance byte count)
+  const int tkBase = tkLen;
   const int nTokBytes = mIdxLen;
   const int distBase = tkBase + nTokBytes;
   const int mLenBase = distBase + mLenLen;
-  (void)mIdx;
   const int srcEndLit = tkBase - 13;        // `srcIdx >= srcEnd` ends the walk (:673-674)
   const int litEnd = tkBase;
   const int maxDist = ((src[12] & 1) == 0) ? LZ_MAX_DISTANCE1 : LZ_MAX_DISTANCE2;
   const int minMatch = ((src[12] >> 1) & 0x07) + 2;
   LziTok* T = toks + (i64)b * tokStride;
-  if ((i64)nTokBytes > tokStride) { if (lane == 0) atomicExch(&B.status, -KZG_ERR_PROCESS_BLOCK); return; }
+  if ((i64)nTokBytes > tokStride) { if (tid == 0) atomicExch(&B.status, -KZG_ERR_PROCESS_BLOCK); return; }
+  // per-block lists: extK[j] literal bytes of ordinary tokens before extended-literal token j; extE[j] literal-area bytes of
+  // the extended tokens before j (extE[nExtL] = all of them); extLS[j] = its length | record size << 28; mxVal[k]
+  u32* extK = extPool + (i64)b * 4 * tokStride;
+  u32* extE = extK + tokStride;
+  u32* extLS = extE + tokStride;
+  u32* mxVal = extLS + tokStride;
 
-  u32 litCur = 13, distCur = (u32)distBase, mLenCur = (u32)mLenBase, outCur = 0;
-  u32 rep0 = (u32)count, rep1 = (u32)count;
-  int nTok = 0;
-  bool fail = false, finished = false;
-  for (int base = 0; base < nTokBytes && !finished; base += 32) {
-    const int t = base + lane;
+  if (tid == 0) { S.carryK = 0; S.carryL = 0; S.carryM = 0; S.fail = 0; }
+  __syncthreads();
+  // ---- tile loop 1: ranks of the extended tokens and the ordinary literal bytes before each extended-literal token ----
+  for (int base = 0; base < nTokBytes; base += LZI_TT) {
+    const int t = base + tid;
     const bool on = t < nTokBytes;
     const int token = on ? src[tkBase + t] : 0;
     const bool hasLit = on && token >= 32;
+    const bool lExt = hasLit && token >= 0xE0;
+    const bool isRep = (token & 0x18) == 0;
+    const bool mExt = on && (isRep ? ((token & 3) == 3) : ((token & 7) == 7));
+    const u32 known = (hasLit && !lExt) ? (u32)(token >> 5) : 0u;
+    u32 kOff, cOff;
+    lzi_cta_scan2(known, ((u32)lExt << 16) | (u32)mExt, kOff, cOff, S, lane, warp);
+    if (lExt) extK[S.carryL + (cOff >> 16)] = S.carryK + kOff;
+    __syncthreads();
+    if (tid == 0) { S.carryK += S.totA; S.carryL += S.totB >> 16; S.carryM += S.totB & 0xFFFFu; }
+    __syncthreads();
+  }
+  if (tid == 0) { S.nExtL = (int)S.carryL; S.nExtM = (int)S.carryM; S.nExtLValid = 0; S.nExtMValid = 0; }
+  __syncthreads();
+  // ---- the two cursor chains ----
+  if (warp == 0) {
+    if (lane == 0) {
+      const int nExtL = S.nExtL;
+      u32 E = 0; int j = 0;
+      for (; j < nExtL; j++) {
+        const u32 c = 13u + extK[j] + E;
+        if (c + 4 > (u32)count + 8) break;                      // beyond the block: whatever follows cannot be a live token
+        u32 r = src[c], sz;
+        if (r < 254) sz = 1;
+        else if (r == 254) { r += ((u32)src[c + 1] << 8) + (u32)src[c + 2]; sz = 3; }
+        else { r += ((u32)src[c + 1] << 16) + ((u32)src[c + 2] << 8) + (u32)src[c + 3]; sz = 4; }
+        const u32 len = 7 + r;
+        extE[j] = E; extLS[j] = len | (sz << 28);
+        E += len + sz;
+      }
+      extE[j] = E;
+      S.nExtLValid = j;
+    }
+  } else if (warp == 1) {
+    const int nExtM = S.nExtM;
+    u32 c = (u32)mLenBase; int k = 0;
+    while (k < nExtM) {
+      if (c + 32 + 4 > (u32)count + 8) {                         // tail: one record at a time
+        if (c + 4 > (u32)count + 8) break;
+        u32 r = src[c], sz;
+        if (r < 254) sz = 1;
+        else if (r == 254) { r += ((u32)src[c + 1] << 8) + (u32)src[c + 2]; sz = 3; }
+        else { r += ((u32)src[c + 1] << 16) + ((u32)src[c + 2] << 8) + (u32)src[c + 3]; sz = 4; }
+        if (lane == 0) mxVal[k] = r;
+        k++; c += sz;
+        continue;
+      }
+      const u32 v = src[c + lane];
+      const u32 big = __ballot_sync(0xFFFFFFFFu, v >= 254);
+      const int nSmall = big ? (__ffs(big) - 1) : 32;           // one-byte records before the first long one
+      const int take = min(nSmall, nExtM - k);
+      if (lane < take) mxVal[k + lane] = v;
+      k += take; c += take;
+      if (big && k < nExtM && take == nSmall) {
+        u32 r = src[c], sz;
+        if (r == 254) { r += ((u32)src[c + 1] << 8) + (u32)src[c + 2]; sz = 3; }
+        else { r += ((u32)src[c + 1] << 16) + ((u32)src[c + 2] << 8) + (u32)src[c + 3]; sz = 4; }
+        if (lane == 0) mxVal[k] = r;
+        k++; c += sz;
+      }
+    }
+    if (lane == 0) S.nExtMValid = k;
+  }
+  __syncthreads();
+  if (tid == 0) { S.carryK = 0; S.carryL = 0; S.carryM = 0; S.carryD = (u32)distBase; S.carryOut = 0; S.rep0 = (u32)count; S.rep1 = (u32)count; }
+  __syncthreads();
+  const int nExtLValid = S.nExtLValid, nExtMValid = S.nExtMValid;
+  // ---- tile loop 2: lengths, cursors, repeat offsets, output offsets ----
+  int nTok = 0;
+  bool finished = false;
+  u32 litCurEnd = 13;
+  for (int base = 0; base < nTokBytes && !finished; base += LZI_TT) {
+    const int t = base + tid;
+    const bool on = t < nTokBytes;
+    const int token = on ? src[tkBase + t] : 0;
+    const bool hasLit = on && token >= 32;
+    const bool lExt = hasLit && token >= 0xE0;
     const int f = token & 0x18;
     const bool isRep = (f == 0);
-    // distance bytes
-    const u32 nd = (on && !isRep) ? (u32)(f >> 3) : 0u;
-    u32 ndTot; const u32 ndOff = lzi_scan_u32(nd, lane, ndTot);
-    // match length extensions, resolved in lane order (each needs the cursor left by the previous one)
     const bool mExt = on && (isRep ? ((token & 3) == 3) : ((token & 7) == 7));
-    u32 mLen = on ? (u32)(isRep ? (token & 3) : (token & 7)) + (u32)minMatch : 0u;
-    u32 em = __ballot_sync(0xFFFFFFFFu, mExt);
-    while (em) {
-      const int l = __ffs(em) - 1; em &= em - 1;
-      u32 sz = 0;
-      if (lane == l) {
-        u32 c = mLenCur;
-        if (c + 4 > (u32)count + 8) { fail = true; }
-        else {
-          u32 r = src[c];
-          if (r < 254) sz = 1;
-          else if (r == 254) { r += ((u32)src[c + 1] << 8) + (u32)src[c + 2]; sz = 3; }
-          else { r += ((u32)src[c + 1] << 16) + ((u32)src[c + 2] << 8) + (u32)src[c + 3]; sz = 4; }
-          mLen += r;
-        }
-      }
-      mLenCur += __shfl_sync(0xFFFFFFFFu, sz, l);
-    }
-    // literal lengths: tokens with LLL == 7 carry an extension at the head of their literal run
-    const bool lExt = hasLit && token >= 0xE0;
-    u32 litLen = hasLit ? (u32)(token >> 5) : 0u;           // 7 for extended ones until resolved
-    u32 known = lExt ? 0u : litLen;
-    u32 kTot; const u32 kOff = lzi_scan_u32(known, lane, kTot);
-    u32 extra = 0;                                            // literal-area bytes of resolved extended tokens in lower lanes
-    u32 myExtra = 0; u32 extSz = 0;
-    u32 el = __ballot_sync(0xFFFFFFFFu, lExt);
-    while (el) {
-      const int l = __ffs(el) - 1; el &= el - 1;
-      u32 add = 0;
-      if (lane == l) {
-        const u32 c = litCur + kOff + extra;
-        if (c + 4 > (u32)count + 8) { fail = true; }
-        else {
-          u32 r = src[c];
-          if (r < 254) extSz = 1;
-          else if (r == 254) { r += ((u32)src[c + 1] << 8) + (u32)src[c + 2]; extSz = 3; }
-          else { r += ((u32)src[c + 1] << 16) + ((u32)src[c + 2] << 8) + (u32)src[c + 3]; extSz = 4; }
-          litLen = 7 + r;
-          add = litLen + extSz;
-          myExtra = extra;
-        }
-      }
-      const u32 a = __shfl_sync(0xFFFFFFFFu, add, l);
-      if (lane > l) extra += a;
-    }
-    if (!lExt) myExtra = extra;
-    // where this token's literal bytes start (after its own extension bytes) and end
-    const u32 litSrc = litCur + kOff + myExtra + extSz;
+    const u32 nd = (on && !isRep) ? (u32)(f >> 3) : 0u;
+    const u32 known = (hasLit && !lExt) ? (u32)(token >> 5) : 0u;
+    u32 kOff, cOff;
+    u32 aOff;
+    lzi_cta_scan2(known | (nd << 16), ((u32)lExt << 16) | (u32)mExt, aOff, cOff, S, lane, warp);   // (sums stay below 2^16 per tile)
+    kOff = aOff & 0xFFFFu;
+    const u32 totA = S.totA, totC = S.totB;
+    const u32 jb = S.carryL + (cOff >> 16), kb = S.carryM + (cOff & 0xFFFFu), ndOff = aOff >> 16;
+    bool bad = false;
+    u32 litLen = known, extSz = 0;
+    u32 Eb = extE[min(jb, (u32)nExtLValid)];
+    if (lExt) {
+      if ((int)jb >= nExtLValid) bad = true;
+      else { const u32 ls = extLS[jb]; litLen = ls & 0x0FFFFFFFu; extSz = ls >> 28; }
+    } else if ((int)jb > nExtLValid) bad = true;
+    const u32 litSrc = 13u + S.carryK + kOff + Eb + extSz;
     const u32 litAfter = litSrc + litLen;
+    u32 mLen = on ? (u32)(isRep ? (token & 3) : (token & 7)) + (u32)minMatch : 0u;
+    bool mBad = false;
+    if (mExt) { if ((int)kb >= nExtMValid) mBad = true; else mLen += mxVal[kb]; }
     // the walk ends at the first literal-carrying token whose literals reach srcEnd (:673-674)
-    const bool isLast = hasLit && ((i32)litAfter >= srcEndLit);
-    const u32 lastMask = __ballot_sync(0xFFFFFFFFu, isLast);
-    int nValid = on ? 32 : 0;
-    nValid = __popc(__ballot_sync(0xFFFFFFFFu, on));
-    if (lastMask) { nValid = __ffs(lastMask); finished = true; }
-    const bool live = lane < nValid;
-    const bool hasMatch = live && !(finished && lane == nValid - 1);
+    const bool isLast = hasLit && (bad || ((i32)litAfter >= srcEndLit));
+    __syncthreads();
+    if (tid == 0) S.lastIdx = 0x7FFFFFFF;
+    __syncthreads();
+    if (isLast) atomicMin(&S.lastIdx, tid);
+    __syncthreads();
+    const int lastIdx = S.lastIdx;
+    int nValid = min(LZI_TT, nTokBytes - base);
+    if (lastIdx != 0x7FFFFFFF) { nValid = lastIdx + 1; finished = true; }
+    const bool live = tid < nValid;
+    const bool hasMatch = live && !(finished && tid == nValid - 1);
     if (!hasMatch) mLen = 0;
-    // bounds of the literal run (:657-661)
+    bool fail = live && (bad || (hasMatch && mBad));
     if (live && hasLit && (litAfter > (u32)litEnd)) fail = true;
     // distances: explicit bytes, then the repeat-offset scan
     u32 dExp = 0;
     if (hasMatch && !isRep) {
-      const u32 c = distCur + ndOff;
+      const u32 c = S.carryD + ndOff;
       if (c + nd > (u32)count + 8) fail = true;
       else { dExp = src[c]; if (nd >= 2) dExp = (dExp << 8) | src[c + 1]; if (nd == 3) dExp = (dExp << 8) | src[c + 2]; }
     }
@@ -159,19 +248,28 @@ __global__ void __launch_bounds__(32) lzi_tokens_kernel(KzgBlock* __restrict__ b
     else if (!isRep) { m0 = dExp; m1 = LZI_IN0; }
     else if ((token & 0x04) == 0) { m0 = LZI_IN0; m1 = LZI_IN0; }
     else { m0 = LZI_IN1; m1 = LZI_IN0; }
-    // inclusive scan of map composition (later o earlier)
-    u32 s0 = m0, s1 = m1;
+    u32 s0 = m0, s1 = m1;                       // inclusive scan of map composition (later o earlier) inside the warp
     for (int o = 1; o < 32; o <<= 1) {
       const u32 p0 = __shfl_up_sync(0xFFFFFFFFu, s0, o), p1 = __shfl_up_sync(0xFFFFFFFFu, s1, o);
       if (lane >= o) { const u32 n0 = lzi_apply(s0, p0, p1), n1 = lzi_apply(s1, p0, p1); s0 = n0; s1 = n1; }
     }
-    // state after this token = inclusive map applied to the carried state; the distance used is out0
-    const u32 a0 = lzi_apply(s0, rep0, rep1), a1 = lzi_apply(s1, rep0, rep1);
-    const u32 dist = a0;
-    // output offsets
+    if (lane == 31) { S.wm0[warp] = s0; S.wm1[warp] = s1; }
     const u32 span = live ? (litLen + mLen) : 0u;
-    u32 spanTot; const u32 spanOff = lzi_scan_u32(span, lane, spanTot);
-    const u32 outPos = outCur + spanOff;
+    u32 spanOff, dummy;
+    lzi_cta_scan2(span, 0u, spanOff, dummy, S, lane, warp);     // (its barriers also publish wm0/wm1)
+    const u32 totSpan = S.totA;
+    if (tid == 0) {                              // state at the start of every warp
+      u32 r0 = S.rep0, r1 = S.rep1;
+      for (int w = 0; w < 32; w++) {
+        S.ws0[w] = r0; S.ws1[w] = r1;
+        const u32 n0 = lzi_apply(S.wm0[w], r0, r1), n1 = lzi_apply(S.wm1[w], r0, r1);
+        r0 = n0; r1 = n1;
+      }
+      S.rep0 = r0; S.rep1 = r1;
+    }
+    __syncthreads();
+    const u32 dist = lzi_apply(s0, S.ws0[warp], S.ws1[warp]);
+    const u32 outPos = S.carryOut + spanOff;
     if (live) {
       // sanity checks of the reference (:657-661, 706-711)
       if (hasLit && (litLen > (u32)dstEnd - min(outPos, (u32)dstEnd))) fail = true;
@@ -180,22 +278,23 @@ __global__ void __launch_bounds__(32) lzi_tokens_kernel(KzgBlock* __restrict__ b
         if (dist > mStart || dist == 0 || dist > (u32)maxDist || mStart + mLen > (u32)dstEnd) fail = true;
       }
       LziTok tk; tk.outPos = outPos; tk.litSrc = litSrc; tk.litLen = litLen; tk.mLen = mLen; tk.dist = dist;
-      T[nTok + lane] = tk;
+      T[nTok + tid] = tk;
+      if (tid == nValid - 1) { S.totA = litAfter; }             // literal cursor after the last live token (tokens without literals keep it)
     }
-    if (__any_sync(0xFFFFFFFFu, fail)) { fail = true; break; }
-    // carry
-    const int lastLane = nValid - 1;
-    rep0 = __shfl_sync(0xFFFFFFFFu, a0, lastLane); rep1 = __shfl_sync(0xFFFFFFFFu, a1, lastLane);
-    litCur = __shfl_sync(0xFFFFFFFFu, litAfter, lastLane);
-    // cursors of lanes without literals keep the running value: litAfter of such a lane equals the cursor before it
-    distCur += __shfl_sync(0xFFFFFFFFu, ndOff + nd, lastLane);
-    outCur += __shfl_sync(0xFFFFFFFFu, spanOff + span, lastLane);
+    if (fail) S.fail = 1;
+    __syncthreads();
+    litCurEnd = S.totA;
+    if (tid == 0) {
+      S.carryK += totA & 0xFFFFu; S.carryD += totA >> 16; S.carryL += totC >> 16; S.carryM += totC & 0xFFFFu; S.carryOut += totSpan;
+    }
     nTok += nValid;
+    __syncthreads();
+    if (S.fail) return;                         // inverse returns false (res[0] stays 0)
   }
-  if (fail || !finished) return;            // inverse returns false (res[0] stays 0)
-  if (lane == 0) {
-    H.nTok = nTok; H.outLen = (i32)outCur; H.ok = (litCur == (u32)litEnd) ? 1 : 0;      // `return srcIdx == srcEnd + 13`
-    res[1] = (int)outCur;                   // res[0] is set by the gather pass
+  if (!finished) return;
+  if (tid == 0) {
+    H.nTok = nTok; H.outLen = (i32)S.carryOut; H.ok = (litCurEnd == (u32)litEnd) ? 1 : 0;      // `return srcIdx == srcEnd + 13`
+    res[1] = (int)S.carryOut;                   // res[0] is set by the gather pass
   }
 }
 
@@ -302,20 +401,21 @@ __global__ void __launch_bounds__(256) lzi_gather_kernel(KzgBlock* __restrict__ 
 // scratch: per block tokens (20 B each, up to maxLen/4 + 1024) + 4 bytes per output byte + header
 void kzg_lzi_scratch(i32 maxLen, size_t* perBlockBytes, size_t* aux32) {
   const size_t toks = (size_t)maxLen / 4 + 1024;
-  *perBlockBytes = std::max(*perBlockBytes, toks * sizeof(LziTok) + 256 + 512);
+  *perBlockBytes = std::max(*perBlockBytes, toks * (sizeof(LziTok) + 16) + 256 + 512);
   *aux32 = std::max(*aux32, (size_t)maxLen + 64);
 }
 
 int kzg_lz_inverse_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, const KzgXfParams& P, i32 maxLen) {
   // flat scratch pool (nBlocks * scratchStride bytes): [dense headers, 256 B reserved per block][token arrays]; pointers in aux32
   const i64 tokStride = (i64)maxLen / 4 + 1024;
-  const size_t need = (size_t)nBlocks * (256 + (size_t)tokStride * sizeof(LziTok));
+  const size_t need = (size_t)nBlocks * (256 + (size_t)tokStride * (sizeof(LziTok) + 16));
   if (need > (size_t)nBlocks * (size_t)P.scratchStride) { kzg_set_error("lz inverse: scratch pool too small"); return -KZG_ERR_CREATE_CODEC; }
   LziHdr* hdrs = (LziHdr*)P.scratch;
   LziTok* toks = (LziTok*)(P.scratch + (size_t)nBlocks * 256);
+  u32* extPool = (u32*)(toks + (size_t)nBlocks * tokStride);
   u32* ptrs = (u32*)P.aux32;
   const i64 ptrStride = P.aux32Stride;
-  lzi_tokens_kernel<<<nBlocks, 32, 0, s>>>(d_blocks, P, toks, tokStride, hdrs);
+  lzi_tokens_kernel<<<nBlocks, LZI_TT, 0, s>>>(d_blocks, P, toks, tokStride, hdrs, extPool);
   const int tiles = (maxLen + LZI_TILE - 1) / LZI_TILE;
   lzi_fill_kernel<<<dim3(tiles, nBlocks), 256, 0, s>>>(d_blocks, toks, tokStride, hdrs, ptrs, ptrStride);
   for (int r = 0; r < 6; r++) lzi_jump_kernel<<<dim3(tiles, nBlocks), 256, 0, s>>>(hdrs, ptrs, ptrStride, r);
