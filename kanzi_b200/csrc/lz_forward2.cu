@@ -47,11 +47,14 @@ struct LzfBlock {                 // per-block scratch pointers (device)
   uint4* patchEv;                 // matches the stitcher had to find itself
   struct LzfSeg* seg;             // per-segment end state
   struct LzfRange* rng;           // final match list as ranges of the two logs
+  uint4* fin;                     // the stitched match list, contiguous
+  u32* tileSum;                   // per 1024 matches: literal-area / distance / length bytes (sums, then offsets)
   i32 segLen, nSeg, evStride, patchCap, nRng, aMax, active, needSerial;
+  i32 nFin, giveUpIdx, emitGo, tkBase, mBase, mlBase;
 };
 struct LzfState { i32 srcIdx, anchor, srcInc, repd0, repd1, repIdx, lastSkip, overLo, overHi; };
 struct LzfSeg { LzfState entry; LzfState end; LzfState trueEntry; i32 nEv; i32 fail; i32 haveTrue; i32 pad; };
-struct LzfRange { const uint4* ev; i32 count; i32 pad; };
+struct LzfRange { const uint4* ev; i32 count; i32 start; };
 
 __device__ __forceinline__ u64 lzf_ld64(const u8* __restrict__ p) {
   const uintptr_t a = (uintptr_t)p;
@@ -957,7 +960,8 @@ __global__ void __launch_bounds__(32) lzf_stitch_kernel(const KzgBlock* __restri
   const u8* __restrict__ src = blocks[b].cur;
   int nR = 0, nPatch = 0, fail = 0;
   int nSync = 0, nDead = 0, nOver = 0, nEnd = 0, nAtOnce = 0; long long t0 = clock64();
-  auto addRange = [&](const uint4* p, int cnt) { if (cnt > 0) { if (lane == 0) { L.rng[nR].ev = p; L.rng[nR].count = cnt; } nR++; } };
+  int nFin = 0;
+  auto addRange = [&](const uint4* p, int cnt) { if (cnt > 0) { if (lane == 0) { L.rng[nR].ev = p; L.rng[nR].count = cnt; L.rng[nR].start = nFin; } nR++; nFin += cnt; } };
   auto applyOver = [&](const LzfState& e) {          // positions a segment jumped over beyond its own end
     if (e.overHi >= 0 && lane == 0) for (int q = e.overLo; q <= e.overHi; q++) atomicOr(&L.Kn[q >> 5], 1u << (q & 31));
     __threadfence_block(); __syncwarp();
@@ -1010,7 +1014,7 @@ __global__ void __launch_bounds__(32) lzf_stitch_kernel(const KzgBlock* __restri
       st.lastSkip = max(max(ls, st.lastSkip), st.overHi); st.overLo = 0; st.overHi = -1;
     }
   }
-  if (lane == 0) { lb[b].nRng = nR; if (fail) lb[b].needSerial = 1; }
+  if (lane == 0) { lb[b].nRng = nR; lb[b].nFin = nFin; lb[b].giveUpIdx = 0x7FFFFFFF; if (fail) lb[b].needSerial = 1; }
   if ((dbg & 1) && lane == 0) printf("lzf stitch block %d: %d segs, %d synced (%d at once), %d dead, %d unsynced, %d covered, %d own matches, fail %d, %lld cycles\n", b, L.nSeg, nSync, nAtOnce, nDead, nEnd, nOver, nPatch, fail, clock64() - t0);
 }
 
@@ -1073,144 +1077,191 @@ __device__ __forceinline__ void lzf_put_length(u8* p, int length) {      // emit
   length -= 255; p[0] = 255; p[1] = (u8)(length >> 16); p[2] = (u8)(length >> 8); p[3] = (u8)length;
 }
 #define LZF_ET 1024
-#define LZF_MAX_RNG 1100
-__global__ void __launch_bounds__(LZF_ET) lzf_emit_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P, LzfBlock* __restrict__ lb) {
-  __shared__ int rngStart[LZF_MAX_RNG + 1];
-  __shared__ uint4 tileEv[LZF_ET + 2];                  // [0], [1]: the two matches before the tile
-  __shared__ u32 wsA[32], wsB[32];
-  __shared__ int qSrc[LZF_ET], qDst[LZF_ET], qLen[LZF_ET];
-  __shared__ int qN, sErr, sGiveUp, sLastEnd;
-  __shared__ u32 carryLit, carryM, carryML, totA, totB;
+struct LzfTok { int litLen, token, nd, mlSize, mlExt, leSize; };
+// token of match e given the match before it (p1: previous end and distance) and the distance two matches back
+__device__ __forceinline__ LzfTok lzf_tok(const uint4 e, const uint4 p1, const u32 p2z, const int minMatch) {
+  LzfTok k;
+  k.nd = 0; k.mlSize = 0; k.mlExt = 0; k.leSize = 0;
+  k.litLen = (int)e.x - (int)(p1.x + p1.y);
+  const int dist = (int)e.z;
+  int th;
+  if (dist == (int)p1.z) { k.token = 0x00; th = 3; }
+  else if (dist == (int)p2z) { k.token = 0x04; th = 3; }
+  else { k.nd = 1 + (dist >= 256 ? 1 : 0) + (dist >= 65536 ? 1 : 0); k.token = k.nd << 3; th = 7; }
+  const int mLen = (int)e.y - minMatch;
+  if (mLen >= th) { k.token += th; k.mlExt = mLen - th; k.mlSize = lzf_len_size(k.mlExt); } else k.token += mLen;
+  if (k.litLen >= 7) { k.token |= (7 << 5); k.leSize = lzf_len_size(k.litLen - 7); } else k.token |= (k.litLen << 5);
+  return k;
+}
+__device__ __forceinline__ void lzf_neighbours(const uint4* __restrict__ fin, int i, int count, uint4& p1, u32& p2z) {
+  p1 = (i > 0) ? fin[i - 1] : make_uint4(0, 0, (u32)count, 0);
+  p2z = (i > 1) ? fin[i - 2].z : (u32)count;
+}
+// E1: the match list as one array (ranges of the segment logs and of the stitcher's own log, in order)
+__global__ void __launch_bounds__(LZF_ET) lzf_emit_gather_kernel(LzfBlock* __restrict__ lb) {
+  const LzfBlock& L = lb[blockIdx.y];
+  if (L.n <= 0 || L.needSerial) return;
+  const int i = blockIdx.x * LZF_ET + threadIdx.x;
+  if (i >= L.nFin) return;
+  int lo = 0, hi = L.nRng - 1;                          // last range whose start <= i
+  while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (L.rng[mid].start <= i) lo = mid; else hi = mid - 1; }
+  L.fin[i] = L.rng[lo].ev[i - L.rng[lo].start];
+}
+// E2: bytes every tile of 1024 matches adds to the literal area, the distance bytes and the length bytes
+__global__ void __launch_bounds__(LZF_ET) lzf_emit_size_kernel(LzfBlock* __restrict__ lb) {
+  __shared__ u32 sA[32], sB[32];
+  LzfBlock& L = lb[blockIdx.y];
+  if (L.n <= 0 || L.needSerial) return;
+  const int base = blockIdx.x * LZF_ET;
+  if (base >= L.nFin) return;
+  const int i = base + threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  u32 vA = 0, vB = 0;
+  if (i < L.nFin) {
+    uint4 p1; u32 p2z;
+    lzf_neighbours(L.fin, i, L.count, p1, p2z);
+    const LzfTok k = lzf_tok(L.fin[i], p1, p2z, L.minMatch);
+    vA = (u32)(k.leSize + k.litLen); vB = ((u32)k.nd << 16) | (u32)k.mlSize;
+    if (k.litLen >= (1 << 24)) atomicMin(&L.giveUpIdx, i);
+  }
+  for (int o = 16; o > 0; o >>= 1) { vA += __shfl_xor_sync(0xFFFFFFFFu, vA, o); vB += __shfl_xor_sync(0xFFFFFFFFu, vB, o); }
+  if (lane == 0) { sA[warp] = vA; sB[warp] = vB; }
+  __syncthreads();
+  if (warp == 0) {
+    vA = sA[lane]; vB = sB[lane];
+    for (int o = 16; o > 0; o >>= 1) { vA += __shfl_xor_sync(0xFFFFFFFFu, vA, o); vB += __shfl_xor_sync(0xFFFFFFFFu, vB, o); }
+    if (lane == 0) { L.tileSum[3 * blockIdx.x] = vA; L.tileSum[3 * blockIdx.x + 1] = vB >> 16; L.tileSum[3 * blockIdx.x + 2] = vB & 0xFFFFu; }
+  }
+}
+// E3 (one CTA per block): tile offsets, the reference's end-of-block decisions (:568-596), header and last literals
+__global__ void __launch_bounds__(LZF_ET) lzf_emit_scan_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P, LzfBlock* __restrict__ lb) {
+  __shared__ u32 ws[3][32];
+  __shared__ u32 carry[3];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const LzfBlock L = lb[b];
+  LzfBlock& L = lb[b];
   if (L.n <= 0 || L.needSerial) return;
   KzgBlock& B = blocks[b];
   int* res = P.result + 2 * b;
   const u8* __restrict__ src = B.cur;
   u8* __restrict__ dst = B.alt;
-  const int count = L.count, minMatch = L.minMatch, cap = B.cap;
-  const int nR = min(L.nRng, LZF_MAX_RNG);
-  for (int r = tid; r < nR; r += LZF_ET) rngStart[r + 1] = L.rng[r].count;
+  const int count = L.count, m = L.nFin;
+  const int nT = (m + LZF_ET - 1) / LZF_ET;
+  if (tid == 0) { carry[0] = 13; carry[1] = 0; carry[2] = 0; L.emitGo = 0; }
   __syncthreads();
-  if (tid == 0) {
-    int acc = 0;
-    rngStart[0] = 0;
-    for (int r = 1; r <= nR; r++) { acc += rngStart[r]; rngStart[r] = acc; }
-    carryLit = 13; carryM = 0; carryML = 0; sErr = 0x7FFFFFFF; sGiveUp = 0x7FFFFFFF; sLastEnd = 0;
-    tileEv[0] = make_uint4(0, 0, (u32)count, 0); tileEv[1] = make_uint4(0, 0, (u32)count, 0);
-  }
-  __syncthreads();
-  const int m = rngStart[nR];
-  u8* tkBuf = L.tk; u8* mBuf = L.m; u8* mLenBuf = L.ml;
-  for (int base = 0; base < m; base += LZF_ET) {
-    const int i = base + tid;
-    const bool on = i < m;
-    uint4 e = make_uint4(0, 0, 0, 0);
-    if (on) {
-      int lo = 0, hi = nR - 1;                          // last range whose start <= i
-      while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (rngStart[mid] <= i) lo = mid; else hi = mid - 1; }
-      e = L.rng[lo].ev[i - rngStart[lo]];
-      if (i == m - 1) sLastEnd = (int)(e.x + e.y);
-    }
-    tileEv[tid + 2] = e;
-    if (tid == 0) qN = 0;
-    __syncthreads();
-    const uint4 p1 = tileEv[tid + 1], p2 = tileEv[tid];
-    int litLen = 0, token = 0, nd = 0, mlSize = 0, mlExt = 0, leSize = 0;
-    const int dist = (int)e.z;
-    if (on) {
-      litLen = (int)e.x - (int)(p1.x + p1.y);
-      int th;
-      if (dist == (int)p1.z) { token = 0x00; th = 3; }
-      else if (dist == (int)p2.z) { token = 0x04; th = 3; }
-      else { nd = 1 + (dist >= 256 ? 1 : 0) + (dist >= 65536 ? 1 : 0); token = nd << 3; th = 7; }
-      const int mLen = (int)e.y - minMatch;
-      if (mLen >= th) { token += th; mlExt = mLen - th; mlSize = lzf_len_size(mlExt); } else token += mLen;
-      if (litLen >= 7) { token |= (7 << 5); leSize = lzf_len_size(litLen - 7); } else token |= (litLen << 5);
-    }
-    // exclusive offsets inside the tile: literal area, and (distance bytes | length bytes) packed
-    const u32 vA = (u32)(leSize + litLen), vB = ((u32)nd << 16) | (u32)mlSize;
-    u32 iA = vA, iB = vB;
-    for (int o = 1; o < 32; o <<= 1) {
-      const u32 tA = __shfl_up_sync(0xFFFFFFFFu, iA, o), tB = __shfl_up_sync(0xFFFFFFFFu, iB, o);
-      if (lane >= o) { iA += tA; iB += tB; }
-    }
-    if (lane == 31) { wsA[warp] = iA; wsB[warp] = iB; }
+  for (int base = 0; base < nT; base += LZF_ET) {
+    const int t = base + tid;
+    u32 v[3], inc[3];
+    for (int k = 0; k < 3; k++) { v[k] = (t < nT) ? L.tileSum[3 * t + k] : 0u; inc[k] = v[k]; }
+    for (int o = 1; o < 32; o <<= 1)
+      for (int k = 0; k < 3; k++) { const u32 x = __shfl_up_sync(0xFFFFFFFFu, inc[k], o); if (lane >= o) inc[k] += x; }
+    if (lane == 31) for (int k = 0; k < 3; k++) ws[k][warp] = inc[k];
     __syncthreads();
     if (warp == 0) {
-      const u32 a = wsA[lane], bb = wsB[lane];
-      u32 ia = a, ib = bb;
-      for (int o = 1; o < 32; o <<= 1) {
-        const u32 tA = __shfl_up_sync(0xFFFFFFFFu, ia, o), tB = __shfl_up_sync(0xFFFFFFFFu, ib, o);
-        if (lane >= o) { ia += tA; ib += tB; }
-      }
-      wsA[lane] = ia - a; wsB[lane] = ib - bb;
-      if (lane == 31) { totA = ia; totB = ib; }
-    }
-    __syncthreads();
-    const u32 offLit = carryLit + wsA[warp] + iA - vA;
-    const u32 offB = wsB[warp] + iB - vB;
-    const u32 offM = carryM + (offB >> 16), offML = carryML + (offB & 0xFFFFu);
-    if (on) {
-      if (litLen >= (1 << 24)) atomicMin(&sGiveUp, i);
-      if (i >= L.tkCap || (long long)offLit + leSize + litLen > (long long)cap || (nd && (int)offM + 3 > L.mCap) || (mlSize && (int)offML + 4 > L.mlCap)) atomicMin(&sErr, i);
-      else {
-        tkBuf[i] = (u8)token;
-        if (nd) { u8* q = mBuf + offM; int k = 0; if (nd == 3) q[k++] = (u8)(dist >> 16); if (nd >= 2) q[k++] = (u8)(dist >> 8); q[k] = (u8)dist; }
-        if (mlSize) lzf_put_length(mLenBuf + offML, mlExt);
-        if (leSize) lzf_put_length(dst + offLit, litLen - 7);
-        const int ls = (int)(p1.x + p1.y), ld = (int)offLit + leSize;
-        if (litLen <= 16) { for (int k = 0; k < litLen; k++) dst[ld + k] = src[ls + k]; }
-        else { const int q = atomicAdd(&qN, 1); qSrc[q] = ls; qDst[q] = ld; qLen[q] = litLen; }
+      for (int k = 0; k < 3; k++) {
+        const u32 a = ws[k][lane]; u32 ia = a;
+        for (int o = 1; o < 32; o <<= 1) { const u32 x = __shfl_up_sync(0xFFFFFFFFu, ia, o); if (lane >= o) ia += x; }
+        ws[k][lane] = ia - a;
       }
     }
     __syncthreads();
-    {                                                   // long literal runs: one warp per run
-      const int n = qN;
-      for (int q = warp; q < n; q += LZF_ET / 32) {
-        const int ls = qSrc[q], ld = qDst[q], len = qLen[q];
-        for (int k = lane; k < len; k += 32) dst[ld + k] = src[ls + k];
-      }
+    u32 tot[3];
+    for (int k = 0; k < 3; k++) {
+      const u32 off = carry[k] + ws[k][warp] + inc[k] - v[k];
+      if (t < nT) L.tileSum[3 * t + k] = off;                     // now the exclusive offset of the tile
+      tot[k] = off + v[k];
     }
-    if (tid == 0) {
-      carryLit += totA; carryM += (totB >> 16); carryML += (totB & 0xFFFFu);
-      tileEv[0] = tileEv[LZF_ET]; tileEv[1] = tileEv[LZF_ET + 1];
-    }
+    __syncthreads();
+    if (tid == LZF_ET - 1) for (int k = 0; k < 3; k++) carry[k] = tot[k];
     __syncthreads();
   }
+  int dstIdx = (int)carry[0]; const int mIdx = (int)carry[1], mLenIdx = (int)carry[2];
+  const bool litOverflow = (long long)carry[0] > (long long)B.cap;
   // (error ordering follows the serial loop: the first offending match decides)
-  const int errIdx = sErr, gvIdx = sGiveUp;
-  if (gvIdx != 0x7FFFFFFF && gvIdx <= errIdx) return;                                    // forward returns false (:523-524)
-  if (errIdx != 0x7FFFFFFF) { if (tid == 0) atomicExch(&B.status, -KZG_ERR_PROCESS_BLOCK); return; }
-  // last literals (:568-596)
-  const int prevEnd = sLastEnd;
+  const int gvIdx = L.giveUpIdx;
+  // tkBuf is never grown (:324-333): match number tkCap (0-based) is the first whose token does not fit -> block error
+  if (gvIdx != 0x7FFFFFFF && !(m > L.tkCap && L.tkCap < gvIdx)) return;                    // forward returns false (:523-524)
+  if (m > L.tkCap || litOverflow || mIdx + 3 > L.mCap || mLenIdx + 4 > L.mlCap) { if (tid == 0) atomicExch(&B.status, -KZG_ERR_PROCESS_BLOCK); return; }
+  const int prevEnd = (m > 0) ? (int)(L.fin[m - 1].x + L.fin[m - 1].y) : 0;
   const int litLen = count - prevEnd;
-  int dstIdx = (int)carryLit; const int mIdx = (int)carryM, mLenIdx = (int)carryML;
   int tkIdx = m;
-  if (dstIdx + litLen + tkIdx + mIdx + mLenIdx >= count) return;                         // forward returns false
-  if (tkIdx >= L.tkCap) { if (tid == 0) atomicExch(&B.status, -KZG_ERR_PROCESS_BLOCK); return; }
-  if (litLen >= 7) {
-    if (tid == 0) { tkBuf[tkIdx] = (u8)(7 << 5); lzf_put_length(dst + dstIdx, litLen - 7); }
-    dstIdx += lzf_len_size(litLen - 7);
-  } else if (tid == 0) tkBuf[tkIdx] = (u8)(litLen << 5);
-  tkIdx++;
-  __syncthreads();
+  if (dstIdx + litLen + tkIdx + mIdx + mLenIdx >= count) return;                           // forward returns false
+  if (m == L.tkCap) { if (tid == 0) atomicExch(&B.status, -KZG_ERR_PROCESS_BLOCK); return; }   // the last token does not fit
+  const int litBase = dstIdx;
+  int lastTok;
+  if (litLen >= 7) { lastTok = 7 << 5; if (tid == 0) lzf_put_length(dst + dstIdx, litLen - 7); dstIdx += lzf_len_size(litLen - 7); }
+  else lastTok = litLen << 5;
+  (void)litBase;
   for (int i = tid; i < litLen; i += LZF_ET) dst[dstIdx + i] = src[prevEnd + i];
   dstIdx += litLen;
+  tkIdx = m + 1;
   if (tid == 0) {
     const u32 a = (u32)dstIdx, t = (u32)tkIdx, mm = (u32)mIdx;
     dst[0] = (u8)a; dst[1] = (u8)(a >> 8); dst[2] = (u8)(a >> 16); dst[3] = (u8)(a >> 24);
     dst[4] = (u8)t; dst[5] = (u8)(t >> 8); dst[6] = (u8)(t >> 16); dst[7] = (u8)(t >> 24);
     dst[8] = (u8)mm; dst[9] = (u8)(mm >> 8); dst[10] = (u8)(mm >> 16); dst[11] = (u8)(mm >> 24);
-    dst[12] = (u8)(((L.maxDist == LZ_MAX_DISTANCE1) ? 0 : 1) | (((minMatch - 2) & 0x07) << 1));
+    dst[12] = (u8)(((L.maxDist == LZ_MAX_DISTANCE1) ? 0 : 1) | (((L.minMatch - 2) & 0x07) << 1));
+    dst[dstIdx + m] = (u8)lastTok;
+    L.tkBase = dstIdx; L.mBase = dstIdx + tkIdx; L.mlBase = dstIdx + tkIdx + mIdx;
+    const int total = dstIdx + tkIdx + mIdx + mLenIdx;
+    res[1] = total; res[0] = (total <= count - (count / 100)) ? 1 : 0;
+    L.emitGo = 1;
   }
-  for (int i = tid; i < tkIdx; i += LZF_ET) dst[dstIdx + i] = tkBuf[i];
-  dstIdx += tkIdx;
-  for (int i = tid; i < mIdx; i += LZF_ET) dst[dstIdx + i] = mBuf[i];
-  dstIdx += mIdx;
-  for (int i = tid; i < mLenIdx; i += LZF_ET) dst[dstIdx + i] = mLenBuf[i];
-  dstIdx += mLenIdx;
-  if (tid == 0) { res[1] = dstIdx; res[0] = (dstIdx <= count - (count / 100)) ? 1 : 0; }
+}
+// E4: every match writes its token, distance bytes, length bytes and literals where the prefix sums put them
+__global__ void __launch_bounds__(LZF_ET) lzf_emit_write_kernel(KzgBlock* __restrict__ blocks, LzfBlock* __restrict__ lb) {
+  __shared__ u32 wsA[32], wsB[32];
+  __shared__ int qSrc[LZF_ET], qDst[LZF_ET], qLen[LZF_ET];
+  __shared__ int qN;
+  const LzfBlock& L = lb[blockIdx.y];
+  if (L.n <= 0 || L.needSerial || !L.emitGo) return;
+  const int base = blockIdx.x * LZF_ET;
+  if (base >= L.nFin) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int i = base + tid;
+  const bool on = i < L.nFin;
+  const KzgBlock& B = blocks[blockIdx.y];
+  const u8* __restrict__ src = B.cur;
+  u8* __restrict__ dst = B.alt;
+  LzfTok k; k.litLen = 0; k.token = 0; k.nd = 0; k.mlSize = 0; k.mlExt = 0; k.leSize = 0;
+  uint4 e = make_uint4(0, 0, 0, 0), p1 = e; u32 p2z = 0;
+  if (on) { e = L.fin[i]; lzf_neighbours(L.fin, i, L.count, p1, p2z); k = lzf_tok(e, p1, p2z, L.minMatch); }
+  const u32 vA = (u32)(k.leSize + k.litLen), vB = ((u32)k.nd << 16) | (u32)k.mlSize;
+  u32 iA = vA, iB = vB;
+  for (int o = 1; o < 32; o <<= 1) {
+    const u32 tA = __shfl_up_sync(0xFFFFFFFFu, iA, o), tB = __shfl_up_sync(0xFFFFFFFFu, iB, o);
+    if (lane >= o) { iA += tA; iB += tB; }
+  }
+  if (lane == 31) { wsA[warp] = iA; wsB[warp] = iB; }
+  if (tid == 0) qN = 0;
+  __syncthreads();
+  if (warp == 0) {
+    const u32 a = wsA[lane], bb = wsB[lane];
+    u32 ia = a, ib = bb;
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 tA = __shfl_up_sync(0xFFFFFFFFu, ia, o), tB = __shfl_up_sync(0xFFFFFFFFu, ib, o);
+      if (lane >= o) { ia += tA; ib += tB; }
+    }
+    wsA[lane] = ia - a; wsB[lane] = ib - bb;
+  }
+  __syncthreads();
+  const u32 offLit = L.tileSum[3 * blockIdx.x] + wsA[warp] + iA - vA;
+  const u32 offB = wsB[warp] + iB - vB;
+  const u32 offM = L.tileSum[3 * blockIdx.x + 1] + (offB >> 16), offML = L.tileSum[3 * blockIdx.x + 2] + (offB & 0xFFFFu);
+  if (on) {
+    const int dist = (int)e.z;
+    dst[L.tkBase + i] = (u8)k.token;
+    if (k.nd) { u8* q = dst + L.mBase + offM; int j = 0; if (k.nd == 3) q[j++] = (u8)(dist >> 16); if (k.nd >= 2) q[j++] = (u8)(dist >> 8); q[j] = (u8)dist; }
+    if (k.mlSize) lzf_put_length(dst + L.mlBase + offML, k.mlExt);
+    if (k.leSize) lzf_put_length(dst + offLit, k.litLen - 7);
+    const int ls = (int)(p1.x + p1.y), ld = (int)offLit + k.leSize;
+    if (k.litLen <= 16) { for (int j = 0; j < k.litLen; j++) dst[ld + j] = src[ls + j]; }
+    else { const int q = atomicAdd(&qN, 1); qSrc[q] = ls; qDst[q] = ld; qLen[q] = k.litLen; }
+  }
+  __syncthreads();
+  const int n = qN;                                     // long literal runs: one warp per run
+  for (int q = warp; q < n; q += LZF_ET / 32) {
+    const int ls = qSrc[q], ld = qDst[q], len = qLen[q];
+    for (int j = lane; j < len; j += 32) dst[ld + j] = src[ls + j];
+  }
 }
 
 // ---- host ------------------------------------------------------------------------------------------------------------------------------
@@ -1254,6 +1305,8 @@ int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
     L.specEv = (uint4*)o; o += z.spec; L.patchEv = (uint4*)o; o += z.patch;
     L.seg = (LzfSeg*)o; o += z.seg; L.rng = (LzfRange*)o; o += z.rng;
     L.evStride = z.evStride; L.patchCap = z.patchCap;
+    L.fin = (uint4*)L.hash;                     // (hashes and radix scratch are dead once prev[] and its flags exist)
+    L.tileSum = L.hist;
   }
   CUDA_TRY(cudaMemcpyAsync(dlb, hl.data(), sizeof(LzfBlock) * nb, cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaStreamSynchronize(s));          // hl is stack-owned
@@ -1305,8 +1358,12 @@ int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
     else lzf_walk_kernel<false><<<nBlocks, 64, 0, s>>>(d_blocks, P, dlb);
     launches++;
   }
-  lzf_emit_kernel<<<nBlocks, LZF_ET, 0, s>>>(d_blocks, P, dlb);
-  launches++;
+  const int evTiles = (maxLen / 4 + 64 + LZF_ET - 1) / LZF_ET;
+  lzf_emit_gather_kernel<<<dim3(evTiles, nBlocks), LZF_ET, 0, s>>>(dlb);
+  lzf_emit_size_kernel<<<dim3(evTiles, nBlocks), LZF_ET, 0, s>>>(dlb);
+  lzf_emit_scan_kernel<<<nBlocks, LZF_ET, 0, s>>>(d_blocks, P, dlb);
+  lzf_emit_write_kernel<<<dim3(evTiles, nBlocks), LZF_ET, 0, s>>>(d_blocks, dlb);
+  launches += 4;
   CUDA_TRY(cudaGetLastError());
   kzg_count_launch(launches);
   return 0;

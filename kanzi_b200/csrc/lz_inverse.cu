@@ -47,11 +47,16 @@ __device__ __forceinline__ u32 lzi_apply(u32 sel, u32 f0, u32 f1) {      // g.se
 // the match-length records 32 at a time; tile loop 2 derives lengths, cursors, the repeat-offset state (a scan over
 // composable maps) and output offsets for all tokens.
 #define LZI_TT 1024
+#define LZI_WIN 16384
+#define LZI_KB 1024
 struct LziShared {
   u32 wsA[32], wsB[32];
   u32 wm0[32], wm1[32], ws0[32], ws1[32];
   u32 carryK, carryL, carryM, carryD, carryOut, rep0, rep1, totA, totB;
   int nExtL, nExtM, nExtLValid, nExtMValid, lastIdx, fail;
+  u32 winBase; int winJ, chaseDone;
+  u32 winK[LZI_KB];
+  u8 win[LZI_WIN + 16];
 };
 
 // exclusive scan of two values over the CTA (1024 threads); totals left in S.totA / S.totB
@@ -135,25 +140,9 @@ __global__ void __launch_bounds__(LZI_TT) lzi_tokens_kernel(KzgBlock* __restrict
   if (tid == 0) { S.nExtL = (int)S.carryL; S.nExtM = (int)S.carryM; S.nExtLValid = 0; S.nExtMValid = 0; }
   __syncthreads();
   // ---- the two cursor chains ----
-  if (warp == 0) {
-    if (lane == 0) {
-      const int nExtL = S.nExtL;
-      u32 E = 0; int j = 0;
-      for (; j < nExtL; j++) {
-        const u32 c = 13u + extK[j] + E;
-        if (c + 4 > (u32)count + 8) break;                      // beyond the block: whatever follows cannot be a live token
-        u32 r = src[c], sz;
-        if (r < 254) sz = 1;
-        else if (r == 254) { r += ((u32)src[c + 1] << 8) + (u32)src[c + 2]; sz = 3; }
-        else { r += ((u32)src[c + 1] << 16) + ((u32)src[c + 2] << 8) + (u32)src[c + 3]; sz = 4; }
-        const u32 len = 7 + r;
-        extE[j] = E; extLS[j] = len | (sz << 28);
-        E += len + sz;
-      }
-      extE[j] = E;
-      S.nExtLValid = j;
-    }
-  } else if (warp == 1) {
+  // warp 1 decodes the match-length records on its own; the other 31 warps stage windows of the literal area and of
+  // extK in shared memory so that thread 0's chase runs at shared-memory latency (named barrier 1, 992 threads)
+  if (warp == 1) {
     const int nExtM = S.nExtM;
     u32 c = (u32)mLenBase; int k = 0;
     while (k < nExtM) {
@@ -182,6 +171,45 @@ __global__ void __launch_bounds__(LZI_TT) lzi_tokens_kernel(KzgBlock* __restrict
       }
     }
     if (lane == 0) S.nExtMValid = k;
+  } else {
+    const int wtid = (warp == 0) ? tid : tid - 32;             // 0..991
+    const int nExtL = S.nExtL;
+    u32 E = 0; int j = 0;                                       // (thread 0)
+    bool stop = (nExtL == 0);
+    for (;;) {
+      if (tid == 0) {
+        if (!stop) {
+          const u32 c = 13u + extK[j] + E;
+          if (c + 4 > (u32)count + 8) stop = true;              // beyond the block: whatever follows cannot be a live token
+          S.winBase = c; S.winJ = j;
+        }
+        S.chaseDone = stop ? 1 : 0;
+      }
+      asm volatile("bar.sync 1, 992;" ::: "memory");
+      if (S.chaseDone) break;
+      const u32 wb = S.winBase; const int j0 = S.winJ;
+      for (int i = wtid; i < LZI_WIN + 8; i += 992) S.win[i] = (wb + i < (u32)count + 8) ? src[wb + i] : (u8)0;
+      for (int i = wtid; i < LZI_KB; i += 992) S.winK[i] = (j0 + i < nExtL) ? extK[j0 + i] : 0u;
+      asm volatile("bar.sync 1, 992;" ::: "memory");
+      if (tid == 0) {
+        while (j < nExtL && j - j0 < LZI_KB) {
+          const u32 c = 13u + S.winK[j - j0] + E;
+          if (c + 4 > wb + LZI_WIN + 8) break;                  // next window
+          if (c + 4 > (u32)count + 8) { stop = true; break; }
+          const u8* w = S.win + (c - wb);
+          u32 r = w[0], sz;
+          if (r < 254) sz = 1;
+          else if (r == 254) { r += ((u32)w[1] << 8) + (u32)w[2]; sz = 3; }
+          else { r += ((u32)w[1] << 16) + ((u32)w[2] << 8) + (u32)w[3]; sz = 4; }
+          const u32 len = 7 + r;
+          extE[j] = E; extLS[j] = len | (sz << 28);
+          E += len + sz;
+          j++;
+        }
+        if (j >= nExtL) stop = true;
+      }
+    }
+    if (tid == 0) { extE[j] = E; S.nExtLValid = j; }
   }
   __syncthreads();
   if (tid == 0) { S.carryK = 0; S.carryL = 0; S.carryM = 0; S.carryD = (u32)distBase; S.carryOut = 0; S.rep0 = (u32)count; S.rep1 = (u32)count; }
