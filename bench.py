@@ -175,10 +175,11 @@ def main():
     assert dec_dev(knz_len) == n
     assert torch.equal(d_back[:n], d_in[:n]), "GPU round trip mismatch"
     if rank == 0:
+        # the whole .knz the timed path produces must be the oracle's, byte for byte (bounded: the oracle is one CPU thread)
         import oracle_lib as O
-        chk = min(n, 2 * bs)
+        chk = n if n <= (256 << 20) else 8 * bs
         ref = O.compress(data[:chk], transforms, entropy, bs, bwt_bounds=flags)
-        got = K.compress(data[:chk], transforms, entropy, bs, flags=flags)
+        got = h_knz[:knz_len].numpy().tobytes() if chk == n else K.compress(data[:chk], transforms, entropy, bs, flags=flags)
         assert got == ref, "GPU .knz differs from the oracle's"
 
     l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
