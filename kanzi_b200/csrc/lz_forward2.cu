@@ -18,6 +18,8 @@
 #include "kzg_common.cuh"
 #include "kzg_transforms.cuh"
 #include <algorithm>
+#include <cstdlib>
+#include <cstdio>
 #include <vector>
 
 #define LZ_HASH_SEED 0x1E35A7BDull
@@ -30,7 +32,9 @@
 
 struct LzfBlock {                 // per-block scratch pointers (device)
   u32* hash;                      // hash of position p (16 or 19 bits)
-  u32* sa; u32* sa2;              // positions sorted by hash
+  u32* sa; u32* sa2;              // positions sorted by hash (radix ping-pong)
+  u32* hs;                        // the hash-sorted order kept: hs[i] = position | LZF_RUNSTART when it opens its hash class
+  u32* rank;                      // rank[p] = index of p in hs: the chain of p is hs[rank[p]-1], hs[rank[p]-2], ... (contiguous)
   u32* prev;                      // previous position with the same hash (0 = none)
   u8* len0;                       // findMatch(p, prev[p]) capped at 255, 0 if the candidate fails the pre-checks
   u32* skipped;                   // bitmap of positions the acceleration jumped over
@@ -140,6 +144,7 @@ __global__ void lzf_hash_kernel(const KzgBlock* __restrict__ blocks, LzfBlock* _
 // ---- phase 1b: stable LSD radix sort of positions by hash (8-bit digits) -----------------------------------------------------------
 // sort key of position s: a digit of its hash, or (second sort) of a 16-bit fingerprint of its first 4 bytes
 #define LZF_NOCAND 0x80000000u
+#define LZF_RUNSTART 0x80000000u
 __device__ __forceinline__ u32 lzf_fp(const u8* __restrict__ src, u32 s) { return (lzf_ld32(src + s) * 0x9E3779B1u) >> 16; }
 __device__ __forceinline__ int lzf_digit(const LzfBlock& L, const u8* __restrict__ src, u32 s, int shift, int useFp) {
   return (int)(((useFp ? lzf_fp(src, s) : L.hash[s]) >> shift) & 255);
@@ -231,6 +236,8 @@ __global__ void lzf_prev_kernel(LzfBlock* __restrict__ lb, int lastPass) {
     u32 pv = 0;
     if (i > 0) { const u32 q = sorted[i - 1]; if (L.hash[q] == L.hash[s]) pv = q; }
     L.prev[s] = pv;
+    L.hs[i] = s | (pv == 0 ? LZF_RUNSTART : 0u);
+    L.rank[s] = (u32)i;
   }
 }
 // ---- phase 1c: candidate match lengths ---------------------------------------------------------------------------------------------
@@ -619,17 +626,42 @@ __device__ __forceinline__ void lzf_core(const LzfBlock& L, const u8* __restrict
     if (q >= ownStart) return (q <= lastSkip) && (((__ldcg(D + (q >> 5)) >> (q & 31)) & 1u) != 0);
     return (q <= aHi) && (((__ldg(A + (q >> 5)) >> (q & 31)) & 1u) != 0);
   };
+  // First inserted entry of the chain of position x, given its first entry q0 = prev[x].  The chain is contiguous in hs[]
+  // (descending from rank[x] - 1), so past the first entry it is read four entries at a time and their states tested
+  // together instead of chasing prev[] one dependent load at a time.  cq: first entry before the segment (its state is an
+  // assumption); unsure: an entry above `limitPos` (this batch may still jump over it) stops the walk.
+  auto chain = [&](int q0, int x, int limitPos, int& cq, bool& unsure) -> int {
+    unsure = false;
+    if (q0 <= 0) return 0;
+    if (q0 > limitPos) { unsure = true; return 0; }
+    if (q0 < ownStart) cq = q0;
+    if (!skippedAt(q0)) return q0;
+    int i = (int)L.rank[x] - 1;               // index of q0 in hs
+    if (L.hs[i] & LZF_RUNSTART) return 0;
+    for (;;) {
+      // entries i-1 .. i-4 (older ones); stop at the one that opens the hash class
+      u32 e[4]; bool sk[4];
+      #pragma unroll
+      for (int k = 0; k < 4; k++) e[k] = (i - 1 - k >= 0) ? L.hs[i - 1 - k] : LZF_RUNSTART;
+      #pragma unroll
+      for (int k = 0; k < 4; k++) { const int q = (int)(e[k] & ~LZF_RUNSTART); sk[k] = (q > 0) && skippedAt(q); }
+      #pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int q = (int)(e[k] & ~LZF_RUNSTART);
+        if (q <= 0) return 0;
+        if (q < ownStart && cq == 0) cq = q;
+        if (!sk[k]) return q;
+        if (e[k] & LZF_RUNSTART) return 0;
+      }
+      i -= 4;
+    }
+  };
   auto cand = [&](int x) -> int {           // table content for position x: first inserted entry of the prev chain
     const u32 r = L.prev[x];
     if (r & LZF_NOCAND) return 0;             // no earlier occurrence of these 4 bytes: whatever the table holds fails the pre-check
-    int q = (int)r;
-    bool marked = false;
-    while (q > 0) {
-      if (q < ownStart && !marked) { atomicOr(&C[q >> 5], 1u << (q & 31)); marked = true; }   // (all lanes, same address)
-      const int nq = (int)(L.prev[q] & ~LZF_NOCAND);
-      if (!skippedAt(q)) break;
-      q = nq;
-    }
+    int cq = 0; bool unsure;
+    const int q = chain((int)r, x, 0x7FFFFFFF, cq, unsure);
+    if (cq > 0) atomicOr(&C[cq >> 5], 1u << (cq & 31));        // (all lanes, same address)
     return q;
   };
   auto markSkipped = [&](int lo, int hi) {  // called by one lane: positions lo..hi were jumped over
@@ -678,15 +710,8 @@ __device__ __forceinline__ void lzf_core(const LzfBlock& L, const u8* __restrict
       if (repRef > 0) repSmall = (maxM < 8) ? 0 : ((diff == 0) ? 8 : ((__ffsll((long long)diff) - 1) >> 3));
       // every lane walks its own chain past jumped-over entries; an entry this very batch may jump over is left for later
       const bool inBatch = ((srcInc + 31) >> 6) > 0;
-      int q = (pvRaw & LZF_NOCAND) ? 0 : pv;  // flagged: nothing the table can hold passes the 4-byte pre-check
-      bool unsure = false;
-      while (q > 0) {
-        if (inBatch && q > srcIdx) { unsure = true; break; }
-        if (q < ownStart && cq == 0) cq = q;
-        const int nq = (int)(L.prev[q] & ~LZF_NOCAND);
-        if (!skippedAt(q)) break;
-        q = nq;
-      }
+      bool unsure = false;                    // flagged: nothing the table can hold passes the 4-byte pre-check
+      const int q = (pvRaw & LZF_NOCAND) ? 0 : chain(pv, p, inBatch ? srcIdx : 0x7FFFFFFF, cq, unsure);
       bool tableHit;
       if (unsure) tableHit = true;
       else if (pvRaw & LZF_NOCAND) { cnd = 0; tableHit = false; }
@@ -890,7 +915,16 @@ __global__ void __launch_bounds__(32) lzf_spec_kernel(const KzgBlock* __restrict
   } else if (s > 0) {
     // warm-up: parse the tail of the previous segment so that the state at the segment start is, most of the time,
     // already the reference's (greedy parses re-synchronise within a few matches); nothing of it is kept but the state
-    st.srcIdx = st.anchor = max(segStart - LZF_WARMUP, 0);
+    // (where matches are sparse — few positions of the last 2 KiB have a table candidate — two parses meet less often:
+    // take a longer run-up there)
+    int cnt = 0;
+    for (int q = segStart - LZF_WARMUP + lane * 4; q < segStart; q += 128) {
+      const u32 w = *reinterpret_cast<const u32*>(L.len0 + q);
+      cnt += __popc(__vcmpgeu4(w, 0x04040404u)) >> 3;
+    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+    const int warm = (cnt < LZF_WARMUP / 5) ? 4 * LZF_WARMUP : LZF_WARMUP;
+    st.srcIdx = st.anchor = max(segStart - warm, 0);
     lzf_core<EXTRA>(L, src, st, segStart, L.A, min(L.aMax, segStart - 1), segStart, L.D, L.C, segStart, dEnd, ev, nEv, L.evStride, fail, lane, ns);
     nEv = 0;
   }
@@ -1027,8 +1061,10 @@ __device__ __forceinline__ int lzf_resolve(const LzfBlock& L, const u32* __restr
   while (q > 0 && ((X[q >> 5] >> (q & 31)) & 1u)) q = (int)(L.prev[q] & ~LZF_NOCAND);
   return q;
 }
-__global__ void __launch_bounds__(1024) lzf_check_kernel(LzfBlock* __restrict__ lb, int lastRound, int* __restrict__ nActive) {
+__global__ void __launch_bounds__(1024) lzf_check_kernel(LzfBlock* __restrict__ lb, int lastRound, int* __restrict__ nActive, int dbg) {
   __shared__ int sDiff, sMax;
+  __shared__ int dBits, dBad, dMin, dMax, dMarks;
+  if (threadIdx.x == 0) { dBits = 0; dBad = 0; dMin = 0x7FFFFFFF; dMax = -1; dMarks = 0; }
   LzfBlock& L = lb[blockIdx.x];
   if (L.n <= 0 || !L.active) return;
   if (threadIdx.x == 0) { sDiff = 0; sMax = -1; }
@@ -1037,7 +1073,7 @@ __global__ void __launch_bounds__(1024) lzf_check_kernel(LzfBlock* __restrict__ 
   int same = 1, mx = -1;
   for (int i = threadIdx.x; i < nW; i += blockDim.x) {
     const u32 k = L.Kn[i], a = L.A[i];
-    if (k != a) same = 0;
+    if (k != a) { same = 0; if (dbg & 1) atomicAdd(&dBits, __popc(k ^ a)); }
     if (k) mx = i * 32 + 31 - __clz(k);
   }
   if (!same) sDiff = 1;
@@ -1049,17 +1085,23 @@ __global__ void __launch_bounds__(1024) lzf_check_kernel(LzfBlock* __restrict__ 
     if (threadIdx.x == 0) sDiff = 0;
     __syncthreads();
     int bad = 0;
-    for (int i = threadIdx.x; i < nW && !bad; i += blockDim.x) {
+    for (int i = threadIdx.x; i < nW && (!bad || (dbg & 1)); i += blockDim.x) {
       u32 c = L.C[i];
+      if (dbg & 1) atomicAdd(&dMarks, __popc(c));
       while (c) {
         const int q = i * 32 + __ffs(c) - 1;
         c &= c - 1;
-        if (lzf_resolve(L, L.A, q) != lzf_resolve(L, L.Kn, q)) { bad = 1; break; }
+        if (lzf_resolve(L, L.A, q) != lzf_resolve(L, L.Kn, q)) {
+          bad = 1;
+          if (dbg & 1) { atomicAdd(&dBad, 1); atomicMin(&dMin, q); atomicMax(&dMax, q); } else break;
+        }
       }
     }
     if (bad) sDiff = 1;
     __syncthreads();
   }
+  if ((dbg & 1) && threadIdx.x == 0 && differ)
+    printf("lzf check block %d: %d bits differ, %d marks, %d bad marks in [%d, %d], Kn max %d\n", (int)blockIdx.x, dBits, dMarks, dBad, dMin, dMax, sMax);
   if (threadIdx.x == 0) {
     if (L.needSerial) { L.active = 0; }
     else if (!sDiff) { L.active = 0; }
@@ -1274,16 +1316,30 @@ static LzfSizes lzf_sizes(i32 maxLen) {
   z.hash = lzf_al(4 * n); z.sa = lzf_al(4 * n); z.prev = lzf_al(4 * n); z.len0 = lzf_al(n); z.skipped = lzf_al(n / 8 + 64);
   z.hist = lzf_al(4 * 256 * nT);
   z.tk = lzf_al(std::max<size_t>(n / 5, 256) + 64); z.m = lzf_al(n + 64); z.ml = lzf_al(n / 2 + 64);
-  z.segLen = std::max(32768, (int)((n / 512 + 4095) / 4096 * 4096));
+  static const int segMin = getenv("KZG_LZ_SEG") ? std::max(8192, atoi(getenv("KZG_LZ_SEG")) / 4096 * 4096) : 32768;   // developer knob
+  z.segLen = std::max(segMin, (int)((n / 512 + 4095) / 4096 * 4096));
   z.maxSeg = (int)((n + z.segLen - 1) / z.segLen);
   z.evStride = z.segLen / 4 + 16;
   z.patchCap = (int)(n / 4 + 64);
   z.spec = lzf_al((size_t)z.maxSeg * z.evStride * sizeof(uint4)); z.patch = lzf_al((size_t)z.patchCap * sizeof(uint4));
   z.seg = lzf_al((size_t)z.maxSeg * sizeof(LzfSeg)); z.rng = lzf_al((size_t)(2 * z.maxSeg + 4) * sizeof(LzfRange));
-  z.total = z.hash + 2 * z.sa + z.prev + z.len0 + 5 * z.skipped + 2 * z.hist + z.tk + z.m + z.ml + z.spec + z.patch + z.seg + z.rng + 1024;
+  z.total = z.hash + 4 * z.sa + z.prev + z.len0 + 5 * z.skipped + 2 * z.hist + z.tk + z.m + z.ml + z.spec + z.patch + z.seg + z.rng + 1024;
   return z;
 }
 void kzg_lzf_scratch(i32 maxLen, size_t* perBlockBytes) { *perBlockBytes = std::max(*perBlockBytes, lzf_sizes(maxLen).total + sizeof(LzfBlock) + 256 + 1024); }
+
+// developer aid (KZG_DEBUG bit 4): per-phase times of one launch
+struct LzfTimer {
+  cudaStream_t s; bool on; std::vector<cudaEvent_t> ev; std::vector<const char*> name;
+  LzfTimer(cudaStream_t st, bool o) : s(st), on(o) { mark("start"); }
+  void mark(const char* n) { if (!on) return; cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); ev.push_back(e); name.push_back(n); }
+  void report() {
+    if (!on) return;
+    cudaStreamSynchronize(s);
+    for (size_t i = 1; i < ev.size(); i++) { float ms = 0; cudaEventElapsedTime(&ms, ev[i - 1], ev[i]); fprintf(stderr, "  lzf %-10s %8.3f ms\n", name[i], ms); }
+    for (auto e : ev) cudaEventDestroy(e);
+  }
+};
 
 int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, const KzgXfParams& P, bool extra, i32 maxLen) {
   const LzfSizes z = lzf_sizes(maxLen);
@@ -1297,7 +1353,7 @@ int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
     u8* o = base + (size_t)b * z.total;
     LzfBlock& L = hl[b];
     memset(&L, 0, sizeof(L));
-    L.hash = (u32*)o; o += z.hash; L.sa = (u32*)o; o += z.sa; L.sa2 = (u32*)o; o += z.sa; L.prev = (u32*)o; o += z.prev;
+    L.hash = (u32*)o; o += z.hash; L.sa = (u32*)o; o += z.sa; L.sa2 = (u32*)o; o += z.sa; L.hs = (u32*)o; o += z.sa; L.rank = (u32*)o; o += z.sa; L.prev = (u32*)o; o += z.prev;
     L.len0 = o; o += z.len0; L.skipped = (u32*)o; o += z.skipped; L.hist = (u32*)o; o += z.hist; L.offs = (u32*)o; o += z.hist;
     L.tk = o; o += z.tk; L.m = o; o += z.m; L.ml = o; o += z.ml;
     L.mCap = (i32)z.m - 16; L.mlCap = (i32)z.ml - 16;
@@ -1311,6 +1367,7 @@ int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
   CUDA_TRY(cudaMemcpyAsync(dlb, hl.data(), sizeof(LzfBlock) * nb, cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaStreamSynchronize(s));          // hl is stack-owned
   const int dbg = P.flags >> 12;
+  LzfTimer tm(s, (dbg & 16) != 0);
   lzf_setup_kernel<<<(nBlocks + 63) / 64, 64, 0, s>>>(d_blocks, nBlocks, P, dlb, z.segLen, (dbg & 8) ? 1 : 0);
   const int gx = std::max(1, std::min((maxLen + 255) / 256, 8 * KZG_SM_COUNT));
   if (extra) lzf_hash_kernel<true><<<dim3(gx, nBlocks), 256, 0, s>>>(d_blocks, dlb);
@@ -1324,6 +1381,7 @@ int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
     lzf_scan_kernel<<<nBlocks, 1024, 0, s>>>(dlb);
     lzf_scatter_kernel<<<gridT, 32 * LZF_WARPS, 0, s>>>(d_blocks, dlb, shift, pass, 0);
   }
+  tm.mark("sort1");
   lzf_prev_kernel<<<dim3(gx, nBlocks), 256, 0, s>>>(dlb, pass - 1);
   lzf_cand_kernel<<<dim3(gx, nBlocks), 256, 0, s>>>(d_blocks, dlb);
   for (int shift = 0; shift < 16; shift += 8, pass++) {   // second sort key: the 4-byte fingerprint
@@ -1332,6 +1390,7 @@ int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
     lzf_scatter_kernel<<<gridT, 32 * LZF_WARPS, 0, s>>>(d_blocks, dlb, shift, pass, 1);
   }
   lzf_flag_kernel<<<dim3(gx, nBlocks), 256, 0, s>>>(d_blocks, dlb, pass - 1);
+  tm.mark("sort2");
   int launches = 6 + 3 * pass;
   // phase 2/3: speculative segments + stitch, repeated until the assumed skipped-position bitmap is the produced one
   int* dCnt = (int*)(base + nb * z.total);
@@ -1343,12 +1402,17 @@ int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
       rounds++;
       CUDA_TRY(cudaMemsetAsync(dCnt, 0, 2 * sizeof(int), s));
       lzf_round_init_kernel<<<dim3(std::min(gx, 64), nBlocks), 256, 0, s>>>(dlb, round == 0 ? 1 : 0);
-      if (extra) { lzf_spec_kernel<true><<<dim3(z.maxSeg, nBlocks), 32, 0, s>>>(d_blocks, dlb); lzf_stitch_kernel<true><<<nBlocks, 32, 0, s>>>(d_blocks, dlb, dbg); }
-      else { lzf_spec_kernel<false><<<dim3(z.maxSeg, nBlocks), 32, 0, s>>>(d_blocks, dlb); lzf_stitch_kernel<false><<<nBlocks, 32, 0, s>>>(d_blocks, dlb, dbg); }
-      lzf_check_kernel<<<nBlocks, 1024, 0, s>>>(dlb, round == maxRounds - 1 ? 1 : 0, dCnt);
+      if (extra) lzf_spec_kernel<true><<<dim3(z.maxSeg, nBlocks), 32, 0, s>>>(d_blocks, dlb);
+      else lzf_spec_kernel<false><<<dim3(z.maxSeg, nBlocks), 32, 0, s>>>(d_blocks, dlb);
+      tm.mark("spec");
+      if (extra) lzf_stitch_kernel<true><<<nBlocks, 32, 0, s>>>(d_blocks, dlb, dbg);
+      else lzf_stitch_kernel<false><<<nBlocks, 32, 0, s>>>(d_blocks, dlb, dbg);
+      tm.mark("stitch");
+      lzf_check_kernel<<<nBlocks, 1024, 0, s>>>(dlb, round == maxRounds - 1 ? 1 : 0, dCnt, dbg);
       launches += 4;
       CUDA_TRY(cudaMemcpyAsync(hCnt, dCnt, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
       CUDA_TRY(cudaStreamSynchronize(s));
+      tm.mark("check");
       if (hCnt[0] == 0) break;
     }
   }
@@ -1364,6 +1428,8 @@ int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
   lzf_emit_scan_kernel<<<nBlocks, LZF_ET, 0, s>>>(d_blocks, P, dlb);
   lzf_emit_write_kernel<<<dim3(evTiles, nBlocks), LZF_ET, 0, s>>>(d_blocks, dlb);
   launches += 4;
+  tm.mark("emit");
+  tm.report();
   CUDA_TRY(cudaGetLastError());
   kzg_count_launch(launches);
   return 0;
