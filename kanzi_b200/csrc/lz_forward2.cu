@@ -31,8 +31,7 @@
 #define LZF_WARPS 8
 
 struct LzfBlock {                 // per-block scratch pointers (device)
-  u32* hash;                      // hash of position p (16 or 19 bits)
-  u32* sa; u32* sa2;              // positions sorted by hash (radix ping-pong)
+  u64* ka; u64* kb;               // radix ping-pong of (sort key << 30 | position); key = hash | fingerprint << hash bits
   u32* hs;                        // the hash-sorted order kept: hs[i] = position | LZF_RUNSTART when it opens its hash class
   u32* rank;                      // rank[p] = index of p in hs: the chain of p is hs[rank[p]-1], hs[rank[p]-2], ... (contiguous)
   u32* prev;                      // previous position with the same hash (0 = none)
@@ -135,22 +134,22 @@ __global__ void lzf_hash_kernel(const KzgBlock* __restrict__ blocks, LzfBlock* _
   const int n = L.n;
   const u8* __restrict__ src = blocks[blockIdx.y].cur;
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
-    const u64 v = (lzf_ld64(src + p) << 24) * LZ_HASH_SEED;             // LZCodec.java:904-911
-    L.hash[p] = (u32)(v >> (EXTRA ? (64 - 19) : (64 - 16)));
+    const u64 w = lzf_ld64(src + p);
+    const u64 v = (w << 24) * LZ_HASH_SEED;                              // LZCodec.java:904-911
+    const u64 hash = v >> (EXTRA ? (64 - 19) : (64 - 16));
+    // 16-bit (13 with the 19-bit hash) fingerprint of the first 4 bytes: second sort key
+    const u64 fp = ((u32)w * 0x9E3779B1u) >> (EXTRA ? 19 : 16);
+    L.ka[p] = ((hash | (fp << (EXTRA ? 19 : 16))) << 30) | (u64)p;
   }
   if (blockIdx.x == 0) for (int i = threadIdx.x; i < (n + 31) / 32 + 2; i += blockDim.x) { L.skipped[i] = 0; L.A[i] = 0; }
 }
 
 // ---- phase 1b: stable LSD radix sort of positions by hash (8-bit digits) -----------------------------------------------------------
-// sort key of position s: a digit of its hash, or (second sort) of a 16-bit fingerprint of its first 4 bytes
+// elements carry their key, so every pass streams: pass k reads ka (k even) or kb (k odd) and writes the other one
 #define LZF_NOCAND 0x80000000u
 #define LZF_RUNSTART 0x80000000u
-__device__ __forceinline__ u32 lzf_fp(const u8* __restrict__ src, u32 s) { return (lzf_ld32(src + s) * 0x9E3779B1u) >> 16; }
-__device__ __forceinline__ int lzf_digit(const LzfBlock& L, const u8* __restrict__ src, u32 s, int shift, int useFp) {
-  return (int)(((useFp ? lzf_fp(src, s) : L.hash[s]) >> shift) & 255);
-}
-// pass k reads identity (k == 0), sa (k odd) or sa2 (k even) and writes sa (k even) or sa2 (k odd)
-__global__ void __launch_bounds__(32 * LZF_WARPS) lzf_hist_kernel(const KzgBlock* __restrict__ blocks, LzfBlock* __restrict__ lb, int shift, int k, int useFp) {
+#define LZF_POSMASK ((1ull << 30) - 1)
+__global__ void __launch_bounds__(32 * LZF_WARPS) lzf_hist_kernel(LzfBlock* __restrict__ lb, int shift, int mask, int k) {
   __shared__ u32 cnt[LZF_WARPS][256];
   const LzfBlock& L = lb[blockIdx.y];
   const int n = L.n;
@@ -161,12 +160,8 @@ __global__ void __launch_bounds__(32 * LZF_WARPS) lzf_hist_kernel(const KzgBlock
   for (int i = lane; i < 256; i += 32) cnt[warp][i] = 0;
   __syncwarp();
   const int beg = tile * LZF_WT, end = min(beg + LZF_WT, n);
-  const u8* __restrict__ src = blocks[blockIdx.y].cur;
-  const u32* __restrict__ in = (k & 1) ? L.sa : L.sa2;
-  for (int i = beg + lane; i < end; i += 32) {
-    const u32 s = (k == 0) ? (u32)i : in[i];
-    atomicAdd(&cnt[warp][lzf_digit(L, src, s, shift, useFp)], 1u);
-  }
+  const u64* __restrict__ in = (k & 1) ? L.kb : L.ka;
+  for (int i = beg + lane; i < end; i += 32) atomicAdd(&cnt[warp][(int)(in[i] >> shift) & mask], 1u);
   __syncwarp();
   for (int d = lane; d < 256; d += 32) L.hist[(size_t)d * nT + tile] = cnt[warp][d];
 }
@@ -199,7 +194,7 @@ __global__ void __launch_bounds__(1024) lzf_scan_kernel(LzfBlock* __restrict__ l
     __syncthreads();
   }
 }
-__global__ void __launch_bounds__(32 * LZF_WARPS) lzf_scatter_kernel(const KzgBlock* __restrict__ blocks, LzfBlock* __restrict__ lb, int shift, int k, int useFp) {
+__global__ void __launch_bounds__(32 * LZF_WARPS) lzf_scatter_kernel(LzfBlock* __restrict__ lb, int shift, int mask, int k) {
   __shared__ u32 pos[LZF_WARPS][256];
   const LzfBlock& L = lb[blockIdx.y];
   const int n = L.n;
@@ -211,30 +206,31 @@ __global__ void __launch_bounds__(32 * LZF_WARPS) lzf_scatter_kernel(const KzgBl
   __syncwarp();
   const int beg = tile * LZF_WT, end = min(beg + LZF_WT, n);
   const u32 lower = (1u << lane) - 1;
-  const u8* __restrict__ src = blocks[blockIdx.y].cur;
-  const u32* __restrict__ in = (k & 1) ? L.sa : L.sa2;
-  u32* __restrict__ out = (k & 1) ? L.sa2 : L.sa;
+  const u64* __restrict__ in = (k & 1) ? L.kb : L.ka;
+  u64* __restrict__ out = (k & 1) ? L.ka : L.kb;
   for (int base = beg; base < end; base += 32) {
     const int i = base + lane;
     const bool on = i < end;
-    u32 s = 0; int d = 256 + lane;
-    if (on) { s = (k == 0) ? (u32)i : in[i]; d = lzf_digit(L, src, s, shift, useFp); }
+    u64 v = 0; int d = 256 + lane;
+    if (on) { v = in[i]; d = (int)(v >> shift) & mask; }
     const u32 peers = __match_any_sync(0xFFFFFFFFu, d);
-    if (on) out[pos[warp][d] + __popc(peers & lower)] = s;
+    if (on) out[pos[warp][d] + __popc(peers & lower)] = v;
     __syncwarp();
     if (on && (peers >> lane) <= 1u) pos[warp][d] += __popc(peers);
     __syncwarp();
   }
 }
-// sorted[i-1] precedes sorted[i] in (hash, position) order: same hash -> it is the previous occurrence
-__global__ void lzf_prev_kernel(LzfBlock* __restrict__ lb, int lastPass) {
+// after the hash passes: sorted[i-1] precedes sorted[i] in (hash, position) order: same hash -> it is the previous occurrence
+__global__ void lzf_prev_kernel(LzfBlock* __restrict__ lb, int nPass, int hashBits) {
   const LzfBlock& L = lb[blockIdx.y];
   const int n = L.n;
-  const u32* __restrict__ sorted = (lastPass & 1) ? L.sa2 : L.sa;
+  const u64* __restrict__ sorted = (nPass & 1) ? L.kb : L.ka;
+  const u64 hmask = ((1ull << hashBits) - 1) << 30;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const u32 s = sorted[i];
+    const u64 v = sorted[i];
+    const u32 s = (u32)(v & LZF_POSMASK);
     u32 pv = 0;
-    if (i > 0) { const u32 q = sorted[i - 1]; if (L.hash[q] == L.hash[s]) pv = q; }
+    if (i > 0) { const u64 w = sorted[i - 1]; if (((w ^ v) & hmask) == 0) pv = (u32)(w & LZF_POSMASK); }
     L.prev[s] = pv;
     L.hs[i] = s | (pv == 0 ? LZF_RUNSTART : 0u);
     L.rank[s] = (u32)i;
@@ -258,16 +254,14 @@ __global__ void lzf_cand_kernel(const KzgBlock* __restrict__ blocks, LzfBlock* _
 // After the second sort (fingerprint, hash, position): a position whose predecessor differs in hash or fingerprint has no
 // earlier occurrence of its first 4 bytes among the positions with its hash, so no table content can ever pass the 4-byte
 // pre-check there (:389-395, :405-422 need bestLen >= 4).  Those positions never need the table: flag them in prev[].
-__global__ void lzf_flag_kernel(const KzgBlock* __restrict__ blocks, LzfBlock* __restrict__ lb, int lastPass) {
+__global__ void lzf_flag_kernel(LzfBlock* __restrict__ lb, int nPass) {
   const LzfBlock& L = lb[blockIdx.y];
   const int n = L.n;
-  const u8* __restrict__ src = blocks[blockIdx.y].cur;
-  const u32* __restrict__ sorted = (lastPass & 1) ? L.sa2 : L.sa;
+  const u64* __restrict__ sorted = (nPass & 1) ? L.kb : L.ka;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const u32 s = sorted[i];
-    bool has = false;
-    if (i > 0) { const u32 q = sorted[i - 1]; has = (L.hash[q] == L.hash[s]) && (lzf_fp(src, q) == lzf_fp(src, s)); }
-    if (!has) L.prev[s] |= LZF_NOCAND;
+    const u64 v = sorted[i];
+    const bool has = (i > 0) && ((sorted[i - 1] >> 30) == (v >> 30));
+    if (!has) L.prev[(u32)(v & LZF_POSMASK)] |= LZF_NOCAND;
   }
 }
 
@@ -627,7 +621,7 @@ __device__ __forceinline__ void lzf_core(const LzfBlock& L, const u8* __restrict
     return (q <= aHi) && (((__ldg(A + (q >> 5)) >> (q & 31)) & 1u) != 0);
   };
   // First inserted entry of the chain of position x, given its first entry q0 = prev[x].  The chain is contiguous in hs[]
-  // (descending from rank[x] - 1), so past the first entry it is read four entries at a time and their states tested
+  // (descending from rank[x] - 1), so past the first entry it is read eight entries at a time and their states tested
   // together instead of chasing prev[] one dependent load at a time.  cq: first entry before the segment (its state is an
   // assumption); unsure: an entry above `limitPos` (this batch may still jump over it) stops the walk.
   auto chain = [&](int q0, int x, int limitPos, int& cq, bool& unsure) -> int {
@@ -639,21 +633,21 @@ __device__ __forceinline__ void lzf_core(const LzfBlock& L, const u8* __restrict
     int i = (int)L.rank[x] - 1;               // index of q0 in hs
     if (L.hs[i] & LZF_RUNSTART) return 0;
     for (;;) {
-      // entries i-1 .. i-4 (older ones); stop at the one that opens the hash class
-      u32 e[4]; bool sk[4];
+      // entries i-1 .. i-8 (older ones); stop at the one that opens the hash class
+      u32 e[8]; bool sk[8];
       #pragma unroll
-      for (int k = 0; k < 4; k++) e[k] = (i - 1 - k >= 0) ? L.hs[i - 1 - k] : LZF_RUNSTART;
+      for (int k = 0; k < 8; k++) e[k] = (i - 1 - k >= 0) ? L.hs[i - 1 - k] : LZF_RUNSTART;
       #pragma unroll
-      for (int k = 0; k < 4; k++) { const int q = (int)(e[k] & ~LZF_RUNSTART); sk[k] = (q > 0) && skippedAt(q); }
+      for (int k = 0; k < 8; k++) { const int q = (int)(e[k] & ~LZF_RUNSTART); sk[k] = (q > 0) && skippedAt(q); }
       #pragma unroll
-      for (int k = 0; k < 4; k++) {
+      for (int k = 0; k < 8; k++) {
         const int q = (int)(e[k] & ~LZF_RUNSTART);
         if (q <= 0) return 0;
         if (q < ownStart && cq == 0) cq = q;
         if (!sk[k]) return q;
         if (e[k] & LZF_RUNSTART) return 0;
       }
-      i -= 4;
+      i -= 8;
     }
   };
   auto cand = [&](int x) -> int {           // table content for position x: first inserted entry of the prev chain
@@ -1308,12 +1302,12 @@ __global__ void __launch_bounds__(LZF_ET) lzf_emit_write_kernel(KzgBlock* __rest
 
 // ---- host ------------------------------------------------------------------------------------------------------------------------------
 static size_t lzf_al(size_t v) { return (v + 255) / 256 * 256; }
-struct LzfSizes { size_t hash, sa, prev, len0, skipped, hist, tk, m, ml, spec, patch, seg, rng, total; int segLen, maxSeg, evStride, patchCap; };
+struct LzfSizes { size_t key, sa, prev, len0, skipped, hist, tk, m, ml, spec, patch, seg, rng, total; int segLen, maxSeg, evStride, patchCap; };
 static LzfSizes lzf_sizes(i32 maxLen) {
   LzfSizes z;
   const size_t n = (size_t)maxLen + 64;
   const size_t nT = (n + LZF_WT - 1) / LZF_WT;
-  z.hash = lzf_al(4 * n); z.sa = lzf_al(4 * n); z.prev = lzf_al(4 * n); z.len0 = lzf_al(n); z.skipped = lzf_al(n / 8 + 64);
+  z.key = lzf_al(8 * n); z.sa = lzf_al(4 * n); z.prev = lzf_al(4 * n); z.len0 = lzf_al(n); z.skipped = lzf_al(n / 8 + 64);
   z.hist = lzf_al(4 * 256 * nT);
   z.tk = lzf_al(std::max<size_t>(n / 5, 256) + 64); z.m = lzf_al(n + 64); z.ml = lzf_al(n / 2 + 64);
   static const int segMin = getenv("KZG_LZ_SEG") ? std::max(8192, atoi(getenv("KZG_LZ_SEG")) / 4096 * 4096) : 32768;   // developer knob
@@ -1323,7 +1317,7 @@ static LzfSizes lzf_sizes(i32 maxLen) {
   z.patchCap = (int)(n / 4 + 64);
   z.spec = lzf_al((size_t)z.maxSeg * z.evStride * sizeof(uint4)); z.patch = lzf_al((size_t)z.patchCap * sizeof(uint4));
   z.seg = lzf_al((size_t)z.maxSeg * sizeof(LzfSeg)); z.rng = lzf_al((size_t)(2 * z.maxSeg + 4) * sizeof(LzfRange));
-  z.total = z.hash + 4 * z.sa + z.prev + z.len0 + 5 * z.skipped + 2 * z.hist + z.tk + z.m + z.ml + z.spec + z.patch + z.seg + z.rng + 1024;
+  z.total = 2 * z.key + 2 * z.sa + z.prev + z.len0 + 5 * z.skipped + 2 * z.hist + z.tk + z.m + z.ml + z.spec + z.patch + z.seg + z.rng + 1024;
   return z;
 }
 void kzg_lzf_scratch(i32 maxLen, size_t* perBlockBytes) { *perBlockBytes = std::max(*perBlockBytes, lzf_sizes(maxLen).total + sizeof(LzfBlock) + 256 + 1024); }
@@ -1353,7 +1347,7 @@ int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
     u8* o = base + (size_t)b * z.total;
     LzfBlock& L = hl[b];
     memset(&L, 0, sizeof(L));
-    L.hash = (u32*)o; o += z.hash; L.sa = (u32*)o; o += z.sa; L.sa2 = (u32*)o; o += z.sa; L.hs = (u32*)o; o += z.sa; L.rank = (u32*)o; o += z.sa; L.prev = (u32*)o; o += z.prev;
+    L.ka = (u64*)o; o += z.key; L.kb = (u64*)o; o += z.key; L.hs = (u32*)o; o += z.sa; L.rank = (u32*)o; o += z.sa; L.prev = (u32*)o; o += z.prev;
     L.len0 = o; o += z.len0; L.skipped = (u32*)o; o += z.skipped; L.hist = (u32*)o; o += z.hist; L.offs = (u32*)o; o += z.hist;
     L.tk = o; o += z.tk; L.m = o; o += z.m; L.ml = o; o += z.ml;
     L.mCap = (i32)z.m - 16; L.mlCap = (i32)z.ml - 16;
@@ -1361,7 +1355,7 @@ int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
     L.specEv = (uint4*)o; o += z.spec; L.patchEv = (uint4*)o; o += z.patch;
     L.seg = (LzfSeg*)o; o += z.seg; L.rng = (LzfRange*)o; o += z.rng;
     L.evStride = z.evStride; L.patchCap = z.patchCap;
-    L.fin = (uint4*)L.hash;                     // (hashes and radix scratch are dead once prev[] and its flags exist)
+    L.fin = (uint4*)L.ka;                       // (the radix buffers are dead once prev[] and its flags exist)
     L.tileSum = L.hist;
   }
   CUDA_TRY(cudaMemcpyAsync(dlb, hl.data(), sizeof(LzfBlock) * nb, cudaMemcpyHostToDevice, s));
@@ -1374,22 +1368,24 @@ int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
   else lzf_hash_kernel<false><<<dim3(gx, nBlocks), 256, 0, s>>>(d_blocks, dlb);
   const int nT = (maxLen + LZF_WT - 1) / LZF_WT;
   dim3 gridT((nT + LZF_WARPS - 1) / LZF_WARPS, nBlocks);
-  const int bits = extra ? 19 : 16;
+  const int bits = extra ? 19 : 16, fpBits = extra ? 13 : 16;
   int pass = 0;
   for (int shift = 0; shift < bits; shift += 8, pass++) {
-    lzf_hist_kernel<<<gridT, 32 * LZF_WARPS, 0, s>>>(d_blocks, dlb, shift, pass, 0);
+    const int mask = (1 << std::min(8, bits - shift)) - 1;
+    lzf_hist_kernel<<<gridT, 32 * LZF_WARPS, 0, s>>>(dlb, 30 + shift, mask, pass);
     lzf_scan_kernel<<<nBlocks, 1024, 0, s>>>(dlb);
-    lzf_scatter_kernel<<<gridT, 32 * LZF_WARPS, 0, s>>>(d_blocks, dlb, shift, pass, 0);
+    lzf_scatter_kernel<<<gridT, 32 * LZF_WARPS, 0, s>>>(dlb, 30 + shift, mask, pass);
   }
   tm.mark("sort1");
-  lzf_prev_kernel<<<dim3(gx, nBlocks), 256, 0, s>>>(dlb, pass - 1);
+  lzf_prev_kernel<<<dim3(gx, nBlocks), 256, 0, s>>>(dlb, pass, bits);
   lzf_cand_kernel<<<dim3(gx, nBlocks), 256, 0, s>>>(d_blocks, dlb);
-  for (int shift = 0; shift < 16; shift += 8, pass++) {   // second sort key: the 4-byte fingerprint
-    lzf_hist_kernel<<<gridT, 32 * LZF_WARPS, 0, s>>>(d_blocks, dlb, shift, pass, 1);
+  for (int shift = 0; shift < fpBits; shift += 8, pass++) {   // second sort key: the 4-byte fingerprint
+    const int mask = (1 << std::min(8, fpBits - shift)) - 1;
+    lzf_hist_kernel<<<gridT, 32 * LZF_WARPS, 0, s>>>(dlb, 30 + bits + shift, mask, pass);
     lzf_scan_kernel<<<nBlocks, 1024, 0, s>>>(dlb);
-    lzf_scatter_kernel<<<gridT, 32 * LZF_WARPS, 0, s>>>(d_blocks, dlb, shift, pass, 1);
+    lzf_scatter_kernel<<<gridT, 32 * LZF_WARPS, 0, s>>>(dlb, 30 + bits + shift, mask, pass);
   }
-  lzf_flag_kernel<<<dim3(gx, nBlocks), 256, 0, s>>>(d_blocks, dlb, pass - 1);
+  lzf_flag_kernel<<<dim3(gx, nBlocks), 256, 0, s>>>(dlb, pass);
   tm.mark("sort2");
   int launches = 6 + 3 * pass;
   // phase 2/3: speculative segments + stitch, repeated until the assumed skipped-position bitmap is the produced one
