@@ -24,6 +24,7 @@ struct Workspace {
   cudaStream_t stream = nullptr;
   u8* dArena = nullptr; size_t dCap = 0, dOff = 0;
   u8* hPinned = nullptr; size_t hCap = 0, hOff = 0;
+  u8* ioBuf[2] = {nullptr, nullptr}; size_t ioCap[2] = {0, 0};      // device copies of the host-buffer entry points' streams (grow-only)
   i64 launches = 0;
   char err[512] = {0};
 };
@@ -50,6 +51,17 @@ static int ws_init() {
   CUDA_TRY(cudaStreamCreateWithFlags(&W.stream, cudaStreamNonBlocking));
   W.init = true;
   return 0;
+}
+
+// device staging for kzg_compress / kzg_decompress (host buffers): kept between calls, cudaMalloc/cudaFree cost milliseconds each
+static u8* ws_io(int which, size_t bytes) {
+  if (bytes > W.ioCap[which]) {
+    if (W.ioBuf[which]) { cudaStreamSynchronize(W.stream); cudaFree(W.ioBuf[which]); W.ioBuf[which] = nullptr; W.ioCap[which] = 0; }
+    const size_t want = bytes + bytes / 16 + (1 << 20);
+    if (cudaMalloc((void**)&W.ioBuf[which], want) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    W.ioCap[which] = want;
+  }
+  return W.ioBuf[which];
 }
 
 static int ws_reserve(size_t dBytes, size_t hBytes) {
@@ -734,11 +746,9 @@ int64_t kzg_compress(const uint8_t* in, int64_t n, const int32_t* transforms, in
   int r = ws_init(); if (r < 0) return r;
   if (n < 0 || (n > 0 && in == nullptr) || out == nullptr) return -KZG_ERR_INVALID_PARAM;
   const i64 bound = std::min<i64>(outCap, kzg_compress_bound(n, blockSize)) + 16;
-  u8* dIn = nullptr; u8* dOut = nullptr;
   const size_t inCap = rnd((size_t)n + 64);
-  if (cudaMalloc((void**)&dIn, inCap) != cudaSuccess || cudaMalloc((void**)&dOut, rnd((size_t)bound + 64)) != cudaSuccess) {
-    cudaGetLastError(); if (dIn) cudaFree(dIn); kzg_set_error("cudaMalloc failed for stream buffers"); return -KZG_ERR_CREATE_CODEC;
-  }
+  u8* dIn = ws_io(0, inCap); u8* dOut = ws_io(1, rnd((size_t)bound + 64));
+  if (!dIn || !dOut) { kzg_set_error("cudaMalloc failed for stream buffers"); return -KZG_ERR_CREATE_CODEC; }
   i64 res;
   do {
     if (cudaMemsetAsync(dIn + n, 0, inCap - n, W.stream) != cudaSuccess) { res = -KZG_ERR_PROCESS_BLOCK; break; }
@@ -748,19 +758,16 @@ int64_t kzg_compress(const uint8_t* in, int64_t n, const int32_t* transforms, in
     if (res > outCap) { res = -KZG_ERR_WRITE_FILE; break; }
     if (cudaMemcpy(out, dOut, (size_t)res, cudaMemcpyDeviceToHost) != cudaSuccess) { res = -KZG_ERR_PROCESS_BLOCK; break; }
   } while (0);
-  cudaFree(dIn); cudaFree(dOut);
   return res;
 }
 
 int64_t kzg_decompress(const uint8_t* in, int64_t nBytes, int32_t flags, uint8_t* out, int64_t outCap) {
   int r = ws_init(); if (r < 0) return r;
   if (in == nullptr || out == nullptr || nBytes < 0 || outCap < 0) return -KZG_ERR_INVALID_PARAM;
-  u8* dIn = nullptr; u8* dOut = nullptr;
   const size_t inCap = rnd((size_t)nBytes + 64);
   // room for whole blocks: the last block may be short but kernels address by block
-  if (cudaMalloc((void**)&dIn, inCap) != cudaSuccess || cudaMalloc((void**)&dOut, rnd((size_t)outCap + 64)) != cudaSuccess) {
-    cudaGetLastError(); if (dIn) cudaFree(dIn); kzg_set_error("cudaMalloc failed for stream buffers"); return -KZG_ERR_CREATE_CODEC;
-  }
+  u8* dIn = ws_io(0, inCap); u8* dOut = ws_io(1, rnd((size_t)outCap + 64));
+  if (!dIn || !dOut) { kzg_set_error("cudaMalloc failed for stream buffers"); return -KZG_ERR_CREATE_CODEC; }
   i64 res;
   do {
     if (cudaMemsetAsync(dIn + nBytes, 0, inCap - nBytes, W.stream) != cudaSuccess) { res = -KZG_ERR_PROCESS_BLOCK; break; }
@@ -769,7 +776,6 @@ int64_t kzg_decompress(const uint8_t* in, int64_t nBytes, int32_t flags, uint8_t
     if (res < 0) break;
     if (cudaMemcpy(out, dOut, (size_t)res, cudaMemcpyDeviceToHost) != cudaSuccess) { res = -KZG_ERR_PROCESS_BLOCK; break; }
   } while (0);
-  cudaFree(dIn); cudaFree(dOut);
   return res;
 }
 
