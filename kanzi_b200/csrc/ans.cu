@@ -269,18 +269,116 @@ __global__ void __launch_bounds__(128) ans0_encode_kernel(const KzgBlock* __rest
 }
 
 // ================================================================================================================
-// chunk scan for decode (order 0 and 1): one thread per block walks the chunk headers to find where each
-// chunk starts (the only serial part of decoding: chunk k+1 starts where chunk k's byte count says).
+// chunk scan for decode (order 0 and 1): one warp per block walks the chunk headers to find where each chunk starts
+// (the only serial part of decoding: chunk k+1 starts where chunk k's byte count says).  The header bytes are staged
+// 512 at a time into shared memory by the whole warp; every lane then runs the same parse out of the window
+// (warp-uniform control flow, broadcast reads), so a field costs a shared-memory access instead of a trip to L2/HBM;
+// the alphabet bitmap is counted 32 mask bytes at a time.
 // ================================================================================================================
-__global__ void ans_scan_kernel(KzgBlock* __restrict__ blocks, int nBlocks, KzgEntParams P, int order) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+#define ANS_SCAN_WARPS 4
+#define ANS_SCAN_WIN 512            // bytes
+struct WarpBits {                   // MSB-first reader (format of BitReaderD) over a sliding shared window; all lanes in lock step
+  const u8* stream; u64 pos, end; u32* win; u64 winBit0; int lane;
+  __device__ __forceinline__ void stage() {
+    __syncwarp();
+    const u64 base4 = (pos >> 3) & ~3ull;
+    const u64 lastByte = (end + 7) >> 3;
+    #pragma unroll
+    for (int k = 0; k < ANS_SCAN_WIN / 128; k++) {
+      const u64 o = base4 + 4ull * (u64)(lane + 32 * k);
+      win[lane + 32 * k] = (o < lastByte) ? *reinterpret_cast<const u32*>(stream + o) : 0u;
+    }
+    winBit0 = base4 * 8;
+    __syncwarp();
+  }
+  __device__ __forceinline__ u32 read(int n) {      // n in 1..32; reads past `end` yield zeros
+    u32 v = 0;
+    if (pos + (u64)n <= end) {
+      if (pos + 40 > winBit0 + 8ull * ANS_SCAN_WIN) stage();
+      const u8* p = reinterpret_cast<const u8*>(win) + ((pos - winBit0) >> 3);
+      const int sh = (int)(pos & 7);
+      const u64 w = ((u64)p[0] << 32) | ((u64)p[1] << 24) | ((u64)p[2] << 16) | ((u64)p[3] << 8) | (u64)p[4];
+      v = (u32)((w >> (40 - sh - n)) & ((n == 32) ? 0xFFFFFFFFull : ((1ull << n) - 1)));
+    }
+    pos += (u64)n;
+    return v;
+  }
+  __device__ __forceinline__ void skip(u64 bits) { pos += bits; }
+  __device__ __forceinline__ bool overrun() const { return pos > end; }
+};
+__device__ __forceinline__ int ans_skip_alphabet_warp(WarpBits& br) {   // EntropyUtils.decodeAlphabet sizes only
+  if (br.read(1) == 0) return (br.read(1) == 1) ? 0 : 256;
+  const int lastMask = (int)br.read(5);
+  // lastMask + 1 mask bytes: lane i counts byte i
+  const u64 p0 = br.pos;
+  if (p0 + 8ull * (lastMask + 1) + 40 > br.winBit0 + 8ull * ANS_SCAN_WIN) br.stage();
+  int c = 0;
+  if (br.lane <= lastMask && p0 + 8ull * (br.lane + 1) <= br.end) {
+    const u64 q = p0 + 8ull * br.lane;
+    const u8* p = reinterpret_cast<const u8*>(br.win) + ((q - br.winBit0) >> 3);
+    const int sh = (int)(q & 7);
+    c = __popc(((((u32)p[0] << 8) | (u32)p[1]) >> (8 - sh)) & 0xFFu);
+  }
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+  br.pos = p0 + 8ull * (lastMask + 1);
+  return c;
+}
+__global__ void __launch_bounds__(32 * ANS_SCAN_WARPS) ans_scan_kernel(KzgBlock* __restrict__ blocks, int nBlocks, KzgEntParams P, int order) {
+  __shared__ u32 wins[ANS_SCAN_WARPS][ANS_SCAN_WIN / 4 + 4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * ANS_SCAN_WARPS + warp;
   if (b >= nBlocks) return;
   KzgBlock& B = blocks[b];
   if (B.status != 0 || B.entropy != P.entropy) return;
-  BitReaderD br(P.stream, (u64)B.srcBit, (u64)(B.srcBit + B.srcBits));
-  const int r = ans_scan_stream(br, B.preLen, P.chunkSize, order, P.chunks + (i64)b * P.maxChunks);
-  if (r < 0) { B.status = r; return; }
-  B.entBits = (i64)br.pos - B.srcBit;
+  const int len = B.preLen;
+  if (len <= 32) {   // raw (ANSRangeDecoder.decode :193-196)
+    if (lane == 0) { if ((u64)len * 8 > (u64)B.srcBits) B.status = -KZG_ERR_PROCESS_BLOCK; else B.entBits = (i64)len * 8; }
+    return;
+  }
+  WarpBits br; br.stream = P.stream; br.pos = (u64)B.srcBit; br.end = (u64)(B.srcBit + B.srcBits); br.win = wins[warp]; br.lane = lane;
+  br.stage();
+  KzgChunkInfo* ci = P.chunks + (i64)b * P.maxChunks;
+  const int chunkSize = P.chunkSize;
+  const int nChunks = (len + chunkSize - 1) / chunkSize;
+  const int dim = 255 * order + 1;
+  int status = 0;
+  for (int c = 0; c < nChunks && status == 0; c++) {
+    KzgChunkInfo info;
+    info.hdrBit = (i64)br.pos;
+    const int lr = 8 + (int)br.read(3);
+    int llr = 3;
+    while ((1 << llr) <= lr) llr++;
+    int res = 0;
+    for (int k = 0; k < dim; k++) {
+      const int alphabetSize = ans_skip_alphabet_warp(br);
+      if (alphabetSize == 0) continue;
+      const int chkSize = (alphabetSize >= 64) ? 8 : 6;
+      for (int i = 1; i < alphabetSize; i += chkSize) {
+        const int logMax = (int)br.read(llr);
+        const int endj = (i + chkSize < alphabetSize) ? i + chkSize : alphabetSize;
+        br.skip((u64)(logMax * (endj - i)));
+      }
+      res += alphabetSize;
+      if (br.overrun()) break;
+    }
+    info.alphabetSize = res;
+    info.sz = 0; info.payBit = 0;
+    info.st[0] = info.st[1] = info.st[2] = info.st[3] = 0;
+    if (res == 0 || br.overrun()) { status = -KZG_ERR_PROCESS_BLOCK; break; }   // decode returns early (:218-219)
+    if (!(order == 0 && res == 1)) {
+      u32 value = br.read(8), sz = value & 0x7F;          // EntropyUtils.readVarInt (:283-300)
+      int shift = 7;
+      while (value >= 128) { value = br.read(8); sz |= ((value & 0x7F) << shift); if (shift == 28) break; shift += 7; }
+      if ((i32)sz < 0 || sz >= (1u << 27)) { status = -KZG_ERR_PROCESS_BLOCK; break; }
+      info.st[0] = br.read(32); info.st[1] = br.read(32); info.st[2] = br.read(32); info.st[3] = br.read(32);
+      info.sz = (i32)sz;
+      info.payBit = (i64)br.pos;
+      br.skip((u64)sz * 8);
+    }
+    if (br.overrun()) { status = -KZG_ERR_PROCESS_BLOCK; break; }
+    if (lane == 0) ci[c] = info;
+  }
+  if (lane == 0) { if (status < 0) B.status = status; else B.entBits = (i64)br.pos - B.srcBit; }
 }
 
 // 16 bits at byte offset `off` of a payload that starts at absolute bit `payBit`; bytes at or beyond `sz`
@@ -731,7 +829,7 @@ int kzg_ans_encode_launch(cudaStream_t s, const KzgBlock* d_blocks, int nBlocks,
 
 int kzg_ans_decode_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, const KzgEntParams& P, int order, bool withScan) {
   if (withScan) {
-    ans_scan_kernel<<<(nBlocks + 31) / 32, 32, 0, s>>>(d_blocks, nBlocks, P, order);
+    ans_scan_kernel<<<(nBlocks + ANS_SCAN_WARPS - 1) / ANS_SCAN_WARPS, 32 * ANS_SCAN_WARPS, 0, s>>>(d_blocks, nBlocks, P, order);
     CUDA_TRY(cudaGetLastError());
   }
   if (order == 0) {

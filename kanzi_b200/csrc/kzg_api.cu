@@ -193,7 +193,11 @@ static int run_transform_stage(Batch& bt, int type, int stage, bool forward, con
           r = kzg_lz_forward2_launch(W.stream, bt.dBlocks, bt.nBlocks, P, type == KZG_T_LZX, bt.maxLen);
         }
       }
-      else r = kzg_lz_inverse_launch(W.stream, bt.dBlocks, bt.nBlocks, P, bt.maxLen);
+      else {
+        static const char* dbgEnvI = getenv("KZG_DEBUG");         // developer aid: bit 0 per-block statistics of the token chase
+        if (dbgEnvI) P.flags |= (atoi(dbgEnvI) << 12);
+        r = kzg_lz_inverse_launch(W.stream, bt.dBlocks, bt.nBlocks, P, bt.maxLen);
+      }
       break;
     default:
       r = kzg_stage_launch(W.stream, type, forward, bt.dBlocks, bt.nBlocks, P, bt.maxLen);

@@ -54,9 +54,12 @@ struct LzfBlock {                 // per-block scratch pointers (device)
   u32* tileSum;                   // per 1024 matches: literal-area / distance / length bytes (sums, then offsets)
   i32 segLen, nSeg, evStride, patchCap, nRng, aMax, active, needSerial;
   i32 nFin, giveUpIdx, emitGo, tkBase, mBase, mlBase;
+  i32 chkDiff, chkMax, chkFlag, chkPad;   // per-round verdict of lzf_check_marks_kernel
 };
 struct LzfState { i32 srcIdx, anchor, srcInc, repd0, repd1, repIdx, lastSkip, overLo, overHi; };
-struct LzfSeg { LzfState entry; LzfState end; LzfState trueEntry; i32 nEv; i32 fail; i32 haveTrue; i32 pad; };
+// rerun: a lookup of this segment's adopted parse resolved differently under the produced bitmap -> parse it again next round;
+// adopted: the stitched parse of this round took (part of) the segment's own log
+struct LzfSeg { LzfState entry; LzfState end; LzfState trueEntry; i32 nEv; i32 fail; i32 haveTrue; int16_t rerun; int16_t adopted; };
 struct LzfRange { const uint4* ev; i32 count; i32 start; };
 
 __device__ __forceinline__ u64 lzf_ld64(const u8* __restrict__ p) {
@@ -194,30 +197,69 @@ __global__ void __launch_bounds__(1024) lzf_scan_kernel(LzfBlock* __restrict__ l
     __syncthreads();
   }
 }
+// One CTA per tile of 4096 elements.  Every warp ranks its 512 consecutive elements by digit (16 rounds of
+// __match_any_sync), the per-warp digit counts are scanned across warps and digits, the elements are staged in shared
+// memory in digit order and leave from there: consecutive threads write consecutive elements of a digit run, so the
+// stores cover whole sectors (element-wise scattering costs ~3x the DRAM traffic in partial-sector fills and evictions).
 __global__ void __launch_bounds__(32 * LZF_WARPS) lzf_scatter_kernel(LzfBlock* __restrict__ lb, int shift, int mask, int k) {
-  __shared__ u32 pos[LZF_WARPS][256];
+  __shared__ u64 stage[LZF_WT];
+  __shared__ u32 cnt[LZF_WARPS][256];
+  __shared__ u32 digitBase[256 + 1];
+  __shared__ u32 gOff[256];
+  __shared__ u32 wsum[LZF_WARPS];
   const LzfBlock& L = lb[blockIdx.y];
   const int n = L.n;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x * LZF_WARPS + warp;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.x;
   const int nT = (n + LZF_WT - 1) / LZF_WT;
   if (tile >= nT) return;
-  for (int d = lane; d < 256; d += 32) pos[warp][d] = L.offs[(size_t)d * nT + tile];
-  __syncwarp();
+  for (int i = tid; i < LZF_WARPS * 256; i += 32 * LZF_WARPS) (&cnt[0][0])[i] = 0;
+  gOff[tid] = L.offs[(size_t)tid * nT + tile];
+  __syncthreads();
   const int beg = tile * LZF_WT, end = min(beg + LZF_WT, n);
   const u32 lower = (1u << lane) - 1;
   const u64* __restrict__ in = (k & 1) ? L.kb : L.ka;
   u64* __restrict__ out = (k & 1) ? L.ka : L.kb;
-  for (int base = beg; base < end; base += 32) {
-    const int i = base + lane;
+  constexpr int R = LZF_WT / (32 * LZF_WARPS);          // rounds per warp
+  u64 v[R]; u32 rk[R];
+  const int wbeg = beg + warp * (32 * R);
+  #pragma unroll
+  for (int r = 0; r < R; r++) { const int i = wbeg + r * 32 + lane; v[r] = (i < end) ? in[i] : 0ull; }
+  #pragma unroll
+  for (int r = 0; r < R; r++) {
+    const int i = wbeg + r * 32 + lane;
     const bool on = i < end;
-    u64 v = 0; int d = 256 + lane;
-    if (on) { v = in[i]; d = (int)(v >> shift) & mask; }
+    const int d = on ? ((int)(v[r] >> shift) & mask) : (256 + lane);
     const u32 peers = __match_any_sync(0xFFFFFFFFu, d);
-    if (on) out[pos[warp][d] + __popc(peers & lower)] = v;
+    rk[r] = on ? (cnt[warp][d] + __popc(peers & lower)) : 0u;
     __syncwarp();
-    if (on && (peers >> lane) <= 1u) pos[warp][d] += __popc(peers);
+    if (on && (peers >> lane) <= 1u) cnt[warp][d] += __popc(peers);
     __syncwarp();
+  }
+  __syncthreads();
+  // digit tid: exclusive scan over the warps, then over the digits
+  u32 tot = 0;
+  #pragma unroll
+  for (int w = 0; w < LZF_WARPS; w++) { const u32 c = cnt[w][tid]; cnt[w][tid] = tot; tot += c; }
+  u32 incl = tot;
+  for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  u32 wb = 0;
+  for (int w = 0; w < warp; w++) wb += wsum[w];
+  digitBase[tid] = wb + incl - tot;
+  __syncthreads();
+  #pragma unroll
+  for (int r = 0; r < R; r++) {
+    const int i = wbeg + r * 32 + lane;
+    if (i < end) { const int d = (int)(v[r] >> shift) & mask; stage[digitBase[d] + cnt[warp][d] + rk[r]] = v[r]; }
+  }
+  __syncthreads();
+  const int count = end - beg;
+  for (int j = tid; j < count; j += 32 * LZF_WARPS) {
+    const u64 x = stage[j];
+    const int d = (int)(x >> shift) & mask;
+    out[gOff[d] + (u32)j - digitBase[d]] = x;
   }
 }
 // after the hash passes: sorted[i-1] precedes sorted[i] in (hash, position) order: same hash -> it is the previous occurrence
@@ -680,6 +722,24 @@ __device__ __forceinline__ void lzf_core(const LzfBlock& L, const u8* __restrict
     }
     const int p = srcIdx + lane + (int)(exIncl - stepExtra);
     const bool valid = p < limit;
+    if (srcInc >= 64) {
+      // inside a run of misses the next visits are known in advance (every batch all misses): pull the lines of the next two
+      // batches towards the SM while this one is evaluated.  (srcInc' + lane) >> 6 changes at most once inside a batch, so the
+      // positions come without a scan.
+      int nb = __shfl_sync(0xFFFFFFFFu, p + (int)stepExtra + 1, 31);
+      #pragma unroll
+      for (int d = 1; d <= 2; d++) {
+        const int inc = srcInc + 32 * d;
+        const int e0 = inc >> 6, kc = 64 - (inc & 63);
+        const int q = nb + lane * (1 + e0) + max(0, lane - kc);
+        if (q < limit) {
+          lzf_prefetch(src + q + 1); lzf_prefetch(L.len0 + q); lzf_prefetch(L.prev + q);
+          if (q + 1 - repd0 > 0) lzf_prefetch(src + q + 1 - repd0);
+          if (q + 1 - repd1 > 0) lzf_prefetch(src + q + 1 - repd1);
+        }
+        nb += 32 * (1 + e0) + max(0, 32 - kc);
+      }
+    }
     bool hit = false;
     int l0 = 0, pv = 0, repSmall = 0, repRef = 0;
     int cnd = -1;                             // table content for p (first inserted entry of its prev chain); -1: resolve after the commit
@@ -866,13 +926,20 @@ __device__ __forceinline__ void lzf_core(const LzfBlock& L, const u8* __restrict
 
 __device__ __forceinline__ int lzf_seg_end(const LzfBlock& L, int s) { return (s + 1 >= L.nSeg) ? L.srcEnd : (s + 1) * L.segLen; }
 
-// (re)start of a round: clear the per-round bitmaps of the blocks still running
+// (re)start of a round.  Round 0 clears every per-round bitmap.  Later rounds parse again only the segments the check flagged:
+// their own jumped-over bits (D) are cleared, everybody else's D, log and dependency marks (C) stay; Kn is rebuilt by the stitch.
 __global__ void lzf_round_init_kernel(LzfBlock* __restrict__ lb, int first) {
-  const LzfBlock& L = lb[blockIdx.y];
+  LzfBlock& L = lb[blockIdx.y];
   if (L.n <= 0 || !L.active) return;
-  if (first) for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L.nSeg; i += gridDim.x * blockDim.x) L.seg[i].haveTrue = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { L.chkDiff = 0; L.chkMax = -1; L.chkFlag = 0; }
+  if (first) for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L.nSeg; i += gridDim.x * blockDim.x) { L.seg[i].haveTrue = 0; L.seg[i].rerun = 1; L.seg[i].adopted = 0; }
   const int nW = (L.n + 31) / 32 + 2;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nW; i += gridDim.x * blockDim.x) { L.D[i] = 0; L.Kn[i] = 0; L.C[i] = 0; }
+  const int wps = L.segLen >> 5;                     // bitmap words per segment (segLen is a multiple of 4096)
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nW; i += gridDim.x * blockDim.x) {
+    L.Kn[i] = 0;
+    if (first) { L.D[i] = 0; L.C[i] = 0; }
+    else if (L.seg[min(i / wps, L.nSeg - 1)].rerun) L.D[i] = 0;
+  }
 }
 
 template <bool EXTRA>
@@ -880,6 +947,7 @@ __global__ void __launch_bounds__(32) lzf_spec_kernel(const KzgBlock* __restrict
   const int b = blockIdx.y, s = blockIdx.x, lane = threadIdx.x;
   const LzfBlock L = lb[b];
   if (L.n <= 0 || !L.active || s >= L.nSeg) return;
+  if (!L.seg[s].rerun) return;                 // its log still stands (no lookup of it resolved differently last round)
   const u8* __restrict__ src = blocks[b].cur;
   const int segStart = s * L.segLen, segEnd = lzf_seg_end(L, s);
   LzfState st;
@@ -924,7 +992,7 @@ __global__ void __launch_bounds__(32) lzf_spec_kernel(const KzgBlock* __restrict
   }
   const LzfState entry = st;
   lzf_core<EXTRA>(L, src, st, segEnd, L.A, min(L.aMax, segStart - 1), segStart, L.D, L.C, segStart, dEnd, ev, nEv, L.evStride, fail, lane, ns);
-  if (lane == 0) { LzfSeg& S = L.seg[s]; S.entry = entry; S.end = st; S.nEv = nEv; S.fail = fail; }
+  if (lane == 0) { LzfSeg& S = L.seg[s]; S.entry = entry; S.end = st; S.nEv = nEv; S.fail = fail; S.rerun = 0; }
 }
 
 // D == Kn on bit positions [lo, hi)?
@@ -1004,7 +1072,7 @@ __global__ void __launch_bounds__(32) lzf_stitch_kernel(const KzgBlock* __restri
   for (int s = 1; s < L.nSeg; s++) {
     const int segStart = s * L.segLen, segEnd = lzf_seg_end(L, s);
     LzfSeg& S = L.seg[s];
-    if (lane == 0) { S.trueEntry = st; S.haveTrue = 1; }
+    if (lane == 0) { S.trueEntry = st; S.haveTrue = 1; S.adopted = 0; }
     if (st.srcIdx >= segEnd) { nOver++; continue; }    // a match ran over the whole segment
     LzfSync sy;
     sy.spec = L.specEv + (size_t)s * L.evStride; sy.nSpec = S.nEv; sy.j = 0; sy.entryRepd0 = S.entry.repd0;
@@ -1033,6 +1101,7 @@ __global__ void __launch_bounds__(32) lzf_stitch_kernel(const KzgBlock* __restri
     }
     if (sy.synced) {
       nSync++;
+      if (lane == 0) S.adopted = 1;
       addRange(sy.spec + sy.j + 1, S.nEv - sy.j - 1);
       if (S.end.lastSkip >= segStart)                  // (nothing to merge when the segment never jumped)
         lzf_bits_copy(L.D, L.Kn, atOnce ? segStart : st.anchor, segEnd + ((s + 1 >= L.nSeg) ? 2 : 0), lane);
@@ -1046,63 +1115,60 @@ __global__ void __launch_bounds__(32) lzf_stitch_kernel(const KzgBlock* __restri
   if ((dbg & 1) && lane == 0) printf("lzf stitch block %d: %d segs, %d synced (%d at once), %d dead, %d unsynced, %d covered, %d own matches, fail %d, %lld cycles\n", b, L.nSeg, nSync, nAtOnce, nDead, nEnd, nOver, nPatch, fail, clock64() - t0);
 }
 
-// Did any lookup depend on a position whose assumed state (A) is not the produced one (Kn)?  (one CTA per block)
+// Did any lookup depend on a position whose assumed state (A) is not the produced one (Kn)?
 // A lookup that entered the assumed range at chain entry q resolved to the first entry from q on that A does not mark;
-// it would have found the same thing under Kn iff that resolution is the same.  If so for every such q, parsing with Kn
-// assumed reproduces this very parse, so Kn is the fixed point and the parse is the reference's.  Otherwise A := Kn for
-// the next round, or the serial walk after the last one.
+// it would have found the same thing under Kn iff that resolution is the same.  If so for every such q of every segment
+// whose log the stitched parse adopted, parsing with Kn assumed reproduces this very parse, so the parse is the
+// reference's (the stitcher's own matches never look at A).  A mark q that resolves differently can only come from the
+// segment holding the next entry y of q's hash class (q was the last entry below that segment's start; a lazy step may
+// look one or two positions past a segment's end, hence seg(y) - 1 when y opens its segment): those segments are parsed
+// again next round with A := Kn, everybody else keeps log, D bits and marks (stale marks only cost a spurious re-run).
 __device__ __forceinline__ int lzf_resolve(const LzfBlock& L, const u32* __restrict__ X, int q) {
   while (q > 0 && ((X[q >> 5] >> (q & 31)) & 1u)) q = (int)(L.prev[q] & ~LZF_NOCAND);
   return q;
 }
-__global__ void __launch_bounds__(1024) lzf_check_kernel(LzfBlock* __restrict__ lb, int lastRound, int* __restrict__ nActive, int dbg) {
-  __shared__ int sDiff, sMax;
-  __shared__ int dBits, dBad, dMin, dMax, dMarks;
-  if (threadIdx.x == 0) { dBits = 0; dBad = 0; dMin = 0x7FFFFFFF; dMax = -1; dMarks = 0; }
-  LzfBlock& L = lb[blockIdx.x];
-  if (L.n <= 0 || !L.active) return;
-  if (threadIdx.x == 0) { sDiff = 0; sMax = -1; }
-  __syncthreads();
+__global__ void __launch_bounds__(256) lzf_check_marks_kernel(LzfBlock* __restrict__ lb) {
+  LzfBlock& L = lb[blockIdx.y];
+  if (L.n <= 0 || !L.active || L.needSerial) return;
   const int nW = (L.n + 31) / 32 + 1;
-  int same = 1, mx = -1;
-  for (int i = threadIdx.x; i < nW; i += blockDim.x) {
+  int differ = 0, mx = -1, flagged = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nW; i += gridDim.x * blockDim.x) {
     const u32 k = L.Kn[i], a = L.A[i];
-    if (k != a) { same = 0; if (dbg & 1) atomicAdd(&dBits, __popc(k ^ a)); }
+    if (k != a) differ = 1;
     if (k) mx = i * 32 + 31 - __clz(k);
-  }
-  if (!same) sDiff = 1;
-  if (mx >= 0) atomicMax(&sMax, mx);
-  __syncthreads();
-  const int differ = sDiff;
-  __syncthreads();
-  if (differ) {                      // bitmaps differ somewhere: does it matter to any lookup?
-    if (threadIdx.x == 0) sDiff = 0;
-    __syncthreads();
-    int bad = 0;
-    for (int i = threadIdx.x; i < nW && (!bad || (dbg & 1)); i += blockDim.x) {
-      u32 c = L.C[i];
-      if (dbg & 1) atomicAdd(&dMarks, __popc(c));
-      while (c) {
-        const int q = i * 32 + __ffs(c) - 1;
-        c &= c - 1;
-        if (lzf_resolve(L, L.A, q) != lzf_resolve(L, L.Kn, q)) {
-          bad = 1;
-          if (dbg & 1) { atomicAdd(&dBad, 1); atomicMin(&dMin, q); atomicMax(&dMax, q); } else break;
-        }
-      }
+    u32 c = L.C[i] & (a | k);          // an entry neither bitmap marks resolves to itself under both
+    while (c) {
+      const int q = i * 32 + __ffs(c) - 1;
+      c &= c - 1;
+      if (lzf_resolve(L, L.A, q) == lzf_resolve(L, L.Kn, q)) continue;
+      const u32 r = L.rank[q] + 1;
+      if ((int)r >= L.n) continue;
+      const u32 e = L.hs[r];
+      if (e & LZF_RUNSTART) continue;                      // q is the last entry of its class: nobody looked it up
+      const int y = (int)e, sq = q / L.segLen;
+      const int sy = min(y / L.segLen, L.nSeg - 1);
+      if (sy > sq && L.seg[sy].adopted) { L.seg[sy].rerun = 1; flagged = 1; }
+      if (y - sy * L.segLen <= 2 && sy - 1 > sq && L.seg[sy - 1].adopted) { L.seg[sy - 1].rerun = 1; flagged = 1; }
     }
-    if (bad) sDiff = 1;
-    __syncthreads();
   }
-  if ((dbg & 1) && threadIdx.x == 0 && differ)
-    printf("lzf check block %d: %d bits differ, %d marks, %d bad marks in [%d, %d], Kn max %d\n", (int)blockIdx.x, dBits, dMarks, dBad, dMin, dMax, sMax);
-  if (threadIdx.x == 0) {
-    if (L.needSerial) { L.active = 0; }
-    else if (!sDiff) { L.active = 0; }
-    else if (lastRound) { L.active = 0; L.needSerial = 1; }
-    else { u32* t = L.A; L.A = L.Kn; L.Kn = t; L.aMax = sMax; atomicAdd(nActive, 1); }
-    if (L.needSerial) atomicAdd(nActive + 1, 1);
+  if (__syncthreads_or(differ) && threadIdx.x == 0) L.chkDiff = 1;
+  if (__syncthreads_or(flagged) && threadIdx.x == 0) L.chkFlag = 1;
+  if (mx >= 0) atomicMax(&L.chkMax, mx);
+}
+__global__ void lzf_check_final_kernel(LzfBlock* __restrict__ lb, int nBlocks, int lastRound, int* __restrict__ nActive, int dbg) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nBlocks) return;
+  LzfBlock& L = lb[b];
+  if (L.n <= 0 || !L.active) return;
+  if ((dbg & 1) && L.chkDiff) {
+    int nr = 0; for (int s = 0; s < L.nSeg; s++) nr += L.seg[s].rerun;
+    printf("lzf check block %d: bitmaps differ, %d segments to parse again, Kn max %d\n", b, nr, L.chkMax);
   }
+  if (L.needSerial) { L.active = 0; }
+  else if (!L.chkDiff || !L.chkFlag) { L.active = 0; }
+  else if (lastRound) { L.active = 0; L.needSerial = 1; }
+  else { u32* t = L.A; L.A = L.Kn; L.Kn = t; L.aMax = L.chkMax; atomicAdd(nActive, 1); }
+  if (L.needSerial) atomicAdd(nActive + 1, 1);
 }
 
 // ---- phase 4: tokens from the match list (:467-538, :568-596) ----------------------------------------------------------------------
@@ -1242,11 +1308,15 @@ __global__ void __launch_bounds__(LZF_ET) lzf_emit_scan_kernel(KzgBlock* __restr
     L.emitGo = 1;
   }
 }
-// E4: every match writes its token, distance bytes, length bytes and literals where the prefix sums put them
+// E4: every match writes its token, distance bytes and length bytes where the prefix sums put them; the literal area of the
+// tile (length-extension bytes + literal runs, contiguous in dst) is then written output-centred: every thread takes four
+// consecutive destination bytes, finds the match they belong to in the tile's shared prefix table and fetches the bytes, so
+// stores are aligned words and consecutive lanes read consecutive source bytes inside a run.
 __global__ void __launch_bounds__(LZF_ET) lzf_emit_write_kernel(KzgBlock* __restrict__ blocks, LzfBlock* __restrict__ lb) {
   __shared__ u32 wsA[32], wsB[32];
-  __shared__ int qSrc[LZF_ET], qDst[LZF_ET], qLen[LZF_ET];
-  __shared__ int qN;
+  __shared__ u32 sOff[LZF_ET + 1];                  // literal-area offset of every match of the tile, relative to the tile's start
+  __shared__ int sSrc[LZF_ET];                      // source position of area byte 0 (= literal start - leSize)
+  __shared__ u8 sLe[LZF_ET];                        // length-extension bytes that open the area
   const LzfBlock& L = lb[blockIdx.y];
   if (L.n <= 0 || L.needSerial || !L.emitGo) return;
   const int base = blockIdx.x * LZF_ET;
@@ -1267,7 +1337,6 @@ __global__ void __launch_bounds__(LZF_ET) lzf_emit_write_kernel(KzgBlock* __rest
     if (lane >= o) { iA += tA; iB += tB; }
   }
   if (lane == 31) { wsA[warp] = iA; wsB[warp] = iB; }
-  if (tid == 0) qN = 0;
   __syncthreads();
   if (warp == 0) {
     const u32 a = wsA[lane], bb = wsB[lane];
@@ -1277,26 +1346,49 @@ __global__ void __launch_bounds__(LZF_ET) lzf_emit_write_kernel(KzgBlock* __rest
       if (lane >= o) { ia += tA; ib += tB; }
     }
     wsA[lane] = ia - a; wsB[lane] = ib - bb;
+    if (lane == 31) sOff[LZF_ET] = ia;              // literal-area bytes of the whole tile
   }
   __syncthreads();
-  const u32 offLit = L.tileSum[3 * blockIdx.x] + wsA[warp] + iA - vA;
+  const u32 relLit = wsA[warp] + iA - vA;
   const u32 offB = wsB[warp] + iB - vB;
   const u32 offM = L.tileSum[3 * blockIdx.x + 1] + (offB >> 16), offML = L.tileSum[3 * blockIdx.x + 2] + (offB & 0xFFFFu);
+  sOff[tid] = relLit; sSrc[tid] = (int)(p1.x + p1.y) - k.leSize; sLe[tid] = (u8)k.leSize;
   if (on) {
     const int dist = (int)e.z;
     dst[L.tkBase + i] = (u8)k.token;
     if (k.nd) { u8* q = dst + L.mBase + offM; int j = 0; if (k.nd == 3) q[j++] = (u8)(dist >> 16); if (k.nd >= 2) q[j++] = (u8)(dist >> 8); q[j] = (u8)dist; }
     if (k.mlSize) lzf_put_length(dst + L.mlBase + offML, k.mlExt);
-    if (k.leSize) lzf_put_length(dst + offLit, k.litLen - 7);
-    const int ls = (int)(p1.x + p1.y), ld = (int)offLit + k.leSize;
-    if (k.litLen <= 16) { for (int j = 0; j < k.litLen; j++) dst[ld + j] = src[ls + j]; }
-    else { const int q = atomicAdd(&qN, 1); qSrc[q] = ls; qDst[q] = ld; qLen[q] = k.litLen; }
   }
   __syncthreads();
-  const int n = qN;                                     // long literal runs: one warp per run
-  for (int q = warp; q < n; q += LZF_ET / 32) {
-    const int ls = qSrc[q], ld = qDst[q], len = qLen[q];
-    for (int j = lane; j < len; j += 32) dst[ld + j] = src[ls + j];
+  const u32 total = sOff[LZF_ET];
+  const u32 t0 = L.tileSum[3 * blockIdx.x];         // absolute dst offset of the tile's literal area
+  const u32 t1 = t0 + total;
+  for (u32 g = (t0 & ~3u) + 4u * tid; g < t1; g += 4u * LZF_ET) {
+    const u32 lo = max(g, t0), hi = min(g + 4u, t1);
+    // last match whose area starts at or before byte lo (areas of length 0 share their start with the next one)
+    const u32 o0 = lo - t0;
+    int a = 0, b = LZF_ET - 1;
+    while (a < b) { const int mid = (a + b + 1) >> 1; if (sOff[mid] <= o0) a = mid; else b = mid - 1; }
+    u32 w = 0;
+    for (u32 x = lo; x < hi; x++) {
+      const u32 o = x - t0;
+      while (sOff[a + 1] <= o) a++;
+      const int j = (int)(o - sOff[a]);
+      const int le = sLe[a];
+      u32 v;
+      if (j >= le) v = src[sSrc[a] + j];
+      else {                                        // byte j of emitLength(litLen - 7) (:211-231)
+        const int litLen = (int)(sOff[a + 1] - sOff[a]) - le;
+        int len = litLen - 7;
+        if (len < 254) v = (u32)len;
+        else if (len < 65536 + 254) { len -= 254; v = (j == 0) ? 254u : ((j == 1) ? (u32)(len >> 8) : (u32)len); }
+        else { len -= 255; v = (j == 0) ? 255u : ((j == 1) ? (u32)(len >> 16) : ((j == 2) ? (u32)(len >> 8) : (u32)len)); }
+        v &= 0xFFu;
+      }
+      w |= v << (8 * (x - g));
+    }
+    if (hi - lo == 4u) *reinterpret_cast<u32*>(dst + g) = w;
+    else for (u32 x = lo; x < hi; x++) dst[x] = (u8)(w >> (8 * (x - g)));
   }
 }
 
@@ -1374,7 +1466,7 @@ int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
     const int mask = (1 << std::min(8, bits - shift)) - 1;
     lzf_hist_kernel<<<gridT, 32 * LZF_WARPS, 0, s>>>(dlb, 30 + shift, mask, pass);
     lzf_scan_kernel<<<nBlocks, 1024, 0, s>>>(dlb);
-    lzf_scatter_kernel<<<gridT, 32 * LZF_WARPS, 0, s>>>(dlb, 30 + shift, mask, pass);
+    lzf_scatter_kernel<<<dim3(nT, nBlocks), 32 * LZF_WARPS, 0, s>>>(dlb, 30 + shift, mask, pass);
   }
   tm.mark("sort1");
   lzf_prev_kernel<<<dim3(gx, nBlocks), 256, 0, s>>>(dlb, pass, bits);
@@ -1383,7 +1475,7 @@ int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
     const int mask = (1 << std::min(8, fpBits - shift)) - 1;
     lzf_hist_kernel<<<gridT, 32 * LZF_WARPS, 0, s>>>(dlb, 30 + bits + shift, mask, pass);
     lzf_scan_kernel<<<nBlocks, 1024, 0, s>>>(dlb);
-    lzf_scatter_kernel<<<gridT, 32 * LZF_WARPS, 0, s>>>(dlb, 30 + bits + shift, mask, pass);
+    lzf_scatter_kernel<<<dim3(nT, nBlocks), 32 * LZF_WARPS, 0, s>>>(dlb, 30 + bits + shift, mask, pass);
   }
   lzf_flag_kernel<<<dim3(gx, nBlocks), 256, 0, s>>>(dlb, pass);
   tm.mark("sort2");
@@ -1393,7 +1485,7 @@ int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
   int hCnt[2] = {0, (dbg & 8) ? nBlocks : 0};
   int rounds = 0;
   if (!(dbg & 8)) {
-    const int maxRounds = 4;
+    const int maxRounds = 8;
     for (int round = 0; round < maxRounds; round++) {
       rounds++;
       CUDA_TRY(cudaMemsetAsync(dCnt, 0, 2 * sizeof(int), s));
@@ -1404,8 +1496,9 @@ int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
       if (extra) lzf_stitch_kernel<true><<<nBlocks, 32, 0, s>>>(d_blocks, dlb, dbg);
       else lzf_stitch_kernel<false><<<nBlocks, 32, 0, s>>>(d_blocks, dlb, dbg);
       tm.mark("stitch");
-      lzf_check_kernel<<<nBlocks, 1024, 0, s>>>(dlb, round == maxRounds - 1 ? 1 : 0, dCnt, dbg);
-      launches += 4;
+      lzf_check_marks_kernel<<<dim3(16, nBlocks), 256, 0, s>>>(dlb);
+      lzf_check_final_kernel<<<(nBlocks + 63) / 64, 64, 0, s>>>(dlb, nBlocks, round == maxRounds - 1 ? 1 : 0, dCnt, dbg);
+      launches += 5;
       CUDA_TRY(cudaMemcpyAsync(hCnt, dCnt, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
       CUDA_TRY(cudaStreamSynchronize(s));
       tm.mark("check");

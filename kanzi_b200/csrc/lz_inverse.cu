@@ -20,8 +20,8 @@
 #define LZ_MAX_DISTANCE1 ((1 << 16) - 2)
 #define LZ_MAX_DISTANCE2 ((1 << 24) - 2)
 
-struct LziTok { u32 outPos, litSrc, litLen, mLen, dist; };
-struct LziHdr { i32 nTok, outLen, ok, done[8]; };
+struct LziTok { u32 outPos, litSrc, litLen, mLen, dist, flags; };
+struct LziHdr { i32 nTok, outLen, ok, done[8]; i32 valid, lastTok, fail, nTokRaw, outLenRaw, okRaw, nExtL, nExtM, nExtLValid, nExtMValid; };
 
 __device__ __forceinline__ u32 lzi_scan_u32(u32 v, int lane, u32& total) {
   u32 incl = v;
@@ -56,7 +56,8 @@ struct LziShared {
   int nExtL, nExtM, nExtLValid, nExtMValid, lastIdx, fail;
   u32 winBase; int winJ, chaseDone;
   u32 winK[LZI_KB];
-  u8 win[LZI_WIN + 16];
+  u32 winE[LZI_KB];
+  u16 G[LZI_WIN];
 };
 
 // exclusive scan of two values over the CTA (1024 threads); totals left in S.totA / S.totB
@@ -83,67 +84,145 @@ __device__ __forceinline__ void lzi_cta_scan2(u32 vA, u32 vB, u32& offA, u32& of
   offA = S.wsA[warp] + iA - vA; offB = S.wsB[warp] + iB - vB;
 }
 
-__global__ void __launch_bounds__(LZI_TT) lzi_tokens_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P, LziTok* __restrict__ toks, i64 tokStride,
-                                                           LziHdr* __restrict__ hdrs, u32* __restrict__ extPool) {
-  __shared__ LziShared S;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.x;
-  KzgBlock& B = blocks[b];
-  int* res = P.result + 2 * b;
-  LziHdr& H = hdrs[b];
-  if (tid == 0) { res[0] = 0; res[1] = 0; H.nTok = 0; H.outLen = 0; H.ok = 0; for (int i = 0; i < 8; i++) H.done[i] = 0; }
-  if (B.status != 0 || !P.enabled[b]) return;
+// block layout shared by the token kernels (header checks of :636-660)
+struct LziLayout { int count, tkBase, nTokBytes, distBase, mLenBase, srcEndLit, litEnd, maxDist, minMatch, dstEnd; };
+__device__ __forceinline__ bool lzi_layout(const KzgBlock& B, const KzgXfParams& P, int b, LziLayout& Y) {
+  if (B.status != 0 || !P.enabled[b]) return false;
   const int count = B.curLen;
   const u8* __restrict__ src = B.cur;
-  const int dstEnd = min(P.dstLimit[b], B.cap);
-  if (count < 13) return;
+  if (count < 13) return false;
   auto le32 = [&](int o) { return (i32)((u32)src[o] | ((u32)src[o + 1] << 8) | ((u32)src[o + 2] << 16) | ((u32)src[o + 3] << 24)); };
   const i32 tkLen = le32(0), mIdxLen = le32(4), mLenLen = le32(8);
-  if ((tkLen < 0) || (mIdxLen < 0) || (mLenLen < 0)) return;
-  if ((tkLen < 13) || (tkLen > count) || (mIdxLen > count - tkLen) || (mLenLen > count - tkLen - mIdxLen)) return;
+  if ((tkLen < 0) || (mIdxLen < 0) || (mLenLen < 0)) return false;
+  if ((tkLen < 13) || (tkLen > count) || (mIdxLen > count - tkLen) || (mLenLen > count - tkLen - mIdxLen)) return false;
   // (Java names: the first header field is where the tokens start, the second the token byte count, the third the distance byte count)
-  const int tkBase = tkLen;
-  const int nTokBytes = mIdxLen;
-  const int distBase = tkBase + nTokBytes;
-  const int mLenBase = distBase + mLenLen;
-  const int srcEndLit = tkBase - 13;        // `srcIdx >= srcEnd` ends the walk (:673-674)
-  const int litEnd = tkBase;
-  const int maxDist = ((src[12] & 1) == 0) ? LZ_MAX_DISTANCE1 : LZ_MAX_DISTANCE2;
-  const int minMatch = ((src[12] >> 1) & 0x07) + 2;
-  LziTok* T = toks + (i64)b * tokStride;
-  if ((i64)nTokBytes > tokStride) { if (tid == 0) atomicExch(&B.status, -KZG_ERR_PROCESS_BLOCK); return; }
-  // per-block lists: extK[j] literal bytes of ordinary tokens before extended-literal token j; extE[j] literal-area bytes of
-  // the extended tokens before j (extE[nExtL] = all of them); extLS[j] = its length | record size << 28; mxVal[k]
-  u32* extK = extPool + (i64)b * 4 * tokStride;
-  u32* extE = extK + tokStride;
-  u32* extLS = extE + tokStride;
-  u32* mxVal = extLS + tokStride;
+  Y.count = count; Y.tkBase = tkLen; Y.nTokBytes = mIdxLen; Y.distBase = Y.tkBase + Y.nTokBytes; Y.mLenBase = Y.distBase + mLenLen;
+  Y.srcEndLit = Y.tkBase - 13;             // `srcIdx >= srcEnd` ends the walk (:673-674)
+  Y.litEnd = Y.tkBase;
+  Y.maxDist = ((src[12] & 1) == 0) ? LZ_MAX_DISTANCE1 : LZ_MAX_DISTANCE2;
+  Y.minMatch = ((src[12] >> 1) & 0x07) + 2;
+  Y.dstEnd = min(P.dstLimit[b], B.cap);
+  return true;
+}
+// per-block scratch of the token passes
+struct LziArrays { LziTok* T; u32 *extK, *extE, *extLS, *mxVal; uint2* tileSum; uint4* tileOff; uint4* tileSpan; u32* tileOut; uint2* tileRep; };
+__device__ __forceinline__ LziArrays lzi_arrays(LziTok* toks, u32* extPool, u32* tilePool, i64 tokStride, i64 tileStride, int b) {
+  LziArrays A;
+  A.T = toks + (i64)b * tokStride;
+  A.extK = extPool + (i64)b * 4 * tokStride; A.extE = A.extK + tokStride; A.extLS = A.extE + tokStride; A.mxVal = A.extLS + tokStride;
+  u32* t = tilePool + (i64)b * 16 * tileStride;
+  A.tileSum = (uint2*)t; A.tileOff = (uint4*)(t + 2 * tileStride); A.tileSpan = (uint4*)(t + 6 * tileStride);
+  A.tileOut = t + 10 * tileStride; A.tileRep = (uint2*)(t + 12 * tileStride);
+  return A;
+}
+struct LziFlags { bool on, hasLit, lExt, isRep, mExt; u32 known, nd; };
+__device__ __forceinline__ LziFlags lzi_flags(int token, bool on) {
+  LziFlags F;
+  F.on = on;
+  F.hasLit = on && token >= 32;
+  F.lExt = F.hasLit && token >= 0xE0;
+  const int f = token & 0x18;
+  F.isRep = (f == 0);
+  F.mExt = on && (F.isRep ? ((token & 3) == 3) : ((token & 7) == 7));
+  F.nd = (on && !F.isRep) ? (u32)(f >> 3) : 0u;
+  F.known = (F.hasLit && !F.lExt) ? (u32)(token >> 5) : 0u;
+  return F;
+}
 
-  if (tid == 0) { S.carryK = 0; S.carryL = 0; S.carryM = 0; S.fail = 0; }
+// T1: per tile of 1024 tokens: ordinary literal bytes, explicit distance bytes, extended-literal and extended-match tokens
+__global__ void __launch_bounds__(LZI_TT) lzi_tok_sums_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P, LziTok* toks, i64 tokStride, LziHdr* __restrict__ hdrs,
+                                                             u32* extPool, u32* tilePool, i64 tileStride) {
+  __shared__ LziShared S;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.y;
+  KzgBlock& B = blocks[b];
+  LziHdr& H = hdrs[b];
+  LziLayout Y;
+  bool ok = lzi_layout(B, P, b, Y);
+  if (ok && (i64)Y.nTokBytes > tokStride) { if (blockIdx.x == 0 && tid == 0) atomicExch(&B.status, -KZG_ERR_PROCESS_BLOCK); ok = false; }
+  if (blockIdx.x == 0 && tid == 0) {
+    int* res = P.result + 2 * b;
+    res[0] = 0; res[1] = 0; H.nTok = 0; H.outLen = 0; H.ok = 0; for (int i = 0; i < 8; i++) H.done[i] = 0;
+    H.valid = ok ? 1 : 0; H.lastTok = 0x7FFFFFFF; H.fail = 0; H.nTokRaw = 0; H.outLenRaw = 0; H.okRaw = 0;
+    H.nExtL = 0; H.nExtM = 0; H.nExtLValid = 0; H.nExtMValid = 0;
+  }
+  if (!ok) return;
+  const int base = blockIdx.x * LZI_TT;
+  if (base >= Y.nTokBytes) return;
+  const LziArrays A = lzi_arrays(toks, extPool, tilePool, tokStride, tileStride, b);
+  const int t = base + tid;
+  const bool on = t < Y.nTokBytes;
+  const LziFlags F = lzi_flags(on ? B.cur[Y.tkBase + t] : 0, on);
+  u32 o0, o1;
+  lzi_cta_scan2(F.known | (F.nd << 16), ((u32)F.lExt << 16) | (u32)F.mExt, o0, o1, S, lane, warp);
+  if (tid == 0) A.tileSum[blockIdx.x] = make_uint2(S.totA, S.totB);
+}
+// T2 (one CTA per block): exclusive scan of the tile sums
+__global__ void __launch_bounds__(LZI_TT) lzi_tok_scan1_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P, LziTok* toks, i64 tokStride, LziHdr* __restrict__ hdrs,
+                                                              u32* extPool, u32* tilePool, i64 tileStride) {
+  __shared__ LziShared S;
+  __shared__ u32 carry[4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.x;
+  LziHdr& H = hdrs[b];
+  if (!H.valid) return;
+  LziLayout Y;
+  if (!lzi_layout(blocks[b], P, b, Y)) return;
+  const LziArrays A = lzi_arrays(toks, extPool, tilePool, tokStride, tileStride, b);
+  const int nTiles = (Y.nTokBytes + LZI_TT - 1) / LZI_TT;
+  if (tid < 4) carry[tid] = 0;
   __syncthreads();
-  // ---- tile loop 1: ranks of the extended tokens and the ordinary literal bytes before each extended-literal token ----
-  for (int base = 0; base < nTokBytes; base += LZI_TT) {
+  for (int base = 0; base < nTiles; base += LZI_TT) {
     const int t = base + tid;
-    const bool on = t < nTokBytes;
-    const int token = on ? src[tkBase + t] : 0;
-    const bool hasLit = on && token >= 32;
-    const bool lExt = hasLit && token >= 0xE0;
-    const bool isRep = (token & 0x18) == 0;
-    const bool mExt = on && (isRep ? ((token & 3) == 3) : ((token & 7) == 7));
-    const u32 known = (hasLit && !lExt) ? (u32)(token >> 5) : 0u;
-    u32 kOff, cOff;
-    lzi_cta_scan2(known, ((u32)lExt << 16) | (u32)mExt, kOff, cOff, S, lane, warp);
-    if (lExt) extK[S.carryL + (cOff >> 16)] = S.carryK + kOff;
+    const uint2 v = (t < nTiles) ? A.tileSum[t] : make_uint2(0u, 0u);
+    u32 oK, oD, oL, oM;
+    lzi_cta_scan2(v.x & 0xFFFFu, v.x >> 16, oK, oD, S, lane, warp);
+    const u32 tK = S.totA, tD = S.totB;
+    lzi_cta_scan2(v.y >> 16, v.y & 0xFFFFu, oL, oM, S, lane, warp);
+    const u32 tL = S.totA, tM = S.totB;
+    if (t < nTiles) A.tileOff[t] = make_uint4(carry[0] + oK, carry[1] + oD, carry[2] + oL, carry[3] + oM);
     __syncthreads();
-    if (tid == 0) { S.carryK += S.totA; S.carryL += S.totB >> 16; S.carryM += S.totB & 0xFFFFu; }
+    if (tid == 0) { carry[0] += tK; carry[1] += tD; carry[2] += tL; carry[3] += tM; }
     __syncthreads();
   }
-  if (tid == 0) { S.nExtL = (int)S.carryL; S.nExtM = (int)S.carryM; S.nExtLValid = 0; S.nExtMValid = 0; }
-  __syncthreads();
-  // ---- the two cursor chains ----
+  if (tid == 0) { H.nExtL = (int)carry[2]; H.nExtM = (int)carry[3]; }
+}
+// T3: extK[j] = ordinary literal bytes before extended-literal token j
+__global__ void __launch_bounds__(LZI_TT) lzi_tok_extk_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P, LziTok* toks, i64 tokStride, LziHdr* __restrict__ hdrs,
+                                                             u32* extPool, u32* tilePool, i64 tileStride) {
+  __shared__ LziShared S;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.y;
+  if (!hdrs[b].valid) return;
+  LziLayout Y;
+  if (!lzi_layout(blocks[b], P, b, Y)) return;
+  const int base = blockIdx.x * LZI_TT;
+  if (base >= Y.nTokBytes) return;
+  const LziArrays A = lzi_arrays(toks, extPool, tilePool, tokStride, tileStride, b);
+  const int t = base + tid;
+  const bool on = t < Y.nTokBytes;
+  const LziFlags F = lzi_flags(on ? blocks[b].cur[Y.tkBase + t] : 0, on);
+  const uint4 off = A.tileOff[blockIdx.x];
+  u32 kOff, cOff;
+  lzi_cta_scan2(F.known, (u32)F.lExt, kOff, cOff, S, lane, warp);
+  if (F.lExt) A.extK[off.z + cOff] = off.x + kOff;
+}
+// T4 (one CTA per block): the two cursor chains
+__global__ void __launch_bounds__(LZI_TT) lzi_tok_chase_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P, LziTok* toks, i64 tokStride, LziHdr* __restrict__ hdrs,
+                                                              u32* extPool, u32* tilePool, i64 tileStride) {
+  __shared__ LziShared S;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.x;
+  LziHdr& H = hdrs[b];
+  if (!H.valid) return;
+  LziLayout Y;
+  if (!lzi_layout(blocks[b], P, b, Y)) return;
+  const LziArrays A = lzi_arrays(toks, extPool, tilePool, tokStride, tileStride, b);
+  const u8* __restrict__ src = blocks[b].cur;
+  const int count = Y.count, mLenBase = Y.mLenBase;
+  u32* extK = A.extK; u32* extE = A.extE; u32* extLS = A.extLS; u32* mxVal = A.mxVal;
   // warp 1 decodes the match-length records on its own; the other 31 warps stage windows of the literal area and of
   // extK in shared memory so that thread 0's chase runs at shared-memory latency (named barrier 1, 992 threads)
+  const bool dbg = ((P.flags >> 12) & 1) != 0;
+  const long long tStart = clock64();
   if (warp == 1) {
-    const int nExtM = S.nExtM;
+    const int nExtM = H.nExtM;
     u32 c = (u32)mLenBase; int k = 0;
     while (k < nExtM) {
       if (c + 32 + 4 > (u32)count + 8) {                         // tail: one record at a time
@@ -170,160 +249,294 @@ __global__ void __launch_bounds__(LZI_TT) lzi_tokens_kernel(KzgBlock* __restrict
         k++; c += sz;
       }
     }
-    if (lane == 0) S.nExtMValid = k;
+    if (lane == 0) H.nExtMValid = k;
+    if (dbg && lane == 0) printf("lzi chase block %d: %d match-length records, warp 1 took %lld cycles\n", b, nExtM, clock64() - tStart);
   } else {
+    // Record j sits at c_j = 13 + extK[j] + E_j with E_{j+1} = E_j + (record bytes + literal bytes it announces): a chain of
+    // dependent loads by construction.  The 31 warps take everything else off that chain: for every byte position of a
+    // 16 KiB window they precompute what a record starting there would add (G), so that thread 0's step is one shared load
+    // and two additions; the E values it leaves behind are turned into extE / extLS by the same warps afterwards.
     const int wtid = (warp == 0) ? tid : tid - 32;             // 0..991
-    const int nExtL = S.nExtL;
+    const int nExtL = H.nExtL;
+    const u32 lim = (u32)count + 8;
     u32 E = 0; int j = 0;                                       // (thread 0)
     bool stop = (nExtL == 0);
+    u32 wbOld = 0; int pj0 = 0, pj1 = 0;
+    int nWin = 0; long long tChase = 0;
     for (;;) {
       if (tid == 0) {
         if (!stop) {
           const u32 c = 13u + extK[j] + E;
-          if (c + 4 > (u32)count + 8) stop = true;              // beyond the block: whatever follows cannot be a live token
-          S.winBase = c; S.winJ = j;
+          if (c + 4 > lim) stop = true;                         // beyond the block: whatever follows cannot be a live token
+          S.winBase = c;
         }
+        S.winJ = j;
         S.chaseDone = stop ? 1 : 0;
       }
       asm volatile("bar.sync 1, 992;" ::: "memory");
+      pj1 = S.winJ;
+      // records the chase placed in the previous window: their lengths and sizes
+      for (int i = pj0 + wtid; i < pj1; i += 992) {
+        const u32 e = S.winE[i - pj0];
+        const u32 c = wbOld + S.winK[i - pj0] + e;
+        u32 r = src[c], sz;
+        if (r < 254) sz = 1;
+        else if (r == 254) { r += ((u32)src[c + 1] << 8) + (u32)src[c + 2]; sz = 3; }
+        else { r += ((u32)src[c + 1] << 16) + ((u32)src[c + 2] << 8) + (u32)src[c + 3]; sz = 4; }
+        extE[i] = e; extLS[i] = (7 + r) | (sz << 28);
+      }
       if (S.chaseDone) break;
-      const u32 wb = S.winBase; const int j0 = S.winJ;
-      for (int i = wtid; i < LZI_WIN + 8; i += 992) S.win[i] = (wb + i < (u32)count + 8) ? src[wb + i] : (u8)0;
-      for (int i = wtid; i < LZI_KB; i += 992) S.winK[i] = (j0 + i < nExtL) ? extK[j0 + i] : 0u;
+      const u32 wb = S.winBase; const int j0 = pj1;
+      asm volatile("bar.sync 1, 992;" ::: "memory");           // winK / winE of the previous window are consumed
+      for (int i = wtid; i < LZI_KB; i += 992) S.winK[i] = (j0 + i < nExtL) ? (13u + extK[j0 + i] - wb) : 0u;   // relative to the window
+      for (int x = wtid; x < LZI_WIN; x += 992) {
+        const u32 c = wb + (u32)x;
+        u32 g = 0;
+        if (c + 4 <= lim) {
+          u32 r = src[c], sz;
+          if (r < 254) sz = 1;
+          else if (r == 254) { r += ((u32)src[c + 1] << 8) + (u32)src[c + 2]; sz = 3; }
+          else { r += ((u32)src[c + 1] << 16) + ((u32)src[c + 2] << 8) + (u32)src[c + 3]; sz = 4; }
+          g = min(7u + r + sz, 0xFFFFu);
+        }
+        S.G[x] = (u16)g;
+      }
+      if (wtid < 128 && wb + LZI_WIN + 128u * wtid < lim) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + wb + LZI_WIN + 128u * wtid));
       asm volatile("bar.sync 1, 992;" ::: "memory");
       if (tid == 0) {
-        while (j < nExtL && j - j0 < LZI_KB) {
-          const u32 c = 13u + S.winK[j - j0] + E;
-          if (c + 4 > wb + LZI_WIN + 8) break;                  // next window
-          if (c + 4 > (u32)count + 8) { stop = true; break; }
-          const u8* w = S.win + (c - wb);
-          u32 r = w[0], sz;
-          if (r < 254) sz = 1;
-          else if (r == 254) { r += ((u32)w[1] << 8) + (u32)w[2]; sz = 3; }
-          else { r += ((u32)w[1] << 16) + ((u32)w[2] << 8) + (u32)w[3]; sz = 4; }
-          const u32 len = 7 + r;
-          extE[j] = E; extLS[j] = len | (sz << 28);
-          E += len + sz;
+        nWin++; const long long tc = clock64();
+        // The loop-carried chain is e -> c = base[j] + e -> G[c] -> e + g.  Four steps are issued back to back with the
+        // range and sentinel tests kept off that chain (checked once per group); a step that fails them is redone by the
+        // careful loop below.
+        const int jMax = min(nExtL, j0 + LZI_KB);
+        const u32 hiRel = min((u32)LZI_WIN, lim - 3u - wb);     // c valid iff c < hiRel (inside the window and the block)
+        const int* kb = reinterpret_cast<const int*>(S.winK);
+        for (;;) {
+          int e = (int)E;
+          while (j + 4 <= jMax) {
+            const int q = j - j0;
+            const int c0 = kb[q] + e;      const u32 g0 = S.G[min((u32)c0, (u32)LZI_WIN - 1u)]; const int e1 = e + (int)g0;
+            const int c1 = kb[q + 1] + e1; const u32 g1 = S.G[min((u32)c1, (u32)LZI_WIN - 1u)]; const int e2 = e1 + (int)g1;
+            const int c2 = kb[q + 2] + e2; const u32 g2 = S.G[min((u32)c2, (u32)LZI_WIN - 1u)]; const int e3 = e2 + (int)g2;
+            const int c3 = kb[q + 3] + e3; const u32 g3 = S.G[min((u32)c3, (u32)LZI_WIN - 1u)]; const int e4 = e3 + (int)g3;
+            const bool v0 = ((u32)c0 < hiRel) && (g0 != 0xFFFFu), v1 = ((u32)c1 < hiRel) && (g1 != 0xFFFFu);
+            const bool v2 = ((u32)c2 < hiRel) && (g2 != 0xFFFFu), v3 = ((u32)c3 < hiRel) && (g3 != 0xFFFFu);
+            if (v0 && v1 && v2 && v3) { S.winE[q] = (u32)e; S.winE[q + 1] = (u32)e1; S.winE[q + 2] = (u32)e2; S.winE[q + 3] = (u32)e3; e = e4; j += 4; continue; }
+            if (!v0) break;
+            S.winE[q] = (u32)e; e = e1; j++;
+            if (!v1) break;
+            S.winE[q + 1] = (u32)e; e = e2; j++;
+            if (!v2) break;
+            S.winE[q + 2] = (u32)e; e = e3; j++;
+            break;
+          }
+          E = (u32)e;
+          // one careful step: the group's odd record, the last records of a window, a long run
+          if (j >= jMax) break;
+          const u32 c = wb + S.winK[j - j0] + E;
+          if (c >= wb + LZI_WIN) break;                         // next window
+          if (c + 4 > lim) { stop = true; break; }
+          u32 g = S.G[c - wb];
+          if (g == 0xFFFFu) {                                   // a literal run of 64 KiB or more
+            u32 r = src[c], sz;
+            if (r == 254) { r += ((u32)src[c + 1] << 8) + (u32)src[c + 2]; sz = 3; }
+            else { r += ((u32)src[c + 1] << 16) + ((u32)src[c + 2] << 8) + (u32)src[c + 3]; sz = 4; }
+            g = 7u + r + sz;
+          }
+          S.winE[j - j0] = E;
+          E += g;
           j++;
         }
         if (j >= nExtL) stop = true;
+        tChase += clock64() - tc;
       }
+      wbOld = wb; pj0 = j0;
     }
-    if (tid == 0) { extE[j] = E; S.nExtLValid = j; }
+    (void)wbOld;
+    if (tid == 0) { extE[j] = E; H.nExtLValid = j; }
+    if (dbg && tid == 0) printf("lzi chase block %d: %d literal records, %d windows, %lld cycles (%lld in the chain)\n", b, nExtL, nWin, clock64() - tStart, tChase);
+  }
+}
+// inclusive scan of repeat-offset maps over the CTA: on return (s0, s1) is the map from the CTA's entry state to the state
+// after this thread's element; S.totA / S.totB hold the map of the whole CTA tile
+__device__ __forceinline__ void lzi_cta_mapscan(u32& s0, u32& s1, LziShared& S, int tid, int lane, int warp) {
+  for (int o = 1; o < 32; o <<= 1) {
+    const u32 p0 = __shfl_up_sync(0xFFFFFFFFu, s0, o), p1 = __shfl_up_sync(0xFFFFFFFFu, s1, o);
+    if (lane >= o) { const u32 n0 = lzi_apply(s0, p0, p1), n1 = lzi_apply(s1, p0, p1); s0 = n0; s1 = n1; }
   }
   __syncthreads();
-  if (tid == 0) { S.carryK = 0; S.carryL = 0; S.carryM = 0; S.carryD = (u32)distBase; S.carryOut = 0; S.rep0 = (u32)count; S.rep1 = (u32)count; }
+  if (lane == 31) { S.wm0[warp] = s0; S.wm1[warp] = s1; }
   __syncthreads();
-  const int nExtLValid = S.nExtLValid, nExtMValid = S.nExtMValid;
-  // ---- tile loop 2: lengths, cursors, repeat offsets, output offsets ----
-  int nTok = 0;
+  if (tid == 0) {                                // map from the tile entry to the start of every warp
+    u32 r0 = LZI_IN0, r1 = LZI_IN1;
+    for (int w = 0; w < 32; w++) {
+      S.ws0[w] = r0; S.ws1[w] = r1;
+      const u32 n0 = lzi_apply(S.wm0[w], r0, r1), n1 = lzi_apply(S.wm1[w], r0, r1);
+      r0 = n0; r1 = n1;
+    }
+    S.rep0 = r0; S.rep1 = r1;
+  }
+  __syncthreads();
+  const u32 n0 = lzi_apply(s0, S.ws0[warp], S.ws1[warp]), n1 = lzi_apply(s1, S.ws0[warp], S.ws1[warp]);
+  s0 = n0; s1 = n1;
+}
+#define LZI_F_FAIL 1u
+#define LZI_F_LIT 2u
+#define LZI_F_MATCH 4u
+// T5: lengths, cursors and, relative to the tile, output offsets and repeat-offset selectors of every token
+__global__ void __launch_bounds__(LZI_TT) lzi_tok_span_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P, LziTok* toks, i64 tokStride, LziHdr* __restrict__ hdrs,
+                                                             u32* extPool, u32* tilePool, i64 tileStride) {
+  __shared__ LziShared S;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.y;
+  LziHdr& H = hdrs[b];
+  if (!H.valid) return;
+  LziLayout Y;
+  if (!lzi_layout(blocks[b], P, b, Y)) return;
+  const int base = blockIdx.x * LZI_TT;
+  if (base >= Y.nTokBytes) return;
+  const LziArrays A = lzi_arrays(toks, extPool, tilePool, tokStride, tileStride, b);
+  const u8* __restrict__ src = blocks[b].cur;
+  const int nExtLValid = H.nExtLValid, nExtMValid = H.nExtMValid;
+  const int t = base + tid;
+  const bool on = t < Y.nTokBytes;
+  const int token = on ? src[Y.tkBase + t] : 0;
+  const LziFlags F = lzi_flags(token, on);
+  const uint4 off = A.tileOff[blockIdx.x];
+  u32 aOff, cOff;
+  lzi_cta_scan2(F.known | (F.nd << 16), ((u32)F.lExt << 16) | (u32)F.mExt, aOff, cOff, S, lane, warp);   // (sums stay below 2^16 per tile)
+  const u32 kOff = aOff & 0xFFFFu, ndOff = aOff >> 16;
+  const u32 jb = off.z + (cOff >> 16), kb = off.w + (cOff & 0xFFFFu);
+  bool bad = false;
+  u32 litLen = F.known, extSz = 0;
+  const u32 Eb = A.extE[min(jb, (u32)nExtLValid)];
+  if (F.lExt) {
+    if ((int)jb >= nExtLValid) bad = true;
+    else { const u32 ls = A.extLS[jb]; litLen = ls & 0x0FFFFFFFu; extSz = ls >> 28; }
+  } else if ((int)jb > nExtLValid) bad = true;
+  const u32 litSrc = 13u + off.x + kOff + Eb + extSz;
+  const u32 litAfter = litSrc + litLen;
+  u32 mLen = on ? (u32)(F.isRep ? (token & 3) : (token & 7)) + (u32)Y.minMatch : 0u;
+  bool mBad = false;
+  if (F.mExt) { if ((int)kb >= nExtMValid) mBad = true; else mLen += A.mxVal[kb]; }
+  // the walk ends at the first literal-carrying token whose literals reach srcEnd (:673-674)
+  const bool isLast = F.hasLit && (bad || ((i32)litAfter >= Y.srcEndLit));
+  __syncthreads();
+  if (tid == 0) S.lastIdx = 0x7FFFFFFF;
+  __syncthreads();
+  if (isLast) atomicMin(&S.lastIdx, tid);
+  __syncthreads();
+  const int lastIdx = S.lastIdx;
+  int nValid = min(LZI_TT, Y.nTokBytes - base);
   bool finished = false;
-  u32 litCurEnd = 13;
-  for (int base = 0; base < nTokBytes && !finished; base += LZI_TT) {
-    const int t = base + tid;
-    const bool on = t < nTokBytes;
-    const int token = on ? src[tkBase + t] : 0;
-    const bool hasLit = on && token >= 32;
-    const bool lExt = hasLit && token >= 0xE0;
-    const int f = token & 0x18;
-    const bool isRep = (f == 0);
-    const bool mExt = on && (isRep ? ((token & 3) == 3) : ((token & 7) == 7));
-    const u32 nd = (on && !isRep) ? (u32)(f >> 3) : 0u;
-    const u32 known = (hasLit && !lExt) ? (u32)(token >> 5) : 0u;
-    u32 kOff, cOff;
-    u32 aOff;
-    lzi_cta_scan2(known | (nd << 16), ((u32)lExt << 16) | (u32)mExt, aOff, cOff, S, lane, warp);   // (sums stay below 2^16 per tile)
-    kOff = aOff & 0xFFFFu;
-    const u32 totA = S.totA, totC = S.totB;
-    const u32 jb = S.carryL + (cOff >> 16), kb = S.carryM + (cOff & 0xFFFFu), ndOff = aOff >> 16;
-    bool bad = false;
-    u32 litLen = known, extSz = 0;
-    u32 Eb = extE[min(jb, (u32)nExtLValid)];
-    if (lExt) {
-      if ((int)jb >= nExtLValid) bad = true;
-      else { const u32 ls = extLS[jb]; litLen = ls & 0x0FFFFFFFu; extSz = ls >> 28; }
-    } else if ((int)jb > nExtLValid) bad = true;
-    const u32 litSrc = 13u + S.carryK + kOff + Eb + extSz;
-    const u32 litAfter = litSrc + litLen;
-    u32 mLen = on ? (u32)(isRep ? (token & 3) : (token & 7)) + (u32)minMatch : 0u;
-    bool mBad = false;
-    if (mExt) { if ((int)kb >= nExtMValid) mBad = true; else mLen += mxVal[kb]; }
-    // the walk ends at the first literal-carrying token whose literals reach srcEnd (:673-674)
-    const bool isLast = hasLit && (bad || ((i32)litAfter >= srcEndLit));
-    __syncthreads();
-    if (tid == 0) S.lastIdx = 0x7FFFFFFF;
-    __syncthreads();
-    if (isLast) atomicMin(&S.lastIdx, tid);
-    __syncthreads();
-    const int lastIdx = S.lastIdx;
-    int nValid = min(LZI_TT, nTokBytes - base);
-    if (lastIdx != 0x7FFFFFFF) { nValid = lastIdx + 1; finished = true; }
-    const bool live = tid < nValid;
-    const bool hasMatch = live && !(finished && tid == nValid - 1);
-    if (!hasMatch) mLen = 0;
-    bool fail = live && (bad || (hasMatch && mBad));
-    if (live && hasLit && (litAfter > (u32)litEnd)) fail = true;
-    // distances: explicit bytes, then the repeat-offset scan
-    u32 dExp = 0;
-    if (hasMatch && !isRep) {
-      const u32 c = S.carryD + ndOff;
-      if (c + nd > (u32)count + 8) fail = true;
-      else { dExp = src[c]; if (nd >= 2) dExp = (dExp << 8) | src[c + 1]; if (nd == 3) dExp = (dExp << 8) | src[c + 2]; }
-    }
-    // map of this token: NEW(d): (d, IN0); REP0: (IN0, IN0); REP1: (IN1, IN0); no match: identity
-    u32 m0, m1;
-    if (!hasMatch) { m0 = LZI_IN0; m1 = LZI_IN1; }
-    else if (!isRep) { m0 = dExp; m1 = LZI_IN0; }
-    else if ((token & 0x04) == 0) { m0 = LZI_IN0; m1 = LZI_IN0; }
-    else { m0 = LZI_IN1; m1 = LZI_IN0; }
-    u32 s0 = m0, s1 = m1;                       // inclusive scan of map composition (later o earlier) inside the warp
-    for (int o = 1; o < 32; o <<= 1) {
-      const u32 p0 = __shfl_up_sync(0xFFFFFFFFu, s0, o), p1 = __shfl_up_sync(0xFFFFFFFFu, s1, o);
-      if (lane >= o) { const u32 n0 = lzi_apply(s0, p0, p1), n1 = lzi_apply(s1, p0, p1); s0 = n0; s1 = n1; }
-    }
-    if (lane == 31) { S.wm0[warp] = s0; S.wm1[warp] = s1; }
-    const u32 span = live ? (litLen + mLen) : 0u;
-    u32 spanOff, dummy;
-    lzi_cta_scan2(span, 0u, spanOff, dummy, S, lane, warp);     // (its barriers also publish wm0/wm1)
-    const u32 totSpan = S.totA;
-    if (tid == 0) {                              // state at the start of every warp
-      u32 r0 = S.rep0, r1 = S.rep1;
-      for (int w = 0; w < 32; w++) {
-        S.ws0[w] = r0; S.ws1[w] = r1;
-        const u32 n0 = lzi_apply(S.wm0[w], r0, r1), n1 = lzi_apply(S.wm1[w], r0, r1);
-        r0 = n0; r1 = n1;
-      }
-      S.rep0 = r0; S.rep1 = r1;
-    }
-    __syncthreads();
-    const u32 dist = lzi_apply(s0, S.ws0[warp], S.ws1[warp]);
-    const u32 outPos = S.carryOut + spanOff;
-    if (live) {
-      // sanity checks of the reference (:657-661, 706-711)
-      if (hasLit && (litLen > (u32)dstEnd - min(outPos, (u32)dstEnd))) fail = true;
-      if (hasMatch) {
-        const u32 mStart = outPos + litLen;
-        if (dist > mStart || dist == 0 || dist > (u32)maxDist || mStart + mLen > (u32)dstEnd) fail = true;
-      }
-      LziTok tk; tk.outPos = outPos; tk.litSrc = litSrc; tk.litLen = litLen; tk.mLen = mLen; tk.dist = dist;
-      T[nTok + tid] = tk;
-      if (tid == nValid - 1) { S.totA = litAfter; }             // literal cursor after the last live token (tokens without literals keep it)
-    }
-    if (fail) S.fail = 1;
-    __syncthreads();
-    litCurEnd = S.totA;
-    if (tid == 0) {
-      S.carryK += totA & 0xFFFFu; S.carryD += totA >> 16; S.carryL += totC >> 16; S.carryM += totC & 0xFFFFu; S.carryOut += totSpan;
-    }
-    nTok += nValid;
-    __syncthreads();
-    if (S.fail) return;                         // inverse returns false (res[0] stays 0)
+  if (lastIdx != 0x7FFFFFFF) { nValid = lastIdx + 1; finished = true; }
+  const bool live = tid < nValid;
+  const bool hasMatch = live && !(finished && tid == nValid - 1);
+  if (!hasMatch) mLen = 0;
+  bool fail = live && (bad || (hasMatch && mBad));
+  if (live && F.hasLit && (litAfter > (u32)Y.litEnd)) fail = true;
+  // distances: explicit bytes, then the repeat-offset scan
+  u32 dExp = 0;
+  if (hasMatch && !F.isRep) {
+    const u32 c = (u32)Y.distBase + off.y + ndOff;
+    if (c + F.nd > (u32)Y.count + 8) fail = true;
+    else { dExp = src[c]; if (F.nd >= 2) dExp = (dExp << 8) | src[c + 1]; if (F.nd == 3) dExp = (dExp << 8) | src[c + 2]; }
   }
-  if (!finished) return;
+  // map of this token: NEW(d): (d, IN0); REP0: (IN0, IN0); REP1: (IN1, IN0); no match: identity
+  u32 s0, s1;
+  if (!hasMatch) { s0 = LZI_IN0; s1 = LZI_IN1; }
+  else if (!F.isRep) { s0 = dExp; s1 = LZI_IN0; }
+  else if ((token & 0x04) == 0) { s0 = LZI_IN0; s1 = LZI_IN0; }
+  else { s0 = LZI_IN1; s1 = LZI_IN0; }
+  lzi_cta_mapscan(s0, s1, S, tid, lane, warp);
+  const u32 tile0 = S.rep0, tile1 = S.rep1;
+  const u32 span = live ? (litLen + mLen) : 0u;
+  u32 spanOff, dummy;
+  lzi_cta_scan2(span, 0u, spanOff, dummy, S, lane, warp);
+  if (live) {
+    LziTok tk; tk.outPos = spanOff; tk.litSrc = litSrc; tk.litLen = litLen; tk.mLen = mLen; tk.dist = s0;
+    tk.flags = (fail ? LZI_F_FAIL : 0u) | (F.hasLit ? LZI_F_LIT : 0u) | (hasMatch ? LZI_F_MATCH : 0u);
+    A.T[t] = tk;
+  }
   if (tid == 0) {
-    H.nTok = nTok; H.outLen = (i32)S.carryOut; H.ok = (litCurEnd == (u32)litEnd) ? 1 : 0;      // `return srcIdx == srcEnd + 13`
-    res[1] = (int)S.carryOut;                   // res[0] is set by the gather pass
+    A.tileSpan[blockIdx.x] = make_uint4(S.totA, tile0, tile1, 0u);
+    if (finished) atomicMin(&H.lastTok, base + lastIdx);
   }
+}
+// T6 (one CTA per block): output offset and repeat-offset state at the start of every tile
+__global__ void __launch_bounds__(LZI_TT) lzi_tok_scan2_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P, LziTok* toks, i64 tokStride, LziHdr* __restrict__ hdrs,
+                                                              u32* extPool, u32* tilePool, i64 tileStride) {
+  __shared__ LziShared S;
+  __shared__ u32 carryOut, c0, c1;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.x;
+  LziHdr& H = hdrs[b];
+  if (!H.valid || H.lastTok == 0x7FFFFFFF) return;
+  LziLayout Y;
+  if (!lzi_layout(blocks[b], P, b, Y)) return;
+  const LziArrays A = lzi_arrays(toks, extPool, tilePool, tokStride, tileStride, b);
+  const int nTiles = H.lastTok / LZI_TT + 1;
+  if (tid == 0) { carryOut = 0; c0 = (u32)Y.count; c1 = (u32)Y.count; }
+  __syncthreads();
+  for (int base = 0; base < nTiles; base += LZI_TT) {
+    const int t = base + tid;
+    const uint4 v = (t < nTiles) ? A.tileSpan[t] : make_uint4(0u, LZI_IN0, LZI_IN1, 0u);
+    u32 s0 = v.y, s1 = v.z;
+    lzi_cta_mapscan(s0, s1, S, tid, lane, warp);          // inclusive: state after tile t as a function of the chunk's entry state
+    const u32 all0 = S.rep0, all1 = S.rep1;
+    // exclusive = inclusive of the element before
+    u32 e0 = __shfl_up_sync(0xFFFFFFFFu, s0, 1), e1 = __shfl_up_sync(0xFFFFFFFFu, s1, 1);
+    __syncthreads();
+    if (lane == 31) { S.wm0[warp] = s0; S.wm1[warp] = s1; }
+    __syncthreads();
+    if (lane == 0) { if (warp == 0) { e0 = LZI_IN0; e1 = LZI_IN1; } else { e0 = S.wm0[warp - 1]; e1 = S.wm1[warp - 1]; } }
+    u32 oOff, dummy;
+    lzi_cta_scan2(v.x, 0u, oOff, dummy, S, lane, warp);
+    const u32 totOut = S.totA;
+    if (t < nTiles) { A.tileOut[t] = carryOut + oOff; A.tileRep[t] = make_uint2(lzi_apply(e0, c0, c1), lzi_apply(e1, c0, c1)); }
+    __syncthreads();
+    if (tid == 0) { carryOut += totOut; const u32 n0 = lzi_apply(all0, c0, c1), n1 = lzi_apply(all1, c0, c1); c0 = n0; c1 = n1; }
+    __syncthreads();
+  }
+}
+// T7: absolute output offsets and distances, the reference's sanity checks (:657-661, 706-711)
+__global__ void __launch_bounds__(256) lzi_tok_final_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P, LziTok* toks, i64 tokStride, LziHdr* __restrict__ hdrs,
+                                                           u32* extPool, u32* tilePool, i64 tileStride) {
+  const int b = blockIdx.y;
+  LziHdr& H = hdrs[b];
+  if (!H.valid) return;
+  const int lastTok = H.lastTok;
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (lastTok == 0x7FFFFFFF || t > lastTok) return;
+  LziLayout Y;
+  if (!lzi_layout(blocks[b], P, b, Y)) return;
+  const LziArrays A = lzi_arrays(toks, extPool, tilePool, tokStride, tileStride, b);
+  const int tile = t / LZI_TT;
+  LziTok tk = A.T[t];
+  const uint2 rep = A.tileRep[tile];
+  const u32 outPos = A.tileOut[tile] + tk.outPos;
+  const u32 dist = lzi_apply(tk.dist, rep.x, rep.y);
+  bool fail = (tk.flags & LZI_F_FAIL) != 0;
+  const u32 dstEnd = (u32)Y.dstEnd;
+  if ((tk.flags & LZI_F_LIT) && (tk.litLen > dstEnd - min(outPos, dstEnd))) fail = true;
+  if (tk.flags & LZI_F_MATCH) {
+    const u32 mStart = outPos + tk.litLen;
+    if (dist > mStart || dist == 0 || dist > (u32)Y.maxDist || mStart + tk.mLen > dstEnd) fail = true;
+  }
+  tk.outPos = outPos; tk.dist = dist;
+  A.T[t] = tk;
+  if (fail) H.fail = 1;
+  if (t == lastTok) {
+    H.nTokRaw = lastTok + 1; H.outLenRaw = (i32)(outPos + tk.litLen + tk.mLen);
+    H.okRaw = (tk.litSrc + tk.litLen == (u32)Y.litEnd) ? 1 : 0;                               // `return srcIdx == srcEnd + 13`
+  }
+}
+// T8: commit (a failed check anywhere leaves nTok = 0: inverse returns false, res[0] stays 0)
+__global__ void lzi_tok_commit_kernel(KzgXfParams P, LziHdr* __restrict__ hdrs, int nBlocks) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nBlocks) return;
+  LziHdr& H = hdrs[b];
+  if (!H.valid || H.lastTok == 0x7FFFFFFF || H.fail) return;
+  H.nTok = H.nTokRaw; H.outLen = H.outLenRaw; H.ok = H.okRaw;
+  P.result[2 * b + 1] = H.outLenRaw;              // res[0] is set by the gather pass
 }
 
 // ---- pass 2: pointer fill -----------------------------------------------------------------------------------------------
@@ -426,29 +639,44 @@ __global__ void __launch_bounds__(256) lzi_gather_kernel(KzgBlock* __restrict__ 
   else for (int k = 0; pos0 + k < outLen; k++) dst[pos0 + k] = (u8)(outw >> (8 * k));
 }
 
-// scratch: per block tokens (20 B each, up to maxLen/4 + 1024) + 4 bytes per output byte + header
+// scratch: per block tokens (24 B each, up to maxLen/4 + 1024) + 16 B of record lists per token + 64 B per tile of 1024 tokens
+// + 4 bytes per output byte + header
+static i64 lzi_tok_stride(i32 maxLen) { return (((i64)maxLen / 4 + 1024) + 15) & ~(i64)15; }
+static i64 lzi_tile_stride(i64 tokStride) { return (((tokStride + LZI_TT - 1) / LZI_TT + 8) + 3) & ~(i64)3; }
 void kzg_lzi_scratch(i32 maxLen, size_t* perBlockBytes, size_t* aux32) {
-  const size_t toks = (size_t)maxLen / 4 + 1024;
-  *perBlockBytes = std::max(*perBlockBytes, toks * (sizeof(LziTok) + 16) + 256 + 512);
+  const size_t toks = (size_t)lzi_tok_stride(maxLen);
+  *perBlockBytes = std::max(*perBlockBytes, toks * (sizeof(LziTok) + 16) + (size_t)lzi_tile_stride((i64)toks) * 64 + 256 + 512);
   *aux32 = std::max(*aux32, (size_t)maxLen + 64);
 }
 
 int kzg_lz_inverse_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, const KzgXfParams& P, i32 maxLen) {
   // flat scratch pool (nBlocks * scratchStride bytes): [dense headers, 256 B reserved per block][token arrays]; pointers in aux32
-  const i64 tokStride = (i64)maxLen / 4 + 1024;
-  const size_t need = (size_t)nBlocks * (256 + (size_t)tokStride * (sizeof(LziTok) + 16));
+  const i64 tokStride = lzi_tok_stride(maxLen);
+  const i64 tileStride = lzi_tile_stride(tokStride);
+  const size_t need = (size_t)nBlocks * (256 + (size_t)tokStride * (sizeof(LziTok) + 16) + (size_t)tileStride * 64);
   if (need > (size_t)nBlocks * (size_t)P.scratchStride) { kzg_set_error("lz inverse: scratch pool too small"); return -KZG_ERR_CREATE_CODEC; }
+  static_assert(sizeof(LziHdr) <= 256, "LziHdr must fit its 256-byte slot");
   LziHdr* hdrs = (LziHdr*)P.scratch;
   LziTok* toks = (LziTok*)(P.scratch + (size_t)nBlocks * 256);
   u32* extPool = (u32*)(toks + (size_t)nBlocks * tokStride);
+  u32* tilePool = extPool + (size_t)nBlocks * 4 * tokStride;
   u32* ptrs = (u32*)P.aux32;
   const i64 ptrStride = P.aux32Stride;
-  lzi_tokens_kernel<<<nBlocks, LZI_TT, 0, s>>>(d_blocks, P, toks, tokStride, hdrs, extPool);
+  const int tokTiles = (int)((tokStride + LZI_TT - 1) / LZI_TT);
+  const dim3 gT(tokTiles, nBlocks);
+  lzi_tok_sums_kernel<<<gT, LZI_TT, 0, s>>>(d_blocks, P, toks, tokStride, hdrs, extPool, tilePool, tileStride);
+  lzi_tok_scan1_kernel<<<nBlocks, LZI_TT, 0, s>>>(d_blocks, P, toks, tokStride, hdrs, extPool, tilePool, tileStride);
+  lzi_tok_extk_kernel<<<gT, LZI_TT, 0, s>>>(d_blocks, P, toks, tokStride, hdrs, extPool, tilePool, tileStride);
+  lzi_tok_chase_kernel<<<nBlocks, LZI_TT, 0, s>>>(d_blocks, P, toks, tokStride, hdrs, extPool, tilePool, tileStride);
+  lzi_tok_span_kernel<<<gT, LZI_TT, 0, s>>>(d_blocks, P, toks, tokStride, hdrs, extPool, tilePool, tileStride);
+  lzi_tok_scan2_kernel<<<nBlocks, LZI_TT, 0, s>>>(d_blocks, P, toks, tokStride, hdrs, extPool, tilePool, tileStride);
+  lzi_tok_final_kernel<<<dim3((int)((tokStride + 255) / 256), nBlocks), 256, 0, s>>>(d_blocks, P, toks, tokStride, hdrs, extPool, tilePool, tileStride);
+  lzi_tok_commit_kernel<<<(nBlocks + 63) / 64, 64, 0, s>>>(P, hdrs, nBlocks);
   const int tiles = (maxLen + LZI_TILE - 1) / LZI_TILE;
   lzi_fill_kernel<<<dim3(tiles, nBlocks), 256, 0, s>>>(d_blocks, toks, tokStride, hdrs, ptrs, ptrStride);
   for (int r = 0; r < 6; r++) lzi_jump_kernel<<<dim3(tiles, nBlocks), 256, 0, s>>>(hdrs, ptrs, ptrStride, r);
   lzi_gather_kernel<<<dim3(tiles, nBlocks), 256, 0, s>>>(d_blocks, hdrs, ptrs, ptrStride, P.result);
   CUDA_TRY(cudaGetLastError());
-  kzg_count_launch(9);
+  kzg_count_launch(16);
   return 0;
 }
