@@ -266,6 +266,12 @@ static int run_entropy_decode(Batch& bt, int entropy, const EntScratch& es, cons
 // ============================================================================================================
 // library entry points
 // ============================================================================================================
+// The LZ forward rounds run block groups on up to 32 side streams; with the default of 8 hardware work queues streams
+// alias onto each other and a group's one-warp stitch kernel serialises behind another group's parse.  The variable is
+// read when the CUDA context is created, so it only helps when this library is loaded before that (never overrides a
+// value the host already set).
+__attribute__((constructor)) static void kzg_on_load() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+
 extern "C" {
 
 int kzg_abi_version(void) { return 1; }

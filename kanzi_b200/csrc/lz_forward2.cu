@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <cstdio>
 #include <vector>
+#include <thread>
 
 #define LZ_HASH_SEED 0x1E35A7BDull
 #define LZ_MAX_DISTANCE1 ((1 << 16) - 2)
@@ -54,7 +55,8 @@ struct LzfBlock {                 // per-block scratch pointers (device)
   u32* tileSum;                   // per 1024 matches: literal-area / distance / length bytes (sums, then offsets)
   i32 segLen, nSeg, evStride, patchCap, nRng, aMax, active, needSerial;
   i32 nFin, giveUpIdx, emitGo, tkBase, mBase, mlBase;
-  i32 chkDiff, chkMax, chkFlag, chkPad;   // per-round verdict of lzf_check_marks_kernel
+  i32 chkDiff, chkMax, chkFlag;           // per-round verdict of lzf_check_marks_kernel
+  i32 estHits;                            // positions whose hash candidate is a match of 4+ bytes: how dense the parse will be
 };
 struct LzfState { i32 srcIdx, anchor, srcInc, repd0, repd1, repIdx, lastSkip, overLo, overHi; };
 // rerun: a lookup of this segment's adopted parse resolved differently under the produced bitmap -> parse it again next round;
@@ -128,7 +130,7 @@ __global__ void lzf_setup_kernel(const KzgBlock* __restrict__ blocks, int nBlock
   L.tkCap = max(count / 5, 256);                                         // tkBuf is never grown (:324-333)
   L.n = L.srcEnd + 2;                                                    // positions 0..srcEnd+1 can be visited or looked up (lazy steps)
   L.segLen = segLen; L.nSeg = max(1, (L.srcEnd + segLen - 1) / segLen);
-  L.nRng = 0; L.aMax = -1; L.active = forceSerial ? 0 : 1; L.needSerial = forceSerial;
+  L.nRng = 0; L.aMax = -1; L.active = forceSerial ? 0 : 1; L.needSerial = forceSerial; L.estHits = 0;
 }
 
 template <bool EXTRA>
@@ -280,9 +282,10 @@ __global__ void lzf_prev_kernel(LzfBlock* __restrict__ lb, int nPass, int hashBi
 }
 // ---- phase 1c: candidate match lengths ---------------------------------------------------------------------------------------------
 __global__ void lzf_cand_kernel(const KzgBlock* __restrict__ blocks, LzfBlock* __restrict__ lb) {
-  const LzfBlock& L = lb[blockIdx.y];
+  LzfBlock& L = lb[blockIdx.y];
   const int n = L.n;
   const u8* __restrict__ src = blocks[blockIdx.y].cur;
+  int hits = 0;
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
     const int ref = (int)L.prev[p];
     const int minRef = max(p - L.maxDist, 0);
@@ -290,7 +293,11 @@ __global__ void lzf_cand_kernel(const KzgBlock* __restrict__ blocks, LzfBlock* _
     if (ref > minRef && lzf_ld32(src + ref) == lzf_ld32(src + p))
       len = lzf_find_match(src, p, ref, min(L.srcEnd - p, LZ_MAX_MATCH), 256);
     L.len0[p] = (u8)min(len, 255);
+    hits += (len >= 4);
   }
+  hits = __syncthreads_count(hits > 0) ? hits : 0;
+  for (int o = 16; o > 0; o >>= 1) hits += __shfl_xor_sync(0xFFFFFFFFu, hits, o);
+  if ((threadIdx.x & 31) == 0 && hits > 0) atomicAdd(&L.estHits, hits);
 }
 
 // After the second sort (fingerprint, hash, position): a position whose predecessor differs in hash or fingerprint has no
@@ -756,6 +763,7 @@ __device__ __forceinline__ void lzf_core(const LzfBlock& L, const u8* __restrict
       l0 = L.len0[p];
       const u32 pvRaw = L.prev[p];
       pv = (int)(pvRaw & ~LZF_NOCAND);
+      if (l0 >= minMatch && pv >= 8) lzf_prefetch(src + pv - 8);     // the bytes a backward extension will compare
       // the reference tries repd[repIdx] first and only falls to the other one when the 4-byte pre-check fails (:374-387)
       u64 diff;
       if ((u32)(a8 ^ n8) == 0) { diff = a8 ^ n8; repRef = refA; }
@@ -928,8 +936,8 @@ __device__ __forceinline__ int lzf_seg_end(const LzfBlock& L, int s) { return (s
 
 // (re)start of a round.  Round 0 clears every per-round bitmap.  Later rounds parse again only the segments the check flagged:
 // their own jumped-over bits (D) are cleared, everybody else's D, log and dependency marks (C) stay; Kn is rebuilt by the stitch.
-__global__ void lzf_round_init_kernel(LzfBlock* __restrict__ lb, int first) {
-  LzfBlock& L = lb[blockIdx.y];
+__global__ void lzf_round_init_kernel(LzfBlock* __restrict__ lb, const int* __restrict__ bmap, int first) {
+  LzfBlock& L = lb[bmap[blockIdx.y]];
   if (L.n <= 0 || !L.active) return;
   if (blockIdx.x == 0 && threadIdx.x == 0) { L.chkDiff = 0; L.chkMax = -1; L.chkFlag = 0; }
   if (first) for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L.nSeg; i += gridDim.x * blockDim.x) { L.seg[i].haveTrue = 0; L.seg[i].rerun = 1; L.seg[i].adopted = 0; }
@@ -943,8 +951,8 @@ __global__ void lzf_round_init_kernel(LzfBlock* __restrict__ lb, int first) {
 }
 
 template <bool EXTRA>
-__global__ void __launch_bounds__(32) lzf_spec_kernel(const KzgBlock* __restrict__ blocks, LzfBlock* __restrict__ lb) {
-  const int b = blockIdx.y, s = blockIdx.x, lane = threadIdx.x;
+__global__ void __launch_bounds__(32) lzf_spec_kernel(const KzgBlock* __restrict__ blocks, LzfBlock* __restrict__ lb, const int* __restrict__ bmap) {
+  const int b = bmap[blockIdx.y], s = blockIdx.x, lane = threadIdx.x;
   const LzfBlock L = lb[b];
   if (L.n <= 0 || !L.active || s >= L.nSeg) return;
   if (!L.seg[s].rerun) return;                 // its log still stands (no lookup of it resolved differently last round)
@@ -1049,8 +1057,8 @@ struct LzfSync {           // stitcher side of the re-synchronisation test
 };
 
 template <bool EXTRA>
-__global__ void __launch_bounds__(32) lzf_stitch_kernel(const KzgBlock* __restrict__ blocks, LzfBlock* __restrict__ lb, int dbg) {
-  const int b = blockIdx.x, lane = threadIdx.x;
+__global__ void __launch_bounds__(32) lzf_stitch_kernel(const KzgBlock* __restrict__ blocks, LzfBlock* __restrict__ lb, const int* __restrict__ bmap, int dbg) {
+  const int b = bmap[blockIdx.x], lane = threadIdx.x;
   const LzfBlock L = lb[b];
   if (L.n <= 0 || !L.active) return;
   const u8* __restrict__ src = blocks[b].cur;
@@ -1127,8 +1135,8 @@ __device__ __forceinline__ int lzf_resolve(const LzfBlock& L, const u32* __restr
   while (q > 0 && ((X[q >> 5] >> (q & 31)) & 1u)) q = (int)(L.prev[q] & ~LZF_NOCAND);
   return q;
 }
-__global__ void __launch_bounds__(256) lzf_check_marks_kernel(LzfBlock* __restrict__ lb) {
-  LzfBlock& L = lb[blockIdx.y];
+__global__ void __launch_bounds__(256) lzf_check_marks_kernel(LzfBlock* __restrict__ lb, const int* __restrict__ bmap) {
+  LzfBlock& L = lb[bmap[blockIdx.y]];
   if (L.n <= 0 || !L.active || L.needSerial) return;
   const int nW = (L.n + 31) / 32 + 1;
   int differ = 0, mx = -1, flagged = 0;
@@ -1155,20 +1163,29 @@ __global__ void __launch_bounds__(256) lzf_check_marks_kernel(LzfBlock* __restri
   if (__syncthreads_or(flagged) && threadIdx.x == 0) L.chkFlag = 1;
   if (mx >= 0) atomicMax(&L.chkMax, mx);
 }
-__global__ void lzf_check_final_kernel(LzfBlock* __restrict__ lb, int nBlocks, int lastRound, int* __restrict__ nActive, int dbg) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nBlocks) return;
+__global__ void lzf_check_final_kernel(LzfBlock* __restrict__ lb, const int* __restrict__ bmap, int nBlocks, int lastRound, int* __restrict__ nActive, int dbg) {
+  const int i = blockIdx.x;
+  if (i >= nBlocks) return;
+  const int b = bmap[i];
   LzfBlock& L = lb[b];
   if (L.n <= 0 || !L.active) return;
-  if ((dbg & 1) && L.chkDiff) {
-    int nr = 0; for (int s = 0; s < L.nSeg; s++) nr += L.seg[s].rerun;
-    printf("lzf check block %d: bitmaps differ, %d segments to parse again, Kn max %d\n", b, nr, L.chkMax);
+  __shared__ int go;
+  if (threadIdx.x == 0) {
+    if ((dbg & 1) && L.chkDiff) {
+      int nr = 0; for (int s = 0; s < L.nSeg; s++) nr += L.seg[s].rerun;
+      printf("lzf check block %d: bitmaps differ, %d segments to parse again, Kn max %d\n", b, nr, L.chkMax);
+    }
+    go = 0;
+    if (L.needSerial) { L.active = 0; }
+    else if (!L.chkDiff || !L.chkFlag) { L.active = 0; }
+    else if (lastRound) { L.active = 0; L.needSerial = 1; }
+    else { u32* t = L.A; L.A = L.Kn; L.Kn = t; L.aMax = L.chkMax; atomicAdd(nActive, 1); go = 1; }
+    if (L.needSerial) atomicAdd(nActive + 1, 1);
   }
-  if (L.needSerial) { L.active = 0; }
-  else if (!L.chkDiff || !L.chkFlag) { L.active = 0; }
-  else if (lastRound) { L.active = 0; L.needSerial = 1; }
-  else { u32* t = L.A; L.A = L.Kn; L.Kn = t; L.aMax = L.chkMax; atomicAdd(nActive, 1); }
-  if (L.needSerial) atomicAdd(nActive + 1, 1);
+  __syncthreads();
+  // a block that runs another round also parses again the segments the stitcher could not adopt: started from the state the
+  // stitcher reached them in (srcInc included) they are adopted at once next time instead of being walked by one warp again
+  if (go) for (int s = 1 + threadIdx.x; s < L.nSeg; s += blockDim.x) if (!L.seg[s].adopted) L.seg[s].rerun = 1;
 }
 
 // ---- phase 4: tokens from the match list (:467-538, :568-596) ----------------------------------------------------------------------
@@ -1402,7 +1419,7 @@ static LzfSizes lzf_sizes(i32 maxLen) {
   z.key = lzf_al(8 * n); z.sa = lzf_al(4 * n); z.prev = lzf_al(4 * n); z.len0 = lzf_al(n); z.skipped = lzf_al(n / 8 + 64);
   z.hist = lzf_al(4 * 256 * nT);
   z.tk = lzf_al(std::max<size_t>(n / 5, 256) + 64); z.m = lzf_al(n + 64); z.ml = lzf_al(n / 2 + 64);
-  static const int segMin = getenv("KZG_LZ_SEG") ? std::max(8192, atoi(getenv("KZG_LZ_SEG")) / 4096 * 4096) : 32768;   // developer knob
+  static const int segMin = getenv("KZG_LZ_SEG") ? std::max(8192, atoi(getenv("KZG_LZ_SEG")) / 4096 * 4096) : 16384;   // developer knob
   z.segLen = std::max(segMin, (int)((n / 512 + 4095) / 4096 * 4096));
   z.maxSeg = (int)((n + z.segLen - 1) / z.segLen);
   z.evStride = z.segLen / 4 + 16;
@@ -1426,6 +1443,18 @@ struct LzfTimer {
     for (auto e : ev) cudaEventDestroy(e);
   }
 };
+
+// per-thread pool of side streams for the grouped rounds (created once; the calling thread's codec stream forks into them)
+#define LZF_MAXG 64
+struct LzfStreams {
+  cudaStream_t st[LZF_MAXG]; cudaEvent_t fork; int n = 0; int* hCnt = nullptr;
+  int init(int g) {
+    if (!hCnt) { if (cudaMallocHost(&hCnt, 2 * LZF_MAXG * sizeof(int)) != cudaSuccess) return -1; if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess) return -1; }
+    while (n < g) { if (cudaStreamCreateWithFlags(&st[n], cudaStreamNonBlocking) != cudaSuccess) return -1; n++; }
+    return 0;
+  }
+};
+static LzfStreams& lzf_streams() { static thread_local LzfStreams S; return S; }
 
 int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, const KzgXfParams& P, bool extra, i32 maxLen) {
   const LzfSizes z = lzf_sizes(maxLen);
@@ -1480,30 +1509,68 @@ int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
   lzf_flag_kernel<<<dim3(gx, nBlocks), 256, 0, s>>>(dlb, pass);
   tm.mark("sort2");
   int launches = 6 + 3 * pass;
-  // phase 2/3: speculative segments + stitch, repeated until the assumed skipped-position bitmap is the produced one
-  int* dCnt = (int*)(base + nb * z.total);
+  // phase 2/3: speculative segments + stitch, repeated until the assumed skipped-position bitmap is the produced one.
+  // The blocks are dealt into groups that run their rounds on streams of their own: a group's stitch (one warp per block,
+  // latency bound) then overlaps the other groups' segment parses.  Blocks whose parse will be sparse (few positions with a
+  // 4-byte candidate: the stitcher walks them itself, jumped-over positions never re-synchronise) go first.
+  int* dCnt = (int*)(base + nb * z.total);                 // [2 * LZF_MAXG] counters, then the block order
+  int* dMap = dCnt + 2 * LZF_MAXG;
   int hCnt[2] = {0, (dbg & 8) ? nBlocks : 0};
   int rounds = 0;
   if (!(dbg & 8)) {
+    CUDA_TRY(cudaMemcpyAsync(hl.data(), dlb, sizeof(LzfBlock) * nb, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    std::vector<int> order(nBlocks);
+    for (int b = 0; b < nBlocks; b++) order[b] = b;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+      const double dx = hl[x].n > 0 ? (double)hl[x].estHits / hl[x].n : 2.0, dy = hl[y].n > 0 ? (double)hl[y].estHits / hl[y].n : 2.0;
+      return dx < dy;
+    });
+    static const int gEnv = getenv("KZG_LZ_GROUPS") ? atoi(getenv("KZG_LZ_GROUPS")) : 0;   // developer knob
+    const int G = std::max(1, std::min(std::min(gEnv > 0 ? gEnv : 32, LZF_MAXG), nBlocks));
+    LzfStreams& ST = lzf_streams();
+    if (ST.init(G) < 0) return -KZG_ERR_CREATE_CODEC;
+    CUDA_TRY(cudaMemcpyAsync(dMap, order.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemsetAsync(dCnt, 0, 2 * LZF_MAXG * sizeof(int), s));
+    CUDA_TRY(cudaEventRecord(ST.fork, s));
     const int maxRounds = 8;
-    for (int round = 0; round < maxRounds; round++) {
-      rounds++;
-      CUDA_TRY(cudaMemsetAsync(dCnt, 0, 2 * sizeof(int), s));
-      lzf_round_init_kernel<<<dim3(std::min(gx, 64), nBlocks), 256, 0, s>>>(dlb, round == 0 ? 1 : 0);
-      if (extra) lzf_spec_kernel<true><<<dim3(z.maxSeg, nBlocks), 32, 0, s>>>(d_blocks, dlb);
-      else lzf_spec_kernel<false><<<dim3(z.maxSeg, nBlocks), 32, 0, s>>>(d_blocks, dlb);
-      tm.mark("spec");
-      if (extra) lzf_stitch_kernel<true><<<nBlocks, 32, 0, s>>>(d_blocks, dlb, dbg);
-      else lzf_stitch_kernel<false><<<nBlocks, 32, 0, s>>>(d_blocks, dlb, dbg);
-      tm.mark("stitch");
-      lzf_check_marks_kernel<<<dim3(16, nBlocks), 256, 0, s>>>(dlb);
-      lzf_check_final_kernel<<<(nBlocks + 63) / 64, 64, 0, s>>>(dlb, nBlocks, round == maxRounds - 1 ? 1 : 0, dCnt, dbg);
+    int gBeg[LZF_MAXG + 1];
+    for (int g = 0; g <= G; g++) gBeg[g] = (int)((long long)nBlocks * g / G);
+    auto enqueue = [&](int g, int round) {
+      cudaStream_t q = ST.st[g];
+      const int* bm = dMap + gBeg[g];
+      const int cnt = gBeg[g + 1] - gBeg[g];
+      if (round > 0) cudaMemsetAsync(dCnt + 2 * g, 0, 2 * sizeof(int), q);
+      lzf_round_init_kernel<<<dim3(std::min(gx, 64), cnt), 256, 0, q>>>(dlb, bm, round == 0 ? 1 : 0);
+      if (extra) lzf_spec_kernel<true><<<dim3(z.maxSeg, cnt), 32, 0, q>>>(d_blocks, dlb, bm);
+      else lzf_spec_kernel<false><<<dim3(z.maxSeg, cnt), 32, 0, q>>>(d_blocks, dlb, bm);
+      if (extra) lzf_stitch_kernel<true><<<cnt, 32, 0, q>>>(d_blocks, dlb, bm, dbg);
+      else lzf_stitch_kernel<false><<<cnt, 32, 0, q>>>(d_blocks, dlb, bm, dbg);
+      lzf_check_marks_kernel<<<dim3(16, cnt), 256, 0, q>>>(dlb, bm);
+      lzf_check_final_kernel<<<cnt, 128, 0, q>>>(dlb, bm, cnt, round == maxRounds - 1 ? 1 : 0, dCnt + 2 * g, dbg);
+      cudaMemcpyAsync(ST.hCnt + 2 * g, dCnt + 2 * g, 2 * sizeof(int), cudaMemcpyDeviceToHost, q);
       launches += 5;
-      CUDA_TRY(cudaMemcpyAsync(hCnt, dCnt, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
-      CUDA_TRY(cudaStreamSynchronize(s));
-      tm.mark("check");
-      if (hCnt[0] == 0) break;
+    };
+    int groupRound[LZF_MAXG];
+    bool live[LZF_MAXG];
+    for (int g = 0; g < G; g++) { CUDA_TRY(cudaStreamWaitEvent(ST.st[g], ST.fork, 0)); groupRound[g] = 0; live[g] = true; enqueue(g, 0); }
+    int nLive = G;
+    while (nLive > 0) {                                    // whichever group has finished its round gets the next one
+      bool progressed = false;
+      for (int g = 0; g < G; g++) {
+        if (!live[g]) continue;
+        const cudaError_t qe = cudaStreamQuery(ST.st[g]);
+        if (qe == cudaErrorNotReady) continue;
+        if (qe != cudaSuccess) { kzg_set_error("lz forward: %s", cudaGetErrorString(qe)); return -KZG_ERR_PROCESS_BLOCK; }
+        progressed = true;
+        rounds = std::max(rounds, groupRound[g] + 1);
+        if (ST.hCnt[2 * g] == 0 || groupRound[g] + 1 >= maxRounds) { live[g] = false; nLive--; hCnt[1] += ST.hCnt[2 * g + 1]; continue; }
+        groupRound[g]++;
+        enqueue(g, groupRound[g]);
+      }
+      if (!progressed) std::this_thread::yield();          // (rounds last milliseconds; a query costs microseconds)
     }
+    tm.mark("rounds");
   }
   if (dbg & 1) fprintf(stderr, "lzf: %d blocks, %d rounds, %d serial\n", nBlocks, rounds, hCnt[1]);
   if (hCnt[1] > 0) {
