@@ -600,13 +600,17 @@ __global__ void __launch_bounds__(256) lzi_jump_kernel(LziHdr* __restrict__ hdrs
   uint4 q = *reinterpret_cast<uint4*>(ptr + pos0);
   u32 v[4] = {q.x, q.y, q.z, q.w};
   bool changed = false, open = false;
+  u32 p[4] = {v[0], v[1], v[2], v[3]};
+  for (int hop = 0; hop < 16; hop++) {          // the four chains advance together: four independent loads in flight per step
+    const bool o0 = !(p[0] & LZI_LIT), o1 = !(p[1] & LZI_LIT), o2 = !(p[2] & LZI_LIT), o3 = !(p[3] & LZI_LIT);
+    if (!(o0 | o1 | o2 | o3)) break;
+    const u32 n0 = o0 ? ptr[p[0]] : p[0], n1 = o1 ? ptr[p[1]] : p[1], n2 = o2 ? ptr[p[2]] : p[2], n3 = o3 ? ptr[p[3]] : p[3];
+    p[0] = n0; p[1] = n1; p[2] = n2; p[3] = n3;
+  }
   #pragma unroll
   for (int k = 0; k < 4; k++) {
-    u32 p = v[k];
-    if (p & LZI_LIT) continue;
-    for (int hop = 0; hop < 16 && !(p & LZI_LIT); hop++) p = ptr[p];
-    if (p != v[k]) { v[k] = p; changed = true; }
-    if (!(p & LZI_LIT)) open = true;
+    if (p[k] != v[k]) { v[k] = p[k]; changed = true; }
+    if (!(p[k] & LZI_LIT)) open = true;
   }
   if (changed) *reinterpret_cast<uint4*>(ptr + pos0) = make_uint4(v[0], v[1], v[2], v[3]);
   if (open) H.done[round] = 1;                                // benign race: any writer stores 1
