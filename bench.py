@@ -99,7 +99,7 @@ def cpu_arm(data, transforms, entropy, bs, sample_mb, flags, steps=1, warmup=0):
     te, td = sum(enc_t) / len(enc_t), sum(dec_t) / len(dec_t)
     mb = len(sample) / 1e6
     return {"value": mb / (te + td), "unit": "MB/s", "cores": cores, "kind": "port",
-            "sample": f"first {len(sample)} bytes ({len(sample) // bs} blocks) of the workload, {cores} threads, one block per thread",
+            "sample": f"first {len(sample)} bytes ({(len(sample) + bs - 1) // bs} blocks) of the workload, {cores} threads, one block per thread",
             "encode_MBps": mb / te, "decode_MBps": mb / td, "ms_per_step": 1e3 * (te + td)}
 
 

@@ -22,6 +22,7 @@
 #include <cstdio>
 #include <vector>
 #include <thread>
+#include <chrono>
 
 #define LZ_HASH_SEED 0x1E35A7BDull
 #define LZ_MAX_DISTANCE1 ((1 << 16) - 2)
@@ -56,12 +57,13 @@ struct LzfBlock {                 // per-block scratch pointers (device)
   i32 segLen, nSeg, evStride, patchCap, nRng, aMax, active, needSerial;
   i32 nFin, giveUpIdx, emitGo, tkBase, mBase, mlBase;
   i32 chkDiff, chkMax, chkFlag;           // per-round verdict of lzf_check_marks_kernel
-  i32 estHits;                            // positions whose hash candidate is a match of 4+ bytes: how dense the parse will be
+  i32 direct;                             // the stitcher parsed the whole block itself against a real table (sparse block)
+  i32 estHits[8];                         // per eighth of the block: positions whose hash candidate is a match of 4+ bytes (how dense the parse will be)
 };
 struct LzfState { i32 srcIdx, anchor, srcInc, repd0, repd1, repIdx, lastSkip, overLo, overHi; };
 // rerun: a lookup of this segment's adopted parse resolved differently under the produced bitmap -> parse it again next round;
 // adopted: the stitched parse of this round took (part of) the segment's own log
-struct LzfSeg { LzfState entry; LzfState end; LzfState trueEntry; i32 nEv; i32 fail; i32 haveTrue; int16_t rerun; int16_t adopted; };
+struct LzfSeg { LzfState entry; LzfState end; LzfState trueEntry; i32 nEv; i32 fail; i32 haveTrue; int16_t rerun; int16_t adopted; i32 nSkip; i32 pad; };
 struct LzfRange { const uint4* ev; i32 count; i32 start; };
 
 __device__ __forceinline__ u64 lzf_ld64(const u8* __restrict__ p) {
@@ -130,7 +132,7 @@ __global__ void lzf_setup_kernel(const KzgBlock* __restrict__ blocks, int nBlock
   L.tkCap = max(count / 5, 256);                                         // tkBuf is never grown (:324-333)
   L.n = L.srcEnd + 2;                                                    // positions 0..srcEnd+1 can be visited or looked up (lazy steps)
   L.segLen = segLen; L.nSeg = max(1, (L.srcEnd + segLen - 1) / segLen);
-  L.nRng = 0; L.aMax = -1; L.active = forceSerial ? 0 : 1; L.needSerial = forceSerial; L.estHits = 0;
+  L.nRng = 0; L.aMax = -1; L.active = forceSerial ? 0 : 1; L.needSerial = forceSerial; L.direct = 0; for (int k = 0; k < 8; k++) L.estHits[k] = 0;
 }
 
 template <bool EXTRA>
@@ -285,19 +287,26 @@ __global__ void lzf_cand_kernel(const KzgBlock* __restrict__ blocks, LzfBlock* _
   LzfBlock& L = lb[blockIdx.y];
   const int n = L.n;
   const u8* __restrict__ src = blocks[blockIdx.y].cur;
-  int hits = 0;
-  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+  // consecutive CTAs take consecutive ranges, so that a CTA's hits all fall into one or two eighths of the block
+  const int per = (n + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int beg = blockIdx.x * per, end = min(beg + per, n);
+  const int eighth = max((n + 7) / 8, 1);
+  int hits = 0, hits2 = 0;
+  const int e0 = beg / eighth;
+  for (int p = beg + threadIdx.x; p < end; p += blockDim.x) {
     const int ref = (int)L.prev[p];
     const int minRef = max(p - L.maxDist, 0);
     int len = 0;
     if (ref > minRef && lzf_ld32(src + ref) == lzf_ld32(src + p))
       len = lzf_find_match(src, p, ref, min(L.srcEnd - p, LZ_MAX_MATCH), 256);
     L.len0[p] = (u8)min(len, 255);
-    hits += (len >= 4);
+    if (len >= 4) { if (p / eighth == e0) hits++; else hits2++; }
   }
-  hits = __syncthreads_count(hits > 0) ? hits : 0;
-  for (int o = 16; o > 0; o >>= 1) hits += __shfl_xor_sync(0xFFFFFFFFu, hits, o);
-  if ((threadIdx.x & 31) == 0 && hits > 0) atomicAdd(&L.estHits, hits);
+  for (int o = 16; o > 0; o >>= 1) { hits += __shfl_xor_sync(0xFFFFFFFFu, hits, o); hits2 += __shfl_xor_sync(0xFFFFFFFFu, hits2, o); }
+  if ((threadIdx.x & 31) == 0) {
+    if (hits > 0) atomicAdd(&L.estHits[min(e0, 7)], hits);
+    if (hits2 > 0) atomicAdd(&L.estHits[min(e0 + 1, 7)], hits2);
+  }
 }
 
 // After the second sort (fingerprint, hash, position): a position whose predecessor differs in hash or fingerprint has no
@@ -932,7 +941,245 @@ __device__ __forceinline__ void lzf_core(const LzfBlock& L, const u8* __restrict
   st.lastSkip = lastSkip; st.overLo = overLo; st.overHi = overHi;
 }
 
+// ---- the whole-block walk against a real table (sparse blocks) -------------------------------------------------------------------
+// Where nearly every position is jumped over (srcInc >> 6 large for long stretches: noise, PCM) speculative segments never
+// meet the true parse (srcInc is part of the state and only a match resets it) and the chains of hs[] consist of
+// jumped-over entries, so each lookup walks dozens of them.  Such a block is cheap to parse in order instead: the visits
+// are few, 32 of them are evaluated per step, and the table is the reference's own (`hashes`, LZCodec.java:372-376): T[h] =
+// last inserted position, kept in global memory (L2 resident), updated for every visit and every match interior.
+__device__ __forceinline__ u32 lzf_hash_of(u64 w, bool extra) { return (u32)(((w << 24) * LZ_HASH_SEED) >> (extra ? (64 - 19) : (64 - 16))); }
+
+template <bool EXTRA>
+__device__ __forceinline__ void lzf_direct_core(const LzfBlock& L, const u8* __restrict__ src, u32* __restrict__ T, u32* __restrict__ Kn, LzfState& st,
+                                                uint4* __restrict__ ev, int& nEv, const int evCap, int& fail, const int lane) {
+  const int srcEnd = L.srcEnd, maxDist = L.maxDist, minMatch = L.minMatch;
+  int srcIdx = st.srcIdx, anchor = st.anchor, srcInc = st.srcInc, repd0 = st.repd0, repd1 = st.repd1, repIdx = st.repIdx;
+  int lastSkip = st.lastSkip;
+  const u32 lower = (1u << lane) - 1;
+  int spanSeg = srcIdx / L.segLen, spanMatches = 0;
+  auto insertRange = [&](int lo, int hi) {            // T[hash(q)] = q for q in [lo, hi), in order (max wins)
+    for (int q = lo + lane; q < hi; q += 32) atomicMax(&T[lzf_hash_of(lzf_ld64(src + q), EXTRA)], (u32)q);
+    __threadfence_block(); __syncwarp();
+  };
+  auto markSkipped = [&](int lo, int hi) {            // one lane: positions lo..hi were jumped over (the bitmap later segments and the check read)
+    hi = min(hi, srcEnd);
+    if (lo > hi) return;
+    const int w0 = lo >> 5, w1 = hi >> 5;
+    for (int w = w0; w <= w1; w++) {
+      u32 mask = 0xFFFFFFFFu;
+      if (w == w0) mask &= 0xFFFFFFFFu << (lo & 31);
+      if (w == w1) mask &= 0xFFFFFFFFu >> (31 - (hi & 31));
+      atomicOr(&Kn[w], mask);
+    }
+  };
+  auto save = [&]() { st.srcIdx = srcIdx; st.anchor = anchor; st.srcInc = srcInc; st.repd0 = repd0; st.repd1 = repd1; st.repIdx = repIdx;
+                      st.lastSkip = lastSkip; st.overLo = 0; st.overHi = -1; };
+  while (srcIdx < srcEnd) {
+    // back to the segment logs once the data turns dense again (a segment's worth of positions with a match per KiB)
+    const int sg = srcIdx / L.segLen;
+    if (sg != spanSeg) {
+      // the segments entered are not adopted this round; should the block run another one they are parsed again from the
+      // state recorded here and adopted at once
+      if (lane == 0) {
+        for (int k = spanSeg + 1; k <= min(sg, L.nSeg - 1); k++) {
+          LzfSeg& S = L.seg[k];
+          S.trueEntry.srcIdx = srcIdx; S.trueEntry.anchor = anchor; S.trueEntry.srcInc = srcInc; S.trueEntry.repd0 = repd0; S.trueEntry.repd1 = repd1;
+          S.trueEntry.repIdx = repIdx; S.trueEntry.lastSkip = lastSkip; S.trueEntry.overLo = 0; S.trueEntry.overHi = -1;
+          S.haveTrue = 1; S.adopted = 0;
+        }
+      }
+      if (spanMatches >= (sg - spanSeg) * (L.segLen >> 10)) { save(); return; }
+      spanSeg = sg; spanMatches = 0;
+    }
+    // ---- the next 32 visits, assuming the ones before each are misses ----
+    const u32 stepExtra = (u32)((srcInc + lane) >> 6);
+    u32 exIncl = stepExtra;
+    if (srcInc + 31 >= 64) {
+      for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(0xFFFFFFFFu, exIncl, o); if (lane >= o) exIncl += t; }
+    }
+    const int p = srcIdx + lane + (int)(exIncl - stepExtra);
+    const bool valid = p < min(srcEnd, (sg + 1) * L.segLen);      // (a batch ends with its segment: the state recorded above is the stitcher's)
+    if (srcInc >= 64) {                              // next two batches of a run of misses: pull their lines in (see lzf_core)
+      int nb = __shfl_sync(0xFFFFFFFFu, p + (int)stepExtra + 1, 31);
+      #pragma unroll
+      for (int d = 1; d <= 2; d++) {
+        const int inc = srcInc + 32 * d;
+        const int e0 = inc >> 6, kc = 64 - (inc & 63);
+        const int q = nb + lane * (1 + e0) + max(0, lane - kc);
+        if (q < srcEnd) {
+          lzf_prefetch(src + q);
+          if (q + 1 - repd0 > 0) lzf_prefetch(src + q + 1 - repd0);
+          if (q + 1 - repd1 > 0) lzf_prefetch(src + q + 1 - repd1);
+        }
+        nb += 32 * (1 + e0) + max(0, 32 - kc);
+      }
+    }
+    bool hit = false;
+    int repSmall = 0, repRef = 0, cnd = 0;
+    u32 h = 0x80000000u | (u32)lane;                 // (lanes without a position never match anybody)
+    if (valid) {
+      const int p1 = p + 1;
+      const int minRef = max(p - maxDist, 0);
+      const int maxM = min(srcEnd - p1, LZ_MAX_MATCH);
+      const int rA = (lane == 0 && repIdx) ? repd1 : repd0, rB = (lane == 0 && repIdx) ? repd0 : repd1;
+      const int refA = p1 - rA, refB = p1 - rB;
+      const u64 w = lzf_ld64(src + p);
+      const u64 n8 = lzf_ld64(src + p1);
+      const u64 a8 = (refA > minRef) ? lzf_ld64(src + refA) : ~n8;
+      const u64 b8 = (refB > minRef) ? lzf_ld64(src + refB) : ~n8;
+      h = lzf_hash_of(w, EXTRA);
+      u64 diff;
+      if ((u32)(a8 ^ n8) == 0) { diff = a8 ^ n8; repRef = refA; }
+      else if ((u32)(b8 ^ n8) == 0) { diff = b8 ^ n8; repRef = refB; }
+      else { diff = 1; repRef = 0; }
+      if (repRef > 0) repSmall = (maxM < 8) ? 0 : ((diff == 0) ? 8 : ((__ffsll((long long)diff) - 1) >> 3));
+      cnd = (int)__ldcg(T + h);
+    }
+    // an earlier visit of this batch with the same hash is what the table holds by the time this one looks
+    const u32 peers = __match_any_sync(0xFFFFFFFFu, h) & lower;
+    const int peerP = __shfl_sync(0xFFFFFFFFu, p, peers ? (31 - __clz(peers)) : 0);
+    if (valid) {
+      if (peers) cnd = peerP;
+      const int minRef = max(p - maxDist, 0);
+      const bool tableHit = (cnd > minRef) && (lzf_ld32(src + cnd) == lzf_ld32(src + p));
+      hit = (repSmall >= minMatch) || tableHit;
+    }
+    const u32 stopMask = __ballot_sync(0xFFFFFFFFu, hit);
+    const u32 validMask = __ballot_sync(0xFFFFFFFFu, valid);
+    const int nValid = __popc(validMask);
+    const int nMiss = stopMask ? min(__ffs(stopMask) - 1, nValid) : nValid;
+    // ---- commit the misses: every visit enters the table ----
+    if (nMiss > 0) {
+      if (lane < nMiss) atomicMax(&T[h], (u32)p);
+      const int lastEx = __shfl_sync(0xFFFFFFFFu, (int)stepExtra, nMiss - 1);
+      const int lastP = __shfl_sync(0xFFFFFFFFu, p, nMiss - 1);
+      if (lastEx > 0) {
+        if (lane < nMiss && stepExtra > 0) markSkipped(p + 1, p + (int)stepExtra);
+        lastSkip = max(lastSkip, min(lastP + lastEx, srcEnd));
+      }
+      srcIdx = lastP + 1 + lastEx;
+      srcInc += nMiss;
+      repIdx = 0;
+      __threadfence_block(); __syncwarp();
+    }
+    if (!stopMask || nMiss >= nValid) continue;
+    if (srcIdx >= srcEnd) break;
+    // ---- one iteration of the reference loop at srcIdx (:366-566), exact ----
+    const int f = nMiss;
+    const int evRepSmall = __shfl_sync(0xFFFFFFFFu, repSmall, f);
+    const int evRepRef = __shfl_sync(0xFFFFFFFFu, repRef, f);
+    const int evCnd = __shfl_sync(0xFFFFFFFFu, cnd, f);
+    if (lane == f) atomicMax(&T[h], (u32)p);         // hashes[h0] = srcIdx (:372-373)
+    __threadfence_block(); __syncwarp();
+    int bestLen = 0;
+    const int srcIdx1 = srcIdx + 1;
+    const int minRef = max(srcIdx - maxDist, 0);
+    int ref = evRepRef;
+    int insLo;                                       // first position the match inserts again (:553-565 and :456-458)
+    if (ref > 0) bestLen = (evRepSmall < 8) ? evRepSmall : lzf_find_match_warp(src, srcIdx1, ref, min(srcEnd - srcIdx1, LZ_MAX_MATCH), lane);
+    if (bestLen < minMatch) {
+      ref = evCnd;
+      int hl = 0;
+      if ((ref > minRef) && (lzf_ld32(src + ref) == lzf_ld32(src + srcIdx))) hl = lzf_find_match_warp(src, srcIdx, ref, min(srcEnd - srcIdx, LZ_MAX_MATCH), lane);
+      bestLen = (hl >= minMatch) ? hl : 0;
+      if (bestLen < minMatch) {       // no good match
+        const int ex = srcInc >> 6;
+        if (ex > 0) {
+          if (lane == 0) markSkipped(srcIdx + 1, srcIdx + ex);
+          lastSkip = max(lastSkip, min(srcIdx + ex, srcEnd));
+          __threadfence_block(); __syncwarp();
+        }
+        srcIdx = srcIdx1 + ex;
+        srcInc++;
+        repIdx = 0;
+        continue;
+      }
+      if ((ref != srcIdx - repd0) && (ref != srcIdx - repd1)) {
+        // check if better match at next position (:405-422): the table already holds srcIdx
+        const u32 h1 = lzf_hash_of(lzf_ld64(src + srcIdx1), EXTRA);
+        const int ref1 = __shfl_sync(0xFFFFFFFFu, (int)__ldcg(T + h1), 0);
+        if (lane == 0) atomicMax(&T[h1], (u32)srcIdx1);
+        __threadfence_block(); __syncwarp();
+        if ((ref1 > minRef + 1) && (lzf_ld32(src + ref1 + bestLen - 3) == lzf_ld32(src + srcIdx1 + bestLen - 3))) {
+          const int bestLen1 = lzf_find_match_warp(src, srcIdx1, ref1, min(srcEnd - srcIdx1, LZ_MAX_MATCH), lane);
+          if (bestLen1 >= bestLen) { ref = ref1; bestLen = bestLen1; srcIdx = srcIdx1; }
+        }
+        if (EXTRA) {
+          const int srcIdx2 = srcIdx1 + 1;
+          const u32 h2 = lzf_hash_of(lzf_ld64(src + srcIdx2), EXTRA);
+          const int ref2 = __shfl_sync(0xFFFFFFFFu, (int)__ldcg(T + h2), 0);
+          if (lane == 0) atomicMax(&T[h2], (u32)srcIdx2);
+          __threadfence_block(); __syncwarp();
+          if ((ref2 > minRef + 2) && (lzf_ld32(src + ref2 + bestLen - 3) == lzf_ld32(src + srcIdx2 + bestLen - 3))) {
+            const int bestLen2 = lzf_find_match_warp(src, srcIdx2, ref2, min(srcEnd - srcIdx2, LZ_MAX_MATCH), lane);
+            if (bestLen2 >= bestLen) { ref = ref2; bestLen = bestLen2; srcIdx = srcIdx2; }
+          }
+        }
+      }
+      // extend backwards (:446-450), 8 bytes per step
+      const int visited = srcIdx;
+      while (true) {
+        const int room = min(srcIdx - anchor, ref - minRef);
+        if (room <= 0) break;
+        const bool wide = (srcIdx >= 8) && (ref >= 8);
+        int e;
+        if (wide) {
+          const u64 d = lzf_ld64(src + srcIdx - 8) ^ lzf_ld64(src + ref - 8);
+          e = (d == 0) ? 8 : (__clzll((long long)d) >> 3);
+        } else {
+          e = (src[srcIdx - 1] == src[ref - 1]) ? 1 : 0;
+        }
+        const int lim = wide ? 8 : 1;
+        const int take = min(e, room);
+        bestLen += take; ref -= take; srcIdx -= take;
+        if (take < lim) break;
+      }
+      if (bestLen > LZ_MAX_MATCH) { ref += (bestLen - LZ_MAX_MATCH); srcIdx += (bestLen - LZ_MAX_MATCH); bestLen = LZ_MAX_MATCH; }
+      insLo = srcIdx + 1;
+      if (lastSkip > srcIdx && srcIdx < visited) {   // jumped-over positions the match covers are inserted again (:553-565)
+        const int hi = min(visited, lastSkip);
+        for (int q = srcIdx + 1 + lane; q <= hi; q += 32) atomicAnd(&Kn[q >> 5], ~(1u << (q & 31)));
+        __threadfence_block(); __syncwarp();
+      }
+    } else {
+      if ((bestLen >= LZ_MAX_MATCH) || (src[srcIdx] != src[ref - 1])) { srcIdx++; insLo = srcIdx; }   // hashes[h1] = srcIdx (:456-458)
+      else { bestLen++; ref--; insLo = srcIdx + 1; }
+    }
+    srcInc = 0;
+    const int dist = srcIdx - ref;
+    repd1 = repd0; repd0 = dist; repIdx = 1;
+    if (nEv >= evCap) { fail = 1; break; }
+    if (lane == 0) ev[nEv] = make_uint4((u32)srcIdx, (u32)bestLen, (u32)dist, 0u);
+    nEv++;
+    anchor = srcIdx + bestLen;
+    insertRange(insLo, anchor);                      // (:553-565)
+    srcIdx = anchor;
+    spanMatches++;
+  }
+  save();
+}
+
 __device__ __forceinline__ int lzf_seg_end(const LzfBlock& L, int s) { return (s + 1 >= L.nSeg) ? L.srcEnd : (s + 1) * L.segLen; }
+
+// Head of every block, parsed for real before the first round.  A block starts with srcInc climbing until the first match, so
+// its first few hundred bytes nearly always hold jumped-over positions; rare 4-grams whose only earlier occurrence sits
+// there make later segments depend on them, and with nothing assumed about them the block needed a second round for a
+// handful of lookups.  The exact bits of [0, LZF_HEAD) go straight into the assumed bitmap A.
+#define LZF_HEAD 2048
+template <bool EXTRA>
+__global__ void __launch_bounds__(32) lzf_head_kernel(const KzgBlock* __restrict__ blocks, LzfBlock* __restrict__ lb) {
+  const int b = blockIdx.x, lane = threadIdx.x;
+  const LzfBlock L = lb[b];
+  if (L.n <= 0 || !L.active || L.nSeg < 2) return;
+  const u8* __restrict__ src = blocks[b].cur;
+  LzfState st;
+  st.srcIdx = 0; st.anchor = 0; st.srcInc = 0; st.repd0 = L.count; st.repd1 = L.count; st.repIdx = 0;
+  st.lastSkip = -1; st.overLo = 0; st.overHi = -1;
+  int nEv = 0, fail = 0;
+  LzfNoSync ns;
+  lzf_core<EXTRA>(L, src, st, min(LZF_HEAD, L.segLen), nullptr, -1, 0, L.A, nullptr, 0, 0x7FFFFFFF, L.patchEv, nEv, L.patchCap, fail, lane, ns);
+  if (lane == 0) lb[b].aMax = st.lastSkip;
+}
 
 // (re)start of a round.  Round 0 clears every per-round bitmap.  Later rounds parse again only the segments the check flagged:
 // their own jumped-over bits (D) are cleared, everybody else's D, log and dependency marks (C) stay; Kn is rebuilt by the stitch.
@@ -1000,7 +1247,10 @@ __global__ void __launch_bounds__(32) lzf_spec_kernel(const KzgBlock* __restrict
   }
   const LzfState entry = st;
   lzf_core<EXTRA>(L, src, st, segEnd, L.A, min(L.aMax, segStart - 1), segStart, L.D, L.C, segStart, dEnd, ev, nEv, L.evStride, fail, lane, ns);
-  if (lane == 0) { LzfSeg& S = L.seg[s]; S.entry = entry; S.end = st; S.nEv = nEv; S.fail = fail; S.rerun = 0; }
+  int nSkip = 0;
+  if (st.lastSkip >= segStart) for (int w = (segStart >> 5) + lane; w < (segEnd >> 5); w += 32) nSkip += __popc(__ldcg(L.D + w));
+  for (int o = 16; o > 0; o >>= 1) nSkip += __shfl_xor_sync(0xFFFFFFFFu, nSkip, o);
+  if (lane == 0) { LzfSeg& S = L.seg[s]; S.entry = entry; S.end = st; S.nEv = nEv; S.fail = fail; S.rerun = 0; S.nSkip = nSkip; }
 }
 
 // D == Kn on bit positions [lo, hi)?
@@ -1063,7 +1313,7 @@ __global__ void __launch_bounds__(32) lzf_stitch_kernel(const KzgBlock* __restri
   if (L.n <= 0 || !L.active) return;
   const u8* __restrict__ src = blocks[b].cur;
   int nR = 0, nPatch = 0, fail = 0;
-  int nSync = 0, nDead = 0, nOver = 0, nEnd = 0, nAtOnce = 0; long long t0 = clock64();
+  int nSync = 0, nDead = 0, nOver = 0, nEnd = 0, nAtOnce = 0, lostRun = 0, nDirect = 0, nDbg = 0; long long t0 = clock64();
   int nFin = 0;
   auto addRange = [&](const uint4* p, int cnt) { if (cnt > 0) { if (lane == 0) { L.rng[nR].ev = p; L.rng[nR].count = cnt; L.rng[nR].start = nFin; } nR++; nFin += cnt; } };
   auto applyOver = [&](const LzfState& e) {          // positions a segment jumped over beyond its own end
@@ -1089,6 +1339,11 @@ __global__ void __launch_bounds__(32) lzf_stitch_kernel(const KzgBlock* __restri
     const LzfState& en = S.entry;
     const bool atOnce = !sy.dead && st.srcIdx == en.srcIdx && st.anchor == en.anchor && st.srcInc == en.srcInc && st.repd0 == en.repd0 &&
                         st.repd1 == en.repd1 && st.repIdx == en.repIdx && lzf_bits_equal(L.D, L.Kn, segStart, st.srcIdx, lane);
+    if ((dbg & 32) && !atOnce && lane == 0 && nDbg < 6 && s > 0) {
+      nDbg++;
+      printf("lzf stitch block %d seg %d not at once: true (%d %d %d %d %d %d) entry (%d %d %d %d %d %d) dead %d nEv %d bitsEq %d\n", b, s, st.srcIdx, st.anchor, st.srcInc,
+             st.repd0, st.repd1, st.repIdx, en.srcIdx, en.anchor, en.srcInc, en.repd0, en.repd1, en.repIdx, (int)sy.dead, S.nEv, -1);
+    }
     if (atOnce) {                                      // the warm-up already was in the reference's state at the segment start
       nAtOnce++;
       sy.synced = true; sy.j = -1;
@@ -1107,8 +1362,49 @@ __global__ void __launch_bounds__(32) lzf_stitch_kernel(const KzgBlock* __restri
       if (fail) break;
       if (sy.dead) nDead++; else if (!sy.synced) nEnd++;
     }
+    if (!sy.synced && !fail) {
+      // Several segments in a row that never met the true parse, deep inside a run of misses: the data is sparse (noise,
+      // PCM ...).  Segment logs are useless there (srcInc never agrees) and the hs[] chains consist of jumped-over entries.
+      // Continue in order against a real table until the data turns dense again (lzf_direct_core).
+      // (the table is rebuilt from everything before srcIdx by this one warp: only worth it near the start of a block)
+      if (++lostRun >= 4 && st.srcInc >= 256 && s + 1 < L.nSeg && st.srcIdx < L.srcEnd && st.srcIdx <= (1 << 18)) {
+        u32* T = reinterpret_cast<u32*>(L.kb);                  // (the radix buffers are dead by now)
+        for (int i = lane; i < (EXTRA ? (1 << 19) : (1 << 16)); i += 32) T[i] = 0;
+        __threadfence_block(); __syncwarp();
+        // every position below srcIdx that was not jumped over is in the reference's table: rebuild it from the exact bitmap
+        for (int q0 = 0; q0 < st.srcIdx; q0 += 128) {           // (a streaming pass: four positions per lane in flight, lines pulled in ahead)
+          if (q0 + 4096 + 128 * lane < st.srcIdx) lzf_prefetch(src + q0 + 4096 + 128 * lane);
+          u64 w[4]; u32 km[4];
+          #pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const int q = q0 + 32 * k + lane;
+            const bool in = q > 0 && q < st.srcIdx;
+            km[k] = in ? __ldcg(L.Kn + (q >> 5)) : 0xFFFFFFFFu;
+            w[k] = in ? lzf_ld64(src + q) : 0ull;
+          }
+          #pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const int q = q0 + 32 * k + lane;
+            if (!((km[k] >> (q & 31)) & 1u)) atomicMax(&T[lzf_hash_of(w[k], EXTRA)], (u32)q);
+          }
+        }
+        __threadfence_block(); __syncwarp();
+        const int from = nPatch;
+        if (lane == 0) for (int k = s + 1; k <= min(st.srcIdx / L.segLen, L.nSeg - 1); k++) { L.seg[k].trueEntry = st; L.seg[k].haveTrue = 1; L.seg[k].adopted = 0; }
+        lzf_direct_core<EXTRA>(L, src, T, L.Kn, st, L.patchEv, nPatch, L.patchCap, fail, lane);
+        addRange(L.patchEv + from, nPatch - from);
+        if (fail) break;
+        nDirect++;
+        lostRun = 0;
+        // the segments walked this way were not adopted; the loop resumes at the segment holding srcIdx
+        const int sTo = min(st.srcIdx / L.segLen, L.nSeg);
+        s = sTo - 1;
+        continue;
+      }
+    }
     if (sy.synced) {
       nSync++;
+      lostRun = 0;
       if (lane == 0) S.adopted = 1;
       addRange(sy.spec + sy.j + 1, S.nEv - sy.j - 1);
       if (S.end.lastSkip >= segStart)                  // (nothing to merge when the segment never jumped)
@@ -1120,7 +1416,7 @@ __global__ void __launch_bounds__(32) lzf_stitch_kernel(const KzgBlock* __restri
     }
   }
   if (lane == 0) { lb[b].nRng = nR; lb[b].nFin = nFin; lb[b].giveUpIdx = 0x7FFFFFFF; if (fail) lb[b].needSerial = 1; }
-  if ((dbg & 1) && lane == 0) printf("lzf stitch block %d: %d segs, %d synced (%d at once), %d dead, %d unsynced, %d covered, %d own matches, fail %d, %lld cycles\n", b, L.nSeg, nSync, nAtOnce, nDead, nEnd, nOver, nPatch, fail, clock64() - t0);
+  if ((dbg & 1) && lane == 0) printf("lzf stitch block %d: %d segs, %d synced (%d at once), %d dead, %d unsynced, %d covered, %d own matches, %d in-order stretches, fail %d, %lld cycles\n", b, L.nSeg, nSync, nAtOnce, nDead, nEnd, nOver, nPatch, nDirect, fail, clock64() - t0);
 }
 
 // Did any lookup depend on a position whose assumed state (A) is not the produced one (Kn)?
@@ -1450,7 +1746,14 @@ struct LzfStreams {
   cudaStream_t st[LZF_MAXG]; cudaEvent_t fork; int n = 0; int* hCnt = nullptr;
   int init(int g) {
     if (!hCnt) { if (cudaMallocHost(&hCnt, 2 * LZF_MAXG * sizeof(int)) != cudaSuccess) return -1; if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess) return -1; }
-    while (n < g) { if (cudaStreamCreateWithFlags(&st[n], cudaStreamNonBlocking) != cudaSuccess) return -1; n++; }
+    int lo = 0, hi = 0;                               // (numerically lower = more urgent)
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    while (n < LZF_MAXG && n < std::max(g, 32)) {     // the groups dealt first (sparse blocks, blocks that need more rounds) get the urgent streams
+      const int levels = lo - hi + 1;
+      const int pr = hi + std::min(levels - 1, n * levels / 32);
+      if (cudaStreamCreateWithPriority(&st[n], cudaStreamNonBlocking, pr) != cudaSuccess) return -1;
+      n++;
+    }
     return 0;
   }
 };
@@ -1522,14 +1825,22 @@ int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
     CUDA_TRY(cudaStreamSynchronize(s));
     std::vector<int> order(nBlocks);
     for (int b = 0; b < nBlocks; b++) order[b] = b;
-    std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
-      const double dx = hl[x].n > 0 ? (double)hl[x].estHits / hl[x].n : 2.0, dy = hl[y].n > 0 ? (double)hl[y].estHits / hl[y].n : 2.0;
-      return dx < dy;
-    });
+    // key: the sparsest eighth of the block (a block that is sparse anywhere ties up its stitcher for long)
+    std::vector<double> key(nBlocks, 2.0);
+    for (int b = 0; b < nBlocks; b++) {
+      if (hl[b].n <= 0) continue;
+      const double per = std::max(1.0, hl[b].n / 8.0);
+      for (int k = 0; k < 8; k++) if ((long long)k * ((hl[b].n + 7) / 8) < hl[b].n) key[b] = std::min(key[b], hl[b].estHits[k] / per);
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return key[x] < key[y]; });
+    if (dbg & 1) for (int b = 0; b < nBlocks; b++) fprintf(stderr, "lzf block %d: n %d, sparsest eighth has %.4f %% positions with a 4-byte candidate\n", b, hl[b].n, 100.0 * key[b]);
     static const int gEnv = getenv("KZG_LZ_GROUPS") ? atoi(getenv("KZG_LZ_GROUPS")) : 0;   // developer knob
     const int G = std::max(1, std::min(std::min(gEnv > 0 ? gEnv : 32, LZF_MAXG), nBlocks));
     LzfStreams& ST = lzf_streams();
     if (ST.init(G) < 0) return -KZG_ERR_CREATE_CODEC;
+    if (extra) lzf_head_kernel<true><<<nBlocks, 32, 0, s>>>(d_blocks, dlb);
+    else lzf_head_kernel<false><<<nBlocks, 32, 0, s>>>(d_blocks, dlb);
+    launches++;
     CUDA_TRY(cudaMemcpyAsync(dMap, order.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemsetAsync(dCnt, 0, 2 * LZF_MAXG * sizeof(int), s));
     CUDA_TRY(cudaEventRecord(ST.fork, s));
@@ -1555,6 +1866,7 @@ int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
     bool live[LZF_MAXG];
     for (int g = 0; g < G; g++) { CUDA_TRY(cudaStreamWaitEvent(ST.st[g], ST.fork, 0)); groupRound[g] = 0; live[g] = true; enqueue(g, 0); }
     int nLive = G;
+    const auto tHost0 = std::chrono::steady_clock::now();
     while (nLive > 0) {                                    // whichever group has finished its round gets the next one
       bool progressed = false;
       for (int g = 0; g < G; g++) {
@@ -1563,6 +1875,8 @@ int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
         if (qe == cudaErrorNotReady) continue;
         if (qe != cudaSuccess) { kzg_set_error("lz forward: %s", cudaGetErrorString(qe)); return -KZG_ERR_PROCESS_BLOCK; }
         progressed = true;
+        if (dbg & 64) fprintf(stderr, "lzf t=%7.3f ms: group %d (blocks %d..%d of the order, first block %d) finished round %d, %d still active\n",
+                              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tHost0).count(), g, gBeg[g], gBeg[g + 1] - 1, order[gBeg[g]], groupRound[g], ST.hCnt[2 * g]);
         rounds = std::max(rounds, groupRound[g] + 1);
         if (ST.hCnt[2 * g] == 0 || groupRound[g] + 1 >= maxRounds) { live[g] = false; nLive--; hCnt[1] += ST.hCnt[2 * g + 1]; continue; }
         groupRound[g]++;

@@ -52,7 +52,25 @@ def small_cases():
     c["dna"] = bytes(r.choice(np.frombuffer(b"ACGT", dtype=np.uint8), 90000))
     c["numeric"] = bytes(r.choice(np.frombuffer(b"0123456789", dtype=np.uint8), 70000))
     c["rep17"] = (b"0123456789abcdef" * 7 + b"Z") * 900
+    # sparse parses (LZ jumps over most positions): noise / PCM with and without long repeats
+    c["pcm300k"] = synth.pcm_like(300000, 13).tobytes()
+    c["noise_rep400k"] = sparse_with_repeats(400000, 14)
+    c["pcm_rep300k"] = sparse_with_repeats(300000, 15, pcm=True)
     return c
+
+
+def sparse_with_repeats(n, seed, pcm=False, every=6600, length=600):
+    """Incompressible data with a long repeat every `every` bytes: LZ's miss acceleration jumps over most positions and
+    still finds the repeats (the device parses such blocks in order against a real table)."""
+    r = rng(seed)
+    d = (synth.pcm_like(n, seed) if pcm else synth.noise(n, seed)).copy()
+    for at in range(every, n - length - 1, every):
+        at2 = at + int(r.integers(0, every // 2))
+        src = int(r.integers(0, at2 - length))
+        ln = int(r.integers(length // 4, length))
+        if at2 + ln < n:
+            d[at2:at2 + ln] = d[src:src + ln]
+    return d.tobytes()
 
 
 def fibonacci_chunk():

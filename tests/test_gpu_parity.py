@@ -136,6 +136,16 @@ def test_stream_bit_exact(tr, ent, bs, flags):
     assert K.decompress(ref, len(d) + 1024, flags=flags) == d
 
 
+def test_stream_sparse_blocks():
+    """Blocks the LZ forward parses in order against a real table (sparse: nearly every position jumped over), next to dense ones."""
+    d = corpus.sparse_with_repeats(1_500_000, 21) + synth.text(700_000, 22).tobytes() + corpus.sparse_with_repeats(900_000, 23, pcm=True)
+    for tr, ent, bs in ((["LZ"], "ANS0", 1 << 20), (["LZX"], "HUFFMAN", 1 << 19), (["LZ"], "NONE", 1 << 18)):
+        ref = O.compress(d, tr, ent, bs)
+        got = K.compress(d, tr, ent, bs)
+        assert len(got) == len(ref) and got == ref, (tr, ent, len(got), len(ref), "first differing byte", first_diff(got, ref))
+        assert K.decompress(ref, len(d) + 1024) == d
+
+
 def test_stream_tiny_and_ragged():
     for n in (0, 1, 8, 15, 16, 17, 100, 1023, 1024, 1025, 4097):
         d = bytes((i * 7 + 3) & 0xFF for i in range(n))
