@@ -136,10 +136,11 @@ __global__ void lzf_setup_kernel(const KzgBlock* __restrict__ blocks, int nBlock
 }
 
 template <bool EXTRA>
-__global__ void lzf_hash_kernel(const KzgBlock* __restrict__ blocks, LzfBlock* __restrict__ lb) {
-  const LzfBlock& L = lb[blockIdx.y];
+__global__ void lzf_hash_kernel(const KzgBlock* __restrict__ blocks, LzfBlock* __restrict__ lb, const int* __restrict__ bmap) {
+  const int b = bmap[blockIdx.y];
+  const LzfBlock& L = lb[b];
   const int n = L.n;
-  const u8* __restrict__ src = blocks[blockIdx.y].cur;
+  const u8* __restrict__ src = blocks[b].cur;
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
     const u64 w = lzf_ld64(src + p);
     const u64 v = (w << 24) * LZ_HASH_SEED;                              // LZCodec.java:904-911
@@ -156,9 +157,9 @@ __global__ void lzf_hash_kernel(const KzgBlock* __restrict__ blocks, LzfBlock* _
 #define LZF_NOCAND 0x80000000u
 #define LZF_RUNSTART 0x80000000u
 #define LZF_POSMASK ((1ull << 30) - 1)
-__global__ void __launch_bounds__(32 * LZF_WARPS) lzf_hist_kernel(LzfBlock* __restrict__ lb, int shift, int mask, int k) {
+__global__ void __launch_bounds__(32 * LZF_WARPS) lzf_hist_kernel(LzfBlock* __restrict__ lb, const int* __restrict__ bmap, int shift, int mask, int k) {
   __shared__ u32 cnt[LZF_WARPS][256];
-  const LzfBlock& L = lb[blockIdx.y];
+  const LzfBlock& L = lb[bmap[blockIdx.y]];
   const int n = L.n;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x * LZF_WARPS + warp;
@@ -172,10 +173,10 @@ __global__ void __launch_bounds__(32 * LZF_WARPS) lzf_hist_kernel(LzfBlock* __re
   __syncwarp();
   for (int d = lane; d < 256; d += 32) L.hist[(size_t)d * nT + tile] = cnt[warp][d];
 }
-__global__ void __launch_bounds__(1024) lzf_scan_kernel(LzfBlock* __restrict__ lb) {
+__global__ void __launch_bounds__(1024) lzf_scan_kernel(LzfBlock* __restrict__ lb, const int* __restrict__ bmap) {
   __shared__ u32 wsum[32];
   __shared__ u32 carry;
-  const LzfBlock& L = lb[blockIdx.x];
+  const LzfBlock& L = lb[bmap[blockIdx.x]];
   if (L.n <= 0) return;
   const int total = 256 * ((L.n + LZF_WT - 1) / LZF_WT);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -205,13 +206,13 @@ __global__ void __launch_bounds__(1024) lzf_scan_kernel(LzfBlock* __restrict__ l
 // __match_any_sync), the per-warp digit counts are scanned across warps and digits, the elements are staged in shared
 // memory in digit order and leave from there: consecutive threads write consecutive elements of a digit run, so the
 // stores cover whole sectors (element-wise scattering costs ~3x the DRAM traffic in partial-sector fills and evictions).
-__global__ void __launch_bounds__(32 * LZF_WARPS) lzf_scatter_kernel(LzfBlock* __restrict__ lb, int shift, int mask, int k) {
+__global__ void __launch_bounds__(32 * LZF_WARPS) lzf_scatter_kernel(LzfBlock* __restrict__ lb, const int* __restrict__ bmap, int shift, int mask, int k) {
   __shared__ u64 stage[LZF_WT];
   __shared__ u32 cnt[LZF_WARPS][256];
   __shared__ u32 digitBase[256 + 1];
   __shared__ u32 gOff[256];
   __shared__ u32 wsum[LZF_WARPS];
-  const LzfBlock& L = lb[blockIdx.y];
+  const LzfBlock& L = lb[bmap[blockIdx.y]];
   const int n = L.n;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tile = blockIdx.x;
@@ -267,8 +268,8 @@ __global__ void __launch_bounds__(32 * LZF_WARPS) lzf_scatter_kernel(LzfBlock* _
   }
 }
 // after the hash passes: sorted[i-1] precedes sorted[i] in (hash, position) order: same hash -> it is the previous occurrence
-__global__ void lzf_prev_kernel(LzfBlock* __restrict__ lb, int nPass, int hashBits) {
-  const LzfBlock& L = lb[blockIdx.y];
+__global__ void lzf_prev_kernel(LzfBlock* __restrict__ lb, const int* __restrict__ bmap, int nPass, int hashBits) {
+  const LzfBlock& L = lb[bmap[blockIdx.y]];
   const int n = L.n;
   const u64* __restrict__ sorted = (nPass & 1) ? L.kb : L.ka;
   const u64 hmask = ((1ull << hashBits) - 1) << 30;
@@ -283,10 +284,11 @@ __global__ void lzf_prev_kernel(LzfBlock* __restrict__ lb, int nPass, int hashBi
   }
 }
 // ---- phase 1c: candidate match lengths ---------------------------------------------------------------------------------------------
-__global__ void lzf_cand_kernel(const KzgBlock* __restrict__ blocks, LzfBlock* __restrict__ lb) {
-  LzfBlock& L = lb[blockIdx.y];
+__global__ void lzf_cand_kernel(const KzgBlock* __restrict__ blocks, LzfBlock* __restrict__ lb, const int* __restrict__ bmap) {
+  const int b = bmap[blockIdx.y];
+  LzfBlock& L = lb[b];
   const int n = L.n;
-  const u8* __restrict__ src = blocks[blockIdx.y].cur;
+  const u8* __restrict__ src = blocks[b].cur;
   // consecutive CTAs take consecutive ranges, so that a CTA's hits all fall into one or two eighths of the block
   const int per = (n + (int)gridDim.x - 1) / (int)gridDim.x;
   const int beg = blockIdx.x * per, end = min(beg + per, n);
@@ -312,8 +314,8 @@ __global__ void lzf_cand_kernel(const KzgBlock* __restrict__ blocks, LzfBlock* _
 // After the second sort (fingerprint, hash, position): a position whose predecessor differs in hash or fingerprint has no
 // earlier occurrence of its first 4 bytes among the positions with its hash, so no table content can ever pass the 4-byte
 // pre-check there (:389-395, :405-422 need bestLen >= 4).  Those positions never need the table: flag them in prev[].
-__global__ void lzf_flag_kernel(LzfBlock* __restrict__ lb, int nPass) {
-  const LzfBlock& L = lb[blockIdx.y];
+__global__ void lzf_flag_kernel(LzfBlock* __restrict__ lb, const int* __restrict__ bmap, int nPass) {
+  const LzfBlock& L = lb[bmap[blockIdx.y]];
   const int n = L.n;
   const u64* __restrict__ sorted = (nPass & 1) ? L.kb : L.ka;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -1167,8 +1169,8 @@ __device__ __forceinline__ int lzf_seg_end(const LzfBlock& L, int s) { return (s
 // handful of lookups.  The exact bits of [0, LZF_HEAD) go straight into the assumed bitmap A.
 #define LZF_HEAD 2048
 template <bool EXTRA>
-__global__ void __launch_bounds__(32) lzf_head_kernel(const KzgBlock* __restrict__ blocks, LzfBlock* __restrict__ lb) {
-  const int b = blockIdx.x, lane = threadIdx.x;
+__global__ void __launch_bounds__(32) lzf_head_kernel(const KzgBlock* __restrict__ blocks, LzfBlock* __restrict__ lb, const int* __restrict__ bmap) {
+  const int b = bmap[blockIdx.x], lane = threadIdx.x;
   const LzfBlock L = lb[b];
   if (L.n <= 0 || !L.active || L.nSeg < 2) return;
   const u8* __restrict__ src = blocks[b].cur;
@@ -1740,6 +1742,35 @@ struct LzfTimer {
   }
 };
 
+// How repetitive is each eighth of a block?  One CTA hashes the 4-grams of a 4 KiB sample into a 64 Kibit set and counts the
+// positions whose 4-gram was already there.  The sparsest eighth decides how early the block's group is dealt (the order
+// must be known before anything else runs: every group runs its whole pipeline on a stream of its own).
+__global__ void __launch_bounds__(256) lzf_sample_kernel(const KzgBlock* __restrict__ blocks, const LzfBlock* __restrict__ lb, int* __restrict__ key) {
+  __shared__ u32 seen[2048];
+  __shared__ int dup;
+  const int b = blockIdx.y, e = blockIdx.x;
+  const LzfBlock& L = lb[b];
+  if (L.n <= 0) return;
+  const int eighth = (L.n + 7) / 8;
+  const int beg = e * eighth;
+  if (beg >= L.n) return;
+  const int len = min(min(eighth, L.n - beg), 4096);
+  const u8* __restrict__ src = blocks[b].cur + beg + max(0, (min(eighth, L.n - beg) - len) / 2);
+  for (int i = threadIdx.x; i < 2048; i += 256) seen[i] = 0;
+  if (threadIdx.x == 0) dup = 0;
+  __syncthreads();
+  int d = 0;
+  for (int i = threadIdx.x; i < len; i += 256) {
+    const u32 hsh = (lzf_ld32(src + i) * 0x9E3779B1u) >> 16;
+    const u32 bit = 1u << (hsh & 31);
+    if (atomicOr(&seen[hsh >> 5], bit) & bit) d++;
+  }
+  for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xFFFFFFFFu, d, o);
+  if ((threadIdx.x & 31) == 0 && d) atomicAdd(&dup, d);
+  __syncthreads();
+  if (threadIdx.x == 0) atomicMin(&key[b], (int)(((long long)dup << 16) / max(len, 1)));
+}
+
 // per-thread pool of side streams for the grouped rounds (created once; the calling thread's codec stream forks into them)
 #define LZF_MAXG 64
 struct LzfStreams {
@@ -1788,59 +1819,63 @@ int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
   LzfTimer tm(s, (dbg & 16) != 0);
   lzf_setup_kernel<<<(nBlocks + 63) / 64, 64, 0, s>>>(d_blocks, nBlocks, P, dlb, z.segLen, (dbg & 8) ? 1 : 0);
   const int gx = std::max(1, std::min((maxLen + 255) / 256, 8 * KZG_SM_COUNT));
-  if (extra) lzf_hash_kernel<true><<<dim3(gx, nBlocks), 256, 0, s>>>(d_blocks, dlb);
-  else lzf_hash_kernel<false><<<dim3(gx, nBlocks), 256, 0, s>>>(d_blocks, dlb);
   const int nT = (maxLen + LZF_WT - 1) / LZF_WT;
-  dim3 gridT((nT + LZF_WARPS - 1) / LZF_WARPS, nBlocks);
   const int bits = extra ? 19 : 16, fpBits = extra ? 13 : 16;
-  int pass = 0;
-  for (int shift = 0; shift < bits; shift += 8, pass++) {
-    const int mask = (1 << std::min(8, bits - shift)) - 1;
-    lzf_hist_kernel<<<gridT, 32 * LZF_WARPS, 0, s>>>(dlb, 30 + shift, mask, pass);
-    lzf_scan_kernel<<<nBlocks, 1024, 0, s>>>(dlb);
-    lzf_scatter_kernel<<<dim3(nT, nBlocks), 32 * LZF_WARPS, 0, s>>>(dlb, 30 + shift, mask, pass);
-  }
-  tm.mark("sort1");
-  lzf_prev_kernel<<<dim3(gx, nBlocks), 256, 0, s>>>(dlb, pass, bits);
-  lzf_cand_kernel<<<dim3(gx, nBlocks), 256, 0, s>>>(d_blocks, dlb);
-  for (int shift = 0; shift < fpBits; shift += 8, pass++) {   // second sort key: the 4-byte fingerprint
-    const int mask = (1 << std::min(8, fpBits - shift)) - 1;
-    lzf_hist_kernel<<<gridT, 32 * LZF_WARPS, 0, s>>>(dlb, 30 + bits + shift, mask, pass);
-    lzf_scan_kernel<<<nBlocks, 1024, 0, s>>>(dlb);
-    lzf_scatter_kernel<<<dim3(nT, nBlocks), 32 * LZF_WARPS, 0, s>>>(dlb, 30 + bits + shift, mask, pass);
-  }
-  lzf_flag_kernel<<<dim3(gx, nBlocks), 256, 0, s>>>(dlb, pass);
-  tm.mark("sort2");
-  int launches = 6 + 3 * pass;
-  // phase 2/3: speculative segments + stitch, repeated until the assumed skipped-position bitmap is the produced one.
-  // The blocks are dealt into groups that run their rounds on streams of their own: a group's stitch (one warp per block,
-  // latency bound) then overlaps the other groups' segment parses.  Blocks whose parse will be sparse (few positions with a
-  // 4-byte candidate: the stitcher walks them itself, jumped-over positions never re-synchronise) go first.
-  int* dCnt = (int*)(base + nb * z.total);                 // [2 * LZF_MAXG] counters, then the block order
+  int launches = 2;
+  int* dCnt = (int*)(base + nb * z.total);                 // [2 * LZF_MAXG] counters, the block order, the sampled keys
   int* dMap = dCnt + 2 * LZF_MAXG;
+  int* dKey = dMap + nb;
+  // phase 1 of `cnt` blocks (bm = their indices) on stream q: hashes, hash sort, prev / len0, fingerprint sort, flags, block head
+  auto sortPhase = [&](cudaStream_t q, const int* bm, int cnt, bool head) {
+    const dim3 gridT((nT + LZF_WARPS - 1) / LZF_WARPS, cnt);
+    if (extra) lzf_hash_kernel<true><<<dim3(gx, cnt), 256, 0, q>>>(d_blocks, dlb, bm);
+    else lzf_hash_kernel<false><<<dim3(gx, cnt), 256, 0, q>>>(d_blocks, dlb, bm);
+    int pass = 0;
+    for (int shift = 0; shift < bits; shift += 8, pass++) {
+      const int mask = (1 << std::min(8, bits - shift)) - 1;
+      lzf_hist_kernel<<<gridT, 32 * LZF_WARPS, 0, q>>>(dlb, bm, 30 + shift, mask, pass);
+      lzf_scan_kernel<<<cnt, 1024, 0, q>>>(dlb, bm);
+      lzf_scatter_kernel<<<dim3(nT, cnt), 32 * LZF_WARPS, 0, q>>>(dlb, bm, 30 + shift, mask, pass);
+    }
+    lzf_prev_kernel<<<dim3(gx, cnt), 256, 0, q>>>(dlb, bm, pass, bits);
+    lzf_cand_kernel<<<dim3(gx, cnt), 256, 0, q>>>(d_blocks, dlb, bm);
+    for (int shift = 0; shift < fpBits; shift += 8, pass++) {   // second sort key: the 4-byte fingerprint
+      const int mask = (1 << std::min(8, fpBits - shift)) - 1;
+      lzf_hist_kernel<<<gridT, 32 * LZF_WARPS, 0, q>>>(dlb, bm, 30 + bits + shift, mask, pass);
+      lzf_scan_kernel<<<cnt, 1024, 0, q>>>(dlb, bm);
+      lzf_scatter_kernel<<<dim3(nT, cnt), 32 * LZF_WARPS, 0, q>>>(dlb, bm, 30 + bits + shift, mask, pass);
+    }
+    lzf_flag_kernel<<<dim3(gx, cnt), 256, 0, q>>>(dlb, bm, pass);
+    launches += 4 + 3 * pass;
+    if (head) {
+      if (extra) lzf_head_kernel<true><<<cnt, 32, 0, q>>>(d_blocks, dlb, bm);
+      else lzf_head_kernel<false><<<cnt, 32, 0, q>>>(d_blocks, dlb, bm);
+      launches++;
+    }
+  };
+  // Every group of blocks runs its whole pipeline on a stream of its own: the sort passes of one group (HBM bound) overlap
+  // the segment parses of another (latency / issue bound), and a group's stitch (one warp per block) overlaps everything.
+  // Blocks with a sparse stretch go first on the urgent streams: the stitcher walks those stretches itself.
   int hCnt[2] = {0, (dbg & 8) ? nBlocks : 0};
   int rounds = 0;
-  if (!(dbg & 8)) {
-    CUDA_TRY(cudaMemcpyAsync(hl.data(), dlb, sizeof(LzfBlock) * nb, cudaMemcpyDeviceToHost, s));
+  std::vector<int> order(nBlocks);
+  for (int b = 0; b < nBlocks; b++) order[b] = b;
+  if (dbg & 8) {                                          // developer switch: everything by the serial walker
+    CUDA_TRY(cudaMemcpyAsync(dMap, order.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, s));
+    sortPhase(s, dMap, nBlocks, false);
+    CUDA_TRY(cudaStreamSynchronize(s));                   // order is stack-owned
+  } else {
+    std::vector<int> key(nBlocks, 0x7FFFFFFF);
+    CUDA_TRY(cudaMemcpyAsync(dKey, key.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, s));
+    lzf_sample_kernel<<<dim3(8, nBlocks), 256, 0, s>>>(d_blocks, dlb, dKey);
+    CUDA_TRY(cudaMemcpyAsync(key.data(), dKey, sizeof(int) * nb, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
-    std::vector<int> order(nBlocks);
-    for (int b = 0; b < nBlocks; b++) order[b] = b;
-    // key: the sparsest eighth of the block (a block that is sparse anywhere ties up its stitcher for long)
-    std::vector<double> key(nBlocks, 2.0);
-    for (int b = 0; b < nBlocks; b++) {
-      if (hl[b].n <= 0) continue;
-      const double per = std::max(1.0, hl[b].n / 8.0);
-      for (int k = 0; k < 8; k++) if ((long long)k * ((hl[b].n + 7) / 8) < hl[b].n) key[b] = std::min(key[b], hl[b].estHits[k] / per);
-    }
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return key[x] < key[y]; });
-    if (dbg & 1) for (int b = 0; b < nBlocks; b++) fprintf(stderr, "lzf block %d: n %d, sparsest eighth has %.4f %% positions with a 4-byte candidate\n", b, hl[b].n, 100.0 * key[b]);
+    if (dbg & 1) for (int b = 0; b < nBlocks; b++) fprintf(stderr, "lzf block %d: sparsest eighth repeats %.2f %% of its sampled 4-grams\n", b, key[b] == 0x7FFFFFFF ? -1.0 : 100.0 * key[b] / 65536.0);
     static const int gEnv = getenv("KZG_LZ_GROUPS") ? atoi(getenv("KZG_LZ_GROUPS")) : 0;   // developer knob
     const int G = std::max(1, std::min(std::min(gEnv > 0 ? gEnv : 32, LZF_MAXG), nBlocks));
     LzfStreams& ST = lzf_streams();
     if (ST.init(G) < 0) return -KZG_ERR_CREATE_CODEC;
-    if (extra) lzf_head_kernel<true><<<nBlocks, 32, 0, s>>>(d_blocks, dlb);
-    else lzf_head_kernel<false><<<nBlocks, 32, 0, s>>>(d_blocks, dlb);
-    launches++;
     CUDA_TRY(cudaMemcpyAsync(dMap, order.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemsetAsync(dCnt, 0, 2 * LZF_MAXG * sizeof(int), s));
     CUDA_TRY(cudaEventRecord(ST.fork, s));
@@ -1864,7 +1899,12 @@ int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
     };
     int groupRound[LZF_MAXG];
     bool live[LZF_MAXG];
-    for (int g = 0; g < G; g++) { CUDA_TRY(cudaStreamWaitEvent(ST.st[g], ST.fork, 0)); groupRound[g] = 0; live[g] = true; enqueue(g, 0); }
+    for (int g = 0; g < G; g++) {
+      CUDA_TRY(cudaStreamWaitEvent(ST.st[g], ST.fork, 0));
+      groupRound[g] = 0; live[g] = true;
+      sortPhase(ST.st[g], dMap + gBeg[g], gBeg[g + 1] - gBeg[g], true);
+      enqueue(g, 0);
+    }
     int nLive = G;
     const auto tHost0 = std::chrono::steady_clock::now();
     while (nLive > 0) {                                    // whichever group has finished its round gets the next one
@@ -1884,7 +1924,7 @@ int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
       }
       if (!progressed) std::this_thread::yield();          // (rounds last milliseconds; a query costs microseconds)
     }
-    tm.mark("rounds");
+    tm.mark("pipeline");
   }
   if (dbg & 1) fprintf(stderr, "lzf: %d blocks, %d rounds, %d serial\n", nBlocks, rounds, hCnt[1]);
   if (hCnt[1] > 0) {
