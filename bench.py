@@ -51,11 +51,14 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, gpu):
         super().__init__(daemon=True)
-        self.gpu, self.rows, self.proc = gpu, [], None
+        self.gpu, self.rows, self.proc, self.marks = gpu, [], None, []
+
+    def mark(self):
+        self.marks.append(len(self.rows))
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.rows.append([x.strip() for x in line.split(",")])
@@ -65,6 +68,12 @@ class ClockSampler(threading.Thread):
     def stop(self):
         if self.proc:
             self.proc.terminate()
+        # samples inside the resident timed region when it was long enough to hold any; otherwise everything sampled while the
+        # benchmark was running (warm-up, timed steps, e2e steps: the same workload throughout)
+        region = self.rows[self.marks[0]:self.marks[1]] if len(self.marks) >= 2 else []
+        scope = "timed region" if region else "warm-up + timed + e2e steps"
+        self.rows = region or self.rows
+        self.scope = scope
         sm = sorted(int(float(r[1])) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
         mx = [int(float(r[2])) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
         reasons = set()
@@ -73,7 +82,7 @@ class ClockSampler(threading.Thread):
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(self.rows)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(self.rows), "scope": self.scope}
 
 
 def cpu_arm(data, transforms, entropy, bs, sample_mb, flags, steps=1, warmup=0):
@@ -226,11 +235,15 @@ def main():
         torch.cuda.synchronize()
         return e0.elapsed_time(e1), e1.elapsed_time(e2), k
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t_wait = time.time()
+    while not sampler.rows and time.time() - t_wait < 3.0:      # nvidia-smi takes a moment to print its first line
+        time.sleep(0.02)
     for _ in range(a.warmup):
         step_resident(False)
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark()
     K.launch_count(reset=True)
     t_enc, t_dec, stage_e, stage_d = [], [], [], []
     for _ in range(a.steps):
@@ -238,7 +251,7 @@ def main():
         t_enc.append(te); t_dec.append(td); stage_e.append(se); stage_d.append(sd)
     barrier()
     launches = K.launch_count()
-    clocks = sampler.stop()
+    sampler.mark()
     # e2e (host buffers), fewer repetitions of the same workload
     for _ in range(min(a.warmup, 1)):
         step_e2e()
@@ -248,6 +261,7 @@ def main():
         e_enc.append(te); e_dec.append(td)
     assert np.array_equal(h_back[:n].numpy(), data), "e2e round trip mismatch"
     barrier()
+    clocks = sampler.stop()
 
     def rmax(x):          # max over ranks of a per-rank scalar
         if world == 1:
@@ -282,6 +296,13 @@ def main():
     alg_bytes = {"enc_transform_ms": n + post_bytes, "enc_entropy_ms": n + post_bytes, "enc_container_ms": 2 * post_bytes,
                  "dec_entropy_ms": post_bytes + n, "dec_transform_ms": post_bytes + n}[dom]
     achieved = alg_bytes / (stages[dom] * 1e-3) / 1e9 if stages[dom] > 0 else 0.0
+    traffic, traffic_src = None, None
+    try:      # DRAM bytes of the stage's kernels per invocation, from the committed ncu launch list (full cfg2 only)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic_cfg2.json")))
+        if a.config == "cfg2" and scale == 1.0:
+            traffic, traffic_src = int(tj[dom]), tj.get("_source")
+    except Exception:
+        pass
     line = {"metric": "encode+decode MB/s", "value": round(total_mb / (step_ms * 1e-3), 2), "unit": "MB/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": round(step_ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
@@ -293,7 +314,8 @@ def main():
                     "h2d_bytes_per_step": int(n + knz_len), "d2h_bytes_per_step": int(knz_len + n),
                     "encode_MBps": round(total_mb / (e2e_enc_ms * 1e-3), 2), "decode_MBps": round(total_mb / (e2e_dec_ms * 1e-3), 2)},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 3), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 6),
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes)},
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes),
+                         "note": "the dominant 'kernel' is a stage (all LZ forward kernels of one encode, timed with CUDA events on the library stream); its groups overlap on side streams"},
             "clocks": clocks, "gpu_launches": int(launches)}
     if not a.no_cpu_baseline:
         try:

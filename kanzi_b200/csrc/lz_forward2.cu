@@ -1779,7 +1779,7 @@ struct LzfStreams {
     if (!hCnt) { if (cudaMallocHost(&hCnt, 2 * LZF_MAXG * sizeof(int)) != cudaSuccess) return -1; if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess) return -1; }
     int lo = 0, hi = 0;                               // (numerically lower = more urgent)
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
-    while (n < LZF_MAXG && n < std::max(g, 32)) {     // the groups dealt first (sparse blocks, blocks that need more rounds) get the urgent streams
+    while (n < LZF_MAXG && n < g) {                   // the groups dealt first (sparse blocks, blocks that need more rounds) get the urgent streams
       const int levels = lo - hi + 1;
       const int pr = hi + std::min(levels - 1, n * levels / 32);
       if (cudaStreamCreateWithPriority(&st[n], cudaStreamNonBlocking, pr) != cudaSuccess) return -1;
