@@ -27,6 +27,7 @@ struct Workspace {
   u8* ioBuf[2] = {nullptr, nullptr}; size_t ioCap[2] = {0, 0};      // device copies of the host-buffer entry points' streams (grow-only)
   i64 launches = 0;
   char err[512] = {0};
+  cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr}; cudaEvent_t sideEv[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; bool sideInit = false;
 };
 static thread_local Workspace W;
 
@@ -54,6 +55,17 @@ static int ws_init() {
 }
 
 // device staging for kzg_compress / kzg_decompress (host buffers): kept between calls, cudaMalloc/cudaFree cost milliseconds each
+// side streams of the grouped decode (created once per calling thread; the first group gets the most urgent one)
+static int ws_side_init() {
+  if (W.sideInit) return 0;
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  for (int g = 0; g < 4; g++) CUDA_TRY(cudaStreamCreateWithPriority(&W.side[g], cudaStreamNonBlocking, std::min(lo, hi + g)));
+  for (int g = 0; g < 5; g++) CUDA_TRY(cudaEventCreateWithFlags(&W.sideEv[g], cudaEventDisableTiming));
+  W.sideInit = true;
+  return 0;
+}
+
 static u8* ws_io(int which, size_t bytes) {
   if (bytes > W.ioCap[which]) {
     if (W.ioBuf[which]) { cudaStreamSynchronize(W.stream); cudaFree(W.ioBuf[which]); W.ioBuf[which] = nullptr; W.ioCap[which] = 0; }
@@ -590,8 +602,11 @@ struct HostBits {
   }
 };
 
-int64_t kzg_decompress_dev(const uint8_t* d_in, int64_t nBytes, const uint8_t* h_in, int32_t flags, uint8_t* d_out, int64_t outCap,
-                           float* timing3) {
+// d_in / d_out: device stream and destination.  h_in: the stream on the host (the container walk runs there).  copyIn: the
+// device copy of the stream is not there yet, every group uploads its own byte range first.  h_out (optional): every group
+// downloads its blocks as soon as they are done.
+static int64_t decompress_impl(const uint8_t* d_in, int64_t nBytes, const uint8_t* h_in, int32_t flags, uint8_t* d_out, int64_t outCap,
+                               float* timing3, bool copyIn, uint8_t* h_out) {
   int r = ws_init(); if (r < 0) return r;
   if (nBytes < 20 || h_in == nullptr) return -KZG_ERR_INVALID_FILE;
   HostBits hb{h_in, (u64)nBytes * 8};
@@ -721,20 +736,53 @@ int64_t kzg_decompress_dev(const uint8_t* d_in, int64_t nBytes, const uint8_t* h
   CUDA_TRY(cudaMemcpyAsync(dEnabledAll, bt.hEnabled, nb * nf, cudaMemcpyHostToDevice, W.stream));
   CUDA_TRY(cudaMemcpyAsync(bt.dDstLimit, bt.hDstLimit, nb * sizeof(int), cudaMemcpyHostToDevice, W.stream));
   r = batch_upload(bt); if (r < 0) return r;
+  // Blocks are independent: contiguous groups of them run the whole decode on streams of their own (most urgent first), so
+  // that the latency-bound kernels of one group (chunk scan, the literal-record chain) overlap the streaming kernels of the
+  // others and, for host buffers, a group's upload / download overlaps the other groups' kernels.
+  const int G = (nBlocks >= 8) ? 4 : 1;
+  if (G > 1) { r = ws_side_init(); if (r < 0) return r; }
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   if (timing3) { for (int i = 0; i < 3; i++) CUDA_TRY(cudaEventCreate(&ev[i])); CUDA_TRY(cudaEventRecord(ev[0], W.stream)); }
-  if (anyEnt) { r = run_entropy_decode(bt, entropy, es, d_in, dChunks, dTab); if (r < 0) return r; }
-  if (anyNone) { r = run_entropy_decode(bt, KZG_E_NONE, es, d_in, dChunks, dTab); if (r < 0) return r; }
-  if (timing3) CUDA_TRY(cudaEventRecord(ev[1], W.stream));
-  for (int i = nf - 1; i >= 0; i--) {
-    if (fn[i] == KZG_T_NONE) continue;
-    bt.dEnabled = dEnabledAll + (size_t)i * nb;
-    r = run_transform_stage(bt, fn[i], i, false, xs, dScratch, dHash, dAux, flags); if (r < 0) return r;
+  if (G > 1) CUDA_TRY(cudaEventRecord(W.sideEv[4], W.stream));
+  cudaStream_t const mainStream = W.stream;
+  int rc = 0;
+  for (int g = 0; g < G && rc == 0; g++) {
+    const int b0 = (int)((i64)nBlocks * g / G), b1 = (int)((i64)nBlocks * (g + 1) / G), cnt = b1 - b0;
+    cudaStream_t q = (G > 1) ? W.side[g] : mainStream;
+    if (G > 1) CUDA_TRY(cudaStreamWaitEvent(q, W.sideEv[4], 0));
+    if (copyIn) {                               // the bytes that hold this group's block records (+ the slack the bit readers touch)
+      const i64 lo = (recs[b0].payBit >> 3) & ~(i64)63;
+      const i64 hi = std::min<i64>(nBytes, ((recs[b1 - 1].payBit + recs[b1 - 1].payBits + 7) >> 3) + 128);
+      if (hi > lo) CUDA_TRY(cudaMemcpyAsync((u8*)d_in + lo, h_in + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, q));
+    }
+    Batch sub = bt;
+    sub.nBlocks = cnt; sub.hBlocks = bt.hBlocks + b0; sub.dBlocks = bt.dBlocks + b0; sub.dResult = bt.dResult + 2 * b0; sub.dDstLimit = bt.dDstLimit + b0;
+    W.stream = q;                               // (the launch helpers enqueue on the calling thread's current stream)
+    do {
+      if (anyEnt) { rc = run_entropy_decode(sub, entropy, es, d_in, dChunks + (size_t)b0 * es.maxChunks, dTab + (size_t)b0 * es.maxChunks * es.tabStride); if (rc < 0) break; }
+      if (anyNone) { rc = run_entropy_decode(sub, KZG_E_NONE, es, d_in, dChunks + (size_t)b0 * es.maxChunks, dTab + (size_t)b0 * es.maxChunks * es.tabStride); if (rc < 0) break; }
+      if (timing3 && g == 0) { if (cudaEventRecord(ev[1], q) != cudaSuccess) { rc = -KZG_ERR_PROCESS_BLOCK; break; } }
+      for (int i = nf - 1; i >= 0; i--) {
+        if (fn[i] == KZG_T_NONE) continue;
+        sub.dEnabled = dEnabledAll + (size_t)i * nb + b0;
+        rc = run_transform_stage(sub, fn[i], i, false, xs, dScratch + (size_t)b0 * xs.perBlock, dHash + (size_t)b0 * xs.hashInts, dAux + (size_t)b0 * xs.aux32, flags);
+        if (rc < 0) break;
+      }
+    } while (0);
+    W.stream = mainStream;
+    if (rc < 0) break;
+    if (h_out) {                                // every block but the stream's last is blockSize bytes; the last one follows below
+      const int full = (b1 == nBlocks) ? cnt - 1 : cnt;
+      if (full > 0) CUDA_TRY(cudaMemcpyAsync(h_out + (size_t)b0 * blockSize, d_out + (size_t)b0 * blockSize, (size_t)full * blockSize, cudaMemcpyDeviceToHost, q));
+    }
+    if (G > 1) { CUDA_TRY(cudaEventRecord(W.sideEv[g], q)); CUDA_TRY(cudaStreamWaitEvent(mainStream, W.sideEv[g], 0)); }
   }
+  if (rc < 0) { for (int g = 0; g < G && G > 1; g++) cudaStreamSynchronize(W.side[g]); return rc; }
   if (timing3) CUDA_TRY(cudaEventRecord(ev[2], W.stream));
   r = batch_download(bt); if (r < 0) return r;
-  if (timing3) {
-    CUDA_TRY(cudaEventElapsedTime(&timing3[1], ev[0], ev[1])); CUDA_TRY(cudaEventElapsedTime(&timing3[0], ev[1], ev[2])); timing3[2] = 0;
+  if (timing3) {      // [1] = entropy stage of the first group, [0] = everything else up to the join (groups overlap: a split, not a sum of kernels)
+    float tot = 0;
+    CUDA_TRY(cudaEventElapsedTime(&timing3[1], ev[0], ev[1])); CUDA_TRY(cudaEventElapsedTime(&tot, ev[0], ev[2])); timing3[0] = tot - timing3[1]; timing3[2] = 0;
     for (int i = 0; i < 3; i++) cudaEventDestroy(ev[i]);
   }
   i64 total = 0;
@@ -747,7 +795,17 @@ int64_t kzg_decompress_dev(const uint8_t* d_in, int64_t nBytes, const uint8_t* h
     total += B.curLen;
   }
   if (total > outCap) return -KZG_ERR_WRITE_FILE;
+  if (h_out) {
+    const KzgBlock& L = bt.hBlocks[nBlocks - 1];
+    if (L.curLen > 0 && cudaMemcpy(h_out + (size_t)(nBlocks - 1) * blockSize, d_out + (size_t)(nBlocks - 1) * blockSize, (size_t)L.curLen, cudaMemcpyDeviceToHost) != cudaSuccess)
+      return -KZG_ERR_PROCESS_BLOCK;
+  }
   return total;
+}
+
+int64_t kzg_decompress_dev(const uint8_t* d_in, int64_t nBytes, const uint8_t* h_in, int32_t flags, uint8_t* d_out, int64_t outCap,
+                           float* timing3) {
+  return decompress_impl(d_in, nBytes, h_in, flags, d_out, outCap, timing3, false, nullptr);
 }
 
 // ---- host-buffer forms: H2D, the device path, D2H ---------------------------------------------------------------------
@@ -781,10 +839,9 @@ int64_t kzg_decompress(const uint8_t* in, int64_t nBytes, int32_t flags, uint8_t
   i64 res;
   do {
     if (cudaMemsetAsync(dIn + nBytes, 0, inCap - nBytes, W.stream) != cudaSuccess) { res = -KZG_ERR_PROCESS_BLOCK; break; }
-    if (cudaMemcpyAsync(dIn, in, (size_t)nBytes, cudaMemcpyHostToDevice, W.stream) != cudaSuccess) { res = -KZG_ERR_PROCESS_BLOCK; break; }
-    res = kzg_decompress_dev(dIn, nBytes, in, flags, dOut, outCap, nullptr);
+    // every block group uploads its own byte range of the stream and downloads its blocks (decompress_impl)
+    res = decompress_impl(dIn, nBytes, in, flags, dOut, outCap, nullptr, true, out);
     if (res < 0) break;
-    if (cudaMemcpy(out, dOut, (size_t)res, cudaMemcpyDeviceToHost) != cudaSuccess) { res = -KZG_ERR_PROCESS_BLOCK; break; }
   } while (0);
   return res;
 }
