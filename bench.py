@@ -260,6 +260,7 @@ def main():
         te, td, k = step_e2e()
         e_enc.append(te); e_dec.append(td)
     assert np.array_equal(h_back[:n].numpy(), data), "e2e round trip mismatch"
+    assert k == knz_len and torch.equal(h_knz[:k], d_knz[:k].cpu()), "the host-buffer entry's .knz differs from the device-resident one (which equals the oracle's)"
     barrier()
     clocks = sampler.stop()
 

@@ -154,6 +154,7 @@ struct Batch {
   u8* dEnabled = nullptr; u8* hEnabled = nullptr;
   int* dDstLimit = nullptr; int* hDstLimit = nullptr;
   i32 maxLen = 0;                  // largest block length at any stage
+  const u8* lazyHost = nullptr; u8* lazyDev = nullptr; i64 lazyN = 0; i32 lazyBlock = 0;   // see KzgXfParams (stage 0 of a host-buffer encode)
 };
 
 static int batch_upload(Batch& bt) {
@@ -193,11 +194,14 @@ static int run_transform_stage(Batch& bt, int type, int stage, bool forward, con
   P.result = bt.dResult; P.enabled = bt.dEnabled; P.dstLimit = bt.dDstLimit;
   P.scratch = dScratch; P.scratchStride = (i64)xs.perBlock; P.tkStride = xs.tk; P.mStride = xs.m; P.mLenStride = xs.ml;
   P.hashBuf = dHash; P.aux32 = dAux32; P.aux32Stride = (i64)xs.aux32; P.flags = flags;
+  const bool lazy = forward && stage == 0 && bt.lazyHost && (type == KZG_T_LZ || type == KZG_T_LZX);
+  P.lazyHost = lazy ? bt.lazyHost : nullptr; P.lazyDev = bt.lazyDev; P.lazyN = bt.lazyN; P.lazyBlock = bt.lazyBlock;
   int r = 0;
   switch (type) {
     case KZG_T_LZ: case KZG_T_LZX:
       if (forward) {
         static const bool v1 = getenv("KZG_LZ_V1") != nullptr;      // developer switch: the first-generation single-kernel walker
+        if (v1 && P.lazyHost) { CUDA_TRY(cudaMemcpyAsync(P.lazyDev, P.lazyHost, (size_t)P.lazyN, cudaMemcpyHostToDevice, W.stream)); }
         if (v1) r = kzg_lz_forward_launch(W.stream, bt.dBlocks, bt.nBlocks, P, type == KZG_T_LZX, (type == KZG_T_LZ) && (bt.maxLen <= (1 << 24)));
         else {
           static const char* dbgEnv = getenv("KZG_DEBUG");          // developer aid: bit 0 stats printf, bits 1-2 disable walker shortcuts
@@ -492,8 +496,10 @@ static int stream_header(u8* h, int entropy, u64 transformType, i32 blockSize, i
   return nb;
 }
 
-int64_t kzg_compress_dev(const uint8_t* d_in, int64_t n, const int32_t* transforms, int32_t nTransforms, int32_t entropy,
-                         int32_t blockSize, int32_t flags, uint8_t* d_out, int64_t outCap, float* timing3) {
+// h_in (optional): the input is still on the host; it is uploaded here — whole, or, when the chain starts with LZ and the
+// batch is large, a sample per eighth of every block now and the blocks themselves by the LZ stage on its group streams.
+static int64_t compress_impl(const uint8_t* d_in, int64_t n, const int32_t* transforms, int32_t nTransforms, int32_t entropy,
+                             int32_t blockSize, int32_t flags, uint8_t* d_out, int64_t outCap, float* timing3, const uint8_t* h_in) {
   if (n < 0 || nTransforms < 0 || nTransforms > 8 || !ent_known(entropy)) return -KZG_ERR_INVALID_PARAM;
   if (blockSize > (1 << 30) || blockSize < 1024 || (blockSize & -16) != blockSize) return -KZG_ERR_BLOCK_SIZE;    // COS:165-174
   for (int i = 0; i < nTransforms; i++) if (!xf_known(transforms[i])) return -KZG_ERR_INVALID_CODEC;
@@ -517,11 +523,25 @@ int64_t kzg_compress_dev(const uint8_t* d_in, int64_t n, const int32_t* transfor
   if (outCap < hdrLen + 2) return -KZG_ERR_WRITE_FILE;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   if (timing3) for (int i = 0; i < 4; i++) CUDA_TRY(cudaEventCreate(&ev[i]));
+  const bool lazyIn = h_in && nf >= 1 && (fn[0] == KZG_T_LZ || fn[0] == KZG_T_LZX) && nBlocks >= 8 && blockSize >= (1 << 18) && getenv("KZG_LZ_V1") == nullptr;
+  if (h_in && n > 0) {
+    if (!lazyIn) CUDA_TRY(cudaMemcpyAsync((u8*)d_in, h_in, (size_t)n, cudaMemcpyHostToDevice, W.stream));
+    else {
+      for (int b = 0; b < nBlocks; b++) {       // the samples the LZ stage orders its blocks by (they also hold the block's magic bytes)
+        const i64 off = (i64)b * blockSize;
+        const i64 len = std::min<i64>(blockSize, n - off);
+        const i64 eighth = len / LZF_SAMPLES;
+        if (eighth < LZF_SAMPLE) { CUDA_TRY(cudaMemcpyAsync((u8*)d_in + off, h_in + off, (size_t)len, cudaMemcpyHostToDevice, W.stream)); continue; }
+        CUDA_TRY(cudaMemcpy2DAsync((u8*)d_in + off, (size_t)eighth, h_in + off, (size_t)eighth, LZF_SAMPLE, LZF_SAMPLES, cudaMemcpyHostToDevice, W.stream));
+      }
+    }
+  }
   CUDA_TRY(cudaMemsetAsync(d_out, 0, (size_t)outCap, W.stream));
   CUDA_TRY(cudaMemcpyAsync(d_out, hdr, hdrLen, cudaMemcpyHostToDevice, W.stream));
   i64 totalBits = (i64)hdrLen * 8 + 8;
   if (nBlocks > 0) {
     Batch bt; bt.nBlocks = nBlocks; bt.maxLen = required;
+    if (lazyIn) { bt.lazyHost = h_in; bt.lazyDev = (u8*)d_in; bt.lazyN = n; bt.lazyBlock = blockSize; }
     bt.hBlocks = halloc<KzgBlock>(nb); NN(bt.hBlocks);
     bt.hEnabled = halloc<u8>(nb); NN(bt.hEnabled);
     bt.hDstLimit = halloc<int>(nb); NN(bt.hDstLimit);
@@ -589,6 +609,11 @@ int64_t kzg_compress_dev(const uint8_t* d_in, int64_t n, const int32_t* transfor
   const i64 bytes = (totalBits + 7) >> 3;
   if (bytes > outCap - 8) { kzg_set_error("compressed stream (%lld bytes) exceeds capacity %lld", (long long)bytes, (long long)outCap); return -KZG_ERR_WRITE_FILE; }
   return bytes;
+}
+
+int64_t kzg_compress_dev(const uint8_t* d_in, int64_t n, const int32_t* transforms, int32_t nTransforms, int32_t entropy,
+                         int32_t blockSize, int32_t flags, uint8_t* d_out, int64_t outCap, float* timing3) {
+  return compress_impl(d_in, n, transforms, nTransforms, entropy, blockSize, flags, d_out, outCap, timing3, nullptr);
 }
 
 // ---- decode side: the host walks the container (CIS:359-515, 1025-1095, 1127-1167), the device does the rest -------
@@ -820,8 +845,7 @@ int64_t kzg_compress(const uint8_t* in, int64_t n, const int32_t* transforms, in
   i64 res;
   do {
     if (cudaMemsetAsync(dIn + n, 0, inCap - n, W.stream) != cudaSuccess) { res = -KZG_ERR_PROCESS_BLOCK; break; }
-    if (n > 0 && cudaMemcpyAsync(dIn, in, (size_t)n, cudaMemcpyHostToDevice, W.stream) != cudaSuccess) { res = -KZG_ERR_PROCESS_BLOCK; break; }
-    res = kzg_compress_dev(dIn, n, transforms, nTransforms, entropy, blockSize, flags, dOut, bound, nullptr);
+    res = compress_impl(dIn, n, transforms, nTransforms, entropy, blockSize, flags, dOut, bound, nullptr, in);   // (uploads the input itself)
     if (res < 0) break;
     if (res > outCap) { res = -KZG_ERR_WRITE_FILE; break; }
     if (cudaMemcpy(out, dOut, (size_t)res, cudaMemcpyDeviceToHost) != cudaSuccess) { res = -KZG_ERR_PROCESS_BLOCK; break; }

@@ -1751,11 +1751,10 @@ __global__ void __launch_bounds__(256) lzf_sample_kernel(const KzgBlock* __restr
   const int b = blockIdx.y, e = blockIdx.x;
   const LzfBlock& L = lb[b];
   if (L.n <= 0) return;
-  const int eighth = (L.n + 7) / 8;
-  const int beg = e * eighth;
-  if (beg >= L.n) return;
-  const int len = min(min(eighth, L.n - beg), 4096);
-  const u8* __restrict__ src = blocks[b].cur + beg + max(0, (min(eighth, L.n - beg) - len) / 2);
+  const int eighth = blocks[b].curLen / LZF_SAMPLES;          // sample e = the first LZF_SAMPLE bytes of eighth e (the layout a
+  const int len = min(eighth, LZF_SAMPLE) - 8;                 // host-buffer encode uploads ahead of the blocks themselves)
+  if (len < 60) return;
+  const u8* __restrict__ src = blocks[b].cur + (size_t)e * eighth;
   for (int i = threadIdx.x; i < 2048; i += 256) seen[i] = 0;
   if (threadIdx.x == 0) dup = 0;
   __syncthreads();
@@ -1773,6 +1772,7 @@ __global__ void __launch_bounds__(256) lzf_sample_kernel(const KzgBlock* __restr
 
 // per-thread pool of side streams for the grouped rounds (created once; the calling thread's codec stream forks into them)
 #define LZF_MAXG 64
+// (LZF_SAMPLES / LZF_SAMPLE: include/.. kzg_transforms.cuh users upload exactly these ranges ahead of the blocks)
 struct LzfStreams {
   cudaStream_t st[LZF_MAXG]; cudaEvent_t fork; int n = 0; int* hCnt = nullptr;
   int init(int g) {
@@ -1861,13 +1861,14 @@ int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
   std::vector<int> order(nBlocks);
   for (int b = 0; b < nBlocks; b++) order[b] = b;
   if (dbg & 8) {                                          // developer switch: everything by the serial walker
+    if (P.lazyHost) CUDA_TRY(cudaMemcpyAsync(P.lazyDev, P.lazyHost, (size_t)P.lazyN, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemcpyAsync(dMap, order.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, s));
     sortPhase(s, dMap, nBlocks, false);
     CUDA_TRY(cudaStreamSynchronize(s));                   // order is stack-owned
   } else {
     std::vector<int> key(nBlocks, 0x7FFFFFFF);
     CUDA_TRY(cudaMemcpyAsync(dKey, key.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, s));
-    lzf_sample_kernel<<<dim3(8, nBlocks), 256, 0, s>>>(d_blocks, dlb, dKey);
+    lzf_sample_kernel<<<dim3(LZF_SAMPLES, nBlocks), 256, 0, s>>>(d_blocks, dlb, dKey);
     CUDA_TRY(cudaMemcpyAsync(key.data(), dKey, sizeof(int) * nb, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return key[x] < key[y]; });
@@ -1902,6 +1903,12 @@ int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
     for (int g = 0; g < G; g++) {
       CUDA_TRY(cudaStreamWaitEvent(ST.st[g], ST.fork, 0));
       groupRound[g] = 0; live[g] = true;
+      if (P.lazyHost) {                                  // this group's blocks are still on the host: upload them on its stream
+        for (int i = gBeg[g]; i < gBeg[g + 1]; i++) {
+          const i64 off = (i64)order[i] * P.lazyBlock, len = std::min<i64>(P.lazyBlock, P.lazyN - off);
+          if (len > 0) CUDA_TRY(cudaMemcpyAsync(P.lazyDev + off, P.lazyHost + off, (size_t)len, cudaMemcpyHostToDevice, ST.st[g]));
+        }
+      }
       sortPhase(ST.st[g], dMap + gBeg[g], gBeg[g + 1] - gBeg[g], true);
       enqueue(g, 0);
     }

@@ -146,6 +146,17 @@ def test_stream_sparse_blocks():
         assert K.decompress(ref, len(d) + 1024) == d
 
 
+def test_stream_many_blocks_host_buffers():
+    """Enough large blocks for the batched entries to deal them into groups: the encode uploads a sample of every block first
+    and the blocks themselves on the group streams, the decode uploads / downloads per group (kzg_compress / kzg_decompress)."""
+    d = synth.text(2_500_000, 31).tobytes() + synth.exe_like(2_000_000, 32).tobytes() + corpus.sparse_with_repeats(1_200_000, 33) + synth.records(900_001, 34).tobytes()
+    for tr, ent, bs in ((["LZ"], "ANS0", 1 << 19), (["LZX"], "ANS0", 1 << 18), (["LZ"], "HUFFMAN", 1 << 18)):
+        ref = O.compress(d, tr, ent, bs)
+        got = K.compress(d, tr, ent, bs)
+        assert len(got) == len(ref) and got == ref, (tr, ent, len(got), len(ref), "first differing byte", first_diff(got, ref))
+        assert K.decompress(ref, len(d) + 1024) == d
+
+
 def test_stream_tiny_and_ragged():
     for n in (0, 1, 8, 15, 16, 17, 100, 1023, 1024, 1025, 4097):
         d = bytes((i * 7 + 3) & 0xFF for i in range(n))
