@@ -21,6 +21,8 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+# the LZ forward runs block groups on up to 32 side streams: more hardware work queues than the default 8 (read at CUDA context creation)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

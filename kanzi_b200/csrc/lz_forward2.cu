@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(1024) lzf_scan_kernel(LzfBlock* __restrict__ l
 // __match_any_sync), the per-warp digit counts are scanned across warps and digits, the elements are staged in shared
 // memory in digit order and leave from there: consecutive threads write consecutive elements of a digit run, so the
 // stores cover whole sectors (element-wise scattering costs ~3x the DRAM traffic in partial-sector fills and evictions).
-__global__ void __launch_bounds__(32 * LZF_WARPS) lzf_scatter_kernel(LzfBlock* __restrict__ lb, const int* __restrict__ bmap, int shift, int mask, int k) {
+__global__ void __launch_bounds__(32 * LZF_WARPS, 3) lzf_scatter_kernel(LzfBlock* __restrict__ lb, const int* __restrict__ bmap, int shift, int mask, int k) {
   __shared__ u64 stage[LZF_WT];
   __shared__ u32 cnt[LZF_WARPS][256];
   __shared__ u32 digitBase[256 + 1];
