@@ -1515,8 +1515,8 @@ __device__ __forceinline__ void lzf_neighbours(const uint4* __restrict__ fin, in
   p2z = (i > 1) ? fin[i - 2].z : (u32)count;
 }
 // E1: the match list as one array (ranges of the segment logs and of the stitcher's own log, in order)
-__global__ void __launch_bounds__(LZF_ET) lzf_emit_gather_kernel(LzfBlock* __restrict__ lb) {
-  const LzfBlock& L = lb[blockIdx.y];
+__global__ void __launch_bounds__(LZF_ET) lzf_emit_gather_kernel(LzfBlock* __restrict__ lb, const int* __restrict__ bmap) {
+  const LzfBlock& L = lb[bmap[blockIdx.y]];
   if (L.n <= 0 || L.needSerial) return;
   const int i = blockIdx.x * LZF_ET + threadIdx.x;
   if (i >= L.nFin) return;
@@ -1525,9 +1525,9 @@ __global__ void __launch_bounds__(LZF_ET) lzf_emit_gather_kernel(LzfBlock* __res
   L.fin[i] = L.rng[lo].ev[i - L.rng[lo].start];
 }
 // E2: bytes every tile of 1024 matches adds to the literal area, the distance bytes and the length bytes
-__global__ void __launch_bounds__(LZF_ET) lzf_emit_size_kernel(LzfBlock* __restrict__ lb) {
+__global__ void __launch_bounds__(LZF_ET) lzf_emit_size_kernel(LzfBlock* __restrict__ lb, const int* __restrict__ bmap) {
   __shared__ u32 sA[32], sB[32];
-  LzfBlock& L = lb[blockIdx.y];
+  LzfBlock& L = lb[bmap[blockIdx.y]];
   if (L.n <= 0 || L.needSerial) return;
   const int base = blockIdx.x * LZF_ET;
   if (base >= L.nFin) return;
@@ -1550,10 +1550,10 @@ __global__ void __launch_bounds__(LZF_ET) lzf_emit_size_kernel(LzfBlock* __restr
   }
 }
 // E3 (one CTA per block): tile offsets, the reference's end-of-block decisions (:568-596), header and last literals
-__global__ void __launch_bounds__(LZF_ET) lzf_emit_scan_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P, LzfBlock* __restrict__ lb) {
+__global__ void __launch_bounds__(LZF_ET) lzf_emit_scan_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P, LzfBlock* __restrict__ lb, const int* __restrict__ bmap) {
   __shared__ u32 ws[3][32];
   __shared__ u32 carry[3];
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = bmap[blockIdx.x], tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   LzfBlock& L = lb[b];
   if (L.n <= 0 || L.needSerial) return;
   KzgBlock& B = blocks[b];
@@ -1627,19 +1627,19 @@ __global__ void __launch_bounds__(LZF_ET) lzf_emit_scan_kernel(KzgBlock* __restr
 // tile (length-extension bytes + literal runs, contiguous in dst) is then written output-centred: every thread takes four
 // consecutive destination bytes, finds the match they belong to in the tile's shared prefix table and fetches the bytes, so
 // stores are aligned words and consecutive lanes read consecutive source bytes inside a run.
-__global__ void __launch_bounds__(LZF_ET) lzf_emit_write_kernel(KzgBlock* __restrict__ blocks, LzfBlock* __restrict__ lb) {
+__global__ void __launch_bounds__(LZF_ET) lzf_emit_write_kernel(KzgBlock* __restrict__ blocks, LzfBlock* __restrict__ lb, const int* __restrict__ bmap) {
   __shared__ u32 wsA[32], wsB[32];
   __shared__ u32 sOff[LZF_ET + 1];                  // literal-area offset of every match of the tile, relative to the tile's start
   __shared__ int sSrc[LZF_ET];                      // source position of area byte 0 (= literal start - leSize)
   __shared__ u8 sLe[LZF_ET];                        // length-extension bytes that open the area
-  const LzfBlock& L = lb[blockIdx.y];
+  const LzfBlock& L = lb[bmap[blockIdx.y]];
   if (L.n <= 0 || L.needSerial || !L.emitGo) return;
   const int base = blockIdx.x * LZF_ET;
   if (base >= L.nFin) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int i = base + tid;
   const bool on = i < L.nFin;
-  const KzgBlock& B = blocks[blockIdx.y];
+  const KzgBlock& B = blocks[bmap[blockIdx.y]];
   const u8* __restrict__ src = B.cur;
   u8* __restrict__ dst = B.alt;
   LzfTok k; k.litLen = 0; k.token = 0; k.nd = 0; k.mlSize = 0; k.mlExt = 0; k.leSize = 0;
@@ -1853,6 +1853,15 @@ int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
       launches++;
     }
   };
+  const int evTiles = (maxLen / 4 + 64 + LZF_ET - 1) / LZF_ET;
+  auto emit = [&](cudaStream_t q, const int* bm, int cnt) {   // phase 4 of `cnt` blocks
+    lzf_emit_gather_kernel<<<dim3(evTiles, cnt), LZF_ET, 0, q>>>(dlb, bm);
+    lzf_emit_size_kernel<<<dim3(evTiles, cnt), LZF_ET, 0, q>>>(dlb, bm);
+    lzf_emit_scan_kernel<<<cnt, LZF_ET, 0, q>>>(d_blocks, P, dlb, bm);
+    lzf_emit_write_kernel<<<dim3(evTiles, cnt), LZF_ET, 0, q>>>(d_blocks, dlb, bm);
+    launches += 4;
+  };
+  bool emitted = false;
   // Every group of blocks runs its whole pipeline on a stream of its own: the sort passes of one group (HBM bound) overlap
   // the segment parses of another (latency / issue bound), and a group's stitch (one warp per block) overlaps everything.
   // Blocks with a sparse stretch go first on the urgent streams: the stitcher walks those stretches itself.
@@ -1899,7 +1908,8 @@ int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
       launches += 5;
     };
     int groupRound[LZF_MAXG];
-    bool live[LZF_MAXG];
+    bool live[LZF_MAXG], emittedGroup[LZF_MAXG];
+    for (int g = 0; g < LZF_MAXG; g++) emittedGroup[g] = false;
     for (int g = 0; g < G; g++) {
       CUDA_TRY(cudaStreamWaitEvent(ST.st[g], ST.fork, 0));
       groupRound[g] = 0; live[g] = true;
@@ -1925,26 +1935,37 @@ int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
         if (dbg & 64) fprintf(stderr, "lzf t=%7.3f ms: group %d (blocks %d..%d of the order, first block %d) finished round %d, %d still active\n",
                               std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tHost0).count(), g, gBeg[g], gBeg[g + 1] - 1, order[gBeg[g]], groupRound[g], ST.hCnt[2 * g]);
         rounds = std::max(rounds, groupRound[g] + 1);
-        if (ST.hCnt[2 * g] == 0 || groupRound[g] + 1 >= maxRounds) { live[g] = false; nLive--; hCnt[1] += ST.hCnt[2 * g + 1]; continue; }
+        if (ST.hCnt[2 * g] == 0 || groupRound[g] + 1 >= maxRounds) {
+          live[g] = false; nLive--; hCnt[1] += ST.hCnt[2 * g + 1];
+          if (ST.hCnt[2 * g + 1] == 0) { emit(ST.st[g], dMap + gBeg[g], gBeg[g + 1] - gBeg[g]); emittedGroup[g] = true; }   // the group's tokens, while the others still parse
+          continue;
+        }
         groupRound[g]++;
         enqueue(g, groupRound[g]);
       }
       if (!progressed) std::this_thread::yield();          // (rounds last milliseconds; a query costs microseconds)
     }
+    // join: the groups' emit kernels still run; blocks left to the serial walker (never on the test corpora) are emitted after it
+    for (int g = 0; g < G; g++) {
+      if (emittedGroup[g]) CUDA_TRY(cudaStreamSynchronize(ST.st[g]));
+    }
+    if (hCnt[1] == 0) emitted = true;
+    else {
+      if (extra) lzf_walk_kernel<true><<<nBlocks, 64, 0, s>>>(d_blocks, P, dlb);
+      else lzf_walk_kernel<false><<<nBlocks, 64, 0, s>>>(d_blocks, P, dlb);
+      launches++;
+      for (int g = 0; g < G; g++) if (!emittedGroup[g]) emit(s, dMap + gBeg[g], gBeg[g + 1] - gBeg[g]);
+      emitted = true;
+    }
     tm.mark("pipeline");
   }
   if (dbg & 1) fprintf(stderr, "lzf: %d blocks, %d rounds, %d serial\n", nBlocks, rounds, hCnt[1]);
-  if (hCnt[1] > 0) {
+  if (!emitted && hCnt[1] > 0) {                          // (developer switch)
     if (extra) lzf_walk_kernel<true><<<nBlocks, 64, 0, s>>>(d_blocks, P, dlb);
     else lzf_walk_kernel<false><<<nBlocks, 64, 0, s>>>(d_blocks, P, dlb);
     launches++;
   }
-  const int evTiles = (maxLen / 4 + 64 + LZF_ET - 1) / LZF_ET;
-  lzf_emit_gather_kernel<<<dim3(evTiles, nBlocks), LZF_ET, 0, s>>>(dlb);
-  lzf_emit_size_kernel<<<dim3(evTiles, nBlocks), LZF_ET, 0, s>>>(dlb);
-  lzf_emit_scan_kernel<<<nBlocks, LZF_ET, 0, s>>>(d_blocks, P, dlb);
-  lzf_emit_write_kernel<<<dim3(evTiles, nBlocks), LZF_ET, 0, s>>>(d_blocks, dlb);
-  launches += 4;
+  if (!emitted) { emit(s, dMap, nBlocks); }                // (serial-walker blocks somewhere, or the developer switch: everything at the end)
   tm.mark("emit");
   tm.report();
   CUDA_TRY(cudaGetLastError());
