@@ -1717,7 +1717,7 @@ static LzfSizes lzf_sizes(i32 maxLen) {
   z.key = lzf_al(8 * n); z.sa = lzf_al(4 * n); z.prev = lzf_al(4 * n); z.len0 = lzf_al(n); z.skipped = lzf_al(n / 8 + 64);
   z.hist = lzf_al(4 * 256 * nT);
   z.tk = lzf_al(std::max<size_t>(n / 5, 256) + 64); z.m = lzf_al(n + 64); z.ml = lzf_al(n / 2 + 64);
-  static const int segMin = getenv("KZG_LZ_SEG") ? std::max(8192, atoi(getenv("KZG_LZ_SEG")) / 4096 * 4096) : 16384;   // developer knob
+  static const int segMin = getenv("KZG_LZ_SEG") ? std::max(8192, atoi(getenv("KZG_LZ_SEG")) / 4096 * 4096) : 8192;   // developer knob
   z.segLen = std::max(segMin, (int)((n / 512 + 4095) / 4096 * 4096));
   z.maxSeg = (int)((n + z.segLen - 1) / z.segLen);
   z.evStride = z.segLen / 4 + 16;
