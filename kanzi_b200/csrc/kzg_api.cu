@@ -18,6 +18,7 @@
 #include <algorithm>
 
 // ---- per-thread workspace --------------------------------------------------------------------------------
+#define KZG_DEC_MAXG 16            // block groups of the decode (streams of their own)
 struct Workspace {
   bool init = false;
   int device = 0;
@@ -27,7 +28,7 @@ struct Workspace {
   u8* ioBuf[2] = {nullptr, nullptr}; size_t ioCap[2] = {0, 0};      // device copies of the host-buffer entry points' streams (grow-only)
   i64 launches = 0;
   char err[512] = {0};
-  cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr}; cudaEvent_t sideEv[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; bool sideInit = false;
+  cudaStream_t side[KZG_DEC_MAXG] = {}; cudaEvent_t sideEv[KZG_DEC_MAXG + 1] = {}; bool sideInit = false;
 };
 static thread_local Workspace W;
 
@@ -60,8 +61,8 @@ static int ws_side_init() {
   if (W.sideInit) return 0;
   int lo = 0, hi = 0;
   cudaDeviceGetStreamPriorityRange(&lo, &hi);
-  for (int g = 0; g < 4; g++) CUDA_TRY(cudaStreamCreateWithPriority(&W.side[g], cudaStreamNonBlocking, std::min(lo, hi + g)));
-  for (int g = 0; g < 5; g++) CUDA_TRY(cudaEventCreateWithFlags(&W.sideEv[g], cudaEventDisableTiming));
+  for (int g = 0; g < KZG_DEC_MAXG; g++) CUDA_TRY(cudaStreamCreateWithPriority(&W.side[g], cudaStreamNonBlocking, std::min(lo, hi + g)));
+  for (int g = 0; g <= KZG_DEC_MAXG; g++) CUDA_TRY(cudaEventCreateWithFlags(&W.sideEv[g], cudaEventDisableTiming));
   W.sideInit = true;
   return 0;
 }
@@ -764,17 +765,18 @@ static int64_t decompress_impl(const uint8_t* d_in, int64_t nBytes, const uint8_
   // Blocks are independent: contiguous groups of them run the whole decode on streams of their own (most urgent first), so
   // that the latency-bound kernels of one group (chunk scan, the literal-record chain) overlap the streaming kernels of the
   // others and, for host buffers, a group's upload / download overlaps the other groups' kernels.
-  const int G = (nBlocks >= 8) ? 4 : 1;
+  static const int gDec = getenv("KZG_DEC_GROUPS") ? std::max(1, std::min(KZG_DEC_MAXG, atoi(getenv("KZG_DEC_GROUPS")))) : 12;   // developer knob
+  const int G = (nBlocks >= 8) ? std::min(gDec, nBlocks / 2) : 1;
   if (G > 1) { r = ws_side_init(); if (r < 0) return r; }
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   if (timing3) { for (int i = 0; i < 3; i++) CUDA_TRY(cudaEventCreate(&ev[i])); CUDA_TRY(cudaEventRecord(ev[0], W.stream)); }
-  if (G > 1) CUDA_TRY(cudaEventRecord(W.sideEv[4], W.stream));
+  if (G > 1) CUDA_TRY(cudaEventRecord(W.sideEv[KZG_DEC_MAXG], W.stream));
   cudaStream_t const mainStream = W.stream;
   int rc = 0;
   for (int g = 0; g < G && rc == 0; g++) {
     const int b0 = (int)((i64)nBlocks * g / G), b1 = (int)((i64)nBlocks * (g + 1) / G), cnt = b1 - b0;
     cudaStream_t q = (G > 1) ? W.side[g] : mainStream;
-    if (G > 1) CUDA_TRY(cudaStreamWaitEvent(q, W.sideEv[4], 0));
+    if (G > 1) CUDA_TRY(cudaStreamWaitEvent(q, W.sideEv[KZG_DEC_MAXG], 0));
     if (copyIn) {                               // the bytes that hold this group's block records (+ the slack the bit readers touch)
       const i64 lo = (recs[b0].payBit >> 3) & ~(i64)63;
       const i64 hi = std::min<i64>(nBytes, ((recs[b1 - 1].payBit + recs[b1 - 1].payBits + 7) >> 3) + 128);
