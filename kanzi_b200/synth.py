@@ -208,3 +208,9 @@ def make(cfg, scale=1.0):
     n = max(1024, int(size * scale))
     seed = {"cfg1": 1, "cfg2": 2, "cfg3": 3, "cfg4": 4, "cfg5": 5}[cfg]
     return gen(n, seed), tr, ent, bs
+
+
+if __name__ == "__main__":      # python -m kanzi_b200.synth <generator> <bytes> <seed> <out file>   (tools/make_goldens.sh)
+    import sys
+    _gen, _n, _seed, _out = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), sys.argv[4]
+    globals()[_gen](_n, _seed).tofile(_out)
