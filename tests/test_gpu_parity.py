@@ -157,6 +157,20 @@ def test_stream_many_blocks_host_buffers():
         assert K.decompress(ref, len(d) + 1024) == d
 
 
+@pytest.mark.parametrize("tr,ent,bs,flags", [
+    (["BWT", "RANK", "ZRLT"], "ANS1", 1 << 18, K.FLAG_BWT_ASREF), (["BWT", "RANK", "ZRLT"], "ANS1", 1 << 18, 0),
+    (["BWT", "SRT", "ZRLT"], "FPAQ", 1 << 18, 0), (["ROLZ"], "ANS0", 1 << 18, K.FLAG_BWT_ASREF), (["MTFT", "ZRLT"], "HUFFMAN", 1 << 17, K.FLAG_BWT_ASREF),
+    (["LZ", "RANK"], "FPAQ", 1 << 18, K.FLAG_BWT_ASREF)])
+def test_stream_many_blocks_all_chains(tr, ent, bs, flags):
+    """Twelve or more blocks per stream, so that the decode deals them into groups on streams of their own, for the chains whose
+    stages keep per-block scratch (BWT, ROLZ tables, SRT / RANK lists, FPAQ / ANS1 state)."""
+    d = synth.text(1_400_000, 41).tobytes() + synth.records(900_000, 42).tobytes() + synth.exe_like(850_001, 43).tobytes()
+    ref = O.compress(d, tr, ent, bs, bwt_bounds=1 if flags else 0)
+    got = K.compress(d, tr, ent, bs, flags=flags)
+    assert len(got) == len(ref) and got == ref, (tr, ent, len(got), len(ref), "first differing byte", first_diff(got, ref))
+    assert K.decompress(ref, len(d) + 1024, flags=flags) == d
+
+
 def test_stream_tiny_and_ragged():
     for n in (0, 1, 8, 15, 16, 17, 100, 1023, 1024, 1025, 4097):
         d = bytes((i * 7 + 3) & 0xFF for i in range(n))
