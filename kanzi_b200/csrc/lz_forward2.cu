@@ -1,20 +1,22 @@
-// lz_forward2.cu — LZ forward (`-t LZ` / `-t LZX`), two-phase bit-exact encoder (sm_100a).
+// lz_forward2.cu — LZ forward (`-t LZ` / `-t LZX`), bit-exact encoder (sm_100a).
 //
 // Replaces K/transform/LZCodec.java LZXCodec.forward (:299-597).  The reference's greedy
 // parse consults a single-entry hash table whose content at position p is "the most recent inserted position
 // with the same hash".  Every position below p is inserted except the ones the skip acceleration jumped over
-// (srcInc >> 6, :399-400), so the table is *almost* parse-independent.  That splits the work:
-//   phase 1 (data-parallel, every block at once, HBM-bound):
-//     hash of every position -> stable LSD radix sort of positions by hash (2 x 8-bit passes) ->
-//     prev[p] = previous position with the same hash -> len0[p] = length of the match against prev[p]
-//     exactly as findMatch would report it (8-byte steps, capped at 255; 0 when the 4-byte pre-check fails).
-//   phase 2 (one warp per block): the decision sequence itself.  32 upcoming visit positions are evaluated at
-//     once (repeat-offset checks + the precomputed len0), a ballot finds the first position where the
-//     reference would emit a match, the misses before it are committed in one step, and the match is
-//     emitted with the reference's exact rules (lazy step, backward extension, token layout).
-//     Positions jumped over by the acceleration are recorded in a bitmap; a candidate that falls at or below
-//     the highest skipped position is resolved by walking the prev chain past skipped entries.
-// The hash table of the reference no longer exists on the device; phase 2 touches prev/len0 sequentially.
+// (srcInc >> 6, :399-400), so the table is *almost* parse-independent.  That splits the work (DESIGN.md "LZ forward"):
+//   phase 1 (data parallel, HBM-bound): hash of every position -> stable LSD radix sort of packed key|position
+//     elements by hash -> prev[p] / hs[] / rank[] -> len0[p] = findMatch(p, prev[p]) capped at 255; a second
+//     sort key (4-byte fingerprint) flags positions that can never hit the table.
+//   head: the first 2 KiB of every block parsed for real; their jumped-over bits seed the assumed bitmap A.
+//   segments (lzf_spec_kernel, one warp per 8 KiB segment): speculative parses after a warm-up, 32 visit positions per
+//     batch, with A for positions before the segment; matches are logged, lookups that depended on A are marked.
+//   stitch (lzf_stitch_kernel, one warp per block): adopts the segments whose entry state was the true one, parses the
+//     rest itself; sparse stretches (noise, PCM) are parsed in order against a real table (lzf_direct_core).
+//   check (lzf_check_marks_kernel): the segments whose marked lookups resolve differently under the produced bitmap are
+//     parsed again next round with A := Kn; fixed point = the reference's parse.
+//   emit: tokens, distances, lengths and literals from the match list with prefix sums.
+// Every block group runs this pipeline on a CUDA stream of its own (kzg_lz_forward2_launch).  lzf_walk_kernel is the
+// first-generation exact one-warp walker, kept as the fallback for blocks that do not settle within 8 rounds.
 #include "kzg_common.cuh"
 #include "kzg_transforms.cuh"
 #include <algorithm>
