@@ -814,8 +814,7 @@ __global__ void __launch_bounds__(32) ans1_decode_kernel(KzgBlock* __restrict__ 
 // ================================================================================================================
 int kzg_ans_encode_launch(cudaStream_t s, const KzgBlock* d_blocks, int nBlocks, const KzgEntParams& P, int order) {
   if (order == 0) {
-    static bool attr = false;
-    if (!attr) { CUDA_TRY(cudaFuncSetAttribute(ans0_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(A0EncSmem))); attr = true; }
+    CUDA_TRY(cudaFuncSetAttribute(ans0_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(A0EncSmem)));   // per device: set on every launch
     dim3 grid((P.maxChunks + A0_GROUPS - 1) / A0_GROUPS, nBlocks);
     ans0_encode_kernel<<<grid, 128, sizeof(A0EncSmem), s>>>(d_blocks, P);
   } else {
@@ -833,8 +832,7 @@ int kzg_ans_decode_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, const
     CUDA_TRY(cudaGetLastError());
   }
   if (order == 0) {
-    static bool attr = false;
-    if (!attr) { CUDA_TRY(cudaFuncSetAttribute(ans0_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(A0DecSmem))); attr = true; }
+    CUDA_TRY(cudaFuncSetAttribute(ans0_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(A0DecSmem)));
     dim3 grid((P.maxChunks + A0_GROUPS - 1) / A0_GROUPS, nBlocks);
     ans0_decode_kernel<<<grid, 128, sizeof(A0DecSmem), s>>>(d_blocks, P);
   } else {

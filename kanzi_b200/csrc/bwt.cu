@@ -512,7 +512,7 @@ int kzg_bwtblock_launch(cudaStream_t s, bool forward, KzgBlock* d_blocks, int nB
       B.pidx[i] = (int)pi + 1;
     }
     if (!ok || n <= 0) continue;
-    if (n > lim[b] || n > K.cap) continue;
+    if (n > kzg_dst_limit(K, lim[b]) || n > K.cap) continue;
     if (n == 1) { CUDA_TRY(cudaMemcpyAsync(K.alt, K.cur + headerSize, 1, cudaMemcpyDeviceToDevice, s)); hres[2 * b] = 1; hres[2 * b + 1] = 1; continue; }
     // BWT.inverse guards (BWT.java:260-262, 300-306): primary indexes in range
     if (B.pidx[0] <= 0 || B.pidx[0] > n) continue;

@@ -528,8 +528,7 @@ __global__ void __launch_bounds__(64) huff_decode_kernel(KzgBlock* __restrict__ 
 }
 
 int kzg_huff_encode_launch(cudaStream_t s, const KzgBlock* d_blocks, int nBlocks, const KzgEntParams& P) {
-  static bool attr = false;
-  if (!attr) { CUDA_TRY(cudaFuncSetAttribute(huff_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HfEncSmem))); attr = true; }
+  CUDA_TRY(cudaFuncSetAttribute(huff_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HfEncSmem)));   // per device: set on every launch
   dim3 grid((P.maxChunks + HF_GROUPS - 1) / HF_GROUPS, nBlocks);
   huff_encode_kernel<<<grid, 64, sizeof(HfEncSmem), s>>>(d_blocks, P);
   CUDA_TRY(cudaGetLastError());
@@ -540,8 +539,7 @@ int kzg_huff_encode_launch(cudaStream_t s, const KzgBlock* d_blocks, int nBlocks
 int kzg_huff_decode_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, const KzgEntParams& P) {
   huff_scan_kernel<<<(nBlocks + 31) / 32, 32, 0, s>>>(d_blocks, nBlocks, P);
   CUDA_TRY(cudaGetLastError());
-  static bool attr = false;
-  if (!attr) { CUDA_TRY(cudaFuncSetAttribute(huff_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HfDecSmem))); attr = true; }
+  CUDA_TRY(cudaFuncSetAttribute(huff_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HfDecSmem)));
   dim3 grid((P.maxChunks + HF_GROUPS - 1) / HF_GROUPS, nBlocks);
   huff_decode_kernel<<<grid, 64, sizeof(HfDecSmem), s>>>(d_blocks, P);
   CUDA_TRY(cudaGetLastError());

@@ -48,7 +48,7 @@ static int ws_init() {
     cudaGetLastError();
     return -KZG_ERR_NO_DEVICE;
   }
-  if (W.device >= n) W.device = 0;
+  if (W.device < 0 || W.device >= n) { kzg_set_error("device %d out of range (%d CUDA devices)", W.device, n); return -KZG_ERR_INVALID_PARAM; }
   CUDA_TRY(cudaSetDevice(W.device));
   CUDA_TRY(cudaStreamCreateWithFlags(&W.stream, cudaStreamNonBlocking));
   W.init = true;
@@ -106,6 +106,13 @@ template <typename T> static T* halloc(size_t count) {
   if (W.hOff + bytes > W.hCap) { kzg_set_error("internal: pinned arena exhausted"); return nullptr; }
   T* p = (T*)(W.hPinned + W.hOff); W.hOff += bytes; return p;
 }
+// timing events of one call: destroyed on every exit path
+struct EvSet {
+  cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
+  int create(int n) { for (int i = 0; i < n; i++) if (cudaEventCreate(&e[i]) != cudaSuccess) return -KZG_ERR_PROCESS_BLOCK; return 0; }
+  cudaEvent_t& operator[](int i) { return e[i]; }
+  ~EvSet() { for (int i = 0; i < 4; i++) if (e[i]) cudaEventDestroy(e[i]); }
+};
 #define NN(p) do { if ((p) == nullptr) return -KZG_ERR_CREATE_CODEC; } while (0)
 
 // ---- ids / sizes (TransformFactory, getMaxEncodedLength of each codec) --------------------------------------
@@ -177,8 +184,6 @@ static XfScratch xf_scratch_size(const int* fn, int nf, i32 maxLen, bool forward
       if (forward) {
         s.tk = (int)rnd(std::max(maxLen / 5, 256) + 16, 16); s.m = (int)rnd((size_t)maxLen + 16, 16); s.ml = (int)rnd((size_t)maxLen / 2 + 64, 16);
         s.perBlock = std::max(s.perBlock, (size_t)s.tk + s.m + s.ml);
-        const bool smemTable = (fn[i] == KZG_T_LZ) && (maxLen <= (1 << 24));
-        if (!smemTable) s.hashInts = std::max(s.hashInts, (size_t)((fn[i] == KZG_T_LZX) ? (1 << 19) : (1 << 16)));
         kzg_lzf_scratch(maxLen, &s.perBlock);
       } else {
         kzg_lzi_scratch(maxLen, &s.perBlock, &s.aux32);
@@ -201,14 +206,9 @@ static int run_transform_stage(Batch& bt, int type, int stage, bool forward, con
   switch (type) {
     case KZG_T_LZ: case KZG_T_LZX:
       if (forward) {
-        static const bool v1 = getenv("KZG_LZ_V1") != nullptr;      // developer switch: the first-generation single-kernel walker
-        if (v1 && P.lazyHost) { CUDA_TRY(cudaMemcpyAsync(P.lazyDev, P.lazyHost, (size_t)P.lazyN, cudaMemcpyHostToDevice, W.stream)); }
-        if (v1) r = kzg_lz_forward_launch(W.stream, bt.dBlocks, bt.nBlocks, P, type == KZG_T_LZX, (type == KZG_T_LZ) && (bt.maxLen <= (1 << 24)));
-        else {
-          static const char* dbgEnv = getenv("KZG_DEBUG");          // developer aid: bit 0 stats printf, bits 1-2 disable walker shortcuts
-          if (dbgEnv) P.flags |= (atoi(dbgEnv) << 12);
-          r = kzg_lz_forward2_launch(W.stream, bt.dBlocks, bt.nBlocks, P, type == KZG_T_LZX, bt.maxLen);
-        }
+        const char* dbgEnv = getenv("KZG_DEBUG");          // developer aid: bit 0 stats printf, bits 1-2 disable walker shortcuts, bit 3 = serial walker only
+        if (dbgEnv) P.flags |= (atoi(dbgEnv) << 12);
+        r = kzg_lz_forward2_launch(W.stream, bt.dBlocks, bt.nBlocks, P, type == KZG_T_LZX, bt.maxLen);
       }
       else {
         static const char* dbgEnvI = getenv("KZG_DEBUG");         // developer aid: bit 0 per-block statistics of the token chase
@@ -284,23 +284,33 @@ static int run_entropy_decode(Batch& bt, int entropy, const EntScratch& es, cons
 // library entry points
 // ============================================================================================================
 // The LZ forward rounds run block groups on up to 32 side streams; with the default of 8 hardware work queues streams
-// alias onto each other and a group's one-warp stitch kernel serialises behind another group's parse.  The variable is
-// read when the CUDA context is created, so it only helps when this library is loaded before that (never overrides a
-// value the host already set).
-__attribute__((constructor)) static void kzg_on_load() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+// alias onto each other and a group's one-warp stitch kernel serialises behind another group's parse.  The host process
+// decides: export CUDA_DEVICE_MAX_CONNECTIONS=32 before the CUDA context exists (the Python package and
+// bench.py do).  The library itself never touches the environment.
 
 extern "C" {
 
 int kzg_abi_version(void) { return 1; }
 int kzg_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
-int kzg_set_device(int device) {
-  if (W.init && W.device != device) {
-    cudaStreamSynchronize(W.stream);
-    if (W.dArena) cudaFree(W.dArena);
-    if (W.hPinned) cudaFreeHost(W.hPinned);
-    cudaStreamDestroy(W.stream);
-    W = Workspace();
+// frees everything the calling thread's workspace owns (device of the workspace must be current)
+static void ws_release() {
+  if (!W.init) { W = Workspace(); return; }
+  cudaSetDevice(W.device);
+  cudaStreamSynchronize(W.stream);
+  if (W.sideInit) {
+    for (int g = 0; g < KZG_DEC_MAXG; g++) { cudaStreamSynchronize(W.side[g]); cudaStreamDestroy(W.side[g]); }
+    for (int g = 0; g <= KZG_DEC_MAXG; g++) cudaEventDestroy(W.sideEv[g]);
   }
+  kzg_lzf_release();
+  if (W.dArena) cudaFree(W.dArena);
+  if (W.hPinned) cudaFreeHost(W.hPinned);
+  for (int i = 0; i < 2; i++) if (W.ioBuf[i]) cudaFree(W.ioBuf[i]);
+  cudaStreamDestroy(W.stream);
+  cudaGetLastError();
+  W = Workspace();
+}
+int kzg_set_device(int device) {
+  if (W.init && W.device != device) ws_release();
   W.device = device;
   return ws_init();
 }
@@ -308,9 +318,12 @@ const char* kzg_last_error(void) { return W.err; }
 int64_t kzg_launch_count(int reset) { const i64 v = W.launches; if (reset) W.launches = 0; return v; }
 void* kzg_stream(void) { if (ws_init() < 0) return nullptr; return (void*)W.stream; }
 int32_t kzg_transform_max_encoded_len(int type, int32_t n) { return xf_known(type) ? xf_max_len(type, n) : -KZG_ERR_INVALID_CODEC; }
+// Worst case of any supported chain: a block whose entropy stage does not pay is stored as a "transformed copy"
+// (COS:926-973) = its transform output (at most Sequence.getMaxEncodedLength: LZ n + n/64 + 2, BWT + 33, SRT + 1024) plus a
+// record header (5 + 32 bits of length, mode, skip flags, 4 length bytes, checksum).
 int64_t kzg_compress_bound(int64_t n, int32_t blockSize) {
-  const i64 nb = (n + blockSize - 1) / std::max(blockSize, 1);
-  return n + nb * 16 + 64 + n / 64;
+  const i64 nb = (n + blockSize - 1) / std::max(blockSize, 1) + 1;
+  return n + n / 64 + nb * (2 + 33 + 1024 + 16) + 64;
 }
 
 // ---- one ByteTransform call -------------------------------------------------------------------------------------
@@ -522,9 +535,9 @@ static int64_t compress_impl(const uint8_t* d_in, int64_t n, const int32_t* tran
   u8 hdr[64];
   const int hdrLen = stream_header(hdr, entropy, transformType, blockSize, n);
   if (outCap < hdrLen + 2) return -KZG_ERR_WRITE_FILE;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  if (timing3) for (int i = 0; i < 4; i++) CUDA_TRY(cudaEventCreate(&ev[i]));
-  const bool lazyIn = h_in && nf >= 1 && (fn[0] == KZG_T_LZ || fn[0] == KZG_T_LZX) && nBlocks >= 8 && blockSize >= (1 << 18) && getenv("KZG_LZ_V1") == nullptr;
+  EvSet ev;
+  if (timing3) { r = ev.create(4); if (r < 0) return r; }
+  const bool lazyIn = h_in && nf >= 1 && (fn[0] == KZG_T_LZ || fn[0] == KZG_T_LZX) && nBlocks >= 8 && blockSize >= (1 << 18);
   if (h_in && n > 0) {
     if (!lazyIn) CUDA_TRY(cudaMemcpyAsync((u8*)d_in, h_in, (size_t)n, cudaMemcpyHostToDevice, W.stream));
     else {
@@ -601,11 +614,10 @@ static int64_t compress_impl(const uint8_t* d_in, int64_t n, const int32_t* tran
     if (totalBits < 0) return -KZG_ERR_PROCESS_BLOCK;
     if (timing3) {
       for (int i = 0; i < 3; i++) CUDA_TRY(cudaEventElapsedTime(&timing3[i], ev[i], ev[i + 1]));
-      for (int i = 0; i < 4; i++) cudaEventDestroy(ev[i]);
     }
   } else {
     CUDA_TRY(cudaStreamSynchronize(W.stream));
-    if (timing3) { timing3[0] = timing3[1] = timing3[2] = 0; for (int i = 0; i < 4; i++) cudaEventDestroy(ev[i]); }
+    if (timing3) { timing3[0] = timing3[1] = timing3[2] = 0; }
   }
   const i64 bytes = (totalBits + 7) >> 3;
   if (bytes > outCap - 8) { kzg_set_error("compressed stream (%lld bytes) exceeds capacity %lld", (long long)bytes, (long long)outCap); return -KZG_ERR_WRITE_FILE; }
@@ -710,7 +722,9 @@ static int64_t decompress_impl(const uint8_t* d_in, int64_t nBytes, const uint8_
   }
   const int nBlocks = (int)recs.size();
   if (nBlocks == 0) return 0;
-  if ((i64)nBlocks * blockSize > outCap + blockSize) { kzg_set_error("output capacity too small"); return -KZG_ERR_WRITE_FILE; }
+  // every block but the last decodes to blockSize bytes; the last needs at least one byte of room (its kernels are clamped to
+  // what is left: KzgBlock.finalCap, kzg_dst_limit)
+  if ((i64)(nBlocks - 1) * blockSize >= outCap) { kzg_set_error("output capacity too small"); return -KZG_ERR_WRITE_FILE; }
 
   i32 maxPre = 0; for (auto& rc : recs) maxPre = std::max(maxPre, rc.preLen);
   const i32 blkBuf = std::max(blockSize + 512, blockSize + (blockSize >> 4));      // CIS:694-695
@@ -749,13 +763,14 @@ static int64_t decompress_impl(const uint8_t* d_in, int64_t nBytes, const uint8_
       if (runs) k++;
     }
     u8* dest = d_out + (size_t)b * blockSize;
-    B.aux0 = dest; B.stagesLeft = k;
+    const i32 avail = (i32)std::min<i64>(blockSize, outCap - (i64)b * blockSize);    // bytes of the caller's buffer this block owns
+    B.aux0 = dest; B.stagesLeft = k; B.finalCap = avail;
     B.cur = (k == 0) ? dest : dE + (size_t)b * cap;
     B.alt = (k == 1) ? dest : dF + (size_t)b * cap;
     B.aux1 = dF + (size_t)b * cap;
     B.curLen = rc.preLen; B.preLen = rc.preLen; B.cap = (i32)cap - 64; B.skipFlags = rc.skipFlags;
     B.entropy = rc.entropy; B.srcBit = rc.payBit; B.srcBits = rc.payBits;
-    if (k == 0 && rc.preLen > blockSize) { kzg_set_error("Block %d incorrectly decompressed", b + 1); return -KZG_ERR_PROCESS_BLOCK; }
+    if (k == 0 && rc.preLen > avail) { kzg_set_error(rc.preLen > blockSize ? "Block %d incorrectly decompressed" : "output capacity too small for block %d", b + 1); return rc.preLen > blockSize ? -KZG_ERR_PROCESS_BLOCK : -KZG_ERR_WRITE_FILE; }
     bt.hDstLimit[b] = blkBuf;
     if (rc.entropy == KZG_E_NONE) anyNone = true; else anyEnt = true;
   }
@@ -768,8 +783,8 @@ static int64_t decompress_impl(const uint8_t* d_in, int64_t nBytes, const uint8_
   static const int gDec = getenv("KZG_DEC_GROUPS") ? std::max(1, std::min(KZG_DEC_MAXG, atoi(getenv("KZG_DEC_GROUPS")))) : 12;   // developer knob
   const int G = (nBlocks >= 8) ? std::min(gDec, nBlocks / 2) : 1;
   if (G > 1) { r = ws_side_init(); if (r < 0) return r; }
-  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
-  if (timing3) { for (int i = 0; i < 3; i++) CUDA_TRY(cudaEventCreate(&ev[i])); CUDA_TRY(cudaEventRecord(ev[0], W.stream)); }
+  EvSet ev;
+  if (timing3) { r = ev.create(3); if (r < 0) return r; CUDA_TRY(cudaEventRecord(ev[0], W.stream)); }
   if (G > 1) CUDA_TRY(cudaEventRecord(W.sideEv[KZG_DEC_MAXG], W.stream));
   cudaStream_t const mainStream = W.stream;
   int rc = 0;
@@ -804,13 +819,12 @@ static int64_t decompress_impl(const uint8_t* d_in, int64_t nBytes, const uint8_
     }
     if (G > 1) { CUDA_TRY(cudaEventRecord(W.sideEv[g], q)); CUDA_TRY(cudaStreamWaitEvent(mainStream, W.sideEv[g], 0)); }
   }
-  if (rc < 0) { for (int g = 0; g < G && G > 1; g++) cudaStreamSynchronize(W.side[g]); return rc; }
+  if (rc < 0) { W.stream = mainStream; for (int g = 0; g < G && G > 1; g++) cudaStreamSynchronize(W.side[g]); return rc; }
   if (timing3) CUDA_TRY(cudaEventRecord(ev[2], W.stream));
   r = batch_download(bt); if (r < 0) return r;
   if (timing3) {      // [1] = entropy stage of the first group, [0] = everything else up to the join (groups overlap: a split, not a sum of kernels)
     float tot = 0;
     CUDA_TRY(cudaEventElapsedTime(&timing3[1], ev[0], ev[1])); CUDA_TRY(cudaEventElapsedTime(&tot, ev[0], ev[2])); timing3[0] = tot - timing3[1]; timing3[2] = 0;
-    for (int i = 0; i < 3; i++) cudaEventDestroy(ev[i]);
   }
   i64 total = 0;
   for (int b = 0; b < nBlocks; b++) {

@@ -42,8 +42,15 @@ struct KzgBlock {
   // buffer rotation: encode: aux0 = the read-only input block, aux1 = second scratch buffer;
   // decode: aux0 = final destination of the block, stagesLeft = inverse stages still to run
   u8* aux0; u8* aux1;
-  i32 stagesLeft; i32 pad0;
+  i32 stagesLeft;
+  i32 finalCap;   // decode: bytes the caller's output buffer holds at aux0 (0 = no clamp); see kzg_dst_limit
 };
+
+// dst limit of a stage as its kernels must see it: the Java-visible limit, clamped to the caller's buffer when the stage
+// writes straight into the final destination (decode: alt == aux0), so no kernel ever writes past the caller's outCap
+__host__ __device__ __forceinline__ int kzg_dst_limit(const KzgBlock& B, int limit) {
+  return (B.finalCap > 0 && B.alt == B.aux0 && limit > B.finalCap) ? B.finalCap : limit;
+}
 
 // ---- MSB-first bit I/O on byte buffers (format of K/bitstream/Default{In,Out}putBitStream.java) -------
 __device__ __forceinline__ u32 ld_be32_unaligned(const u8* p) {

@@ -21,9 +21,9 @@ struct KzgXfParams {
   const u8* lazyHost; u8* lazyDev; i64 lazyN; i32 lazyBlock;
 };
 
-int kzg_lz_forward_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, const KzgXfParams& P, bool extra, bool smemTable);
 int kzg_lz_inverse_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, const KzgXfParams& P, i32 maxLen);
 void kzg_lzi_scratch(i32 maxLen, size_t* perBlockBytes, size_t* aux32);
 int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, const KzgXfParams& P, bool extra, i32 maxLen);
 void kzg_lzf_scratch(i32 maxLen, size_t* perBlockBytes);
+void kzg_lzf_release();
 void kzg_count_launch(int n);

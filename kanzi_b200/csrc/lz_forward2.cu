@@ -1791,6 +1791,13 @@ struct LzfStreams {
   }
 };
 static LzfStreams& lzf_streams() { static thread_local LzfStreams S; return S; }
+// frees the calling thread's side streams (kzg_set_device moving the thread to another GPU)
+void kzg_lzf_release() {
+  LzfStreams& S = lzf_streams();
+  for (int i = 0; i < S.n; i++) { cudaStreamSynchronize(S.st[i]); cudaStreamDestroy(S.st[i]); }
+  if (S.hCnt) { cudaFreeHost(S.hCnt); cudaEventDestroy(S.fork); }
+  S.n = 0; S.hCnt = nullptr;
+}
 
 int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, const KzgXfParams& P, bool extra, i32 maxLen) {
   const LzfSizes z = lzf_sizes(maxLen);
@@ -1884,14 +1891,16 @@ int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
     CUDA_TRY(cudaStreamSynchronize(s));
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return key[x] < key[y]; });
     if (dbg & 1) for (int b = 0; b < nBlocks; b++) fprintf(stderr, "lzf block %d: sparsest eighth repeats %.2f %% of its sampled 4-grams\n", b, key[b] == 0x7FFFFFFF ? -1.0 : 100.0 * key[b] / 65536.0);
-    static const int gEnv = getenv("KZG_LZ_GROUPS") ? atoi(getenv("KZG_LZ_GROUPS")) : 0;   // developer knob
+    const int gEnv = getenv("KZG_LZ_GROUPS") ? atoi(getenv("KZG_LZ_GROUPS")) : 0;   // developer knob (read per call: the tests flip it)
     const int G = std::max(1, std::min(std::min(gEnv > 0 ? gEnv : 32, LZF_MAXG), nBlocks));
     LzfStreams& ST = lzf_streams();
     if (ST.init(G) < 0) return -KZG_ERR_CREATE_CODEC;
     CUDA_TRY(cudaMemcpyAsync(dMap, order.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemsetAsync(dCnt, 0, 2 * LZF_MAXG * sizeof(int), s));
     CUDA_TRY(cudaEventRecord(ST.fork, s));
-    const int maxRounds = 8;
+    // after maxRounds fixed-point rounds a block goes to the exact serial walker; KZG_LZ_MAXROUNDS (1..8) lowers the cap so the
+    // tests can drive blocks down that path (tests/test_gpu_fuzz.py)
+    const int maxRounds = getenv("KZG_LZ_MAXROUNDS") ? std::max(1, std::min(8, atoi(getenv("KZG_LZ_MAXROUNDS")))) : 8;
     int gBeg[LZF_MAXG + 1];
     for (int g = 0; g <= G; g++) gBeg[g] = (int)((long long)nBlocks * g / G);
     auto enqueue = [&](int g, int round) {

@@ -101,7 +101,7 @@ __device__ __forceinline__ bool lzi_layout(const KzgBlock& B, const KzgXfParams&
   Y.litEnd = Y.tkBase;
   Y.maxDist = ((src[12] & 1) == 0) ? LZ_MAX_DISTANCE1 : LZ_MAX_DISTANCE2;
   Y.minMatch = ((src[12] >> 1) & 0x07) + 2;
-  Y.dstEnd = min(P.dstLimit[b], B.cap);
+  Y.dstEnd = min(kzg_dst_limit(B, P.dstLimit[b]), B.cap);
   return true;
 }
 // per-block scratch of the token passes

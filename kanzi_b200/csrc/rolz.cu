@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(32) rolz_parse_kernel(KzgBlock* __restrict__ b
   if (B.status != 0 || !P.enabled[b]) return;
   const int count = B.curLen;
   if (count < 64 || count > (1 << 30)) return;                 // MIN_BLOCK_SIZE / MAX_BLOCK_SIZE (:207-212)
-  if (((count <= 512) ? count + 64 : count) > min(B.cap, P.dstLimit[b])) return;    // output.length - output.index < getMaxEncodedLength(count)
+  if (((count <= 512) ? count + 64 : count) > min(B.cap, kzg_dst_limit(B, P.dstLimit[b]))) return;    // output.length - output.index < getMaxEncodedLength(count)
   if (count - 4 > RZ_CHUNK) { if (lane == 0) atomicExch(&B.status, -KZG_ERR_BLOCK_SIZE); return; }
   const u8* __restrict__ src = B.cur;
   u8* __restrict__ dst = B.alt;
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(256) rolz_layout_kernel(KzgBlock* __restrict__
   const int count = B.curLen;
   const i64 bytes = (tb == ~0ull) ? -1 : (i64)((tb + 7) >> 3);
   // dstIdx + buf.length > dst.length (:629-633) / dstIdx + 4 > dst.length (:642-646) -> false
-  const bool fits = (bytes >= 0) && (bytes + 4 <= (i64)min(B.cap, P.dstLimit[b]));      // dst slice length as the Java call sees it
+  const bool fits = (bytes >= 0) && (bytes + 4 <= (i64)min(B.cap, kzg_dst_limit(B, P.dstLimit[b])));      // dst slice length as the Java call sees it
   if (!fits) {
     for (int i = threadIdx.x; i < 4 * segsPerVb; i += blockDim.x) S[i].nBits = 0;
     if (threadIdx.x == 0) { res[0] = 0; res[1] = 0; if (tb == ~0ull) atomicExch(&B.status, -KZG_ERR_PROCESS_BLOCK); }
@@ -327,7 +327,7 @@ __global__ void rolz_scan_kernel(KzgBlock* __restrict__ blocks, int nBlocks, Kzg
   const u8* __restrict__ src = B.cur;
   if (count < 5 + 16 + 4) return;
   const int szBlock = (int)(((u32)src[0] << 24) | ((u32)src[1] << 16) | ((u32)src[2] << 8) | (u32)src[3]) - 4;
-  const int outLimit = min(P.dstLimit[b], B.cap);
+  const int outLimit = min(kzg_dst_limit(B, P.dstLimit[b]), B.cap);
   if (szBlock <= 0 || szBlock > outLimit - 4) return;
   if (szBlock > RZ_CHUNK) { B.status = -KZG_ERR_BLOCK_SIZE; return; }
   const int flags = src[4];
@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(32) rolz_replay_kernel(KzgBlock* __restrict__ 
     if ((tkIdx != I.tkLen) || (mIdxIdx != I.mIdxLen) || (litIdx != I.litLen) || (lenIdx != I.mLenLen)) return;
   }
   // a valid ROLZ block leaves exactly 4 raw tail bytes (:943-957)
-  if ((dstIdx + 4 > min(P.dstLimit[b], B.cap)) || (count - srcIdx != 4)) return;
+  if ((dstIdx + 4 > min(kzg_dst_limit(B, P.dstLimit[b]), B.cap)) || (count - srcIdx != 4)) return;
   if (lane < 4) dst[dstIdx + lane] = src[srcIdx + lane];
   if (lane == 0) { res[0] = 1; res[1] = dstIdx + 4; }
 }

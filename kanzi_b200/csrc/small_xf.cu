@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(32) zrlt_inverse_kernel(KzgBlock* __restrict__
   const int count = B.curLen;
   const u8* __restrict__ src = B.cur;
   u8* __restrict__ dst = B.alt;
-  const i64 dstEnd = min(P.dstLimit[b], B.cap);
+  const i64 dstEnd = min(kzg_dst_limit(B, P.dstLimit[b]), B.cap);
   i64 dstIdx = 0;
   u64 carryVal = 1;          // run length accumulated by the digit sequence in progress (1 = none)
   bool pendingEsc = false;   // the previous tile ended with an unpaired 0xFF
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(32) srt_inverse_kernel(KzgBlock* __restrict__ 
   const int hdr = S.hdrLen;
   if (hdr < 0) return;
   const int count = length - hdr;
-  if (count > min(P.dstLimit[b], B.cap) || count < 0) return;
+  if (count > min(kzg_dst_limit(B, P.dstLimit[b]), B.cap) || count < 0) return;
   const u8* __restrict__ in = src + hdr;
   for (int i = lane; i < 256; i += 32) { S.r2s[i] = 0; S.buckets[i] = 0; S.bucketEnds[i] = 0; if (S.freqs[i] < 0) S.freqs[i] = 0; }
   __syncwarp();

@@ -61,3 +61,34 @@ def test_cfg3_full_block_size_round_trip():
         ref = O.compress(data[:bs], tr, ent, bs, bwt_bounds=1 if flags else 0)
         got = K.compress(data[:bs], tr, ent, bs, flags=flags)
         assert got == ref, (flags, "first differing byte", _first_diff(got, ref))
+
+
+@pytest.mark.timeout(1800)
+def test_cfg4_real_block_size_two_blocks():
+    """cfg4's chain (BWT+SRT+ZRLT & FPAQ) at its real block size: two blocks of 32 MiB (the n > 8 MiB regime: biPSIv2 on the
+    reference side, K/transform/BWT.java:384-544; 8 FPAQ chunks of 4 MiB sharing state, K/entropy/FPAQEncoder.java:140-170),
+    both readings of the BWT bounds clause.  First block's record against the oracle, both blocks round trip."""
+    gen, size, tr, ent, bs = synth.CONFIGS["cfg4"]
+    assert bs == 32 << 20
+    data = gen(2 * bs - 54321, 4).tobytes()
+    for flags in (K.FLAG_BWT_ASREF, 0):
+        knz = K.compress(data, tr, ent, bs, flags=flags)
+        assert K.decompress(knz, len(data), flags=flags) == data
+        ref = O.compress(data[:bs], tr, ent, bs, bwt_bounds=1 if flags else 0)
+        got = K.compress(data[:bs], tr, ent, bs, flags=flags)
+        assert got == ref, (flags, "first differing byte", _first_diff(got, ref))
+        hdr, body = 24, len(got) - 2          # block independence: the one-block stream's record opens the two-block stream
+        assert knz[hdr:body] == got[hdr:body]
+
+
+@pytest.mark.timeout(1800)
+def test_cfg5_real_block_size_four_blocks():
+    """cfg5's chain (ROLZ & ANS0) at its real block size: four blocks of 16 MiB (one full ROLZ chunk each, ROLZCodec.java:497-509),
+    whole stream against the oracle, and the decode of the oracle's stream."""
+    gen, size, tr, ent, bs = synth.CONFIGS["cfg5"]
+    assert bs == 16 << 20
+    data = gen(4 * bs - 777, 5).tobytes()
+    ref = O.compress(data, tr, ent, bs)
+    got = K.compress(data, tr, ent, bs)
+    assert got == ref, ("first differing byte", _first_diff(got, ref))
+    assert K.decompress(ref, len(data)) == data

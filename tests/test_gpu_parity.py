@@ -46,13 +46,82 @@ def test_entropy_interfaces_like_reference_test(ent):
         assert bytes(out) == d
 
 
-def test_entropy_decode_rejects_corruption():
-    d = CASES["text64k"]
-    ref, bits = O.entropy_encode("ANS0", d)
-    bad = bytearray(ref)
-    bad[len(bad) // 2] ^= 0x55
-    out, r, used = K.entropy_decode("ANS0", bytes(bad[: len(bad) // 3]), (len(bad) // 3) * 8, len(d))
-    assert r != len(d) or out != d
+def _varint_len(b):
+    n = 0
+    while b[n] & 0x80:
+        n += 1
+    return n + 1
+
+
+def test_fpaq_zero_declared_size_like_reference_test():
+    """T/test/TestEntropyCodec.java:293-326 (testFPAQZeroDeclaredSize): the chunk's declared byte count replaced by 0 must not
+    decode to `size` bytes."""
+    size = 1 << 20
+    d = bytes((i * 17) & 0xFF for i in range(size))
+    enc, bits = K.entropy_encode("FPAQ", d)
+    assert (enc, bits) == O.entropy_encode("FPAQ", d)
+    skip = _varint_len(enc)
+    assert skip > 0
+    mutated = bytes([0]) + enc[skip:]
+    out, r, used = K.entropy_decode("FPAQ", mutated, 8 * len(mutated), size)
+    assert r != size
+    _, r_ref, _ = O.entropy_decode("FPAQ", mutated, 8 * len(mutated), size)
+    assert r_ref != size
+
+
+@pytest.mark.parametrize("ent", ["HUFFMAN", "ANS0", "ANS1", "FPAQ"])
+def test_entropy_decode_corrupt_payload(ent):
+    """Bit flips INSIDE the payload (the stream keeps its length): every flip must either fail the call or change the bytes, never
+    return the original data as if nothing happened, and never fault.  Truncation must fail or differ as well."""
+    d = CASES["text64k"] + CASES["exe"][:40000]
+    ref, bits = O.entropy_encode(ent, d)
+    rng = np.random.default_rng(77)
+    flips = sorted(set(int(x) for x in rng.integers(64, bits - 64, 24)))
+    silent = 0
+    for pos in flips:
+        bad = bytearray(ref)
+        bad[pos >> 3] ^= 0x80 >> (pos & 7)
+        out, r, used = K.entropy_decode(ent, bytes(bad), bits, len(d))
+        assert r != len(d) or out != d, (ent, "flip at bit", pos, "went unnoticed")
+        if r == len(d):
+            silent += 1
+    # a truncated stream (a third of it) never yields the data
+    cut = (bits // 3) & ~7
+    out, r, used = K.entropy_decode(ent, ref[: cut >> 3], cut, len(d))
+    assert r != len(d) or out != d, (ent, "truncation went unnoticed")
+    # and the clean stream still decodes after all that (no sticky device error)
+    out, r, used = K.entropy_decode(ent, ref, bits, len(d))
+    assert r == len(d) and out == d and used == bits
+
+
+def test_stream_corruption_is_reported():
+    """Whole-stream negative cases: bad magic, header checksum, block-header checksum, truncated stream, undersized output."""
+    d = synth.text(300_000, 61).tobytes()
+    knz = K.compress(d, ["LZ"], "ANS0", 1 << 16)
+    for mutate in (lambda b: b.__setitem__(0, b[0] ^ 1), lambda b: b.__setitem__(10, b[10] ^ 0x10), lambda b: b.__setitem__(23, b[23] ^ 0x01), lambda b: b.__setitem__(25, b[25] ^ 0x40)):
+        bad = bytearray(knz)
+        mutate(bad)
+        with pytest.raises(K.KzgError):
+            K.decompress(bytes(bad), len(d) + 1024)
+    with pytest.raises(K.KzgError):
+        K.decompress(knz[: len(knz) // 2], len(d) + 1024)
+    # ADVICE r01 (high): an output buffer smaller than the data must fail cleanly, not overrun
+    for cap in (len(d) - 1, len(d) - 65536, 65536 + 1, 1):
+        with pytest.raises(K.KzgError):
+            K.decompress(knz, cap)
+    assert K.decompress(knz, len(d)) == d                      # exactly enough room is enough
+
+
+def test_compress_bound_covers_srt_headers():
+    """SRT prepends 256 varints (256..1024 bytes) to every block; on incompressible small blocks the
+    stream exceeds n + 16 per block.  kzg_compress_bound must cover it and kzg_compress must succeed."""
+    d = synth.noise(40_000, 62).tobytes()
+    for bs in (1024, 4096, 65536):
+        ref = O.compress(d, ["BWT", "SRT", "ZRLT"], "FPAQ", bs)
+        assert len(ref) <= K.compress_bound(len(d), bs)
+        got = K.compress(d, ["BWT", "SRT", "ZRLT"], "FPAQ", bs)
+        assert got == ref
+        assert K.decompress(got, len(d)) == d
 
 
 # ---- transforms: TestTransforms.java-style ---------------------------------------------------------------------------------
