@@ -434,121 +434,327 @@ __device__ int ans_decode_ctx_header(BitReaderD& br, int lr, int llr, u16* freq,
 }
 
 // ================================================================================================================
-// order 0 decode: grid (ceil(maxChunks/32), nBlocks), 128 threads; group of 4 lanes = one chunk
+// order 0 decode: one warp = 8 chunks of 4 lanes (one lane per interleaved state), one warp per CTA, 5 CTAs per SM
+// (42 KiB of tables each).
+//   * headers are parsed by the whole warp out of a shared-memory copy (alphabet bitmap: one mask byte per lane; the
+//     frequency groups: one group per lane once the 32-step chain of group offsets is known), cumulative frequencies by a
+//     warp scan, the slot -> symbol table filled slot-parallel (every lane owns 1/32 of the slots);
+//   * the coded bytes never touch shared memory: every group keeps the next 128 bits of its byte stream in registers
+//     (two 64-bit words, pre-shifted to the stream's bit offset) plus three raw words in flight, 8-byte aligned loads
+//     issued two refills ahead; the whole payload is pulled into L2 while the headers are parsed;
+//   * output: the four symbols of a step are packed with two shuffles, every lane stores one 32-bit word per four
+//     steps (16 contiguous bytes per group).
+// ANSRangeDecoder.decodeChunkV2 (:357-440): symbol i+j is decoded with state st(3-j); states below TOP read 16 bits
+// each in lane order (the ballot / popcount below).
 // ================================================================================================================
+#define A0D_CHUNKS 8
+#define A0D_HDR_WORDS 144
 struct A0DecSmem {
-  u8 f2s[A0_GROUPS][4096];
-  u32 sym[A0_GROUPS][256];      // freq | cumFreq << 16
-  u16 freq[A0_GROUPS][256];
-  u8 alpha[A0_GROUPS][256];
+  u8 f2s[A0D_CHUNKS][4096];
+  u32 sym[A0D_CHUNKS][256];      // freq | cumFreq << 16
+  u32 hdr[A0D_HDR_WORDS + 2];    // header bytes of the chunk being parsed, as big-endian words
+  u16 freq[256];
+  u8 alpha[256];
 };
+__device__ __forceinline__ u64 kzg_shl64(u64 x, u32 n) { u64 r; asm("shl.b64 %0, %1, %2;" : "=l"(r) : "l"(x), "r"(n)); return r; }   // n >= 64 -> 0
+__device__ __forceinline__ u64 kzg_shr64(u64 x, u32 n) { u64 r; asm("shr.u64 %0, %1, %2;" : "=l"(r) : "l"(x), "r"(n)); return r; }
+__device__ __forceinline__ u64 a0d_ld_be64(const u8* p, const u8* limit) {        // p 8-byte aligned; words at or beyond limit read as zero
+  if (p >= limit) return 0ull;
+  const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+  return ((u64)__byte_perm(v.x, 0, 0x0123) << 32) | (u64)__byte_perm(v.y, 0, 0x0123);
+}
+__device__ __forceinline__ u32 a0d_bits(const u32* w, u32 pos, int n) {           // n in 1..32, MSB first
+  const u32 i = pos >> 5;
+  return __funnelshift_l(w[i + 1], w[i], pos & 31) >> (32 - n);
+}
 
-__global__ void __launch_bounds__(128) ans0_decode_kernel(KzgBlock* __restrict__ blocks, KzgEntParams P) {
-  extern __shared__ __align__(16) u8 smem_raw[];
-  A0DecSmem& S = *reinterpret_cast<A0DecSmem*>(smem_raw);
-  const int g = threadIdx.x >> 2, j = threadIdx.x & 3;
+// ANSRangeDecoder.decodeHeader (:452-544) for chunk slot k of this warp, all 32 lanes: fills S.sym[k] / S.f2s[k].
+// Returns the alphabet size (1: `single` is the symbol, no tables), or -1 for a header the reference rejects.
+__device__ int a0d_parse_header(A0DecSmem& S, int k, const u8* __restrict__ stream, u64 hdrBit, u64 endBit, int lane, int& lrOut, int& single) {
+  const u64 byte0 = (hdrBit >> 3) & ~3ull;
+  const u64 lastByte = (endBit + 7) >> 3;
+  __syncwarp();
+  for (int i = lane; i < A0D_HDR_WORDS + 2; i += 32) {
+    const u64 o = byte0 + 4ull * i;
+    S.hdr[i] = (o < lastByte) ? __byte_perm(__ldg(reinterpret_cast<const u32*>(stream + o)), 0, 0x0123) : 0u;
+  }
+  __syncwarp();
+  u32 pos = (u32)(hdrBit - 8 * byte0);
+  const int lr = 8 + (int)a0d_bits(S.hdr, pos, 3); pos += 3;
+  lrOut = lr;
+  single = 0;
+  if (lr > 12) return -1;                    // order-0 tables are sized for the reference's logRange 12 (ANSRangeEncoder :40)
+  const int llr = 4;                         // while ((1 << llr) <= lr) llr++ from 3: 4 for every lr in 8..15
+  const int scale = 1 << lr;
+  int as;
+  if (a0d_bits(S.hdr, pos, 1) == 0) {        // EntropyUtils.decodeAlphabet (:84-131)
+    if (a0d_bits(S.hdr, pos + 1, 1) == 1) return -1;      // empty alphabet: decode() stops (:218-219)
+    pos += 2; as = 256;
+    for (int i = lane; i < 256; i += 32) S.alpha[i] = (u8)i;
+  } else {
+    const int lastMask = (int)a0d_bits(S.hdr, pos + 1, 5); pos += 6;
+    const u32 m = (lane <= lastMask) ? a0d_bits(S.hdr, pos + 8 * lane, 8) : 0u;
+    const int cnt = __popc(m);
+    int incl = cnt;
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+    as = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    int at = incl - cnt;
+    for (u32 mm = m; mm; mm &= mm - 1) S.alpha[at++] = (u8)((lane << 3) + (__ffs(mm) - 1));
+    pos += 8 * (lastMask + 1);
+    if (as == 0) return -1;
+  }
+  if (as != 256) for (int i = lane; i < 256; i += 32) S.freq[i] = 0;
+  __syncwarp();
+  // the chain of group offsets (every lane runs it; lane gi keeps group gi)
+  const int chk = (as >= 64) ? 8 : 6;
+  int myPos = 0, myLog = 0, myCnt = 0, gi = 0;
+  bool bad = false;
+  for (int i = 1; i < as; i += chk, gi++) {
+    const int logMax = (int)a0d_bits(S.hdr, pos, llr);
+    const int cnt = min(chk, as - i);
+    if (lane == gi) { myPos = (int)pos + llr; myLog = logMax; myCnt = cnt; }
+    if ((1 << logMax) > scale) bad = true;
+    pos += llr + logMax * cnt;
+  }
+  int sum = 0;
+  if (!bad) {
+    for (int t = 0; t < myCnt; t++) {
+      const int f = (myLog == 0) ? 1 : 1 + (int)a0d_bits(S.hdr, (u32)(myPos + t * myLog), myLog);
+      if (f >= scale) bad = true;
+      S.freq[S.alpha[1 + lane * chk + t]] = (u16)f;
+      sum += f;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+  if (__any_sync(0xFFFFFFFFu, bad) || scale <= sum) return -1;
+  if (lane == 0) S.freq[S.alpha[0]] = (u16)(scale - sum);
+  __syncwarp();
+  if (as == 1) { single = S.alpha[0]; return 1; }
+  // cumulative frequencies: lane owns symbols 8*lane .. 8*lane+7
+  int f8[8], tot = 0;
+  #pragma unroll
+  for (int t = 0; t < 8; t++) { f8[t] = S.freq[8 * lane + t]; tot += f8[t]; }
+  int incl = tot;
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+  int cum = incl - tot;
+  #pragma unroll
+  for (int t = 0; t < 8; t++) { S.sym[k][8 * lane + t] = (u32)f8[t] | ((u32)cum << 16); cum += f8[t]; }
+  __syncwarp();
+  // slot -> symbol, slot-parallel: lane owns slots [lane * per, (lane + 1) * per)
+  const int per = scale >> 5;                  // 8 .. 128
+  const int slot0 = lane * per;
+  int lo = 0, hi = 255;
+  while (lo < hi) {                            // first symbol whose interval ends beyond slot0
+    const int mid = (lo + hi) >> 1;
+    const u32 e = S.sym[k][mid];
+    if ((int)((e >> 16) + (e & 0xFFFFu)) > slot0) hi = mid; else lo = mid + 1;
+  }
+  int sy = lo;
+  u32 e = S.sym[k][sy];
+  int endOf = (int)((e >> 16) + (e & 0xFFFFu));
+  u32* row = reinterpret_cast<u32*>(&S.f2s[k][slot0]);
+  for (int i = 0; i < per; i += 4) {
+    u32 w = 0;
+    #pragma unroll
+    for (int t = 0; t < 4; t++) {
+      while (slot0 + i + t >= endOf) { sy++; e = S.sym[k][sy]; endOf = (int)((e >> 16) + (e & 0xFFFFu)); }
+      w |= (u32)sy << (8 * t);
+    }
+    row[i >> 2] = w;
+  }
+  __syncwarp();
+  return as;
+}
+
+// Chunk scan, order 0: one CTA per block.  Warp 0 walks the chunk headers (chunk k+1 starts where chunk k's byte count says:
+// the one serial chain of the decode) out of a shared-memory copy of each header, every lane running the same parse; the other
+// three warps pull the block's whole payload into L2 meanwhile, so the walk (and the decode kernel after it) never waits for DRAM.
+// Per chunk: one staging round trip to L2 + the 32-step chain of frequency-group offsets.
+__global__ void __launch_bounds__(128) ans0_scan_kernel(KzgBlock* __restrict__ blocks, int nBlocks, KzgEntParams P) {
+  __shared__ u32 hdr[A0D_HDR_WORDS + 2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x;
+  KzgBlock& B = blocks[b];
+  if (B.status != 0 || B.entropy != P.entropy) return;
+  const int len = B.preLen;
+  if (len <= 32) {   // raw (ANSRangeDecoder.decode :193-196)
+    if (threadIdx.x == 0) { if ((u64)len * 8 > (u64)B.srcBits) B.status = -KZG_ERR_PROCESS_BLOCK; else B.entBits = (i64)len * 8; }
+    return;
+  }
+  const u8* __restrict__ stream = P.stream;
+  const u64 endBit = (u64)(B.srcBit + B.srcBits);
+  const u64 lastByte = (endBit + 7) >> 3;
+  if (warp > 0) {
+    const u64 first = ((u64)B.srcBit >> 3) & ~127ull;
+    for (u64 o = first + 128ull * (threadIdx.x - 32); o < lastByte; o += 128ull * 96) asm volatile("prefetch.global.L2 [%0];" ::"l"(stream + o));
+    return;
+  }
+  KzgChunkInfo* ci = P.chunks + (i64)b * P.maxChunks;
+  const int chunkSize = P.chunkSize;
+  const int nChunks = (len + chunkSize - 1) / chunkSize;
+  u64 at = (u64)B.srcBit;
+  int status = 0;
+  for (int c = 0; c < nChunks; c++) {
+    if (at + 3 > endBit) { status = -KZG_ERR_PROCESS_BLOCK; break; }
+    const u64 byte0 = (at >> 3) & ~3ull;
+    __syncwarp();
+    for (int i = lane; i < A0D_HDR_WORDS + 2; i += 32) {
+      const u64 o = byte0 + 4ull * i;
+      hdr[i] = (o < lastByte) ? __byte_perm(__ldcg(reinterpret_cast<const u32*>(stream + o)), 0, 0x0123) : 0u;
+    }
+    __syncwarp();
+    u32 pos = (u32)(at - 8 * byte0);
+    const u32 pos00 = pos;
+    pos += 3;                                // logRange
+    int as;
+    if (a0d_bits(hdr, pos, 1) == 0) { as = (a0d_bits(hdr, pos + 1, 1) == 1) ? 0 : 256; pos += 2; }
+    else {
+      const int lastMask = (int)a0d_bits(hdr, pos + 1, 5); pos += 6;
+      int cnt = (lane <= lastMask) ? __popc(a0d_bits(hdr, pos + 8 * lane, 8)) : 0;
+      for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+      as = cnt;
+      pos += 8 * (lastMask + 1);
+    }
+    if (as == 0) { status = -KZG_ERR_PROCESS_BLOCK; break; }       // decode returns early (:218-219)
+    const int chk = (as >= 64) ? 8 : 6;
+    for (int i = 1; i < as; i += chk) pos += 4 + (int)a0d_bits(hdr, pos, 4) * min(chk, as - i);
+    KzgChunkInfo info;
+    info.hdrBit = (i64)at; info.alphabetSize = as; info.sz = 0; info.payBit = 0;
+    info.st[0] = info.st[1] = info.st[2] = info.st[3] = 0;
+    if (as != 1) {
+      u32 value = a0d_bits(hdr, pos, 8), sz = value & 0x7F; pos += 8;          // EntropyUtils.readVarInt (:283-300)
+      int shift = 7;
+      while (value >= 128) { value = a0d_bits(hdr, pos, 8); pos += 8; sz |= ((value & 0x7F) << shift); if (shift == 28) break; shift += 7; }
+      if ((i32)sz < 0 || sz >= (1u << 27)) { status = -KZG_ERR_PROCESS_BLOCK; break; }
+      info.st[0] = a0d_bits(hdr, pos, 32); info.st[1] = a0d_bits(hdr, pos + 32, 32); info.st[2] = a0d_bits(hdr, pos + 64, 32); info.st[3] = a0d_bits(hdr, pos + 96, 32);
+      pos += 128;
+      info.sz = (i32)sz;
+      info.payBit = (i64)(at + (pos - pos00));
+      at += (u64)(pos - pos00) + (u64)sz * 8;
+    } else at += (u64)(pos - pos00);
+    if (at > endBit) { status = -KZG_ERR_PROCESS_BLOCK; break; }
+    if (lane == 0) ci[c] = info;
+  }
+  if (lane == 0) { if (status < 0) B.status = status; else B.entBits = (i64)at - B.srcBit; }
+}
+
+__global__ void __launch_bounds__(32) ans0_decode_kernel(KzgBlock* __restrict__ blocks, KzgEntParams P) {
+  __shared__ A0DecSmem S;
+  const int lane = threadIdx.x, g = lane >> 2, j = lane & 3, gl = lane & ~3;
   const int b = blockIdx.y;
-  const int c = blockIdx.x * A0_GROUPS + g;
   KzgBlock& B = blocks[b];
   const bool blockOk = (B.status == 0 && B.entropy == P.entropy);
   const int len = blockOk ? B.preLen : 0;
   u8* __restrict__ out = B.cur;
   const u8* __restrict__ stream = P.stream;
+  if (len <= 32) {   // raw (ANSRangeDecoder.decode :193-196)
+    if (blockOk && blockIdx.x == 0 && lane < len) out[lane] = (u8)get_bits(stream, (u64)B.srcBit + 8ull * lane, 8);
+    return;
+  }
   const int chunkSize = P.chunkSize;
+  const int nChunks = min((len + chunkSize - 1) / chunkSize, P.maxChunks);
+  const int c0 = blockIdx.x * A0D_CHUNKS;
+  if (c0 >= nChunks) return;
+  const int c = c0 + g;
+  const bool active = c < nChunks;
   const int start = c * chunkSize;
-
-  if (len <= 32) {   // raw
-    if (blockOk && c == 0 && j == 0) for (int i = 0; i < len; i++) out[i] = (u8)get_bits(stream, (u64)B.srcBit + 8ull * i, 8);
-    return;          // whole CTA shares (b): uniform exit for every warp
-  }
-  const bool active = (c < P.maxChunks) && (start < len);
   const int end = active ? min(start + chunkSize, len) : 0;
+  const u64 endBit = (u64)(B.srcBit + B.srcBits);
+  const u8* limit = reinterpret_cast<const u8*>((reinterpret_cast<uintptr_t>(stream + ((endBit + 7) >> 3)) + 7) & ~(uintptr_t)7);
   KzgChunkInfo info;
-  info.alphabetSize = 0;
+  info.hdrBit = 0; info.payBit = 0; info.sz = 0; info.alphabetSize = 0; info.st[0] = info.st[1] = info.st[2] = info.st[3] = 0;
   if (active) info = P.chunks[(i64)b * P.maxChunks + c];
-
-  // ---- header -> tables ----
-  int lr = 12;
-  int bad = 0;
-  if (active && j == 0) {
-    BitReaderD br(stream, (u64)info.hdrBit, (u64)(B.srcBit + B.srcBits));
-    lr = 8 + (int)br.read(3);
-    int llr = 3;
-    while ((1 << llr) <= lr) llr++;
-    bool cleared = false;
-    if (lr > 12) bad = 1;     // order-0 tables are sized for the reference's logRange 12 (ANSRangeEncoder :40)
-    else {
-      const int as = ans_decode_ctx_header(br, lr, llr, S.freq[g], S.alpha[g], cleared);
-      if (as <= 0) bad = 1;
-      else {
-        int sum = 0;
-        for (int i = 0; i < 256; i++) {
-          const int f = S.freq[g][i];
-          if (f == 0 && as != 256) continue;
-          if (as == 256 && f == 0) { bad = 1; break; }
-          const int fe = (f >= (1 << lr)) ? (1 << lr) - 1 : f;
-          S.sym[g][i] = (u32)fe | ((u32)sum << 16);
-          sum += f;
-        }
-      }
-    }
+  const u8* payByte = stream + ((u64)info.payBit >> 3);
+  if (active && info.sz > 0) {       // pull the coded bytes into L2 while the headers are parsed
+    for (int o = 128 * j; o < info.sz + 64; o += 512) if (payByte + o < limit) asm volatile("prefetch.global.L2 [%0];" ::"l"(payByte + o));
   }
-  const int gl = (threadIdx.x & 31) & ~3;
-  lr = __shfl_sync(0xFFFFFFFFu, lr, gl);
-  bad = __shfl_sync(0xFFFFFFFFu, bad, gl);
-  __syncwarp();
-  const bool single = active && (info.alphabetSize == 1);
-  const bool coding = active && !single && !bad;
-  if (coding) {   // f2s fill, 4 lanes interleaved over symbols
-    for (int s = j; s < 256; s += 4) {
-      const u32 f = S.freq[g][s];
-      if (f == 0) continue;
-      const u32 cum = S.sym[g][s] >> 16;
-      for (u32 k = 0; k < f; k++) S.f2s[g][cum + k] = (u8)s;
-    }
-  }
-  if (single) {     // shortcut for chunks with only one symbol (:221-224)
-    const u8 v = S.alpha[g][0];
-    for (int i = start + j; i < end; i += 4) out[i] = v;
+  // ---- headers -> tables, one chunk after the other, the whole warp on each ----
+  int lr = 12, bad = 0, single = -1;
+  for (int k = 0; k < A0D_CHUNKS; k++) {
+    if (c0 + k >= nChunks) break;
+    const u64 hb = (u64)__shfl_sync(0xFFFFFFFFu, (unsigned long long)info.hdrBit, 4 * k);
+    int lrK, sgl;
+    const int as = a0d_parse_header(S, k, stream, hb, endBit, lane, lrK, sgl);
+    if (g == k) { lr = lrK; bad = (as <= 0) ? 1 : 0; single = (as == 1) ? sgl : -1; }
   }
   __syncwarp();
+  const bool coding = active && !bad && single < 0;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(out) + (uintptr_t)start) & 3) == 0;
+  if (active && single >= 0) {     // shortcut for chunks with only one symbol (:221-224)
+    for (int i = start + j; i < end; i += 4) out[i] = (u8)single;
+  }
 
   // ---- decodeChunkV2 (:357-440) ----
   const int end4 = start + ((end - start) & -4);
-  int steps = coding ? ((end4 - start) >> 2) : 0;
+  const int steps = coding ? ((end4 - start) >> 2) : 0;
   int maxSteps = steps;
   for (int o = 16; o > 0; o >>= 1) maxSteps = max(maxSteps, __shfl_xor_sync(0xFFFFFFFFu, maxSteps, o));
-  i32 st = coding ? (i32)info.st[3 - j] : 0;     // lane j decodes symbol i+j with state st(3-j) (:392-405)
-  const int mask = (1 << lr) - 1;
-  int cursor = 0;
+  u32 st = (j == 0) ? info.st[3] : ((j == 1) ? info.st[2] : ((j == 2) ? info.st[1] : info.st[0]));   // lane j decodes symbol i+j with state st(3-j) (:392-405)
+  if (!coding) st = 0u;
+  const u32 mask = (1u << lr) - 1;
   const u32 lowerMask = (1u << j) - 1;
-  const i64 payBit = info.payBit;
-  const int sz = info.sz;
+  // the group's byte stream: q0:q1 = its next 128 bits (bitpos < 64 of them already consumed)
+  const u8* w0 = reinterpret_cast<const u8*>(reinterpret_cast<uintptr_t>(payByte) & ~(uintptr_t)7);
+  const u32 off = (u32)((payByte - w0) * 8) + (u32)((u64)info.payBit & 7);
+  u64 q0 = 0, q1 = 0, rawPrev = 0, rawN1 = 0, rawN2 = 0;
+  const u8* wp = w0;
+  if (coding) {
+    const u64 r0 = a0d_ld_be64(w0, limit), r1 = a0d_ld_be64(w0 + 8, limit), r2 = a0d_ld_be64(w0 + 16, limit);
+    rawN1 = a0d_ld_be64(w0 + 24, limit); rawN2 = a0d_ld_be64(w0 + 32, limit);
+    q0 = kzg_shl64(r0, off) | kzg_shr64(r1, 64 - off);
+    q1 = kzg_shl64(r1, off) | kzg_shr64(r2, 64 - off);
+    rawPrev = r2;
+    wp = w0 + 40;
+  }
+  u32 bitpos = 0;
+  int consumed = 0;                          // bytes
+  const u8* f2s = S.f2s[g];
+  const u32* symt = S.sym[g];
+  u32* out32 = reinterpret_cast<u32*>(out + (aligned ? start : 0));
+  u32 keep = 0;
   for (int s = 0; s < maxSteps; s++) {
     const bool on = s < steps;
     bool need = false;
+    u32 symv = 0;
     if (on) {
-      const int slot = st & mask;
-      const int sym = S.f2s[g][slot];
-      const u32 fc = S.sym[g][sym];
-      out[start + 4 * s + j] = (u8)sym;
-      st = (i32)((fc & 0xFFFFu) * ((u32)st >> lr) + (u32)slot - (fc >> 16));
-      need = st < ANS_TOP;
+      const u32 slot = st & mask;
+      symv = f2s[slot];
+      const u32 fc = symt[symv];
+      st = (fc & 0xFFFFu) * (st >> lr) + slot - (fc >> 16);
+      need = st < (u32)ANS_TOP;
     }
     const u32 m = (__ballot_sync(0xFFFFFFFFu, need) >> gl) & 0xFu;
+    u32 pk = symv << (8 * j);
+    pk |= __shfl_xor_sync(0xFFFFFFFFu, pk, 1);
+    pk |= __shfl_xor_sync(0xFFFFFFFFu, pk, 2);
     if (on) {
       if (need) {
-        const int off = cursor + 2 * __popc(m & lowerMask);
-        st = (i32)(((u32)st << 16) | ans_pay16(stream, payBit, off, sz));
+        const u32 p = bitpos + 16u * __popc(m & lowerMask);
+        const u64 src = (p & 64u) ? q1 : q0;
+        st = (st << 16) | ((u32)kzg_shr64(src, 48u - (p & 63u)) & 0xFFFFu);
       }
-      cursor += 2 * __popc(m);
+      const u32 cbits = 16u * __popc(m);
+      bitpos += cbits;
+      consumed += (int)(cbits >> 3);
+      if (bitpos >= 64u) {                   // the group moves on by one word; the load issued here is used two refills from now
+        bitpos -= 64u;
+        q0 = q1;
+        q1 = kzg_shl64(rawPrev, off) | kzg_shr64(rawN1, 64 - off);
+        rawPrev = rawN1; rawN1 = rawN2; rawN2 = a0d_ld_be64(wp, limit); wp += 8;
+      }
+      if (aligned) {
+        if ((s & 3) == j) keep = pk;
+        if ((s & 3) == 3) out32[4 * (s >> 2) + j] = keep;
+      } else out[start + 4 * s + j] = (u8)symv;
     }
   }
   if (coding) {
+    if (aligned && j < (steps & 3)) out32[(steps & ~3) + j] = keep;
     const int tail = end - end4;
+    const int sz = info.sz;
     if (j == 0) {
-      for (int i = 0; i < tail; i++) out[end4 + i] = (cursor + i < sz) ? (u8)ans_pay8(stream, payBit, cursor + i) : 0;
-      if (cursor + tail != sz) atomicExch(&B.status, -KZG_ERR_PROCESS_BLOCK);   // decodeChunkV2 returns n == sz
+      for (int i = 0; i < tail; i++) out[end4 + i] = (consumed + i < sz) ? (u8)get_bits(stream, (u64)info.payBit + 8ull * (u64)(consumed + i), 8) : 0;
+      if (consumed + tail != sz) atomicExch(&B.status, -KZG_ERR_PROCESS_BLOCK);   // decodeChunkV2 returns n == sz
     }
   }
   if (active && bad && j == 0) atomicExch(&B.status, -KZG_ERR_PROCESS_BLOCK);
@@ -828,13 +1034,13 @@ int kzg_ans_encode_launch(cudaStream_t s, const KzgBlock* d_blocks, int nBlocks,
 
 int kzg_ans_decode_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, const KzgEntParams& P, int order, bool withScan) {
   if (withScan) {
-    ans_scan_kernel<<<(nBlocks + ANS_SCAN_WARPS - 1) / ANS_SCAN_WARPS, 32 * ANS_SCAN_WARPS, 0, s>>>(d_blocks, nBlocks, P, order);
+    if (order == 0) ans0_scan_kernel<<<nBlocks, 128, 0, s>>>(d_blocks, nBlocks, P);
+    else ans_scan_kernel<<<(nBlocks + ANS_SCAN_WARPS - 1) / ANS_SCAN_WARPS, 32 * ANS_SCAN_WARPS, 0, s>>>(d_blocks, nBlocks, P, order);
     CUDA_TRY(cudaGetLastError());
   }
   if (order == 0) {
-    CUDA_TRY(cudaFuncSetAttribute(ans0_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(A0DecSmem)));
-    dim3 grid((P.maxChunks + A0_GROUPS - 1) / A0_GROUPS, nBlocks);
-    ans0_decode_kernel<<<grid, 128, sizeof(A0DecSmem), s>>>(d_blocks, P);
+    dim3 grid((P.maxChunks + A0D_CHUNKS - 1) / A0D_CHUNKS, nBlocks);
+    ans0_decode_kernel<<<grid, 32, 0, s>>>(d_blocks, P);
   } else {
     dim3 grid(P.maxChunks, nBlocks);
     ans1_decode_kernel<<<grid, 32, 0, s>>>(d_blocks, P);

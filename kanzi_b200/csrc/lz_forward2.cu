@@ -1711,12 +1711,13 @@ __global__ void __launch_bounds__(LZF_ET) lzf_emit_write_kernel(KzgBlock* __rest
 
 // ---- host ------------------------------------------------------------------------------------------------------------------------------
 static size_t lzf_al(size_t v) { return (v + 255) / 256 * 256; }
-struct LzfSizes { size_t key, sa, prev, len0, skipped, hist, tk, m, ml, spec, patch, seg, rng, total; int segLen, maxSeg, evStride, patchCap; };
+struct LzfSizes { size_t key, keyB, sa, prev, len0, skipped, hist, tk, m, ml, spec, patch, seg, rng, total; int segLen, maxSeg, evStride, patchCap; };
 static LzfSizes lzf_sizes(i32 maxLen) {
   LzfSizes z;
   const size_t n = (size_t)maxLen + 64;
   const size_t nT = (n + LZF_WT - 1) / LZF_WT;
-  z.key = lzf_al(8 * n); z.sa = lzf_al(4 * n); z.prev = lzf_al(4 * n); z.len0 = lzf_al(n); z.skipped = lzf_al(n / 8 + 64);
+  z.key = lzf_al(8 * n); z.keyB = lzf_al(std::max(8 * n, (size_t)4 << 19));   // kb doubles as the real hash table of the sparse walk (2^19 entries for LZX)
+  z.sa = lzf_al(4 * n); z.prev = lzf_al(4 * n); z.len0 = lzf_al(n); z.skipped = lzf_al(n / 8 + 64);
   z.hist = lzf_al(4 * 256 * nT);
   z.tk = lzf_al(std::max<size_t>(n / 5, 256) + 64); z.m = lzf_al(n + 64); z.ml = lzf_al(n / 2 + 64);
   static const int segMin = getenv("KZG_LZ_SEG") ? std::max(8192, atoi(getenv("KZG_LZ_SEG")) / 4096 * 4096) : 8192;   // developer knob
@@ -1726,7 +1727,7 @@ static LzfSizes lzf_sizes(i32 maxLen) {
   z.patchCap = (int)(n / 4 + 64);
   z.spec = lzf_al((size_t)z.maxSeg * z.evStride * sizeof(uint4)); z.patch = lzf_al((size_t)z.patchCap * sizeof(uint4));
   z.seg = lzf_al((size_t)z.maxSeg * sizeof(LzfSeg)); z.rng = lzf_al((size_t)(2 * z.maxSeg + 4) * sizeof(LzfRange));
-  z.total = 2 * z.key + 2 * z.sa + z.prev + z.len0 + 5 * z.skipped + 2 * z.hist + z.tk + z.m + z.ml + z.spec + z.patch + z.seg + z.rng + 1024;
+  z.total = z.key + z.keyB + 2 * z.sa + z.prev + z.len0 + 5 * z.skipped + 2 * z.hist + z.tk + z.m + z.ml + z.spec + z.patch + z.seg + z.rng + 1024;
   return z;
 }
 void kzg_lzf_scratch(i32 maxLen, size_t* perBlockBytes) { *perBlockBytes = std::max(*perBlockBytes, lzf_sizes(maxLen).total + sizeof(LzfBlock) + 256 + 1024); }
@@ -1811,7 +1812,7 @@ int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
     u8* o = base + (size_t)b * z.total;
     LzfBlock& L = hl[b];
     memset(&L, 0, sizeof(L));
-    L.ka = (u64*)o; o += z.key; L.kb = (u64*)o; o += z.key; L.hs = (u32*)o; o += z.sa; L.rank = (u32*)o; o += z.sa; L.prev = (u32*)o; o += z.prev;
+    L.ka = (u64*)o; o += z.key; L.kb = (u64*)o; o += z.keyB; L.hs = (u32*)o; o += z.sa; L.rank = (u32*)o; o += z.sa; L.prev = (u32*)o; o += z.prev;
     L.len0 = o; o += z.len0; L.skipped = (u32*)o; o += z.skipped; L.hist = (u32*)o; o += z.hist; L.offs = (u32*)o; o += z.hist;
     L.tk = o; o += z.tk; L.m = o; o += z.m; L.ml = o; o += z.ml;
     L.mCap = (i32)z.m - 16; L.mlCap = (i32)z.ml - 16;

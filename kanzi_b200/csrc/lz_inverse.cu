@@ -6,12 +6,9 @@
 //   1. token parse (one warp per block, 32 tokens per step): literal / match lengths, extension bytes,
 //      distance bytes, the repeat-offset state (a warp scan over composable "select" maps) and the
 //      output offset of every token (prefix sums).  The only serial part, O(tokens/32) steps.
-//   2. pointer fill (one thread per 4 output bytes): ptr[pos] = LIT | literal-stream offset for literal
-//      bytes, pos - dist for match bytes (the byte the reference would copy from).
-//   3. pointer jumping: ptr[pos] = ptr[ptr[pos]] until every byte points at a literal (up to 16 hops per
-//      round with path compression; chains only run backwards, so a handful of rounds suffice).
-//   4. gather: dst[pos] = src[ptr[pos]].
-// Passes 2-4 are HBM-bound streaming / gather passes over 4 bytes of scratch per output byte.
+//   2. copy resolution (see "pass 2" below): pointers built and resolved per 8 KiB tile in shared memory, literal-resolved
+//      bytes written at once; only bytes whose chain leaves the tile go through the global pointer array.
+// Pass 2 moves 4 bytes of pointer per output byte once, plus the open tiles' re-reads.
 #include "kzg_common.cuh"
 #include "kzg_transforms.cuh"
 #include <algorithm>
@@ -539,14 +536,31 @@ __global__ void lzi_tok_commit_kernel(KzgXfParams P, LziHdr* __restrict__ hdrs, 
   P.result[2 * b + 1] = H.outLenRaw;              // res[0] is set by the gather pass
 }
 
-// ---- pass 2: pointer fill -----------------------------------------------------------------------------------------------
-#define LZI_TILE 1024
-__global__ void __launch_bounds__(256) lzi_fill_kernel(const KzgBlock* __restrict__ blocks, const LziTok* __restrict__ toks, i64 tokStride,
-                                                     const LziHdr* __restrict__ hdrs, u32* __restrict__ ptrs, i64 ptrStride) {
-  __shared__ u32 sOut[LZI_TILE / 2 + 8];
-  __shared__ int sT0, sCnt;
-  const int b = blockIdx.y;
+// ---- pass 2: copy resolution ---------------------------------------------------------------------------------------------------
+// Every output byte is a literal (a byte of the literal area) or a copy of an earlier output byte.  ptr[pos] = LIT | literal
+// offset, or the output position it copies.  A match that overlaps itself (dist < length) points straight into the bytes
+// before it: pos' = mStart - dist + (pos - mStart) mod dist, so runs do not build chains of their own.
+//   lzi_resolve_kernel : one CTA per tile of 8192 output bytes.  Pointers are built in shared memory, pointers that stay
+//                        inside the tile are resolved there by pointer doubling (no DRAM traffic), literal-resolved bytes are
+//                        gathered and written at once; what is left points before the tile.  The tile's pointers go to
+//                        global memory (targets of later tiles' lookups), plus a per-tile count of open bytes.
+//   lzi_global_kernel  : open tiles only: up to four hops through the global pointer array per round, writing every byte
+//                        whose chain ends (later tiles' chains shorten through the updated pointers: doubling across rounds).
+//   lzi_finish_kernel  : whatever is still open walks its chain to the end.
+#define LZI_TILE 8192
+#define LZI_RT 256                      // threads per resolve CTA
+#define LZI_MAXTOK (LZI_TILE / 4 + 8)   // tokens overlapping a tile: every token but a block's last covers >= minMatch (>= 4) bytes
+#define LZI_OUT 0x40000000u             // shared-memory pointers only: points before the tile (global position in the low 30 bits)
+__global__ void __launch_bounds__(LZI_RT) lzi_resolve_kernel(KzgBlock* __restrict__ blocks, const LziTok* __restrict__ toks, i64 tokStride,
+                                                            const LziHdr* __restrict__ hdrs, u32* __restrict__ ptrs, i64 ptrStride,
+                                                            int* __restrict__ open, int tilesPerBlock, int* __restrict__ result) {
+  __shared__ u32 sPtr[LZI_TILE];
+  __shared__ u32 sOut[LZI_MAXTOK];
+  __shared__ int sT0;
+  const int b = blockIdx.y, tid = threadIdx.x;
   const LziHdr& H = hdrs[b];
+  if (blockIdx.x == 0 && tid == 0) result[2 * b] = (H.nTok > 0) ? H.ok : 0;
+  if (tid == 0) open[(i64)b * tilesPerBlock + blockIdx.x] = 0;
   if (H.nTok <= 0) return;
   const int outLen = H.outLen;
   const int tileBeg = blockIdx.x * LZI_TILE;
@@ -554,93 +568,127 @@ __global__ void __launch_bounds__(256) lzi_fill_kernel(const KzgBlock* __restric
   const int tileEnd = min(tileBeg + LZI_TILE, outLen);
   const LziTok* T = toks + (i64)b * tokStride;
   u32* ptr = ptrs + (i64)b * ptrStride;
-  if (threadIdx.x == 0) {
-    // last token with outPos <= tileBeg
+  const KzgBlock& B = blocks[b];
+  const u8* __restrict__ src = B.cur;
+  u8* __restrict__ dst = B.alt;
+  if (tid == 0) {                       // last token with outPos <= tileBeg
     int lo = 0, hi = H.nTok - 1;
     while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (T[mid].outPos <= (u32)tileBeg) lo = mid; else hi = mid - 1; }
     sT0 = lo;
   }
   __syncthreads();
   const int t0 = sT0;
-  // tokens overlapping the tile: t0 .. first token starting at or after tileEnd (exclusive); at most TILE/2 + 2 (every match is >= 2 bytes)
-  for (int i = threadIdx.x; i < LZI_TILE / 2 + 8; i += 256) {
+  for (int i = tid; i < LZI_MAXTOK; i += LZI_RT) {
     const int t = t0 + i;
     sOut[i] = (t < H.nTok) ? T[t].outPos : 0xFFFFFFFFu;
   }
   __syncthreads();
-  const int pos0 = tileBeg + threadIdx.x * 4;
-  if (pos0 >= tileEnd) return;
-  // token of pos0: last i with sOut[i] <= pos0
-  int lo = 0, hi = LZI_TILE / 2 + 7;
-  while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (sOut[mid] <= (u32)pos0) lo = mid; else hi = mid - 1; }
-  int ti = lo;
-  LziTok tk = T[t0 + ti];
-  u32 v[4];
-  #pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const u32 pos = (u32)pos0 + k;
-    if ((int)pos >= tileEnd) { v[k] = LZI_LIT; continue; }
-    while (pos >= tk.outPos + tk.litLen + tk.mLen) { ti++; tk = T[t0 + ti]; }
-    const u32 off = pos - tk.outPos;
-    v[k] = (off < tk.litLen) ? (LZI_LIT | (tk.litSrc + off)) : (pos - tk.dist);
+  // build: thread owns 4 consecutive positions per 1024-position slab
+  for (int slab = 0; slab < LZI_TILE; slab += 4 * LZI_RT) {
+    const int pos0 = tileBeg + slab + 4 * tid;
+    if (pos0 >= tileEnd) break;
+    int lo = 0, hi = LZI_MAXTOK - 1;    // token of pos0: last i with sOut[i] <= pos0
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (sOut[mid] <= (u32)pos0) lo = mid; else hi = mid - 1; }
+    int ti = lo;
+    LziTok tk = T[t0 + ti];
+    #pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const u32 pos = (u32)pos0 + k;
+      u32 v = LZI_LIT;
+      if ((int)pos < tileEnd) {
+        while (pos >= tk.outPos + tk.litLen + tk.mLen) { ti++; tk = T[t0 + ti]; }
+        const u32 off = pos - tk.outPos;
+        if (off < tk.litLen) v = LZI_LIT | (tk.litSrc + off);
+        else {
+          const u32 k2 = off - tk.litLen;                     // byte of the match
+          const u32 from = (k2 < tk.dist) ? pos - tk.dist : (pos - k2) - tk.dist + (k2 % tk.dist);
+          v = (from >= (u32)tileBeg) ? (from - (u32)tileBeg) : (LZI_OUT | from);
+        }
+      }
+      sPtr[slab + 4 * tid + k] = v;
+    }
   }
-  *reinterpret_cast<uint4*>(ptr + pos0) = make_uint4(v[0], v[1], v[2], v[3]);
+  __syncthreads();
+  // pointer doubling inside the tile (in place: a reader sees the old or the new pointer of its target, both lead to the same byte)
+  for (int round = 0; round < 16; round++) {
+    int local = 0;
+    for (int i = tid; i < LZI_TILE; i += LZI_RT) {
+      u32 v = sPtr[i];
+      if (!(v & (LZI_LIT | LZI_OUT))) {
+        v = sPtr[v];
+        if (!(v & (LZI_LIT | LZI_OUT))) { v = sPtr[v]; }
+        sPtr[i] = v;
+        if (!(v & (LZI_LIT | LZI_OUT))) local = 1;
+      }
+    }
+    if (!__syncthreads_or(local)) break;
+  }
+  // (a chain deeper than 2^32 hops cannot exist in 8192 positions: every local pointer is resolved now)
+  int nOpen = 0;
+  for (int slab = 0; slab < LZI_TILE; slab += 4 * LZI_RT) {
+    const int i0 = slab + 4 * tid;
+    const int pos0 = tileBeg + i0;
+    if (pos0 >= tileEnd) break;
+    u32 v[4]; u32 outw = 0; int nLit = 0;
+    #pragma unroll
+    for (int k = 0; k < 4; k++) {
+      u32 x = sPtr[i0 + k];
+      if (x & LZI_LIT) { if (pos0 + k < tileEnd) { outw |= (u32)src[x & ~LZI_LIT] << (8 * k); nLit++; } }
+      else { x &= ~LZI_OUT; nOpen++; }
+      v[k] = x;
+    }
+    *reinterpret_cast<uint4*>(ptr + pos0) = make_uint4(v[0], v[1], v[2], v[3]);
+    if (nLit == 4) *reinterpret_cast<u32*>(dst + pos0) = outw;
+    else {
+      #pragma unroll
+      for (int k = 0; k < 4; k++) if ((v[k] & LZI_LIT) && pos0 + k < tileEnd) dst[pos0 + k] = (u8)(outw >> (8 * k));
+    }
+  }
+  if (__syncthreads_or(nOpen)) { if (tid == 0) open[(i64)b * tilesPerBlock + blockIdx.x] = 1; }
 }
 
-// ---- pass 3: pointer jumping with path compression ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) lzi_jump_kernel(LziHdr* __restrict__ hdrs, u32* __restrict__ ptrs, i64 ptrStride, int round) {
-  const int b = blockIdx.y;
-  LziHdr& H = hdrs[b];
-  if (H.nTok <= 0) return;
-  if (round > 0 && H.done[round - 1] == 0) return;            // previous round left nothing unresolved
-  const int outLen = H.outLen;
-  const int pos0 = (blockIdx.x * 256 + threadIdx.x) * 4;
-  if (pos0 >= outLen) return;
-  u32* ptr = ptrs + (i64)b * ptrStride;
-  uint4 q = *reinterpret_cast<uint4*>(ptr + pos0);
-  u32 v[4] = {q.x, q.y, q.z, q.w};
-  bool changed = false, open = false;
-  u32 p[4] = {v[0], v[1], v[2], v[3]};
-  for (int hop = 0; hop < 16; hop++) {          // the four chains advance together: four independent loads in flight per step
-    const bool o0 = !(p[0] & LZI_LIT), o1 = !(p[1] & LZI_LIT), o2 = !(p[2] & LZI_LIT), o3 = !(p[3] & LZI_LIT);
-    if (!(o0 | o1 | o2 | o3)) break;
-    const u32 n0 = o0 ? ptr[p[0]] : p[0], n1 = o1 ? ptr[p[1]] : p[1], n2 = o2 ? ptr[p[2]] : p[2], n3 = o3 ? ptr[p[3]] : p[3];
-    p[0] = n0; p[1] = n1; p[2] = n2; p[3] = n3;
-  }
-  #pragma unroll
-  for (int k = 0; k < 4; k++) {
-    if (p[k] != v[k]) { v[k] = p[k]; changed = true; }
-    if (!(p[k] & LZI_LIT)) open = true;
-  }
-  if (changed) *reinterpret_cast<uint4*>(ptr + pos0) = make_uint4(v[0], v[1], v[2], v[3]);
-  if (open) H.done[round] = 1;                                // benign race: any writer stores 1
-}
-
-// ---- pass 4: gather ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) lzi_gather_kernel(KzgBlock* __restrict__ blocks, const LziHdr* __restrict__ hdrs, const u32* __restrict__ ptrs,
-                                                        i64 ptrStride, int* __restrict__ result) {
-  const int b = blockIdx.y;
+// open tiles only: hop through the global pointers
+__global__ void __launch_bounds__(LZI_RT) lzi_global_kernel(KzgBlock* __restrict__ blocks, const LziHdr* __restrict__ hdrs, u32* __restrict__ ptrs, i64 ptrStride,
+                                                           int* __restrict__ open, int tilesPerBlock, int finish) {
+  const int b = blockIdx.y, tid = threadIdx.x;
+  int* flag = open + (i64)b * tilesPerBlock + blockIdx.x;
+  if (*flag == 0) return;
   const LziHdr& H = hdrs[b];
-  if (H.nTok <= 0) return;
   const int outLen = H.outLen;
-  const int pos0 = (blockIdx.x * 256 + threadIdx.x) * 4;
-  if (blockIdx.x == 0 && threadIdx.x == 0) result[2 * b] = H.ok;
-  if (pos0 >= outLen) return;
+  const int tileBeg = blockIdx.x * LZI_TILE;
+  const int tileEnd = min(tileBeg + LZI_TILE, outLen);
+  u32* ptr = ptrs + (i64)b * ptrStride;
   const KzgBlock& B = blocks[b];
   const u8* __restrict__ src = B.cur;
   u8* __restrict__ dst = B.alt;
-  const u32* ptr = ptrs + (i64)b * ptrStride;
-  const uint4 q = *reinterpret_cast<const uint4*>(ptr + pos0);
-  u32 v[4] = {q.x, q.y, q.z, q.w};
-  u32 outw = 0;
-  #pragma unroll
-  for (int k = 0; k < 4; k++) {
-    u32 p = v[k];
-    while (!(p & LZI_LIT)) p = ptr[p];                        // leftovers of very deep chains
-    outw |= (u32)src[p & ~LZI_LIT] << (8 * k);
+  int still = 0;
+  for (int slab = 0; slab < LZI_TILE; slab += 4 * LZI_RT) {
+    const int pos0 = tileBeg + slab + 4 * tid;
+    if (pos0 >= tileEnd) break;
+    const uint4 q = *reinterpret_cast<const uint4*>(ptr + pos0);
+    u32 v[4] = {q.x, q.y, q.z, q.w};
+    if ((v[0] & v[1] & v[2] & v[3]) & LZI_LIT) continue;
+    u32 p[4] = {v[0], v[1], v[2], v[3]};
+    const int hops = finish ? (1 << 30) : 4;
+    for (int hop = 0; hop < hops; hop++) {          // the four chains advance together: four independent loads in flight per step
+      const bool o0 = !(p[0] & LZI_LIT), o1 = !(p[1] & LZI_LIT), o2 = !(p[2] & LZI_LIT), o3 = !(p[3] & LZI_LIT);
+      if (!(o0 | o1 | o2 | o3)) break;
+      const u32 n0 = o0 ? __ldcg(ptr + p[0]) : p[0], n1 = o1 ? __ldcg(ptr + p[1]) : p[1], n2 = o2 ? __ldcg(ptr + p[2]) : p[2], n3 = o3 ? __ldcg(ptr + p[3]) : p[3];
+      p[0] = n0; p[1] = n1; p[2] = n2; p[3] = n3;
+    }
+    bool changed = false;
+    #pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (p[k] != v[k]) {
+        changed = true;
+        if ((p[k] & LZI_LIT) && pos0 + k < tileEnd) dst[pos0 + k] = src[p[k] & ~LZI_LIT];
+      }
+      if (!(p[k] & LZI_LIT)) still = 1;
+    }
+    if (changed) *reinterpret_cast<uint4*>(ptr + pos0) = make_uint4(p[0], p[1], p[2], p[3]);
   }
-  if (pos0 + 4 <= outLen) *reinterpret_cast<u32*>(dst + pos0) = outw;
-  else for (int k = 0; pos0 + k < outLen; k++) dst[pos0 + k] = (u8)(outw >> (8 * k));
+  still = __syncthreads_or(still);
+  if (tid == 0 && !still) *flag = 0;
 }
 
 // scratch: per block tokens (24 B each, up to maxLen/4 + 1024) + 16 B of record lists per token + 64 B per tile of 1024 tokens
@@ -649,7 +697,7 @@ static i64 lzi_tok_stride(i32 maxLen) { return (((i64)maxLen / 4 + 1024) + 15) &
 static i64 lzi_tile_stride(i64 tokStride) { return (((tokStride + LZI_TT - 1) / LZI_TT + 8) + 3) & ~(i64)3; }
 void kzg_lzi_scratch(i32 maxLen, size_t* perBlockBytes, size_t* aux32) {
   const size_t toks = (size_t)lzi_tok_stride(maxLen);
-  *perBlockBytes = std::max(*perBlockBytes, toks * (sizeof(LziTok) + 16) + (size_t)lzi_tile_stride((i64)toks) * 64 + 256 + 512);
+  *perBlockBytes = std::max(*perBlockBytes, toks * (sizeof(LziTok) + 16) + (size_t)lzi_tile_stride((i64)toks) * 64 + 256 + 512 + 4 * ((size_t)maxLen / LZI_TILE + 2));
   *aux32 = std::max(*aux32, (size_t)maxLen + 64);
 }
 
@@ -657,7 +705,7 @@ int kzg_lz_inverse_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, const
   // flat scratch pool (nBlocks * scratchStride bytes): [dense headers, 256 B reserved per block][token arrays]; pointers in aux32
   const i64 tokStride = lzi_tok_stride(maxLen);
   const i64 tileStride = lzi_tile_stride(tokStride);
-  const size_t need = (size_t)nBlocks * (256 + (size_t)tokStride * (sizeof(LziTok) + 16) + (size_t)tileStride * 64);
+  const size_t need = (size_t)nBlocks * (256 + (size_t)tokStride * (sizeof(LziTok) + 16) + (size_t)tileStride * 64 + 4 * ((size_t)maxLen / LZI_TILE + 2));
   if (need > (size_t)nBlocks * (size_t)P.scratchStride) { kzg_set_error("lz inverse: scratch pool too small"); return -KZG_ERR_CREATE_CODEC; }
   static_assert(sizeof(LziHdr) <= 256, "LziHdr must fit its 256-byte slot");
   LziHdr* hdrs = (LziHdr*)P.scratch;
@@ -677,10 +725,11 @@ int kzg_lz_inverse_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, const
   lzi_tok_final_kernel<<<dim3((int)((tokStride + 255) / 256), nBlocks), 256, 0, s>>>(d_blocks, P, toks, tokStride, hdrs, extPool, tilePool, tileStride);
   lzi_tok_commit_kernel<<<(nBlocks + 63) / 64, 64, 0, s>>>(P, hdrs, nBlocks);
   const int tiles = (maxLen + LZI_TILE - 1) / LZI_TILE;
-  lzi_fill_kernel<<<dim3(tiles, nBlocks), 256, 0, s>>>(d_blocks, toks, tokStride, hdrs, ptrs, ptrStride);
-  for (int r = 0; r < 6; r++) lzi_jump_kernel<<<dim3(tiles, nBlocks), 256, 0, s>>>(hdrs, ptrs, ptrStride, r);
-  lzi_gather_kernel<<<dim3(tiles, nBlocks), 256, 0, s>>>(d_blocks, hdrs, ptrs, ptrStride, P.result);
+  int* open = (int*)(tilePool + (size_t)nBlocks * 16 * tileStride);
+  lzi_resolve_kernel<<<dim3(tiles, nBlocks), LZI_RT, 0, s>>>(d_blocks, toks, tokStride, hdrs, ptrs, ptrStride, open, tiles, P.result);
+  for (int r = 0; r < 5; r++) lzi_global_kernel<<<dim3(tiles, nBlocks), LZI_RT, 0, s>>>(d_blocks, hdrs, ptrs, ptrStride, open, tiles, 0);
+  lzi_global_kernel<<<dim3(tiles, nBlocks), LZI_RT, 0, s>>>(d_blocks, hdrs, ptrs, ptrStride, open, tiles, 1);
   CUDA_TRY(cudaGetLastError());
-  kzg_count_launch(16);
+  kzg_count_launch(15);
   return 0;
 }
