@@ -612,7 +612,7 @@ __global__ void __launch_bounds__(LZI_RT) lzi_resolve_kernel(KzgBlock* __restric
   // pointer doubling inside the tile (in place: a reader sees the old or the new pointer of its target, both lead to the same byte)
   for (int round = 0; round < 16; round++) {
     int local = 0;
-    for (int i = tid; i < LZI_TILE; i += LZI_RT) {
+    for (int i = tid; i < tileEnd - tileBeg; i += LZI_RT) {      // (entries beyond the block's last byte were never built)
       u32 v = sPtr[i];
       if (!(v & (LZI_LIT | LZI_OUT))) {
         v = sPtr[v];
