@@ -93,12 +93,26 @@ int kzg_bwt_inverse(const uint8_t* src, int32_t n, uint8_t* dst, const int32_t* 
 int64_t kzg_entropy_encode(int type, kzg_ctx* ctx, const uint8_t* src, int32_t n, uint8_t* out, int64_t outCap, int64_t* outBits);
 int32_t kzg_entropy_decode(int type, kzg_ctx* ctx, const uint8_t* in, int64_t inBits, int64_t* bitsUsed, uint8_t* dst, int32_t n);
 
+/* Coalescing of concurrent per-block calls.  Off by default: every call above runs alone on the
+ * calling thread's stream.  kzg_set_coalescing(maxBatch > 1, windowMicros) starts one service thread (device = the calling
+ * thread's): calls of the same kind/type arriving within windowMicros of each other, up to maxBatch of them, run as ONE
+ * batch of blocks — what Kanzi's <= 64 EncodingTask / DecodingTask pool threads produce, one block each
+ * (K/io/CompressedOutputStream.java:537-573).  Results are identical to uncoalesced calls.  maxBatch <= 1 stops the service.
+ * kzg_coalescing_stats: requests served by the service so far (*batches = launches they were folded into). */
+int kzg_set_coalescing(int maxBatch, int windowMicros);
+int64_t kzg_coalescing_stats(int64_t* batches);
+
 /* ---- batched whole-chain entries (SURVEY.md §8b "batched forms", §8f rank 1-2) ------------------------
  * What CompressedOutputStream / CompressedInputStream + EncodingTask / DecodingTask produce and
  * consume (COS:236-313,733-1054; CIS:359-515,1025-1378) for `nTransforms` chained ids + one entropy id,
  * with every block of the input in flight at once on the calling thread's device.  Host buffers.
  * kzg_compress: returns the .knz byte length (<0 on error).  kzg_decompress: returns decoded bytes.
- * checksum kinds are not supported (-KZG_ERR_INVALID_PARAM).  flags as kzg_ctx.flags. */
+ * checksum kinds are not supported (-KZG_ERR_INVALID_PARAM).  flags as kzg_ctx.flags.
+ * Capacities: kzg_compress needs outCap >= kzg_compress_bound(n, blockSize) to be sure of success (a smaller buffer
+ * fails with -KZG_ERR_WRITE_FILE only if the stream really does not fit).  kzg_decompress needs outCap >= the decoded size
+ * and never writes beyond `out + outCap`: every block but the last decodes to blockSize bytes, the last to what is left
+ * (-KZG_ERR_WRITE_FILE when the stream holds more than outCap bytes).  Host libraries should export
+ * CUDA_DEVICE_MAX_CONNECTIONS=32 before the CUDA context exists (the LZ stages run block groups on up to 32 streams). */
 int64_t kzg_compress(const uint8_t* in, int64_t n, const int32_t* transforms, int32_t nTransforms, int32_t entropy,
                      int32_t blockSize, int32_t flags, uint8_t* out, int64_t outCap);
 int64_t kzg_decompress(const uint8_t* in, int64_t nBytes, int32_t flags, uint8_t* out, int64_t outCap);
@@ -106,12 +120,27 @@ int64_t kzg_decompress(const uint8_t* in, int64_t nBytes, int32_t flags, uint8_t
 int64_t kzg_compress_bound(int64_t n, int32_t blockSize);
 
 /* Same, device-resident (bench `value`: inputs already in HBM; pointers are device pointers, 16-byte
- * aligned).  The codec runs on the calling thread's stream; these calls synchronise before returning.
+ * aligned; d_in of kzg_decompress_dev must be readable up to the next multiple of 8 bytes beyond nBytes, which every
+ * cudaMalloc'ed buffer is).  The codec runs on the calling thread's stream; these calls synchronise before returning.
  * timing (optional, may be NULL): ms spent in [0] transforms, [1] entropy, [2] container assembly. */
 int64_t kzg_compress_dev(const uint8_t* d_in, int64_t n, const int32_t* transforms, int32_t nTransforms, int32_t entropy,
                          int32_t blockSize, int32_t flags, uint8_t* d_out, int64_t outCap, float* timing3);
 int64_t kzg_decompress_dev(const uint8_t* d_in, int64_t nBytes, const uint8_t* h_in, int32_t flags, uint8_t* d_out, int64_t outCap,
                            float* timing3);
+
+/* ---- block sharding across GPUs (CompressedOutputStream.java:1024-1035) ---------------------------------
+ * Blocks are independent: GPU r of G encodes blocks r, r+G, ... of a joint stream with kzg_compress[_dev] and reports each
+ * record's bit length; the lengths are the one thing ranks exchange (NCCL all-gather), after which every rank knows the bit
+ * offset of every record in the joint stream.
+ * kzg_last_block_bits: record bit lengths (5 + lw + written) of the calling thread's last compress call; returns the count.
+ * kzg_stream_index: host-side walk of a .knz: bit offset / bit length of every block record, *headerBits = first record. */
+int32_t kzg_last_block_bits(int64_t* recBits, int32_t cap);
+int32_t kzg_stream_index(const uint8_t* in, int64_t nBytes, int64_t* recBit, int64_t* recBits, int32_t cap, int64_t* headerBits);
+
+/* per-kernel CUDA-event timing of the calling thread's calls (measurement aid: bench.py's per-kernel roofline).
+ * kzg_set_profiling(1) starts a collection, kzg_profile_json() ends it: {"kernel name": [launches, total ms], ...}. */
+void kzg_set_profiling(int on);
+const char* kzg_profile_json(void);
 
 /* the CUDA stream of the calling thread as a cudaStream_t cast to void* (for event timing by callers) */
 void* kzg_stream(void);

@@ -7,7 +7,7 @@ import os as _os
 _os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 from .binding import (lib, KzgError, T, E, DT, FLAG_BWT_ASREF, device_count, set_device, last_error, launch_count,
                       transform_forward, transform_inverse, transform_max_encoded_len, bwt_forward, bwt_inverse,
-                      entropy_encode, entropy_decode, compress, decompress, compress_bound)
+                      entropy_encode, entropy_decode, compress, decompress, compress_bound, last_block_bits, stream_index)
 from .interfaces import SliceByteArray, ByteTransform, EntropyEncoder, EntropyDecoder, OutputBitStream, InputBitStream, \
     TransformFactory, EntropyCodecFactory
 

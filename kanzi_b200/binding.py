@@ -70,6 +70,10 @@ def lib():
                                        C.POINTER(C.c_float)]
         L.kzg_decompress_dev.restype = C.c_int64
         L.kzg_decompress_dev.argtypes = [C.c_void_p, C.c_int64, u8p, C.c_int32, C.c_void_p, C.c_int64, C.POINTER(C.c_float)]
+        L.kzg_last_block_bits.restype = C.c_int32
+        L.kzg_last_block_bits.argtypes = [i64p, C.c_int32]
+        L.kzg_stream_index.restype = C.c_int32
+        L.kzg_stream_index.argtypes = [u8p, C.c_int64, i64p, i64p, C.c_int32, i64p]
         _LIB = L
     return _LIB
 
@@ -211,3 +215,24 @@ def decompress(stream, max_out, flags=FLAG_BWT_ASREF):
     if r < 0:
         raise KzgError(r, "kzg_decompress")
     return out[:r].tobytes()
+
+
+def last_block_bits():
+    """Record bit lengths (5 + lw + written) of the blocks of the calling thread's last compress call (block sharding)."""
+    n = lib().kzg_last_block_bits(None, 0)
+    out = np.zeros(max(n, 1), dtype=np.int64)
+    lib().kzg_last_block_bits(out.ctypes.data_as(i64p), n)
+    return out[:n]
+
+
+def stream_index(stream):
+    """Host-side walk of a .knz: (header bits, record bit offsets, record bit lengths)."""
+    a, p = _u8(stream)
+    hb = C.c_int64(0)
+    n = lib().kzg_stream_index(p, len(a), None, None, 0, C.byref(hb))
+    if n < 0:
+        raise KzgError(n, "kzg_stream_index")
+    off = np.zeros(max(n, 1), dtype=np.int64)
+    bits = np.zeros(max(n, 1), dtype=np.int64)
+    lib().kzg_stream_index(p, len(a), off.ctypes.data_as(i64p), bits.ctypes.data_as(i64p), n, C.byref(hb))
+    return hb.value, off[:n], bits[:n]

@@ -50,5 +50,17 @@ def build(force=False, verbose=False):
     return LIB
 
 
+NATIVE_SRC = os.path.join(HERE, "..", "tests", "native", "kzg_blocks_mt.c")
+NATIVE_BIN = os.path.join(HERE, "..", "tests", "native", "kzg_blocks_mt")
+
+
+def build_native():
+    """The pthread driver of the per-block C ABI (tests/native/kzg_blocks_mt.c): what Kanzi's Java pool threads do, in C."""
+    if os.path.exists(NATIVE_BIN) and os.path.getmtime(NATIVE_BIN) > max(os.path.getmtime(NATIVE_SRC), os.path.getmtime(LIB)):
+        return NATIVE_BIN
+    subprocess.check_call(["gcc", "-O2", "-std=c11", "-Wall", "-pthread", NATIVE_SRC, "-L" + HERE, "-lkanzi_b200", "-Wl,-rpath,$ORIGIN/../../kanzi_b200", "-o", NATIVE_BIN])
+    return NATIVE_BIN
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

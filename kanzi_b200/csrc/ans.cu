@@ -439,9 +439,10 @@ __device__ int ans_decode_ctx_header(BitReaderD& br, int lr, int llr, u16* freq,
 //   * headers are parsed by the whole warp out of a shared-memory copy (alphabet bitmap: one mask byte per lane; the
 //     frequency groups: one group per lane once the 32-step chain of group offsets is known), cumulative frequencies by a
 //     warp scan, the slot -> symbol table filled slot-parallel (every lane owns 1/32 of the slots);
-//   * the coded bytes never touch shared memory: every group keeps the next 128 bits of its byte stream in registers
-//     (two 64-bit words, pre-shifted to the stream's bit offset) plus three raw words in flight, 8-byte aligned loads
-//     issued two refills ahead; the whole payload is pulled into L2 while the headers are parsed;
+//   * the coded bytes stream through a 256-byte shared-memory ring per chunk, filled by cp.async (LDGSTS) 64 bytes at a
+//     time on a fixed schedule (every 8 steps, the most a chunk can consume), so no lane ever waits on a global load and
+//     the eight chunks of a warp never diverge; a lane that renormalises reads its 16 bits straight from the ring;
+//     the whole payload is pulled into L2 while the headers are parsed;
 //   * output: the four symbols of a step are packed with two shuffles, every lane stores one 32-bit word per four
 //     steps (16 contiguous bytes per group).
 // ANSRangeDecoder.decodeChunkV2 (:357-440): symbol i+j is decoded with state st(3-j); states below TOP read 16 bits
@@ -449,20 +450,17 @@ __device__ int ans_decode_ctx_header(BitReaderD& br, int lr, int llr, u16* freq,
 // ================================================================================================================
 #define A0D_CHUNKS 8
 #define A0D_HDR_WORDS 144
+#define A0D_RING 256
 struct A0DecSmem {
   u8 f2s[A0D_CHUNKS][4096];
   u32 sym[A0D_CHUNKS][256];      // freq | cumFreq << 16
   u32 hdr[A0D_HDR_WORDS + 2];    // header bytes of the chunk being parsed, as big-endian words
   u16 freq[256];
   u8 alpha[256];
+  uint4 ring[A0D_CHUNKS][A0D_RING / 16];   // per chunk: a 256-byte window of its coded bytes, filled by cp.async
 };
 __device__ __forceinline__ u64 kzg_shl64(u64 x, u32 n) { u64 r; asm("shl.b64 %0, %1, %2;" : "=l"(r) : "l"(x), "r"(n)); return r; }   // n >= 64 -> 0
 __device__ __forceinline__ u64 kzg_shr64(u64 x, u32 n) { u64 r; asm("shr.u64 %0, %1, %2;" : "=l"(r) : "l"(x), "r"(n)); return r; }
-__device__ __forceinline__ u64 a0d_ld_be64(const u8* p, const u8* limit) {        // p 8-byte aligned; words at or beyond limit read as zero
-  if (p >= limit) return 0ull;
-  const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
-  return ((u64)__byte_perm(v.x, 0, 0x0123) << 32) | (u64)__byte_perm(v.y, 0, 0x0123);
-}
 __device__ __forceinline__ u32 a0d_bits(const u32* w, u32 pos, int n) {           // n in 1..32, MSB first
   const u32 i = pos >> 5;
   return __funnelshift_l(w[i + 1], w[i], pos & 31) >> (32 - n);
@@ -693,21 +691,22 @@ __global__ void __launch_bounds__(32) ans0_decode_kernel(KzgBlock* __restrict__ 
   if (!coding) st = 0u;
   const u32 mask = (1u << lr) - 1;
   const u32 lowerMask = (1u << j) - 1;
-  // the group's byte stream: q0:q1 = its next 128 bits (bitpos < 64 of them already consumed)
-  const u8* w0 = reinterpret_cast<const u8*>(reinterpret_cast<uintptr_t>(payByte) & ~(uintptr_t)7);
-  const u32 off = (u32)((payByte - w0) * 8) + (u32)((u64)info.payBit & 7);
-  u64 q0 = 0, q1 = 0, rawPrev = 0, rawN1 = 0, rawN2 = 0;
-  const u8* wp = w0;
-  if (coding) {
-    const u64 r0 = a0d_ld_be64(w0, limit), r1 = a0d_ld_be64(w0 + 8, limit), r2 = a0d_ld_be64(w0 + 16, limit);
-    rawN1 = a0d_ld_be64(w0 + 24, limit); rawN2 = a0d_ld_be64(w0 + 32, limit);
-    q0 = kzg_shl64(r0, off) | kzg_shr64(r1, 64 - off);
-    q1 = kzg_shl64(r1, off) | kzg_shr64(r2, 64 - off);
-    rawPrev = r2;
-    wp = w0 + 40;
-  }
-  u32 bitpos = 0;
-  int consumed = 0;                          // bytes
+  // the chunk's coded bytes: ring byte x holds stream byte base16 + x (mod 256); lane j fetches the j-th 16 bytes of a batch
+  const u8* base16 = reinterpret_cast<const u8*>(reinterpret_cast<uintptr_t>(payByte) & ~(uintptr_t)15);
+  u32 cbits = (u32)((payByte - base16) * 8) + (u32)((u64)info.payBit & 7);      // bit position of the cursor, relative to base16
+  const u32 cbits0 = cbits;
+  u32 fetched = 0;                                                               // bytes requested so far (multiple of 64)
+  const u32 ringAddr = (u32)__cvta_generic_to_shared(&S.ring[g][0]);
+  const u32* ring32 = reinterpret_cast<const u32*>(&S.ring[g][0]);
+  auto fetch = [&]() {                         // 64 more bytes into the ring (reads beyond the block's payload are skipped)
+    const u8* srcp = base16 + fetched + 16 * j;
+    if (coding && srcp < limit) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ringAddr + ((fetched + 16 * j) & (A0D_RING - 1))), "l"(srcp) : "memory");
+    fetched += 64;
+  };
+  fetch(); fetch(); fetch();
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
   const u8* f2s = S.f2s[g];
   const u32* symt = S.sym[g];
   u32* out32 = reinterpret_cast<u32*>(out + (aligned ? start : 0));
@@ -727,29 +726,31 @@ __global__ void __launch_bounds__(32) ans0_decode_kernel(KzgBlock* __restrict__ 
     u32 pk = symv << (8 * j);
     pk |= __shfl_xor_sync(0xFFFFFFFFu, pk, 1);
     pk |= __shfl_xor_sync(0xFFFFFFFFu, pk, 2);
+    if (need) {                                // 16 bits at bit p of the ring (big-endian bit order inside the byte stream)
+      const u32 p = cbits + 16u * __popc(m & lowerMask);
+      const u32 w = (p >> 5) & (A0D_RING / 4 - 1);
+      const u32 hi = __byte_perm(ring32[w], 0, 0x0123), lo = __byte_perm(ring32[(w + 1) & (A0D_RING / 4 - 1)], 0, 0x0123);
+      st = (st << 16) | (__funnelshift_l(lo, hi, p & 31u) >> 16);
+    }
+    cbits += 16u * __popc(m);
     if (on) {
-      if (need) {
-        const u32 p = bitpos + 16u * __popc(m & lowerMask);
-        const u64 src = (p & 64u) ? q1 : q0;
-        st = (st << 16) | ((u32)kzg_shr64(src, 48u - (p & 63u)) & 0xFFFFu);
-      }
-      const u32 cbits = 16u * __popc(m);
-      bitpos += cbits;
-      consumed += (int)(cbits >> 3);
-      if (bitpos >= 64u) {                   // the group moves on by one word; the load issued here is used two refills from now
-        bitpos -= 64u;
-        q0 = q1;
-        q1 = kzg_shl64(rawPrev, off) | kzg_shr64(rawN1, 64 - off);
-        rawPrev = rawN1; rawN1 = rawN2; rawN2 = a0d_ld_be64(wp, limit); wp += 8;
-      }
       if (aligned) {
         if ((s & 3) == j) keep = pk;
         if ((s & 3) == 3) out32[4 * (s >> 2) + j] = keep;
       } else out[start + 4 * s + j] = (u8)symv;
     }
+    if ((s & 7) == 7) {                        // every chunk tops its ring up on the same steps: at most 64 bytes go per 8 steps
+      // invariant: fetched - cursor >= 72 bytes at every top-up (64 to consume + 8 of read slack), and < 200 (the ring keeps the cursor's word)
+      if (fetched - (cbits >> 3) < 136u) fetch();
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 1;" ::: "memory");      // everything but the batch just issued has landed
+      __syncwarp();
+    }
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   if (coding) {
     if (aligned && j < (steps & 3)) out32[(steps & ~3) + j] = keep;
+    const int consumed = (int)((cbits - cbits0) >> 3);
     const int tail = end - end4;
     const int sz = info.sz;
     if (j == 0) {
@@ -1022,7 +1023,7 @@ int kzg_ans_encode_launch(cudaStream_t s, const KzgBlock* d_blocks, int nBlocks,
   if (order == 0) {
     CUDA_TRY(cudaFuncSetAttribute(ans0_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(A0EncSmem)));   // per device: set on every launch
     dim3 grid((P.maxChunks + A0_GROUPS - 1) / A0_GROUPS, nBlocks);
-    ans0_encode_kernel<<<grid, 128, sizeof(A0EncSmem), s>>>(d_blocks, P);
+    KZG_PROF("ans0_encode_kernel", s, (ans0_encode_kernel<<<grid, 128, sizeof(A0EncSmem), s>>>(d_blocks, P)));
   } else {
     dim3 grid(P.maxChunks, nBlocks);
     ans1_encode_kernel<<<grid, 32, 0, s>>>(d_blocks, P);
@@ -1034,13 +1035,14 @@ int kzg_ans_encode_launch(cudaStream_t s, const KzgBlock* d_blocks, int nBlocks,
 
 int kzg_ans_decode_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, const KzgEntParams& P, int order, bool withScan) {
   if (withScan) {
-    if (order == 0) ans0_scan_kernel<<<nBlocks, 128, 0, s>>>(d_blocks, nBlocks, P);
+    if (order == 0) KZG_PROF("ans0_scan_kernel", s, (ans0_scan_kernel<<<nBlocks, 128, 0, s>>>(d_blocks, nBlocks, P)));
     else ans_scan_kernel<<<(nBlocks + ANS_SCAN_WARPS - 1) / ANS_SCAN_WARPS, 32 * ANS_SCAN_WARPS, 0, s>>>(d_blocks, nBlocks, P, order);
     CUDA_TRY(cudaGetLastError());
   }
   if (order == 0) {
     dim3 grid((P.maxChunks + A0D_CHUNKS - 1) / A0D_CHUNKS, nBlocks);
-    ans0_decode_kernel<<<grid, 32, 0, s>>>(d_blocks, P);
+    CUDA_TRY(cudaFuncSetAttribute(ans0_decode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));   // five 42 KiB CTAs per SM
+    KZG_PROF("ans0_decode_kernel", s, (ans0_decode_kernel<<<grid, 32, 0, s>>>(d_blocks, P)));
   } else {
     dim3 grid(P.maxChunks, nBlocks);
     ans1_decode_kernel<<<grid, 32, 0, s>>>(d_blocks, P);

@@ -15,7 +15,13 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <vector>
+#include <string>
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 
 // ---- per-thread workspace --------------------------------------------------------------------------------
 #define KZG_DEC_MAXG 16            // block groups of the decode (streams of their own)
@@ -29,6 +35,7 @@ struct Workspace {
   i64 launches = 0;
   char err[512] = {0};
   cudaStream_t side[KZG_DEC_MAXG] = {}; cudaEvent_t sideEv[KZG_DEC_MAXG + 1] = {}; bool sideInit = false;
+  std::vector<i64> lastRecBits;    // record bit lengths (5 + lw + written) of the blocks of this thread's last kzg_compress* call
 };
 static thread_local Workspace W;
 
@@ -38,6 +45,23 @@ void kzg_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void kzg_count_launch(int n) { W.launches += n; }
+
+// ---- per-kernel event timing --------------------------------------------------------------------------------------------
+struct ProfRec { const char* name; cudaEvent_t e0, e1; };
+static thread_local bool gProfOn = false;
+static thread_local std::vector<ProfRec> gProf;
+static thread_local std::string gProfJson;
+void kzg_prof_begin(const char* name, cudaStream_t s) {
+  if (!gProfOn) return;
+  ProfRec r; r.name = name; r.e0 = nullptr; r.e1 = nullptr;
+  if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) { cudaGetLastError(); return; }
+  cudaEventRecord(r.e0, s);
+  gProf.push_back(r);
+}
+void kzg_prof_end(cudaStream_t s) {
+  if (!gProfOn || gProf.empty()) return;
+  cudaEventRecord(gProf.back().e1, s);
+}
 
 static int ws_init() {
   if (W.init) return 0;
@@ -316,6 +340,68 @@ int kzg_set_device(int device) {
 }
 const char* kzg_last_error(void) { return W.err; }
 int64_t kzg_launch_count(int reset) { const i64 v = W.launches; if (reset) W.launches = 0; return v; }
+// Block sharding: the bit length of every block record of the calling thread's last kzg_compress /
+// kzg_compress_dev call, in block order.  A rank that holds blocks b = r, r + G, ... of a joint stream all-gathers these and
+// every rank knows every block's bit offset in the joint stream (CompressedOutputStream.java:1024-1035 appends records
+// back to back, bit-granular).  Returns the block count.
+int32_t kzg_last_block_bits(int64_t* recBits, int32_t cap) {
+  const int n = (int)W.lastRecBits.size();
+  for (int i = 0; i < n && i < cap; i++) recBits[i] = W.lastRecBits[i];
+  return n;
+}
+// Walks a .knz stream on the host: bit offset and bit length (5 + lw + written) of every block record, *headerBits = where the
+// first record starts.  Returns the block count (the end-of-stream marker is not a block) or < 0.
+int32_t kzg_stream_index(const uint8_t* in, int64_t nBytes, int64_t* recBit, int64_t* recBits, int32_t cap, int64_t* headerBits) {
+  if (in == nullptr || nBytes < 20) return -KZG_ERR_INVALID_FILE;
+  auto rd = [&](u64 pos, int n) -> u64 { u64 v = 0; for (int i = 0; i < n; i++, pos++) v = (v << 1) | ((u64)(in[pos >> 3] >> (7 - (pos & 7))) & 1u); return v; };
+  const u64 nbits = (u64)nBytes * 8;
+  if ((u32)rd(0, 32) != 0x4B414E5Au) return -KZG_ERR_INVALID_FILE;
+  const int szMask = (int)rd(32 + 4 + 2 + 5 + 48 + 28, 2);
+  u64 pos = 32 + 4 + 2 + 5 + 48 + 28 + 2 + 16ull * szMask + 15 + 24;
+  if (headerBits) *headerBits = (i64)pos;
+  int nb = 0;
+  for (;;) {
+    if (pos + 8 > nbits) return -KZG_ERR_READ_FILE;
+    const int lw = (int)rd(pos, 5) + 3;
+    if (pos + 5 + lw > nbits) return -KZG_ERR_READ_FILE;
+    const u64 written = rd(pos + 5, lw);
+    if (written == 0) break;
+    if (pos + 5 + lw + written > nbits) return -KZG_ERR_READ_FILE;
+    if (nb < cap) { if (recBit) recBit[nb] = (i64)pos; if (recBits) recBits[nb] = (i64)(5 + lw + written); }
+    nb++;
+    pos += 5 + lw + written;
+  }
+  return nb;
+}
+// Per-kernel CUDA-event timing of the calling thread's next calls (bench.py: roofline of the top kernel).  on != 0 starts a
+// fresh collection; kzg_profile_json() synchronises the device and returns {"kernel": [launches, total ms], ...} for the
+// launch sites wrapped in KZG_PROF (the hot kernels of every stage), then clears the collection.
+void kzg_set_profiling(int on) {
+  for (auto& r : gProf) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  gProf.clear();
+  gProfOn = on != 0;
+}
+const char* kzg_profile_json(void) {
+  cudaDeviceSynchronize();
+  std::vector<std::pair<std::string, std::pair<int, double>>> agg;
+  for (auto& r : gProf) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) { cudaGetLastError(); continue; }
+    bool found = false;
+    for (auto& a : agg) if (a.first == r.name) { a.second.first++; a.second.second += ms; found = true; break; }
+    if (!found) agg.push_back({r.name, {1, (double)ms}});
+  }
+  gProfJson = "{";
+  for (size_t i = 0; i < agg.size(); i++) {
+    char buf[160];
+    snprintf(buf, sizeof(buf), "%s\"%s\": [%d, %.6f]", i ? ", " : "", agg[i].first.c_str(), agg[i].second.first, agg[i].second.second);
+    gProfJson += buf;
+  }
+  gProfJson += "}";
+  for (auto& r : gProf) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  gProf.clear();
+  return gProfJson.c_str();
+}
 void* kzg_stream(void) { if (ws_init() < 0) return nullptr; return (void*)W.stream; }
 int32_t kzg_transform_max_encoded_len(int type, int32_t n) { return xf_known(type) ? xf_max_len(type, n) : -KZG_ERR_INVALID_CODEC; }
 // Worst case of any supported chain: a block whose entropy stage does not pay is stored as a "transformed copy"
@@ -326,68 +412,286 @@ int64_t kzg_compress_bound(int64_t n, int32_t blockSize) {
   return n + n / 64 + nb * (2 + 33 + 1024 + 16) + 64;
 }
 
-// ---- one ByteTransform call -------------------------------------------------------------------------------------
-static int transform_call(int type, bool forward, kzg_ctx* ctx, const uint8_t* src, int32_t srcLen, uint8_t* dst, int32_t dstLen,
-                          int32_t dstCap, int32_t* srcUsed, int32_t* dstUsed) {
-  *srcUsed = 0; *dstUsed = 0;
-  if (!xf_known(type)) return -KZG_ERR_INVALID_CODEC;
-  if (srcLen == 0) return 1;                                   // every codec: `if (input.length == 0) return true`
-  if (srcLen < 0 || dstLen < 0 || dstCap < 0 || dstLen > dstCap || src == nullptr || dst == nullptr) return 0;
-  int r = ws_init(); if (r < 0) return r;
-  // host-evaluated slice preconditions (the parts of each codec's guard block that depend on lengths only)
-  const int pre = kzg_stage_precheck(type, forward, ctx, srcLen, dstLen, dstCap);
-  if (pre <= 0) return pre;
+// ---- per-block calls: ByteTransform.forward / inverse, EntropyEncoder.encode, EntropyDecoder.decode -----------------------
+// One request = one call of the Java interface.  Requests of the same kind run as ONE batch of blocks through the batched
+// kernels (the kernels take block arrays anyway); a direct call is a batch of one.  With coalescing on
+// (kzg_set_coalescing), concurrent callers — Kanzi's EncodingTask / DecodingTask pool threads, one block each,
+// K/io/CompressedOutputStream.java:537-573 — are gathered by a service thread and launched together, so the path the
+// Java host really drives is not one launch train per block.
+enum { KZG_REQ_XF_FWD = 0, KZG_REQ_XF_INV = 1, KZG_REQ_ENT_ENC = 2, KZG_REQ_ENT_DEC = 3 };
+struct KzgReq {
+  int kind, type;
+  kzg_ctx* ctx; int flags;
+  const uint8_t* src; int32_t srcLen;        // transform input / entropy encoder input / decoder bit string
+  uint8_t* dst; int32_t dstLen, dstCap;      // transform output slice; entropy: dstCap = encoder out capacity (bytes) or n to decode
+  int64_t inBits;                            // decoder: bits available
+  int32_t srcUsed = 0, dstUsed = 0; int64_t bits = 0;
+  int64_t ret = 0;
+  bool done = false;
+};
+
+static int transform_batch(std::vector<KzgReq*>& rq) {
+  const int n = (int)rq.size();
+  const int type = rq[0]->type; const bool forward = rq[0]->kind == KZG_REQ_XF_FWD;
+  int r = ws_init(); if (r < 0) { for (auto q : rq) q->ret = r; return 0; }
+  std::vector<int> live;                                   // requests that reach the device
+  i32 maxLen = 0;
+  for (int i = 0; i < n; i++) {
+    KzgReq& Q = *rq[i];
+    Q.srcUsed = 0; Q.dstUsed = 0;
+    if (!xf_known(type)) { Q.ret = -KZG_ERR_INVALID_CODEC; continue; }
+    if (Q.srcLen == 0) { Q.ret = 1; continue; }               // every codec: `if (input.length == 0) return true`
+    if (Q.srcLen < 0 || Q.dstLen < 0 || Q.dstCap < 0 || Q.dstLen > Q.dstCap || Q.src == nullptr || Q.dst == nullptr) { Q.ret = 0; continue; }
+    // host-evaluated slice preconditions (the parts of each codec's guard block that depend on lengths only)
+    const int pre = kzg_stage_precheck(type, forward, Q.ctx, Q.srcLen, Q.dstLen, Q.dstCap);
+    if (pre <= 0) { Q.ret = pre; continue; }
+    live.push_back(i);
+    maxLen = std::max(maxLen, std::max(Q.srcLen, Q.dstCap));
+  }
+  if (live.empty()) return 0;
+  auto failAll = [&](int code) { for (int i : live) rq[i]->ret = code; return 0; };
+  const size_t nl = live.size();
   const int fn[1] = {type};
-  const i32 maxLen = std::max(srcLen, dstCap);
   XfScratch xs = xf_scratch_size(fn, 1, maxLen, forward);
   const size_t cap = rnd((size_t)maxLen + 64);
-  size_t need = 2 * cap + xs.perBlock + (xs.hashInts + xs.aux32) * 4 + 8192;
-  r = ws_reserve(need, sizeof(KzgBlock) + 4096); if (r < 0) return r;
-  Batch bt; bt.nBlocks = 1; bt.maxLen = maxLen;
-  bt.hBlocks = halloc<KzgBlock>(1); NN(bt.hBlocks);
-  bt.dBlocks = dalloc<KzgBlock>(1); NN(bt.dBlocks);
-  bt.dResult = dalloc<int>(2); NN(bt.dResult);
-  bt.dEnabled = dalloc<u8>(16); NN(bt.dEnabled);
-  bt.dDstLimit = dalloc<int>(4); NN(bt.dDstLimit);
-  u8* dA = dalloc<u8>(cap); NN(dA);
-  u8* dB = dalloc<u8>(cap); NN(dB);
-  u8* dScratch = dalloc<u8>(xs.perBlock + 16); NN(dScratch);
-  i32* dHash = dalloc<i32>(xs.hashInts + 4); NN(dHash);
-  i32* dAux = dalloc<i32>(xs.aux32 + 4); NN(dAux);
-  KzgBlock& B = bt.hBlocks[0];
-  memset(&B, 0, sizeof(B));
-  B.cur = dA; B.alt = dB; B.curLen = srcLen; B.cap = forward ? dstLen : dstCap; B.origLen = srcLen; B.skipFlags = 0xFF;
-  B.dataType = ctx ? ctx->dataType : 0; B.aux0 = nullptr; B.aux1 = dA; B.stagesLeft = 2;
-  u8 en = 1; int lim = forward ? dstLen : dstCap;
-  CUDA_TRY(cudaMemsetAsync(dA + srcLen, 0, cap - srcLen, W.stream));
-  CUDA_TRY(cudaMemcpyAsync(dA, src, srcLen, cudaMemcpyHostToDevice, W.stream));
-  CUDA_TRY(cudaMemcpyAsync(bt.dEnabled, &en, 1, cudaMemcpyHostToDevice, W.stream));
-  CUDA_TRY(cudaMemcpyAsync(bt.dDstLimit, &lim, sizeof(int), cudaMemcpyHostToDevice, W.stream));
-  r = batch_upload(bt); if (r < 0) return r;
-  const int flags = ctx ? ctx->flags : 0;
-  // (commit's inverse branch flags a failed inverse as a block error; here a false result is reported as 0)
-  r = run_transform_stage(bt, type, 0, forward, xs, dScratch, dHash, dAux, flags & ~KZG_FLAG_BWT_ASREF); if (r < 0) return r;   // the slice guards were evaluated by kzg_stage_precheck
-  int hres[2] = {0, 0};
-  CUDA_TRY(cudaMemcpyAsync(hres, bt.dResult, sizeof(hres), cudaMemcpyDeviceToHost, W.stream));
-  r = batch_download(bt); if (r < 0) return r;
-  if (ctx) ctx->dataType = B.dataType;
-  if (B.status != 0 && !(B.status == -KZG_ERR_PROCESS_BLOCK && !forward && hres[0] == 0)) return B.status;
-  if (hres[0] == 1) {
-    if (hres[1] > dstCap) { kzg_set_error("transform output %d exceeds dst capacity %d", hres[1], dstCap); return -KZG_ERR_PROCESS_BLOCK; }
-    CUDA_TRY(cudaMemcpy(dst, B.cur, hres[1], cudaMemcpyDeviceToHost));
-    *srcUsed = srcLen; *dstUsed = hres[1];
-    return 1;
+  const size_t need = nl * (2 * cap + xs.perBlock + (xs.hashInts + xs.aux32) * 4 + sizeof(KzgBlock) + 64) + 65536;
+  r = ws_reserve(need, nl * (sizeof(KzgBlock) + 32) + 4096); if (r < 0) return failAll(r);
+  Batch bt; bt.nBlocks = (int)nl; bt.maxLen = maxLen;
+  bt.hBlocks = halloc<KzgBlock>(nl); bt.hEnabled = halloc<u8>(nl); bt.hDstLimit = halloc<int>(nl);
+  bt.dBlocks = dalloc<KzgBlock>(nl); bt.dResult = dalloc<int>(2 * nl); bt.dEnabled = dalloc<u8>(nl); bt.dDstLimit = dalloc<int>(nl);
+  u8* dA = dalloc<u8>(nl * cap); u8* dB = dalloc<u8>(nl * cap);
+  u8* dScratch = dalloc<u8>(nl * xs.perBlock + 16); i32* dHash = dalloc<i32>(nl * xs.hashInts + 4); i32* dAux = dalloc<i32>(nl * xs.aux32 + 4);
+  if (!bt.hBlocks || !bt.hEnabled || !bt.hDstLimit || !bt.dBlocks || !bt.dResult || !bt.dEnabled || !bt.dDstLimit || !dA || !dB || !dScratch || !dHash || !dAux)
+    return failAll(-KZG_ERR_CREATE_CODEC);
+  auto cu = [&](cudaError_t e) { if (e != cudaSuccess) { kzg_set_error("transform batch: %s", cudaGetErrorString(e)); cudaGetLastError(); return false; } return true; };
+  for (size_t k = 0; k < nl; k++) {
+    KzgReq& Q = *rq[live[k]];
+    KzgBlock& B = bt.hBlocks[k];
+    memset(&B, 0, sizeof(B));
+    B.cur = dA + k * cap; B.alt = dB + k * cap; B.curLen = Q.srcLen; B.cap = forward ? Q.dstLen : Q.dstCap; B.origLen = Q.srcLen; B.skipFlags = 0xFF;
+    B.dataType = Q.ctx ? Q.ctx->dataType : 0; B.aux0 = nullptr; B.aux1 = B.cur; B.stagesLeft = 2;
+    bt.hEnabled[k] = 1; bt.hDstLimit[k] = forward ? Q.dstLen : Q.dstCap;
+    if (!cu(cudaMemsetAsync(B.cur + Q.srcLen, 0, cap - Q.srcLen, W.stream)) || !cu(cudaMemcpyAsync(B.cur, Q.src, Q.srcLen, cudaMemcpyHostToDevice, W.stream)))
+      return failAll(-KZG_ERR_PROCESS_BLOCK);
   }
+  if (!cu(cudaMemcpyAsync(bt.dEnabled, bt.hEnabled, nl, cudaMemcpyHostToDevice, W.stream)) ||
+      !cu(cudaMemcpyAsync(bt.dDstLimit, bt.hDstLimit, nl * sizeof(int), cudaMemcpyHostToDevice, W.stream))) return failAll(-KZG_ERR_PROCESS_BLOCK);
+  r = batch_upload(bt); if (r < 0) return failAll(r);
+  // (commit's inverse branch flags a failed inverse as a block error; here a false result is reported as 0)
+  r = run_transform_stage(bt, type, 0, forward, xs, dScratch, dHash, dAux, rq[live[0]]->flags & ~KZG_FLAG_BWT_ASREF);   // the slice guards were evaluated by kzg_stage_precheck
+  if (r < 0) return failAll(r);
+  int* hres = halloc<int>(2 * nl); if (!hres) return failAll(-KZG_ERR_CREATE_CODEC);
+  if (!cu(cudaMemcpyAsync(hres, bt.dResult, sizeof(int) * 2 * nl, cudaMemcpyDeviceToHost, W.stream))) return failAll(-KZG_ERR_PROCESS_BLOCK);
+  r = batch_download(bt); if (r < 0) return failAll(r);
+  for (size_t k = 0; k < nl; k++) {
+    KzgReq& Q = *rq[live[k]];
+    const KzgBlock& B = bt.hBlocks[k];
+    if (Q.ctx) Q.ctx->dataType = B.dataType;
+    if (B.status != 0 && !(B.status == -KZG_ERR_PROCESS_BLOCK && !forward && hres[2 * k] == 0)) { Q.ret = B.status; continue; }
+    if (hres[2 * k] == 1) {
+      if (hres[2 * k + 1] > Q.dstCap) { kzg_set_error("transform output %d exceeds dst capacity %d", hres[2 * k + 1], Q.dstCap); Q.ret = -KZG_ERR_PROCESS_BLOCK; continue; }
+      if (!cu(cudaMemcpyAsync(Q.dst, B.cur, hres[2 * k + 1], cudaMemcpyDeviceToHost, W.stream))) { Q.ret = -KZG_ERR_PROCESS_BLOCK; continue; }
+      Q.srcUsed = Q.srcLen; Q.dstUsed = hres[2 * k + 1]; Q.ret = 1;
+    } else Q.ret = 0;
+  }
+  if (!cu(cudaStreamSynchronize(W.stream))) return failAll(-KZG_ERR_PROCESS_BLOCK);
   return 0;
 }
 
+static int entropy_encode_batch(std::vector<KzgReq*>& rq) {
+  const int type = rq[0]->type;
+  int r = ws_init(); if (r < 0) { for (auto q : rq) q->ret = r; return 0; }
+  std::vector<int> live;
+  i32 maxN = 0;
+  for (int i = 0; i < (int)rq.size(); i++) {
+    KzgReq& Q = *rq[i];
+    Q.bits = 0;
+    if (!ent_known(type)) { Q.ret = -KZG_ERR_INVALID_CODEC; continue; }
+    if (Q.srcLen < 0 || Q.src == nullptr || Q.dst == nullptr) { Q.ret = -1; continue; }     // Java: encode returns -1 on bad arguments
+    if (Q.srcLen == 0) { Q.ret = 0; continue; }
+    live.push_back(i); maxN = std::max(maxN, Q.srcLen);
+  }
+  if (live.empty()) return 0;
+  auto failAll = [&](int code) { for (int i : live) rq[i]->ret = code; return 0; };
+  const size_t nl = live.size();
+  EntScratch es = ent_scratch_size(type, maxN, true);
+  const size_t cap = rnd((size_t)maxN + 64);
+  const size_t outBytes = rnd(2 * (size_t)maxN + (256 << 10));     // ANS1 on noise: 256 context headers + up to 2 bytes per symbol
+  const size_t need = nl * (cap + outBytes + (size_t)es.maxChunks * (es.hdrStride + es.payStride + es.tabStride * 4) +
+                            (size_t)es.segsPerBlock * sizeof(KzgSeg) + sizeof(KzgBlock) + 64) + 65536;
+  r = ws_reserve(need, nl * (sizeof(KzgBlock) + 16) + 4096); if (r < 0) return failAll(r);
+  Batch bt; bt.nBlocks = (int)nl; bt.maxLen = maxN;
+  bt.hBlocks = halloc<KzgBlock>(nl); bt.dBlocks = dalloc<KzgBlock>(nl);
+  u8* dIn = dalloc<u8>(nl * cap); u8* dOut = dalloc<u8>(nl * outBytes);
+  u8* dHdr = dalloc<u8>(nl * es.maxChunks * es.hdrStride + 16); u8* dPay = dalloc<u8>(nl * es.maxChunks * es.payStride + 16);
+  u32* dTab = dalloc<u32>(nl * es.maxChunks * es.tabStride + 4); KzgSeg* dSegs = dalloc<KzgSeg>(nl * es.segsPerBlock);
+  u8* dHdrBytes = dalloc<u8>(nl * 8 + 16); i64* dTotal = dalloc<i64>(2);
+  if (!bt.hBlocks || !bt.dBlocks || !dIn || !dOut || !dHdr || !dPay || !dTab || !dSegs || !dHdrBytes || !dTotal) return failAll(-KZG_ERR_CREATE_CODEC);
+  auto cu = [&](cudaError_t e) { if (e != cudaSuccess) { kzg_set_error("entropy batch: %s", cudaGetErrorString(e)); cudaGetLastError(); return false; } return true; };
+  for (size_t k = 0; k < nl; k++) {
+    KzgReq& Q = *rq[live[k]];
+    KzgBlock& B = bt.hBlocks[k];
+    memset(&B, 0, sizeof(B));
+    B.cur = dIn + k * cap; B.alt = nullptr; B.curLen = Q.srcLen; B.cap = (i32)cap; B.origLen = Q.srcLen; B.entropy = type;
+    B.srcBit = (i64)(k * outBytes) * 8;                    // container == 0: the payload lands at this bit of dOut
+    if (!cu(cudaMemsetAsync(B.cur + Q.srcLen, 0, cap - Q.srcLen, W.stream)) || !cu(cudaMemcpyAsync(B.cur, Q.src, Q.srcLen, cudaMemcpyHostToDevice, W.stream)))
+      return failAll(-KZG_ERR_PROCESS_BLOCK);
+  }
+  if (!cu(cudaMemsetAsync(dOut, 0, nl * outBytes, W.stream)) || !cu(cudaMemsetAsync(dSegs, 0, sizeof(KzgSeg) * nl * es.segsPerBlock, W.stream))) return failAll(-KZG_ERR_PROCESS_BLOCK);
+  r = batch_upload(bt); if (r < 0) return failAll(r);
+  r = run_entropy_encode(bt, type, es, dHdr, dPay, dTab, dSegs); if (r < 0) return failAll(r);
+  r = kzg_assemble_launch(W.stream, bt.dBlocks, (int)nl, dSegs, es.segsPerBlock, dHdrBytes, 1, 0, dOut, 0, dTotal, (i64)(nl * outBytes) - 8); if (r < 0) return failAll(r);
+  r = batch_download(bt); if (r < 0) return failAll(r);
+  for (size_t k = 0; k < nl; k++) {
+    KzgReq& Q = *rq[live[k]];
+    const KzgBlock& B = bt.hBlocks[k];
+    if (B.status != 0) { Q.ret = B.status; continue; }
+    const i64 bits = B.entBits, bytes = (bits + 7) >> 3;
+    if (bytes > (i64)Q.dstCap || bytes > (i64)outBytes - 8) { kzg_set_error("entropy output (%lld bytes) exceeds capacity", (long long)bytes); Q.ret = -KZG_ERR_PROCESS_BLOCK; continue; }
+    if (!cu(cudaMemcpyAsync(Q.dst, dOut + k * outBytes, (size_t)bytes, cudaMemcpyDeviceToHost, W.stream))) { Q.ret = -KZG_ERR_PROCESS_BLOCK; continue; }
+    Q.bits = bits; Q.ret = Q.srcLen;
+  }
+  if (!cu(cudaStreamSynchronize(W.stream))) return failAll(-KZG_ERR_PROCESS_BLOCK);
+  return 0;
+}
+
+static int entropy_decode_batch(std::vector<KzgReq*>& rq) {
+  const int type = rq[0]->type;
+  int r = ws_init(); if (r < 0) { for (auto q : rq) q->ret = r; return 0; }
+  std::vector<int> live;
+  i32 maxN = 0; size_t maxIn = 0;
+  for (int i = 0; i < (int)rq.size(); i++) {
+    KzgReq& Q = *rq[i];
+    Q.bits = 0;
+    if (!ent_known(type)) { Q.ret = -KZG_ERR_INVALID_CODEC; continue; }
+    if (Q.dstCap < 0 || Q.src == nullptr || Q.dst == nullptr || Q.inBits < 0) { Q.ret = -1; continue; }
+    if (Q.dstCap == 0) { Q.ret = 0; continue; }
+    live.push_back(i); maxN = std::max(maxN, Q.dstCap); maxIn = std::max(maxIn, (size_t)((Q.inBits + 7) >> 3));
+  }
+  if (live.empty()) return 0;
+  auto failAll = [&](int code) { for (int i : live) rq[i]->ret = code; return 0; };
+  const size_t nl = live.size();
+  EntScratch es = ent_scratch_size(type, maxN, false);
+  const size_t inCap = rnd(maxIn + 64), cap = rnd((size_t)maxN + 64);
+  const size_t need = nl * (inCap + cap + (size_t)es.maxChunks * (sizeof(KzgChunkInfo) + es.tabStride * 4) + sizeof(KzgBlock) + 64) + 65536;
+  r = ws_reserve(need, nl * (sizeof(KzgBlock) + 16) + 4096); if (r < 0) return failAll(r);
+  Batch bt; bt.nBlocks = (int)nl; bt.maxLen = maxN;
+  bt.hBlocks = halloc<KzgBlock>(nl); bt.dBlocks = dalloc<KzgBlock>(nl);
+  u8* dIn = dalloc<u8>(nl * inCap); u8* dOut = dalloc<u8>(nl * cap);
+  KzgChunkInfo* dChunks = dalloc<KzgChunkInfo>(nl * es.maxChunks + 1); u32* dTab = dalloc<u32>(nl * es.maxChunks * es.tabStride + 4);
+  if (!bt.hBlocks || !bt.dBlocks || !dIn || !dOut || !dChunks || !dTab) return failAll(-KZG_ERR_CREATE_CODEC);
+  auto cu = [&](cudaError_t e) { if (e != cudaSuccess) { kzg_set_error("entropy batch: %s", cudaGetErrorString(e)); cudaGetLastError(); return false; } return true; };
+  for (size_t k = 0; k < nl; k++) {
+    KzgReq& Q = *rq[live[k]];
+    KzgBlock& B = bt.hBlocks[k];
+    memset(&B, 0, sizeof(B));
+    const size_t inBytes = (size_t)((Q.inBits + 7) >> 3);
+    B.cur = dOut + k * cap; B.curLen = Q.dstCap; B.cap = (i32)cap; B.preLen = Q.dstCap; B.entropy = type;
+    B.srcBit = (i64)(k * inCap) * 8; B.srcBits = Q.inBits;
+    if (!cu(cudaMemsetAsync(dIn + k * inCap + inBytes, 0, inCap - inBytes, W.stream)) || !cu(cudaMemcpyAsync(dIn + k * inCap, Q.src, inBytes, cudaMemcpyHostToDevice, W.stream)))
+      return failAll(-KZG_ERR_PROCESS_BLOCK);
+  }
+  r = batch_upload(bt); if (r < 0) return failAll(r);
+  r = run_entropy_decode(bt, type, es, dIn, dChunks, dTab); if (r < 0) return failAll(r);
+  r = batch_download(bt); if (r < 0) return failAll(r);
+  for (size_t k = 0; k < nl; k++) {
+    KzgReq& Q = *rq[live[k]];
+    const KzgBlock& B = bt.hBlocks[k];
+    if (B.status != 0) { Q.ret = 0; continue; }          // the Java decoders signal corrupt input by a short count / exception
+    if (!cu(cudaMemcpyAsync(Q.dst, B.cur, Q.dstCap, cudaMemcpyDeviceToHost, W.stream))) { Q.ret = 0; continue; }
+    Q.bits = B.entBits; Q.ret = Q.dstCap;
+  }
+  if (!cu(cudaStreamSynchronize(W.stream))) return failAll(-KZG_ERR_PROCESS_BLOCK);
+  return 0;
+}
+
+static void run_batch(std::vector<KzgReq*>& rq) {
+  switch (rq[0]->kind) {
+    case KZG_REQ_XF_FWD: case KZG_REQ_XF_INV: transform_batch(rq); break;
+    case KZG_REQ_ENT_ENC: entropy_encode_batch(rq); break;
+    default: entropy_decode_batch(rq); break;
+  }
+}
+
+// ---- the coalescing service: one thread per process, owns a workspace of its own on the device it was enabled for -----------------
+struct Coalescer {
+  std::mutex m; std::condition_variable cvWork, cvDone;
+  std::vector<KzgReq*> pending;
+  std::thread worker; bool running = false, stop = false;
+  int maxBatch = 0, windowMicros = 0, device = 0;
+  std::atomic<long long> batches{0}, requests{0};
+  ~Coalescer() { if (running) { { std::lock_guard<std::mutex> g(m); stop = true; } cvWork.notify_all(); if (worker.joinable()) worker.join(); } }
+  void loop() {
+    W.device = device;
+    std::unique_lock<std::mutex> lk(m);
+    for (;;) {
+      cvWork.wait(lk, [&] { return stop || !pending.empty(); });
+      if (stop) return;
+      // gather: wait for company until the batch is full or the window (counted from the first arrival) has passed
+      const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(windowMicros);
+      while ((int)pending.size() < maxBatch && !stop) { if (cvWork.wait_until(lk, deadline) == std::cv_status::timeout) break; }
+      std::vector<KzgReq*> take, rest;
+      const KzgReq* f = pending[0];
+      for (KzgReq* q : pending) {
+        if ((int)take.size() < maxBatch && q->kind == f->kind && q->type == f->type && q->flags == f->flags) take.push_back(q); else rest.push_back(q);
+      }
+      pending.swap(rest);
+      lk.unlock();
+      run_batch(take);
+      batches++; requests += (long long)take.size();
+      lk.lock();
+      for (KzgReq* q : take) q->done = true;
+      cvDone.notify_all();
+    }
+  }
+  void submit(KzgReq& q) {
+    std::unique_lock<std::mutex> lk(m);
+    pending.push_back(&q);
+    cvWork.notify_one();
+    cvDone.wait(lk, [&] { return q.done; });
+  }
+};
+static Coalescer gCo;
+
+static void submit_or_run(KzgReq& q) {
+  if (gCo.running) { gCo.submit(q); return; }
+  std::vector<KzgReq*> one{&q};
+  run_batch(one);
+}
+
+int kzg_set_coalescing(int maxBatch, int windowMicros) {
+  std::unique_lock<std::mutex> lk(gCo.m);
+  if (maxBatch <= 1) {                       // off: stop the service once its queue is empty
+    if (gCo.running) {
+      gCo.stop = true; gCo.cvWork.notify_all();
+      lk.unlock(); gCo.worker.join(); lk.lock();
+      gCo.running = false; gCo.stop = false;
+    }
+    return 0;
+  }
+  gCo.maxBatch = std::min(maxBatch, 1024); gCo.windowMicros = std::max(0, windowMicros);
+  if (!gCo.running) {
+    gCo.device = W.device;                   // the calling thread's device (kzg_set_device first for another one)
+    gCo.running = true;
+    gCo.worker = std::thread([] { gCo.loop(); });
+  }
+  return 0;
+}
+int64_t kzg_coalescing_stats(int64_t* batches) { if (batches) *batches = gCo.batches.load(); return gCo.requests.load(); }
+
 int kzg_transform_forward(int type, kzg_ctx* ctx, const uint8_t* src, int32_t srcLen, uint8_t* dst, int32_t dstLen, int32_t dstCap,
                           int32_t* srcUsed, int32_t* dstUsed) {
-  return transform_call(type, true, ctx, src, srcLen, dst, dstLen, dstCap, srcUsed, dstUsed);
+  KzgReq q; q.kind = KZG_REQ_XF_FWD; q.type = type; q.ctx = ctx; q.flags = ctx ? ctx->flags : 0; q.src = src; q.srcLen = srcLen; q.dst = dst; q.dstLen = dstLen; q.dstCap = dstCap; q.inBits = 0;
+  submit_or_run(q);
+  if (srcUsed) *srcUsed = q.srcUsed; if (dstUsed) *dstUsed = q.dstUsed;
+  return (int)q.ret;
 }
 int kzg_transform_inverse(int type, kzg_ctx* ctx, const uint8_t* src, int32_t srcLen, uint8_t* dst, int32_t dstLen, int32_t dstCap,
                           int32_t* srcUsed, int32_t* dstUsed) {
-  return transform_call(type, false, ctx, src, srcLen, dst, dstLen, dstCap, srcUsed, dstUsed);
+  KzgReq q; q.kind = KZG_REQ_XF_INV; q.type = type; q.ctx = ctx; q.flags = ctx ? ctx->flags : 0; q.src = src; q.srcLen = srcLen; q.dst = dst; q.dstLen = dstLen; q.dstCap = dstCap; q.inBits = 0;
+  submit_or_run(q);
+  if (srcUsed) *srcUsed = q.srcUsed; if (dstUsed) *dstUsed = q.dstUsed;
+  return (int)q.ret;
 }
 
 int kzg_bwt_forward(const uint8_t* src, int32_t n, uint8_t* dst, int32_t* primaryIndexes8) {
@@ -399,81 +703,18 @@ int kzg_bwt_inverse(const uint8_t* src, int32_t n, uint8_t* dst, const int32_t* 
   return kzg_bwt_raw(W.stream, false, src, n, dst, (int32_t*)primaryIndexes8);
 }
 
-// ---- one EntropyEncoder.encode (+dispose) / EntropyDecoder.decode call --------------------------------------------
 int64_t kzg_entropy_encode(int type, kzg_ctx* ctx, const uint8_t* src, int32_t n, uint8_t* out, int64_t outCap, int64_t* outBits) {
-  if (outBits) *outBits = 0;
-  if (!ent_known(type)) return -KZG_ERR_INVALID_CODEC;
-  if (n < 0 || src == nullptr || out == nullptr) return -1;          // Java: encode returns -1 on bad arguments
-  int r = ws_init(); if (r < 0) return r;
-  if (n == 0) return 0;
-  EntScratch es = ent_scratch_size(type, n, true);
-  const size_t cap = rnd((size_t)n + 64);
-  const size_t outBytes = rnd(2 * (size_t)n + (256 << 10));     // ANS1 on noise: 256 context headers + up to 2 bytes per symbol
-  const size_t need = cap + outBytes + (size_t)es.maxChunks * (es.hdrStride + es.payStride + es.tabStride * 4) +
-                      (size_t)es.segsPerBlock * sizeof(KzgSeg) + 65536;
-  r = ws_reserve(need, sizeof(KzgBlock) + 4096); if (r < 0) return r;
-  Batch bt; bt.nBlocks = 1; bt.maxLen = n;
-  bt.hBlocks = halloc<KzgBlock>(1); NN(bt.hBlocks);
-  bt.dBlocks = dalloc<KzgBlock>(1); NN(bt.dBlocks);
-  u8* dIn = dalloc<u8>(cap); NN(dIn);
-  u8* dOut = dalloc<u8>(outBytes); NN(dOut);
-  u8* dHdr = dalloc<u8>((size_t)es.maxChunks * es.hdrStride + 16); NN(dHdr);
-  u8* dPay = dalloc<u8>((size_t)es.maxChunks * es.payStride + 16); NN(dPay);
-  u32* dTab = dalloc<u32>((size_t)es.maxChunks * es.tabStride + 4); NN(dTab);
-  KzgSeg* dSegs = dalloc<KzgSeg>(es.segsPerBlock); NN(dSegs);
-  u8* dHdrBytes = dalloc<u8>(16); NN(dHdrBytes);
-  i64* dTotal = dalloc<i64>(2); NN(dTotal);
-  KzgBlock& B = bt.hBlocks[0];
-  memset(&B, 0, sizeof(B));
-  B.cur = dIn; B.alt = nullptr; B.curLen = n; B.cap = (i32)cap; B.origLen = n; B.entropy = type; B.srcBit = 0;
-  CUDA_TRY(cudaMemsetAsync(dIn + n, 0, cap - n, W.stream));
-  CUDA_TRY(cudaMemcpyAsync(dIn, src, n, cudaMemcpyHostToDevice, W.stream));
-  CUDA_TRY(cudaMemsetAsync(dOut, 0, outBytes, W.stream));
-  CUDA_TRY(cudaMemsetAsync(dSegs, 0, sizeof(KzgSeg) * es.segsPerBlock, W.stream));
-  r = batch_upload(bt); if (r < 0) return r;
-  r = run_entropy_encode(bt, type, es, dHdr, dPay, dTab, dSegs); if (r < 0) return r;
-  r = kzg_assemble_launch(W.stream, bt.dBlocks, 1, dSegs, es.segsPerBlock, dHdrBytes, 1, 0, dOut, 0, dTotal, (i64)outBytes - 8); if (r < 0) return r;
-  r = batch_download(bt); if (r < 0) return r;
-  if (B.status != 0) return B.status;
-  const i64 bits = B.entBits;
-  const i64 bytes = (bits + 7) >> 3;
-  if (bytes > outCap || bytes > (i64)outBytes - 8) { kzg_set_error("entropy output (%lld bytes) exceeds capacity", (long long)bytes); return -KZG_ERR_PROCESS_BLOCK; }
-  CUDA_TRY(cudaMemcpy(out, dOut, (size_t)bytes, cudaMemcpyDeviceToHost));
-  if (outBits) *outBits = bits;
-  return n;
+  KzgReq q; q.kind = KZG_REQ_ENT_ENC; q.type = type; q.ctx = ctx; q.flags = 0; q.src = src; q.srcLen = n; q.dst = out; q.dstLen = 0;
+  q.dstCap = (int32_t)std::min<int64_t>(outCap, 0x7FFFFFFF); q.inBits = 0;
+  submit_or_run(q);
+  if (outBits) *outBits = q.bits;
+  return q.ret;
 }
-
 int32_t kzg_entropy_decode(int type, kzg_ctx* ctx, const uint8_t* in, int64_t inBits, int64_t* bitsUsed, uint8_t* dst, int32_t n) {
-  if (bitsUsed) *bitsUsed = 0;
-  if (!ent_known(type)) return -KZG_ERR_INVALID_CODEC;
-  if (n < 0 || in == nullptr || dst == nullptr || inBits < 0) return -1;
-  int r = ws_init(); if (r < 0) return r;
-  if (n == 0) return 0;
-  EntScratch es = ent_scratch_size(type, n, false);
-  const size_t inBytes = (size_t)((inBits + 7) >> 3);
-  const size_t inCap = rnd(inBytes + 64);
-  const size_t cap = rnd((size_t)n + 64);
-  const size_t need = inCap + cap + (size_t)es.maxChunks * (sizeof(KzgChunkInfo) + es.tabStride * 4) + 65536;
-  r = ws_reserve(need, sizeof(KzgBlock) + 4096); if (r < 0) return r;
-  Batch bt; bt.nBlocks = 1; bt.maxLen = n;
-  bt.hBlocks = halloc<KzgBlock>(1); NN(bt.hBlocks);
-  bt.dBlocks = dalloc<KzgBlock>(1); NN(bt.dBlocks);
-  u8* dIn = dalloc<u8>(inCap); NN(dIn);
-  u8* dOut = dalloc<u8>(cap); NN(dOut);
-  KzgChunkInfo* dChunks = dalloc<KzgChunkInfo>(es.maxChunks); NN(dChunks);
-  u32* dTab = dalloc<u32>((size_t)es.maxChunks * es.tabStride + 4); NN(dTab);
-  KzgBlock& B = bt.hBlocks[0];
-  memset(&B, 0, sizeof(B));
-  B.cur = dOut; B.curLen = n; B.cap = (i32)cap; B.preLen = n; B.entropy = type; B.srcBit = 0; B.srcBits = inBits;
-  CUDA_TRY(cudaMemsetAsync(dIn + inBytes, 0, inCap - inBytes, W.stream));
-  CUDA_TRY(cudaMemcpyAsync(dIn, in, inBytes, cudaMemcpyHostToDevice, W.stream));
-  r = batch_upload(bt); if (r < 0) return r;
-  r = run_entropy_decode(bt, type, es, dIn, dChunks, dTab); if (r < 0) return r;
-  r = batch_download(bt); if (r < 0) return r;
-  if (B.status != 0) return 0;        // the Java decoders signal corrupt input by a short count / exception
-  CUDA_TRY(cudaMemcpy(dst, dOut, n, cudaMemcpyDeviceToHost));
-  if (bitsUsed) *bitsUsed = B.entBits;
-  return n;
+  KzgReq q; q.kind = KZG_REQ_ENT_DEC; q.type = type; q.ctx = ctx; q.flags = 0; q.src = in; q.srcLen = 0; q.dst = dst; q.dstLen = 0; q.dstCap = n; q.inBits = inBits;
+  submit_or_run(q);
+  if (bitsUsed) *bitsUsed = q.bits;
+  return (int32_t)q.ret;
 }
 
 // ---- whole streams ------------------------------------------------------------------------------------------------
@@ -521,6 +762,7 @@ static int64_t compress_impl(const uint8_t* d_in, int64_t n, const int32_t* tran
   int fn[8]; const int nf = seq_functions(transforms, nTransforms, fn);
   u64 transformType = 0;
   for (int i = 0; i < nTransforms && i < 8; i++) transformType |= ((u64)transforms[i] << (42 - 6 * i));
+  W.lastRecBits.clear();
   const int nBlocks = (int)((n + blockSize - 1) / blockSize);
   const i32 maxBlock = (i32)std::min<i64>(n, blockSize);
   const i32 required = seq_max_len(fn, nf, maxBlock);
@@ -612,6 +854,12 @@ static int64_t compress_impl(const uint8_t* d_in, int64_t n, const int32_t* tran
     for (int b = 0; b < nBlocks; b++)
       if (bt.hBlocks[b].status != 0) { kzg_set_error("block %d failed with status %d", b + 1, bt.hBlocks[b].status); return bt.hBlocks[b].status; }
     if (totalBits < 0) return -KZG_ERR_PROCESS_BLOCK;
+    W.lastRecBits.resize(nBlocks);
+    for (int b = 0; b < nBlocks; b++) {          // COS:1024-1035: 5 bits of (lw - 3), lw bits of `written`, then `written` bits
+      const i64 written = bt.hBlocks[b].written;
+      int lw = 3; if (written >= 8) { lw = 0; while ((2LL << lw) <= (written >> 3)) lw++; lw += 4; }
+      W.lastRecBits[b] = 5 + lw + written;
+    }
     if (timing3) {
       for (int i = 0; i < 3; i++) CUDA_TRY(cudaEventElapsedTime(&timing3[i], ev[i], ev[i + 1]));
     }

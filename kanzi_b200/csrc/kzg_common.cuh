@@ -132,5 +132,10 @@ __host__ __device__ __forceinline__ u32 kzg_mix32(u32 c, u32 h, u32 v) {
 // words are merged with atomicOr so neighbouring segments may share a 32-bit word.
 struct KzgSeg { const u8* src; u64 srcBit; u64 dstBit; u64 nBits; };
 
+// per-kernel event timing (bench.py's roofline block): a no-op unless kzg_set_profiling(1) was called on this thread
+void kzg_prof_begin(const char* name, cudaStream_t s);
+void kzg_prof_end(cudaStream_t s);
+#define KZG_PROF(name, s, launch) do { kzg_prof_begin(name, s); launch; kzg_prof_end(s); } while (0)
+
 #define CUDA_TRY(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { kzg_set_error("%s:%d %s: %s", __FILE__, __LINE__, #x, cudaGetErrorString(e__)); return -KZG_ERR_PROCESS_BLOCK; } } while (0)
 void kzg_set_error(const char* fmt, ...);

@@ -5,8 +5,8 @@
 // with the same hash".  Every position below p is inserted except the ones the skip acceleration jumped over
 // (srcInc >> 6, :399-400), so the table is *almost* parse-independent.  That splits the work (DESIGN.md "LZ forward"):
 //   phase 1 (data parallel, HBM-bound): hash of every position -> stable LSD radix sort of packed key|position
-//     elements by hash -> prev[p] / hs[] / rank[] -> len0[p] = findMatch(p, prev[p]) capped at 255; a second
-//     sort key (4-byte fingerprint) flags positions that can never hit the table.
+//     elements by hash -> prev[p] / hs[] / rank[] -> len0[p] = findMatch(p, prev[p]) capped at 255; a look-back
+//     through the hash class (4-byte fingerprint carried in the key) flags positions that can never hit the table.
 //   head: the first 2 KiB of every block parsed for real; their jumped-over bits seed the assumed bitmap A.
 //   segments (lzf_spec_kernel, one warp per 8 KiB segment): speculative parses after a warm-up, 32 visit positions per
 //     batch, with A for positions before the segment; matches are logged, lookups that depended on A are marked.
@@ -269,18 +269,35 @@ __global__ void __launch_bounds__(32 * LZF_WARPS, 3) lzf_scatter_kernel(LzfBlock
     out[gOff[d] + (u32)j - digitBase[d]] = x;
   }
 }
-// after the hash passes: sorted[i-1] precedes sorted[i] in (hash, position) order: same hash -> it is the previous occurrence
+// after the hash passes: sorted[i-1] precedes sorted[i] in (hash, position) order: same hash -> it is the previous occurrence.
+// A position with no earlier occurrence of its 4-byte fingerprint inside its hash class can never pass the 4-byte pre-check
+// (:389-395, :405-422 need bestLen >= 4) whatever the table holds: flagged LZF_NOCAND here by looking back through the class
+// (at most 1024 entries: an unfinished search leaves the flag off, which is always safe).
+#define LZF_FP_LOOKBACK 1024
 __global__ void lzf_prev_kernel(LzfBlock* __restrict__ lb, const int* __restrict__ bmap, int nPass, int hashBits) {
   const LzfBlock& L = lb[bmap[blockIdx.y]];
   const int n = L.n;
   const u64* __restrict__ sorted = (nPass & 1) ? L.kb : L.ka;
   const u64 hmask = ((1ull << hashBits) - 1) << 30;
+  const int fpShift = 30 + hashBits;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const u64 v = sorted[i];
     const u32 s = (u32)(v & LZF_POSMASK);
     u32 pv = 0;
     if (i > 0) { const u64 w = sorted[i - 1]; if (((w ^ v) & hmask) == 0) pv = (u32)(w & LZF_POSMASK); }
-    L.prev[s] = pv;
+    bool has = false;
+    if (pv != 0) {
+      const u64 fp = v >> fpShift;
+      int j = i - 1;
+      for (int steps = 0; ; steps++, j--) {
+        if (steps >= LZF_FP_LOOKBACK) { has = true; break; }
+        const u64 w = sorted[j];
+        if (((w ^ v) & hmask) != 0) break;
+        if ((w >> fpShift) == fp) { has = true; break; }
+        if (j == 0) break;
+      }
+    }
+    L.prev[s] = pv | (has ? 0u : LZF_NOCAND);
     L.hs[i] = s | (pv == 0 ? LZF_RUNSTART : 0u);
     L.rank[s] = (u32)i;
   }
@@ -298,10 +315,11 @@ __global__ void lzf_cand_kernel(const KzgBlock* __restrict__ blocks, LzfBlock* _
   int hits = 0, hits2 = 0;
   const int e0 = beg / eighth;
   for (int p = beg + threadIdx.x; p < end; p += blockDim.x) {
-    const int ref = (int)L.prev[p];
+    const u32 pvRaw = L.prev[p];
+    const int ref = (int)(pvRaw & ~LZF_NOCAND);
     const int minRef = max(p - L.maxDist, 0);
     int len = 0;
-    if (ref > minRef && lzf_ld32(src + ref) == lzf_ld32(src + p))
+    if (!(pvRaw & LZF_NOCAND) && ref > minRef && lzf_ld32(src + ref) == lzf_ld32(src + p))
       len = lzf_find_match(src, p, ref, min(L.srcEnd - p, LZ_MAX_MATCH), 256);
     L.len0[p] = (u8)min(len, 255);
     if (len >= 4) { if (p / eighth == e0) hits++; else hits2++; }
@@ -310,20 +328,6 @@ __global__ void lzf_cand_kernel(const KzgBlock* __restrict__ blocks, LzfBlock* _
   if ((threadIdx.x & 31) == 0) {
     if (hits > 0) atomicAdd(&L.estHits[min(e0, 7)], hits);
     if (hits2 > 0) atomicAdd(&L.estHits[min(e0 + 1, 7)], hits2);
-  }
-}
-
-// After the second sort (fingerprint, hash, position): a position whose predecessor differs in hash or fingerprint has no
-// earlier occurrence of its first 4 bytes among the positions with its hash, so no table content can ever pass the 4-byte
-// pre-check there (:389-395, :405-422 need bestLen >= 4).  Those positions never need the table: flag them in prev[].
-__global__ void lzf_flag_kernel(LzfBlock* __restrict__ lb, const int* __restrict__ bmap, int nPass) {
-  const LzfBlock& L = lb[bmap[blockIdx.y]];
-  const int n = L.n;
-  const u64* __restrict__ sorted = (nPass & 1) ? L.kb : L.ka;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const u64 v = sorted[i];
-    const bool has = (i > 0) && ((sorted[i - 1] >> 30) == (v >> 30));
-    if (!has) L.prev[(u32)(v & LZF_POSMASK)] |= LZF_NOCAND;
   }
 }
 
@@ -1830,7 +1834,7 @@ int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
   lzf_setup_kernel<<<(nBlocks + 63) / 64, 64, 0, s>>>(d_blocks, nBlocks, P, dlb, z.segLen, (dbg & 8) ? 1 : 0);
   const int gx = std::max(1, std::min((maxLen + 255) / 256, 8 * KZG_SM_COUNT));
   const int nT = (maxLen + LZF_WT - 1) / LZF_WT;
-  const int bits = extra ? 19 : 16, fpBits = extra ? 13 : 16;
+  const int bits = extra ? 19 : 16;
   int launches = 2;
   int* dCnt = (int*)(base + nb * z.total);                 // [2 * LZF_MAXG] counters, the block order, the sampled keys
   int* dMap = dCnt + 2 * LZF_MAXG;
@@ -1843,20 +1847,13 @@ int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
     int pass = 0;
     for (int shift = 0; shift < bits; shift += 8, pass++) {
       const int mask = (1 << std::min(8, bits - shift)) - 1;
-      lzf_hist_kernel<<<gridT, 32 * LZF_WARPS, 0, q>>>(dlb, bm, 30 + shift, mask, pass);
+      KZG_PROF("lzf_hist_kernel", q, (lzf_hist_kernel<<<gridT, 32 * LZF_WARPS, 0, q>>>(dlb, bm, 30 + shift, mask, pass)));
       lzf_scan_kernel<<<cnt, 1024, 0, q>>>(dlb, bm);
-      lzf_scatter_kernel<<<dim3(nT, cnt), 32 * LZF_WARPS, 0, q>>>(dlb, bm, 30 + shift, mask, pass);
+      KZG_PROF("lzf_scatter_kernel", q, (lzf_scatter_kernel<<<dim3(nT, cnt), 32 * LZF_WARPS, 0, q>>>(dlb, bm, 30 + shift, mask, pass)));
     }
-    lzf_prev_kernel<<<dim3(gx, cnt), 256, 0, q>>>(dlb, bm, pass, bits);
-    lzf_cand_kernel<<<dim3(gx, cnt), 256, 0, q>>>(d_blocks, dlb, bm);
-    for (int shift = 0; shift < fpBits; shift += 8, pass++) {   // second sort key: the 4-byte fingerprint
-      const int mask = (1 << std::min(8, fpBits - shift)) - 1;
-      lzf_hist_kernel<<<gridT, 32 * LZF_WARPS, 0, q>>>(dlb, bm, 30 + bits + shift, mask, pass);
-      lzf_scan_kernel<<<cnt, 1024, 0, q>>>(dlb, bm);
-      lzf_scatter_kernel<<<dim3(nT, cnt), 32 * LZF_WARPS, 0, q>>>(dlb, bm, 30 + bits + shift, mask, pass);
-    }
-    lzf_flag_kernel<<<dim3(gx, cnt), 256, 0, q>>>(dlb, bm, pass);
-    launches += 4 + 3 * pass;
+    KZG_PROF("lzf_prev_kernel", q, (lzf_prev_kernel<<<dim3(gx, cnt), 256, 0, q>>>(dlb, bm, pass, bits)));
+    KZG_PROF("lzf_cand_kernel", q, (lzf_cand_kernel<<<dim3(gx, cnt), 256, 0, q>>>(d_blocks, dlb, bm)));
+    launches += 3 + 3 * pass;
     if (head) {
       if (extra) lzf_head_kernel<true><<<cnt, 32, 0, q>>>(d_blocks, dlb, bm);
       else lzf_head_kernel<false><<<cnt, 32, 0, q>>>(d_blocks, dlb, bm);
@@ -1910,11 +1907,15 @@ int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
       const int cnt = gBeg[g + 1] - gBeg[g];
       if (round > 0) cudaMemsetAsync(dCnt + 2 * g, 0, 2 * sizeof(int), q);
       lzf_round_init_kernel<<<dim3(std::min(gx, 64), cnt), 256, 0, q>>>(dlb, bm, round == 0 ? 1 : 0);
+      kzg_prof_begin("lzf_spec_kernel", q);
       if (extra) lzf_spec_kernel<true><<<dim3(z.maxSeg, cnt), 32, 0, q>>>(d_blocks, dlb, bm);
       else lzf_spec_kernel<false><<<dim3(z.maxSeg, cnt), 32, 0, q>>>(d_blocks, dlb, bm);
+      kzg_prof_end(q);
+      kzg_prof_begin("lzf_stitch_kernel", q);
       if (extra) lzf_stitch_kernel<true><<<cnt, 32, 0, q>>>(d_blocks, dlb, bm, dbg);
       else lzf_stitch_kernel<false><<<cnt, 32, 0, q>>>(d_blocks, dlb, bm, dbg);
-      lzf_check_marks_kernel<<<dim3(16, cnt), 256, 0, q>>>(dlb, bm);
+      kzg_prof_end(q);
+      KZG_PROF("lzf_check_marks_kernel", q, (lzf_check_marks_kernel<<<dim3(16, cnt), 256, 0, q>>>(dlb, bm)));
       lzf_check_final_kernel<<<cnt, 128, 0, q>>>(dlb, bm, cnt, round == maxRounds - 1 ? 1 : 0, dCnt + 2 * g, dbg);
       cudaMemcpyAsync(ST.hCnt + 2 * g, dCnt + 2 * g, 2 * sizeof(int), cudaMemcpyDeviceToHost, q);
       launches += 5;

@@ -51,10 +51,6 @@ struct LziShared {
   u32 wm0[32], wm1[32], ws0[32], ws1[32];
   u32 carryK, carryL, carryM, carryD, carryOut, rep0, rep1, totA, totB;
   int nExtL, nExtM, nExtLValid, nExtMValid, lastIdx, fail;
-  u32 winBase; int winJ, chaseDone;
-  u32 winK[LZI_KB];
-  u32 winE[LZI_KB];
-  u16 G[LZI_WIN];
 };
 
 // exclusive scan of two values over the CTA (1024 threads); totals left in S.totA / S.totB
@@ -143,15 +139,17 @@ __global__ void __launch_bounds__(LZI_TT) lzi_tok_sums_kernel(KzgBlock* __restri
     H.nExtL = 0; H.nExtM = 0; H.nExtLValid = 0; H.nExtMValid = 0;
   }
   if (!ok) return;
-  const int base = blockIdx.x * LZI_TT;
-  if (base >= Y.nTokBytes) return;
   const LziArrays A = lzi_arrays(toks, extPool, tilePool, tokStride, tileStride, b);
-  const int t = base + tid;
-  const bool on = t < Y.nTokBytes;
-  const LziFlags F = lzi_flags(on ? B.cur[Y.tkBase + t] : 0, on);
-  u32 o0, o1;
-  lzi_cta_scan2(F.known | (F.nd << 16), ((u32)F.lExt << 16) | (u32)F.mExt, o0, o1, S, lane, warp);
-  if (tid == 0) A.tileSum[blockIdx.x] = make_uint2(S.totA, S.totB);
+  // (the grid is a fixed number of CTAs per block: the token count is only known on the device)
+  for (int tile = blockIdx.x; tile * LZI_TT < Y.nTokBytes; tile += gridDim.x) {
+    const int t = tile * LZI_TT + tid;
+    const bool on = t < Y.nTokBytes;
+    const LziFlags F = lzi_flags(on ? B.cur[Y.tkBase + t] : 0, on);
+    u32 o0, o1;
+    lzi_cta_scan2(F.known | (F.nd << 16), ((u32)F.lExt << 16) | (u32)F.mExt, o0, o1, S, lane, warp);
+    if (tid == 0) A.tileSum[tile] = make_uint2(S.totA, S.totB);
+    __syncthreads();
+  }
 }
 // T2 (one CTA per block): exclusive scan of the tile sums
 __global__ void __launch_bounds__(LZI_TT) lzi_tok_scan1_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P, LziTok* toks, i64 tokStride, LziHdr* __restrict__ hdrs,
@@ -190,21 +188,31 @@ __global__ void __launch_bounds__(LZI_TT) lzi_tok_extk_kernel(KzgBlock* __restri
   if (!hdrs[b].valid) return;
   LziLayout Y;
   if (!lzi_layout(blocks[b], P, b, Y)) return;
-  const int base = blockIdx.x * LZI_TT;
-  if (base >= Y.nTokBytes) return;
   const LziArrays A = lzi_arrays(toks, extPool, tilePool, tokStride, tileStride, b);
-  const int t = base + tid;
-  const bool on = t < Y.nTokBytes;
-  const LziFlags F = lzi_flags(on ? blocks[b].cur[Y.tkBase + t] : 0, on);
-  const uint4 off = A.tileOff[blockIdx.x];
-  u32 kOff, cOff;
-  lzi_cta_scan2(F.known, (u32)F.lExt, kOff, cOff, S, lane, warp);
-  if (F.lExt) A.extK[off.z + cOff] = off.x + kOff;
+  for (int tile = blockIdx.x; tile * LZI_TT < Y.nTokBytes; tile += gridDim.x) {
+    const int t = tile * LZI_TT + tid;
+    const bool on = t < Y.nTokBytes;
+    const LziFlags F = lzi_flags(on ? blocks[b].cur[Y.tkBase + t] : 0, on);
+    const uint4 off = A.tileOff[tile];
+    u32 kOff, cOff;
+    lzi_cta_scan2(F.known, (u32)F.lExt, kOff, cOff, S, lane, warp);
+    if (F.lExt) A.extK[off.z + cOff] = off.x + kOff;
+    __syncthreads();
+  }
 }
 // T4 (one CTA per block): the two cursor chains
+#define LZI_GCAP 8190                                   // largest advance a table entry can hold (stored doubled in 16 bits)
+#define LZI_GZERO (LZI_WIN + LZI_GCAP + 2)              // zero region behind the window: reach of four unchecked steps
+struct LziChaseSmem {
+  u32 winBase, winEbase; int winJ, chaseDone;
+  u32 winKaddr[LZI_KB];                                 // shared-memory address of G[13 + extK[j] - window base], clamped to the window end
+  u32 winKrel[LZI_KB];                                  // the same, unclamped and as a position
+  u32 winE[LZI_KB];                                     // 2 * (E_j - E at the window start)
+  u16 G[LZI_WIN + LZI_GZERO];
+};
+extern __shared__ __align__(16) u8 lzi_chase_smem[];
 __global__ void __launch_bounds__(LZI_TT) lzi_tok_chase_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P, LziTok* toks, i64 tokStride, LziHdr* __restrict__ hdrs,
                                                               u32* extPool, u32* tilePool, i64 tileStride) {
-  __shared__ LziShared S;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.x;
   LziHdr& H = hdrs[b];
   if (!H.valid) return;
@@ -250,42 +258,57 @@ __global__ void __launch_bounds__(LZI_TT) lzi_tok_chase_kernel(KzgBlock* __restr
     if (dbg && lane == 0) printf("lzi chase block %d: %d match-length records, warp 1 took %lld cycles\n", b, nExtM, clock64() - tStart);
   } else {
     // Record j sits at c_j = 13 + extK[j] + E_j with E_{j+1} = E_j + (record bytes + literal bytes it announces): a chain of
-    // dependent loads by construction.  The 31 warps take everything else off that chain: for every byte position of a
-    // 16 KiB window they precompute what a record starting there would add (G), so that thread 0's step is one shared load
-    // and two additions; the E values it leaves behind are turned into extE / extLS by the same warps afterwards.
+    // dependent loads by construction (no earlier byte says where record j is).  The 31 warps take everything else off that
+    // chain: for every byte position x of a 16 KiB window they precompute G[x] = 2 * (what a record starting at x adds), and
+    // for the window's next 1024 records the shared-memory ADDRESS of G[13 + extK[j] - window base]; thread 0's step is then
+    //     address = kaddr[j] + e2;  g2 = G[address];  e2 += g2                      (two additions and one shared load)
+    // with e2 = 2 * (E - E at the window start).  No range test sits on the chain: G is followed by a zero region long
+    // enough for any four steps, kaddr is clamped to the window end, positions past the block and runs too long for 16 bits
+    // hold 0, and "0" (a real record adds at least 8) sends the step to the careful path, once per group of four.
+    // The E values left behind are turned into extE / extLS by the helper warps afterwards.
+    LziChaseSmem& C = *reinterpret_cast<LziChaseSmem*>(lzi_chase_smem);
     const int wtid = (warp == 0) ? tid : tid - 32;             // 0..991
     const int nExtL = H.nExtL;
     const u32 lim = (u32)count + 8;
+    const u32 gAddr = (u32)__cvta_generic_to_shared(&C.G[0]);
     u32 E = 0; int j = 0;                                       // (thread 0)
     bool stop = (nExtL == 0);
-    u32 wbOld = 0; int pj0 = 0, pj1 = 0;
+    u32 wbOld = 0, ebOld = 0; int pj0 = 0, pj1 = 0;
     int nWin = 0; long long tChase = 0;
+    for (int x = wtid; x < LZI_GZERO; x += 992) C.G[LZI_WIN + x] = 0;      // the zero region (never rewritten)
     for (;;) {
       if (tid == 0) {
         if (!stop) {
           const u32 c = 13u + extK[j] + E;
           if (c + 4 > lim) stop = true;                         // beyond the block: whatever follows cannot be a live token
-          S.winBase = c;
+          C.winBase = c; C.winEbase = E;
         }
-        S.winJ = j;
-        S.chaseDone = stop ? 1 : 0;
+        C.winJ = j;
+        C.chaseDone = stop ? 1 : 0;
       }
       asm volatile("bar.sync 1, 992;" ::: "memory");
-      pj1 = S.winJ;
+      pj1 = C.winJ;
       // records the chase placed in the previous window: their lengths and sizes
       for (int i = pj0 + wtid; i < pj1; i += 992) {
-        const u32 e = S.winE[i - pj0];
-        const u32 c = wbOld + S.winK[i - pj0] + e;
+        const u32 e = ebOld + (C.winE[i - pj0] >> 1);
+        const u32 c = wbOld + C.winKrel[i - pj0] + (C.winE[i - pj0] >> 1);
         u32 r = src[c], sz;
         if (r < 254) sz = 1;
         else if (r == 254) { r += ((u32)src[c + 1] << 8) + (u32)src[c + 2]; sz = 3; }
         else { r += ((u32)src[c + 1] << 16) + ((u32)src[c + 2] << 8) + (u32)src[c + 3]; sz = 4; }
         extE[i] = e; extLS[i] = (7 + r) | (sz << 28);
       }
-      if (S.chaseDone) break;
-      const u32 wb = S.winBase; const int j0 = pj1;
-      asm volatile("bar.sync 1, 992;" ::: "memory");           // winK / winE of the previous window are consumed
-      for (int i = wtid; i < LZI_KB; i += 992) S.winK[i] = (j0 + i < nExtL) ? (13u + extK[j0 + i] - wb) : 0u;   // relative to the window
+      if (C.chaseDone) break;
+      const u32 wb = C.winBase, eb = C.winEbase; const int j0 = pj1;
+      asm volatile("bar.sync 1, 992;" ::: "memory");           // winKrel / winE of the previous window are consumed
+      {
+        const u32 k0 = extK[j0];
+        for (int i = wtid; i < LZI_KB; i += 992) {
+          const u32 kr = (j0 + i < nExtL) ? (extK[j0 + i] - k0) : (u32)LZI_WIN;       // relative to the window base
+          C.winKrel[i] = kr;
+          C.winKaddr[i] = gAddr + 2u * min(kr, (u32)LZI_WIN);
+        }
+      }
       for (int x = wtid; x < LZI_WIN; x += 992) {
         const u32 c = wb + (u32)x;
         u32 g = 0;
@@ -294,62 +317,66 @@ __global__ void __launch_bounds__(LZI_TT) lzi_tok_chase_kernel(KzgBlock* __restr
           if (r < 254) sz = 1;
           else if (r == 254) { r += ((u32)src[c + 1] << 8) + (u32)src[c + 2]; sz = 3; }
           else { r += ((u32)src[c + 1] << 16) + ((u32)src[c + 2] << 8) + (u32)src[c + 3]; sz = 4; }
-          g = min(7u + r + sz, 0xFFFFu);
+          g = 7u + r + sz;
+          if (g > (u32)LZI_GCAP) g = 0;                         // a literal run too long for the table: careful path
         }
-        S.G[x] = (u16)g;
+        C.G[x] = (u16)(2u * g);
       }
       if (wtid < 128 && wb + LZI_WIN + 128u * wtid < lim) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + wb + LZI_WIN + 128u * wtid));
       asm volatile("bar.sync 1, 992;" ::: "memory");
       if (tid == 0) {
         nWin++; const long long tc = clock64();
-        // The loop-carried chain is e -> c = base[j] + e -> G[c] -> e + g.  Four steps are issued back to back with the
-        // range and sentinel tests kept off that chain (checked once per group); a step that fails them is redone by the
-        // careful loop below.
-        const int jMax = min(nExtL, j0 + LZI_KB);
-        const u32 hiRel = min((u32)LZI_WIN, lim - 3u - wb);     // c valid iff c < hiRel (inside the window and the block)
-        const int* kb = reinterpret_cast<const int*>(S.winK);
+        const int qMax = min(nExtL - j0, LZI_KB);
+        int q = 0;
+        u32 e2 = 0;
+        const u32* ka = C.winKaddr;
         for (;;) {
-          int e = (int)E;
-          while (j + 4 <= jMax) {
-            const int q = j - j0;
-            const int c0 = kb[q] + e;      const u32 g0 = S.G[min((u32)c0, (u32)LZI_WIN - 1u)]; const int e1 = e + (int)g0;
-            const int c1 = kb[q + 1] + e1; const u32 g1 = S.G[min((u32)c1, (u32)LZI_WIN - 1u)]; const int e2 = e1 + (int)g1;
-            const int c2 = kb[q + 2] + e2; const u32 g2 = S.G[min((u32)c2, (u32)LZI_WIN - 1u)]; const int e3 = e2 + (int)g2;
-            const int c3 = kb[q + 3] + e3; const u32 g3 = S.G[min((u32)c3, (u32)LZI_WIN - 1u)]; const int e4 = e3 + (int)g3;
-            const bool v0 = ((u32)c0 < hiRel) && (g0 != 0xFFFFu), v1 = ((u32)c1 < hiRel) && (g1 != 0xFFFFu);
-            const bool v2 = ((u32)c2 < hiRel) && (g2 != 0xFFFFu), v3 = ((u32)c3 < hiRel) && (g3 != 0xFFFFu);
-            if (v0 && v1 && v2 && v3) { S.winE[q] = (u32)e; S.winE[q + 1] = (u32)e1; S.winE[q + 2] = (u32)e2; S.winE[q + 3] = (u32)e3; e = e4; j += 4; continue; }
-            if (!v0) break;
-            S.winE[q] = (u32)e; e = e1; j++;
-            if (!v1) break;
-            S.winE[q + 1] = (u32)e; e = e2; j++;
-            if (!v2) break;
-            S.winE[q + 2] = (u32)e; e = e3; j++;
+          if ((e2 >> 1) >= (u32)LZI_WIN) break;                 // (a long run of the careful path can leave the window: the unchecked loads below must not)
+          while (q + 4 <= qMax) {
+            u32 g0, g1, g2, g3;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(g0) : "r"(ka[q] + e2));
+            const u32 e1 = e2 + g0;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(g1) : "r"(ka[q + 1] + e1));
+            const u32 e2b = e1 + g1;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(g2) : "r"(ka[q + 2] + e2b));
+            const u32 e3 = e2b + g2;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(g3) : "r"(ka[q + 3] + e3));
+            const u32 e4 = e3 + g3;
+            if (g0 != 0 && g1 != 0 && g2 != 0 && g3 != 0) { C.winE[q] = e2; C.winE[q + 1] = e1; C.winE[q + 2] = e2b; C.winE[q + 3] = e3; e2 = e4; q += 4; continue; }
+            if (g0 == 0) break;
+            C.winE[q] = e2; e2 = e1; q++;
+            if (g1 == 0) break;
+            C.winE[q] = e2; e2 = e2b; q++;
+            if (g2 == 0) break;
+            C.winE[q] = e2; e2 = e3; q++;
             break;
           }
-          E = (u32)e;
           // one careful step: the group's odd record, the last records of a window, a long run
-          if (j >= jMax) break;
-          const u32 c = wb + S.winK[j - j0] + E;
-          if (c >= wb + LZI_WIN) break;                         // next window
+          if (q >= qMax) break;
+          const u32 cRel = C.winKrel[q] + (e2 >> 1);
+          if (cRel >= (u32)LZI_WIN) break;                      // next window
+          const u32 c = wb + cRel;
           if (c + 4 > lim) { stop = true; break; }
-          u32 g = S.G[c - wb];
-          if (g == 0xFFFFu) {                                   // a literal run of 64 KiB or more
+          u32 g = (u32)C.G[cRel] >> 1;
+          if (g == 0) {                                         // a literal run beyond the table's range
             u32 r = src[c], sz;
-            if (r == 254) { r += ((u32)src[c + 1] << 8) + (u32)src[c + 2]; sz = 3; }
+            if (r < 254) sz = 1;
+            else if (r == 254) { r += ((u32)src[c + 1] << 8) + (u32)src[c + 2]; sz = 3; }
             else { r += ((u32)src[c + 1] << 16) + ((u32)src[c + 2] << 8) + (u32)src[c + 3]; sz = 4; }
             g = 7u + r + sz;
           }
-          S.winE[j - j0] = E;
-          E += g;
-          j++;
+          C.winE[q] = e2;
+          e2 += 2u * g;
+          q++;
         }
+        E = eb + (e2 >> 1);
+        j = j0 + q;
         if (j >= nExtL) stop = true;
         tChase += clock64() - tc;
       }
-      wbOld = wb; pj0 = j0;
+      wbOld = wb; ebOld = eb; pj0 = j0;
     }
-    (void)wbOld;
+    (void)wbOld; (void)ebOld;
     if (tid == 0) { extE[j] = E; H.nExtLValid = j; }
     if (dbg && tid == 0) printf("lzi chase block %d: %d literal records, %d windows, %lld cycles (%lld in the chain)\n", b, nExtL, nWin, clock64() - tStart, tChase);
   }
@@ -389,16 +416,16 @@ __global__ void __launch_bounds__(LZI_TT) lzi_tok_span_kernel(KzgBlock* __restri
   if (!H.valid) return;
   LziLayout Y;
   if (!lzi_layout(blocks[b], P, b, Y)) return;
-  const int base = blockIdx.x * LZI_TT;
-  if (base >= Y.nTokBytes) return;
   const LziArrays A = lzi_arrays(toks, extPool, tilePool, tokStride, tileStride, b);
   const u8* __restrict__ src = blocks[b].cur;
   const int nExtLValid = H.nExtLValid, nExtMValid = H.nExtMValid;
+  for (int tile = blockIdx.x; tile * LZI_TT < Y.nTokBytes; tile += gridDim.x) {
+  const int base = tile * LZI_TT;
   const int t = base + tid;
   const bool on = t < Y.nTokBytes;
   const int token = on ? src[Y.tkBase + t] : 0;
   const LziFlags F = lzi_flags(token, on);
-  const uint4 off = A.tileOff[blockIdx.x];
+  const uint4 off = A.tileOff[tile];
   u32 aOff, cOff;
   lzi_cta_scan2(F.known | (F.nd << 16), ((u32)F.lExt << 16) | (u32)F.mExt, aOff, cOff, S, lane, warp);   // (sums stay below 2^16 per tile)
   const u32 kOff = aOff & 0xFFFFu, ndOff = aOff >> 16;
@@ -455,8 +482,10 @@ __global__ void __launch_bounds__(LZI_TT) lzi_tok_span_kernel(KzgBlock* __restri
     A.T[t] = tk;
   }
   if (tid == 0) {
-    A.tileSpan[blockIdx.x] = make_uint4(S.totA, tile0, tile1, 0u);
+    A.tileSpan[tile] = make_uint4(S.totA, tile0, tile1, 0u);
     if (finished) atomicMin(&H.lastTok, base + lastIdx);
+  }
+  __syncthreads();
   }
 }
 // T6 (one CTA per block): output offset and repeat-offset state at the start of every tile
@@ -501,11 +530,11 @@ __global__ void __launch_bounds__(256) lzi_tok_final_kernel(KzgBlock* __restrict
   LziHdr& H = hdrs[b];
   if (!H.valid) return;
   const int lastTok = H.lastTok;
-  const int t = blockIdx.x * 256 + threadIdx.x;
-  if (lastTok == 0x7FFFFFFF || t > lastTok) return;
+  if (lastTok == 0x7FFFFFFF) return;
   LziLayout Y;
   if (!lzi_layout(blocks[b], P, b, Y)) return;
   const LziArrays A = lzi_arrays(toks, extPool, tilePool, tokStride, tileStride, b);
+  for (int t = blockIdx.x * 256 + threadIdx.x; t <= lastTok; t += gridDim.x * 256) {
   const int tile = t / LZI_TT;
   LziTok tk = A.T[t];
   const uint2 rep = A.tileRep[tile];
@@ -524,6 +553,7 @@ __global__ void __launch_bounds__(256) lzi_tok_final_kernel(KzgBlock* __restrict
   if (t == lastTok) {
     H.nTokRaw = lastTok + 1; H.outLenRaw = (i32)(outPos + tk.litLen + tk.mLen);
     H.okRaw = (tk.litSrc + tk.litLen == (u32)Y.litEnd) ? 1 : 0;                               // `return srcIdx == srcEnd + 13`
+  }
   }
 }
 // T8: commit (a failed check anywhere leaves nTok = 0: inverse returns false, res[0] stays 0)
@@ -544,9 +574,9 @@ __global__ void lzi_tok_commit_kernel(KzgXfParams P, LziHdr* __restrict__ hdrs, 
 //                        inside the tile are resolved there by pointer doubling (no DRAM traffic), literal-resolved bytes are
 //                        gathered and written at once; what is left points before the tile.  The tile's pointers go to
 //                        global memory (targets of later tiles' lookups), plus a per-tile count of open bytes.
-//   lzi_global_kernel  : open tiles only: up to four hops through the global pointer array per round, writing every byte
-//                        whose chain ends (later tiles' chains shorten through the updated pointers: doubling across rounds).
-//   lzi_finish_kernel  : whatever is still open walks its chain to the end.
+//   lzi_global_kernel  : open tiles only: up to 16 hops through the global pointer array (every hop lands on a pointer its own
+//                        tile has already resolved, so a hop crosses a whole tile), writing every byte whose chain ends; a
+//                        second launch walks whatever is still open to the end of its chain.
 #define LZI_TILE 8192
 #define LZI_RT 256                      // threads per resolve CTA
 #define LZI_MAXTOK (LZI_TILE / 4 + 8)   // tokens overlapping a tile: every token but a block's last covers >= minMatch (>= 4) bytes
@@ -669,7 +699,7 @@ __global__ void __launch_bounds__(LZI_RT) lzi_global_kernel(KzgBlock* __restrict
     u32 v[4] = {q.x, q.y, q.z, q.w};
     if ((v[0] & v[1] & v[2] & v[3]) & LZI_LIT) continue;
     u32 p[4] = {v[0], v[1], v[2], v[3]};
-    const int hops = finish ? (1 << 30) : 4;
+    const int hops = finish ? (1 << 30) : 16;
     for (int hop = 0; hop < hops; hop++) {          // the four chains advance together: four independent loads in flight per step
       const bool o0 = !(p[0] & LZI_LIT), o1 = !(p[1] & LZI_LIT), o2 = !(p[2] & LZI_LIT), o3 = !(p[3] & LZI_LIT);
       if (!(o0 | o1 | o2 | o3)) break;
@@ -715,21 +745,22 @@ int kzg_lz_inverse_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, const
   u32* ptrs = (u32*)P.aux32;
   const i64 ptrStride = P.aux32Stride;
   const int tokTiles = (int)((tokStride + LZI_TT - 1) / LZI_TT);
-  const dim3 gT(tokTiles, nBlocks);
+  const dim3 gT(std::min(tokTiles, 96), nBlocks);     // CTAs loop over the token tiles that exist (the count is device-side knowledge)
   lzi_tok_sums_kernel<<<gT, LZI_TT, 0, s>>>(d_blocks, P, toks, tokStride, hdrs, extPool, tilePool, tileStride);
   lzi_tok_scan1_kernel<<<nBlocks, LZI_TT, 0, s>>>(d_blocks, P, toks, tokStride, hdrs, extPool, tilePool, tileStride);
   lzi_tok_extk_kernel<<<gT, LZI_TT, 0, s>>>(d_blocks, P, toks, tokStride, hdrs, extPool, tilePool, tileStride);
-  lzi_tok_chase_kernel<<<nBlocks, LZI_TT, 0, s>>>(d_blocks, P, toks, tokStride, hdrs, extPool, tilePool, tileStride);
-  lzi_tok_span_kernel<<<gT, LZI_TT, 0, s>>>(d_blocks, P, toks, tokStride, hdrs, extPool, tilePool, tileStride);
+  CUDA_TRY(cudaFuncSetAttribute(lzi_tok_chase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LziChaseSmem)));
+  KZG_PROF("lzi_tok_chase_kernel", s, (lzi_tok_chase_kernel<<<nBlocks, LZI_TT, sizeof(LziChaseSmem), s>>>(d_blocks, P, toks, tokStride, hdrs, extPool, tilePool, tileStride)));
+  KZG_PROF("lzi_tok_span_kernel", s, (lzi_tok_span_kernel<<<gT, LZI_TT, 0, s>>>(d_blocks, P, toks, tokStride, hdrs, extPool, tilePool, tileStride)));
   lzi_tok_scan2_kernel<<<nBlocks, LZI_TT, 0, s>>>(d_blocks, P, toks, tokStride, hdrs, extPool, tilePool, tileStride);
-  lzi_tok_final_kernel<<<dim3((int)((tokStride + 255) / 256), nBlocks), 256, 0, s>>>(d_blocks, P, toks, tokStride, hdrs, extPool, tilePool, tileStride);
+  lzi_tok_final_kernel<<<dim3(std::min((int)((tokStride + 255) / 256), 256), nBlocks), 256, 0, s>>>(d_blocks, P, toks, tokStride, hdrs, extPool, tilePool, tileStride);
   lzi_tok_commit_kernel<<<(nBlocks + 63) / 64, 64, 0, s>>>(P, hdrs, nBlocks);
   const int tiles = (maxLen + LZI_TILE - 1) / LZI_TILE;
   int* open = (int*)(tilePool + (size_t)nBlocks * 16 * tileStride);
-  lzi_resolve_kernel<<<dim3(tiles, nBlocks), LZI_RT, 0, s>>>(d_blocks, toks, tokStride, hdrs, ptrs, ptrStride, open, tiles, P.result);
-  for (int r = 0; r < 5; r++) lzi_global_kernel<<<dim3(tiles, nBlocks), LZI_RT, 0, s>>>(d_blocks, hdrs, ptrs, ptrStride, open, tiles, 0);
-  lzi_global_kernel<<<dim3(tiles, nBlocks), LZI_RT, 0, s>>>(d_blocks, hdrs, ptrs, ptrStride, open, tiles, 1);
+  KZG_PROF("lzi_resolve_kernel", s, (lzi_resolve_kernel<<<dim3(tiles, nBlocks), LZI_RT, 0, s>>>(d_blocks, toks, tokStride, hdrs, ptrs, ptrStride, open, tiles, P.result)));
+  KZG_PROF("lzi_global_kernel", s, (lzi_global_kernel<<<dim3(tiles, nBlocks), LZI_RT, 0, s>>>(d_blocks, hdrs, ptrs, ptrStride, open, tiles, 0)));
+  KZG_PROF("lzi_global_kernel", s, (lzi_global_kernel<<<dim3(tiles, nBlocks), LZI_RT, 0, s>>>(d_blocks, hdrs, ptrs, ptrStride, open, tiles, 1)));
   CUDA_TRY(cudaGetLastError());
-  kzg_count_launch(15);
+  kzg_count_launch(11);
   return 0;
 }
