@@ -397,6 +397,17 @@ const char* kzg_profile_json(void) {
     snprintf(buf, sizeof(buf), "%s\"%s\": [%d, %.6f]", i ? ", " : "", agg[i].first.c_str(), agg[i].second.first, agg[i].second.second);
     gProfJson += buf;
   }
+  if (getenv("KZG_TIMELINE") && !gProf.empty()) {       // developer aid: every launch's start / end in ms since the first one
+    gProfJson += ", \"_timeline\": [";
+    for (size_t i = 0; i < gProf.size(); i++) {
+      float a = 0, b = 0;
+      cudaEventElapsedTime(&a, gProf[0].e0, gProf[i].e0); cudaEventElapsedTime(&b, gProf[0].e0, gProf[i].e1);
+      char buf[160];
+      snprintf(buf, sizeof(buf), "%s[\"%s\", %.3f, %.3f]", i ? ", " : "", gProf[i].name, a, b);
+      gProfJson += buf;
+    }
+    gProfJson += "]";
+  }
   gProfJson += "}";
   for (auto& r : gProf) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   gProf.clear();
@@ -1028,7 +1039,7 @@ static int64_t decompress_impl(const uint8_t* d_in, int64_t nBytes, const uint8_
   // Blocks are independent: contiguous groups of them run the whole decode on streams of their own (most urgent first), so
   // that the latency-bound kernels of one group (chunk scan, the literal-record chain) overlap the streaming kernels of the
   // others and, for host buffers, a group's upload / download overlaps the other groups' kernels.
-  static const int gDec = getenv("KZG_DEC_GROUPS") ? std::max(1, std::min(KZG_DEC_MAXG, atoi(getenv("KZG_DEC_GROUPS")))) : 12;   // developer knob
+  const int gDec = getenv("KZG_DEC_GROUPS") ? std::max(1, std::min(KZG_DEC_MAXG, atoi(getenv("KZG_DEC_GROUPS")))) : 12;   // developer knob (read per call)
   const int G = (nBlocks >= 8) ? std::min(gDec, nBlocks / 2) : 1;
   if (G > 1) { r = ws_side_init(); if (r < 0) return r; }
   EvSet ev;

@@ -32,6 +32,7 @@
 #define LZ_MAX_MATCH (65535 + 254 + 4)
 #define LZ_MIN_BLOCK_LENGTH 24
 #define LZF_WT 4096
+#define LZF_FP_LOOKBACK 1024
 #define LZF_WARPS 8
 
 struct LzfBlock {                 // per-block scratch pointers (device)
@@ -60,6 +61,7 @@ struct LzfBlock {                 // per-block scratch pointers (device)
   i32 nFin, giveUpIdx, emitGo, tkBase, mBase, mlBase;
   i32 chkDiff, chkMax, chkFlag;           // per-round verdict of lzf_check_marks_kernel
   i32 direct;                             // the stitcher parsed the whole block itself against a real table (sparse block)
+  i32 fpLookback;                         // how far lzf_prev_kernel looks back through a hash class for an earlier equal fingerprint (0: dense block, flag not needed)
   i32 estHits[8];                         // per eighth of the block: positions whose hash candidate is a match of 4+ bytes (how dense the parse will be)
 };
 struct LzfState { i32 srcIdx, anchor, srcInc, repd0, repd1, repIdx, lastSkip, overLo, overHi; };
@@ -134,7 +136,7 @@ __global__ void lzf_setup_kernel(const KzgBlock* __restrict__ blocks, int nBlock
   L.tkCap = max(count / 5, 256);                                         // tkBuf is never grown (:324-333)
   L.n = L.srcEnd + 2;                                                    // positions 0..srcEnd+1 can be visited or looked up (lazy steps)
   L.segLen = segLen; L.nSeg = max(1, (L.srcEnd + segLen - 1) / segLen);
-  L.nRng = 0; L.aMax = -1; L.active = forceSerial ? 0 : 1; L.needSerial = forceSerial; L.direct = 0; for (int k = 0; k < 8; k++) L.estHits[k] = 0;
+  L.nRng = 0; L.aMax = -1; L.active = forceSerial ? 0 : 1; L.needSerial = forceSerial; L.direct = 0; L.fpLookback = LZF_FP_LOOKBACK; for (int k = 0; k < 8; k++) L.estHits[k] = 0;
 }
 
 template <bool EXTRA>
@@ -273,13 +275,13 @@ __global__ void __launch_bounds__(32 * LZF_WARPS, 3) lzf_scatter_kernel(LzfBlock
 // A position with no earlier occurrence of its 4-byte fingerprint inside its hash class can never pass the 4-byte pre-check
 // (:389-395, :405-422 need bestLen >= 4) whatever the table holds: flagged LZF_NOCAND here by looking back through the class
 // (at most 1024 entries: an unfinished search leaves the flag off, which is always safe).
-#define LZF_FP_LOOKBACK 1024
 __global__ void lzf_prev_kernel(LzfBlock* __restrict__ lb, const int* __restrict__ bmap, int nPass, int hashBits) {
   const LzfBlock& L = lb[bmap[blockIdx.y]];
   const int n = L.n;
   const u64* __restrict__ sorted = (nPass & 1) ? L.kb : L.ka;
   const u64 hmask = ((1ull << hashBits) - 1) << 30;
   const int fpShift = 30 + hashBits;
+  const int lookback = L.fpLookback;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const u64 v = sorted[i];
     const u32 s = (u32)(v & LZF_POSMASK);
@@ -290,7 +292,7 @@ __global__ void lzf_prev_kernel(LzfBlock* __restrict__ lb, const int* __restrict
       const u64 fp = v >> fpShift;
       int j = i - 1;
       for (int steps = 0; ; steps++, j--) {
-        if (steps >= LZF_FP_LOOKBACK) { has = true; break; }
+        if (steps >= lookback) { has = true; break; }
         const u64 w = sorted[j];
         if (((w ^ v) & hmask) != 0) break;
         if ((w >> fpShift) == fp) { has = true; break; }
@@ -1206,8 +1208,12 @@ __global__ void lzf_round_init_kernel(LzfBlock* __restrict__ lb, const int* __re
 }
 
 template <bool EXTRA>
-__global__ void __launch_bounds__(32) lzf_spec_kernel(const KzgBlock* __restrict__ blocks, LzfBlock* __restrict__ lb, const int* __restrict__ bmap) {
-  const int b = bmap[blockIdx.y], s = blockIdx.x, lane = threadIdx.x;
+// One segment per warp, one warp per CTA (72 registers, 28 CTAs per SM).  Measured alternative (round 2): two segments per
+// CTA at <= 48 registers (42+ warps per SM) — every launch got slower by about as much as there were more warps (5-8 ms
+// instead of 3.5-5 ms per group), no gain in throughput: the parse waits on L2 / DRAM round trips that more warps only queue up.
+#define LZF_SPEC_WARPS 1
+__global__ void __launch_bounds__(32 * LZF_SPEC_WARPS) lzf_spec_kernel(const KzgBlock* __restrict__ blocks, LzfBlock* __restrict__ lb, const int* __restrict__ bmap) {
+  const int b = bmap[blockIdx.y], s = blockIdx.x * LZF_SPEC_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   const LzfBlock L = lb[b];
   if (L.n <= 0 || !L.active || s >= L.nSeg) return;
   if (!L.seg[s].rerun) return;                 // its log still stands (no lookup of it resolved differently last round)
@@ -1777,6 +1783,12 @@ __global__ void __launch_bounds__(256) lzf_sample_kernel(const KzgBlock* __restr
   if (threadIdx.x == 0) atomicMin(&key[b], (int)(((long long)dup << 16) / max(len, 1)));
 }
 
+// LZF_NOCAND only pays where lookups walk chains of jumped-over entries, i.e. in sparse blocks; dense blocks skip the search
+__global__ void lzf_lookback_kernel(LzfBlock* __restrict__ lb, const int* __restrict__ key, int nBlocks, int threshold) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < nBlocks) lb[b].fpLookback = (key[b] < threshold) ? LZF_FP_LOOKBACK : 0;
+}
+
 // per-thread pool of side streams for the grouped rounds (created once; the calling thread's codec stream forks into them)
 #define LZF_MAXG 64
 // (LZF_SAMPLES / LZF_SAMPLE: include/.. kzg_transforms.cuh users upload exactly these ranges ahead of the blocks)
@@ -1885,6 +1897,7 @@ int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
     std::vector<int> key(nBlocks, 0x7FFFFFFF);
     CUDA_TRY(cudaMemcpyAsync(dKey, key.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, s));
     lzf_sample_kernel<<<dim3(LZF_SAMPLES, nBlocks), 256, 0, s>>>(d_blocks, dlb, dKey);
+    lzf_lookback_kernel<<<(nBlocks + 63) / 64, 64, 0, s>>>(dlb, dKey, nBlocks, (int)(0.08 * 65536));      // sparsest eighth repeats < 8 % of its sampled 4-grams
     CUDA_TRY(cudaMemcpyAsync(key.data(), dKey, sizeof(int) * nb, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return key[x] < key[y]; });
@@ -1908,8 +1921,8 @@ int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
       if (round > 0) cudaMemsetAsync(dCnt + 2 * g, 0, 2 * sizeof(int), q);
       lzf_round_init_kernel<<<dim3(std::min(gx, 64), cnt), 256, 0, q>>>(dlb, bm, round == 0 ? 1 : 0);
       kzg_prof_begin("lzf_spec_kernel", q);
-      if (extra) lzf_spec_kernel<true><<<dim3(z.maxSeg, cnt), 32, 0, q>>>(d_blocks, dlb, bm);
-      else lzf_spec_kernel<false><<<dim3(z.maxSeg, cnt), 32, 0, q>>>(d_blocks, dlb, bm);
+      if (extra) lzf_spec_kernel<true><<<dim3((z.maxSeg + LZF_SPEC_WARPS - 1) / LZF_SPEC_WARPS, cnt), 32 * LZF_SPEC_WARPS, 0, q>>>(d_blocks, dlb, bm);
+      else lzf_spec_kernel<false><<<dim3((z.maxSeg + LZF_SPEC_WARPS - 1) / LZF_SPEC_WARPS, cnt), 32 * LZF_SPEC_WARPS, 0, q>>>(d_blocks, dlb, bm);
       kzg_prof_end(q);
       kzg_prof_begin("lzf_stitch_kernel", q);
       if (extra) lzf_stitch_kernel<true><<<cnt, 32, 0, q>>>(d_blocks, dlb, bm, dbg);

@@ -746,15 +746,19 @@ int kzg_lz_inverse_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, const
   const i64 ptrStride = P.aux32Stride;
   const int tokTiles = (int)((tokStride + LZI_TT - 1) / LZI_TT);
   const dim3 gT(std::min(tokTiles, 96), nBlocks);     // CTAs loop over the token tiles that exist (the count is device-side knowledge)
-  lzi_tok_sums_kernel<<<gT, LZI_TT, 0, s>>>(d_blocks, P, toks, tokStride, hdrs, extPool, tilePool, tileStride);
-  lzi_tok_scan1_kernel<<<nBlocks, LZI_TT, 0, s>>>(d_blocks, P, toks, tokStride, hdrs, extPool, tilePool, tileStride);
-  lzi_tok_extk_kernel<<<gT, LZI_TT, 0, s>>>(d_blocks, P, toks, tokStride, hdrs, extPool, tilePool, tileStride);
-  CUDA_TRY(cudaFuncSetAttribute(lzi_tok_chase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LziChaseSmem)));
-  KZG_PROF("lzi_tok_chase_kernel", s, (lzi_tok_chase_kernel<<<nBlocks, LZI_TT, sizeof(LziChaseSmem), s>>>(d_blocks, P, toks, tokStride, hdrs, extPool, tilePool, tileStride)));
+  KZG_PROF("lzi_tok_sums_kernel", s, (lzi_tok_sums_kernel<<<gT, LZI_TT, 0, s>>>(d_blocks, P, toks, tokStride, hdrs, extPool, tilePool, tileStride)));
+  KZG_PROF("lzi_tok_scan1_kernel", s, (lzi_tok_scan1_kernel<<<nBlocks, LZI_TT, 0, s>>>(d_blocks, P, toks, tokStride, hdrs, extPool, tilePool, tileStride)));
+  KZG_PROF("lzi_tok_extk_kernel", s, (lzi_tok_extk_kernel<<<gT, LZI_TT, 0, s>>>(d_blocks, P, toks, tokStride, hdrs, extPool, tilePool, tileStride)));
+  // (The chase is one dependent chain per block on one warp: 4.5 ms alone for cfg2's longest block, 7.8 ms when the other block
+  // groups' kernels run next to it.  Asking for 200 KiB of shared memory to keep other CTAs off its SM changed nothing (round 2):
+  // what slows it is the window staging's global loads queueing behind the other groups' traffic, not issue slots.)
+  const int chaseSmem = (int)sizeof(LziChaseSmem);
+  CUDA_TRY(cudaFuncSetAttribute(lzi_tok_chase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, chaseSmem));
+  KZG_PROF("lzi_tok_chase_kernel", s, (lzi_tok_chase_kernel<<<nBlocks, LZI_TT, chaseSmem, s>>>(d_blocks, P, toks, tokStride, hdrs, extPool, tilePool, tileStride)));
   KZG_PROF("lzi_tok_span_kernel", s, (lzi_tok_span_kernel<<<gT, LZI_TT, 0, s>>>(d_blocks, P, toks, tokStride, hdrs, extPool, tilePool, tileStride)));
-  lzi_tok_scan2_kernel<<<nBlocks, LZI_TT, 0, s>>>(d_blocks, P, toks, tokStride, hdrs, extPool, tilePool, tileStride);
-  lzi_tok_final_kernel<<<dim3(std::min((int)((tokStride + 255) / 256), 256), nBlocks), 256, 0, s>>>(d_blocks, P, toks, tokStride, hdrs, extPool, tilePool, tileStride);
-  lzi_tok_commit_kernel<<<(nBlocks + 63) / 64, 64, 0, s>>>(P, hdrs, nBlocks);
+  KZG_PROF("lzi_tok_scan2_kernel", s, (lzi_tok_scan2_kernel<<<nBlocks, LZI_TT, 0, s>>>(d_blocks, P, toks, tokStride, hdrs, extPool, tilePool, tileStride)));
+  KZG_PROF("lzi_tok_final_kernel", s, (lzi_tok_final_kernel<<<dim3(std::min((int)((tokStride + 255) / 256), 256), nBlocks), 256, 0, s>>>(d_blocks, P, toks, tokStride, hdrs, extPool, tilePool, tileStride)));
+  KZG_PROF("lzi_tok_commit_kernel", s, (lzi_tok_commit_kernel<<<(nBlocks + 63) / 64, 64, 0, s>>>(P, hdrs, nBlocks)));
   const int tiles = (maxLen + LZI_TILE - 1) / LZI_TILE;
   int* open = (int*)(tilePool + (size_t)nBlocks * 16 * tileStride);
   KZG_PROF("lzi_resolve_kernel", s, (lzi_resolve_kernel<<<dim3(tiles, nBlocks), LZI_RT, 0, s>>>(d_blocks, toks, tokStride, hdrs, ptrs, ptrStride, open, tiles, P.result)));

@@ -245,6 +245,178 @@ __global__ void __launch_bounds__(32) sbrt_kernel(KzgBlock* __restrict__ blocks,
   if (lane == 0) { res[0] = 1; res[1] = count; }
 }
 
+// ---- SBRT forward, tile-parallel -----------------------------------------------------------------------------------------
+// The list of SBRT is always sorted by (q, time of the last move) descending (a symbol that gets key qc moves above everything
+// with q <= qc, SBRT.java:138-146; q never decreases), with the symbols never seen yet at the bottom in index order.  So the
+// rank the forward transform emits at position i for symbol c is a pure function of every symbol's last two occurrences before
+// i:  rank = #{ d : key_d > key_c },  key = (q << 31) | (last occurrence + 256)  for seen symbols, 255 - d for unseen ones, with
+// q = ((t1 & m1) + (t2 & m2)) >> s of the last occurrence t1 and the one before it t2 (0 if none: `p[]` starts at 0).
+// Three kernels: last two occurrences of every symbol per tile of 4096 positions; a scan over the tiles (one thread per
+// symbol) turns them into every tile's entry state; one warp per tile then replays its 4096 positions from that state, every
+// lane holding 8 of the 256 keys in registers (8 compares + one warp reduction per position).
+#define SBRT_TILE 4096
+__global__ void __launch_bounds__(32) sbrt_fwd_last2_kernel(const KzgBlock* __restrict__ blocks, KzgXfParams P) {
+  __shared__ int l1[256], l2[256];
+  const int lane = threadIdx.x, b = blockIdx.y, tile = blockIdx.x;
+  const KzgBlock& B = blocks[b];
+  if (B.status != 0 || !P.enabled[b]) return;
+  const int count = B.curLen;
+  const int beg = tile * SBRT_TILE;
+  if (beg >= count || count > B.cap) return;
+  const int end = min(beg + SBRT_TILE, count);
+  const u8* __restrict__ src = B.cur;
+  for (int i = lane; i < 256; i += 32) { l1[i] = -1; l2[i] = -1; }
+  __syncwarp();
+  for (int base = beg; base < end; base += 32) {
+    const int p = base + lane;
+    const bool on = p < end;
+    const int c = on ? (int)src[p] : 256 + lane;
+    const u32 peers = __match_any_sync(0xFFFFFFFFu, c);
+    if (on && (peers >> lane) == 1u) {                      // highest lane of its symbol group: the last occurrence of this chunk
+      const u32 below = peers & ((1u << lane) - 1);
+      l2[c] = below ? base + (31 - __clz(below)) : l1[c];
+      l1[c] = p;
+    }
+    __syncwarp();
+  }
+  int* info = reinterpret_cast<int*>(P.scratch + (i64)b * P.scratchStride) + (i64)tile * 512;
+  for (int i = lane; i < 256; i += 32) { info[2 * i] = l1[i]; info[2 * i + 1] = l2[i]; }
+}
+__global__ void __launch_bounds__(256) sbrt_fwd_scan_kernel(const KzgBlock* __restrict__ blocks, KzgXfParams P) {
+  const int b = blockIdx.x, sym = threadIdx.x;
+  const KzgBlock& B = blocks[b];
+  if (B.status != 0 || !P.enabled[b] || B.curLen > B.cap) return;
+  const int nTiles = (B.curLen + SBRT_TILE - 1) / SBRT_TILE;
+  int* info = reinterpret_cast<int*>(P.scratch + (i64)b * P.scratchStride);
+  int t1 = -1, t2 = -1;
+  for (int t = 0; t < nTiles; t++) {
+    int* e = info + (i64)t * 512 + 2 * sym;
+    const int a1 = e[0], a2 = e[1];
+    e[0] = t1; e[1] = t2;                                   // the tile's entry state replaces its own summary
+    if (a1 >= 0) { t2 = (a2 >= 0) ? a2 : t1; t1 = a1; }
+  }
+}
+__global__ void __launch_bounds__(32) sbrt_fwd_rank_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P, int mode) {
+  __shared__ u64 K[256];
+  const int lane = threadIdx.x, b = blockIdx.y, tile = blockIdx.x;
+  KzgBlock& B = blocks[b];
+  int* res = P.result + 2 * b;
+  if (B.status != 0 || !P.enabled[b]) { if (tile == 0 && lane == 0) { res[0] = 0; res[1] = 0; } return; }
+  const int count = B.curLen;
+  if (count > B.cap) { if (tile == 0 && lane == 0) { res[0] = 0; res[1] = 0; } return; }
+  if (tile == 0 && lane == 0) { res[0] = 1; res[1] = count; }
+  const int beg = tile * SBRT_TILE;
+  if (beg >= count) return;
+  const int end = min(beg + SBRT_TILE, count);
+  const u8* __restrict__ src = B.cur;
+  u8* __restrict__ dst = B.alt;
+  const int m1 = (mode == 3) ? 0 : -1, m2 = (mode == 1) ? 0 : -1, s = (mode == 2) ? 1 : 0;
+  const int* info = reinterpret_cast<const int*>(P.scratch + (i64)b * P.scratchStride) + (i64)tile * 512;
+  u64 kr[8];
+  #pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const int d = lane + 32 * k;
+    const int t1 = info[2 * d], t2 = info[2 * d + 1];
+    u64 key = (u64)(255 - d);
+    if (t1 >= 0) { const int q = ((t1 & m1) + (max(t2, 0) & m2)) >> s; key = ((u64)(u32)q << 31) | (u64)(u32)(t1 + 256); }
+    kr[k] = key; K[d] = key;
+  }
+  __syncwarp();
+  for (int base = beg; base < end; base += 32) {
+    const int nIn = min(32, end - base);
+    const int mine = (lane < nIn) ? (int)src[base + lane] : 0;
+    int outv = 0;
+    for (int t = 0; t < nIn; t++) {
+      const int i = base + t;
+      const int c = __shfl_sync(0xFFFFFFFFu, mine, t);
+      const u64 kc = K[c];
+      int cnt = 0;
+      #pragma unroll
+      for (int k = 0; k < 8; k++) cnt += (kr[k] > kc) ? 1 : 0;
+      const int r = (int)__reduce_add_sync(0xFFFFFFFFu, (unsigned)cnt);
+      if (lane == t) outv = r;
+      const u32 low = (u32)(kc & 0x7FFFFFFFull);
+      const int pOld = (low >= 256u) ? (int)(low - 256u) : 0;
+      const int qc = ((i & m1) + (pOld & m2)) >> s;
+      const u64 nk = ((u64)(u32)qc << 31) | (u64)(u32)(i + 256);
+      __syncwarp();
+      if (lane == 0) K[c] = nk;
+      if (lane == (c & 31)) {
+        #pragma unroll
+        for (int k = 0; k < 8; k++) if (k == (c >> 5)) kr[k] = nk;
+      }
+      __syncwarp();
+    }
+    if (lane < nIn) dst[base + lane] = (u8)outv;
+  }
+}
+
+// ---- SBRT inverse: one warp per block (the list state depends on every symbol decoded so far).  The list is kept in rank order
+// (symbol + key per rank); a position costs one round of shared-memory traffic when its rank is below 32.
+__global__ void __launch_bounds__(32) sbrt_inv_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P, int mode) {
+  __shared__ u64 KR[256 + 32];
+  __shared__ u8 r2s[256 + 32];
+  const int lane = threadIdx.x, b = blockIdx.x;
+  KzgBlock& B = blocks[b];
+  int* res = P.result + 2 * b;
+  if (lane == 0) { res[0] = 0; res[1] = 0; }
+  if (B.status != 0 || !P.enabled[b]) return;
+  const int count = B.curLen;
+  const u8* __restrict__ src = B.cur;
+  u8* __restrict__ dst = B.alt;
+  if (count > min(kzg_dst_limit(B, P.dstLimit[b]), B.cap)) return;
+  const int m1 = (mode == 3) ? 0 : -1, m2 = (mode == 1) ? 0 : -1, s = (mode == 2) ? 1 : 0;
+  for (int i = lane; i < 256; i += 32) { KR[i] = (u64)(255 - i); r2s[i] = (u8)i; }
+  __syncwarp();
+  for (int base = 0; base < count; base += 32) {
+    const int nIn = min(32, count - base);
+    const int mine = (lane < nIn) ? (int)src[base + lane] : 0;
+    int outv = 0;
+    for (int t = 0; t < nIn; t++) {
+      const int i = base + t;
+      const int r = __shfl_sync(0xFFFFFFFFu, mine, t);
+      const int c = r2s[r];
+      const u64 kc = KR[r];
+      if (lane == t) outv = c;
+      const u32 low = (u32)(kc & 0x7FFFFFFFull);
+      const int pOld = (low >= 256u) ? (int)(low - 256u) : 0;
+      const int qc = ((i & m1) + (pOld & m2)) >> s;
+      const u64 nk = ((u64)(u32)qc << 31) | (u64)(u32)(i + 256);
+      if (r <= 32) {
+        // entries 0..r-1: how many keep their place (key > nk); the rest move down one slot
+        const u64 kk = (lane < r) ? KR[lane] : 0ull;
+        const int sy = (lane < r) ? (int)r2s[lane] : 0;
+        const int rn = __popc(__ballot_sync(0xFFFFFFFFu, (lane < r) && (kk > nk)));
+        __syncwarp();
+        if (lane >= rn && lane < r) { KR[lane + 1] = kk; r2s[lane + 1] = (u8)sy; }
+        if (lane == 0) { KR[rn] = nk; r2s[rn] = (u8)c; }
+        __syncwarp();
+      } else {
+        int rn = 0;
+        for (int lo = 0; lo < r; lo += 32) {                  // keys descend with the rank: count the ones above nk
+          const int k = lo + lane;
+          const u32 m = __ballot_sync(0xFFFFFFFFu, (k < r) && (KR[k] > nk));
+          rn += __popc(m);
+          if (m != 0xFFFFFFFFu) break;
+        }
+        for (int top = r - 1; top >= rn; top -= 32) {         // entries [rn, r) move down one slot, highest chunk first
+          const int k = top - lane;
+          const bool on = k >= rn;
+          u64 kk = 0; int sy = 0;
+          if (on) { kk = KR[k]; sy = r2s[k]; }
+          __syncwarp();
+          if (on) { KR[k + 1] = kk; r2s[k + 1] = (u8)sy; }
+          __syncwarp();
+        }
+        if (lane == 0) { KR[rn] = nk; r2s[rn] = (u8)c; }
+        __syncwarp();
+      }
+    }
+    if (lane < nIn) dst[base + lane] = (u8)outv;
+  }
+  if (lane == 0) { res[0] = 1; res[1] = count; }
+}
+
 // ================================================================================================================
 // SRT (SRT.java:73-168 forward, 178-257 inverse)
 // ================================================================================================================
@@ -437,7 +609,10 @@ __global__ void __launch_bounds__(32) srt_inverse_kernel(KzgBlock* __restrict__ 
 }
 
 // ---- launchers -------------------------------------------------------------------------------------------------------
-void kzg_small_scratch(int, i32, bool, size_t*, size_t*) {}
+void kzg_small_scratch(int type, i32 maxLen, bool forward, size_t* perBlockBytes, size_t*) {
+  // SBRT forward: per tile of 4096 positions the last two occurrences of every symbol (2 KiB), then the tile's entry state
+  if (forward && (type == KZG_T_RANK || type == KZG_T_MTFT)) *perBlockBytes = std::max(*perBlockBytes, ((size_t)maxLen / SBRT_TILE + 2) * 2048);
+}
 
 int kzg_zrlt_launch(cudaStream_t s, bool forward, KzgBlock* d_blocks, int nBlocks, const KzgXfParams& P) {
   if (forward) zrlt_forward_kernel<<<nBlocks, 32, 0, s>>>(d_blocks, P);
@@ -446,9 +621,15 @@ int kzg_zrlt_launch(cudaStream_t s, bool forward, KzgBlock* d_blocks, int nBlock
   kzg_count_launch(1);
   return 0;
 }
-int kzg_sbrt_launch(cudaStream_t s, bool forward, int mode, KzgBlock* d_blocks, int nBlocks, const KzgXfParams& P) {
-  if (forward) sbrt_kernel<true><<<nBlocks, 32, 0, s>>>(d_blocks, P, mode);
-  else sbrt_kernel<false><<<nBlocks, 32, 0, s>>>(d_blocks, P, mode);
+int kzg_sbrt_launch(cudaStream_t s, bool forward, int mode, KzgBlock* d_blocks, int nBlocks, const KzgXfParams& P, i32 maxLen) {
+  if (forward) {
+    const int tiles = (maxLen + SBRT_TILE - 1) / SBRT_TILE;
+    if (((size_t)maxLen / SBRT_TILE + 2) * 2048 > (size_t)P.scratchStride) { kzg_set_error("sbrt: scratch pool too small"); return -KZG_ERR_CREATE_CODEC; }
+    KZG_PROF("sbrt_fwd_last2_kernel", s, (sbrt_fwd_last2_kernel<<<dim3(tiles, nBlocks), 32, 0, s>>>(d_blocks, P)));
+    KZG_PROF("sbrt_fwd_scan_kernel", s, (sbrt_fwd_scan_kernel<<<nBlocks, 256, 0, s>>>(d_blocks, P)));
+    KZG_PROF("sbrt_fwd_rank_kernel", s, (sbrt_fwd_rank_kernel<<<dim3(tiles, nBlocks), 32, 0, s>>>(d_blocks, P, mode)));
+    kzg_count_launch(2);
+  } else KZG_PROF("sbrt_inv_kernel", s, (sbrt_inv_kernel<<<nBlocks, 32, 0, s>>>(d_blocks, P, mode)));
   CUDA_TRY(cudaGetLastError());
   kzg_count_launch(1);
   return 0;

@@ -22,8 +22,9 @@ static int T = 16, NB = 32, BS = 1 << 20, XF = KZG_T_LZ, ENT = KZG_E_ANS0;
 static uint8_t *data, *enc, *back;
 static int64_t* encBits; static int32_t* xfLen; static int* xfOk;
 static size_t encStride;
-static int failures = 0;
 static pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
+static int failures = 0, failKind[6] = {0, 0, 0, 0, 0, 0}, firstCode = 0; static char firstErr[256] = "";
+static void fail(int kind, int code) { pthread_mutex_lock(&mu); failures++; failKind[kind]++; if (!firstCode) { firstCode = code ? code : -999; snprintf(firstErr, sizeof(firstErr), "kind %d code %d: %s", kind, code, kzg_last_error()); } pthread_mutex_unlock(&mu); }
 static pthread_barrier_t bar;
 static double tEnc, tDec;
 
@@ -63,11 +64,11 @@ static void* worker(void* arg) {
     int r = kzg_transform_forward(XF, &ctx, in, BS, buf, cap, cap, &su, &du);
     const uint8_t* payload = in; int32_t plen = BS;
     if (r == 1) { payload = buf; plen = du; }             /* r == 0: Sequence keeps the block untransformed (skip flag) */
-    else if (r < 0) { pthread_mutex_lock(&mu); failures++; pthread_mutex_unlock(&mu); continue; }
+    else if (r < 0) { fail(0, r); continue; }
     xfOk[b] = (r == 1); xfLen[b] = plen;
     int64_t bits = 0;
     const int64_t e = kzg_entropy_encode(ENT, &ctx, payload, plen, enc + (size_t)b * encStride, (int64_t)encStride, &bits);
-    if (e != plen) { pthread_mutex_lock(&mu); failures++; pthread_mutex_unlock(&mu); continue; }
+    if (e != plen) { fail(1, (int)e); continue; }
     encBits[b] = bits;
   }
   pthread_barrier_wait(&bar);
@@ -76,14 +77,15 @@ static void* worker(void* arg) {
     kzg_ctx ctx = {7, BS, BS, 1, 0, 0};
     int64_t used = 0;
     const int32_t d = kzg_entropy_decode(ENT, &ctx, enc + (size_t)b * encStride, encBits[b], &used, tmp, xfLen[b]);
-    int ok = (d == xfLen[b]) && (used == encBits[b]);
+    if (d != xfLen[b]) { fail(2, d); continue; }
+    if (used != encBits[b]) { fail(3, (int)(used - encBits[b])); continue; }
     uint8_t* out = back + (size_t)b * BS;
-    if (ok && xfOk[b]) {
+    if (xfOk[b]) {
       int32_t su = 0, du = 0;
-      const int r = kzg_transform_inverse(XF, &ctx, tmp, xfLen[b], out, BS + 512 < cap ? BS + 512 : cap, cap, &su, &du);
-      ok = (r == 1) && (du == BS);
-    } else if (ok) memcpy(out, tmp, BS);
-    if (!ok || memcmp(out, data + (size_t)b * BS, BS) != 0) { pthread_mutex_lock(&mu); failures++; pthread_mutex_unlock(&mu); }
+      const int r = kzg_transform_inverse(XF, &ctx, tmp, xfLen[b], out, BS, BS, &su, &du);
+      if (r != 1 || du != BS) { fail(4, r); continue; }
+    } else memcpy(out, tmp, BS);
+    if (memcmp(out, data + (size_t)b * BS, BS) != 0) fail(5, 0);
   }
   pthread_barrier_wait(&bar);
   const double t2 = now();
@@ -130,10 +132,10 @@ int main(int argc, char** argv) {
   int64_t encSum2 = 0; for (int b = 0; b < NB; b++) encSum2 += encBits[b];
   kzg_set_coalescing(0, 0);
   const int same = encSum == encSum2;
-  printf("{\"threads\": %d, \"blocks\": %d, \"block_bytes\": %d, \"transform\": %d, \"entropy\": %d, \"failures\": %d, \"coalesced_bits_equal\": %s, "
+  printf("{\"threads\": %d, \"blocks\": %d, \"block_bytes\": %d, \"transform\": %d, \"entropy\": %d, \"failures\": %d, \"fail_kinds\": [%d, %d, %d, %d, %d, %d], \"first_error\": \"%s\", \"coalesced_bits_equal\": %s, "
          "\"per_block\": {\"encode_MBps\": %.1f, \"decode_MBps\": %.1f, \"MBps\": %.1f}, "
          "\"coalesced\": {\"max_batch\": %d, \"window_us\": %d, \"encode_MBps\": %.1f, \"decode_MBps\": %.1f, \"MBps\": %.1f, \"requests\": %lld, \"batches\": %lld}, \"ratio\": %.3f}\n",
-         T, NB, BS, XF, ENT, failures, same ? "true" : "false", e0, d0, 1.0 / (1.0 / e0 + 1.0 / d0),
+         T, NB, BS, XF, ENT, failures, failKind[0], failKind[1], failKind[2], failKind[3], failKind[4], failKind[5], firstErr, same ? "true" : "false", e0, d0, 1.0 / (1.0 / e0 + 1.0 / d0),
          maxBatch, window, e1, d1, 1.0 / (1.0 / e1 + 1.0 / d1), (long long)(r1 - r0), (long long)(b1 - b0), (double)NB * BS * 8.0 / (double)(encSum ? encSum : 1));
   return (failures == 0 && same) ? 0 : 1;
 }
