@@ -54,6 +54,11 @@ typedef struct kzg_ctx {
   int32_t flags;
 } kzg_ctx;
 #define KZG_FLAG_BWT_ASREF 1
+/* kzg_compress* only: per-block checksum of the original bytes, ctx["checksum"] = 32 / 64 (CompressedOutputStream.java:193-204,
+ * 745-755): K/util/hash/XXHash32.java (the published XXH32) / XXHash64.java (Kanzi's variant), seed 0x4B414E5A.  kzg_decompress*
+ * reads the kind from the stream header and verifies every block (-KZG_ERR_CRC_CHECK on a mismatch). */
+#define KZG_FLAG_XXH32 2
+#define KZG_FLAG_XXH64 4
 
 /* ---- library ---------------------------------------------------------------------------------- */
 int kzg_abi_version(void);
@@ -107,7 +112,7 @@ int64_t kzg_coalescing_stats(int64_t* batches);
  * consume (COS:236-313,733-1054; CIS:359-515,1025-1378) for `nTransforms` chained ids + one entropy id,
  * with every block of the input in flight at once on the calling thread's device.  Host buffers.
  * kzg_compress: returns the .knz byte length (<0 on error).  kzg_decompress: returns decoded bytes.
- * checksum kinds are not supported (-KZG_ERR_INVALID_PARAM).  flags as kzg_ctx.flags.
+ * flags: KZG_FLAG_BWT_ASREF | KZG_FLAG_XXH32 / KZG_FLAG_XXH64.
  * Capacities: kzg_compress needs outCap >= kzg_compress_bound(n, blockSize) to be sure of success (a smaller buffer
  * fails with -KZG_ERR_WRITE_FILE only if the stream really does not fit).  kzg_decompress needs outCap >= the decoded size
  * and never writes beyond `out + outCap`: every block but the last decodes to blockSize bytes, the last to what is left

@@ -5,7 +5,7 @@ There is no CPU fallback: importing works anywhere, every compute call needs a C
 import os as _os
 # up to 32 block groups run on streams of their own (csrc/lz_forward2.cu); must be set before the CUDA context exists
 _os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
-from .binding import (lib, KzgError, T, E, DT, FLAG_BWT_ASREF, device_count, set_device, last_error, launch_count,
+from .binding import (lib, KzgError, T, E, DT, FLAG_BWT_ASREF, FLAG_XXH32, FLAG_XXH64, device_count, set_device, last_error, launch_count,
                       transform_forward, transform_inverse, transform_max_encoded_len, bwt_forward, bwt_inverse,
                       entropy_encode, entropy_decode, compress, decompress, compress_bound, last_block_bits, stream_index)
 from .interfaces import SliceByteArray, ByteTransform, EntropyEncoder, EntropyDecoder, OutputBitStream, InputBitStream, \

@@ -12,6 +12,8 @@ T = dict(NONE=0, BWT=1, LZ=3, ZRLT=6, MTFT=7, RANK=8, ROLZ=11, SRT=13, LZX=16)
 E = dict(NONE=0, HUFFMAN=1, FPAQ=2, ANS0=5, ANS1=8)
 DT = dict(UNDEFINED=0, TEXT=1, MULTIMEDIA=2, EXE=3, NUMERIC=4, BASE64=5, DNA=6, BIN=7, UTF8=8, SMALL_ALPHABET=9)
 FLAG_BWT_ASREF = 1
+FLAG_XXH32 = 2          # per-block XXHash32 of the original bytes (-x 32)
+FLAG_XXH64 = 4          # per-block XXHash64, Kanzi's variant (-x 64)
 ERR_NO_DEVICE = 126
 
 u8p = C.POINTER(C.c_uint8)

@@ -36,6 +36,79 @@ __global__ void kzg_commit_kernel(KzgBlock* __restrict__ blocks, int nBlocks, co
   }
 }
 
+// ---- block checksums: K/util/hash/XXHash32.java:94-142 (the published XXH32) and K/util/hash/XXHash64.java (Kanzi's own variant:
+// the accumulators are folded with `(v << 1) | (v >>> 31)` on 64-bit values, :127-128), seed = 0x4B414E5A (COS:195-200).
+// The four accumulators are four dependent chains over the block: lanes 0-3 run one each, lane 0 finishes.  verify == 0:
+// hash B.aux0[0, origLen) into B.xxh (encode: the original bytes); verify != 0: hash the decoded block and compare (CIS:1348-1370).
+__device__ __forceinline__ u32 xxh32_round(u32 acc, u32 val) { acc += val * 2246822519u; return ((acc << 13) | (acc >> 19)) * 2654435761u; }
+__device__ __forceinline__ u64 xxh64_round(u64 acc, u64 val) { acc += val * 0xC2B2AE3D27D4EB4Full; return ((acc << 31) | (acc >> 33)) * 0x9E3779B185EBCA87ull; }
+__device__ __forceinline__ u64 xxh64_merge(u64 acc, u64 val) { acc ^= xxh64_round(0, val); return acc * 0x9E3779B185EBCA87ull + 0x85EBCA77C2B2AE63ull; }
+__global__ void __launch_bounds__(32) kzg_xxh_kernel(KzgBlock* __restrict__ blocks, int verify) {
+  const int b = blockIdx.x, lane = threadIdx.x;
+  KzgBlock& B = blocks[b];
+  if (B.status != 0 || B.chkBytes == 0) return;
+  const u8* __restrict__ data = verify ? B.cur : B.aux0;
+  const int length = verify ? B.curLen : B.origLen;
+  const u32 SEED = 0x4B414E5Au;
+  u64 h = 0;
+  int idx = 0;
+  if (B.chkBytes == 4) {
+    const u32 P1 = 2654435761u, P2 = 2246822519u, P3 = 3266489917u, P4 = 668265263u, P5 = 374761393u;
+    u32 h32;
+    if (length >= 16) {
+      const int stripes = length >> 4;
+      u32 v = (lane == 0) ? SEED + P1 + P2 : ((lane == 1) ? SEED + P2 : ((lane == 2) ? SEED : SEED - P1));
+      if (lane < 4) {
+        const u8* p = data + 4 * lane;
+        if ((reinterpret_cast<uintptr_t>(data) & 3) == 0) { const u32* q = reinterpret_cast<const u32*>(p); for (int s = 0; s < stripes; s++) v = xxh32_round(v, q[4 * s]); }
+        else for (int s = 0; s < stripes; s++) { const u8* x = p + 16 * s; v = xxh32_round(v, (u32)x[0] | ((u32)x[1] << 8) | ((u32)x[2] << 16) | ((u32)x[3] << 24)); }
+      }
+      const u32 v1 = __shfl_sync(0xFFFFFFFFu, v, 0), v2 = __shfl_sync(0xFFFFFFFFu, v, 1), v3 = __shfl_sync(0xFFFFFFFFu, v, 2), v4 = __shfl_sync(0xFFFFFFFFu, v, 3);
+      h32 = ((v1 << 1) | (v1 >> 31)) + ((v2 << 7) | (v2 >> 25)) + ((v3 << 12) | (v3 >> 20)) + ((v4 << 18) | (v4 >> 14));
+      idx = stripes << 4;
+    } else h32 = SEED + P5;
+    if (lane != 0) return;
+    h32 += (u32)length;
+    while (idx <= length - 4) { const u8* x = data + idx; h32 += ((u32)x[0] | ((u32)x[1] << 8) | ((u32)x[2] << 16) | ((u32)x[3] << 24)) * P3; h32 = ((h32 << 17) | (h32 >> 15)) * P4; idx += 4; }
+    while (idx < length) { h32 += (u32)data[idx] * P5; h32 = ((h32 << 11) | (h32 >> 21)) * P1; idx++; }
+    h32 ^= h32 >> 15; h32 *= P2; h32 ^= h32 >> 13; h32 *= P3;
+    h = (u64)(h32 ^ (h32 >> 16));
+  } else {
+    const u64 P1 = 0x9E3779B185EBCA87ull, P2 = 0xC2B2AE3D27D4EB4Full, P3 = 0x165667B19E3779F9ull, P4 = 0x85EBCA77C2B2AE63ull, P5 = 0x27D4EB2F165667C5ull;
+    const u64 S64 = (u64)SEED;
+    u64 h64;
+    auto ld64 = [&](const u8* x) { u64 r = 0; for (int i = 7; i >= 0; i--) r = (r << 8) | x[i]; return r; };
+    if (length >= 32) {
+      const int stripes = length >> 5;
+      u64 v = (lane == 0) ? S64 + P1 + P2 : ((lane == 1) ? S64 + P2 : ((lane == 2) ? S64 : S64 - P1));
+      if (lane < 4) {
+        const u8* p = data + 8 * lane;
+        if ((reinterpret_cast<uintptr_t>(data) & 7) == 0) { const u64* q = reinterpret_cast<const u64*>(p); for (int s = 0; s < stripes; s++) v = xxh64_round(v, q[4 * s]); }
+        else for (int s = 0; s < stripes; s++) v = xxh64_round(v, ld64(p + 32 * s));
+      }
+      const u64 v1 = __shfl_sync(0xFFFFFFFFu, v, 0), v2 = __shfl_sync(0xFFFFFFFFu, v, 1), v3 = __shfl_sync(0xFFFFFFFFu, v, 2), v4 = __shfl_sync(0xFFFFFFFFu, v, 3);
+      h64 = ((v1 << 1) | (v1 >> 31)) + ((v2 << 7) | (v2 >> 25)) + ((v3 << 12) | (v3 >> 20)) + ((v4 << 18) | (v4 >> 14));      // as written (XXHash64.java:127-128)
+      h64 = xxh64_merge(h64, v1); h64 = xxh64_merge(h64, v2); h64 = xxh64_merge(h64, v3); h64 = xxh64_merge(h64, v4);
+      idx = stripes << 5;
+    } else h64 = S64 + P5;
+    if (lane != 0) return;
+    h64 += (u64)(i64)length;
+    while (idx + 8 <= length) { h64 ^= xxh64_round(0, ld64(data + idx)); h64 = ((h64 << 27) | (h64 >> 37)) * P1 + P4; idx += 8; }
+    while (idx + 4 <= length) { const u8* x = data + idx; const i32 w = (i32)((u32)x[0] | ((u32)x[1] << 8) | ((u32)x[2] << 16) | ((u32)x[3] << 24)); h64 ^= (u64)(i64)w * P1; h64 = ((h64 << 23) | (h64 >> 41)) * P2 + P3; idx += 4; }
+    while (idx < length) { h64 ^= (u64)data[idx] * P5; h64 = ((h64 << 11) | (h64 >> 53)) * P1; idx++; }
+    h64 ^= h64 >> 33; h64 *= P2; h64 ^= h64 >> 29; h64 *= P3;
+    h = h64 ^ (h64 >> 32);
+  }
+  if (!verify) B.xxh = h;
+  else if (h != B.xxh) B.status = -KZG_ERR_CRC_CHECK;       // "Corrupted bitstream: invalid checksum" (CIS:1352-1370)
+}
+int kzg_xxh_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, int verify) {
+  KZG_PROF("kzg_xxh_kernel", s, (kzg_xxh_kernel<<<nBlocks, 32, 0, s>>>(d_blocks, verify)));
+  CUDA_TRY(cudaGetLastError());
+  kzg_count_launch(1);
+  return 0;
+}
+
 // ---- per-block record layout (one warp per block) --------------------------------------------------------------
 // scans the block's chunk segments (relative bit offsets), decides the transformed-copy fallback
 // (COS:926-973) and builds the block header bytes + checksum (COS:861-896, 977-985).
@@ -80,7 +153,8 @@ __global__ void __launch_bounds__(32) kzg_block_layout_kernel(KzgBlock* __restri
   } else {
     mode |= 0x10; skipByte = true;
   }
-  int hb = 1 + (skipByte ? 1 : 0) + dataSize + 1;
+  const int chk = B.chkBytes;                     // XXHash32 / 64 of the original bytes follows the header checksum (COS:892-895)
+  int hb = 1 + (skipByte ? 1 : 0) + dataSize + 1 + chk;
   i64 written = (i64)hb * 8 + (i64)running;
   if (!(mode & 0x80)) {
     const i64 entropyPayloadBytes = (written + 7) >> 3;
@@ -88,7 +162,7 @@ __global__ void __launch_bounds__(32) kzg_block_layout_kernel(KzgBlock* __restri
       mode |= 0x80 | 0x10;
       skipByte = (nbFunctions > 4);
       headerSkipFlags = skipByte ? skipFlags : (((mode << 4) | 0x0F) & 0xFF);
-      hb = 1 + (skipByte ? 1 : 0) + dataSize + 1;
+      hb = 1 + (skipByte ? 1 : 0) + dataSize + 1 + chk;
       S[0] = KzgSeg{B.cur, 0, 0, (u64)post * 8};
       for (int i = 1; i < segsPerBlock; i++) S[i].nBits = 0;
       written = (i64)hb * 8 + (i64)post * 8;
@@ -101,12 +175,13 @@ __global__ void __launch_bounds__(32) kzg_block_layout_kernel(KzgBlock* __restri
   ck = kzg_mix32(ck, 0x1E35A7BDu, (u32)((u64)written >> 32));
   ck = kzg_mix32(ck, 0x1E35A7BDu, (u32)written);
   ck = (ck >> 23) ^ (ck >> 3);
-  u8* h = hdrBytes + b * 8;
+  u8* h = hdrBytes + b * KZG_HDR_STRIDE;
   int k = 0;
   h[k++] = (u8)mode;
   if (skipByte) h[k++] = (u8)skipFlags;
   for (int i = dataSize - 1; i >= 0; i--) h[k++] = (u8)(post >> (8 * i));
   h[k++] = (u8)ck;
+  for (int i = chk - 1; i >= 0; i--) h[k++] = (u8)(B.xxh >> (8 * i));
   B.mode = mode & 0xFF; B.hdrBytes = hb; B.written = written;
 }
 
@@ -145,7 +220,7 @@ __global__ void __launch_bounds__(32) kzg_stream_layout_kernel(KzgBlock* __restr
       put_bits_atomic(dst32, start, (u64)(lw - 3), 5);
       put_bits_atomic(dst32, start + 5, (u64)written, lw);
       const u64 p0 = start + 5 + lw;
-      const u8* h = hdrBytes + b * 8;
+      const u8* h = hdrBytes + b * KZG_HDR_STRIDE;
       const int hb = blocks[b].hdrBytes;
       for (int i = 0; i < hb; i++) put_bits_atomic(dst32, p0 + 8 * i, h[i], 8);
       blocks[b].srcBit = (i64)(p0 + 8ull * hb);      // where this block's entropy payload goes

@@ -536,7 +536,7 @@ static int entropy_encode_batch(std::vector<KzgReq*>& rq) {
   u8* dIn = dalloc<u8>(nl * cap); u8* dOut = dalloc<u8>(nl * outBytes);
   u8* dHdr = dalloc<u8>(nl * es.maxChunks * es.hdrStride + 16); u8* dPay = dalloc<u8>(nl * es.maxChunks * es.payStride + 16);
   u32* dTab = dalloc<u32>(nl * es.maxChunks * es.tabStride + 4); KzgSeg* dSegs = dalloc<KzgSeg>(nl * es.segsPerBlock);
-  u8* dHdrBytes = dalloc<u8>(nl * 8 + 16); i64* dTotal = dalloc<i64>(2);
+  u8* dHdrBytes = dalloc<u8>(nl * KZG_HDR_STRIDE + 16); i64* dTotal = dalloc<i64>(2);
   if (!bt.hBlocks || !bt.dBlocks || !dIn || !dOut || !dHdr || !dPay || !dTab || !dSegs || !dHdrBytes || !dTotal) return failAll(-KZG_ERR_CREATE_CODEC);
   auto cu = [&](cudaError_t e) { if (e != cudaSuccess) { kzg_set_error("entropy batch: %s", cudaGetErrorString(e)); cudaGetLastError(); return false; } return true; };
   for (size_t k = 0; k < nl; k++) {
@@ -730,12 +730,12 @@ int32_t kzg_entropy_decode(int type, kzg_ctx* ctx, const uint8_t* in, int64_t in
 
 // ---- whole streams ------------------------------------------------------------------------------------------------
 // stream header, COS:236-313 (checksum kind 0).  Returns header byte count (whole bytes: 160 + 16*szMask bits).
-static int stream_header(u8* h, int entropy, u64 transformType, i32 blockSize, i64 inputSize) {
+static int stream_header(u8* h, int entropy, u64 transformType, i32 blockSize, i64 inputSize, int chkKind) {
   u64 acc = 0; int nacc = 0, nb = 0;
   auto put = [&](u64 v, int n) {
     for (int i = n - 1; i >= 0; i--) { acc = (acc << 1) | ((v >> i) & 1); if (++nacc == 8) { h[nb++] = (u8)acc; acc = 0; nacc = 0; } }
   };
-  put(0x4B414E5A, 32); put(7, 4); put(0, 2); put((u64)entropy, 5); put(transformType, 48); put((u64)((u32)blockSize >> 4), 28);
+  put(0x4B414E5A, 32); put(7, 4); put((u64)chkKind, 2); put((u64)entropy, 5); put(transformType, 48); put((u64)((u32)blockSize >> 4), 28);
   int szMask = 0;
   if (inputSize != 0 && inputSize < (1LL << 48)) {
     if (inputSize >= (1LL << 32)) szMask = 3;
@@ -751,7 +751,7 @@ static int stream_header(u8* h, int entropy, u64 transformType, i32 blockSize, i
   put(0, 15);
   const u32 HASH = 0x1E35A7BDu;
   u32 c = HASH * (0x01030507u * 7u);
-  c = kzg_mix32(c, HASH, 0);
+  c = kzg_mix32(c, HASH, (u32)chkKind);
   c = kzg_mix32(c, HASH, (u32)entropy);
   c = kzg_mix32(c, HASH, (u32)(transformType >> 32));
   c = kzg_mix32(c, HASH, (u32)transformType);
@@ -786,7 +786,9 @@ static int64_t compress_impl(const uint8_t* d_in, int64_t n, const int32_t* tran
                 nb * (size_t)es.maxChunks * (es.hdrStride + es.payStride + es.tabStride * 4) + nb * (size_t)es.segsPerBlock * sizeof(KzgSeg) + (1 << 20);
   r = ws_reserve(need, nb * (sizeof(KzgBlock) + 32) + 8192); if (r < 0) return r;
   u8 hdr[64];
-  const int hdrLen = stream_header(hdr, entropy, transformType, blockSize, n);
+  if ((flags & KZG_FLAG_XXH32) && (flags & KZG_FLAG_XXH64)) return -KZG_ERR_INVALID_PARAM;
+  const int chkBytes = (flags & KZG_FLAG_XXH32) ? 4 : ((flags & KZG_FLAG_XXH64) ? 8 : 0);       // ctx["checksum"] 32 / 64 (COS:193-204)
+  const int hdrLen = stream_header(hdr, entropy, transformType, blockSize, n, chkBytes / 4);
   if (outCap < hdrLen + 2) return -KZG_ERR_WRITE_FILE;
   EvSet ev;
   if (timing3) { r = ev.create(4); if (r < 0) return r; }
@@ -825,7 +827,7 @@ static int64_t compress_impl(const uint8_t* d_in, int64_t n, const int32_t* tran
     u8* dPay = dalloc<u8>(nb * es.maxChunks * es.payStride + 16); NN(dPay);
     u32* dTab = dalloc<u32>(nb * es.maxChunks * es.tabStride + 4); NN(dTab);
     KzgSeg* dSegs = dalloc<KzgSeg>(nb * es.segsPerBlock); NN(dSegs);
-    u8* dHdrBytes = dalloc<u8>(nb * 8 + 16); NN(dHdrBytes);
+    u8* dHdrBytes = dalloc<u8>(nb * KZG_HDR_STRIDE + 16); NN(dHdrBytes);
     i64* dTotal = dalloc<i64>(2); NN(dTotal);
     for (int b = 0; b < nBlocks; b++) {
       KzgBlock& B = bt.hBlocks[b];
@@ -834,7 +836,7 @@ static int64_t compress_impl(const uint8_t* d_in, int64_t n, const int32_t* tran
       const i32 len = (i32)std::min<i64>(blockSize, n - off);
       B.cur = (u8*)d_in + off; B.aux0 = B.cur;
       B.alt = dA ? dA + (size_t)b * cap : nullptr; B.aux1 = dB ? dB + (size_t)b * cap : B.alt;
-      B.curLen = len; B.cap = (i32)cap - 64; B.origLen = len; B.skipFlags = 0xFF; B.entropy = entropy;
+      B.curLen = len; B.cap = (i32)cap - 64; B.origLen = len; B.skipFlags = 0xFF; B.entropy = entropy; B.chkBytes = chkBytes;
       const bool small = len <= 15;                             // COS:764-767: raw copy block
       if (small) { B.mode = 0x80; B.entropy = KZG_E_NONE; B.skipFlags = 0x7F; }   // NONE&NONE copy block: its NullTransform "succeeds" (COS:764-767, 792-817)
       bt.hEnabled[b] = small ? 0 : 1;
@@ -849,6 +851,14 @@ static int64_t compress_impl(const uint8_t* d_in, int64_t n, const int32_t* tran
     if (timing3) CUDA_TRY(cudaEventRecord(ev[0], W.stream));
     // ctx["dataType"] from the block's magic number (COS:795-804)
     r = kzg_magic_launch(W.stream, bt.dBlocks, nBlocks); if (r < 0) return r;
+    if (chkBytes) {       // block checksums of the original bytes (COS:745-755): four dependent chains per block, on a stream of their own next to the transforms
+      if (lazyIn) CUDA_TRY(cudaMemcpyAsync((u8*)d_in, h_in, (size_t)n, cudaMemcpyHostToDevice, W.stream));      // (the hash needs the whole input now; the LZ stage's own uploads then rewrite the same bytes)
+      r = ws_side_init(); if (r < 0) return r;
+      CUDA_TRY(cudaEventRecord(W.sideEv[KZG_DEC_MAXG], W.stream));
+      CUDA_TRY(cudaStreamWaitEvent(W.side[0], W.sideEv[KZG_DEC_MAXG], 0));
+      r = kzg_xxh_launch(W.side[0], bt.dBlocks, nBlocks, 0); if (r < 0) return r;
+      CUDA_TRY(cudaEventRecord(W.sideEv[0], W.side[0]));
+    }
     // Sequence.forward: a NONE-only chain is a copy that always succeeds (NullTransform) -> skip bit 7 cleared
     for (int i = 0; i < nf; i++) {
       if (fn[i] == KZG_T_NONE) { r = kzg_null_forward_launch(W.stream, bt.dBlocks, nBlocks, bt.dEnabled, i); if (r < 0) return r; continue; }
@@ -857,6 +867,7 @@ static int64_t compress_impl(const uint8_t* d_in, int64_t n, const int32_t* tran
     if (timing3) CUDA_TRY(cudaEventRecord(ev[1], W.stream));
     r = run_entropy_encode(bt, entropy, es, dHdr, dPay, dTab, dSegs); if (r < 0) return r;
     if (timing3) CUDA_TRY(cudaEventRecord(ev[2], W.stream));
+    if (chkBytes) CUDA_TRY(cudaStreamWaitEvent(W.stream, W.sideEv[0], 0));
     r = kzg_assemble_launch(W.stream, bt.dBlocks, nBlocks, dSegs, es.segsPerBlock, dHdrBytes, nf, 1, d_out, (i64)hdrLen * 8, dTotal, outCap - 8);
     if (r < 0) return r;
     if (timing3) CUDA_TRY(cudaEventRecord(ev[3], W.stream));
@@ -911,7 +922,8 @@ static int64_t decompress_impl(const uint8_t* d_in, int64_t nBytes, const uint8_
   const int bsVersion = (int)hb.read(4);
   if (bsVersion != 7) { kzg_set_error("bitstream version %d not supported (7 only)", bsVersion); return -KZG_ERR_STREAM_VERSION; }
   const int chkSize = (int)hb.read(2);
-  if (chkSize != 0) { kzg_set_error("block checksums not supported"); return -KZG_ERR_INVALID_PARAM; }
+  if (chkSize == 3) { kzg_set_error("Invalid bitstream, incorrect block checksum size"); return -KZG_ERR_INVALID_FILE; }
+  const int chkBytes = 4 * chkSize;                 // 1 = XXHash32, 2 = XXHash64 (CIS:382-395)
   const int entropy = (int)hb.read(5);
   const u64 transformType = hb.read(48);
   const i32 blockSize = (i32)(hb.read(28) << 4);
@@ -937,7 +949,7 @@ static int64_t decompress_impl(const uint8_t* d_in, int64_t nBytes, const uint8_
   int fn[8]; const int nf = seq_functions(tr, 8, fn);
 
   // walk the block records
-  struct Rec { i64 payBit, payBits; i32 preLen; int skipFlags; int entropy; bool rawCopy; };
+  struct Rec { i64 payBit, payBits; i32 preLen; int skipFlags; int entropy; bool rawCopy; u64 xxh; };
   std::vector<Rec> recs;
   const i32 maxTransformLength = std::min(std::max(blockSize + blockSize / 2, 2048), 1 << 30);
   while (true) {
@@ -968,10 +980,12 @@ static int64_t decompress_impl(const uint8_t* d_in, int64_t nBytes, const uint8_
     c = (c >> 23) ^ (c >> 3);
     if (hb.bad || hck != (c & 0xFF)) { kzg_set_error("Invalid bitstream, block header checksum mismatch"); return -KZG_ERR_CRC_CHECK; }
     if ((i32)pre < 0 || (i32)pre > maxTransformLength) { kzg_set_error("Invalid compressed block length: %d", (i32)pre); return -KZG_ERR_READ_FILE; }
-    if (((written + 7) >> 3) > (i64)pre + headerSize) return -KZG_ERR_BLOCK_SIZE;
+    if (((written + 7) >> 3) > (i64)pre + headerSize + chkBytes) return -KZG_ERR_BLOCK_SIZE;      // CIS:1158-1165
     if (pre == 0) break;                                         // "last block is empty" (CIS:1223-1227)
     Rec rc;
-    rc.payBit = (i64)hb.pos; rc.payBits = written - (i64)headerSize * 8; rc.preLen = (i32)pre;
+    rc.xxh = 0;
+    if (chkBytes) { if (written < (i64)(headerSize + chkBytes) * 8) return -KZG_ERR_BLOCK_SIZE; rc.xxh = (chkBytes == 4) ? hb.read(32) : ((hb.read(32) << 32) | hb.read(32)); }      // CIS:1247-1253
+    rc.payBit = (i64)hb.pos; rc.payBits = written - (i64)(headerSize + chkBytes) * 8; rc.preLen = (i32)pre;
     rc.rawCopy = copyBlock && !transformedCopy;
     rc.skipFlags = rc.rawCopy ? 0xFF : (skipFlags & 0xFF);
     rc.entropy = copyBlock ? KZG_E_NONE : entropy;
@@ -1028,7 +1042,7 @@ static int64_t decompress_impl(const uint8_t* d_in, int64_t nBytes, const uint8_
     B.alt = (k == 1) ? dest : dF + (size_t)b * cap;
     B.aux1 = dF + (size_t)b * cap;
     B.curLen = rc.preLen; B.preLen = rc.preLen; B.cap = (i32)cap - 64; B.skipFlags = rc.skipFlags;
-    B.entropy = rc.entropy; B.srcBit = rc.payBit; B.srcBits = rc.payBits;
+    B.entropy = rc.entropy; B.srcBit = rc.payBit; B.srcBits = rc.payBits; B.xxh = rc.xxh; B.chkBytes = chkBytes;
     if (k == 0 && rc.preLen > avail) { kzg_set_error(rc.preLen > blockSize ? "Block %d incorrectly decompressed" : "output capacity too small for block %d", b + 1); return rc.preLen > blockSize ? -KZG_ERR_PROCESS_BLOCK : -KZG_ERR_WRITE_FILE; }
     bt.hDstLimit[b] = blkBuf;
     if (rc.entropy == KZG_E_NONE) anyNone = true; else anyEnt = true;
@@ -1069,6 +1083,7 @@ static int64_t decompress_impl(const uint8_t* d_in, int64_t nBytes, const uint8_
         rc = run_transform_stage(sub, fn[i], i, false, xs, dScratch + (size_t)b0 * xs.perBlock, dHash + (size_t)b0 * xs.hashInts, dAux + (size_t)b0 * xs.aux32, flags);
         if (rc < 0) break;
       }
+      if (rc >= 0 && chkBytes) rc = kzg_xxh_launch(q, sub.dBlocks, cnt, 1);       // verify the decoded bytes (CIS:1348-1370)
     } while (0);
     W.stream = mainStream;
     if (rc < 0) break;

@@ -44,6 +44,9 @@ struct KzgBlock {
   u8* aux0; u8* aux1;
   i32 stagesLeft;
   i32 finalCap;   // decode: bytes the caller's output buffer holds at aux0 (0 = no clamp); see kzg_dst_limit
+  u64 xxh;        // block checksum of the original bytes (XXHash32 / Kanzi's XXHash64), encode: computed, decode: expected
+  i32 chkBytes;   // 0, 4 or 8: checksum bytes in the block record (COS:892-895)
+  i32 pad1;
 };
 
 // dst limit of a stage as its kernels must see it: the Java-visible limit, clamped to the caller's buffer when the stage

@@ -119,7 +119,8 @@ static StreamParams mkParams(const int32_t* ids, int nIds, int entropyType, int3
   StreamParams sp;
   int idv[8]; for (int i = 0; i < nIds; i++) idv[i] = ids[i];
   sp.transformType = transformTypeOf(idv, nIds);
-  sp.entropyType = entropyType; sp.blockSize = blockSize; sp.inputSize = inputSize; sp.bwtBounds = bwtBounds;
+  sp.entropyType = entropyType; sp.blockSize = blockSize; sp.inputSize = inputSize; sp.bwtBounds = bwtBounds & 0xFF;
+  sp.checksum = (bwtBounds >> 8) & 0xFF;       // (callers pass bwtBounds | checksum << 8: 0, 32 or 64)
   return sp;
 }
 
@@ -237,6 +238,8 @@ int32_t kzo_expgolomb_signed(int8_t v, uint32_t* bits) {
   r >>= (bs.buf.size() * 8 - nb);
   *bits = r; return nb;
 }
+uint32_t kzo_xxhash32(const uint8_t* d, int32_t n, uint32_t seed) { return xxhash32(d, n, seed); }
+uint64_t kzo_xxhash64(const uint8_t* d, int32_t n, uint64_t seed) { return kanzi_xxhash64(d, n, seed); }
 int kzo_abi_version() { return 1; }
 
 }  // extern "C"

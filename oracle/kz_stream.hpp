@@ -64,19 +64,69 @@ static inline u64 transformTypeOf(const int* ids, int n) {
   return res;
 }
 
+// ---- block checksums: K/util/hash/XXHash32.java:94-142 and XXHash64.java (seed = BITSTREAM_TYPE, COS:195-200) -----------------
+// XXHash32 is the published XXH32.  Kanzi's XXHash64 is NOT the published XXH64: the four accumulators are folded with the
+// 32-bit rotation idiom `(v << 1) | (v >>> 31)` applied to 64-bit values (XXHash64.java:127-128), restated as written.
+static inline u32 xxh32_round(u32 acc, u32 val) { acc += val * 2246822519u; return ((acc << 13) | (acc >> 19)) * 2654435761u; }
+static inline u32 xxhash32(const u8* data, int length, u32 seed) {
+  const u32 P1 = 2654435761u, P2 = 2246822519u, P3 = 3266489917u, P4 = 668265263u, P5 = 374761393u;
+  const int end = length;
+  u32 h32; int idx = 0;
+  if (length >= 16) {
+    const int end16 = end - 16;
+    u32 v1 = seed + P1 + P2, v2 = seed + P2, v3 = seed, v4 = seed - P1;
+    do {
+      v1 = xxh32_round(v1, le32(data + idx)); v2 = xxh32_round(v2, le32(data + idx + 4));
+      v3 = xxh32_round(v3, le32(data + idx + 8)); v4 = xxh32_round(v4, le32(data + idx + 12));
+      idx += 16;
+    } while (idx <= end16);
+    h32 = ((v1 << 1) | (v1 >> 31)) + ((v2 << 7) | (v2 >> 25)) + ((v3 << 12) | (v3 >> 20)) + ((v4 << 18) | (v4 >> 14));
+  } else h32 = seed + P5;
+  h32 += (u32)length;
+  while (idx <= end - 4) { h32 += le32(data + idx) * P3; h32 = ((h32 << 17) | (h32 >> 15)) * P4; idx += 4; }
+  while (idx < end) { h32 += (u32)data[idx] * P5; h32 = ((h32 << 11) | (h32 >> 21)) * P1; idx++; }
+  h32 ^= h32 >> 15; h32 *= P2; h32 ^= h32 >> 13; h32 *= P3;
+  return h32 ^ (h32 >> 16);
+}
+static inline u64 xxh64_round(u64 acc, u64 val) { acc += val * 0xC2B2AE3D27D4EB4Full; return ((acc << 31) | (acc >> 33)) * 0x9E3779B185EBCA87ull; }
+static inline u64 xxh64_merge(u64 acc, u64 val) { acc ^= xxh64_round(0, val); return acc * 0x9E3779B185EBCA87ull + 0x85EBCA77C2B2AE63ull; }
+static inline u64 kanzi_xxhash64(const u8* data, int length, u64 seed) {
+  const u64 P1 = 0x9E3779B185EBCA87ull, P2 = 0xC2B2AE3D27D4EB4Full, P3 = 0x165667B19E3779F9ull, P4 = 0x85EBCA77C2B2AE63ull, P5 = 0x27D4EB2F165667C5ull;
+  const int end = length;
+  u64 h64; int idx = 0;
+  if (length >= 32) {
+    const int end32 = end - 32;
+    u64 v1 = seed + P1 + P2, v2 = seed + P2, v3 = seed, v4 = seed - P1;
+    do {
+      v1 = xxh64_round(v1, le64(data + idx)); v2 = xxh64_round(v2, le64(data + idx + 8));
+      v3 = xxh64_round(v3, le64(data + idx + 16)); v4 = xxh64_round(v4, le64(data + idx + 24));
+      idx += 32;
+    } while (idx <= end32);
+    h64 = ((v1 << 1) | (v1 >> 31)) + ((v2 << 7) | (v2 >> 25)) + ((v3 << 12) | (v3 >> 20)) + ((v4 << 18) | (v4 >> 14));     // as written (:127-128)
+    h64 = xxh64_merge(h64, v1); h64 = xxh64_merge(h64, v2); h64 = xxh64_merge(h64, v3); h64 = xxh64_merge(h64, v4);
+  } else h64 = seed + P5;
+  h64 += (u64)(i64)length;
+  while (idx + 8 <= end) { h64 ^= xxh64_round(0, le64(data + idx)); h64 = ((h64 << 27) | (h64 >> 37)) * P1 + P4; idx += 8; }
+  while (idx + 4 <= end) { h64 ^= (u64)(i64)(i32)le32(data + idx) * P1; h64 = ((h64 << 23) | (h64 >> 41)) * P2 + P3; idx += 4; }   // readInt32 is a signed int widened to long
+  while (idx < end) { h64 ^= (u64)data[idx] * P5; h64 = ((h64 << 11) | (h64 >> 53)) * P1; idx++; }
+  h64 ^= h64 >> 33; h64 *= P2; h64 ^= h64 >> 29; h64 *= P3;
+  return h64 ^ (h64 >> 32);
+}
+
 struct StreamParams {
   u64 transformType = 0;     // 48 bits, 8 x 6
   int entropyType = E_NONE;
   int blockSize = 4 << 20;
   i64 inputSize = 0;         // ctx["fileSize"]; 0 = unknown
   int bwtBounds = 1;         // 1 = as the reference is written (SURVEY E-1), 0 = "fixed"
+  int checksum = 0;          // ctx["checksum"]: 0, 32 or 64 (COS:193-204)
 };
 
-// writeHeader, CompressedOutputStream.java:236-313 (checksum kind 0)
+// writeHeader, CompressedOutputStream.java:236-313
 static inline void writeStreamHeader(BitWriter& obs, const StreamParams& sp) {
   obs.writeBits((u32)BITSTREAM_TYPE, 32);
   obs.writeBits(BITSTREAM_FORMAT_VERSION, 4);
-  const int chkSize = 0;
+  const int chkSize = (sp.checksum == 32) ? 1 : ((sp.checksum == 64) ? 2 : 0);     // COS:248-254
   obs.writeBits(chkSize, 2);
   obs.writeBits((u64)sp.entropyType, 5);
   obs.writeBits(sp.transformType, 48);
@@ -132,6 +182,9 @@ static inline void encodeBlock(BitWriter& obs, EncodeBuffers& eb, int blockLengt
   int mode = 0;
   u64 blockTransformType = sp.transformType; int blockEntropyType = sp.entropyType;
   if (blockLength <= SMALL_BLOCK_SIZE) { blockTransformType = 0; blockEntropyType = E_NONE; mode |= COPY_BLOCK_MASK; }
+  u64 checksum = 0;                              // of the original bytes, before anything else touches them (COS:745-755)
+  if (sp.checksum == 32) checksum = (u64)xxhash32(data.p(), blockLength, (u32)BITSTREAM_TYPE);
+  else if (sp.checksum == 64) checksum = kanzi_xxhash64(data.p(), blockLength, (u64)(i64)BITSTREAM_TYPE);
   ctx.size = blockLength;
   Sequence transform(ctx, blockTransformType);
   const int requiredSize = transform.getMaxEncodedLength(blockLength);
@@ -178,6 +231,7 @@ static inline void encodeBlock(BitWriter& obs, EncodeBuffers& eb, int blockLengt
   int headerChecksumIndex = 1 + dataSize;
   if (((mode & COPY_BLOCK_MASK) == 0) && (nbFunctions > 4)) headerChecksumIndex++;
   os.writeBits(0, 8);
+  if (sp.checksum == 32) os.writeBits(checksum, 32); else if (sp.checksum == 64) os.writeBits(checksum, 64);       // COS:892-895
   if (entropyEncode(blockEntropyType, os, buffer.p(), postTransformLength) != postTransformLength)
     throw JavaException("Entropy coding failed");
   i64 written = (i64)os.written();
@@ -196,6 +250,7 @@ static inline void encodeBlock(BitWriter& obs, EncodeBuffers& eb, int blockLengt
       if (nbFunctions > 4) { headerChecksumIndex++; headerSkipFlags = skipFlags; }
       else headerSkipFlags = ((copyMode << 4) | 0x0F) & 0xFF;
       copyOs.writeBits(0, 8);
+      if (sp.checksum == 32) copyOs.writeBits(checksum, 32); else if (sp.checksum == 64) copyOs.writeBits(checksum, 64);
       copyOs.writeBytesBits(buffer.p(), (i64)postTransformLength << 3);
       written = (i64)copyOs.written();
       copyOs.close();
@@ -251,7 +306,7 @@ static inline StreamHeader readStreamHeader(BitReader& ibs) {
   h.bsVersion = (int)ibs.readBits(4);
   if (h.bsVersion != BITSTREAM_FORMAT_VERSION) throw JavaException("oracle reads bitstream version 7 only");
   h.chkSize = (int)ibs.readBits(2);
-  if (h.chkSize != 0) throw JavaException("oracle: block checksums not restated");
+  if (h.chkSize == 3) throw JavaException("Invalid bitstream, incorrect block checksum size");
   h.entropyType = (int)ibs.readBits(5);
   h.transformType = ibs.readBits(48);
   h.blockSize = (int)ibs.readBits(28) << 4;
@@ -315,7 +370,8 @@ static inline int decodeBlock(BitReader& ibs, const StreamHeader& h, std::vector
   if (headerChecksum != (c & 0xFF)) throw JavaException("Invalid bitstream, block header checksum mismatch");
   const bool rawCopy = copyBlock && !transformedCopy;
   if ((preTransformLength < 0) || (preTransformLength > maxTransformLength)) throw JavaException("Invalid compressed block length");
-  if (encodedBlockBytes > (i64)preTransformLength + headerSize) throw JavaException("Invalid block size");
+  const int checksumSize = (h.chkSize == 2) ? 8 : ((h.chkSize == 1) ? 4 : 0);
+  if (encodedBlockBytes > (i64)preTransformLength + headerSize + checksumSize) throw JavaException("Invalid block size");      // CIS:1158-1165
   read -= (i64)headerSize << 3;
   // payload bits -> private byte array (COS:1182-1187), then a per-block bit reader over it
   const int r = (int)encodedBlockBytes;
@@ -326,6 +382,8 @@ static inline int decodeBlock(BitReader& ibs, const StreamHeader& h, std::vector
   if (rawCopy) { blockTransformType = 0; blockEntropyType = E_NONE; }
   else if (transformedCopy) blockEntropyType = E_NONE;
   if (preTransformLength == 0) return 0;
+  u64 checksum1 = 0;                              // CIS:1247-1253
+  if (h.chkSize == 1) checksum1 = is.readBits(32); else if (h.chkSize == 2) checksum1 = is.readBits(64);
   // buffers: `buffer` (entropy output) and `data` (final output), CIS:719-727, 1283-1288
   const int blkBuf = std::max(h.blockSize + EXTRA_BUFFER_SIZE, h.blockSize + (h.blockSize >> 4));
   std::vector<u8> dataArr((size_t)std::max(blkBuf, std::max(h.blockSize, r)), 0), bufArr;
@@ -346,6 +404,8 @@ static inline int decodeBlock(BitReader& ibs, const StreamHeader& h, std::vector
   if (!transform.inverse(buffer, data)) throw JavaException("Transform inverse failed");
   const int decoded = data.index;
   if (decoded > h.blockSize) throw JavaException("Block incorrectly decompressed");
+  if (h.chkSize == 1 && xxhash32(dataArr.data(), decoded, (u32)BITSTREAM_TYPE) != (u32)checksum1) throw JavaException("Corrupted bitstream: invalid checksum");     // CIS:1348-1370
+  if (h.chkSize == 2 && kanzi_xxhash64(dataArr.data(), decoded, (u64)(i64)BITSTREAM_TYPE) != checksum1) throw JavaException("Corrupted bitstream: invalid checksum");
   out.insert(out.end(), dataArr.begin(), dataArr.begin() + decoded);
   return decoded;
 }

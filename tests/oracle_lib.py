@@ -55,6 +55,10 @@ def lib():
         L.kzo_stream_header.argtypes = [i32p, C.c_int, C.c_int, C.c_int32, C.c_int64, u8p, C.c_int32]
         L.kzo_normalize_frequencies.restype = C.c_int32
         L.kzo_normalize_frequencies.argtypes = [i32p, i32p, C.c_int32, C.c_int32]
+        L.kzo_xxhash32.restype = C.c_uint32
+        L.kzo_xxhash32.argtypes = [u8p, C.c_int32, C.c_uint32]
+        L.kzo_xxhash64.restype = C.c_uint64
+        L.kzo_xxhash64.argtypes = [u8p, C.c_int32, C.c_uint64]
         L.kzo_expgolomb_signed.restype = C.c_int32
         L.kzo_expgolomb_signed.argtypes = [C.c_int8, C.POINTER(C.c_uint32)]
     return _LIB
@@ -135,13 +139,24 @@ def bwt_inverse(data, pis, algo=0):
     return r, out.tobytes()
 
 
-def compress(data, transforms, entropy, block_size, input_size=None, bwt_bounds=1):
+def xxhash32(data, seed=0):
+    a, p = _u8(data)
+    return lib().kzo_xxhash32(p, len(a), seed)
+
+
+def xxhash64(data, seed=0):
+    """Kanzi's XXHash64 (not the published XXH64 for inputs of 32+ bytes: see oracle/kz_stream.hpp)"""
+    a, p = _u8(data)
+    return lib().kzo_xxhash64(p, len(a), seed)
+
+
+def compress(data, transforms, entropy, block_size, input_size=None, bwt_bounds=1, checksum=0):
     a, p = _u8(data)
     ids, n = _ids(transforms)
     cap = len(a) + len(a) // 4 + (1 << 16)
     out = np.zeros(cap, dtype=np.uint8)
     isz = len(a) if input_size is None else input_size
-    r = lib().kzo_compress_stream(p, len(a), ids, n, E[entropy], block_size, isz, bwt_bounds, out.ctypes.data_as(u8p), cap)
+    r = lib().kzo_compress_stream(p, len(a), ids, n, E[entropy], block_size, isz, bwt_bounds | (checksum << 8), out.ctypes.data_as(u8p), cap)
     if r < 0:
         raise RuntimeError(f"oracle compress failed: {r}")
     return out[:r].tobytes()

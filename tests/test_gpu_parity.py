@@ -272,3 +272,24 @@ def test_magic_datatype_paths():
     dna = CASES["dna"] * 3
     assert K.compress(dna, ["ROLZ"], "ANS0", 1 << 17) == O.compress(dna, ["ROLZ"], "ANS0", 1 << 17)
     assert K.compress(dna, ["LZ"], "HUFFMAN", 1 << 17) == O.compress(dna, ["LZ"], "HUFFMAN", 1 << 17)
+
+
+@pytest.mark.parametrize("ck,flag", [(32, K.FLAG_XXH32), (64, K.FLAG_XXH64)])
+def test_stream_block_checksums(ck, flag):
+    """-x 32 / -x 64: XXHash of every block's original bytes in its record (COS:745-755, 892-895), verified on decode (CIS:1348-1370)."""
+    d = stream_input() + bytes(range(7))
+    for tr, ent, bs in ((["LZ"], "ANS0", 1 << 18), (["NONE"], "HUFFMAN", 1 << 16), (["ROLZ"], "ANS0", 1 << 19), (["BWT", "RANK", "ZRLT"], "ANS1", 1 << 18)):
+        ref = O.compress(d, tr, ent, bs, checksum=ck)
+        got = K.compress(d, tr, ent, bs, flags=K.FLAG_BWT_ASREF | flag)
+        assert got == ref, (ck, tr, ent, len(got), len(ref), "first differing byte", first_diff(got, ref))
+        assert K.decompress(ref, len(d)) == d
+    # a flipped payload bit that still decodes must be caught by the checksum; any failure is fine, silence is not
+    knz = bytearray(O.compress(d[:300_000], ["NONE"], "NONE", 1 << 16, checksum=ck))
+    knz[len(knz) // 2] ^= 0x10
+    with pytest.raises(K.KzgError) as e:
+        K.decompress(bytes(knz), 300_000)
+    assert e.value.code == -19         # ERR_CRC_CHECK
+    # tiny blocks (copy blocks, COS:764-767) carry the checksum too
+    for n in (1, 15, 16, 33):
+        t = bytes(range(n))
+        assert K.compress(t, ["LZ"], "ANS0", 1024, flags=K.FLAG_BWT_ASREF | flag) == O.compress(t, ["LZ"], "ANS0", 1024, checksum=ck)

@@ -143,3 +143,28 @@ def test_mt_block_encoder_matches_stream():
     assert (acc << pad).to_bytes((nbits + pad) // 8, "big") == s
     back = O.decode_blocks_mt(recs, off, bits, ["LZ"], "ANS0", bs, 4, len(d))
     assert back.tobytes() == d.tobytes()
+
+
+def test_xxhash_published_vectors():
+    """XXHash32 is the published XXH32 (K/util/hash/XXHash32.java:94-142): the reference vectors of the xxHash project pin it.
+    XXHash64 matches the published XXH64 below 32 bytes; from 32 bytes on Kanzi folds its accumulators with a 32-bit rotation
+    idiom on 64-bit values (XXHash64.java:127-128), so its result is Kanzi's own and only the short vectors apply."""
+    assert O.xxhash32(b"", 0) == 0x02CC5D05
+    assert O.xxhash32(b"abc", 0) == 0x32D153FF
+    assert O.xxhash32(b"Nobody inspects the spammish repetition", 0) == 0xE2293B2F
+    assert O.xxhash64(b"", 0) == 0xEF46DB3751D8E999
+    assert O.xxhash64(b"abc", 0) == 0x44BC2CF5AD770999
+    assert O.xxhash64(b"Nobody inspects the spammish repetition", 0) != 0xFBCEA83C8A378BF1      # the published XXH64: not what Kanzi computes
+
+
+def test_checksummed_streams_round_trip_and_detect_corruption():
+    d = bytes((i * 131 + (i >> 7)) & 0xFF for i in range(200_000))
+    for ck in (32, 64):
+        knz = O.compress(d, ["LZ"], "ANS0", 1 << 16, checksum=ck)
+        plain = O.compress(d, ["LZ"], "ANS0", 1 << 16)
+        assert len(knz) == len(plain) + (ck // 8) * 4            # 4 blocks, ck/8 bytes each (the lw field keeps its width here)
+        assert O.decompress(knz, len(d) + 64) == d
+        bad = bytearray(knz)
+        bad[len(bad) // 2] ^= 0x04
+        with pytest.raises(RuntimeError):
+            O.decompress(bytes(bad), len(d) + 64)
