@@ -764,6 +764,16 @@ static int stream_header(u8* h, int entropy, u64 transformType, i32 blockSize, i
 
 // h_in (optional): the input is still on the host; it is uploaded here — whole, or, when the chain starts with LZ and the
 // batch is large, a sample per eighth of every block now and the blocks themselves by the LZ stage on its group streams.
+// Device memory one call may take for its arena: what is free now (plus what this thread's arena already holds), less a margin.
+// KZG_ARENA_MB (developer / test knob) lowers it so that small inputs exercise the slicing below.
+static size_t arena_budget() {
+  size_t freeB = 0, totalB = 0;
+  if (cudaMemGetInfo(&freeB, &totalB) != cudaSuccess) { cudaGetLastError(); freeB = (size_t)8 << 30; }
+  size_t budget = (size_t)((double)(freeB + W.dCap) * 0.85);
+  if (const char* e = getenv("KZG_ARENA_MB")) budget = std::min(budget, (size_t)std::max(1, atoi(e)) << 20);
+  return budget;
+}
+
 static int64_t compress_impl(const uint8_t* d_in, int64_t n, const int32_t* transforms, int32_t nTransforms, int32_t entropy,
                              int32_t blockSize, int32_t flags, uint8_t* d_out, int64_t outCap, float* timing3, const uint8_t* h_in) {
   if (n < 0 || nTransforms < 0 || nTransforms > 8 || !ent_known(entropy)) return -KZG_ERR_INVALID_PARAM;
@@ -781,36 +791,50 @@ static int64_t compress_impl(const uint8_t* d_in, int64_t n, const int32_t* tran
   bool anyXf = false; for (int i = 0; i < nf; i++) if (fn[i] != KZG_T_NONE) anyXf = true;
   XfScratch xs = xf_scratch_size(fn, nf, required, true);
   EntScratch es = ent_scratch_size(entropy, required, true);
-  const size_t nb = (size_t)std::max(nBlocks, 1);
-  size_t need = nb * (sizeof(KzgBlock) + 64) + (anyXf ? nb * cap * (nf >= 2 ? 2 : 1) : 0) + nb * xs.perBlock + (nb * (xs.hashInts + xs.aux32)) * 4 +
-                nb * (size_t)es.maxChunks * (es.hdrStride + es.payStride + es.tabStride * 4) + nb * (size_t)es.segsPerBlock * sizeof(KzgSeg) + (1 << 20);
-  r = ws_reserve(need, nb * (sizeof(KzgBlock) + 32) + 8192); if (r < 0) return r;
-  u8 hdr[64];
+  // The arena holds every block of a slice at once (descriptors, ping-pong buffers, codec scratch, entropy scratch).  An input
+  // whose blocks do not all fit runs as several slices of whole blocks, one after the other, each appending its records where
+  // the previous slice's ended (records are independent and bit-granular: COS:1024-1035) — the stream is the same.
+  const size_t perBlock = (sizeof(KzgBlock) + 64) + (anyXf ? cap * (nf >= 2 ? 2 : 1) : 0) + xs.perBlock + (xs.hashInts + xs.aux32) * 4 +
+                          (size_t)es.maxChunks * (es.hdrStride + es.payStride + es.tabStride * 4) + (size_t)es.segsPerBlock * sizeof(KzgSeg) + KZG_HDR_STRIDE;
+  const size_t budget = arena_budget();
+  const int sliceBlocks = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(nBlocks, 1), (budget > (2u << 20) ? budget - (2u << 20) : 0) / (perBlock + perBlock / 8)));
+  const size_t nbMax = (size_t)std::max(std::min(nBlocks, sliceBlocks), 1);
+  r = ws_reserve(nbMax * perBlock + (1 << 20), nbMax * (sizeof(KzgBlock) + 32) + 8192); if (r < 0) return r;
   if ((flags & KZG_FLAG_XXH32) && (flags & KZG_FLAG_XXH64)) return -KZG_ERR_INVALID_PARAM;
   const int chkBytes = (flags & KZG_FLAG_XXH32) ? 4 : ((flags & KZG_FLAG_XXH64) ? 8 : 0);       // ctx["checksum"] 32 / 64 (COS:193-204)
+  u8 hdr[64];
   const int hdrLen = stream_header(hdr, entropy, transformType, blockSize, n, chkBytes / 4);
   if (outCap < hdrLen + 2) return -KZG_ERR_WRITE_FILE;
   EvSet ev;
-  if (timing3) { r = ev.create(4); if (r < 0) return r; }
-  const bool lazyIn = h_in && nf >= 1 && (fn[0] == KZG_T_LZ || fn[0] == KZG_T_LZX) && nBlocks >= 8 && blockSize >= (1 << 18);
-  if (h_in && n > 0) {
-    if (!lazyIn) CUDA_TRY(cudaMemcpyAsync((u8*)d_in, h_in, (size_t)n, cudaMemcpyHostToDevice, W.stream));
-    else {
-      for (int b = 0; b < nBlocks; b++) {       // the samples the LZ stage orders its blocks by (they also hold the block's magic bytes)
-        const i64 off = (i64)b * blockSize;
-        const i64 len = std::min<i64>(blockSize, n - off);
-        const i64 eighth = len / LZF_SAMPLES;
-        if (eighth < LZF_SAMPLE) { CUDA_TRY(cudaMemcpyAsync((u8*)d_in + off, h_in + off, (size_t)len, cudaMemcpyHostToDevice, W.stream)); continue; }
-        CUDA_TRY(cudaMemcpy2DAsync((u8*)d_in + off, (size_t)eighth, h_in + off, (size_t)eighth, LZF_SAMPLE, LZF_SAMPLES, cudaMemcpyHostToDevice, W.stream));
-      }
-    }
-  }
+  if (timing3) { r = ev.create(4); if (r < 0) return r; timing3[0] = timing3[1] = timing3[2] = 0; }
   CUDA_TRY(cudaMemsetAsync(d_out, 0, (size_t)outCap, W.stream));
   CUDA_TRY(cudaMemcpyAsync(d_out, hdr, hdrLen, cudaMemcpyHostToDevice, W.stream));
   i64 totalBits = (i64)hdrLen * 8 + 8;
-  if (nBlocks > 0) {
-    Batch bt; bt.nBlocks = nBlocks; bt.maxLen = required;
-    if (lazyIn) { bt.lazyHost = h_in; bt.lazyDev = (u8*)d_in; bt.lazyN = n; bt.lazyBlock = blockSize; }
+  for (int b0 = 0; b0 < nBlocks; b0 += sliceBlocks) {
+    const int cnt = std::min(sliceBlocks, nBlocks - b0);
+    const size_t nb = (size_t)cnt;
+    const i64 off0 = (i64)b0 * blockSize;
+    const i64 sliceN = std::min<i64>((i64)cnt * blockSize, n - off0);
+    const uint8_t* sIn = d_in + off0;
+    const uint8_t* sHost = h_in ? h_in + off0 : nullptr;
+    W.dOff = 0; W.hOff = 0;                        // the arena is reused slice after slice (the stream is in order)
+    const bool lazyIn = sHost && nf >= 1 && (fn[0] == KZG_T_LZ || fn[0] == KZG_T_LZX) && cnt >= 8 && blockSize >= (1 << 18);
+    if (sHost && sliceN > 0) {
+      // the input is still on the host: uploaded here — whole, or, when the chain starts with LZ and the batch is large, a sample
+      // per eighth of every block now and the blocks themselves by the LZ stage on its group streams
+      if (!lazyIn) CUDA_TRY(cudaMemcpyAsync((u8*)sIn, sHost, (size_t)sliceN, cudaMemcpyHostToDevice, W.stream));
+      else {
+        for (int b = 0; b < cnt; b++) {       // the samples the LZ stage orders its blocks by (they also hold the block's magic bytes)
+          const i64 off = (i64)b * blockSize;
+          const i64 len = std::min<i64>(blockSize, sliceN - off);
+          const i64 eighth = len / LZF_SAMPLES;
+          if (eighth < LZF_SAMPLE) { CUDA_TRY(cudaMemcpyAsync((u8*)sIn + off, sHost + off, (size_t)len, cudaMemcpyHostToDevice, W.stream)); continue; }
+          CUDA_TRY(cudaMemcpy2DAsync((u8*)sIn + off, (size_t)eighth, sHost + off, (size_t)eighth, LZF_SAMPLE, LZF_SAMPLES, cudaMemcpyHostToDevice, W.stream));
+        }
+      }
+    }
+    Batch bt; bt.nBlocks = cnt; bt.maxLen = required;
+    if (lazyIn) { bt.lazyHost = sHost; bt.lazyDev = (u8*)sIn; bt.lazyN = sliceN; bt.lazyBlock = blockSize; }
     bt.hBlocks = halloc<KzgBlock>(nb); NN(bt.hBlocks);
     bt.hEnabled = halloc<u8>(nb); NN(bt.hEnabled);
     bt.hDstLimit = halloc<int>(nb); NN(bt.hDstLimit);
@@ -829,12 +853,12 @@ static int64_t compress_impl(const uint8_t* d_in, int64_t n, const int32_t* tran
     KzgSeg* dSegs = dalloc<KzgSeg>(nb * es.segsPerBlock); NN(dSegs);
     u8* dHdrBytes = dalloc<u8>(nb * KZG_HDR_STRIDE + 16); NN(dHdrBytes);
     i64* dTotal = dalloc<i64>(2); NN(dTotal);
-    for (int b = 0; b < nBlocks; b++) {
+    for (int b = 0; b < cnt; b++) {
       KzgBlock& B = bt.hBlocks[b];
       memset(&B, 0, sizeof(B));
       const i64 off = (i64)b * blockSize;
-      const i32 len = (i32)std::min<i64>(blockSize, n - off);
-      B.cur = (u8*)d_in + off; B.aux0 = B.cur;
+      const i32 len = (i32)std::min<i64>(blockSize, sliceN - off);
+      B.cur = (u8*)sIn + off; B.aux0 = B.cur;
       B.alt = dA ? dA + (size_t)b * cap : nullptr; B.aux1 = dB ? dB + (size_t)b * cap : B.alt;
       B.curLen = len; B.cap = (i32)cap - 64; B.origLen = len; B.skipFlags = 0xFF; B.entropy = entropy; B.chkBytes = chkBytes;
       const bool small = len <= 15;                             // COS:764-767: raw copy block
@@ -842,7 +866,7 @@ static int64_t compress_impl(const uint8_t* d_in, int64_t n, const int32_t* tran
       bt.hEnabled[b] = small ? 0 : 1;
       // dst slice length of the transform stage: EncodingTask grows `buffer` to the Sequence's requiredSize and never shrinks it
       // (COS:806-811), so with the blocks of one stream handled in order every block after the first sees the full-block size
-      bt.hDstLimit[b] = (b == 0) ? seq_max_len(fn, nf, len) : required;
+      bt.hDstLimit[b] = (b0 + b == 0) ? seq_max_len(fn, nf, len) : required;
     }
     CUDA_TRY(cudaMemcpyAsync(bt.dEnabled, bt.hEnabled, nb, cudaMemcpyHostToDevice, W.stream));
     CUDA_TRY(cudaMemcpyAsync(bt.dDstLimit, bt.hDstLimit, nb * sizeof(int), cudaMemcpyHostToDevice, W.stream));
@@ -850,45 +874,40 @@ static int64_t compress_impl(const uint8_t* d_in, int64_t n, const int32_t* tran
     r = batch_upload(bt); if (r < 0) return r;
     if (timing3) CUDA_TRY(cudaEventRecord(ev[0], W.stream));
     // ctx["dataType"] from the block's magic number (COS:795-804)
-    r = kzg_magic_launch(W.stream, bt.dBlocks, nBlocks); if (r < 0) return r;
+    r = kzg_magic_launch(W.stream, bt.dBlocks, cnt); if (r < 0) return r;
     if (chkBytes) {       // block checksums of the original bytes (COS:745-755): four dependent chains per block, on a stream of their own next to the transforms
-      if (lazyIn) CUDA_TRY(cudaMemcpyAsync((u8*)d_in, h_in, (size_t)n, cudaMemcpyHostToDevice, W.stream));      // (the hash needs the whole input now; the LZ stage's own uploads then rewrite the same bytes)
+      if (lazyIn) CUDA_TRY(cudaMemcpyAsync((u8*)sIn, sHost, (size_t)sliceN, cudaMemcpyHostToDevice, W.stream));      // (the hash needs the whole input now; the LZ stage's own uploads then rewrite the same bytes)
       r = ws_side_init(); if (r < 0) return r;
       CUDA_TRY(cudaEventRecord(W.sideEv[KZG_DEC_MAXG], W.stream));
       CUDA_TRY(cudaStreamWaitEvent(W.side[0], W.sideEv[KZG_DEC_MAXG], 0));
-      r = kzg_xxh_launch(W.side[0], bt.dBlocks, nBlocks, 0); if (r < 0) return r;
+      r = kzg_xxh_launch(W.side[0], bt.dBlocks, cnt, 0); if (r < 0) return r;
       CUDA_TRY(cudaEventRecord(W.sideEv[0], W.side[0]));
     }
     // Sequence.forward: a NONE-only chain is a copy that always succeeds (NullTransform) -> skip bit 7 cleared
     for (int i = 0; i < nf; i++) {
-      if (fn[i] == KZG_T_NONE) { r = kzg_null_forward_launch(W.stream, bt.dBlocks, nBlocks, bt.dEnabled, i); if (r < 0) return r; continue; }
+      if (fn[i] == KZG_T_NONE) { r = kzg_null_forward_launch(W.stream, bt.dBlocks, cnt, bt.dEnabled, i); if (r < 0) return r; continue; }
       r = run_transform_stage(bt, fn[i], i, true, xs, dScratch, dHash, dAux, flags); if (r < 0) return r;
     }
     if (timing3) CUDA_TRY(cudaEventRecord(ev[1], W.stream));
     r = run_entropy_encode(bt, entropy, es, dHdr, dPay, dTab, dSegs); if (r < 0) return r;
     if (timing3) CUDA_TRY(cudaEventRecord(ev[2], W.stream));
     if (chkBytes) CUDA_TRY(cudaStreamWaitEvent(W.stream, W.sideEv[0], 0));
-    r = kzg_assemble_launch(W.stream, bt.dBlocks, nBlocks, dSegs, es.segsPerBlock, dHdrBytes, nf, 1, d_out, (i64)hdrLen * 8, dTotal, outCap - 8);
+    r = kzg_assemble_launch(W.stream, bt.dBlocks, cnt, dSegs, es.segsPerBlock, dHdrBytes, nf, 1, d_out, totalBits - 8, dTotal, outCap - 8);
     if (r < 0) return r;
     if (timing3) CUDA_TRY(cudaEventRecord(ev[3], W.stream));
     CUDA_TRY(cudaMemcpyAsync(&totalBits, dTotal, sizeof(i64), cudaMemcpyDeviceToHost, W.stream));
     r = batch_download(bt); if (r < 0) return r;
-    for (int b = 0; b < nBlocks; b++)
-      if (bt.hBlocks[b].status != 0) { kzg_set_error("block %d failed with status %d", b + 1, bt.hBlocks[b].status); return bt.hBlocks[b].status; }
+    for (int b = 0; b < cnt; b++)
+      if (bt.hBlocks[b].status != 0) { kzg_set_error("block %d failed with status %d", b0 + b + 1, bt.hBlocks[b].status); return bt.hBlocks[b].status; }
     if (totalBits < 0) return -KZG_ERR_PROCESS_BLOCK;
-    W.lastRecBits.resize(nBlocks);
-    for (int b = 0; b < nBlocks; b++) {          // COS:1024-1035: 5 bits of (lw - 3), lw bits of `written`, then `written` bits
+    for (int b = 0; b < cnt; b++) {          // COS:1024-1035: 5 bits of (lw - 3), lw bits of `written`, then `written` bits
       const i64 written = bt.hBlocks[b].written;
       int lw = 3; if (written >= 8) { lw = 0; while ((2LL << lw) <= (written >> 3)) lw++; lw += 4; }
-      W.lastRecBits[b] = 5 + lw + written;
+      W.lastRecBits.push_back(5 + lw + written);
     }
-    if (timing3) {
-      for (int i = 0; i < 3; i++) CUDA_TRY(cudaEventElapsedTime(&timing3[i], ev[i], ev[i + 1]));
-    }
-  } else {
-    CUDA_TRY(cudaStreamSynchronize(W.stream));
-    if (timing3) { timing3[0] = timing3[1] = timing3[2] = 0; }
+    if (timing3) for (int i = 0; i < 3; i++) { float ms = 0; CUDA_TRY(cudaEventElapsedTime(&ms, ev[i], ev[i + 1])); timing3[i] += ms; }
   }
+  if (nBlocks == 0) CUDA_TRY(cudaStreamSynchronize(W.stream));
   const i64 bytes = (totalBits + 7) >> 3;
   if (bytes > outCap - 8) { kzg_set_error("compressed stream (%lld bytes) exceeds capacity %lld", (long long)bytes, (long long)outCap); return -KZG_ERR_WRITE_FILE; }
   return bytes;
@@ -1005,116 +1024,123 @@ static int64_t decompress_impl(const uint8_t* d_in, int64_t nBytes, const uint8_
   const size_t cap = rnd((size_t)maxLen + 64);
   XfScratch xs = xf_scratch_size(fn, nf, maxLen, false);
   EntScratch es = ent_scratch_size(entropy, maxPre, false);
-  const size_t nb = (size_t)nBlocks;
-  size_t need = nb * (sizeof(KzgBlock) + 64) + nb * cap * 2 + nb * xs.perBlock + nb * (xs.hashInts + xs.aux32) * 4 +
-                nb * (size_t)es.maxChunks * (sizeof(KzgChunkInfo) + es.tabStride * 4) + nf * nb + (1 << 20);
-  r = ws_reserve(need, nb * (sizeof(KzgBlock) + 16 + nf) + 4096); if (r < 0) return r;
-  Batch bt; bt.nBlocks = nBlocks; bt.maxLen = maxLen;
-  bt.hBlocks = halloc<KzgBlock>(nb); NN(bt.hBlocks);
-  bt.hEnabled = halloc<u8>(nb * nf + 16); NN(bt.hEnabled);
-  bt.hDstLimit = halloc<int>(nb); NN(bt.hDstLimit);
-  bt.dBlocks = dalloc<KzgBlock>(nb); NN(bt.dBlocks);
-  bt.dResult = dalloc<int>(2 * nb); NN(bt.dResult);
-  u8* dEnabledAll = dalloc<u8>(nb * nf + 16); NN(dEnabledAll);
-  bt.dDstLimit = dalloc<int>(nb); NN(bt.dDstLimit);
-  u8* dE = dalloc<u8>(nb * cap); NN(dE);
-  u8* dF = dalloc<u8>(nb * cap); NN(dF);
-  u8* dScratch = dalloc<u8>(nb * xs.perBlock + 16); NN(dScratch);
-  i32* dHash = dalloc<i32>(nb * xs.hashInts + 4); NN(dHash);
-  i32* dAux = dalloc<i32>(nb * xs.aux32 + 4); NN(dAux);
-  KzgChunkInfo* dChunks = dalloc<KzgChunkInfo>(nb * es.maxChunks + 1); NN(dChunks);
-  u32* dTab = dalloc<u32>(nb * es.maxChunks * es.tabStride + 4); NN(dTab);
-  bool anyNone = false, anyEnt = false;
-  for (int b = 0; b < nBlocks; b++) {
-    const Rec& rc = recs[b];
-    KzgBlock& B = bt.hBlocks[b];
-    memset(&B, 0, sizeof(B));
-    int k = 0;     // inverse stages this block runs (Sequence.inverse :160-166 skips flagged transforms)
-    for (int i = 0; i < nf; i++) {
-      const bool runs = (rc.skipFlags != 0xFF) && ((rc.skipFlags & (1 << (7 - i))) == 0) && fn[i] != KZG_T_NONE;
-      bt.hEnabled[(size_t)i * nb + b] = runs ? 1 : 0;
-      if (runs) k++;
-    }
-    u8* dest = d_out + (size_t)b * blockSize;
-    const i32 avail = (i32)std::min<i64>(blockSize, outCap - (i64)b * blockSize);    // bytes of the caller's buffer this block owns
-    B.aux0 = dest; B.stagesLeft = k; B.finalCap = avail;
-    B.cur = (k == 0) ? dest : dE + (size_t)b * cap;
-    B.alt = (k == 1) ? dest : dF + (size_t)b * cap;
-    B.aux1 = dF + (size_t)b * cap;
-    B.curLen = rc.preLen; B.preLen = rc.preLen; B.cap = (i32)cap - 64; B.skipFlags = rc.skipFlags;
-    B.entropy = rc.entropy; B.srcBit = rc.payBit; B.srcBits = rc.payBits; B.xxh = rc.xxh; B.chkBytes = chkBytes;
-    if (k == 0 && rc.preLen > avail) { kzg_set_error(rc.preLen > blockSize ? "Block %d incorrectly decompressed" : "output capacity too small for block %d", b + 1); return rc.preLen > blockSize ? -KZG_ERR_PROCESS_BLOCK : -KZG_ERR_WRITE_FILE; }
-    bt.hDstLimit[b] = blkBuf;
-    if (rc.entropy == KZG_E_NONE) anyNone = true; else anyEnt = true;
-  }
-  CUDA_TRY(cudaMemcpyAsync(dEnabledAll, bt.hEnabled, nb * nf, cudaMemcpyHostToDevice, W.stream));
-  CUDA_TRY(cudaMemcpyAsync(bt.dDstLimit, bt.hDstLimit, nb * sizeof(int), cudaMemcpyHostToDevice, W.stream));
-  r = batch_upload(bt); if (r < 0) return r;
-  // Blocks are independent: contiguous groups of them run the whole decode on streams of their own (most urgent first), so
-  // that the latency-bound kernels of one group (chunk scan, the literal-record chain) overlap the streaming kernels of the
-  // others and, for host buffers, a group's upload / download overlaps the other groups' kernels.
+  // as in compress_impl: blocks that do not all fit the arena run as several slices of whole blocks, one after the other
+  const size_t perBlock = (sizeof(KzgBlock) + 64) + cap * 2 + xs.perBlock + (xs.hashInts + xs.aux32) * 4 +
+                          (size_t)es.maxChunks * (sizeof(KzgChunkInfo) + es.tabStride * 4) + nf + 16;
+  const size_t budget = arena_budget();
+  const int sliceBlocks = (int)std::max<size_t>(1, std::min<size_t>((size_t)nBlocks, (budget > (2u << 20) ? budget - (2u << 20) : 0) / (perBlock + perBlock / 8)));
+  r = ws_reserve((size_t)std::min(nBlocks, sliceBlocks) * perBlock + (1 << 20), (size_t)std::min(nBlocks, sliceBlocks) * (sizeof(KzgBlock) + 16 + nf) + 4096); if (r < 0) return r;
   const int gDec = getenv("KZG_DEC_GROUPS") ? std::max(1, std::min(KZG_DEC_MAXG, atoi(getenv("KZG_DEC_GROUPS")))) : 12;   // developer knob (read per call)
-  const int G = (nBlocks >= 8) ? std::min(gDec, nBlocks / 2) : 1;
-  if (G > 1) { r = ws_side_init(); if (r < 0) return r; }
   EvSet ev;
-  if (timing3) { r = ev.create(3); if (r < 0) return r; CUDA_TRY(cudaEventRecord(ev[0], W.stream)); }
-  if (G > 1) CUDA_TRY(cudaEventRecord(W.sideEv[KZG_DEC_MAXG], W.stream));
+  if (timing3) { r = ev.create(3); if (r < 0) return r; timing3[0] = timing3[1] = timing3[2] = 0; }
   cudaStream_t const mainStream = W.stream;
-  int rc = 0;
-  for (int g = 0; g < G && rc == 0; g++) {
-    const int b0 = (int)((i64)nBlocks * g / G), b1 = (int)((i64)nBlocks * (g + 1) / G), cnt = b1 - b0;
-    cudaStream_t q = (G > 1) ? W.side[g] : mainStream;
-    if (G > 1) CUDA_TRY(cudaStreamWaitEvent(q, W.sideEv[KZG_DEC_MAXG], 0));
-    if (copyIn) {                               // the bytes that hold this group's block records (+ the slack the bit readers touch)
-      const i64 lo = (recs[b0].payBit >> 3) & ~(i64)63;
-      const i64 hi = std::min<i64>(nBytes, ((recs[b1 - 1].payBit + recs[b1 - 1].payBits + 7) >> 3) + 128);
-      if (hi > lo) CUDA_TRY(cudaMemcpyAsync((u8*)d_in + lo, h_in + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, q));
-    }
-    Batch sub = bt;
-    sub.nBlocks = cnt; sub.hBlocks = bt.hBlocks + b0; sub.dBlocks = bt.dBlocks + b0; sub.dResult = bt.dResult + 2 * b0; sub.dDstLimit = bt.dDstLimit + b0;
-    W.stream = q;                               // (the launch helpers enqueue on the calling thread's current stream)
-    do {
-      if (anyEnt) { rc = run_entropy_decode(sub, entropy, es, d_in, dChunks + (size_t)b0 * es.maxChunks, dTab + (size_t)b0 * es.maxChunks * es.tabStride); if (rc < 0) break; }
-      if (anyNone) { rc = run_entropy_decode(sub, KZG_E_NONE, es, d_in, dChunks + (size_t)b0 * es.maxChunks, dTab + (size_t)b0 * es.maxChunks * es.tabStride); if (rc < 0) break; }
-      if (timing3 && g == 0) { if (cudaEventRecord(ev[1], q) != cudaSuccess) { rc = -KZG_ERR_PROCESS_BLOCK; break; } }
-      for (int i = nf - 1; i >= 0; i--) {
-        if (fn[i] == KZG_T_NONE) continue;
-        sub.dEnabled = dEnabledAll + (size_t)i * nb + b0;
-        rc = run_transform_stage(sub, fn[i], i, false, xs, dScratch + (size_t)b0 * xs.perBlock, dHash + (size_t)b0 * xs.hashInts, dAux + (size_t)b0 * xs.aux32, flags);
-        if (rc < 0) break;
-      }
-      if (rc >= 0 && chkBytes) rc = kzg_xxh_launch(q, sub.dBlocks, cnt, 1);       // verify the decoded bytes (CIS:1348-1370)
-    } while (0);
-    W.stream = mainStream;
-    if (rc < 0) break;
-    if (h_out) {                                // every block but the stream's last is blockSize bytes; the last one follows below
-      const int full = (b1 == nBlocks) ? cnt - 1 : cnt;
-      if (full > 0) CUDA_TRY(cudaMemcpyAsync(h_out + (size_t)b0 * blockSize, d_out + (size_t)b0 * blockSize, (size_t)full * blockSize, cudaMemcpyDeviceToHost, q));
-    }
-    if (G > 1) { CUDA_TRY(cudaEventRecord(W.sideEv[g], q)); CUDA_TRY(cudaStreamWaitEvent(mainStream, W.sideEv[g], 0)); }
-  }
-  if (rc < 0) { W.stream = mainStream; for (int g = 0; g < G && G > 1; g++) cudaStreamSynchronize(W.side[g]); return rc; }
-  if (timing3) CUDA_TRY(cudaEventRecord(ev[2], W.stream));
-  r = batch_download(bt); if (r < 0) return r;
-  if (timing3) {      // [1] = entropy stage of the first group, [0] = everything else up to the join (groups overlap: a split, not a sum of kernels)
-    float tot = 0;
-    CUDA_TRY(cudaEventElapsedTime(&timing3[1], ev[0], ev[1])); CUDA_TRY(cudaEventElapsedTime(&tot, ev[0], ev[2])); timing3[0] = tot - timing3[1]; timing3[2] = 0;
-  }
   i64 total = 0;
-  for (int b = 0; b < nBlocks; b++) {
-    const KzgBlock& B = bt.hBlocks[b];
-    if (B.status != 0) { kzg_set_error("block %d failed with status %d", b + 1, B.status); return B.status; }
-    if (B.curLen > blockSize) { kzg_set_error("Block %d incorrectly decompressed", b + 1); return -KZG_ERR_PROCESS_BLOCK; }
-    if (b + 1 < nBlocks && B.curLen != blockSize) { kzg_set_error("short block %d (%d bytes) inside the stream", b + 1, B.curLen); return -KZG_ERR_PROCESS_BLOCK; }
-    if (B.cur != d_out + (size_t)b * blockSize) { kzg_set_error("internal: block %d did not land in place", b + 1); return -KZG_ERR_UNKNOWN; }
-    total += B.curLen;
+  for (int s0 = 0; s0 < nBlocks; s0 += sliceBlocks) {
+    const int sN = std::min(sliceBlocks, nBlocks - s0);
+    const size_t nb = (size_t)sN;
+    W.dOff = 0; W.hOff = 0;
+    Batch bt; bt.nBlocks = sN; bt.maxLen = maxLen;
+    bt.hBlocks = halloc<KzgBlock>(nb); NN(bt.hBlocks);
+    bt.hEnabled = halloc<u8>(nb * nf + 16); NN(bt.hEnabled);
+    bt.hDstLimit = halloc<int>(nb); NN(bt.hDstLimit);
+    bt.dBlocks = dalloc<KzgBlock>(nb); NN(bt.dBlocks);
+    bt.dResult = dalloc<int>(2 * nb); NN(bt.dResult);
+    u8* dEnabledAll = dalloc<u8>(nb * nf + 16); NN(dEnabledAll);
+    bt.dDstLimit = dalloc<int>(nb); NN(bt.dDstLimit);
+    u8* dE = dalloc<u8>(nb * cap); NN(dE);
+    u8* dF = dalloc<u8>(nb * cap); NN(dF);
+    u8* dScratch = dalloc<u8>(nb * xs.perBlock + 16); NN(dScratch);
+    i32* dHash = dalloc<i32>(nb * xs.hashInts + 4); NN(dHash);
+    i32* dAux = dalloc<i32>(nb * xs.aux32 + 4); NN(dAux);
+    KzgChunkInfo* dChunks = dalloc<KzgChunkInfo>(nb * es.maxChunks + 1); NN(dChunks);
+    u32* dTab = dalloc<u32>(nb * es.maxChunks * es.tabStride + 4); NN(dTab);
+    bool anyNone = false, anyEnt = false;
+    for (int b = 0; b < sN; b++) {
+      const int gb = s0 + b;                       // block index in the stream
+      const Rec& rc = recs[gb];
+      KzgBlock& B = bt.hBlocks[b];
+      memset(&B, 0, sizeof(B));
+      int k = 0;     // inverse stages this block runs (Sequence.inverse :160-166 skips flagged transforms)
+      for (int i = 0; i < nf; i++) {
+        const bool runs = (rc.skipFlags != 0xFF) && ((rc.skipFlags & (1 << (7 - i))) == 0) && fn[i] != KZG_T_NONE;
+        bt.hEnabled[(size_t)i * nb + b] = runs ? 1 : 0;
+        if (runs) k++;
+      }
+      u8* dest = d_out + (size_t)gb * blockSize;
+      const i32 avail = (i32)std::min<i64>(blockSize, outCap - (i64)gb * blockSize);    // bytes of the caller's buffer this block owns
+      B.aux0 = dest; B.stagesLeft = k; B.finalCap = avail;
+      B.cur = (k == 0) ? dest : dE + (size_t)b * cap;
+      B.alt = (k == 1) ? dest : dF + (size_t)b * cap;
+      B.aux1 = dF + (size_t)b * cap;
+      B.curLen = rc.preLen; B.preLen = rc.preLen; B.cap = (i32)cap - 64; B.skipFlags = rc.skipFlags;
+      B.entropy = rc.entropy; B.srcBit = rc.payBit; B.srcBits = rc.payBits; B.xxh = rc.xxh; B.chkBytes = chkBytes;
+      if (k == 0 && rc.preLen > avail) { kzg_set_error(rc.preLen > blockSize ? "Block %d incorrectly decompressed" : "output capacity too small for block %d", gb + 1); return rc.preLen > blockSize ? -KZG_ERR_PROCESS_BLOCK : -KZG_ERR_WRITE_FILE; }
+      bt.hDstLimit[b] = blkBuf;
+      if (rc.entropy == KZG_E_NONE) anyNone = true; else anyEnt = true;
+    }
+    CUDA_TRY(cudaMemcpyAsync(dEnabledAll, bt.hEnabled, nb * nf, cudaMemcpyHostToDevice, W.stream));
+    CUDA_TRY(cudaMemcpyAsync(bt.dDstLimit, bt.hDstLimit, nb * sizeof(int), cudaMemcpyHostToDevice, W.stream));
+    r = batch_upload(bt); if (r < 0) return r;
+    // Blocks are independent: contiguous groups of them run the whole decode on streams of their own (most urgent first), so
+    // that the latency-bound kernels of one group (chunk scan, the literal-record chain) overlap the streaming kernels of the
+    // others and, for host buffers, a group's upload / download overlaps the other groups' kernels.
+    const int G = (sN >= 8) ? std::min(gDec, sN / 2) : 1;
+    if (G > 1) { r = ws_side_init(); if (r < 0) return r; }
+    if (timing3) CUDA_TRY(cudaEventRecord(ev[0], W.stream));
+    if (G > 1) CUDA_TRY(cudaEventRecord(W.sideEv[KZG_DEC_MAXG], W.stream));
+    int rc = 0;
+    for (int g = 0; g < G && rc == 0; g++) {
+      const int b0 = (int)((i64)sN * g / G), b1 = (int)((i64)sN * (g + 1) / G), cnt = b1 - b0;
+      cudaStream_t q = (G > 1) ? W.side[g] : mainStream;
+      if (G > 1) CUDA_TRY(cudaStreamWaitEvent(q, W.sideEv[KZG_DEC_MAXG], 0));
+      if (copyIn) {                               // the bytes that hold this group's block records (+ the slack the bit readers touch)
+        const i64 lo = (recs[s0 + b0].payBit >> 3) & ~(i64)63;
+        const i64 hi = std::min<i64>(nBytes, ((recs[s0 + b1 - 1].payBit + recs[s0 + b1 - 1].payBits + 7) >> 3) + 128);
+        if (hi > lo) CUDA_TRY(cudaMemcpyAsync((u8*)d_in + lo, h_in + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, q));
+      }
+      Batch sub = bt;
+      sub.nBlocks = cnt; sub.hBlocks = bt.hBlocks + b0; sub.dBlocks = bt.dBlocks + b0; sub.dResult = bt.dResult + 2 * b0; sub.dDstLimit = bt.dDstLimit + b0;
+      W.stream = q;                               // (the launch helpers enqueue on the calling thread's current stream)
+      do {
+        if (anyEnt) { rc = run_entropy_decode(sub, entropy, es, d_in, dChunks + (size_t)b0 * es.maxChunks, dTab + (size_t)b0 * es.maxChunks * es.tabStride); if (rc < 0) break; }
+        if (anyNone) { rc = run_entropy_decode(sub, KZG_E_NONE, es, d_in, dChunks + (size_t)b0 * es.maxChunks, dTab + (size_t)b0 * es.maxChunks * es.tabStride); if (rc < 0) break; }
+        if (timing3 && g == 0) { if (cudaEventRecord(ev[1], q) != cudaSuccess) { rc = -KZG_ERR_PROCESS_BLOCK; break; } }
+        for (int i = nf - 1; i >= 0; i--) {
+          if (fn[i] == KZG_T_NONE) continue;
+          sub.dEnabled = dEnabledAll + (size_t)i * nb + b0;
+          rc = run_transform_stage(sub, fn[i], i, false, xs, dScratch + (size_t)b0 * xs.perBlock, dHash + (size_t)b0 * xs.hashInts, dAux + (size_t)b0 * xs.aux32, flags);
+          if (rc < 0) break;
+        }
+        if (rc >= 0 && chkBytes) rc = kzg_xxh_launch(q, sub.dBlocks, cnt, 1);       // verify the decoded bytes (CIS:1348-1370)
+      } while (0);
+      W.stream = mainStream;
+      if (rc < 0) break;
+      if (h_out) {                                // every block but the stream's last is blockSize bytes; the last one follows below
+        const int full = (s0 + b1 == nBlocks) ? cnt - 1 : cnt;
+        if (full > 0) CUDA_TRY(cudaMemcpyAsync(h_out + (size_t)(s0 + b0) * blockSize, d_out + (size_t)(s0 + b0) * blockSize, (size_t)full * blockSize, cudaMemcpyDeviceToHost, q));
+      }
+      if (G > 1) { CUDA_TRY(cudaEventRecord(W.sideEv[g], q)); CUDA_TRY(cudaStreamWaitEvent(mainStream, W.sideEv[g], 0)); }
+    }
+    if (rc < 0) { W.stream = mainStream; for (int g = 0; g < G && G > 1; g++) cudaStreamSynchronize(W.side[g]); return rc; }
+    if (timing3) CUDA_TRY(cudaEventRecord(ev[2], W.stream));
+    r = batch_download(bt); if (r < 0) return r;
+    if (timing3) {      // [1] = entropy stage of the first group, [0] = everything else up to the join (groups overlap: a split, not a sum of kernels)
+      float tot = 0, ent = 0;
+      CUDA_TRY(cudaEventElapsedTime(&ent, ev[0], ev[1])); CUDA_TRY(cudaEventElapsedTime(&tot, ev[0], ev[2])); timing3[1] += ent; timing3[0] += tot - ent;
+    }
+    for (int b = 0; b < sN; b++) {
+      const KzgBlock& B = bt.hBlocks[b];
+      const int gb = s0 + b;
+      if (B.status != 0) { kzg_set_error("block %d failed with status %d", gb + 1, B.status); return B.status; }
+      if (B.curLen > blockSize) { kzg_set_error("Block %d incorrectly decompressed", gb + 1); return -KZG_ERR_PROCESS_BLOCK; }
+      if (gb + 1 < nBlocks && B.curLen != blockSize) { kzg_set_error("short block %d (%d bytes) inside the stream", gb + 1, B.curLen); return -KZG_ERR_PROCESS_BLOCK; }
+      if (B.cur != d_out + (size_t)gb * blockSize) { kzg_set_error("internal: block %d did not land in place", gb + 1); return -KZG_ERR_UNKNOWN; }
+      total += B.curLen;
+      if (gb + 1 == nBlocks && h_out && B.curLen > 0 &&
+          cudaMemcpy(h_out + (size_t)gb * blockSize, d_out + (size_t)gb * blockSize, (size_t)B.curLen, cudaMemcpyDeviceToHost) != cudaSuccess) return -KZG_ERR_PROCESS_BLOCK;
+    }
   }
   if (total > outCap) return -KZG_ERR_WRITE_FILE;
-  if (h_out) {
-    const KzgBlock& L = bt.hBlocks[nBlocks - 1];
-    if (L.curLen > 0 && cudaMemcpy(h_out + (size_t)(nBlocks - 1) * blockSize, d_out + (size_t)(nBlocks - 1) * blockSize, (size_t)L.curLen, cudaMemcpyDeviceToHost) != cudaSuccess)
-      return -KZG_ERR_PROCESS_BLOCK;
-  }
   return total;
 }
 

