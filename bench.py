@@ -519,7 +519,9 @@ def main():
 
 
 # scaled-down passes of the other BASELINE.json configs (parity-test cases, not the headline): value / e2e / CPU arm on the same sample
-OTHER = {"cfg1": 1.0, "cfg3": 0.25, "cfg4": 0.064, "cfg5": 1.0 / 32}
+# (cfg4: FPAQ is one dependent chain per block, ~170 cycles per bit on one lane = 25 s per 32 MiB block each way; the default run
+#  codes ONE short block of 4 MiB under -b 32M; a full 32 MiB block is exercised by tests/test_gpu_fullsize.py and `--config cfg4`)
+OTHER = {"cfg1": 1.0, "cfg3": 0.25, "cfg4": 0.0042, "cfg5": 1.0 / 32}
 
 
 def other_configs(torch, K, dev, kstream, flags, a):
@@ -527,12 +529,15 @@ def other_configs(torch, K, dev, kstream, flags, a):
     out = {}
     for cfg, sc in OTHER.items():
         gen, full, transforms, entropy, bs = synth.CONFIGS[cfg]
-        n = max(bs, int(full * sc) // bs * bs)
+        n = max(bs, int(full * sc) // bs * bs) if cfg != "cfg4" else (4 << 20)
         data = gen(n, SEEDS[cfg])
-        t0 = time.time()
         c = Codec(torch, K, dev, data, transforms, entropy, bs, flags)
+        t0 = time.time()
         k = c.gate()
-        reps = 1 if time.time() - t0 > 8 else 3
+        gate_s = time.time() - t0
+        # chains whose codecs are one dependent chain per block (FPAQ, inverse RANK / SRT, ANS1) take seconds per pass at these
+        # block counts: one timed pass each is all the default run can afford
+        reps = 1 if gate_s > 2.0 else 3
         res, e2e = [], []
         for _ in range(reps):
             e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
@@ -540,17 +545,19 @@ def other_configs(torch, K, dev, kstream, flags, a):
             e0.record(kstream); kk = c.enc_dev(); e1.record(kstream); c.dec_dev(kk); e2.record(kstream)
             torch.cuda.synchronize()
             res.append((e0.elapsed_time(e1), e1.elapsed_time(e2)))
+        for _ in range(reps if gate_s <= 8.0 else 0):
             e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             e0.record(kstream); kk = c.enc_host(); e1.record(kstream); c.dec_host(kk); e2.record(kstream)
             torch.cuda.synchronize()
             e2e.append((e0.elapsed_time(e1), e1.elapsed_time(e2)))
-        assert np.array_equal(c.h_back[:n].numpy(), data)
+        if e2e:
+            assert np.array_equal(c.h_back[:n].numpy(), data)
         em, dm = sum(x[0] for x in res) / reps, sum(x[1] for x in res) / reps
-        eem, edm = sum(x[0] for x in e2e) / reps, sum(x[1] for x in e2e) / reps
+        eem, edm = (sum(x[0] for x in e2e) / len(e2e), sum(x[1] for x in e2e) / len(e2e)) if e2e else (None, None)
         mb = n / 1e6
         entry = {"workload": f"{cfg}: {'+'.join(transforms)}&{entropy} -b {bs}, {n} bytes ({(n + bs - 1) // bs} blocks), scale {sc:.4g} of the config",
                  "value": round(mb / ((em + dm) * 1e-3), 2), "encode_MBps": round(mb / (em * 1e-3), 2), "decode_MBps": round(mb / (dm * 1e-3), 2),
-                 "e2e": round(mb / ((eem + edm) * 1e-3), 2), "knz_bytes": int(k), "unit": "MB/s",
+                 "e2e": round(mb / ((eem + edm) * 1e-3), 2) if e2e else None, "knz_bytes": int(k), "unit": "MB/s",
                  "hbm_frac_stream": round((n + k) / ((em + dm) * 1e-3) / 1e9 / 6549.1, 6)}
         if not a.no_cpu_baseline:
             r = cpu_arm(data, transforms, entropy, bs, 64.0, flags)

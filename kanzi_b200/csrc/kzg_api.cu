@@ -765,12 +765,15 @@ static int stream_header(u8* h, int entropy, u64 transformType, i32 blockSize, i
 // h_in (optional): the input is still on the host; it is uploaded here — whole, or, when the chain starts with LZ and the
 // batch is large, a sample per eighth of every block now and the blocks themselves by the LZ stage on its group streams.
 // Device memory one call may take for its arena: what is free now (plus what this thread's arena already holds), less a margin.
-// KZG_ARENA_MB (developer / test knob) lowers it so that small inputs exercise the slicing below.
-static size_t arena_budget() {
+// The driver is only asked (cudaMemGetInfo costs milliseconds, more with many streams alive) when the whole batch does not fit the
+// arena this thread already owns.  KZG_ARENA_MB (developer / test knob) lowers the budget so that small inputs exercise the slicing.
+static size_t arena_budget(size_t wantAll) {
+  const char* e = getenv("KZG_ARENA_MB");
+  if (!e && wantAll <= W.dCap) return ~(size_t)0 >> 2;      // everything fits what is already reserved
   size_t freeB = 0, totalB = 0;
   if (cudaMemGetInfo(&freeB, &totalB) != cudaSuccess) { cudaGetLastError(); freeB = (size_t)8 << 30; }
   size_t budget = (size_t)((double)(freeB + W.dCap) * 0.85);
-  if (const char* e = getenv("KZG_ARENA_MB")) budget = std::min(budget, (size_t)std::max(1, atoi(e)) << 20);
+  if (e) budget = std::min(budget, (size_t)std::max(1, atoi(e)) << 20);
   return budget;
 }
 
@@ -796,7 +799,7 @@ static int64_t compress_impl(const uint8_t* d_in, int64_t n, const int32_t* tran
   // the previous slice's ended (records are independent and bit-granular: COS:1024-1035) — the stream is the same.
   const size_t perBlock = (sizeof(KzgBlock) + 64) + (anyXf ? cap * (nf >= 2 ? 2 : 1) : 0) + xs.perBlock + (xs.hashInts + xs.aux32) * 4 +
                           (size_t)es.maxChunks * (es.hdrStride + es.payStride + es.tabStride * 4) + (size_t)es.segsPerBlock * sizeof(KzgSeg) + KZG_HDR_STRIDE;
-  const size_t budget = arena_budget();
+  const size_t budget = arena_budget((size_t)std::max(nBlocks, 1) * perBlock + (1 << 20));
   const int sliceBlocks = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(nBlocks, 1), (budget > (2u << 20) ? budget - (2u << 20) : 0) / (perBlock + perBlock / 8)));
   const size_t nbMax = (size_t)std::max(std::min(nBlocks, sliceBlocks), 1);
   r = ws_reserve(nbMax * perBlock + (1 << 20), nbMax * (sizeof(KzgBlock) + 32) + 8192); if (r < 0) return r;
@@ -1027,7 +1030,7 @@ static int64_t decompress_impl(const uint8_t* d_in, int64_t nBytes, const uint8_
   // as in compress_impl: blocks that do not all fit the arena run as several slices of whole blocks, one after the other
   const size_t perBlock = (sizeof(KzgBlock) + 64) + cap * 2 + xs.perBlock + (xs.hashInts + xs.aux32) * 4 +
                           (size_t)es.maxChunks * (sizeof(KzgChunkInfo) + es.tabStride * 4) + nf + 16;
-  const size_t budget = arena_budget();
+  const size_t budget = arena_budget((size_t)nBlocks * perBlock + (1 << 20));
   const int sliceBlocks = (int)std::max<size_t>(1, std::min<size_t>((size_t)nBlocks, (budget > (2u << 20) ? budget - (2u << 20) : 0) / (perBlock + perBlock / 8)));
   r = ws_reserve((size_t)std::min(nBlocks, sliceBlocks) * perBlock + (1 << 20), (size_t)std::min(nBlocks, sliceBlocks) * (sizeof(KzgBlock) + 16 + nf) + 4096); if (r < 0) return r;
   const int gDec = getenv("KZG_DEC_GROUPS") ? std::max(1, std::min(KZG_DEC_MAXG, atoi(getenv("KZG_DEC_GROUPS")))) : 12;   // developer knob (read per call)

@@ -19,99 +19,187 @@ __device__ __forceinline__ u32 warp_excl_scan(u32 v, int lane, u32& total) {
 }
 
 // ================================================================================================================
-// ZRLT.forward (ZRLT.java:54-136)
+// ZRLT (ZRLT.java:54-136 forward, 146-233 inverse), tile-parallel: a block is cut into tiles of ZR_TILE input bytes, one
+// warp per tile.  What a tile emits depends on the tiles before it only through a few carried values (forward: the zero run
+// in progress; inverse: the digit sequence in progress and whether an escape is waiting for its payload), so a summary pass
+// (one warp per tile), a scan over the summaries (one warp per block) and an emit pass (one warp per tile) reproduce the
+// sequential result, including every "no room" test of the reference (each one is evaluated with the same dstIdx).
 // ================================================================================================================
-__global__ void __launch_bounds__(32) zrlt_forward_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P) {
-  const int lane = threadIdx.x, b = blockIdx.x;
-  KzgBlock& B = blocks[b];
-  int* res = P.result + 2 * b;
-  if (lane == 0) { res[0] = 0; res[1] = 0; }
-  if (B.status != 0 || !P.enabled[b]) return;
-  const int count = B.curLen;
-  const u8* __restrict__ src = B.cur;
-  u8* __restrict__ dst = B.alt;
-  const int dstEnd = count;                 // "do not expand"
-  u32 dstIdx = 0;
-  u32 carry = 0;                            // zeros pending from earlier tiles
-  bool fail = false;
+#define ZR_TILE 4096
+struct ZrSum { u64 a, b; u32 c, d, e, f; };     // 32 bytes per tile (fields documented at the kernels)
+
+// digit sequence value `val` (leading 1 included; 1 = none) extended by n more digits `bits` (MSB first), in Java int arithmetic
+// (`runLength += runLength + val` wraps, ZRLT.java:186): after 32 or more digits only the last 32 are left
+__device__ __forceinline__ u32 zr_append(u32 val, int n, u32 bits) {
+  if (n == 0) return val;
+  if (n >= 32) return bits;
+  return (val << n) | bits;
+}
+// zeros a digit sequence stands for: runLength - 1 if that is positive as a Java int (:193-196)
+__device__ __forceinline__ u32 zr_zeros(u32 val) { const i32 z = (i32)(val - 1u); return z > 0 ? (u32)z : 0u; }
+// digits of lanes [lo, lo + m) of a ballot of ones, first lane most significant
+__device__ __forceinline__ u32 zr_bits(u32 onemask, int lo, int m) {
+  if (m <= 0) return 0u;
+  const u32 w = (onemask >> lo) & ((m >= 32) ? 0xFFFFFFFFu : ((1u << m) - 1));
+  return __brev(w) >> (32 - m);
+}
+
+// ---- forward: one 32-byte step of the original scan; `carry` = zeros pending before the step -------------------------
+template <bool EMIT>
+__device__ __forceinline__ void zrf_tile(const u8* __restrict__ src, u8* __restrict__ dst, int beg, int end, int dstEnd, u32 carry, u32 dstIdx,
+                                         int lane, ZrSum* sum, int* res) {
   const u32 lowMask = (1u << lane) - 1;
-  for (int base = 0; base < count; base += 32) {
+  bool fail = false, reach = true;          // reach: no non-zero byte of this tile seen yet
+  u32 size0 = 0, lead = 0;
+  for (int base = beg; base < end; base += 32) {
     const int i = base + lane;
-    const bool valid = i < count;
+    const bool valid = i < end;
     const int v = valid ? src[i] : 1;
     const bool z = valid && (v == 0);
     const u32 zmask = __ballot_sync(0xFFFFFFFFu, z);
     const u32 vmask = __ballot_sync(0xFFFFFFFFu, valid);
-    // zeros directly below this lane (plus the carry when they reach the start of the tile)
     const u32 nzBelow = ~zmask & lowMask;
     u32 run;
     if (nzBelow == 0) run = (u32)lane + carry;
     else run = (u32)(lane - 1 - (31 - __clz(nzBelow)));
     u32 size = 0; int lg = 0;
+    const bool first = reach && nzBelow == 0;             // this lane's run reaches the start of the tile
     if (valid && !z) {
       if (run > 0) lg = ilog2(run + 1);
-      size = (u32)lg + ((v >= 0xFE) ? 2u : 1u);
+      size = (u32)((EMIT || !first) ? lg : 0) + ((v >= 0xFE) ? 2u : 1u);
     }
     u32 total;
     const u32 off = warp_excl_scan(size, lane, total);
-    if (valid && !z) {
-      u32 o = dstIdx + off;
-      if (run > 0) {
-        if ((i64)o >= (i64)dstEnd - lg) fail = true;        // :76
-        else { const u32 rl = run + 1; for (int k = lg - 1; k >= 0; k--) dst[o++] = (u8)((rl >> k) & 1); }
-      }
-      if (!fail) {
-        if (v >= 0xFE) {
-          if ((i64)o >= (i64)dstEnd - 1) fail = true;       // :94
-          else { dst[o] = 0xFF; dst[o + 1] = (u8)(v - 0xFE); }
-        } else {
-          if ((i64)o >= (i64)dstEnd) fail = true;           // :111
-          else dst[o] = (u8)(v + 1);
+    if (EMIT) {
+      if (valid && !z) {
+        u32 o = dstIdx + off;
+        if (run > 0) {
+          if ((i64)o >= (i64)dstEnd - lg) fail = true;        // :76
+          else { const u32 rl = run + 1; for (int k = lg - 1; k >= 0; k--) dst[o++] = (u8)((rl >> k) & 1); }
+        }
+        if (!fail) {
+          if (v >= 0xFE) {
+            if ((i64)o >= (i64)dstEnd - 1) fail = true;       // :94
+            else { dst[o] = 0xFF; dst[o + 1] = (u8)(v - 0xFE); }
+          } else {
+            if ((i64)o >= (i64)dstEnd) fail = true;           // :111
+            else dst[o] = (u8)(v + 1);
+          }
         }
       }
-    }
-    if (__any_sync(0xFFFFFFFFu, fail)) { fail = true; break; }
-    dstIdx += total;
-    // trailing zeros of this tile
+      if (__any_sync(0xFFFFFFFFu, fail)) { fail = true; break; }
+      dstIdx += total;
+    } else size0 += total;
     const u32 nzAll = ~zmask & vmask;
+    if (!EMIT && reach && nzAll != 0) lead = carry + (u32)(__ffs(nzAll) - 1);
     if (nzAll == 0) carry += __popc(vmask);
-    else carry = (u32)__popc(vmask) - 1 - (31 - __clz(nzAll));
+    else { carry = (u32)__popc(vmask) - 1 - (31 - __clz(nzAll)); reach = false; }
   }
-  if (!fail && carry > 0) {                 // input ends inside a zero run
-    const u32 rl = carry + 1;
-    const int lg = ilog2(rl);
-    if ((i64)dstIdx >= (i64)dstEnd - lg) fail = true;
-    else if (lane == 0) { for (int k = lg - 1; k >= 0; k--) dst[dstIdx + (lg - 1 - k)] = (u8)((rl >> k) & 1); }
-    dstIdx += lg;
-  }
-  if (lane == 0 && !fail) { res[0] = 1; res[1] = (int)dstIdx; }
+  if (EMIT) { if (fail && lane == 0) res[0] = 0; }
+  else if (lane == 0) { sum->a = size0; sum->c = reach ? carry : lead; sum->d = carry; sum->e = reach ? 1u : 0u; }
 }
-
-// ================================================================================================================
-// ZRLT.inverse (ZRLT.java:146-233)
-// ================================================================================================================
-__global__ void __launch_bounds__(32) zrlt_inverse_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P) {
+// summary: a = bytes emitted except the run digits of the first non-zero byte, c = zeros at the start of the tile (all of it when
+// e = 1), d = zeros at its end.  After the scan: a = dstIdx at the tile, c = zeros pending at its start.
+__global__ void __launch_bounds__(32) zrlt_fwd_sum_kernel(const KzgBlock* __restrict__ blocks, KzgXfParams P) {
+  const int lane = threadIdx.x, b = blockIdx.y, tile = blockIdx.x;
+  const KzgBlock& B = blocks[b];
+  if (B.status != 0 || !P.enabled[b]) return;
+  const int count = B.curLen, beg = tile * ZR_TILE;
+  if (beg >= count) return;
+  ZrSum* sums = reinterpret_cast<ZrSum*>(P.scratch + (i64)b * P.scratchStride);
+  zrf_tile<false>(B.cur, nullptr, beg, min(beg + ZR_TILE, count), count, 0u, 0u, lane, sums + tile, nullptr);
+}
+__global__ void __launch_bounds__(32) zrlt_fwd_scan_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P) {
   const int lane = threadIdx.x, b = blockIdx.x;
   KzgBlock& B = blocks[b];
   int* res = P.result + 2 * b;
   if (lane == 0) { res[0] = 0; res[1] = 0; }
   if (B.status != 0 || !P.enabled[b]) return;
   const int count = B.curLen;
-  const u8* __restrict__ src = B.cur;
-  u8* __restrict__ dst = B.alt;
-  const i64 dstEnd = min(kzg_dst_limit(B, P.dstLimit[b]), B.cap);
-  i64 dstIdx = 0;
-  u64 carryVal = 1;          // run length accumulated by the digit sequence in progress (1 = none)
-  bool pendingEsc = false;   // the previous tile ended with an unpaired 0xFF
+  const int nTiles = (count + ZR_TILE - 1) / ZR_TILE;
+  ZrSum* sums = reinterpret_cast<ZrSum*>(P.scratch + (i64)b * P.scratchStride);
+  u32 carry = 0, off = 0;
+  for (int t0 = 0; t0 < nTiles; t0 += 32) {
+    const int t = t0 + lane;
+    u32 a = 0, c = 0, d = 0, e = 1;
+    if (t < nTiles) { a = (u32)sums[t].a; c = sums[t].c; d = sums[t].d; e = sums[t].e; }
+    u32 myOff = 0, myCarry = 0;
+    const int n = min(32, nTiles - t0);
+    for (int k = 0; k < n; k++) {           // the carried pair walks the 32 summaries (a few shuffles each)
+      const u32 ak = __shfl_sync(0xFFFFFFFFu, a, k), ck = __shfl_sync(0xFFFFFFFFu, c, k);
+      const u32 dk = __shfl_sync(0xFFFFFFFFu, d, k), ek = __shfl_sync(0xFFFFFFFFu, e, k);
+      if (lane == k) { myOff = off; myCarry = carry; }
+      u32 size = ak;
+      if (!ek) { const u32 run = ck + carry; if (run > 0) size += (u32)ilog2(run + 1); carry = dk; }
+      else carry += ck;
+      off += size;
+    }
+    if (t < nTiles) { sums[t].a = myOff; sums[t].c = myCarry; }
+  }
   bool fail = false;
+  u8* __restrict__ dst = B.alt;
+  if (carry > 0) {                          // input ends inside a zero run
+    const u32 rl = carry + 1;
+    const int lg = ilog2(rl);
+    if ((i64)off >= (i64)count - lg) fail = true;
+    else if (lane == 0) { for (int k = lg - 1; k >= 0; k--) dst[off + (lg - 1 - k)] = (u8)((rl >> k) & 1); }
+    off += lg;
+  }
+  if (lane == 0 && !fail) { res[0] = 1; res[1] = (int)off; }     // (the emit pass clears res[0] when one of its tests fails)
+}
+__global__ void __launch_bounds__(32) zrlt_fwd_emit_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P) {
+  const int lane = threadIdx.x, b = blockIdx.y, tile = blockIdx.x;
+  KzgBlock& B = blocks[b];
+  if (B.status != 0 || !P.enabled[b]) return;
+  const int count = B.curLen, beg = tile * ZR_TILE;
+  if (beg >= count) return;
+  const ZrSum* sums = reinterpret_cast<const ZrSum*>(P.scratch + (i64)b * P.scratchStride);
+  zrf_tile<true>(B.cur, B.alt, beg, min(beg + ZR_TILE, count), count, sums[tile].c, (u32)sums[tile].a, lane, nullptr, P.result + 2 * b);
+}
+
+// ---- inverse -----------------------------------------------------------------------------------------------------------
+// 0xFF bytes at the end of every tile (an escape pairs with the byte after it: whether a tile starts with a payload byte is the
+// parity of the 0xFF run that ends at its first byte)
+__global__ void __launch_bounds__(32) zrlt_inv_ff_kernel(const KzgBlock* __restrict__ blocks, KzgXfParams P, int maxTiles) {
+  const int lane = threadIdx.x, b = blockIdx.y, tile = blockIdx.x;
+  const KzgBlock& B = blocks[b];
+  if (B.status != 0 || !P.enabled[b]) return;
+  const int count = B.curLen, beg = tile * ZR_TILE;
+  if (beg >= count) return;
+  const int end = min(beg + ZR_TILE, count);
+  const u8* __restrict__ src = B.cur;
+  int cnt = 0;
+  for (int top = end; top > beg; top -= 32) {         // 32 bytes at a time from the end
+    const int i = top - 1 - lane;
+    const bool valid = i >= beg;
+    const u32 nonFF = __ballot_sync(0xFFFFFFFFu, valid && src[i] != 0xFF);
+    if (nonFF == 0) { cnt += min(32, top - beg); continue; }
+    cnt += __ffs(nonFF) - 1;
+    break;
+  }
+  u32* ff = reinterpret_cast<u32*>(P.scratch + (i64)b * P.scratchStride + (i64)maxTiles * sizeof(ZrSum));
+  if (lane == 0) ff[tile] = (u32)cnt;
+}
+__device__ __forceinline__ bool zri_pending_esc(const u32* ff, int tile) {
+  u32 run = 0;
+  for (int u = tile - 1; u >= 0; u--) { const u32 c = ff[u]; run += c; if (c != ZR_TILE) break; }
+  return (run & 1u) != 0;
+}
+
+// one tile of the original scan.  EMIT = false: sizes only (a digit sequence entering the tile counts as absent: the scan corrects)
+template <bool EMIT>
+__device__ __forceinline__ void zri_tile(const u8* __restrict__ src, u8* __restrict__ dst, int beg, int end, i64 dstEnd, u32 carryVal, bool pendingEsc,
+                                         i64 dstIdx, int lane, ZrSum* sum, int* res) {
   const u32 lowMask = (1u << lane) - 1;
-  for (int base = 0; base < count; base += 32) {
+  bool fail = false, lead = true;       // lead: every byte of the tile so far is a digit
+  u64 sizeLocal = 0;
+  int nL = 0; u32 bitsL = 0;
+  for (int base = beg; base < end; base += 32) {
     const int i = base + lane;
-    const bool valid = i < count;
+    const bool valid = i < end;
     const int v = valid ? src[i] : 2;
     const u32 vmask = __ballot_sync(0xFFFFFFFFu, valid);
     const u32 ffmask = __ballot_sync(0xFFFFFFFFu, valid && v == 0xFF);
-    // escapes pair up with their payload: byte is a payload iff the 0xFF run directly below it has odd length
     const u32 nonFFBelow = ~ffmask & lowMask;
     bool payload;
     if (nonFFBelow == 0) payload = (((lane & 1) != 0) != pendingEsc);
@@ -121,62 +209,121 @@ __global__ void __launch_bounds__(32) zrlt_inverse_kernel(KzgBlock* __restrict__
     const bool esc = valid && !payload && v == 0xFF;
     const u32 dmask = __ballot_sync(0xFFFFFFFFu, digit);
     const u32 onemask = __ballot_sync(0xFFFFFFFFu, digit && v == 1);
-    // digits directly below this lane
     const u32 ndBelow = ~dmask & lowMask;
     int k; bool reachesStart;
     if (ndBelow == 0) { k = lane; reachesStart = true; }
     else { k = lane - 1 - (31 - __clz(ndBelow)); reachesStart = false; }
-    u64 zeros = 0;
+    u32 zeros = 0;
     const bool closer = valid && !digit && !payload;          // literal or escape: closes a digit run if one precedes it
-    if (closer) {
-      const u32 bits = (k > 0) ? (__brev((onemask >> (lane - k)) & ((k == 32) ? 0xFFFFFFFFu : ((1u << k) - 1))) >> (32 - k)) : 0u;
-      const u64 base1 = reachesStart ? carryVal : 1ull;
-      const u64 value = (k >= 40 || base1 > (1ull << 40)) ? (1ull << 62) : ((base1 << k) | (u64)bits);
-      zeros = value - 1;
-    }
+    if (closer) zeros = zr_zeros(zr_append(reachesStart ? carryVal : 1u, k, zr_bits(onemask, lane - k, k)));
     const bool lit = closer && !esc;
-    if (zeros >= (u64)dstEnd) { fail = true; zeros = 0; }
-    if (__any_sync(0xFFFFFFFFu, fail)) { fail = true; break; }
-    u32 size = (u32)zeros + ((lit || payload) ? 1u : 0u);
-    u32 total;
-    const u32 off = warp_excl_scan(size, lane, total);
-    // bounds: a run followed by its closer needs dstIdx + run < dstEnd (:172); every byte needs dstIdx < dstEnd
-    const i64 o = dstIdx + off;
-    if (closer && zeros > 0 && o + (i64)zeros >= dstEnd) fail = true;
-    if ((lit || payload) && o + (i64)zeros >= dstEnd) fail = true;
-    if (__any_sync(0xFFFFFFFFu, fail)) { fail = true; break; }
-    if (zeros > 0 && zeros <= 64) for (u32 t = 0; t < (u32)zeros; t++) dst[o + t] = 0;
-    if (lit) dst[o + zeros] = (u8)(v - 1);
-    else if (payload) dst[o] = (u8)(0xFE + v);
-    // long runs: the whole warp fills them
-    u32 longMask = __ballot_sync(0xFFFFFFFFu, zeros > 64);
-    while (longMask) {
-      const int l = __ffs(longMask) - 1;
-      longMask &= longMask - 1;
-      const i64 o2 = __shfl_sync(0xFFFFFFFFu, o, l);
-      const u32 z2 = __shfl_sync(0xFFFFFFFFu, (u32)zeros, l);
-      for (u32 t = lane; t < z2; t += 32) dst[o2 + t] = 0;
-    }
-    dstIdx += total;
-    // carries
     const int nv = __popc(vmask);
     const u32 ndAll = ~dmask & vmask;
-    if (ndAll == 0) {           // the whole tile is digits
-      const u32 bits = __brev(onemask & vmask) >> (32 - nv);
-      carryVal = (carryVal > (1ull << 40)) ? (1ull << 62) : ((carryVal << nv) | (u64)bits);
+    if (EMIT) {
+      if ((i64)zeros >= dstEnd) { fail = true; zeros = 0; }
+      if (__any_sync(0xFFFFFFFFu, fail)) { fail = true; break; }
+      const u32 size = zeros + ((lit || payload) ? 1u : 0u);
+      u32 total;
+      const u32 off = warp_excl_scan(size, lane, total);
+      // bounds: a run followed by its closer needs dstIdx + run < dstEnd (:172); every byte needs dstIdx < dstEnd
+      const i64 o = dstIdx + off;
+      if (closer && zeros > 0 && o + (i64)zeros >= dstEnd) fail = true;
+      if ((lit || payload) && o + (i64)zeros >= dstEnd) fail = true;
+      if (__any_sync(0xFFFFFFFFu, fail)) { fail = true; break; }
+      if (zeros > 0 && zeros <= 64) for (u32 t = 0; t < (u32)zeros; t++) dst[o + t] = 0;
+      if (lit) dst[o + zeros] = (u8)(v - 1);
+      else if (payload) dst[o] = (u8)(0xFE + v);
+      u32 longMask = __ballot_sync(0xFFFFFFFFu, zeros > 64);       // long runs: the whole warp fills them
+      while (longMask) {
+        const int l = __ffs(longMask) - 1;
+        longMask &= longMask - 1;
+        const i64 o2 = __shfl_sync(0xFFFFFFFFu, o, l);
+        const u32 z2 = __shfl_sync(0xFFFFFFFFu, zeros, l);
+        for (u32 t = lane; t < z2; t += 32) dst[o2 + t] = 0;
+      }
+      dstIdx += total;
     } else {
+      u64 size = (u64)zeros + ((lit || payload) ? 1u : 0u);
+      for (int o = 16; o > 0; o >>= 1) size += __shfl_xor_sync(0xFFFFFFFFu, size, o);
+      sizeLocal += size;
+      if (lead) {                             // digits before the tile's first non-digit byte
+        const int m = (ndAll == 0) ? nv : (__ffs(ndAll) - 1);
+        bitsL = zr_append(bitsL, m, zr_bits(onemask, 0, m)); nL = min(nL + m, 64);
+        if (ndAll != 0) lead = false;
+      }
+    }
+    if (ndAll == 0) carryVal = zr_append(carryVal, nv, zr_bits(onemask, 0, nv));      // the whole step is digits
+    else {
       const int top = 31 - __clz(ndAll);            // highest non-digit lane
       const int t = nv - 1 - top;                   // trailing digits
-      carryVal = (t > 0) ? ((1ull << t) | (u64)(__brev((onemask >> (top + 1)) & ((1u << t) - 1)) >> (32 - t))) : 1ull;
+      carryVal = zr_append(1u, t, zr_bits(onemask, top + 1, t));
     }
     pendingEsc = (__shfl_sync(0xFFFFFFFFu, (int)esc, nv - 1) != 0);
   }
-  if (!fail && carryVal > 1) {      // trailing zeros (:221-229)
-    const u64 zeros = carryVal - 1;
-    if (dstIdx + (i64)zeros > dstEnd || zeros > (1ull << 31)) fail = true;
-    else { for (u64 t = lane; t < zeros; t += 32) dst[dstIdx + t] = 0; dstIdx += (i64)zeros; }
+  if (EMIT) { if (fail && lane == 0) res[0] = 0; }
+  else {
+    // a = bytes emitted with no digit sequence entering, b = digit sequence in progress at the end, c / d = number (capped at 64) and
+    // value (last 32) of the digits before the first non-digit byte, e = 1: the tile is digits only
+    if (lane == 0) { sum->a = sizeLocal; sum->b = carryVal; sum->c = (u32)nL; sum->d = bitsL; sum->e = lead ? 1u : 0u; sum->f = 0; }
   }
-  if (lane == 0 && !fail) { res[0] = 1; res[1] = (int)dstIdx; }
+}
+__global__ void __launch_bounds__(32) zrlt_inv_sum_kernel(const KzgBlock* __restrict__ blocks, KzgXfParams P, int maxTiles) {
+  const int lane = threadIdx.x, b = blockIdx.y, tile = blockIdx.x;
+  const KzgBlock& B = blocks[b];
+  if (B.status != 0 || !P.enabled[b]) return;
+  const int count = B.curLen, beg = tile * ZR_TILE;
+  if (beg >= count) return;
+  ZrSum* sums = reinterpret_cast<ZrSum*>(P.scratch + (i64)b * P.scratchStride);
+  const u32* ff = reinterpret_cast<const u32*>(P.scratch + (i64)b * P.scratchStride + (i64)maxTiles * sizeof(ZrSum));
+  zri_tile<false>(B.cur, nullptr, beg, min(beg + ZR_TILE, count), 0, 1u, zri_pending_esc(ff, tile), 0, lane, sums + tile, nullptr);
+}
+__global__ void __launch_bounds__(32) zrlt_inv_scan_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P) {
+  const int lane = threadIdx.x, b = blockIdx.x;
+  KzgBlock& B = blocks[b];
+  int* res = P.result + 2 * b;
+  if (lane == 0) { res[0] = 0; res[1] = 0; }
+  if (B.status != 0 || !P.enabled[b]) return;
+  const int count = B.curLen;
+  const i64 dstEnd = min(kzg_dst_limit(B, P.dstLimit[b]), B.cap);
+  const int nTiles = (count + ZR_TILE - 1) / ZR_TILE;
+  ZrSum* sums = reinterpret_cast<ZrSum*>(P.scratch + (i64)b * P.scratchStride);
+  u32 carry = 1; u64 off = 0;
+  bool fail = false;
+  if (lane == 0) {
+    for (int t = 0; t < nTiles; t++) {
+      const ZrSum S = sums[t];
+      sums[t].a = off; sums[t].b = carry;
+      if (S.e) { carry = zr_append(carry, (int)S.c, S.d); continue; }
+      // the digit sequence that enters the tile changes the run its first non-digit byte closes
+      u64 size = S.a - zr_zeros(zr_append(1u, (int)S.c, S.d)) + zr_zeros(zr_append(carry, (int)S.c, S.d));
+      if (size > (1ull << 32)) { fail = true; size = 0; }
+      off += size;
+      if (off > (1ull << 32)) { fail = true; off = 0; }
+      carry = (u32)S.b;
+    }
+  }
+  carry = __shfl_sync(0xFFFFFFFFu, carry, 0); off = __shfl_sync(0xFFFFFFFFu, off, 0);
+  fail = __shfl_sync(0xFFFFFFFFu, (int)fail, 0) != 0;
+  u8* __restrict__ dst = B.alt;
+  if (!fail && (i32)carry > 0) {      // the input ends inside a digit sequence: runLength - 1 trailing zeros (:221-229)
+    const u64 zeros = carry - 1;
+    if ((i64)off + (i64)zeros > dstEnd) fail = true;
+    else { for (u64 t = lane; t < zeros; t += 32) dst[off + t] = 0; off += zeros; }
+  }
+  if (lane == 0 && !fail) { res[0] = 1; res[1] = (int)off; }      // (the emit pass clears res[0] when one of its tests fails)
+}
+__global__ void __launch_bounds__(32) zrlt_inv_emit_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P, int maxTiles) {
+  const int lane = threadIdx.x, b = blockIdx.y, tile = blockIdx.x;
+  KzgBlock& B = blocks[b];
+  if (B.status != 0 || !P.enabled[b]) return;
+  const int count = B.curLen, beg = tile * ZR_TILE;
+  if (beg >= count) return;
+  const ZrSum* sums = reinterpret_cast<const ZrSum*>(P.scratch + (i64)b * P.scratchStride);
+  const u32* ff = reinterpret_cast<const u32*>(P.scratch + (i64)b * P.scratchStride + (i64)maxTiles * sizeof(ZrSum));
+  int* res = P.result + 2 * b;
+  if (res[0] == 0) return;                 // the scan already failed the block
+  const i64 dstEnd = min(kzg_dst_limit(B, P.dstLimit[b]), B.cap);
+  zri_tile<true>(B.cur, B.alt, beg, min(beg + ZR_TILE, count), dstEnd, (u32)sums[tile].b, zri_pending_esc(ff, tile), (i64)sums[tile].a, lane, nullptr, res);
 }
 
 // ================================================================================================================
@@ -440,73 +587,123 @@ __device__ void srt_preprocess(SrtSmem& S, int lane) {
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(32) srt_forward_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P) {
-  __shared__ SrtSmem S;
-  const int lane = threadIdx.x, b = blockIdx.x;
-  KzgBlock& B = blocks[b];
-  int* res = P.result + 2 * b;
-  if (lane == 0) { res[0] = 0; res[1] = 0; }
+// ---- SRT forward, tile-parallel ------------------------------------------------------------------------------------------
+// The rank SRT emits for position i is the move-to-front rank of its symbol c in a list that starts in order of first
+// appearance (:92-106): the number of symbols whose last occurrence is later than c's, a symbol never seen counting as earliest
+// (the first occurrence of the b-th distinct symbol is emitted as b).  The byte goes to slot (occurrences of c before i) of c's
+// bucket; buckets are ordered by (frequency desc, symbol asc) (preprocess :270-302).  Three kernels, tiles of 4096 positions:
+// per tile and symbol {occurrences, last occurrence}; one CTA per block (a thread per symbol) turns them into every tile's entry
+// state {occurrences before the tile, last occurrence before the tile}, the bucket starts and the header; one warp per tile
+// replays its positions from that state with the 256 keys in registers (8 per lane).
+#define SRT_TILE 4096
+__global__ void __launch_bounds__(32) srt_fwd_tile_kernel(const KzgBlock* __restrict__ blocks, KzgXfParams P) {
+  __shared__ int cnt[256], last[256];
+  const int lane = threadIdx.x, b = blockIdx.y, tile = blockIdx.x;
+  const KzgBlock& B = blocks[b];
   if (B.status != 0 || !P.enabled[b]) return;
   const int count = B.curLen;
+  const int beg = tile * SRT_TILE;
+  if (beg >= count || count + 1024 > B.cap) return;
+  const int end = min(beg + SRT_TILE, count);
   const u8* __restrict__ src = B.cur;
-  u8* __restrict__ dst = B.alt;
-  if (count + 1024 > B.cap) return;
-  for (int i = lane; i < 256; i += 32) { S.freqs[i] = 0; S.firstPos[i] = 0x7FFFFFFF; S.r2s[i] = 0; S.s2r[i] = 0; }
+  for (int i = lane; i < 256; i += 32) { cnt[i] = 0; last[i] = -1; }
   __syncwarp();
-  for (int i = lane; i < count; i += 32) { const int c = src[i]; atomicAdd(&S.freqs[c], 1); atomicMin(&S.firstPos[c], i); }
-  __syncwarp();
-  // first symbols in order of appearance (:92-106): rank of firstPos among present symbols
-  for (int c = lane; c < 256; c += 32) {
-    if (S.freqs[c] == 0) continue;
-    int rk = 0;
-    for (int o = 0; o < 256; o++) if (S.firstPos[o] < S.firstPos[c]) rk++;
-    S.r2s[rk] = (u8)c; S.s2r[c] = (u8)rk;
+  for (int base = beg; base < end; base += 32) {
+    const int p = base + lane;
+    const bool on = p < end;
+    const int c = on ? (int)src[p] : 256 + lane;
+    const u32 peers = __match_any_sync(0xFFFFFFFFu, c);
+    if (on && (peers >> lane) == 1u) { cnt[c] += __popc(peers); last[c] = p; }      // highest lane of its symbol group
+    __syncwarp();
   }
-  __syncwarp();
-  srt_preprocess(S, lane);
-  if (lane == 0) {
-    int bucketPos = 0;
-    for (int i = 0; i < S.nbSymbols; i++) { const int c = S.symbols[i]; S.buckets[c] = bucketPos; bucketPos += S.freqs[c]; }
-    int k = 0;                              // encodeHeader (:312-325)
+  int* info = reinterpret_cast<int*>(P.scratch + (i64)b * P.scratchStride) + 512 + (i64)tile * 512;
+  for (int i = lane; i < 256; i += 32) { info[i] = cnt[i]; info[256 + i] = last[i]; }
+}
+__global__ void __launch_bounds__(256) srt_fwd_scan_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P) {
+  __shared__ int freqs[256];
+  __shared__ int hdrLen;
+  const int b = blockIdx.x, sym = threadIdx.x;
+  KzgBlock& B = blocks[b];
+  int* res = P.result + 2 * b;
+  if (sym == 0) { res[0] = 0; res[1] = 0; }
+  if (B.status != 0 || !P.enabled[b]) return;
+  const int count = B.curLen;
+  if (count == 0) { if (sym == 0) res[0] = 1; return; }       // :74-75
+  if (count + 1024 > B.cap) return;
+  const int nTiles = (count + SRT_TILE - 1) / SRT_TILE;
+  int* head = reinterpret_cast<int*>(P.scratch + (i64)b * P.scratchStride);       // [0,256) bucket starts, [256] header length
+  int* info = head + 512;
+  int occ = 0, lst = -1;
+  for (int t0 = 0; t0 < nTiles; t0 += 8) {       // eight tiles' loads in flight, then their entry states replace them
+    int c[8], l[8];
+    #pragma unroll
+    for (int k = 0; k < 8; k++) if (t0 + k < nTiles) { c[k] = info[(i64)(t0 + k) * 512 + sym]; l[k] = info[(i64)(t0 + k) * 512 + 256 + sym]; }
+    #pragma unroll
+    for (int k = 0; k < 8; k++) if (t0 + k < nTiles) {
+      info[(i64)(t0 + k) * 512 + sym] = occ; info[(i64)(t0 + k) * 512 + 256 + sym] = lst;
+      occ += c[k]; if (l[k] >= 0) lst = l[k];
+    }
+  }
+  freqs[sym] = occ;
+  __syncthreads();
+  int start = 0;                                 // bytes in the buckets ordered before this symbol's (preprocess :270-302)
+  for (int o = 0; o < 256; o++) { const int f = freqs[o]; if (f > occ || (f == occ && o < sym)) start += f; }
+  head[sym] = start;
+  if (sym == 0) {
+    u8* __restrict__ dst = B.alt;
+    int k = 0;                                   // encodeHeader (:312-325)
     for (int i = 0; i < 256; i++) {
-      u32 f = (u32)S.freqs[i];
+      u32 f = (u32)freqs[i];
       while (f >= 128) { dst[k++] = (u8)(0x80 | f); f >>= 7; }
       dst[k++] = (u8)f;
     }
-    S.hdrLen = k;
+    head[256] = k;
+    res[0] = 1; res[1] = k + count;
+  }
+}
+__global__ void __launch_bounds__(32) srt_fwd_rank_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P) {
+  __shared__ u32 K[256];
+  __shared__ int slot[256];
+  const int lane = threadIdx.x, b = blockIdx.y, tile = blockIdx.x;
+  KzgBlock& B = blocks[b];
+  if (B.status != 0 || !P.enabled[b]) return;
+  const int count = B.curLen;
+  const int beg = tile * SRT_TILE;
+  if (beg >= count || count + 1024 > B.cap) return;
+  const int end = min(beg + SRT_TILE, count);
+  const u8* __restrict__ src = B.cur;
+  const int* head = reinterpret_cast<const int*>(P.scratch + (i64)b * P.scratchStride);
+  const int* info = head + 512 + (i64)tile * 512;
+  u8* __restrict__ out = B.alt + head[256];
+  u32 kr[8];
+  #pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const int d = lane + 32 * k;
+    kr[k] = (u32)(info[256 + d] + 1);            // key = last occurrence + 1, 0 = never seen
+    K[d] = kr[k];
+    slot[d] = head[d] + info[d];                 // where this symbol's next rank goes
   }
   __syncwarp();
-  const int hdr = S.hdrLen;
-  u8* __restrict__ out = dst + hdr;
-  // encoding (:139-164): MTF rank at the head of every run, zeros for the rest of the run, bucketed by symbol
-  int i = 0;
-  while (i < count) {
-    const int c = src[i];
-    const int r = S.s2r[c];
-    int p = S.buckets[c];
-    __syncwarp();
-    if (lane == 0) out[p] = (u8)r;
-    p++;
-    if (r != 0) {
-      list_shift_up<false, true>(S.r2s, nullptr, S.s2r, 0, r, lane);
-      if (lane == 0) { S.r2s[0] = (u8)c; S.s2r[c] = 0; }
+  for (int base = beg; base < end; base += 32) {
+    const int nIn = min(32, end - base);
+    const int mine = (lane < nIn) ? (int)src[base + lane] : 0;
+    for (int t = 0; t < nIn; t++) {
+      const int c = __shfl_sync(0xFFFFFFFFu, mine, t);
+      const u32 kc = K[c];
+      int cnt = 0;
+      #pragma unroll
+      for (int k = 0; k < 8; k++) cnt += (kr[k] > kc) ? 1 : 0;
+      const int r = (int)__reduce_add_sync(0xFFFFFFFFu, (unsigned)cnt);
+      const u32 nk = (u32)(base + t + 1);
+      __syncwarp();
+      if (lane == 0) { K[c] = nk; const int sl = slot[c]; slot[c] = sl + 1; out[sl] = (u8)r; }
+      if (lane == (c & 31)) {
+        #pragma unroll
+        for (int k = 0; k < 8; k++) if (k == (c >> 5)) kr[k] = nk;
+      }
       __syncwarp();
     }
-    i++;
-    // rest of the run
-    while (i < count) {
-      const int k = i + lane;
-      const bool same = (k < count) && (src[k] == c);
-      const u32 m = __ballot_sync(0xFFFFFFFFu, !same);
-      const int n = m ? (__ffs(m) - 1) : 32;
-      if (lane < n) out[p + lane] = 0;
-      p += n; i += n;
-      if (m) break;
-    }
-    if (lane == 0) S.buckets[c] = p;
-    __syncwarp();
   }
-  if (lane == 0) { res[0] = 1; res[1] = hdr + count; }
 }
 
 __global__ void __launch_bounds__(32) srt_inverse_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P) {
@@ -610,15 +807,31 @@ __global__ void __launch_bounds__(32) srt_inverse_kernel(KzgBlock* __restrict__ 
 
 // ---- launchers -------------------------------------------------------------------------------------------------------
 void kzg_small_scratch(int type, i32 maxLen, bool forward, size_t* perBlockBytes, size_t*) {
+  // SRT forward: per tile of 4096 positions and symbol {occurrences, last occurrence} (2 KiB), 2 KiB of bucket starts in front
+  if (forward && type == KZG_T_SRT) *perBlockBytes = std::max(*perBlockBytes, ((size_t)maxLen / SRT_TILE + 3) * 2048);
+  // ZRLT: a 32-byte summary per tile of 4096 input bytes (+ the inverse's 0xFF counts)
+  if (type == KZG_T_ZRLT) *perBlockBytes = std::max(*perBlockBytes, ((size_t)maxLen / ZR_TILE + 2) * (sizeof(ZrSum) + 4) + 64);
   // SBRT forward: per tile of 4096 positions the last two occurrences of every symbol (2 KiB), then the tile's entry state
   if (forward && (type == KZG_T_RANK || type == KZG_T_MTFT)) *perBlockBytes = std::max(*perBlockBytes, ((size_t)maxLen / SBRT_TILE + 2) * 2048);
 }
 
-int kzg_zrlt_launch(cudaStream_t s, bool forward, KzgBlock* d_blocks, int nBlocks, const KzgXfParams& P) {
-  if (forward) zrlt_forward_kernel<<<nBlocks, 32, 0, s>>>(d_blocks, P);
-  else zrlt_inverse_kernel<<<nBlocks, 32, 0, s>>>(d_blocks, P);
+int kzg_zrlt_launch(cudaStream_t s, bool forward, KzgBlock* d_blocks, int nBlocks, const KzgXfParams& P, i32 maxLen) {
+  const int tiles = std::max(1, (maxLen + ZR_TILE - 1) / ZR_TILE);
+  if (((size_t)maxLen / ZR_TILE + 2) * (sizeof(ZrSum) + 4) + 64 > (size_t)P.scratchStride) { kzg_set_error("zrlt: scratch pool too small"); return -KZG_ERR_CREATE_CODEC; }
+  const dim3 grid(tiles, nBlocks);
+  if (forward) {
+    KZG_PROF("zrlt_fwd_sum_kernel", s, (zrlt_fwd_sum_kernel<<<grid, 32, 0, s>>>(d_blocks, P)));
+    KZG_PROF("zrlt_fwd_scan_kernel", s, (zrlt_fwd_scan_kernel<<<nBlocks, 32, 0, s>>>(d_blocks, P)));
+    KZG_PROF("zrlt_fwd_emit_kernel", s, (zrlt_fwd_emit_kernel<<<grid, 32, 0, s>>>(d_blocks, P)));
+    kzg_count_launch(3);
+  } else {
+    KZG_PROF("zrlt_inv_ff_kernel", s, (zrlt_inv_ff_kernel<<<grid, 32, 0, s>>>(d_blocks, P, tiles + 1)));
+    KZG_PROF("zrlt_inv_sum_kernel", s, (zrlt_inv_sum_kernel<<<grid, 32, 0, s>>>(d_blocks, P, tiles + 1)));
+    KZG_PROF("zrlt_inv_scan_kernel", s, (zrlt_inv_scan_kernel<<<nBlocks, 32, 0, s>>>(d_blocks, P)));
+    KZG_PROF("zrlt_inv_emit_kernel", s, (zrlt_inv_emit_kernel<<<grid, 32, 0, s>>>(d_blocks, P, tiles + 1)));
+    kzg_count_launch(4);
+  }
   CUDA_TRY(cudaGetLastError());
-  kzg_count_launch(1);
   return 0;
 }
 int kzg_sbrt_launch(cudaStream_t s, bool forward, int mode, KzgBlock* d_blocks, int nBlocks, const KzgXfParams& P, i32 maxLen) {
@@ -634,9 +847,15 @@ int kzg_sbrt_launch(cudaStream_t s, bool forward, int mode, KzgBlock* d_blocks, 
   kzg_count_launch(1);
   return 0;
 }
-int kzg_srt_launch(cudaStream_t s, bool forward, KzgBlock* d_blocks, int nBlocks, const KzgXfParams& P) {
-  if (forward) srt_forward_kernel<<<nBlocks, 32, 0, s>>>(d_blocks, P);
-  else srt_inverse_kernel<<<nBlocks, 32, 0, s>>>(d_blocks, P);
+int kzg_srt_launch(cudaStream_t s, bool forward, KzgBlock* d_blocks, int nBlocks, const KzgXfParams& P, i32 maxLen) {
+  if (forward) {
+    const int tiles = std::max(1, (maxLen + SRT_TILE - 1) / SRT_TILE);
+    if (((size_t)maxLen / SRT_TILE + 3) * 2048 > (size_t)P.scratchStride) { kzg_set_error("srt: scratch pool too small"); return -KZG_ERR_CREATE_CODEC; }
+    KZG_PROF("srt_fwd_tile_kernel", s, (srt_fwd_tile_kernel<<<dim3(tiles, nBlocks), 32, 0, s>>>(d_blocks, P)));
+    KZG_PROF("srt_fwd_scan_kernel", s, (srt_fwd_scan_kernel<<<nBlocks, 256, 0, s>>>(d_blocks, P)));
+    KZG_PROF("srt_fwd_rank_kernel", s, (srt_fwd_rank_kernel<<<dim3(tiles, nBlocks), 32, 0, s>>>(d_blocks, P)));
+    kzg_count_launch(2);
+  } else KZG_PROF("srt_inverse_kernel", s, (srt_inverse_kernel<<<nBlocks, 32, 0, s>>>(d_blocks, P)));
   CUDA_TRY(cudaGetLastError());
   kzg_count_launch(1);
   return 0;

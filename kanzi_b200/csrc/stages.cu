@@ -90,10 +90,10 @@ void kzg_stage_scratch(int type, i32 maxLen, bool forward, size_t* perBlockBytes
 
 int kzg_stage_launch(cudaStream_t s, int type, bool forward, KzgBlock* d_blocks, int nBlocks, const KzgXfParams& P, i32 maxLen) {
   switch (type) {
-    case KZG_T_ZRLT: return kzg_zrlt_launch(s, forward, d_blocks, nBlocks, P);
+    case KZG_T_ZRLT: return kzg_zrlt_launch(s, forward, d_blocks, nBlocks, P, maxLen);
     case KZG_T_RANK: return kzg_sbrt_launch(s, forward, 2, d_blocks, nBlocks, P, maxLen);
     case KZG_T_MTFT: return kzg_sbrt_launch(s, forward, 1, d_blocks, nBlocks, P, maxLen);
-    case KZG_T_SRT: return kzg_srt_launch(s, forward, d_blocks, nBlocks, P);
+    case KZG_T_SRT: return kzg_srt_launch(s, forward, d_blocks, nBlocks, P, maxLen);
     case KZG_T_BWT: return kzg_bwtblock_launch(s, forward, d_blocks, nBlocks, P, maxLen);
     case KZG_T_ROLZ: return kzg_rolz_launch(s, forward, d_blocks, nBlocks, P, maxLen);
     default: kzg_set_error("transform id %d has no kernel", type); return -KZG_ERR_INVALID_CODEC;

@@ -146,6 +146,58 @@ def test_transform_bit_exact(tr):
     assert applied > 5
 
 
+def _zrlt_cases():
+    """Inputs whose carried state crosses the 4096-byte tiles of the ZRLT kernels: zero runs, digit sequences and 0xFF escapes that
+    end on, straddle or span whole tiles; valid and invalid encodings for the inverse."""
+    r = corpus.rng(4321)
+    T = 4096
+    c = {}
+    c["zeros_tile"] = bytes(T)
+    c["zeros_3tiles_then_x"] = bytes(3 * T) + b"x" + bytes(5) + b"y"
+    c["x_then_zeros_over_edge"] = b"q" * (T - 3) + bytes(9) + b"r" * 100
+    c["zeros_end_at_edge"] = b"q" * (T - 7) + bytes(7) + b"r" * T + bytes(T) + b"s"
+    c["ends_in_long_run"] = b"abc" * 1000 + bytes(2 * T + 17)
+    c["ff_over_edge"] = b"a" * (T - 2) + b"\xff" * 5 + b"b" * 50 + b"\xfe" * 3
+    c["ff_tiles"] = b"\xff" * (2 * T + 1) + b"z" * 10
+    c["fe_ff_zero_mix"] = bytes(r.choice([0, 0, 0, 0xFE, 0xFF, 7], 5 * T + 33).astype(np.uint8))
+    c["sparse"] = bytes(np.where(r.random(6 * T + 5) < 0.97, 0, r.integers(1, 256, 6 * T + 5)).astype(np.uint8))
+    c["dense"] = bytes(np.where(r.random(4 * T) < 0.3, 0, r.integers(1, 256, 4 * T)).astype(np.uint8))
+    return c
+
+
+def test_zrlt_tiles_bit_exact():
+    """ZRLT.forward / inverse (K/transform/ZRLT.java:54-233) across tile boundaries, and the inverse on arbitrary bytes (streams no
+    encoder produces: digit runs of any length, unpaired escapes): same boolean, same bytes as the oracle."""
+    for name, d in _zrlt_cases().items():
+        ok_ref, ref, _, _ = O.transform("ZRLT", d, dst_cap=len(d))
+        ok, got, used = K.transform_forward("ZRLT", d, {"blockSize": max(len(d), 1024), "flags": 0}, dst_cap=len(d))
+        assert int(ok) == ok_ref, (name, ok, ok_ref)
+        if ok:
+            assert got == ref, (name, first_diff(got, ref))
+            ok2, back, _ = K.transform_inverse("ZRLT", ref, {"blockSize": max(len(d), 1024), "flags": 0}, dst_cap=len(d) + 512)
+            assert ok2 and back == d, (name, first_diff(back, d))
+    r = corpus.rng(99)
+    T = 4096
+    inv = {
+        "digits_only": bytes(r.integers(0, 2, 20, dtype=np.uint8)),
+        "digits_then_lit_over_edge": b"\x05" * (T - 6) + bytes([1, 0, 1, 1, 0, 1, 0, 1, 1, 0, 0, 1]) + b"\x09" * 40,
+        "short_digit_runs": bytes(r.choice([0, 1, 5, 9, 0xFF], 3 * T + 11, p=[.2, .2, .25, .25, .1]).astype(np.uint8)),
+        "too_many_digits": b"\x03" * 10 + bytes(r.integers(0, 2, 40, dtype=np.uint8)) + b"\x04",
+        "digit_tile": b"\x03" + bytes(r.integers(0, 2, T + 50, dtype=np.uint8)) + b"\x04",
+        "esc_at_end": b"\x07" * (T - 1) + b"\xff",
+        "esc_pairs_over_edges": (b"\x07" * (T - 1) + b"\xff\x01") * 3,
+        "ff_run_odd": b"\x02" * 10 + b"\xff" * (T + 1) + b"\x01\x00\x01\x06",
+        "zeros_17_trailing": b"\x02\x02" + bytes([0, 0, 0, 1]),
+    }
+    for name, d in inv.items():
+        for cap in (len(d) + 70000, 64):
+            ok_ref, ref, _, _ = O.transform("ZRLT", d, inverse=True, dst_cap=cap)
+            ok, got, _ = K.transform_inverse("ZRLT", d, {"blockSize": 1 << 20, "flags": 0}, dst_cap=cap)
+            assert int(ok) == ok_ref, (name, cap, ok, ok_ref)
+            if ok:
+                assert got == ref, (name, cap, len(got), len(ref), first_diff(got, ref))
+
+
 def test_transform_interfaces_like_reference_test():
     # T/test/TestTransforms.java:255-337 flow with SliceByteArray objects
     d = CASES["text64k"]
