@@ -398,6 +398,7 @@ __device__ __forceinline__ u32 ans_pay8(const u8* __restrict__ stream, i64 payBi
 
 // ANSRangeDecoder.decodeHeader (:452-544) for one context: fills freq[256] (0 for absent symbols).
 // Returns alphabetSize, or -1 on an invalid header.
+template <bool CLEAR = true>
 __device__ int ans_decode_ctx_header(BitReaderD& br, int lr, int llr, u16* freq, u8* alphabet, bool& cleared) {
   int alphabetSize = 0;
   if (br.read(1) == 0) {
@@ -414,7 +415,7 @@ __device__ int ans_decode_ctx_header(BitReaderD& br, int lr, int llr, u16* freq,
   }
   if (alphabetSize == 0) return 0;
   const int scale = 1 << lr;
-  if (alphabetSize != 256) { for (int i = 0; i < 256; i++) freq[i] = 0; cleared = true; }
+  if (CLEAR && alphabetSize != 256) { for (int i = 0; i < 256; i++) freq[i] = 0; cleared = true; }
   const int chkSize = (alphabetSize >= 64) ? 8 : 6;
   int sum = 0;
   for (int i = 1; i < alphabetSize; i += chkSize) {
@@ -762,13 +763,22 @@ __global__ void __launch_bounds__(32) ans0_decode_kernel(KzgBlock* __restrict__ 
 }
 
 // ================================================================================================================
-// order 1: one warp per chunk (4 MiB), 4 lanes code, lane 0 builds the 256-context tables in global memory
+// order 1: one CTA per chunk (4 MiB); the 256-context tables live in global memory (L2-resident)
 // ================================================================================================================
-// per-chunk global scratch (encode): symA[256][256], symB[256][256], freq[256][257] (u32), alpha[256]
-// per-chunk global scratch (decode): f2s[256][2048] (u8), sym[256][256] (u32), freq[256] (u16), alpha[256]
+// encode, per-chunk global scratch (u32 units): sym[256][256] (uint2 {invFreq, packed}), freq[256][257], pad, hdrPriv[256][120],
+// alpha[256][256 bytes].  256 threads: histogram (one red.global per byte), one context per thread (normalizeFrequencies, Symbol
+// tables, its header bits into a private buffer), the headers merged bit-granularly into the chunk header; then warp 0 codes:
+// lanes 0-3 run the four states in lock step while all 32 lanes fetch the Symbol entries two batches of 32 steps ahead
+// (data byte -> table entry are dependent global loads; the rANS recurrence itself never waits for memory).
+// decode, per-chunk global scratch: f2s[256][2048] (u8), sym[256][256] (u32), freq[256] (u16), alpha[256]
+#define A1_THREADS 256
+#define A1_HDR_WORDS 120          // private header buffer per context: 2 + 5 + 256 alphabet bits, 43 groups x 4 + 255 x 11 frequency bits < 480 bytes
+#define A1_BATCH 32
 
-__global__ void __launch_bounds__(32) ans1_encode_kernel(const KzgBlock* __restrict__ blocks, KzgEntParams P) {
-  const int lane = threadIdx.x;
+__global__ void __launch_bounds__(A1_THREADS) ans1_encode_kernel(const KzgBlock* __restrict__ blocks, KzgEntParams P) {
+  __shared__ uint2 ring[2][4][A1_BATCH];
+  __shared__ u32 scanBuf[A1_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.y;
   const int c = blockIdx.x;
   const KzgBlock& B = blocks[b];
@@ -780,14 +790,14 @@ __global__ void __launch_bounds__(32) ans1_encode_kernel(const KzgBlock* __restr
   const i64 gidx = (P.slotBase ? (i64)P.slotBase[b] : (i64)b * P.maxChunks) + c;
   KzgSeg* segs = P.segs + (i64)b * P.segsPerBlock + 1 + (i64)c * 2;
   if (len <= 32) {
-    if (lane == 0) {
+    if (tid == 0) {
       segs[0] = (c == 0 && len > 0) ? KzgSeg{data, 0, 0, (u64)len * 8} : KzgSeg{nullptr, 0, 0, 0};
       segs[1] = KzgSeg{nullptr, 0, 0, 0};
     }
     return;
   }
   if ((i64)c * chunkSize >= (i64)len) {          // (64-bit: the grid may be far wider than this block's chunk count)
-    if (lane == 0) { segs[0] = KzgSeg{nullptr, 0, 0, 0}; segs[1] = KzgSeg{nullptr, 0, 0, 0}; }
+    if (tid == 0) { segs[0] = KzgSeg{nullptr, 0, 0, 0}; segs[1] = KzgSeg{nullptr, 0, 0, 0}; }
     return;
   }
   const int start = c * chunkSize;
@@ -796,62 +806,93 @@ __global__ void __launch_bounds__(32) ans1_encode_kernel(const KzgBlock* __restr
   u8* pay = P.payBuf + gidx * (i64)P.payStride;
   const int bufLen = P.payStride - 16;
   u32* tab = P.tabBuf + gidx * (i64)P.tabStride;       // u32 units
-  u32* symA = tab;                       // [256][256]
-  u32* symB = tab + 65536;               // [256][256]
-  u32* freq = tab + 2 * 65536;           // [256][257]
-  u8* alpha = (u8*)(tab + 2 * 65536 + 256 * 257);
+  uint2* sym = reinterpret_cast<uint2*>(tab);          // [256 contexts][256 symbols]
+  u32* freq = tab + 2 * 65536;                         // [256][257]
+  u32* hdrPriv = tab + 2 * 65536 + 256 * 257 + 64;     // [256][A1_HDR_WORDS]
+  u8* alphaAll = (u8*)(hdrPriv + 256 * A1_HDR_WORDS);  // [256][256]
 
+  // Symbol objects are re-created per encode() call (:277-282): zero = "new Symbol()"
+  for (int k = tid; k < 2 * 65536 + 256 * 257; k += A1_THREADS) tab[k] = 0;
+  __syncthreads();
   // ---- order-1 histogram: first byte of each quarter in context 0 (rebuildStatistics :430-446) ----
-  for (int k = lane; k < 256 * 257; k += 32) freq[k] = 0;
-  for (int k = lane; k < 2 * 65536; k += 32) tab[k] = 0;   // Symbol objects are re-created per encode() call (:277-282): zero = "new Symbol()"
-  __syncwarp();
   {
     const int quarter = (end - start) >> 2;
     if (quarter == 0) {
-      if (lane == 0) {
+      if (tid == 0) {
         int prv = 0;
-        for (int i = start; i < end; i++) { freq[prv * 257 + data[i]]++; freq[prv * 257 + 256]++; prv = data[i]; }
+        for (int i = start; i < end; i++) { freq[prv * 257 + data[i]]++; prv = data[i]; }
       }
     } else {
-      // four quarters, each walked by 8 lanes over contiguous sub-ranges
-      const int q = lane >> 3, t = lane & 7;
-      const int qs = start + q * quarter;
-      const int per = (quarter + 7) >> 3;
-      const int s0 = qs + t * per, e0 = min(s0 + per, qs + quarter);
-      for (int i = s0; i < e0; i++) {
-        const int prv = (i == qs) ? 0 : data[i - 1];
-        atomicAdd(&freq[prv * 257 + data[i]], 1u);
-        atomicAdd(&freq[prv * 257 + 256], 1u);
-      }
-    }
-  }
-  __syncwarp();
-  __threadfence_block();
-
-  i64 hdrBits = 0;
-  if (lane == 0) {
-    BitWriterD bw(hdr);
-    bw.write((u32)(lr - 8), 3);
-    for (int k = 0; k < 256; k++) {
-      u32* f = freq + k * 257;
-      const int alphabetSize = ans_normalize(f, alpha, (int)f[256], 1 << lr);
-      if (alphabetSize > 0) {
-        int sum = 0;
-        for (int i = 0; i < alphabetSize; i++) {
-          const int s = alpha[i];
-          ans_symbol_reset(symA[k * 256 + s], symB[k * 256 + s], sum, (int)f[s], lr);
-          sum += (int)f[s];
+      const int n4 = 4 * quarter;
+      for (int p0 = tid * 4; p0 < n4; p0 += A1_THREADS * 4) {
+        int prv = (p0 > 0) ? (int)data[start + p0 - 1] : 0;
+        #pragma unroll
+        for (int r = 0; r < 4; r++) {
+          const int p = p0 + r;
+          if (p >= n4) break;
+          const int cur = data[start + p];
+          if (p == quarter || p == 2 * quarter || p == 3 * quarter) prv = 0;
+          atomicAdd(&freq[prv * 257 + cur], 1u);
+          prv = cur;
         }
       }
-      ans_encode_header(bw, alphabetSize, alpha, f, lr);
     }
-    hdrBits = bw.bits();
+  }
+  __syncthreads();
+
+  // ---- one context per thread: statistics, Symbol table, header bits ----
+  u32 myBits;
+  {
+    const int k = tid;
+    u32* f = freq + k * 257;
+    u8* alpha = alphaAll + k * 256;
+    u32 total = 0;
+    for (int i = 0; i < 256; i++) total += f[i];
+    const int alphabetSize = ans_normalize(f, alpha, (int)total, 1 << lr);
+    if (alphabetSize > 0) {
+      int sum = 0;
+      for (int i = 0; i < alphabetSize; i++) {
+        const int sy = alpha[i];
+        u32 sa, sb;
+        ans_symbol_reset(sa, sb, sum, (int)f[sy], lr);
+        sym[k * 256 + sy] = make_uint2(sa, sb);
+        sum += (int)f[sy];
+      }
+    }
+    BitWriterD bw((u8*)(hdrPriv + k * A1_HDR_WORDS));
+    if (k == 0) bw.write((u32)(lr - 8), 3);
+    ans_encode_header(bw, alphabetSize, alpha, f, lr);
+    myBits = (u32)bw.bits();
     bw.flush();
   }
-  __syncwarp();
+  // exclusive scan of the header lengths over the 256 contexts
+  u32 incl = myBits;
+  for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+  if (lane == 31) scanBuf[warp] = incl;
+  __syncthreads();
+  u32 wbase = 0, hdrBits32 = 0;
+  for (int w = 0; w < A1_THREADS / 32; w++) { const u32 t = scanBuf[w]; if (w < warp) wbase += t; hdrBits32 += t; }
+  const u32 myOff = wbase + incl - myBits;
+  u32* hdrW = reinterpret_cast<u32*>(hdr);
+  for (u32 w = tid; w < (hdrBits32 >> 5) + 2; w += A1_THREADS) hdrW[w] = 0;
+  __syncthreads();
+  {
+    const u32* src = hdrPriv + tid * A1_HDR_WORDS;
+    for (u32 w = 0; w * 32 < myBits; w++) {
+      u32 v = __byte_perm(src[w], 0, 0x0123);                   // the 32 bits in stream order, first bit = MSB
+      const u32 left = myBits - w * 32;
+      if (left < 32) v &= ~(0xFFFFFFFFu >> left);
+      const u32 d = myOff + w * 32, wi = d >> 5, sh = d & 31;
+      atomicOr(&hdrW[wi], __byte_perm(v >> sh, 0, 0x0123));
+      if (sh) atomicOr(&hdrW[wi + 1], __byte_perm(v << (32 - sh), 0, 0x0123));
+    }
+  }
   __threadfence_block();
+  __syncthreads();
+  if (warp != 0) return;
+  const i64 hdrBits = (i64)hdrBits32;
 
-  // ---- encodeChunk order 1 (:359-390): state q codes quarter q backwards; lanes 0..3 ----
+  // ---- encodeChunk order 1 (:359-390): state q codes quarter q backwards ----
   const int end4 = start + ((end - start) & -4);
   int n = bufLen - 1;
   const int tail = end - end4;
@@ -862,41 +903,77 @@ __global__ void __launch_bounds__(32) ans1_encode_kernel(const KzgBlock* __restr
   u32 st = ANS_TOP;
   int idx = n;
   const u32 lowerMask = (1u << (j & 3)) - 1;
-  // Java: i_q = start + (q+1)*quarter - 2, prv_q = block[i_q + 1]; loop while i0 >= start (quarter-1 steps), then "last symbols" in ctx 0
-  int iq = start + (j + 1) * quarter - 2;
-  int prv = 0;
-  if (j < 4) {
-    const int pi = iq + 1;     // may be start-1 when quarter == 0 (degenerate chunk < 4 bytes, SURVEY E-8): pi >= 0 since start > 0 there
-    prv = (pi >= 0) ? data[pi] : 0;
-  }
+  // Java: i_q = start + (q+1)*quarter - 2, prv_q = block[i_q + 1]; loop while i0 >= start (quarter-1 steps), then "last symbols" in ctx 0.
+  // Step s of quarter q codes symbol block[i_q + 1 - s] in context block[i_q - s] (context 0 at the last step, s == steps).
   const int steps = (quarter > 0) ? quarter - 1 : 0;
-  for (int s = 0; s <= steps; s++) {
-    u32 a = 0, bb = 0;
-    bool x = false;
+  const int fq = lane >> 3, fsub = lane & 7;                   // fetch role: quarter fq, steps [4 * fsub, 4 * fsub + 4) of a batch
+  const i64 fiq = (i64)start + (i64)(fq + 1) * quarter - 2;
+  const int nBatches = steps / A1_BATCH + 1;
+  u32 dat[2] = {0, 0};       // the five bytes of a batch (four symbols + contexts): dat[0] = bytes p-3..p, dat[1] = byte p+1, p = i_q - S - 4 fsub
+  uint2 tv[4];
+  auto loadData = [&](int bt, u32* d) {
+    d[0] = 0; d[1] = 0;
+    const i64 s0 = (i64)bt * A1_BATCH + 4 * fsub;
+    if (bt >= nBatches || s0 > steps) return;
+    const i64 p = fiq - s0;              // context position of the batch's first step for this lane
+    #pragma unroll
+    for (int r = 0; r < 4; r++) { const i64 q = p - 3 + r; if (q >= 0 && q >= (i64)start - 1) d[0] |= (u32)data[q] << (8 * r); }
+    if (p + 1 >= 0) d[1] = data[p + 1];
+  };
+  auto loadTab = [&](int bt, const u32* d, uint2* t) {
+    const i64 s0 = (i64)bt * A1_BATCH + 4 * fsub;
+    #pragma unroll
+    for (int r = 0; r < 4; r++) {
+      t[r] = make_uint2(0, 0);
+      const i64 s = s0 + r;
+      if (bt >= nBatches || s > steps) continue;
+      // step s: context byte at p - r (byte 3 - r of d[0]), symbol at p - r + 1
+      const u32 sy = (r == 0) ? d[1] : ((d[0] >> (8 * (4 - r))) & 0xFF);
+      const u32 cx = (s == steps) ? 0u : ((d[0] >> (8 * (3 - r))) & 0xFF);
+      t[r] = sym[cx * 256 + sy];
+    }
+  };
+  auto storeTab = [&](int bt, const uint2* t) {
+    #pragma unroll
+    for (int r = 0; r < 4; r++) ring[bt & 1][fq][4 * fsub + r] = t[r];
+  };
+  u32 dnext[2];
+  uint2 tnext[4];
+  loadData(0, dat); loadTab(0, dat, tv); storeTab(0, tv);
+  loadData(1, dat); loadTab(1, dat, tv);
+  loadData(2, dat);
+  __syncwarp();
+  for (int bt = 0; bt < nBatches; bt++) {
+    loadTab(bt + 2, dat, tnext);           // in flight while this batch is coded
+    loadData(bt + 3, dnext);
+    const int cnt = min(A1_BATCH, steps + 1 - bt * A1_BATCH);
     const bool on = j < 4;
-    int cur = 0;
-    if (on) {
-      const bool last = (s == steps);      // last symbols: symbols[0][prv] (:386-389)
-      cur = last ? 0 : data[iq];
-      a = symA[cur * 256 + prv]; bb = symB[cur * 256 + prv];
+    #pragma unroll 4
+    for (int s = 0; s < cnt; s++) {
+      const uint2 e = ring[bt & 1][j & 3][s];
+      const u32 a = e.x, bb = e.y;
       // uninitialised Symbol (all zero) reproduces Java's default object: xMax 0, bias 0, cmplFreq 0, invFreq 0, invShift 0
       const bool zeroSym = (a == 0 && bb == 0);
       const u32 xMax = zeroSym ? 0u : (((u32)(1 << lr) - ((bb >> 14) & 0x3FFF)) << (31 - lr));
-      x = ((i32)st >= (i32)xMax);
-    }
-    const u32 m = __ballot_sync(0xFFFFFFFFu, x) & 0xFu;
-    if (on) {
-      if (x) {
-        const int pos = idx - 2 * __popc(m & lowerMask);
-        pay[pos] = (u8)st;
-        pay[pos - 1] = (u8)(st >> 8);
-        st = (u32)((i32)st >> 16);
+      const bool x = on && ((i32)st >= (i32)xMax);
+      const u32 m = __ballot_sync(0xFFFFFFFFu, x) & 0xFu;
+      if (on) {
+        if (x) {
+          const int pos = idx - 2 * __popc(m & lowerMask);
+          pay[pos] = (u8)st;
+          pay[pos - 1] = (u8)(st >> 8);
+          st = (u32)((i32)st >> 16);
+        }
+        idx -= 2 * __popc(m);
+        if (!zeroSym) st = ans_enc_step(st, a, bb);
       }
-      idx -= 2 * __popc(m);
-      if (!(a == 0 && bb == 0)) st = ans_enc_step(st, a, bb);
-      prv = cur;
-      iq--;
     }
+    __syncwarp();
+    storeTab(bt + 1, tv);
+    __syncwarp();
+    #pragma unroll
+    for (int r = 0; r < 4; r++) tv[r] = tnext[r];
+    dat[0] = dnext[0]; dat[1] = dnext[1];
   }
   const u32 s1 = __shfl_sync(0xFFFFFFFFu, st, 1);
   const u32 s2 = __shfl_sync(0xFFFFFFFFu, st, 2);
@@ -914,8 +991,17 @@ __global__ void __launch_bounds__(32) ans1_encode_kernel(const KzgBlock* __restr
   }
 }
 
-__global__ void __launch_bounds__(32) ans1_decode_kernel(KzgBlock* __restrict__ blocks, KzgEntParams P) {
-  const int lane = threadIdx.x;
+// decode, per-chunk global scratch (u32 units): sym[256][256] (freq | cum << 16), f2s[256][2048] (u8), freqAll[256][256] (u16).
+// 256 threads: thread 0 walks the 256 context headers (a serial bit stream), every thread then builds one context's cumulative
+// frequencies and slot -> symbol table; warp 0 decodes: lanes 0-3 run the four states, the coded bytes stream through a
+// shared-memory ring that all 32 lanes refill a batch of 32 steps ahead (no lane waits for a global payload load).
+#define A1D_RING 1024
+__global__ void __launch_bounds__(A1_THREADS) ans1_decode_kernel(KzgBlock* __restrict__ blocks, KzgEntParams P) {
+  __shared__ __align__(16) u8 ring[A1D_RING];
+  __shared__ u8 declared[256];
+  __shared__ u8 alphaS[256];
+  __shared__ int hdrState[2];          // lr, bad
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.y;
   const int c = blockIdx.x;
   KzgBlock& B = blocks[b];
@@ -924,7 +1010,7 @@ __global__ void __launch_bounds__(32) ans1_decode_kernel(KzgBlock* __restrict__ 
   u8* __restrict__ out = B.cur;
   const u8* __restrict__ stream = P.stream;
   if (len <= 32) {
-    if (blockOk && c == 0 && lane == 0) for (int i = 0; i < len; i++) out[i] = (u8)get_bits(stream, (u64)B.srcBit + 8ull * i, 8);
+    if (blockOk && c == 0 && tid == 0) for (int i = 0; i < len; i++) out[i] = (u8)get_bits(stream, (u64)B.srcBit + 8ull * i, 8);
     return;
   }
   const int chunkSize = P.chunkSize;
@@ -936,41 +1022,45 @@ __global__ void __launch_bounds__(32) ans1_decode_kernel(KzgBlock* __restrict__ 
   u32* tab = P.tabBuf + ((P.slotBase ? (i64)P.slotBase[b] : (i64)b * P.maxChunks) + c) * (i64)P.tabStride;
   u32* sym = tab;                               // [256][256] freq | cum << 16
   u8* f2s = (u8*)(tab + 65536);                 // [256][2048]  (logRange <= 11 for order 1)
-  u16* freq = (u16*)(f2s + 256 * 2048);         // [256] scratch for one context
-  u8* alpha = (u8*)(freq + 256);
-  u8* declared = alpha + 256;                   // [256] context has a table
+  u16* freqAll = (u16*)(f2s + 256 * 2048);      // [256][256]
 
-  int lr = 11, bad = 0;
-  if (lane == 0) {
+  // frequencies do not persist across contexts here: a context's header either declares a symbol or leaves it absent
+  for (int k = tid; k < 256 * 256 / 2; k += A1_THREADS) reinterpret_cast<u32*>(freqAll)[k] = 0;
+  declared[tid] = 0;
+  __syncthreads();
+  if (tid == 0) {
     BitReaderD br(stream, (u64)info.hdrBit, (u64)(B.srcBit + B.srcBits));
-    lr = 8 + (int)br.read(3);
+    int lr = 8 + (int)br.read(3), bad = 0;
     int llr = 3;
     while ((1 << llr) <= lr) llr++;
     if (lr > 11) bad = 1;   // order-1 tables sized for the reference's logRange 11 (ANSRangeEncoder :112,135)
     for (int k = 0; k < 256 && !bad; k++) {
-      declared[k] = 0;
-      for (int i = 0; i < 256; i++) freq[i] = 0;   // frequencies persist across chunks in Java only when the alphabet is full; a full alphabet overwrites all 256
-      bool cleared = false;
-      const int as = ans_decode_ctx_header(br, lr, llr, freq, alpha, cleared);
+      bool cleared = true;      // (the row is zero already)
+      const int as = ans_decode_ctx_header<false>(br, lr, llr, freqAll + k * 256, alphaS, cleared);
       if (as < 0) { bad = 1; break; }
-      if (as == 0) continue;
-      declared[k] = 1;
-      int sum = 0;
-      for (int i = 0; i < 256; i++) {
-        const int f = freq[i];
-        if (f == 0) continue;
-        for (int t = f - 1; t >= 0; t--) f2s[k * 2048 + sum + t] = (u8)i;
-        const int fe = (f >= (1 << lr)) ? (1 << lr) - 1 : f;
-        sym[k * 256 + i] = (u32)fe | ((u32)sum << 16);
-        sum += f;
-      }
+      if (as > 0) declared[k] = 1;
+    }
+    hdrState[0] = lr; hdrState[1] = bad;
+  }
+  __syncthreads();
+  const int lr = hdrState[0];
+  if (hdrState[1]) { if (tid == 0) atomicExch(&B.status, -KZG_ERR_PROCESS_BLOCK); return; }
+  if (declared[tid]) {
+    const int k = tid;
+    const u16* fr = freqAll + k * 256;
+    int sum = 0;
+    for (int i = 0; i < 256; i++) {
+      const int f = fr[i];
+      if (f == 0) continue;
+      for (int t = f - 1; t >= 0; t--) f2s[k * 2048 + sum + t] = (u8)i;
+      const int fe = (f >= (1 << lr)) ? (1 << lr) - 1 : f;
+      sym[k * 256 + i] = (u32)fe | ((u32)sum << 16);
+      sum += f;
     }
   }
-  lr = __shfl_sync(0xFFFFFFFFu, lr, 0);
-  bad = __shfl_sync(0xFFFFFFFFu, bad, 0);
-  __syncwarp();
   __threadfence_block();
-  if (bad) { if (lane == 0) atomicExch(&B.status, -KZG_ERR_PROCESS_BLOCK); return; }
+  __syncthreads();
+  if (warp != 0) return;
 
   // ---- decodeChunkV2 order 1 (:406-432): lane j walks quarter j with state st_j; read order st3, st2, st1, st0 ----
   const int end4 = start + ((end - start) & -4);
@@ -986,27 +1076,60 @@ __global__ void __launch_bounds__(32) ans1_decode_kernel(KzgBlock* __restrict__ 
   const i64 payBit = info.payBit;
   const int sz = info.sz;
   int undeclared = 0;
-  for (int s = 0; s < quarter; s++) {
-    bool need = false;
-    if (j < 4) {
-      const int slot = st & mask;
-      if (!declared[prv]) undeclared = 1;
-      const int cur = f2s[prv * 2048 + slot];
-      const u32 fc = sym[prv * 256 + cur];
-      out[pos] = (u8)cur;
-      st = (i32)((fc & 0xFFFFu) * ((u32)st >> lr) + (u32)slot - (fc >> 16));
-      need = st < ANS_TOP;
-      prv = cur;
-      pos++;
+  // coded bytes [fill, fill + 256): lane l fetches bytes fill + 8 l .. + 7 (zero beyond sz, as ans_pay16 reads them)
+  auto fetch8 = [&](int fill, u32* w) {
+    w[0] = 0; w[1] = 0;
+    const int o = fill + 8 * lane;
+    if (o >= sz) return;
+    const u64 bp = (u64)payBit + 8ull * (u64)o;
+    const u8* p = stream + (bp >> 3);
+    const int sh = (int)(bp & 7);
+    u32 prevB = p[0];
+    #pragma unroll
+    for (int k = 0; k < 8; k++) {
+      if (o + k >= sz) break;
+      const u32 nextB = p[k + 1];
+      w[k >> 2] |= (((prevB << sh) | (nextB >> (8 - sh))) & 0xFFu) << (8 * (k & 3));
+      prevB = nextB;
     }
-    const u32 m = __ballot_sync(0xFFFFFFFFu, need) & 0xFu;
-    if (j < 4) {
+  };
+  auto put8 = [&](int fill, const u32* w) {
+    *reinterpret_cast<uint2*>(ring + ((fill + 8 * lane) & (A1D_RING - 1))) = make_uint2(w[0], w[1]);
+  };
+  u32 w8[2];
+  int fill = 0;
+  fetch8(0, w8); put8(0, w8); fetch8(256, w8); put8(256, w8);
+  fill = 512;
+  __syncwarp();
+  for (int s0 = 0; s0 < quarter; s0 += 32) {
+    const bool doFill = (fill - cursor) <= A1D_RING - 256;     // uniform: cursor is the same in every coding lane... (lanes >= 4 keep it too)
+    if (doFill) fetch8(fill, w8);
+    const int cnt = min(32, quarter - s0);
+    #pragma unroll 4
+    for (int s = 0; s < cnt; s++) {
+      bool need = false;
+      if (j < 4) {
+        const int slot = st & mask;
+        if (!declared[prv]) undeclared = 1;
+        const int cur = f2s[prv * 2048 + slot];
+        const u32 fc = sym[prv * 256 + cur];
+        out[pos] = (u8)cur;
+        st = (i32)((fc & 0xFFFFu) * ((u32)st >> lr) + (u32)slot - (fc >> 16));
+        need = st < ANS_TOP;
+        prv = cur;
+        pos++;
+      }
+      const u32 m = __ballot_sync(0xFFFFFFFFu, need) & 0xFu;
       if (need) {
         const int off = cursor + 2 * __popc(m & upperMask);
-        st = (i32)(((u32)st << 16) | ans_pay16(stream, payBit, off, sz));
+        const u32 h = *reinterpret_cast<const u16*>(ring + (off & (A1D_RING - 1)));      // two coded bytes, big-endian in the stream
+        st = (i32)(((u32)st << 16) | __byte_perm(h, 0, 0x4401));
       }
       cursor += 2 * __popc(m);
     }
+    __syncwarp();
+    if (doFill) { put8(fill, w8); fill += 256; }
+    __syncwarp();
   }
   undeclared = __any_sync(0xFFFFFFFFu, undeclared);
   if (lane == 0) {
@@ -1026,7 +1149,7 @@ int kzg_ans_encode_launch(cudaStream_t s, const KzgBlock* d_blocks, int nBlocks,
     KZG_PROF("ans0_encode_kernel", s, (ans0_encode_kernel<<<grid, 128, sizeof(A0EncSmem), s>>>(d_blocks, P)));
   } else {
     dim3 grid(P.maxChunks, nBlocks);
-    ans1_encode_kernel<<<grid, 32, 0, s>>>(d_blocks, P);
+    KZG_PROF("ans1_encode_kernel", s, (ans1_encode_kernel<<<grid, A1_THREADS, 0, s>>>(d_blocks, P)));
   }
   CUDA_TRY(cudaGetLastError());
   kzg_count_launch(1);
@@ -1045,12 +1168,12 @@ int kzg_ans_decode_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, const
     KZG_PROF("ans0_decode_kernel", s, (ans0_decode_kernel<<<grid, 32, 0, s>>>(d_blocks, P)));
   } else {
     dim3 grid(P.maxChunks, nBlocks);
-    ans1_decode_kernel<<<grid, 32, 0, s>>>(d_blocks, P);
+    KZG_PROF("ans1_decode_kernel", s, (ans1_decode_kernel<<<grid, A1_THREADS, 0, s>>>(d_blocks, P)));
   }
   CUDA_TRY(cudaGetLastError());
   kzg_count_launch(2);
   return 0;
 }
 
-size_t kzg_ans1_enc_tab_u32() { return 2 * 65536 + 256 * 257 + 64 + 16; }
-size_t kzg_ans1_dec_tab_u32() { return 65536 + (256 * 2048) / 4 + 128 + 64 + 64 + 16; }
+size_t kzg_ans1_enc_tab_u32() { return 2 * 65536 + 256 * 257 + 64 + 256 * A1_HDR_WORDS + 256 * 256 / 4 + 16; }
+size_t kzg_ans1_dec_tab_u32() { return 65536 + (256 * 2048) / 4 + (256 * 256) / 2 + 64 + 16; }

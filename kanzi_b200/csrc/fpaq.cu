@@ -40,27 +40,33 @@ __global__ void __launch_bounds__(32) fpaq_encode_kernel(const KzgBlock* __restr
     int idx = 0;
     bool overflow = false;
     int* p = probs[0];
+    int val = data[startChunk];
     for (int i = startChunk; i < startChunk + chunkSize; i++) {
-      const int val = data[i];
-      int ctx = 1;
+      const int nxt = (i + 1 < startChunk + chunkSize) ? (int)data[i + 1] : 0;      // (the next byte's load overlaps this byte's bits)
+      // the byte's path through the binary context tree is known up front: all eight probabilities are loaded before the arithmetic
+      // (no two nodes of one path coincide; the previous byte's updates precede these loads in program order)
+      int pr[8];
+      #pragma unroll
+      for (int k = 0; k < 8; k++) pr[k] = p[(val | 0x100) >> (8 - k)];
       #pragma unroll
       for (int k = 7; k >= 0; k--) {
         const int bit = (val >> k) & 1;
+        const int pv = pr[7 - k];
         // encodeBit (:182-199)
-        const u64 split = (((high - low) >> 8) * (u64)p[ctx]) >> 8;
-        if (bit == 0) { low += split + 1; p[ctx] -= (p[ctx] >> 6); }
-        else { high = low + split; p[ctx] -= ((p[ctx] - FQ_PSCALE + 64) >> 6); }
+        const u64 split = (((high - low) >> 8) * (u64)pv) >> 8;
+        if (bit == 0) { low += split + 1; p[(val | 0x100) >> (k + 1)] = pv - (pv >> 6); }
+        else { high = low + split; p[(val | 0x100) >> (k + 1)] = pv - ((pv - FQ_PSCALE + 64) >> 6); }
         while (((low ^ high) & FQ_MASK_24_56) == 0) {       // flush (:208-213)
           if (idx + 4 > sbaCap) { overflow = true; idx = 0; }
           const u32 w = (u32)(high >> 24);
-          sba[idx] = (u8)(w >> 24); sba[idx + 1] = (u8)(w >> 16); sba[idx + 2] = (u8)(w >> 8); sba[idx + 3] = (u8)w;
+          *reinterpret_cast<u32*>(sba + idx) = __byte_perm(w, 0, 0x0123);      // big-endian, idx stays a multiple of 4
           idx += 4;
           low <<= 32;
           high = (high << 32) | FQ_MASK_0_32;
         }
-        ctx = (ctx << 1) | bit;
       }
       p = probs[val >> 6];
+      val = nxt;
     }
     if (overflow) { atomicExch((int*)&blocks[b].status, -KZG_ERR_PROCESS_BLOCK); }
     BitWriterD bw(hdr);
@@ -98,24 +104,35 @@ __global__ void __launch_bounds__(32) fpaq_decode_kernel(KzgBlock* __restrict__ 
     int idx = 0;
     const int chunkSize = min(FQ_CHUNK, count - startChunk);
     int* p = probs[0];
+    // the next 32 coded bits are fetched one refill ahead (a refill never waits for global memory)
+    u32 ahead = (szBytes >= 4) ? get_bits(stream, payBit, 32) : 0u;
+    int pv = p[1];                       // probability of the node about to be decoded
     for (int i = startChunk; i < startChunk + chunkSize; i++) {
       int ctx = 1;
       #pragma unroll
       for (int k = 0; k < 8; k++) {
+        // both children's probabilities are requested before the bit is known: the shared-memory latency overlaps the arithmetic
+        // (at the last level the only successor is the root of the next byte's table, fetched after this byte's updates below)
+        int c0 = 0, c1 = 0;
+        if (k < 7) { c0 = p[2 * ctx]; c1 = p[2 * ctx + 1]; }
         // decodeBitV2 (:290-314)
-        const u64 split = ((((high - low) >> 8) * (u64)p[ctx]) >> 8) + low;
-        if (split >= current) { high = split; p[ctx] -= ((p[ctx] - FQ_PSCALE + 64) >> 6); ctx = (ctx << 1) + 1; }
-        else { low = split + 1; p[ctx] -= (p[ctx] >> 6); ctx = ctx << 1; }
+        const u64 split = ((((high - low) >> 8) * (u64)pv) >> 8) + low;
+        if (split >= current) { high = split; p[ctx] = pv - ((pv - FQ_PSCALE + 64) >> 6); ctx = (ctx << 1) + 1; pv = c1; }
+        else { low = split + 1; p[ctx] = pv - (pv >> 6); ctx = ctx << 1; pv = c0; }
         while (((low ^ high) & FQ_MASK_24_56) == 0) {       // read (:322-335)
           low = (low << 32) & FQ_MASK_0_56;
           high = ((high << 32) | FQ_MASK_0_32) & FQ_MASK_0_56;
           if (idx + 4 > szBytes) { current = (current << 32) & FQ_MASK_0_56; idx = szBytes + 1; }
-          else { current = ((current << 32) | (u64)get_bits(stream, payBit + 8ull * idx, 32)) & FQ_MASK_0_56; idx += 4; }
+          else {
+            current = ((current << 32) | (u64)ahead) & FQ_MASK_0_56; idx += 4;
+            if (idx + 4 <= szBytes) ahead = get_bits(stream, payBit + 8ull * idx, 32);
+          }
         }
       }
       out[i] = (u8)ctx;
       if (idx > szBytes) { B.status = -KZG_ERR_PROCESS_BLOCK; return; }
       p = probs[(ctx & 0xFF) >> 6];
+      pv = p[1];
     }
   }
   B.entBits = (i64)br.pos - B.srcBit;

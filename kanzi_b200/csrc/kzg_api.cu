@@ -1087,7 +1087,7 @@ static int64_t decompress_impl(const uint8_t* d_in, int64_t nBytes, const uint8_
     // Blocks are independent: contiguous groups of them run the whole decode on streams of their own (most urgent first), so
     // that the latency-bound kernels of one group (chunk scan, the literal-record chain) overlap the streaming kernels of the
     // others and, for host buffers, a group's upload / download overlaps the other groups' kernels.
-    const int G = (sN >= 8) ? std::min(gDec, sN / 2) : 1;
+    const int G = (sN >= 8 && (i64)sN * blockSize >= (16 << 20)) ? std::min(gDec, sN / 2) : 1;      // (small batches: one launch chain, the groups would only add launches)
     if (G > 1) { r = ws_side_init(); if (r < 0) return r; }
     if (timing3) CUDA_TRY(cudaEventRecord(ev[0], W.stream));
     if (G > 1) CUDA_TRY(cudaEventRecord(W.sideEv[KZG_DEC_MAXG], W.stream));

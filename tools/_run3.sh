@@ -1,0 +1,4 @@
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_fuzz.py -x -q -m gpu 2>&1 | tail -15
+python tools/gpu_cfg_pass.py cfg3 16777216 2
+python tools/gpu_cfg_pass.py cfg4 4194304 2
+python tools/gpu_cfg_pass.py cfg1 1048576 3
