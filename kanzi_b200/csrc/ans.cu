@@ -765,18 +765,28 @@ __global__ void __launch_bounds__(32) ans0_decode_kernel(KzgBlock* __restrict__ 
 // ================================================================================================================
 // order 1: one CTA per chunk (4 MiB); the 256-context tables live in global memory (L2-resident)
 // ================================================================================================================
-// encode, per-chunk global scratch (u32 units): sym[256][256] (uint2 {invFreq, packed}), freq[256][257], pad, hdrPriv[256][120],
-// alpha[256][256 bytes].  256 threads: histogram (one red.global per byte), one context per thread (normalizeFrequencies, Symbol
+// encode, per-chunk global scratch (u32 units): sym[256][256] (uint4 {xMax, invFreq, bias | cmplFreq << 16, invShift - 32}), freq[256][257],
+// pad, hdrPriv[256][120], alpha[256][256 bytes].  256 threads: histogram (one red.global per byte), one context per thread (normalizeFrequencies, Symbol
 // tables, its header bits into a private buffer), the headers merged bit-granularly into the chunk header; then warp 0 codes:
-// lanes 0-3 run the four states in lock step while all 32 lanes fetch the Symbol entries two batches of 32 steps ahead
-// (data byte -> table entry are dependent global loads; the rANS recurrence itself never waits for memory).
+// ONE lane runs the four states as four interleaved dependency chains (a lone warp issues a dependent instruction only every 5-7
+// cycles: instruction-level parallelism inside one thread is worth more than four lanes in lock step) while all 32 lanes fetch the
+// Symbol entries two batches of 32 steps ahead (data byte -> table entry are dependent global loads; the rANS recurrence itself
+// never waits for memory).
 // decode, per-chunk global scratch: f2s[256][2048] (u8), sym[256][256] (u32), freq[256] (u16), alpha[256]
 #define A1_THREADS 256
+#ifdef KZG_A1_TIMING
+#define A1_CLK(i) clk[i] = clock64();
+#else
+#define A1_CLK(i)
+#endif
 #define A1_HDR_WORDS 120          // private header buffer per context: 2 + 5 + 256 alphabet bits, 43 groups x 4 + 255 x 11 frequency bits < 480 bytes
 #define A1_BATCH 32
 
 __global__ void __launch_bounds__(A1_THREADS) ans1_encode_kernel(const KzgBlock* __restrict__ blocks, KzgEntParams P) {
-  __shared__ uint2 ring[2][4][A1_BATCH];
+  __shared__ uint4 ring[2][4][A1_BATCH];
+#ifdef KZG_A1_TIMING
+  long long clk[5];
+#endif
   __shared__ u32 scanBuf[A1_THREADS / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.y;
@@ -806,14 +816,16 @@ __global__ void __launch_bounds__(A1_THREADS) ans1_encode_kernel(const KzgBlock*
   u8* pay = P.payBuf + gidx * (i64)P.payStride;
   const int bufLen = P.payStride - 16;
   u32* tab = P.tabBuf + gidx * (i64)P.tabStride;       // u32 units
-  uint2* sym = reinterpret_cast<uint2*>(tab);          // [256 contexts][256 symbols]
-  u32* freq = tab + 2 * 65536;                         // [256][257]
-  u32* hdrPriv = tab + 2 * 65536 + 256 * 257 + 64;     // [256][A1_HDR_WORDS]
+  uint4* sym = reinterpret_cast<uint4*>(tab);          // [256 contexts][256 symbols]
+  u32* freq = tab + 4 * 65536;                         // [256][257]
+  u32* hdrPriv = tab + 4 * 65536 + 256 * 257 + 64;     // [256][A1_HDR_WORDS]
   u8* alphaAll = (u8*)(hdrPriv + 256 * A1_HDR_WORDS);  // [256][256]
 
+  A1_CLK(0)
   // Symbol objects are re-created per encode() call (:277-282): zero = "new Symbol()"
-  for (int k = tid; k < 2 * 65536 + 256 * 257; k += A1_THREADS) tab[k] = 0;
+  for (int k = tid; k < (4 * 65536 + 256 * 257) / 4; k += A1_THREADS) reinterpret_cast<uint4*>(tab)[k] = make_uint4(0, 0, 0, 0);
   __syncthreads();
+  A1_CLK(1)
   // ---- order-1 histogram: first byte of each quarter in context 0 (rebuildStatistics :430-446) ----
   {
     const int quarter = (end - start) >> 2;
@@ -839,6 +851,7 @@ __global__ void __launch_bounds__(A1_THREADS) ans1_encode_kernel(const KzgBlock*
     }
   }
   __syncthreads();
+  A1_CLK(2)
 
   // ---- one context per thread: statistics, Symbol table, header bits ----
   u32 myBits;
@@ -855,7 +868,8 @@ __global__ void __launch_bounds__(A1_THREADS) ans1_encode_kernel(const KzgBlock*
         const int sy = alpha[i];
         u32 sa, sb;
         ans_symbol_reset(sa, sb, sum, (int)f[sy], lr);
-        sym[k * 256 + sy] = make_uint2(sa, sb);
+        // unpacked for the coding loop: xMax = freq << (31 - lr) (:479), invFreq, bias | cmplFreq << 16, invShift - 32
+        sym[k * 256 + sy] = make_uint4(((u32)(1 << lr) - ((sb >> 14) & 0x3FFF)) << (31 - lr), sa, (sb & 0x3FFF) | (((sb >> 14) & 0x3FFF) << 16), sb >> 28);
         sum += (int)f[sy];
       }
     }
@@ -889,6 +903,7 @@ __global__ void __launch_bounds__(A1_THREADS) ans1_encode_kernel(const KzgBlock*
   }
   __threadfence_block();
   __syncthreads();
+  A1_CLK(3)
   if (warp != 0) return;
   const i64 hdrBits = (i64)hdrBits32;
 
@@ -899,10 +914,8 @@ __global__ void __launch_bounds__(A1_THREADS) ans1_encode_kernel(const KzgBlock*
   if (lane == 0) for (int i = end - 1; i >= end4; i--) pay[n - (end - 1 - i)] = data[i];
   n -= tail;
   const int quarter = (end4 - start) >> 2;
-  const int j = lane;          // lanes >= 4 idle in the coding loop
-  u32 st = ANS_TOP;
+  u32 st0 = ANS_TOP, st1 = ANS_TOP, st2 = ANS_TOP, st3 = ANS_TOP;      // lane 0 runs all four states
   int idx = n;
-  const u32 lowerMask = (1u << (j & 3)) - 1;
   // Java: i_q = start + (q+1)*quarter - 2, prv_q = block[i_q + 1]; loop while i0 >= start (quarter-1 steps), then "last symbols" in ctx 0.
   // Step s of quarter q codes symbol block[i_q + 1 - s] in context block[i_q - s] (context 0 at the last step, s == steps).
   const int steps = (quarter > 0) ? quarter - 1 : 0;
@@ -910,7 +923,7 @@ __global__ void __launch_bounds__(A1_THREADS) ans1_encode_kernel(const KzgBlock*
   const i64 fiq = (i64)start + (i64)(fq + 1) * quarter - 2;
   const int nBatches = steps / A1_BATCH + 1;
   u32 dat[2] = {0, 0};       // the five bytes of a batch (four symbols + contexts): dat[0] = bytes p-3..p, dat[1] = byte p+1, p = i_q - S - 4 fsub
-  uint2 tv[4];
+  uint4 tv[4];
   auto loadData = [&](int bt, u32* d) {
     d[0] = 0; d[1] = 0;
     const i64 s0 = (i64)bt * A1_BATCH + 4 * fsub;
@@ -920,11 +933,11 @@ __global__ void __launch_bounds__(A1_THREADS) ans1_encode_kernel(const KzgBlock*
     for (int r = 0; r < 4; r++) { const i64 q = p - 3 + r; if (q >= 0 && q >= (i64)start - 1) d[0] |= (u32)data[q] << (8 * r); }
     if (p + 1 >= 0) d[1] = data[p + 1];
   };
-  auto loadTab = [&](int bt, const u32* d, uint2* t) {
+  auto loadTab = [&](int bt, const u32* d, uint4* t) {
     const i64 s0 = (i64)bt * A1_BATCH + 4 * fsub;
     #pragma unroll
     for (int r = 0; r < 4; r++) {
-      t[r] = make_uint2(0, 0);
+      t[r] = make_uint4(0, 0, 0, 0);
       const i64 s = s0 + r;
       if (bt >= nBatches || s > steps) continue;
       // step s: context byte at p - r (byte 3 - r of d[0]), symbol at p - r + 1
@@ -933,12 +946,12 @@ __global__ void __launch_bounds__(A1_THREADS) ans1_encode_kernel(const KzgBlock*
       t[r] = sym[cx * 256 + sy];
     }
   };
-  auto storeTab = [&](int bt, const uint2* t) {
+  auto storeTab = [&](int bt, const uint4* t) {
     #pragma unroll
     for (int r = 0; r < 4; r++) ring[bt & 1][fq][4 * fsub + r] = t[r];
   };
   u32 dnext[2];
-  uint2 tnext[4];
+  uint4 tnext[4];
   loadData(0, dat); loadTab(0, dat, tv); storeTab(0, tv);
   loadData(1, dat); loadTab(1, dat, tv);
   loadData(2, dat);
@@ -947,26 +960,26 @@ __global__ void __launch_bounds__(A1_THREADS) ans1_encode_kernel(const KzgBlock*
     loadTab(bt + 2, dat, tnext);           // in flight while this batch is coded
     loadData(bt + 3, dnext);
     const int cnt = min(A1_BATCH, steps + 1 - bt * A1_BATCH);
-    const bool on = j < 4;
-    #pragma unroll 4
-    for (int s = 0; s < cnt; s++) {
-      const uint2 e = ring[bt & 1][j & 3][s];
-      const u32 a = e.x, bb = e.y;
-      // uninitialised Symbol (all zero) reproduces Java's default object: xMax 0, bias 0, cmplFreq 0, invFreq 0, invShift 0
-      const bool zeroSym = (a == 0 && bb == 0);
-      const u32 xMax = zeroSym ? 0u : (((u32)(1 << lr) - ((bb >> 14) & 0x3FFF)) << (31 - lr));
-      const bool x = on && ((i32)st >= (i32)xMax);
-      const u32 m = __ballot_sync(0xFFFFFFFFu, x) & 0xFu;
-      if (on) {
-        if (x) {
-          const int pos = idx - 2 * __popc(m & lowerMask);
-          pay[pos] = (u8)st;
-          pay[pos - 1] = (u8)(st >> 8);
-          st = (u32)((i32)st >> 16);
-        }
-        idx -= 2 * __popc(m);
-        if (!zeroSym) st = ans_enc_step(st, a, bb);
+    if (__shfl_sync(0xFFFFFFFFu, idx, 0) < 8 * A1_BATCH + 8) {      // the coded bytes would run off the front of the chunk's buffer (cannot happen for statistics taken from the data itself)
+      if (lane == 0) atomicExch((int*)&blocks[b].status, -KZG_ERR_PROCESS_BLOCK);
+      break;
+    }
+    if (lane == 0) {
+      // encodeSymbol (:315-328) for st0..st3 in this order (the bytes of st0 land at the higher address); an uninitialised Symbol
+      // (all zero: Java's default object) has xMax 0 -> always emits, and leaves the state alone
+      // (branch-free: the two bytes are stored whether or not the state renormalises; when it does not, idx stays and the next
+      //  emission overwrites them; a lone warp pays ~20 cycles for every taken branch)
+      #define A1_ENC(ST, E) { \
+        const bool x = ((i32)ST >= (i32)E.x); \
+        pay[idx] = (u8)ST; pay[idx - 1] = (u8)(ST >> 8); \
+        idx -= x ? 2 : 0; ST = x ? (u32)((i32)ST >> 16) : ST; \
+        ST += (E.z & 0xFFFFu) + (__umulhi(ST, E.y) >> E.w) * (E.z >> 16); }
+      #pragma unroll 2
+      for (int s = 0; s < cnt; s++) {
+        const uint4 e0 = ring[bt & 1][0][s], e1 = ring[bt & 1][1][s], e2 = ring[bt & 1][2][s], e3 = ring[bt & 1][3][s];
+        A1_ENC(st0, e0) A1_ENC(st1, e1) A1_ENC(st2, e2) A1_ENC(st3, e3)
       }
+      #undef A1_ENC
     }
     __syncwarp();
     storeTab(bt + 1, tv);
@@ -975,16 +988,17 @@ __global__ void __launch_bounds__(A1_THREADS) ans1_encode_kernel(const KzgBlock*
     for (int r = 0; r < 4; r++) tv[r] = tnext[r];
     dat[0] = dnext[0]; dat[1] = dnext[1];
   }
-  const u32 s1 = __shfl_sync(0xFFFFFFFFu, st, 1);
-  const u32 s2 = __shfl_sync(0xFFFFFFFFu, st, 2);
-  const u32 s3 = __shfl_sync(0xFFFFFFFFu, st, 3);
+  A1_CLK(4)
   if (lane == 0) {
+#ifdef KZG_A1_TIMING
+    printf("ans1 enc chunk %d/%d (%d bytes): zero %lld hist %lld ctx %lld code %lld cycles\n", b, c, end - start, clk[1] - clk[0], clk[2] - clk[1], clk[3] - clk[2], clk[4] - clk[3]);
+#endif
     n = idx + 1;
     BitWriterD bw(hdr);
     bw.nbytes = hdrBits >> 3; bw.nacc = (int)(hdrBits & 7);
     bw.acc = (bw.nacc > 0) ? ((u64)hdr[bw.nbytes] >> (8 - bw.nacc)) : 0;
     write_varint(bw, bufLen - n);
-    bw.write(st, 32); bw.write(s1, 32); bw.write(s2, 32); bw.write(s3, 32);
+    bw.write(st0, 32); bw.write(st1, 32); bw.write(st2, 32); bw.write(st3, 32);
     bw.flush();
     segs[0] = KzgSeg{hdr, 0, 0, (u64)bw.bits()};
     segs[1] = KzgSeg{pay + n, 0, 0, (u64)(bufLen - n) * 8};
@@ -993,11 +1007,12 @@ __global__ void __launch_bounds__(A1_THREADS) ans1_encode_kernel(const KzgBlock*
 
 // decode, per-chunk global scratch (u32 units): sym[256][256] (freq | cum << 16), f2s[256][2048] (u8), freqAll[256][256] (u16).
 // 256 threads: thread 0 walks the 256 context headers (a serial bit stream), every thread then builds one context's cumulative
-// frequencies and slot -> symbol table; warp 0 decodes: lanes 0-3 run the four states, the coded bytes stream through a
-// shared-memory ring that all 32 lanes refill a batch of 32 steps ahead (no lane waits for a global payload load).
+// frequencies and slot -> symbol table; warp 0 decodes: ONE lane runs the four states as four interleaved dependency chains (see
+// the encoder), the coded bytes stream through a shared-memory ring (big-endian words) that all 32 lanes refill a batch of 32
+// steps ahead; a step's renormalisation reads come out of one 64-bit window of the ring, no read waits for the one before.
 #define A1D_RING 1024
 __global__ void __launch_bounds__(A1_THREADS) ans1_decode_kernel(KzgBlock* __restrict__ blocks, KzgEntParams P) {
-  __shared__ __align__(16) u8 ring[A1D_RING];
+  __shared__ __align__(16) u32 ring[A1D_RING / 4];        // coded bytes as big-endian words
   __shared__ u8 declared[256];
   __shared__ u8 alphaS[256];
   __shared__ int hdrState[2];          // lr, bad
@@ -1024,6 +1039,10 @@ __global__ void __launch_bounds__(A1_THREADS) ans1_decode_kernel(KzgBlock* __res
   u8* f2s = (u8*)(tab + 65536);                 // [256][2048]  (logRange <= 11 for order 1)
   u16* freqAll = (u16*)(f2s + 256 * 2048);      // [256][256]
 
+#ifdef KZG_A1_TIMING
+  long long clk[5];
+#endif
+  A1_CLK(0)
   // frequencies do not persist across contexts here: a context's header either declares a symbol or leaves it absent
   for (int k = tid; k < 256 * 256 / 2; k += A1_THREADS) reinterpret_cast<u32*>(freqAll)[k] = 0;
   declared[tid] = 0;
@@ -1043,9 +1062,13 @@ __global__ void __launch_bounds__(A1_THREADS) ans1_decode_kernel(KzgBlock* __res
     hdrState[0] = lr; hdrState[1] = bad;
   }
   __syncthreads();
+  A1_CLK(1)
   const int lr = hdrState[0];
   if (hdrState[1]) { if (tid == 0) atomicExch(&B.status, -KZG_ERR_PROCESS_BLOCK); return; }
-  if (declared[tid]) {
+  if (!declared[tid]) {       // a context the header does not declare: all-zero tables, frequency 0 tells the decoder it was used
+    for (int i = 0; i < 2048 / 4; i++) reinterpret_cast<u32*>(f2s + tid * 2048)[i] = 0;
+    for (int i = 0; i < 256; i++) sym[tid * 256 + i] = 0;
+  } else {
     const int k = tid;
     const u16* fr = freqAll + k * 256;
     int sum = 0;
@@ -1060,22 +1083,20 @@ __global__ void __launch_bounds__(A1_THREADS) ans1_decode_kernel(KzgBlock* __res
   }
   __threadfence_block();
   __syncthreads();
+  A1_CLK(2)
   if (warp != 0) return;
 
   // ---- decodeChunkV2 order 1 (:406-432): lane j walks quarter j with state st_j; read order st3, st2, st1, st0 ----
   const int end4 = start + ((end - start) & -4);
   const int quarter = (end4 - start) >> 2;
-  const int j = lane;
-  i32 st = (j < 4) ? (i32)info.st[j] : 0;
-  const int mask = (1 << lr) - 1;
+  u32 st0 = info.st[0], st1 = info.st[1], st2 = info.st[2], st3 = info.st[3];      // lane 0 runs all four states
+  const u32 mask = (1u << lr) - 1;
   int cursor = 0;
-  int prv = 0;
-  int pos = start + j * quarter;
-  // lanes with a higher state index read first: "before" = flags of lanes above me within 0..3
-  const u32 upperMask = (j < 4) ? (0xFu & ~((2u << j) - 1)) : 0u;
+  u32 prv0 = 0, prv1 = 0, prv2 = 0, prv3 = 0;
+  u8* o0 = out + start; u8* o1 = o0 + quarter; u8* o2 = o1 + quarter; u8* o3 = o2 + quarter;
   const i64 payBit = info.payBit;
   const int sz = info.sz;
-  int undeclared = 0;
+  u32 minFreq = 1;                        // becomes 0 when a symbol is decoded in a context without a table
   // coded bytes [fill, fill + 256): lane l fetches bytes fill + 8 l .. + 7 (zero beyond sz, as ans_pay16 reads them)
   auto fetch8 = [&](int fill, u32* w) {
     w[0] = 0; w[1] = 0;
@@ -1094,7 +1115,7 @@ __global__ void __launch_bounds__(A1_THREADS) ans1_decode_kernel(KzgBlock* __res
     }
   };
   auto put8 = [&](int fill, const u32* w) {
-    *reinterpret_cast<uint2*>(ring + ((fill + 8 * lane) & (A1D_RING - 1))) = make_uint2(w[0], w[1]);
+    *reinterpret_cast<uint2*>(ring + (((fill + 8 * lane) & (A1D_RING - 1)) >> 2)) = make_uint2(__byte_perm(w[0], 0, 0x0123), __byte_perm(w[1], 0, 0x0123));
   };
   u32 w8[2];
   int fill = 0;
@@ -1105,37 +1126,51 @@ __global__ void __launch_bounds__(A1_THREADS) ans1_decode_kernel(KzgBlock* __res
     const bool doFill = (fill - cursor) <= A1D_RING - 256;     // uniform: cursor is the same in every coding lane... (lanes >= 4 keep it too)
     if (doFill) fetch8(fill, w8);
     const int cnt = min(32, quarter - s0);
-    #pragma unroll 4
-    for (int s = 0; s < cnt; s++) {
-      bool need = false;
-      if (j < 4) {
-        const int slot = st & mask;
-        if (!declared[prv]) undeclared = 1;
-        const int cur = f2s[prv * 2048 + slot];
-        const u32 fc = sym[prv * 256 + cur];
-        out[pos] = (u8)cur;
-        st = (i32)((fc & 0xFFFFu) * ((u32)st >> lr) + (u32)slot - (fc >> 16));
-        need = st < ANS_TOP;
-        prv = cur;
-        pos++;
+    if (lane == 0) {
+      // decodeSymbol (:333-347) for the four states, then the reads in the order st3, st2, st1, st0 (:419-430)
+      // (all table loads of a step are issued before its output stores: the compiler may not move a load across a store that
+      //  could alias it, and a lone warp has nothing else to hide a load behind)
+      const u8* __restrict__ f2sR = f2s;
+      const u32* __restrict__ symR = sym;
+      #pragma unroll 2
+      for (int s = 0; s < cnt; s++) {
+        // the next eight coded bytes (a step reads at most four 16-bit words)
+        const u32 wi = ((u32)cursor & (A1D_RING - 1)) >> 2;
+        const u32 w0 = ring[wi], w1 = ring[(wi + 1) & (A1D_RING / 4 - 1)], w2 = ring[(wi + 2) & (A1D_RING / 4 - 1)];
+        const u32 sh = ((u32)cursor & 2u) * 8u;
+        const u64 win = ((u64)__funnelshift_l(w1, w0, sh) << 32) | (u64)__funnelshift_l(w2, w1, sh);
+        const u32 sl0 = st0 & mask, sl1 = st1 & mask, sl2 = st2 & mask, sl3 = st3 & mask;
+        const u32 c0 = f2sR[prv0 * 2048 + sl0], c1 = f2sR[prv1 * 2048 + sl1], c2 = f2sR[prv2 * 2048 + sl2], c3 = f2sR[prv3 * 2048 + sl3];
+        const u32 f0 = symR[prv0 * 256 + c0], f1 = symR[prv1 * 256 + c1], f2 = symR[prv2 * 256 + c2], f3 = symR[prv3 * 256 + c3];
+        o0[s0 + s] = (u8)c0; o1[s0 + s] = (u8)c1; o2[s0 + s] = (u8)c2; o3[s0 + s] = (u8)c3;
+        minFreq = min(min(minFreq, f0 & 0xFFFFu), min(f1 & 0xFFFFu, min(f2 & 0xFFFFu, f3 & 0xFFFFu)));
+        st0 = (f0 & 0xFFFFu) * (st0 >> lr) + sl0 - (f0 >> 16); st1 = (f1 & 0xFFFFu) * (st1 >> lr) + sl1 - (f1 >> 16);
+        st2 = (f2 & 0xFFFFu) * (st2 >> lr) + sl2 - (f2 >> 16); st3 = (f3 & 0xFFFFu) * (st3 >> lr) + sl3 - (f3 >> 16);
+        prv0 = c0; prv1 = c1; prv2 = c2; prv3 = c3;
+        const u32 n3 = ((i32)st3 < ANS_TOP) ? 16u : 0u, n2 = ((i32)st2 < ANS_TOP) ? 16u : 0u;
+        const u32 n1 = ((i32)st1 < ANS_TOP) ? 16u : 0u, n0 = ((i32)st0 < ANS_TOP) ? 16u : 0u;
+        const u32 b2 = n3, b1 = n3 + n2, b0 = b1 + n1;            // bits of the window consumed before each state's read
+        if (n3) st3 = (st3 << 16) | (u32)(win >> 48);
+        if (n2) st2 = (st2 << 16) | ((u32)(win >> (48 - b2)) & 0xFFFFu);
+        if (n1) st1 = (st1 << 16) | ((u32)(win >> (48 - b1)) & 0xFFFFu);
+        if (n0) st0 = (st0 << 16) | ((u32)(win >> (48 - b0)) & 0xFFFFu);
+        cursor += (int)((b0 + n0) >> 3);
       }
-      const u32 m = __ballot_sync(0xFFFFFFFFu, need) & 0xFu;
-      if (need) {
-        const int off = cursor + 2 * __popc(m & upperMask);
-        const u32 h = *reinterpret_cast<const u16*>(ring + (off & (A1D_RING - 1)));      // two coded bytes, big-endian in the stream
-        st = (i32)(((u32)st << 16) | __byte_perm(h, 0, 0x4401));
-      }
-      cursor += 2 * __popc(m);
+      #undef A1_DEC
     }
+    cursor = __shfl_sync(0xFFFFFFFFu, cursor, 0);
     __syncwarp();
     if (doFill) { put8(fill, w8); fill += 256; }
     __syncwarp();
   }
-  undeclared = __any_sync(0xFFFFFFFFu, undeclared);
+  A1_CLK(3)
   if (lane == 0) {
+#ifdef KZG_A1_TIMING
+    printf("ans1 dec chunk %d/%d (%d bytes): headers %lld tables %lld decode %lld cycles\n", b, c, end - start, clk[1] - clk[0], clk[2] - clk[1], clk[3] - clk[2]);
+#endif
     const int tail = end - end4;
     for (int i = 0; i < tail; i++) out[end4 + i] = (cursor + i < sz) ? (u8)ans_pay8(stream, payBit, cursor + i) : 0;
-    if (cursor + tail != sz || undeclared) atomicExch(&B.status, -KZG_ERR_PROCESS_BLOCK);
+    if (cursor + tail != sz || minFreq == 0) atomicExch(&B.status, -KZG_ERR_PROCESS_BLOCK);
   }
 }
 
@@ -1175,5 +1210,5 @@ int kzg_ans_decode_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, const
   return 0;
 }
 
-size_t kzg_ans1_enc_tab_u32() { return 2 * 65536 + 256 * 257 + 64 + 256 * A1_HDR_WORDS + 256 * 256 / 4 + 16; }
+size_t kzg_ans1_enc_tab_u32() { return 4 * 65536 + 256 * 257 + 64 + 256 * A1_HDR_WORDS + 256 * 256 / 4 + 16; }
 size_t kzg_ans1_dec_tab_u32() { return 65536 + (256 * 2048) / 4 + (256 * 256) / 2 + 64 + 16; }
