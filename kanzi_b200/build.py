@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libkanzi_b200.so")
-NVCC_FLAGS = (["-DKZG_A1_TIMING"] if os.environ.get("KZG_A1_TIMING") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math",
+NVCC_FLAGS = (["-DKZG_A1_TIMING", "-DKZG_RZ_TIMING"] if os.environ.get("KZG_A1_TIMING") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-Xcudafe", "--diag_suppress=177", "-cudart", "shared"]
 
 

@@ -420,7 +420,13 @@ __global__ void __launch_bounds__(32) rolz_replay_kernel(KzgBlock* __restrict__ 
     dstIdx = n; litIdx = n;
     __syncwarp();
     bool fail = false;
+#ifdef KZG_RZ_TIMING
+    long long tLit = 0, tMatch = 0, nLitTok = 0, nLit = 0, c0, c1;
+#endif
     while (dstIdx < endChunk) {
+#ifdef KZG_RZ_TIMING
+      c0 = clock64();
+#endif
       if (tkIdx >= I.tkLen) { fail = true; break; }
       const int token = tkBuf[tkIdx++];
       int matchLen = token & 0x07;
@@ -432,23 +438,32 @@ __global__ void __launch_bounds__(32) rolz_replay_kernel(KzgBlock* __restrict__ 
         if (litIdx + litLen > I.litLen || dstIdx + litLen > dstEnd + 4) { fail = true; break; }
         for (int i = lane; i < litLen; i += 32) dst[dstIdx + i] = litBuf[litIdx + i];
         __syncwarp();
-        // register the literal positions with the encoder's skip pattern (:889-900); sequential by construction
-        if (lane == 0) {
-          int srcInc = 0;
-          for (int j = 0; j < litLen; j++) {
-            const int key = (mm == 3) ? rz_key1(dst, dstIdx + j - dt) : rz_key2(dst, dstIdx + j - dt);
-            const int c = (counters[key] + 1) & 15;
-            counters[key] = c;
-            matches[(key << RZ_LOGPOS) + c] = dstIdx + j;
-            j += (srcInc >> 6);
-            srcInc++;
+        // register the literal positions with the encoder's skip pattern (:889-900): the t-th registered literal is
+        // j_t = t + sum_{u<t} (u >> 6).  Positions with different keys touch different ring rows, so 32 of them go at once:
+        // lanes with the same key (match_any) take consecutive ring slots in lane order, the last 16 of a group survive.
+        for (int t0 = 0; ; t0 += 32) {
+          const int t = t0 + lane, k6 = t >> 6;
+          const int j = t + 32 * k6 * (k6 - 1) + k6 * (t & 63);
+          const bool on = j < litLen;
+          if (!__any_sync(0xFFFFFFFFu, on)) break;
+          const int key = on ? ((mm == 3) ? rz_key1(dst, dstIdx + j - dt) : rz_key2(dst, dstIdx + j - dt)) : (0x10000 + lane);
+          const u32 peers = __match_any_sync(0xFFFFFFFFu, key);
+          if (on) {
+            const int rank = __popc(peers & ((1u << lane) - 1)), size = __popc(peers);
+            const int c0 = counters[key];
+            if (rank >= size - 16) matches[(key << RZ_LOGPOS) + ((c0 + rank + 1) & 15)] = dstIdx + j;
+            if (rank == size - 1) counters[key] = (c0 + size) & 15;
           }
+          __syncwarp();
         }
         __syncwarp();
         litIdx += litLen;
         dstIdx += litLen;
         if (dstIdx >= endChunk) { if (dstIdx == endChunk) break; fail = true; break; }
       }
+#ifdef KZG_RZ_TIMING
+      c1 = clock64(); tLit += c1 - c0; if (litLen > 0) { nLitTok++; nLit += litLen; }
+#endif
       if (dstIdx + matchLen + mm > dstEnd) { fail = true; break; }
       const int key = (mm == 3) ? rz_key1(dst, dstIdx - dt) : rz_key2(dst, dstIdx - dt);
       const int base = key << RZ_LOGPOS;
@@ -466,7 +481,13 @@ __global__ void __launch_bounds__(32) rolz_replay_kernel(KzgBlock* __restrict__ 
       if (lane == 0) { const int c = (cnt + 1) & 15; counters[key] = c; matches[base + c] = dstIdx; }
       __syncwarp();
       dstIdx += ml;
+#ifdef KZG_RZ_TIMING
+      tMatch += clock64() - c1;
+#endif
     }
+#ifdef KZG_RZ_TIMING
+    if (lane == 0) printf("rolz replay block %d: %d tokens, %lld with literals (%lld literal bytes), literal part %lld cycles, match part %lld cycles\n", b, tkIdx, nLitTok, nLit, tLit, tMatch);
+#endif
     if (fail) return;
     if ((tkIdx != I.tkLen) || (mIdxIdx != I.mIdxLen) || (litIdx != I.litLen) || (lenIdx != I.mLenLen)) return;
   }

@@ -17,7 +17,13 @@ seed = {"cfg1": 1, "cfg2": 2, "cfg3": 3, "cfg4": 4, "cfg5": 5}[cfg]
 K.set_device(0)
 L = K.lib()
 dev = torch.device("cuda", 0)
-data = gen(n, seed)
+BASE = 256 << 20
+if n > BASE and n % BASE == 0:      # large runs: a 256 MiB base rotated by odd amounts (every block differs, same statistics; the generator is slow)
+    import numpy as np
+    base = gen(BASE, seed)
+    data = np.concatenate([base if i == 0 else np.roll(base, i * 1000003) for i in range(n // BASE)])
+else:
+    data = gen(n, seed)
 d_in = torch.zeros(n + 256, dtype=torch.uint8, device=dev); d_in[:n].copy_(torch.from_numpy(data))
 cap = int(K.compress_bound(n, bs))
 d_knz = torch.zeros(cap + 256, dtype=torch.uint8, device=dev)
