@@ -518,10 +518,14 @@ def main():
     return 0
 
 
-# scaled-down passes of the other BASELINE.json configs (parity-test cases, not the headline): value / e2e / CPU arm on the same sample
-# (cfg4: FPAQ is one dependent chain per block, ~170 cycles per bit on one lane = 25 s per 32 MiB block each way; the default run
-#  codes ONE short block of 4 MiB under -b 32M; a full 32 MiB block is exercised by tests/test_gpu_fullsize.py and `--config cfg4`)
-OTHER = {"cfg1": 1.0, "cfg3": 0.25, "cfg4": 0.0042, "cfg5": 1.0 / 32}
+# passes of the other BASELINE.json configs (parity-test cases, not the headline): value / e2e / CPU arm on a sample of the same data.
+# Their codecs are one dependent chain per block or chunk (inverse RANK / SRT, FPAQ, ROLZ, the four rANS states of a 4 MiB order-1
+# chunk): a lone warp runs such a chain at about four cycles per instruction, so what these lines measure is how many blocks are in
+# flight.  cfg3 runs whole (12 blocks); cfg5 runs 128 of its 512 blocks (2 GiB: a 256 MiB base from the generator, rotated by odd
+# amounts so every block differs; the generator itself costs 7 s per 256 MiB); cfg4 (FPAQ: ~25 s per 32 MiB block each way) codes
+# ONE short block of 4 MiB under -b 32M; full 32 MiB blocks are exercised by tests/test_gpu_fullsize.py and `--config cfg4`.
+OTHER = {"cfg1": 1.0, "cfg3": 1.0, "cfg4": 0.0042, "cfg5": 0.25}
+CFG5_BASE = 256 << 20
 
 
 def other_configs(torch, K, dev, kstream, flags, a):
@@ -530,7 +534,15 @@ def other_configs(torch, K, dev, kstream, flags, a):
     for cfg, sc in OTHER.items():
         gen, full, transforms, entropy, bs = synth.CONFIGS[cfg]
         n = max(bs, int(full * sc) // bs * bs) if cfg != "cfg4" else (4 << 20)
-        data = gen(n, SEEDS[cfg])
+        if cfg == "cfg3":
+            n = int(full * sc)
+        if cfg == "cfg5" and n > CFG5_BASE:
+            n = n // CFG5_BASE * CFG5_BASE
+            base5 = gen(CFG5_BASE, SEEDS[cfg])
+            data = np.concatenate([base5 if i == 0 else np.roll(base5, i * 1000003) for i in range(n // CFG5_BASE)])
+            del base5
+        else:
+            data = gen(n, SEEDS[cfg])
         c = Codec(torch, K, dev, data, transforms, entropy, bs, flags)
         t0 = time.time()
         k = c.gate()
@@ -560,11 +572,13 @@ def other_configs(torch, K, dev, kstream, flags, a):
                  "e2e": round(mb / ((eem + edm) * 1e-3), 2) if e2e else None, "knz_bytes": int(k), "unit": "MB/s",
                  "hbm_frac_stream": round((n + k) / ((em + dm) * 1e-3) / 1e9 / 6549.1, 6)}
         if not a.no_cpu_baseline:
-            r = cpu_arm(data, transforms, entropy, bs, 64.0, flags)
+            # CPU arm: one block per host thread where the config has that many (bounded: about 30 s of CPU work)
+            cores = os.cpu_count() or 1
+            r = cpu_arm(data, transforms, entropy, bs, min(max(64.0, cores * bs / 1e6), 600.0), flags)
             entry["cpu_reference_MBps"] = round(r["value"], 2)
             entry["cpu_sample"] = r["sample"]
         out[cfg] = entry
-        del c
+        del c, data
         torch.cuda.empty_cache()
     return out
 

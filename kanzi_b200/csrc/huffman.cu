@@ -220,40 +220,48 @@ __device__ int hf_canonical_codes(const u8* sizes, u32* codes, const u8* present
 }
 
 // ================================================================================================================
-// encode: grid (ceil(maxChunks/16), nBlocks), 64 threads; 4 lanes (= 4 fragments) per chunk; 6 segments per chunk
+// encode: one CTA of 128 threads per chunk (grid (maxChunks, nBlocks)); 6 segments per chunk.
+//   1. the chunk is staged in shared memory while it is counted (per-warp histograms, merged);
+//   2. thread 0 computes the code lengths and canonical codes (order-sensitive, restated literally) and writes the header;
+//   3. warp j packs fragment j: every lane sums the code lengths of its 1/32 of the fragment, a warp scan gives its first bit,
+//      then it packs its symbols into the fragment's bit string in shared memory (whole 32-bit words with plain stores, the two
+//      boundary words with atomicOr);
+//   4. the four bit strings go out with coalesced word stores.
 // ================================================================================================================
+#define HFE_THREADS 128
 struct HfEncSmem {
-  u32 freq[HF_GROUPS][256];
-  u32 codes[HF_GROUPS][256];      // (len << 24) | code
-  int ranks[HF_GROUPS][256];
-  int work[HF_GROUPS][512];
-  u8 sizes[HF_GROUPS][256];
-  u8 alpha[HF_GROUPS][256];
-  u8 present[HF_GROUPS][256];
-  u8 lists[HF_GROUPS][6 * 256];
+  u32 freq[4][256];               // per-warp histograms; freq[0] = merged
+  u32 codes[256];                 // (len << 24) | code
+  int ranks[256];
+  int work[512];
+  u8 sizes[256];
+  u8 alpha[256];
+  u8 present[256];
+  u8 lists[6 * 256];
+  u8 data[HF_CHUNK];
+  u32 bits[4][HF_FRAG_STRIDE / 4];
+  int nsym, err; i64 hdrBits; u32 fragBits[4];
 };
 
-__global__ void __launch_bounds__(64) huff_encode_kernel(const KzgBlock* __restrict__ blocks, KzgEntParams P) {
+__global__ void __launch_bounds__(HFE_THREADS) huff_encode_kernel(const KzgBlock* __restrict__ blocks, KzgEntParams P) {
   extern __shared__ __align__(16) u8 smem_raw[];
   HfEncSmem& S = *reinterpret_cast<HfEncSmem*>(smem_raw);
-  const int g = threadIdx.x >> 2, j = threadIdx.x & 3;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.y;
-  const int c = blockIdx.x * HF_GROUPS + g;
-  if (c >= P.maxChunks) return;     // whole 4-lane groups leave; no warp-wide collectives below
+  const int c = blockIdx.x;
   const KzgBlock& B = blocks[b];
   const int len = (B.status == 0 && B.entropy == P.entropy) ? B.curLen : 0;
   const u8* __restrict__ data = B.cur;
   const i64 gidx = (i64)b * P.maxChunks + c;
   KzgSeg* segs = P.segs + (i64)b * P.segsPerBlock + 1 + (i64)c * 6;
   const int start = c * HF_CHUNK;
-  const u32 gmask = 0xFu << ((threadIdx.x & 31) & ~3);
   if (start >= len) {
-    if (j == 0) for (int k = 0; k < 6; k++) segs[k] = KzgSeg{nullptr, 0, 0, 0};
+    if (tid < 6) segs[tid] = KzgSeg{nullptr, 0, 0, 0};
     return;
   }
   const int count = min(HF_CHUNK, len - start);
   if (count < 32) {     // small chunk stored raw (:400-402)
-    if (j == 0) {
+    if (tid == 0) {
       segs[0] = KzgSeg{data + start, 0, 0, (u64)count * 8};
       for (int k = 1; k < 6; k++) segs[k] = KzgSeg{nullptr, 0, 0, 0};
     }
@@ -262,19 +270,20 @@ __global__ void __launch_bounds__(64) huff_encode_kernel(const KzgBlock* __restr
   u8* hdr = P.hdrBuf + gidx * (i64)P.hdrStride;
   u8* pay = P.payBuf + gidx * (i64)P.payStride;
 
-  for (int k = j; k < 256; k += 4) S.freq[g][k] = 0;
-  __syncwarp(gmask);
-  for (int i = start + j; i < start + count; i += 4) atomicAdd(&S.freq[g][data[i]], 1u);
-  __syncwarp(gmask);
+  for (int k = tid; k < 4 * 256; k += HFE_THREADS) (&S.freq[0][0])[k] = 0;
+  __syncthreads();
+  for (int i = tid; i < count; i += HFE_THREADS) { const u8 v = data[start + i]; S.data[i] = v; atomicAdd(&S.freq[warp][v], 1u); }
+  __syncthreads();
+  for (int k = tid; k < 256; k += HFE_THREADS) S.freq[0][k] += S.freq[1][k] + S.freq[2][k] + S.freq[3][k];
+  __syncthreads();
 
-  int nsym = 0, err = 0;
-  i64 hdrBits = 0;
-  if (j == 0) {   // updateFrequencies (:103-178)
+  if (tid == 0) {   // updateFrequencies (:103-178)
+    int nsym = 0, err = 0;
     BitWriterD bw(hdr);
-    u8* alphabet = S.alpha[g]; u8* sizes = S.sizes[g]; u32* codes = S.codes[g]; int* ranks = S.ranks[g];
+    u8* alphabet = S.alpha; u8* sizes = S.sizes; u32* codes = S.codes; int* ranks = S.ranks;
     for (int i = 0; i < 256; i++) {
-      codes[i] = 0; sizes[i] = 0; S.present[g][i] = 0;
-      if (S.freq[g][i] > 0) { alphabet[nsym++] = (u8)i; S.present[g][i] = 1; }
+      codes[i] = 0; sizes[i] = 0; S.present[i] = 0;
+      if (S.freq[0][i] > 0) { alphabet[nsym++] = (u8)i; S.present[i] = 1; }
     }
     hf_encode_alphabet(bw, alphabet, nsym);
     if (nsym == 1) {
@@ -282,70 +291,100 @@ __global__ void __launch_bounds__(64) huff_encode_kernel(const KzgBlock* __restr
       sizes[alphabet[0]] = 1;
     } else {
       for (int i = 0; i < 256; i++) ranks[i] = 0;
-      for (int i = 0; i < nsym; i++) ranks[i] = (int)((S.freq[g][alphabet[i]] << 8) | alphabet[i]);
-      int maxCodeLen = hf_code_lengths(sizes, ranks, S.work[g], nsym);
+      for (int i = 0; i < nsym; i++) ranks[i] = (int)((S.freq[0][alphabet[i]] << 8) | alphabet[i]);
+      int maxCodeLen = hf_code_lengths(sizes, ranks, S.work, nsym);
       if (maxCodeLen == 0) err = 1;
       if (!err && maxCodeLen > HF_MAXLEN) {
-        maxCodeLen = hf_limit_lengths(alphabet, S.freq[g], sizes, ranks, S.work[g], S.lists[g], nsym, &err);
+        maxCodeLen = hf_limit_lengths(alphabet, S.freq[0], sizes, ranks, S.work, S.lists, nsym, &err);
         if (maxCodeLen == 0) err = 1;
       }
       if (!err) {
         if (maxCodeLen > HF_MAXLEN) {      // unlikely fallback (:146-155)
           for (int i = 0; i < nsym; i++) { codes[alphabet[i]] = (u32)i; sizes[alphabet[i]] = 8; }
         } else {
-          if (hf_canonical_codes(sizes, codes, S.present[g], nsym, S.lists[g]) < 0) err = 1;
+          if (hf_canonical_codes(sizes, codes, S.present, nsym, S.lists) < 0) err = 1;
         }
       }
     }
     if (!err) {
       int prevSize = 2;
       for (int i = 0; i < nsym; i++) {
-        const int s = alphabet[i];
-        const int currSize = sizes[s];
-        codes[s] |= ((u32)currSize << 24);
+        const int sy = alphabet[i];
+        const int currSize = sizes[sy];
+        codes[sy] |= ((u32)currSize << 24);
         hf_expgolomb(bw, currSize - prevSize);
         prevSize = currSize;
       }
     }
-    hdrBits = bw.bits();
+    S.hdrBits = bw.bits();
     bw.flush();
+    S.nsym = nsym; S.err = err;
   }
-  nsym = __shfl_sync(gmask, nsym, (threadIdx.x & 31) & ~3);
-  err = __shfl_sync(gmask, err, (threadIdx.x & 31) & ~3);
-  __syncwarp(gmask);
-  if (err) {
-    if (j == 0) {
+  __syncthreads();
+  const int nsym = S.nsym;
+  if (S.err) {
+    if (tid == 0) {
       atomicExch((int*)&blocks[b].status, -KZG_ERR_PROCESS_BLOCK);
       for (int k = 0; k < 6; k++) segs[k] = KzgSeg{nullptr, 0, 0, 0};
     }
     return;
   }
   if (nsym <= 1) {      // chunk skipped after its header (:407-409)
-    if (j == 0) {
-      segs[0] = KzgSeg{hdr, 0, 0, (u64)hdrBits};
+    if (tid == 0) {
+      segs[0] = KzgSeg{hdr, 0, 0, (u64)S.hdrBits};
       for (int k = 1; k < 6; k++) segs[k] = KzgSeg{nullptr, 0, 0, 0};
     }
     return;
   }
 
-  // ---- encodeChunk (:419-493): lane j packs fragment j ----
+  // ---- encodeChunk (:419-493): warp j packs fragment j ----
   const int szFrag = count / 4;
-  u8* fb = pay + j * HF_FRAG_STRIDE;
-  u64 acc = 0; int nacc = 0; int nb = 0;
-  const u8* __restrict__ p = data + start + j * szFrag;
-  for (int i = 0; i < szFrag; i++) {
-    const u32 code = S.codes[g][p[i]];
-    const int cl = (int)(code >> 24);
-    acc = (acc << cl) | (u64)(code & 0xFFFFFF);
-    nacc += cl;
-    while (nacc >= 8) { nacc -= 8; fb[nb++] = (u8)(acc >> nacc); }
+  {
+    const int j = warp;
+    u32* fb = S.bits[j];
+    for (int k = lane; k < HF_FRAG_STRIDE / 4; k += 32) fb[k] = 0;
+    __syncwarp();
+    const u8* p = S.data + j * szFrag;
+    const int per = (szFrag + 31) >> 5;
+    const int i0 = min(lane * per, szFrag), i1 = min(i0 + per, szFrag);
+    u32 myBits = 0;
+    for (int i = i0; i < i1; i++) myBits += S.codes[p[i]] >> 24;
+    u32 incl = myBits;
+    for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+    const u32 total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    u32 pos = incl - myBits;                       // first bit of this lane's symbols (bit 0 = MSB of byte 0)
+    // pack: `acc` holds `nacc` pending bits that belong at bit `pos - nacc`
+    u64 acc = 0; int nacc = 0;
+    u32 wpos = pos;                                // bit position of the first pending bit
+    for (int i = i0; i < i1; i++) {
+      const u32 code = S.codes[p[i]];
+      const int cl = (int)(code >> 24);
+      acc = (acc << cl) | (u64)(code & 0xFFFFFF);
+      nacc += cl;
+      if (nacc >= 32) {
+        // emit the 32 oldest pending bits at bit wpos: two words when wpos is not word aligned
+        const u32 v = (u32)(acc >> (nacc - 32));
+        const u32 wi = wpos >> 5, sh = wpos & 31;
+        if (sh == 0) fb[wi] = __byte_perm(v, 0, 0x0123);       // a lane's interior words are its own
+        else { atomicOr(&fb[wi], __byte_perm(v >> sh, 0, 0x0123)); atomicOr(&fb[wi + 1], __byte_perm(v << (32 - sh), 0, 0x0123)); }
+        nacc -= 32; wpos += 32;
+      }
+    }
+    if (nacc > 0) {
+      const u32 v = (u32)(acc << (32 - nacc));     // left-aligned remainder
+      const u32 wi = wpos >> 5, sh = wpos & 31;
+      atomicOr(&fb[wi], __byte_perm(v >> sh, 0, 0x0123));
+      if (sh && sh + nacc > 32) atomicOr(&fb[wi + 1], __byte_perm(v << (32 - sh), 0, 0x0123));
+    }
+    __syncwarp();
+    if (lane == 0) S.fragBits[j] = total;
+    u32* out = reinterpret_cast<u32*>(pay + j * HF_FRAG_STRIDE);
+    for (u32 k = lane; k < (total + 31) / 32; k += 32) out[k] = fb[k];
   }
-  const u32 myBits = (u32)(nb * 8 + nacc);
-  if (nacc > 0) fb[nb] = (u8)(acc << (8 - nacc));
-  const int gl = (threadIdx.x & 31) & ~3;
-  const u32 b0 = __shfl_sync(gmask, myBits, gl + 0), b1 = __shfl_sync(gmask, myBits, gl + 1);
-  const u32 b2 = __shfl_sync(gmask, myBits, gl + 2), b3 = __shfl_sync(gmask, myBits, gl + 3);
-  if (j == 0) {
+  __syncthreads();
+  if (tid == 0) {
+    const u32 b0 = S.fragBits[0], b1 = S.fragBits[1], b2 = S.fragBits[2], b3 = S.fragBits[3];
+    const i64 hdrBits = S.hdrBits;
     BitWriterD bw(hdr);
     bw.nbytes = hdrBits >> 3; bw.nacc = (int)(hdrBits & 7);
     bw.acc = (bw.nacc > 0) ? ((u64)hdr[bw.nbytes] >> (8 - bw.nacc)) : 0;
@@ -409,22 +448,29 @@ __global__ void huff_scan_kernel(KzgBlock* __restrict__ blocks, int nBlocks, Kzg
   B.entBits = (i64)br.pos - B.srcBit;
 }
 
+// decode: one CTA of 128 threads per chunk.  Thread 0 reads the code lengths (a serial bit stream) while the other warps stage the
+// four fragments' bit strings in shared memory (word-aligned at the fragment's first bit, big-endian words); all threads fill the
+// 4096-entry table; lanes 0-3 of warp 0 decode one fragment each out of shared memory into shared memory (no global access
+// on the dependent chain); the chunk goes out with coalesced stores.
+#define HFD_THREADS 128
 struct HfDecSmem {
-  u16 table[HF_GROUPS][1 << HF_MAXLEN];
-  u32 codes[HF_GROUPS][256];
-  u8 sizes[HF_GROUPS][256];
-  u8 alpha[HF_GROUPS][256];
-  u8 present[HF_GROUPS][256];
-  u8 order[HF_GROUPS][256];
+  u16 table[1 << HF_MAXLEN];
+  u32 codes[256];
+  u8 sizes[256];
+  u8 alpha[256];
+  u8 present[256];
+  u8 order[256];
+  u32 bits[4][HF_FRAG_STRIDE / 4];
+  u8 out[HF_CHUNK];
+  int nsym, bad;
 };
 
-__global__ void __launch_bounds__(64) huff_decode_kernel(KzgBlock* __restrict__ blocks, KzgEntParams P) {
+__global__ void __launch_bounds__(HFD_THREADS) huff_decode_kernel(KzgBlock* __restrict__ blocks, KzgEntParams P) {
   extern __shared__ __align__(16) u8 smem_raw[];
   HfDecSmem& S = *reinterpret_cast<HfDecSmem*>(smem_raw);
-  const int g = threadIdx.x >> 2, j = threadIdx.x & 3;
+  const int tid = threadIdx.x;
   const int b = blockIdx.y;
-  const int c = blockIdx.x * HF_GROUPS + g;
-  if (c >= P.maxChunks) return;
+  const int c = blockIdx.x;
   KzgBlock& B = blocks[b];
   if (!(B.status == 0 && B.entropy == P.entropy)) return;
   const int len = B.preLen;
@@ -434,18 +480,17 @@ __global__ void __launch_bounds__(64) huff_decode_kernel(KzgBlock* __restrict__ 
   u8* __restrict__ out = B.cur + start;
   const u8* __restrict__ stream = P.stream;
   const KzgChunkInfo info = P.chunks[(i64)b * P.maxChunks + c];
-  const u32 gmask = 0xFu << ((threadIdx.x & 31) & ~3);
-  const int gl = (threadIdx.x & 31) & ~3;
   if (count < 32) {
-    for (int i = j; i < count; i += 4) out[i] = (u8)get_bits(stream, (u64)info.hdrBit + 8ull * i, 8);
+    for (int i = tid; i < count; i += HFD_THREADS) out[i] = (u8)get_bits(stream, (u64)info.hdrBit + 8ull * i, 8);
     return;
   }
-  // ---- readLengths (:115-154) + buildDecodingTables (:162-191), lane 0; table fill shared by the 4 lanes ----
-  int nsym = 0, bad = 0;
-  if (j == 0) {
+  const int szFrag = count / 4;
+  // ---- readLengths (:115-154) on thread 0; the fragments' bits are staged meanwhile ----
+  if (tid == 0) {
+    int nsym = 0, bad = 0;
     BitReaderD br(stream, (u64)info.hdrBit, (u64)(B.srcBit + B.srcBits));
-    u8* alphabet = S.alpha[g];
-    for (int i = 0; i < 256; i++) S.present[g][i] = 0;
+    u8* alphabet = S.alpha;
+    for (int i = 0; i < 256; i++) S.present[i] = 0;
     if (br.read(1) == 0) { if (br.read(1) == 0) { nsym = 256; for (int i = 0; i < 256; i++) alphabet[i] = (u8)i; } }
     else {
       const int lastMask = (int)br.read(5);
@@ -456,72 +501,76 @@ __global__ void __launch_bounds__(64) huff_decode_kernel(KzgBlock* __restrict__ 
     }
     int curSize = 2;
     for (int i = 0; i < nsym; i++) {
-      const int s = alphabet[i];
+      const int sy = alphabet[i];
       curSize += hf_expgolomb_dec(br);
       if ((curSize <= 0) || (curSize > HF_MAXLEN)) { bad = 1; break; }
-      S.sizes[g][s] = (u8)curSize;
-      S.present[g][s] = 1;
+      S.sizes[sy] = (u8)curSize;
+      S.present[sy] = 1;
     }
     if (!bad && nsym > 1) {
-      if (hf_canonical_codes(S.sizes[g], S.codes[g], S.present[g], nsym, S.order[g]) < 0) bad = 1;
+      if (hf_canonical_codes(S.sizes, S.codes, S.present, nsym, S.order) < 0) bad = 1;
+    }
+    S.nsym = nsym; S.bad = bad;
+  } else if (tid >= 32 && info.alphabetSize > 1) {
+    // fragment j: bits [pos_j, pos_j + st_j) of the stream; bits at or beyond the fragment's end read as zero (the Java buffer
+    // is zero-filled, :414-415)
+    u64 pos = (u64)info.payBit;
+    for (int j = 0; j < 4; j++) {
+      const u32 nb = info.st[j];
+      const u32 nw = (nb + 31) >> 5;
+      for (u32 k = tid - 32; k < nw; k += HFD_THREADS - 32) {
+        u32 w = get_bits(stream, pos + 32ull * k, 32);
+        const u32 left = nb - 32 * k;
+        if (left < 32) w &= ~(0xFFFFFFFFu >> left);
+        S.bits[j][k] = w;
+      }
+      for (u32 k = nw + (tid - 32); k < nw + 2 && k < HF_FRAG_STRIDE / 4; k += HFD_THREADS - 32) S.bits[j][k] = 0;
+      pos += nb;
     }
   }
-  nsym = __shfl_sync(gmask, nsym, gl);
-  bad = __shfl_sync(gmask, bad, gl);
-  __syncwarp(gmask);
-  if (bad || nsym == 0) { if (j == 0) atomicExch(&B.status, -KZG_ERR_PROCESS_BLOCK); return; }
+  __syncthreads();
+  const int nsym = S.nsym;
+  if (S.bad || nsym == 0) { if (tid == 0) atomicExch(&B.status, -KZG_ERR_PROCESS_BLOCK); return; }
   if (nsym == 1) {
-    const u8 v = S.alpha[g][0];
-    for (int i = j; i < count; i += 4) out[i] = v;
+    const u8 v = S.alpha[0];
+    for (int i = tid; i < count; i += HFD_THREADS) out[i] = v;
     return;
   }
-  for (int i = j; i < (1 << HF_MAXLEN); i += 4) S.table[g][i] = 7;
-  __syncwarp(gmask);
-  {
-    // buildDecodingTables (:162-191) walks the alphabet re-sorted by (size, symbol) (generateCanonicalCodes
-    // sorts it in place), so its running `length` is the symbol's own size: idx = code << (12 - size).
-    for (int i = j; i < nsym; i += 4) {
-      const int s = S.alpha[g][i];
-      const int sz = S.sizes[g][s];
-      const u16 val = (u16)((sz << 8) | s);
-      const int idx0 = (int)(S.codes[g][s] << (HF_MAXLEN - sz));
-      const int cnt = 1 << (HF_MAXLEN - sz);
-      for (int k = 0; k < cnt; k++) if (idx0 + k < (1 << HF_MAXLEN)) S.table[g][idx0 + k] = val;
-    }
+  for (int i = tid; i < (1 << HF_MAXLEN); i += HFD_THREADS) S.table[i] = 7;
+  __syncthreads();
+  // buildDecodingTables (:162-191) walks the alphabet re-sorted by (size, symbol) (generateCanonicalCodes sorts it in place), so
+  // its running `length` is the symbol's own size: idx = code << (12 - size).
+  for (int i = tid; i < nsym; i += HFD_THREADS) {
+    const int sy = S.alpha[i];
+    const int sz = S.sizes[sy];
+    const u16 val = (u16)((sz << 8) | sy);
+    const int idx0 = (int)(S.codes[sy] << (HF_MAXLEN - sz));
+    const int cnt = 1 << (HF_MAXLEN - sz);
+    for (int k = 0; k < cnt; k++) if (idx0 + k < (1 << HF_MAXLEN)) S.table[idx0 + k] = val;
   }
-  __syncwarp(gmask);
+  __syncthreads();
 
   // ---- decodeChunk (:404-587): lane j decodes fragment j ----
-  const int szFrag = count / 4;
-  u64 pos = (u64)info.payBit;
-  for (int k = 0; k < j; k++) pos += info.st[k];
-  const u64 fragEnd = pos + info.st[j];
-  u8* o = out + j * szFrag;
-  u64 win = 0; int avail = 0;        // `avail` valid bits at the bottom of win
-  int consumed = 0;
-  for (int i = 0; i < szFrag; i++) {
-    if (avail < HF_MAXLEN) {
-      // refill 32 bits; bits at or beyond fragEnd read as zero (the Java buffer is zero-filled, :414-415)
-      u32 w = 0;
-      if (pos < fragEnd) {
-        w = get_bits(stream, pos, 32);
-        const u64 left = fragEnd - pos;
-        if (left < 32) w &= ~((1u << (32 - (int)left)) - 1);
-      }
-      win = (win << 32) | (u64)w;
-      avail += 32;
-      pos += 32;
+  if (tid < 4) {
+    const int j = tid;
+    const u32* __restrict__ fb = S.bits[j];
+    u8* o = S.out + j * szFrag;
+    u64 win = 0; int avail = 0;        // `avail` valid bits at the bottom of win
+    int consumed = 0, wi = 0;
+    for (int i = 0; i < szFrag; i++) {
+      if (avail < HF_MAXLEN) { win = (win << 32) | (u64)fb[min(wi, HF_FRAG_STRIDE / 4 - 1)]; wi++; avail += 32; }
+      const u32 idx = (u32)(win >> (avail - HF_MAXLEN)) & ((1u << HF_MAXLEN) - 1);
+      const u32 val = S.table[idx];
+      const int cl = (int)(val >> 8);
+      avail -= cl;
+      consumed += cl;
+      o[i] = (u8)val;
     }
-    const u32 idx = (u32)(win >> (avail - HF_MAXLEN)) & ((1u << HF_MAXLEN) - 1);
-    const u32 val = S.table[g][idx];
-    const int cl = (int)(val >> 8);
-    avail -= cl;
-    consumed += cl;
-    o[i] = (u8)val;
+    if (consumed != (int)info.st[j]) atomicExch(&B.status, -KZG_ERR_PROCESS_BLOCK);
   }
-  const int okFrag = (consumed == (int)info.st[j]);
-  if (!okFrag) atomicExch(&B.status, -KZG_ERR_PROCESS_BLOCK);
-  if (j == 0) {
+  __syncthreads();
+  for (int i = tid; i < 4 * szFrag; i += HFD_THREADS) out[i] = S.out[i];
+  if (tid == 0) {
     u64 tpos = (u64)info.payBit + info.st[0] + info.st[1] + info.st[2] + info.st[3];
     for (int i = 4 * szFrag; i < count; i++, tpos += 8) out[i] = (u8)get_bits(stream, tpos, 8);
   }
@@ -529,19 +578,19 @@ __global__ void __launch_bounds__(64) huff_decode_kernel(KzgBlock* __restrict__ 
 
 int kzg_huff_encode_launch(cudaStream_t s, const KzgBlock* d_blocks, int nBlocks, const KzgEntParams& P) {
   CUDA_TRY(cudaFuncSetAttribute(huff_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HfEncSmem)));   // per device: set on every launch
-  dim3 grid((P.maxChunks + HF_GROUPS - 1) / HF_GROUPS, nBlocks);
-  huff_encode_kernel<<<grid, 64, sizeof(HfEncSmem), s>>>(d_blocks, P);
+  dim3 grid(P.maxChunks, nBlocks);
+  KZG_PROF("huff_encode_kernel", s, (huff_encode_kernel<<<grid, HFE_THREADS, sizeof(HfEncSmem), s>>>(d_blocks, P)));
   CUDA_TRY(cudaGetLastError());
   kzg_count_launch(1);
   return 0;
 }
 
 int kzg_huff_decode_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, const KzgEntParams& P) {
-  huff_scan_kernel<<<(nBlocks + 31) / 32, 32, 0, s>>>(d_blocks, nBlocks, P);
+  KZG_PROF("huff_scan_kernel", s, (huff_scan_kernel<<<(nBlocks + 31) / 32, 32, 0, s>>>(d_blocks, nBlocks, P)));
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaFuncSetAttribute(huff_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HfDecSmem)));
-  dim3 grid((P.maxChunks + HF_GROUPS - 1) / HF_GROUPS, nBlocks);
-  huff_decode_kernel<<<grid, 64, sizeof(HfDecSmem), s>>>(d_blocks, P);
+  dim3 grid(P.maxChunks, nBlocks);
+  KZG_PROF("huff_decode_kernel", s, (huff_decode_kernel<<<grid, HFD_THREADS, sizeof(HfDecSmem), s>>>(d_blocks, P)));
   CUDA_TRY(cudaGetLastError());
   kzg_count_launch(2);
   return 0;
