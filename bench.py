@@ -557,7 +557,7 @@ def other_configs(torch, K, dev, kstream, flags, a):
             e0.record(kstream); kk = c.enc_dev(); e1.record(kstream); c.dec_dev(kk); e2.record(kstream)
             torch.cuda.synchronize()
             res.append((e0.elapsed_time(e1), e1.elapsed_time(e2)))
-        for _ in range(reps if gate_s <= 8.0 else 0):
+        for _ in range(reps if gate_s <= 25.0 else 0):
             e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             e0.record(kstream); kk = c.enc_host(); e1.record(kstream); c.dec_host(kk); e2.record(kstream)
             torch.cuda.synchronize()

@@ -1110,6 +1110,11 @@ static int64_t decompress_impl(const uint8_t* d_in, int64_t nBytes, const uint8_
         if (timing3 && g == 0) { if (cudaEventRecord(ev[1], q) != cudaSuccess) { rc = -KZG_ERR_PROCESS_BLOCK; break; } }
         for (int i = nf - 1; i >= 0; i--) {
           if (fn[i] == KZG_T_NONE) continue;
+          // a stage no block of this group runs (skip flags; BWT under the reference's bounds) is not launched at all: some launchers
+          // read block headers back and would make the host wait for the whole group, serialising the groups
+          bool anyOn = false;
+          for (int b = b0; b < b1 && !anyOn; b++) anyOn = bt.hEnabled[(size_t)i * nb + b] != 0;
+          if (!anyOn) continue;
           sub.dEnabled = dEnabledAll + (size_t)i * nb + b0;
           rc = run_transform_stage(sub, fn[i], i, false, xs, dScratch + (size_t)b0 * xs.perBlock, dHash + (size_t)b0 * xs.hashInts, dAux + (size_t)b0 * xs.aux32, flags);
           if (rc < 0) break;

@@ -499,8 +499,11 @@ __global__ void __launch_bounds__(32) sbrt_fwd_rank_kernel(KzgBlock* __restrict_
 }
 
 // ---- SBRT inverse: one warp per block (the list state depends on every symbol decoded so far).  The list is kept in rank order
-// (symbol + key per rank); a position costs one round of shared-memory traffic when its rank is below 32.
-__global__ void __launch_bounds__(32) sbrt_inv_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P, int mode) {
+// (symbol + key per rank): ranks 0-31 live in registers, one per lane (a lone warp issues an instruction every ~5 cycles, so the
+// step is written for the fewest instructions: three shuffles fetch the hit entry, one ballot finds its new rank, three
+// shuffle-ups move the entries in between); ranks 32-255 stay in shared memory and are touched only when a deep rank is hit.
+template <int MODE>
+__global__ void __launch_bounds__(32) sbrt_inv_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P) {
   __shared__ u64 KR[256 + 32];
   __shared__ u8 r2s[256 + 32];
   const int lane = threadIdx.x, b = blockIdx.x;
@@ -512,33 +515,43 @@ __global__ void __launch_bounds__(32) sbrt_inv_kernel(KzgBlock* __restrict__ blo
   const u8* __restrict__ src = B.cur;
   u8* __restrict__ dst = B.alt;
   if (count > min(kzg_dst_limit(B, P.dstLimit[b]), B.cap)) return;
-  const int m1 = (mode == 3) ? 0 : -1, m2 = (mode == 1) ? 0 : -1, s = (mode == 2) ? 1 : 0;
+  constexpr int m1 = (MODE == 3) ? 0 : -1, m2 = (MODE == 1) ? 0 : -1, s = (MODE == 2) ? 1 : 0;      // (compile-time: the step is instruction bound)
   for (int i = lane; i < 256; i += 32) { KR[i] = (u64)(255 - i); r2s[i] = (u8)i; }
   __syncwarp();
+  u64 kk = (u64)(255 - lane);           // rank `lane`: key and symbol
+  int sy = lane;
   for (int base = 0; base < count; base += 32) {
     const int nIn = min(32, count - base);
     const int mine = (lane < nIn) ? (int)src[base + lane] : 0;
     int outv = 0;
+    const u32 deep = __ballot_sync(0xFFFFFFFFu, mine >= 32);
     for (int t = 0; t < nIn; t++) {
       const int i = base + t;
       const int r = __shfl_sync(0xFFFFFFFFu, mine, t);
-      const int c = r2s[r];
-      const u64 kc = KR[r];
-      if (lane == t) outv = c;
-      const u32 low = (u32)(kc & 0x7FFFFFFFull);
-      const int pOld = (low >= 256u) ? (int)(low - 256u) : 0;
-      const int qc = ((i & m1) + (pOld & m2)) >> s;
-      const u64 nk = ((u64)(u32)qc << 31) | (u64)(u32)(i + 256);
-      if (r <= 32) {
-        // entries 0..r-1: how many keep their place (key > nk); the rest move down one slot
-        const u64 kk = (lane < r) ? KR[lane] : 0ull;
-        const int sy = (lane < r) ? (int)r2s[lane] : 0;
+      if (!((deep >> t) & 1u)) {
+        const int c = __shfl_sync(0xFFFFFFFFu, sy, r);
+        const u32 low = __shfl_sync(0xFFFFFFFFu, (u32)kk, r) & 0x7FFFFFFFu;
+        const u64 upK = __shfl_up_sync(0xFFFFFFFFu, kk, 1);
+        const int upS = __shfl_up_sync(0xFFFFFFFFu, sy, 1);
+        if (lane == t) outv = c;
+        const int pOld = (low >= 256u) ? (int)(low - 256u) : 0;
+        const int qc = ((i & m1) + (pOld & m2)) >> s;
+        const u64 nk = ((u64)(u32)qc << 31) | (u64)(u32)(i + 256);
+        // entries 0..r-1: those with key > nk keep their place (keys descend with the rank), the rest move down one slot
         const int rn = __popc(__ballot_sync(0xFFFFFFFFu, (lane < r) && (kk > nk)));
-        __syncwarp();
-        if (lane >= rn && lane < r) { KR[lane + 1] = kk; r2s[lane + 1] = (u8)sy; }
-        if (lane == 0) { KR[rn] = nk; r2s[rn] = (u8)c; }
-        __syncwarp();
+        if (lane > rn && lane <= r) { kk = upK; sy = upS; }
+        else if (lane == rn) { kk = nk; sy = c; }
       } else {
+        // deep rank: through the shared-memory list (the registers are its first 32 entries)
+        KR[lane] = kk; r2s[lane] = (u8)sy;
+        __syncwarp();
+        const int c = r2s[r];
+        const u64 kc = KR[r];
+        if (lane == t) outv = c;
+        const u32 low = (u32)(kc & 0x7FFFFFFFull);
+        const int pOld = (low >= 256u) ? (int)(low - 256u) : 0;
+        const int qc = ((i & m1) + (pOld & m2)) >> s;
+        const u64 nk = ((u64)(u32)qc << 31) | (u64)(u32)(i + 256);
         int rn = 0;
         for (int lo = 0; lo < r; lo += 32) {                  // keys descend with the rank: count the ones above nk
           const int k = lo + lane;
@@ -549,14 +562,15 @@ __global__ void __launch_bounds__(32) sbrt_inv_kernel(KzgBlock* __restrict__ blo
         for (int top = r - 1; top >= rn; top -= 32) {         // entries [rn, r) move down one slot, highest chunk first
           const int k = top - lane;
           const bool on = k >= rn;
-          u64 kk = 0; int sy = 0;
-          if (on) { kk = KR[k]; sy = r2s[k]; }
+          u64 k2 = 0; int s2 = 0;
+          if (on) { k2 = KR[k]; s2 = r2s[k]; }
           __syncwarp();
-          if (on) { KR[k + 1] = kk; r2s[k + 1] = (u8)sy; }
+          if (on) { KR[k + 1] = k2; r2s[k + 1] = (u8)s2; }
           __syncwarp();
         }
         if (lane == 0) { KR[rn] = nk; r2s[rn] = (u8)c; }
         __syncwarp();
+        kk = KR[lane]; sy = r2s[lane];
       }
     }
     if (lane < nIn) dst[base + lane] = (u8)outv;
@@ -842,7 +856,9 @@ int kzg_sbrt_launch(cudaStream_t s, bool forward, int mode, KzgBlock* d_blocks, 
     KZG_PROF("sbrt_fwd_scan_kernel", s, (sbrt_fwd_scan_kernel<<<nBlocks, 256, 0, s>>>(d_blocks, P)));
     KZG_PROF("sbrt_fwd_rank_kernel", s, (sbrt_fwd_rank_kernel<<<dim3(tiles, nBlocks), 32, 0, s>>>(d_blocks, P, mode)));
     kzg_count_launch(2);
-  } else KZG_PROF("sbrt_inv_kernel", s, (sbrt_inv_kernel<<<nBlocks, 32, 0, s>>>(d_blocks, P, mode)));
+  } else if (mode == 1) KZG_PROF("sbrt_inv_kernel", s, (sbrt_inv_kernel<1><<<nBlocks, 32, 0, s>>>(d_blocks, P)));
+  else if (mode == 2) KZG_PROF("sbrt_inv_kernel", s, (sbrt_inv_kernel<2><<<nBlocks, 32, 0, s>>>(d_blocks, P)));
+  else KZG_PROF("sbrt_inv_kernel", s, (sbrt_inv_kernel<3><<<nBlocks, 32, 0, s>>>(d_blocks, P)));
   CUDA_TRY(cudaGetLastError());
   kzg_count_launch(1);
   return 0;
