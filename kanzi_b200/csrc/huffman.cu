@@ -238,9 +238,10 @@ struct HfEncSmem {
   u8 alpha[256];
   u8 present[256];
   u8 lists[6 * 256];
-  u8 data[HF_CHUNK];
+  __align__(16) u8 data[HF_CHUNK];
   u32 bits[4][HF_FRAG_STRIDE / 4];
   int nsym, err; i64 hdrBits; u32 fragBits[4];
+  u64 bar;                        // mbarrier of the chunk's bulk copy
 };
 
 __global__ void __launch_bounds__(HFE_THREADS) huff_encode_kernel(const KzgBlock* __restrict__ blocks, KzgEntParams P) {
@@ -270,9 +271,23 @@ __global__ void __launch_bounds__(HFE_THREADS) huff_encode_kernel(const KzgBlock
   u8* hdr = P.hdrBuf + gidx * (i64)P.hdrStride;
   u8* pay = P.payBuf + gidx * (i64)P.payStride;
 
+  // the chunk comes in with ONE bulk asynchronous copy (cp.async.bulk, completion on an mbarrier) when its address allows (16-byte
+  // aligned: always, for buffers of this library and for caller blocks on 16-byte boundaries); the histograms are cleared meanwhile
+  const int bulk = (((uintptr_t)(data + start) & 15) == 0) ? (count & ~15) : 0;
+  if (tid == 0) {
+    kzg_mbar_init(&S.bar, 1);
+    if (bulk) kzg_bulk_g2s(S.data, data + start, (u32)bulk, &S.bar);
+  }
   for (int k = tid; k < 4 * 256; k += HFE_THREADS) (&S.freq[0][0])[k] = 0;
+  for (int i = bulk + tid; i < count; i += HFE_THREADS) S.data[i] = data[start + i];
   __syncthreads();
-  for (int i = tid; i < count; i += HFE_THREADS) { const u8 v = data[start + i]; S.data[i] = v; atomicAdd(&S.freq[warp][v], 1u); }
+  if (bulk) kzg_mbar_wait(&S.bar, 0);
+  for (int i = tid * 4; i < count; i += HFE_THREADS * 4) {        // four symbols per thread and step out of shared memory
+    const u32 w = *reinterpret_cast<const u32*>(S.data + i);
+    const int nv = min(4, count - i);
+    #pragma unroll
+    for (int k = 0; k < 4; k++) if (k < nv) atomicAdd(&S.freq[warp][(w >> (8 * k)) & 0xFF], 1u);
+  }
   __syncthreads();
   for (int k = tid; k < 256; k += HFE_THREADS) S.freq[0][k] += S.freq[1][k] + S.freq[2][k] + S.freq[3][k];
   __syncthreads();

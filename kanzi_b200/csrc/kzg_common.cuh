@@ -123,6 +123,26 @@ __device__ __forceinline__ i32 read_varint(BitReaderD& br) {
 
 __device__ __forceinline__ int ilog2(u32 x) { return 31 - __clz(x); }   // Global.log2, x > 0
 
+// ---- bulk asynchronous copy global -> shared (the TMA engine's 1-D form, sm_90+: `cp.async.bulk`), completion on an mbarrier ----
+// One thread issues the copy of a whole tile; the CTA's other instructions (and the issuing thread's) run while the bytes arrive.
+// dst and src must be 16-byte aligned and `bytes` a multiple of 16.
+__device__ __forceinline__ void kzg_mbar_init(u64* bar, int arrivals) {
+  const u32 a = (u32)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(arrivals));
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // make the initialised barrier visible to the async proxy
+}
+__device__ __forceinline__ void kzg_bulk_g2s(void* dstSmem, const void* srcGlobal, u32 bytes, u64* bar) {
+  const u32 d = (u32)__cvta_generic_to_shared(dstSmem), b = (u32)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(d), "l"(srcGlobal), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void kzg_mbar_wait(u64* bar, u32 phase) {
+  const u32 b = (u32)__cvta_generic_to_shared(bar);
+  asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}"
+               ::"r"(b), "r"(phase) : "memory");
+}
+
 // mix32 of the container checksums (COS:89-93)
 __host__ __device__ __forceinline__ u32 kzg_mix32(u32 c, u32 h, u32 v) {
   c ^= h * ~v;
