@@ -1,12 +1,12 @@
 // small_xf.cu — ZRLT, SBRT (RANK / MTFT) and SRT kernels (sm_100a).
 //
 // Replaces K/transform/ZRLT.java, SBRT.java, SRT.java.
-// ZRLT is a scan: one warp per block walks 32-byte tiles, classifies bytes with ballots (zero runs,
-// 0xFF escapes), sizes each lane's output, prefix-sums the sizes and scatters — run lengths and escape
-// parity are carried across tiles in registers.
-// SBRT / SRT are list-update state machines (the output at i depends on the list after i-1): one warp
-// per block keeps the 256-entry list in shared memory; the search for the insertion rank is a ballot
-// over 32 candidates per step and the shift of the displaced entries is lane-parallel.
+// ZRLT is a scan: 4096-byte tiles, one warp each, classify bytes with ballots (zero runs, 0xFF escapes), size each lane's
+// output, prefix-sum the sizes and scatter; what crosses a tile edge (run in progress, digit sequence, escape parity) is carried by
+// a scan over per-tile summaries.
+// SBRT / SRT forward are tile-parallel too (the emitted rank is a function of the symbols' last occurrences); their inverses are
+// list-update state machines (the output at i depends on the list after i-1): one warp per block, the head of the list in
+// registers.
 #include "kzg_common.cuh"
 #include "kzg_transforms.cuh"
 #include "kzg_xf_kernels.cuh"
@@ -327,71 +327,8 @@ __global__ void __launch_bounds__(32) zrlt_inv_emit_kernel(KzgBlock* __restrict_
 }
 
 // ================================================================================================================
-// list machinery shared by SBRT and SRT: entries [lo, hi) move up one slot (to [lo+1, hi+1))
-// ================================================================================================================
-template <bool WITH_Q, bool WITH_S2R>
-__device__ __forceinline__ void list_shift_up(u8* r2s, i32* qr, u8* s2r, int lo, int hi, int lane) {
-  for (int top = hi - 1; top >= lo; top -= 32) {
-    const int k = top - lane;
-    u8 sym = 0; i32 q = 0;
-    const bool on = k >= lo;
-    if (on) { sym = r2s[k]; if (WITH_Q) q = qr[k]; }
-    __syncwarp();
-    if (on) { r2s[k + 1] = sym; if (WITH_Q) qr[k + 1] = q; if (WITH_S2R) s2r[sym] = (u8)(k + 1); }
-    __syncwarp();
-  }
-}
-
-// ================================================================================================================
 // SBRT forward / inverse (SBRT.java:87-151, 154-214); mode 1 = MTF, 2 = RANK, 3 = TIMESTAMP
 // ================================================================================================================
-struct SbrtSmem { i32 qr[256]; i32 p[256]; u8 r2s[256]; u8 s2r[256]; };
-
-template <bool FORWARD>
-__global__ void __launch_bounds__(32) sbrt_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P, int mode) {
-  __shared__ SbrtSmem S;
-  const int lane = threadIdx.x, b = blockIdx.x;
-  KzgBlock& B = blocks[b];
-  int* res = P.result + 2 * b;
-  if (lane == 0) { res[0] = 0; res[1] = 0; }
-  if (B.status != 0 || !P.enabled[b]) return;
-  const int count = B.curLen;
-  const u8* __restrict__ src = B.cur;
-  u8* __restrict__ dst = B.alt;
-  if (count > B.cap) return;
-  const int m1 = (mode == 3) ? 0 : -1, m2 = (mode == 1) ? 0 : -1, s = (mode == 2) ? 1 : 0;
-  for (int i = lane; i < 256; i += 32) { S.qr[i] = 0; S.p[i] = 0; S.r2s[i] = (u8)i; S.s2r[i] = (u8)i; }
-  __syncwarp();
-  for (int base = 0; base < count; base += 32) {
-    const int nIn = min(32, count - base);
-    const int mine = (lane < nIn) ? src[base + lane] : 0;     // one coalesced load per 32 symbols
-    int outv = 0;
-    for (int t = 0; t < nIn; t++) {
-      const int i = base + t;
-      const int in = __shfl_sync(0xFFFFFFFFu, mine, t);
-      int r, c;
-      if (FORWARD) { c = in; r = S.s2r[c]; if (lane == t) outv = r; }
-      else { r = in; c = S.r2s[r]; if (lane == t) outv = c; }
-      const int qc = ((i & m1) + (S.p[c] & m2)) >> s;
-      __syncwarp();
-      if (lane == 0) S.p[c] = i;
-      // new rank: just above the highest entry below r whose q is greater than qc (:138-142)
-      int rn = 0;
-      for (int top = r - 1; top >= 0; top -= 32) {
-        const int k = top - lane;
-        const bool gt = (k >= 0) && (S.qr[k] > qc);
-        const u32 m = __ballot_sync(0xFFFFFFFFu, gt);
-        if (m) { rn = top - (__ffs(m) - 1) + 1; break; }
-      }
-      if (rn < r) list_shift_up<true, FORWARD>(S.r2s, S.qr, S.s2r, rn, r, lane);
-      if (lane == 0) { S.r2s[rn] = (u8)c; S.qr[rn] = qc; if (FORWARD) S.s2r[c] = (u8)rn; }
-      __syncwarp();
-    }
-    if (lane < nIn) dst[base + lane] = (u8)outv;
-  }
-  if (lane == 0) { res[0] = 1; res[1] = count; }
-}
-
 // ---- SBRT forward, tile-parallel -----------------------------------------------------------------------------------------
 // The list of SBRT is always sorted by (q, time of the last move) descending (a symbol that gets key qc moves above everything
 // with q <= qc, SBRT.java:138-146; q never decreases), with the symbols never seen yet at the bottom in index order.  So the
