@@ -493,6 +493,10 @@ def main():
                          "how": "CUDA events around every launch of the kernel on its own stream during one extra profiled step (kzg_set_profiling); launches of one "
                                 "step summed (the blocks are dealt into groups, one launch per group and round); algorithmic bytes = the bytes the kernel's step must read + write once",
                          "kernels": ktable,
+                         "decode": (lambda dms: {"ms": round(dms, 3), "algorithmic_bytes": int(knz_len + nloc), "achieved": round((knz_len + nloc) / (dms * 1e-3) / 1e9, 3),
+                                                 "frac": round((knz_len + nloc) / (dms * 1e-3) / 1e9 / peak, 6),
+                                                 "top_kernel": next((k["kernel"] for k in ktable if not enc_side(k["kernel"])), None),
+                                                 "note": "whole decode (entropy + inverse transform) of this rank's shard: coded bytes in + original bytes out over its time"})(dent_ms + dxf_ms),
                          "stage": {"name": dom, "ms": round(stages[dom], 3), "algorithmic_bytes": int(alg_stage[dom]),
                                    "achieved": round(alg_stage[dom] / (stages[dom] * 1e-3) / 1e9, 3) if stages[dom] > 0 else None,
                                    "frac": round(alg_stage[dom] / (stages[dom] * 1e-3) / 1e9 / peak, 6) if stages[dom] > 0 else None}},

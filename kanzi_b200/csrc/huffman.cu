@@ -68,9 +68,9 @@ __device__ int hf_phase2(int* data, int n) {
 
 // HuffmanEncoder.computeCodeLengths (:285-308).  ranks in: (freq << 8) | symbol; out: symbols sorted by
 // (freq, symbol).  work: `count` ints.  sizes indexed by symbol.
-__device__ int hf_code_lengths(u8* sizes, int* ranks, int* work, int count) {
-  // Arrays.sort(ranks, 0, count): shell sort (keys are distinct)
-  for (int gap = 1 << 7; gap > 0; gap >>= 1) {
+__device__ int hf_code_lengths(u8* sizes, int* ranks, int* work, int count, bool presorted = false) {
+  // Arrays.sort(ranks, 0, count): shell sort (keys are distinct); the encode kernel sorts with all its threads beforehand
+  for (int gap = presorted ? 0 : (1 << 7); gap > 0; gap >>= 1) {
     for (int i = gap; i < count; i++) {
       const int t = ranks[i];
       int k = i;
@@ -201,22 +201,25 @@ __device__ void hf_encode_alphabet(BitWriterD& bw, const u8* alphabet, int count
   }
 }
 
-// HuffmanCommon.generateCanonicalCodes (HuffmanCommon.java:71-111): symbols sorted by (size, symbol)
-__device__ int hf_canonical_codes(const u8* sizes, u32* codes, const u8* present, int count, u8* order) {
-  int n = 0;
-  for (int len = 1; len <= HF_MAXLEN && n < count; len++)
-    for (int s = 0; s < 256 && n < count; s++)
-      if (present[s] && sizes[s] == len) order[n++] = (u8)s;
-  if (n != count) return -1;
-  int code = 0, curLen = sizes[order[0]];
-  for (int i = 0; i < count; i++) {
-    const int s = order[i];
-    code <<= (sizes[s] - curLen);
-    curLen = sizes[s];
-    codes[s] = (u32)code;
-    code++;
+// HuffmanCommon.generateCanonicalCodes (HuffmanCommon.java:71-111): symbols sorted by (size, symbol), codes counted up, shifted left at
+// every size step.  All threads of a CTA at once: in (size, symbol) order the code of a symbol is the Kraft sum of the symbols before
+// it, sum 2^(12 - size_t), shifted down to its own size (sizes ascend in that order, so the sum is a multiple of 2^(12 - size)).
+// codes[s] = the sum itself (= the symbol's first slot in the 4096-entry decoding table).  Returns false for a present symbol
+// whose size is outside 1..12 (generateCanonicalCodes would not place it).
+__device__ __forceinline__ bool hf_kraft_prefix(const u8* sizes, const u8* present, u32* kraft, int tid, int nthreads) {
+  bool ok = true;
+  for (int sy = tid; sy < 256; sy += nthreads) {
+    if (!present[sy]) continue;
+    const int sz = sizes[sy];
+    if (sz < 1 || sz > HF_MAXLEN) { ok = false; continue; }
+    u32 k = 0;
+    for (int t = 0; t < 256; t++) {
+      const int st = sizes[t];
+      if (present[t] && st >= 1 && st <= HF_MAXLEN && (st < sz || (st == sz && t < sy))) k += 1u << (HF_MAXLEN - st);
+    }
+    kraft[sy] = k;
   }
-  return count;
+  return ok;
 }
 
 // ================================================================================================================
@@ -240,7 +243,7 @@ struct HfEncSmem {
   u8 lists[6 * 256];
   __align__(16) u8 data[HF_CHUNK];
   u32 bits[4][HF_FRAG_STRIDE / 4];
-  int nsym, err; i64 hdrBits; u32 fragBits[4];
+  int nsym, err, direct; i64 hdrBits; u32 fragBits[4];
   u64 bar;                        // mbarrier of the chunk's bulk copy
 };
 
@@ -292,48 +295,66 @@ __global__ void __launch_bounds__(HFE_THREADS) huff_encode_kernel(const KzgBlock
   for (int k = tid; k < 256; k += HFE_THREADS) S.freq[0][k] += S.freq[1][k] + S.freq[2][k] + S.freq[3][k];
   __syncthreads();
 
+  // Arrays.sort of (freq << 8 | symbol) over the present symbols (HuffmanEncoder.java:288): keys are distinct, so a key's place is the
+  // number of smaller keys (every thread places two symbols)
+  for (int sy = tid; sy < 256; sy += HFE_THREADS) {
+    const u32 f = S.freq[0][sy];
+    S.present[sy] = f > 0;
+    if (f == 0) continue;
+    const u32 key = (f << 8) | (u32)sy;
+    int rk = 0;
+    for (int t = 0; t < 256; t++) { const u32 ft = S.freq[0][t]; rk += (ft > 0 && ((ft << 8) | (u32)t) < key) ? 1 : 0; }
+    S.ranks[rk] = (int)key;
+  }
+  __syncthreads();
   if (tid == 0) {   // updateFrequencies (:103-178)
-    int nsym = 0, err = 0;
+    int nsym = 0, err = 0, direct = 0;
     BitWriterD bw(hdr);
     u8* alphabet = S.alpha; u8* sizes = S.sizes; u32* codes = S.codes; int* ranks = S.ranks;
     for (int i = 0; i < 256; i++) {
-      codes[i] = 0; sizes[i] = 0; S.present[i] = 0;
-      if (S.freq[0][i] > 0) { alphabet[nsym++] = (u8)i; S.present[i] = 1; }
+      codes[i] = 0; sizes[i] = 0;
+      if (S.present[i]) alphabet[nsym++] = (u8)i;
     }
     hf_encode_alphabet(bw, alphabet, nsym);
+    for (int i = nsym; i < 256; i++) ranks[i] = 0;       // (the reference's array is zero beyond the alphabet: limitCodeLengths scans it)
     if (nsym == 1) {
-      codes[alphabet[0]] = 0;     // code value of (1 << 24) masks to 0; the length goes in below
-      sizes[alphabet[0]] = 1;
+      sizes[alphabet[0]] = 1;       // (code 0)
     } else {
-      for (int i = 0; i < 256; i++) ranks[i] = 0;
-      for (int i = 0; i < nsym; i++) ranks[i] = (int)((S.freq[0][alphabet[i]] << 8) | alphabet[i]);
-      int maxCodeLen = hf_code_lengths(sizes, ranks, S.work, nsym);
+      int maxCodeLen = hf_code_lengths(sizes, ranks, S.work, nsym, true);
       if (maxCodeLen == 0) err = 1;
       if (!err && maxCodeLen > HF_MAXLEN) {
         maxCodeLen = hf_limit_lengths(alphabet, S.freq[0], sizes, ranks, S.work, S.lists, nsym, &err);
         if (maxCodeLen == 0) err = 1;
       }
-      if (!err) {
-        if (maxCodeLen > HF_MAXLEN) {      // unlikely fallback (:146-155)
-          for (int i = 0; i < nsym; i++) { codes[alphabet[i]] = (u32)i; sizes[alphabet[i]] = 8; }
-        } else {
-          if (hf_canonical_codes(sizes, codes, S.present, nsym, S.lists) < 0) err = 1;
-        }
+      if (!err && maxCodeLen > HF_MAXLEN) {      // unlikely fallback (:146-155): 8-bit codes = the symbol's rank in the alphabet
+        for (int i = 0; i < nsym; i++) { codes[alphabet[i]] = (u32)i; sizes[alphabet[i]] = 8; }
+        direct = 1;
       }
     }
     if (!err) {
       int prevSize = 2;
       for (int i = 0; i < nsym; i++) {
-        const int sy = alphabet[i];
-        const int currSize = sizes[sy];
-        codes[sy] |= ((u32)currSize << 24);
+        const int currSize = sizes[alphabet[i]];
         hf_expgolomb(bw, currSize - prevSize);
         prevSize = currSize;
       }
     }
     S.hdrBits = bw.bits();
     bw.flush();
-    S.nsym = nsym; S.err = err;
+    S.nsym = nsym; S.err = err; S.direct = direct;
+  }
+  __syncthreads();
+  // canonical codes (HuffmanCommon.generateCanonicalCodes :71-111), all threads; codes[] = (size << 24) | code
+  if (!S.err && S.nsym > 1) {
+    if (!S.direct) {
+      if (!hf_kraft_prefix(S.sizes, S.present, S.codes, tid, HFE_THREADS)) S.err = 1;
+      __syncthreads();
+    }
+    for (int sy = tid; sy < 256; sy += HFE_THREADS) {
+      if (!S.present[sy]) continue;
+      const u32 sz = S.sizes[sy];
+      S.codes[sy] = (sz << 24) | (S.direct ? S.codes[sy] : (S.codes[sy] >> (HF_MAXLEN - sz)));
+    }
   }
   __syncthreads();
   const int nsym = S.nsym;
@@ -474,7 +495,6 @@ struct HfDecSmem {
   u8 sizes[256];
   u8 alpha[256];
   u8 present[256];
-  u8 order[256];
   u32 bits[4][HF_FRAG_STRIDE / 4];
   u8 out[HF_CHUNK];
   int nsym, bad;
@@ -522,9 +542,6 @@ __global__ void __launch_bounds__(HFD_THREADS) huff_decode_kernel(KzgBlock* __re
       S.sizes[sy] = (u8)curSize;
       S.present[sy] = 1;
     }
-    if (!bad && nsym > 1) {
-      if (hf_canonical_codes(S.sizes, S.codes, S.present, nsym, S.order) < 0) bad = 1;
-    }
     S.nsym = nsym; S.bad = bad;
   } else if (tid >= 32 && info.alphabetSize > 1) {
     // fragment j: bits [pos_j, pos_j + st_j) of the stream; bits at or beyond the fragment's end read as zero (the Java buffer
@@ -552,14 +569,17 @@ __global__ void __launch_bounds__(HFD_THREADS) huff_decode_kernel(KzgBlock* __re
     return;
   }
   for (int i = tid; i < (1 << HF_MAXLEN); i += HFD_THREADS) S.table[i] = 7;
+  // canonical codes, all threads: codes[] = Kraft prefix = the symbol's first table slot (see hf_kraft_prefix)
+  if (!hf_kraft_prefix(S.sizes, S.present, S.codes, tid, HFD_THREADS)) S.bad = 1;
   __syncthreads();
+  if (S.bad) { if (tid == 0) atomicExch(&B.status, -KZG_ERR_PROCESS_BLOCK); return; }
   // buildDecodingTables (:162-191) walks the alphabet re-sorted by (size, symbol) (generateCanonicalCodes sorts it in place), so
   // its running `length` is the symbol's own size: idx = code << (12 - size).
   for (int i = tid; i < nsym; i += HFD_THREADS) {
     const int sy = S.alpha[i];
     const int sz = S.sizes[sy];
     const u16 val = (u16)((sz << 8) | sy);
-    const int idx0 = (int)(S.codes[sy] << (HF_MAXLEN - sz));
+    const int idx0 = (int)S.codes[sy];
     const int cnt = 1 << (HF_MAXLEN - sz);
     for (int k = 0; k < cnt; k++) if (idx0 + k < (1 << HF_MAXLEN)) S.table[idx0 + k] = val;
   }

@@ -441,7 +441,9 @@ __global__ void __launch_bounds__(32) sbrt_fwd_rank_kernel(KzgBlock* __restrict_
 // shuffle-ups move the entries in between); ranks 32-255 stay in shared memory and are touched only when a deep rank is hit.
 template <int MODE>
 __global__ void __launch_bounds__(32) sbrt_inv_kernel(KzgBlock* __restrict__ blocks, KzgXfParams P) {
-  __shared__ u64 KR[256 + 32];
+  // list entry = {q, last occurrence + 256 (255 - symbol while never seen), symbol}.  A hit entry gets the newest occurrence, so a
+  // tie in q always goes to it: "key > new key" is a comparison of the q fields alone.
+  __shared__ u32 KQ[256 + 32], KT[256 + 32];
   __shared__ u8 r2s[256 + 32];
   const int lane = threadIdx.x, b = blockIdx.x;
   KzgBlock& B = blocks[b];
@@ -453,9 +455,9 @@ __global__ void __launch_bounds__(32) sbrt_inv_kernel(KzgBlock* __restrict__ blo
   u8* __restrict__ dst = B.alt;
   if (count > min(kzg_dst_limit(B, P.dstLimit[b]), B.cap)) return;
   constexpr int m1 = (MODE == 3) ? 0 : -1, m2 = (MODE == 1) ? 0 : -1, s = (MODE == 2) ? 1 : 0;      // (compile-time: the step is instruction bound)
-  for (int i = lane; i < 256; i += 32) { KR[i] = (u64)(255 - i); r2s[i] = (u8)i; }
+  for (int i = lane; i < 256; i += 32) { KQ[i] = 0; KT[i] = (u32)(255 - i); r2s[i] = (u8)i; }
   __syncwarp();
-  u64 kk = (u64)(255 - lane);           // rank `lane`: key and symbol
+  u32 kq = 0, kt = (u32)(255 - lane);   // rank `lane`
   int sy = lane;
   for (int base = 0; base < count; base += 32) {
     const int nIn = min(32, count - base);
@@ -467,47 +469,46 @@ __global__ void __launch_bounds__(32) sbrt_inv_kernel(KzgBlock* __restrict__ blo
       const int r = __shfl_sync(0xFFFFFFFFu, mine, t);
       if (!((deep >> t) & 1u)) {
         const int c = __shfl_sync(0xFFFFFFFFu, sy, r);
-        const u32 low = __shfl_sync(0xFFFFFFFFu, (u32)kk, r) & 0x7FFFFFFFu;
-        const u64 upK = __shfl_up_sync(0xFFFFFFFFu, kk, 1);
+        const u32 low = __shfl_sync(0xFFFFFFFFu, kt, r);
+        const u32 upQ = __shfl_up_sync(0xFFFFFFFFu, kq, 1), upT = __shfl_up_sync(0xFFFFFFFFu, kt, 1);
         const int upS = __shfl_up_sync(0xFFFFFFFFu, sy, 1);
         if (lane == t) outv = c;
         const int pOld = (low >= 256u) ? (int)(low - 256u) : 0;
-        const int qc = ((i & m1) + (pOld & m2)) >> s;
-        const u64 nk = ((u64)(u32)qc << 31) | (u64)(u32)(i + 256);
-        // entries 0..r-1: those with key > nk keep their place (keys descend with the rank), the rest move down one slot
-        const int rn = __popc(__ballot_sync(0xFFFFFFFFu, (lane < r) && (kk > nk)));
-        if (lane > rn && lane <= r) { kk = upK; sy = upS; }
-        else if (lane == rn) { kk = nk; sy = c; }
+        const u32 qc = (u32)(((i & m1) + (pOld & m2)) >> s);
+        // entries 0..r-1: those with a greater q keep their place (q descends with the rank), the rest move down one slot
+        const int rn = __popc(__ballot_sync(0xFFFFFFFFu, (lane < r) && (kq > qc)));
+        const bool mv = (lane > rn) && (lane <= r), at = (lane == rn);      // (selects, not branches: the lanes must not diverge here)
+        kq = mv ? upQ : (at ? qc : kq);
+        kt = mv ? upT : (at ? (u32)(i + 256) : kt);
+        sy = mv ? upS : (at ? c : sy);
       } else {
         // deep rank: through the shared-memory list (the registers are its first 32 entries)
-        KR[lane] = kk; r2s[lane] = (u8)sy;
+        KQ[lane] = kq; KT[lane] = kt; r2s[lane] = (u8)sy;
         __syncwarp();
         const int c = r2s[r];
-        const u64 kc = KR[r];
+        const u32 low = KT[r];
         if (lane == t) outv = c;
-        const u32 low = (u32)(kc & 0x7FFFFFFFull);
         const int pOld = (low >= 256u) ? (int)(low - 256u) : 0;
-        const int qc = ((i & m1) + (pOld & m2)) >> s;
-        const u64 nk = ((u64)(u32)qc << 31) | (u64)(u32)(i + 256);
+        const u32 qc = (u32)(((i & m1) + (pOld & m2)) >> s);
         int rn = 0;
-        for (int lo = 0; lo < r; lo += 32) {                  // keys descend with the rank: count the ones above nk
+        for (int lo = 0; lo < r; lo += 32) {                  // q descends with the rank: count the entries above the new key
           const int k = lo + lane;
-          const u32 m = __ballot_sync(0xFFFFFFFFu, (k < r) && (KR[k] > nk));
+          const u32 m = __ballot_sync(0xFFFFFFFFu, (k < r) && (KQ[k] > qc));
           rn += __popc(m);
           if (m != 0xFFFFFFFFu) break;
         }
         for (int top = r - 1; top >= rn; top -= 32) {         // entries [rn, r) move down one slot, highest chunk first
           const int k = top - lane;
           const bool on = k >= rn;
-          u64 k2 = 0; int s2 = 0;
-          if (on) { k2 = KR[k]; s2 = r2s[k]; }
+          u32 q2 = 0, t2 = 0; int s2 = 0;
+          if (on) { q2 = KQ[k]; t2 = KT[k]; s2 = r2s[k]; }
           __syncwarp();
-          if (on) { KR[k + 1] = k2; r2s[k + 1] = (u8)s2; }
+          if (on) { KQ[k + 1] = q2; KT[k + 1] = t2; r2s[k + 1] = (u8)s2; }
           __syncwarp();
         }
-        if (lane == 0) { KR[rn] = nk; r2s[rn] = (u8)c; }
+        if (lane == 0) { KQ[rn] = qc; KT[rn] = (u32)(i + 256); r2s[rn] = (u8)c; }
         __syncwarp();
-        kk = KR[lane]; sy = r2s[lane];
+        kq = KQ[lane]; kt = KT[lane]; sy = r2s[lane];
       }
     }
     if (lane < nIn) dst[base + lane] = (u8)outv;
