@@ -441,11 +441,13 @@ __global__ void __launch_bounds__(32) rolz_replay_kernel(KzgBlock* __restrict__ 
         // register the literal positions with the encoder's skip pattern (:889-900): the t-th registered literal is
         // j_t = t + sum_{u<t} (u >> 6).  Positions with different keys touch different ring rows, so 32 of them go at once:
         // lanes with the same key (match_any) take consecutive ring slots in lane order, the last 16 of a group survive.
-        for (int t0 = 0; ; t0 += 32) {
+        // number of registered literals: the largest n with j_{n-1} < litLen (j_t = t for t < 64, the common case)
+        int nReg = litLen;
+        if (litLen > 64) { nReg = 64; while (true) { const int k6 = nReg >> 6; if (nReg + 32 * k6 * (k6 - 1) + k6 * (nReg & 63) >= litLen) break; nReg++; } }
+        for (int t0 = 0; t0 < nReg; t0 += 32) {
           const int t = t0 + lane, k6 = t >> 6;
-          const int j = t + 32 * k6 * (k6 - 1) + k6 * (t & 63);
-          const bool on = j < litLen;
-          if (!__any_sync(0xFFFFFFFFu, on)) break;
+          const int j = (k6 == 0) ? t : (t + 32 * k6 * (k6 - 1) + k6 * (t & 63));
+          const bool on = t < nReg;
           const int key = on ? ((mm == 3) ? rz_key1(dst, dstIdx + j - dt) : rz_key2(dst, dstIdx + j - dt)) : (0x10000 + lane);
           const u32 peers = __match_any_sync(0xFFFFFFFFu, key);
           if (on) {
@@ -476,7 +478,8 @@ __global__ void __launch_bounds__(32) rolz_replay_kernel(KzgBlock* __restrict__ 
         if (ref != 0 || dstIdx == 0) { fail = true; break; }
       }
       const int dist = dstIdx - ref;
-      for (int i = lane; i < ml; i += 32) dst[dstIdx + i] = dst[ref + (i % dist)];     // emitCopy (:162-179): forward byte copy
+      if (ml <= dist) { for (int i = lane; i < ml; i += 32) dst[dstIdx + i] = dst[ref + i]; }      // emitCopy (:162-179): forward byte copy
+      else { for (int i = lane; i < ml; i += 32) dst[dstIdx + i] = dst[ref + (i % dist)]; }            // (overlapping: the pattern of `dist` bytes repeats)
       __syncwarp();
       if (lane == 0) { const int c = (cnt + 1) & 15; counters[key] = c; matches[base + c] = dstIdx; }
       __syncwarp();
