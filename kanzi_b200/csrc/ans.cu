@@ -136,10 +136,9 @@ __device__ __forceinline__ u32 ans_enc_step(u32 st, u32 a, u32 b) {
 // order 0 encode: grid (ceil(maxChunks/32), nBlocks), 128 threads; group of 4 lanes = one chunk
 // ================================================================================================================
 #define A0_GROUPS 32
-struct A0EncSmem {
-  u32 freq[A0_GROUPS][256];
-  u32 symA[A0_GROUPS][256];
-  u32 symB[A0_GROUPS][256];
+struct A0EncSmem {          // rows padded by one entry: the eight chunks of a warp look up the same symbols, which must not share a bank
+  u32 freq[A0_GROUPS][257];
+  uint2 sym[A0_GROUPS][257];   // {invFreq, packed} (ans_symbol_reset); .x holds the cumulative frequency until the reset
   u8 alpha[A0_GROUPS][256];
 };
 
@@ -174,14 +173,28 @@ __global__ void __launch_bounds__(128) ans0_encode_kernel(const KzgBlock* __rest
     segs[1] = KzgSeg{nullptr, 0, 0, 0};
   }
 
+#ifdef KZG_A1_TIMING
+  long long tq0 = clock64(), tq1, tq2, tq3;
+#endif
   // ---- histogram (Global.computeHistogramOrder0 :274-330) ----
   for (int k = j; k < 256; k += 4) S.freq[g][k] = 0;
   __syncwarp();
   if (active) {
-    for (int i = start + j; i < end; i += 4) atomicAdd(&S.freq[g][data[i]], 1u);
+    int i = start + j;
+    for (; i + 28 < end; i += 32) {          // eight loads in flight per lane (a byte load that waits for the atomic before it costs an L1 round trip each)
+      u8 v[8];
+      #pragma unroll
+      for (int k = 0; k < 8; k++) v[k] = data[i + 4 * k];
+      #pragma unroll
+      for (int k = 0; k < 8; k++) atomicAdd(&S.freq[g][v[k]], 1u);
+    }
+    for (; i < end; i += 4) atomicAdd(&S.freq[g][data[i]], 1u);
   }
   __syncwarp();
 
+#ifdef KZG_A1_TIMING
+  tq1 = clock64();
+#endif
   // ---- statistics + header (rebuildStatistics :419-449, updateFrequencies :171-200), lane 0 of the group ----
   int alphabetSize = 0;
   i64 hdrBits = 0;
@@ -189,15 +202,8 @@ __global__ void __launch_bounds__(128) ans0_encode_kernel(const KzgBlock* __rest
     BitWriterD bw(hdr);
     bw.write((u32)(lr - 8), 3);
     alphabetSize = ans_normalize(S.freq[g], S.alpha[g], end - start, 1 << lr);
-    if (alphabetSize > 0) {
-      int sum = 0;
-      for (int k = 0; k < alphabetSize; k++) {
-        const int s = S.alpha[g][k];
-        const int f = (int)S.freq[g][s];
-        ans_symbol_reset(S.symA[g][s], S.symB[g][s], sum, f, lr);
-        sum += f;
-      }
-    }
+    int sum = 0;
+    for (int k = 0; k < alphabetSize; k++) { const int sy = S.alpha[g][k]; S.sym[g][sy].x = (u32)sum; sum += (int)S.freq[g][sy]; }
     ans_encode_header(bw, alphabetSize, S.alpha[g], S.freq[g], lr);
     if (alphabetSize <= 1) {     // chunk skipped after its header (:296-299)
       bw.flush();
@@ -211,7 +217,20 @@ __global__ void __launch_bounds__(128) ans0_encode_kernel(const KzgBlock* __rest
   alphabetSize = __shfl_sync(0xFFFFFFFFu, alphabetSize, (threadIdx.x & 31) & ~3);
   __syncwarp();
   const bool coding = active && (alphabetSize > 1);
+  // Symbol.reset (:473-496) for every symbol of the alphabet: a 64-bit division each, shared by the group's four lanes
+  if (coding) {
+    for (int k = j; k < alphabetSize; k += 4) {
+      const int sy = S.alpha[g][k];
+      u32 sa, sb;
+      ans_symbol_reset(sa, sb, (int)S.sym[g][sy].x, (int)S.freq[g][sy], lr);
+      S.sym[g][sy] = make_uint2(sa, sb);
+    }
+  }
+  __syncwarp();
 
+#ifdef KZG_A1_TIMING
+  tq2 = clock64();
+#endif
   // ---- encodeChunk (:337-407): backwards, 4 interleaved states ----
   const int end4 = start + ((end - start) & -4);
   int n = bufLen - 1;
@@ -227,29 +246,43 @@ __global__ void __launch_bounds__(128) ans0_encode_kernel(const KzgBlock* __rest
   int idx = n;
   const int gshift = (threadIdx.x & 31) & ~3;
   const u32 lowerMask = (1u << j) - 1;
-  for (int s = 0; s < maxSteps; s++) {
-    const bool on = s < steps;
-    u32 a = 0, bb = 0;
-    bool x = false;
-    if (on) {
-      const int i = end4 - 1 - 4 * s;
-      const int sym = data[i - j];
-      a = S.symA[g][sym]; bb = S.symB[g][sym];
-      const u32 xMax = ((u32)(1 << lr) - ((bb >> 14) & 0x3FFF)) << (31 - lr);
-      x = (st >= xMax);
-    }
-    const u32 m = (__ballot_sync(0xFFFFFFFFu, x) >> gshift) & 0xFu;
-    if (on) {
-      if (x) {
-        const int pos = idx - 2 * __popc(m & lowerMask);
-        pay[pos] = (u8)st;
-        pay[pos - 1] = (u8)(st >> 8);
-        st >>= 16;
+  for (int s0 = 0; s0 < maxSteps; s0 += 8) {
+    // the symbols of eight steps are requested together: they do not depend on the state, and a lone load per step would put an L1
+    // round trip on every step of the chain
+    int syms[8];
+    #pragma unroll
+    for (int k = 0; k < 8; k++) syms[k] = (s0 + k < steps) ? (int)data[end4 - 1 - 4 * (s0 + k) - j] : 0;
+    #pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int s = s0 + k;
+      if (s >= maxSteps) break;
+      const bool on = s < steps;
+      u32 a = 0, bb = 0;
+      bool x = false;
+      if (on) {
+        const int sym = syms[k];
+        const uint2 e = S.sym[g][sym];
+        a = e.x; bb = e.y;
+        const u32 xMax = ((u32)(1 << lr) - ((bb >> 14) & 0x3FFF)) << (31 - lr);
+        x = (st >= xMax);
       }
-      idx -= 2 * __popc(m);
-      st = ans_enc_step(st, a, bb);
+      const u32 m = (__ballot_sync(0xFFFFFFFFu, x) >> gshift) & 0xFu;
+      if (on) {
+        if (x) {
+          const int pos = idx - 2 * __popc(m & lowerMask);
+          pay[pos] = (u8)st;
+          pay[pos - 1] = (u8)(st >> 8);
+          st >>= 16;
+        }
+        idx -= 2 * __popc(m);
+        st = ans_enc_step(st, a, bb);
+      }
     }
   }
+#ifdef KZG_A1_TIMING
+  tq3 = clock64();
+  if (b == 3 && blockIdx.x == 0 && threadIdx.x == 0) printf("ans0 enc warp: hist %lld stats %lld code %lld cycles (%d steps)\n", tq1 - tq0, tq2 - tq1, tq3 - tq2, maxSteps);
+#endif
   // gather the four final states in lane 0 of the group
   const u32 s1 = __shfl_sync(0xFFFFFFFFu, st, gshift + 1);
   const u32 s2 = __shfl_sync(0xFFFFFFFFu, st, gshift + 2);
