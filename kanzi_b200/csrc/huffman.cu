@@ -26,17 +26,6 @@ __device__ __forceinline__ void hf_expgolomb(BitWriterD& bw, int val) {
   const u32 tail = ((u32)(a + 1 - (1 << lg)) << 1) | (u32)(val < 0);
   bw.write((1u << (lg + 1)) | tail, 2 * lg + 2);
 }
-// K/entropy/ExpGolombDecoder.java:41-60
-__device__ __forceinline__ int hf_expgolomb_dec(BitReaderD& br) {
-  if (br.read(1) == 1) return 0;
-  int lg = 1;
-  while (br.read(1) == 0) { lg++; if (lg > 30 || br.overrun()) return 127; }
-  i64 res = (i64)br.read(lg + 1);
-  const i64 sgn = res & 1;
-  res = (res >> 1) + (1 << lg) - 1;
-  return (int)(int8_t)((res - sgn) ^ -sgn);
-}
-
 // HuffmanEncoder.computeInPlaceSizesPhase1/2 (:317-376)
 __device__ void hf_phase1(int* data, int n) {
   for (int s = 0, r = 0, t = 0; t < n - 1; t++) {
@@ -438,15 +427,26 @@ __global__ void __launch_bounds__(HFE_THREADS) huff_encode_kernel(const KzgBlock
 // ================================================================================================================
 // decode
 // ================================================================================================================
-// chunk scan: one thread per block (HuffmanDecoder.decodeV6 :353-390 walks chunks the same way)
-__global__ void huff_scan_kernel(KzgBlock* __restrict__ blocks, int nBlocks, KzgEntParams P) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nBlocks) return;
+// chunk scan: one warp per block, lane 0 walks the chunk headers (HuffmanDecoder.decodeV6 :353-390 walks chunks the same way; a
+// chunk starts where the one before it ends, and only its header says where that is).  The walk is instruction bound (a lone warp),
+// so the code lengths are skipped out of a 32-bit register window: a signed Exp-Golomb code is `1`, or z zeros, `1`, z + 1 bits —
+// one count-leading-zeros per code instead of a bit read per bit.
+__device__ __forceinline__ u32 hf_peek32(const u8* __restrict__ stream, u64 pos, u64 end) {      // the next 32 bits, zeros beyond `end`
+  if (pos + 32 <= end) return get_bits(stream, pos, 32);
+  if (pos >= end) return 0u;
+  const int rem = (int)(end - pos);
+  return get_bits(stream, pos, rem) << (32 - rem);
+}
+__global__ void __launch_bounds__(32) huff_scan_kernel(KzgBlock* __restrict__ blocks, int nBlocks, KzgEntParams P) {
+  const int b = blockIdx.x;
+  if (b >= nBlocks || threadIdx.x != 0) return;
   KzgBlock& B = blocks[b];
   if (B.status != 0 || B.entropy != P.entropy) return;
   const int len = B.preLen;
   KzgChunkInfo* ci = P.chunks + (i64)b * P.maxChunks;
-  BitReaderD br(P.stream, (u64)B.srcBit, (u64)(B.srcBit + B.srcBits));
+  const u8* __restrict__ stream = P.stream;
+  const u64 end = (u64)(B.srcBit + B.srcBits);
+  BitReaderD br(stream, (u64)B.srcBit, end);
   const int nChunks = (len + HF_CHUNK - 1) / HF_CHUNK;
   for (int c = 0; c < nChunks; c++) {
     const int count = min(HF_CHUNK, len - c * HF_CHUNK);
@@ -458,14 +458,21 @@ __global__ void huff_scan_kernel(KzgBlock* __restrict__ blocks, int nBlocks, Kzg
     } else {
       int n = 0;
       if (br.read(1) == 0) n = (br.read(1) == 1) ? 0 : 256;
-      else { const int lastMask = (int)br.read(5); for (int i = 0; i <= lastMask; i++) n += __popc(br.read(8)); }
-      if (n == 0) { B.status = -KZG_ERR_PROCESS_BLOCK; return; }      // readLengths() <= 0 -> decode returns early
-      for (int i = 0; i < n; i++) {
-        if (br.read(1) == 1) continue;
-        int lg = 1;
-        while (br.read(1) == 0) { lg++; if (br.overrun() || lg > 30) { B.status = -KZG_ERR_PROCESS_BLOCK; return; } }
-        br.pos += (u64)(lg + 1);
+      else {
+        const int nb = (int)br.read(5) + 1;                     // mask bytes
+        for (int i = 0; i < nb; i += 4) { const int k = min(4, nb - i); n += __popc(br.read(8 * k)); }
       }
+      if (n == 0) { B.status = -KZG_ERR_PROCESS_BLOCK; return; }      // readLengths() <= 0 -> decode returns early
+      u64 pos = br.pos;
+      u32 w = 0; int avail = 0;
+      for (int i = 0; i < n; i++) {
+        if (avail < 24) { w = hf_peek32(stream, pos, end); avail = 32; }
+        const int z = __clz(w);
+        if (z > 10) { B.status = -KZG_ERR_PROCESS_BLOCK; return; }    // (a length delta never needs more; all-zero = past the end)
+        const int cl = z ? 2 * z + 2 : 1;
+        pos += (u64)cl; w <<= cl; avail -= cl;
+      }
+      br.pos = pos;
       info.alphabetSize = n;
       if (n > 1) {
         u64 total = 0;
@@ -535,12 +542,30 @@ __global__ void __launch_bounds__(HFD_THREADS) huff_decode_kernel(KzgBlock* __re
       }
     }
     int curSize = 2;
-    for (int i = 0; i < nsym; i++) {
-      const int sy = alphabet[i];
-      curSize += hf_expgolomb_dec(br);
-      if ((curSize <= 0) || (curSize > HF_MAXLEN)) { bad = 1; break; }
-      S.sizes[sy] = (u8)curSize;
-      S.present[sy] = 1;
+    {   // ExpGolombDecoder.decodeByte (:41-60) out of a 32-bit register window (see huff_scan_kernel)
+      const u64 end = (u64)(B.srcBit + B.srcBits);
+      u64 pos = br.pos;
+      u32 w = 0; int avail = 0;
+      for (int i = 0; i < nsym; i++) {
+        const int sy = alphabet[i];
+        if (avail < 24) { w = hf_peek32(stream, pos, end); avail = 32; }
+        const int z = __clz(w);
+        if (z > 10) { bad = 1; break; }
+        int delta = 0, cl = 1;
+        if (z) {
+          cl = 2 * z + 2;
+          i64 res = (i64)((w >> (32 - cl)) & ((2u << z) - 1));       // the z + 1 bits behind the `1`
+          const i64 sgn = res & 1;
+          res = (res >> 1) + (1 << z) - 1;
+          delta = (int)(int8_t)((res - sgn) ^ -sgn);
+        }
+        pos += (u64)cl; w <<= cl; avail -= cl;
+        curSize += delta;
+        if ((curSize <= 0) || (curSize > HF_MAXLEN)) { bad = 1; break; }
+        S.sizes[sy] = (u8)curSize;
+        S.present[sy] = 1;
+      }
+      if (pos > end) bad = 1;
     }
     S.nsym = nsym; S.bad = bad;
   } else if (tid >= 32 && info.alphabetSize > 1) {
@@ -621,7 +646,7 @@ int kzg_huff_encode_launch(cudaStream_t s, const KzgBlock* d_blocks, int nBlocks
 }
 
 int kzg_huff_decode_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, const KzgEntParams& P) {
-  KZG_PROF("huff_scan_kernel", s, (huff_scan_kernel<<<(nBlocks + 31) / 32, 32, 0, s>>>(d_blocks, nBlocks, P)));
+  KZG_PROF("huff_scan_kernel", s, (huff_scan_kernel<<<nBlocks, 32, 0, s>>>(d_blocks, nBlocks, P)));
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaFuncSetAttribute(huff_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HfDecSmem)));
   dim3 grid(P.maxChunks, nBlocks);

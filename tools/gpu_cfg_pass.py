@@ -1,6 +1,6 @@
 """Developer aid: encode + decode passes of one BASELINE config over `nbytes` of its synthetic workload, device-resident, with host
 wall-clock and CUDA-event times per call (run it under `ncu --metrics gpu__time_duration.sum` for the per-kernel launch list).
-Usage: python tools/gpu_cfg_pass.py cfg3 16777216 [reps] [--fixed]"""
+Usage: python tools/gpu_cfg_pass.py cfg3 16777216 [reps] [--fixed] [--chain LZX HUFFMAN 4194304]"""
 import sys, os, time, ctypes as C
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -13,6 +13,9 @@ gen, full, transforms, entropy, bs = synth.CONFIGS[cfg]
 n = int(sys.argv[2]) if len(sys.argv) > 2 else min(full, 4 * bs)
 reps = int(sys.argv[3]) if len(sys.argv) > 3 and not sys.argv[3].startswith("--") else 2
 flags = 0 if "--fixed" in sys.argv else 1
+if "--chain" in sys.argv:          # --chain LZX HUFFMAN 4194304: the config's data under another chain / block size
+    k = sys.argv.index("--chain")
+    transforms, entropy, bs = sys.argv[k + 1].split("+"), sys.argv[k + 2], int(sys.argv[k + 3])
 seed = {"cfg1": 1, "cfg2": 2, "cfg3": 3, "cfg4": 4, "cfg5": 5}[cfg]
 K.set_device(0)
 L = K.lib()
