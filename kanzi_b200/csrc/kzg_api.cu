@@ -1092,11 +1092,17 @@ static int64_t decompress_impl(const uint8_t* d_in, int64_t nBytes, const uint8_
     if (timing3) CUDA_TRY(cudaEventRecord(ev[0], W.stream));
     if (G > 1) CUDA_TRY(cudaEventRecord(W.sideEv[KZG_DEC_MAXG], W.stream));
     int rc = 0;
+    // Two passes over the groups.  The BWT launcher reads block headers back (a host wait for everything its stream holds): run in
+    // the first pass it would stop the host from enqueueing the next group until this group's earlier stages are done, and the
+    // groups would run one after the other.  Pass 0 enqueues every group up to its first such stage; pass 1 the rest, by which time
+    // all groups are running.
+    int resume[KZG_DEC_MAXG];                     // per group: the stage pass 1 resumes at (-1: nothing left)
+    for (int pass = 0; pass < 2 && rc == 0; pass++) {
     for (int g = 0; g < G && rc == 0; g++) {
       const int b0 = (int)((i64)sN * g / G), b1 = (int)((i64)sN * (g + 1) / G), cnt = b1 - b0;
       cudaStream_t q = (G > 1) ? W.side[g] : mainStream;
-      if (G > 1) CUDA_TRY(cudaStreamWaitEvent(q, W.sideEv[KZG_DEC_MAXG], 0));
-      if (copyIn) {                               // the bytes that hold this group's block records (+ the slack the bit readers touch)
+      if (pass == 0 && G > 1) CUDA_TRY(cudaStreamWaitEvent(q, W.sideEv[KZG_DEC_MAXG], 0));
+      if (pass == 0 && copyIn) {                  // the bytes that hold this group's block records (+ the slack the bit readers touch)
         const i64 lo = (recs[s0 + b0].payBit >> 3) & ~(i64)63;
         const i64 hi = std::min<i64>(nBytes, ((recs[s0 + b1 - 1].payBit + recs[s0 + b1 - 1].payBits + 7) >> 3) + 128);
         if (hi > lo) CUDA_TRY(cudaMemcpyAsync((u8*)d_in + lo, h_in + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, q));
@@ -1105,29 +1111,35 @@ static int64_t decompress_impl(const uint8_t* d_in, int64_t nBytes, const uint8_
       sub.nBlocks = cnt; sub.hBlocks = bt.hBlocks + b0; sub.dBlocks = bt.dBlocks + b0; sub.dResult = bt.dResult + 2 * b0; sub.dDstLimit = bt.dDstLimit + b0;
       W.stream = q;                               // (the launch helpers enqueue on the calling thread's current stream)
       do {
-        if (anyEnt) { rc = run_entropy_decode(sub, entropy, es, d_in, dChunks + (size_t)b0 * es.maxChunks, dTab + (size_t)b0 * es.maxChunks * es.tabStride); if (rc < 0) break; }
-        if (anyNone) { rc = run_entropy_decode(sub, KZG_E_NONE, es, d_in, dChunks + (size_t)b0 * es.maxChunks, dTab + (size_t)b0 * es.maxChunks * es.tabStride); if (rc < 0) break; }
-        if (timing3 && g == 0) { if (cudaEventRecord(ev[1], q) != cudaSuccess) { rc = -KZG_ERR_PROCESS_BLOCK; break; } }
-        for (int i = nf - 1; i >= 0; i--) {
+        int first = nf - 1;
+        if (pass == 0) {
+          if (anyEnt) { rc = run_entropy_decode(sub, entropy, es, d_in, dChunks + (size_t)b0 * es.maxChunks, dTab + (size_t)b0 * es.maxChunks * es.tabStride); if (rc < 0) break; }
+          if (anyNone) { rc = run_entropy_decode(sub, KZG_E_NONE, es, d_in, dChunks + (size_t)b0 * es.maxChunks, dTab + (size_t)b0 * es.maxChunks * es.tabStride); if (rc < 0) break; }
+          if (timing3 && g == 0) { if (cudaEventRecord(ev[1], q) != cudaSuccess) { rc = -KZG_ERR_PROCESS_BLOCK; break; } }
+          resume[g] = -1;
+        } else first = resume[g];
+        for (int i = first; i >= 0; i--) {
           if (fn[i] == KZG_T_NONE) continue;
-          // a stage no block of this group runs (skip flags; BWT under the reference's bounds) is not launched at all: some launchers
-          // read block headers back and would make the host wait for the whole group, serialising the groups
+          // a stage no block of this group runs (skip flags; BWT under the reference's bounds) is not launched at all
           bool anyOn = false;
           for (int b = b0; b < b1 && !anyOn; b++) anyOn = bt.hEnabled[(size_t)i * nb + b] != 0;
           if (!anyOn) continue;
+          if (pass == 0 && fn[i] == KZG_T_BWT && G > 1) { resume[g] = i; break; }
           sub.dEnabled = dEnabledAll + (size_t)i * nb + b0;
           rc = run_transform_stage(sub, fn[i], i, false, xs, dScratch + (size_t)b0 * xs.perBlock, dHash + (size_t)b0 * xs.hashInts, dAux + (size_t)b0 * xs.aux32, flags);
           if (rc < 0) break;
         }
-        if (rc >= 0 && chkBytes) rc = kzg_xxh_launch(q, sub.dBlocks, cnt, 1);       // verify the decoded bytes (CIS:1348-1370)
+        if (rc >= 0 && pass == 1 && chkBytes) rc = kzg_xxh_launch(q, sub.dBlocks, cnt, 1);       // verify the decoded bytes (CIS:1348-1370)
       } while (0);
       W.stream = mainStream;
       if (rc < 0) break;
+      if (pass == 0) continue;
       if (h_out) {                                // every block but the stream's last is blockSize bytes; the last one follows below
         const int full = (s0 + b1 == nBlocks) ? cnt - 1 : cnt;
         if (full > 0) CUDA_TRY(cudaMemcpyAsync(h_out + (size_t)(s0 + b0) * blockSize, d_out + (size_t)(s0 + b0) * blockSize, (size_t)full * blockSize, cudaMemcpyDeviceToHost, q));
       }
       if (G > 1) { CUDA_TRY(cudaEventRecord(W.sideEv[g], q)); CUDA_TRY(cudaStreamWaitEvent(mainStream, W.sideEv[g], 0)); }
+    }
     }
     if (rc < 0) { W.stream = mainStream; for (int g = 0; g < G && G > 1; g++) cudaStreamSynchronize(W.side[g]); return rc; }
     if (timing3) CUDA_TRY(cudaEventRecord(ev[2], W.stream));
