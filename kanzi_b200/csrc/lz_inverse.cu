@@ -749,11 +749,23 @@ int kzg_lz_inverse_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, const
   KZG_PROF("lzi_tok_sums_kernel", s, (lzi_tok_sums_kernel<<<gT, LZI_TT, 0, s>>>(d_blocks, P, toks, tokStride, hdrs, extPool, tilePool, tileStride)));
   KZG_PROF("lzi_tok_scan1_kernel", s, (lzi_tok_scan1_kernel<<<nBlocks, LZI_TT, 0, s>>>(d_blocks, P, toks, tokStride, hdrs, extPool, tilePool, tileStride)));
   KZG_PROF("lzi_tok_extk_kernel", s, (lzi_tok_extk_kernel<<<gT, LZI_TT, 0, s>>>(d_blocks, P, toks, tokStride, hdrs, extPool, tilePool, tileStride)));
-  // (The chase is one dependent chain per block on one warp: 4.5 ms alone for cfg2's longest block, 7.8 ms when the other block
-  // groups' kernels run next to it.  Asking for 200 KiB of shared memory to keep other CTAs off its SM changed nothing (round 2):
-  // what slows it is the window staging's global loads queueing behind the other groups' traffic, not issue slots.)
-  const int chaseSmem = (int)sizeof(LziChaseSmem);
+  // The chase is one dependent chain per block on one warp: 4.5 ms alone for cfg2's longest block, but up to 7.8 ms while the other
+  // block groups' throughput kernels (span, resolve, global: CTAs on every SM) share its SM — the chain thread's own loop slows from 54
+  // to 97 cycles per record, because it has to share its scheduler's issue slots.  The CTA therefore asks for ALL of the SM's shared
+  // memory (every CTA needs at least its 1 KiB system slice, so nothing else can become resident next to it): the chains get an SM to
+  // themselves, the throughput kernels the other SMs.  (200 KiB was not enough — small-footprint kernels still fitted — and 32 KiB
+  // windows or a barrier between all groups' chains and the rest of the stage were slower.)
+  int chaseSmem = (int)sizeof(LziChaseSmem);
+  {
+    int dev = 0, optin = 0;
+    cudaFuncAttributes fa;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess &&
+        cudaFuncGetAttributes(&fa, lzi_tok_chase_kernel) == cudaSuccess && optin - (int)fa.sharedSizeBytes > chaseSmem && !getenv("KZG_LZI_SHARE_SM"))
+      chaseSmem = optin - (int)fa.sharedSizeBytes;
+    else cudaGetLastError();
+  }
   CUDA_TRY(cudaFuncSetAttribute(lzi_tok_chase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, chaseSmem));
+  CUDA_TRY(cudaFuncSetAttribute(lzi_tok_chase_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   KZG_PROF("lzi_tok_chase_kernel", s, (lzi_tok_chase_kernel<<<nBlocks, LZI_TT, chaseSmem, s>>>(d_blocks, P, toks, tokStride, hdrs, extPool, tilePool, tileStride)));
   KZG_PROF("lzi_tok_span_kernel", s, (lzi_tok_span_kernel<<<gT, LZI_TT, 0, s>>>(d_blocks, P, toks, tokStride, hdrs, extPool, tilePool, tileStride)));
   KZG_PROF("lzi_tok_scan2_kernel", s, (lzi_tok_scan2_kernel<<<nBlocks, LZI_TT, 0, s>>>(d_blocks, P, toks, tokStride, hdrs, extPool, tilePool, tileStride)));
