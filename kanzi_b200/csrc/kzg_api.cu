@@ -35,6 +35,7 @@ struct Workspace {
   i64 launches = 0;
   char err[512] = {0};
   cudaStream_t side[KZG_DEC_MAXG] = {}; cudaEvent_t sideEv[KZG_DEC_MAXG + 1] = {}; bool sideInit = false;
+  bool lziExclusive = false;       // decode batch with no more blocks than SMs: the LZ inverse's record-chain CTAs take an SM each (lz_inverse.cu)
   std::vector<i64> lastRecBits;    // record bit lengths (5 + lw + written) of the blocks of this thread's last kzg_compress* call
 };
 static thread_local Workspace W;
@@ -237,6 +238,7 @@ static int run_transform_stage(Batch& bt, int type, int stage, bool forward, con
       else {
         static const char* dbgEnvI = getenv("KZG_DEBUG");         // developer aid: bit 0 per-block statistics of the token chase
         if (dbgEnvI) P.flags |= (atoi(dbgEnvI) << 12);
+        if (W.lziExclusive) P.flags |= KZG_XF_LZI_EXCLUSIVE;
         r = kzg_lz_inverse_launch(W.stream, bt.dBlocks, bt.nBlocks, P, bt.maxLen);
       }
       break;
@@ -1087,6 +1089,11 @@ static int64_t decompress_impl(const uint8_t* d_in, int64_t nBytes, const uint8_
     // Blocks are independent: contiguous groups of them run the whole decode on streams of their own (most urgent first), so
     // that the latency-bound kernels of one group (chunk scan, the literal-record chain) overlap the streaming kernels of the
     // others and, for host buffers, a group's upload / download overlaps the other groups' kernels.
+    {
+      int nSM = 0;
+      if (cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, W.device) != cudaSuccess) { cudaGetLastError(); nSM = 0; }
+      W.lziExclusive = sN <= nSM;      // (more chains than SMs: exclusive SMs would only make them queue; measured 4 % slower at 400 blocks)
+    }
     const int G = (sN >= 8 && (i64)sN * blockSize >= (16 << 20)) ? std::min(gDec, sN / 2) : 1;      // (small batches: one launch chain, the groups would only add launches)
     if (G > 1) { r = ws_side_init(); if (r < 0) return r; }
     if (timing3) CUDA_TRY(cudaEventRecord(ev[0], W.stream));

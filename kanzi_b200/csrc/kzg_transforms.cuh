@@ -5,6 +5,7 @@
 
 #define LZF_SAMPLES 8       // samples per block the LZ forward orders its blocks by: the first LZF_SAMPLE bytes of every eighth
 #define LZF_SAMPLE 4096
+#define KZG_XF_LZI_EXCLUSIVE (1 << 24)   // KzgXfParams.flags: LZ inverse, see lzi_tok_chase_kernel's launch
 
 struct KzgXfParams {
   int* result;            // [2 * nBlocks]: {boolean result of forward()/inverse(), bytes produced}

@@ -753,14 +753,14 @@ int kzg_lz_inverse_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, const
   // block groups' throughput kernels (span, resolve, global: CTAs on every SM) share its SM — the chain thread's own loop slows from 54
   // to 97 cycles per record, because it has to share its scheduler's issue slots.  The CTA therefore asks for ALL of the SM's shared
   // memory (every CTA needs at least its 1 KiB system slice, so nothing else can become resident next to it): the chains get an SM to
-  // themselves, the throughput kernels the other SMs.  (200 KiB was not enough — small-footprint kernels still fitted — and 32 KiB
+  // themselves, the throughput kernels the other SMs (only when the batch has no more blocks than the GPU has SMs: KZG_XF_LZI_EXCLUSIVE).  (200 KiB was not enough — small-footprint kernels still fitted — and 32 KiB
   // windows or a barrier between all groups' chains and the rest of the stage were slower.)
   int chaseSmem = (int)sizeof(LziChaseSmem);
   {
     int dev = 0, optin = 0;
     cudaFuncAttributes fa;
     if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess &&
-        cudaFuncGetAttributes(&fa, lzi_tok_chase_kernel) == cudaSuccess && optin - (int)fa.sharedSizeBytes > chaseSmem && !getenv("KZG_LZI_SHARE_SM"))
+        cudaFuncGetAttributes(&fa, lzi_tok_chase_kernel) == cudaSuccess && optin - (int)fa.sharedSizeBytes > chaseSmem && (P.flags & KZG_XF_LZI_EXCLUSIVE))
       chaseSmem = optin - (int)fa.sharedSizeBytes;
     else cudaGetLastError();
   }
