@@ -1092,7 +1092,10 @@ static int64_t decompress_impl(const uint8_t* d_in, int64_t nBytes, const uint8_
     {
       int nSM = 0;
       if (cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, W.device) != cudaSuccess) { cudaGetLastError(); nSM = 0; }
-      W.lziExclusive = sN <= nSM;      // (more chains than SMs: exclusive SMs would only make them queue; measured 4 % slower at 400 blocks)
+      // (more chains than SMs: exclusive SMs would only make them queue, 4 % slower at 400 blocks.  With host buffers the groups are
+      //  staggered by their uploads: a chain CTA that needs a whole SM then waits for one to drain of the other groups' entropy-decode
+      //  CTAs, and the decode as a whole was 4 % slower.)
+      W.lziExclusive = sN <= nSM && !copyIn;
     }
     const int G = (sN >= 8 && (i64)sN * blockSize >= (16 << 20)) ? std::min(gDec, sN / 2) : 1;      // (small batches: one launch chain, the groups would only add launches)
     if (G > 1) { r = ws_side_init(); if (r < 0) return r; }
