@@ -1095,7 +1095,7 @@ static int64_t decompress_impl(const uint8_t* d_in, int64_t nBytes, const uint8_
       // (more chains than SMs: exclusive SMs would only make them queue, 4 % slower at 400 blocks.  With host buffers the groups are
       //  staggered by their uploads: a chain CTA that needs a whole SM then waits for one to drain of the other groups' entropy-decode
       //  CTAs, and the decode as a whole was 4 % slower.)
-      W.lziExclusive = sN <= nSM && !copyIn;
+      W.lziExclusive = sN <= nSM && (!copyIn || getenv("KZG_LZI_EXCL_E2E") != nullptr);
     }
     const int G = (sN >= 8 && (i64)sN * blockSize >= (16 << 20)) ? std::min(gDec, sN / 2) : 1;      // (small batches: one launch chain, the groups would only add launches)
     if (G > 1) { r = ws_side_init(); if (r < 0) return r; }
@@ -1106,9 +1106,10 @@ static int64_t decompress_impl(const uint8_t* d_in, int64_t nBytes, const uint8_
     // the first pass it would stop the host from enqueueing the next group until this group's earlier stages are done, and the
     // groups would run one after the other.  Pass 0 enqueues every group up to its first such stage; pass 1 the rest, by which time
     // all groups are running.
-    int resume[KZG_DEC_MAXG];                     // per group: the stage pass 1 resumes at (-1: nothing left)
+    int resume[KZG_DEC_MAXG];                     // per group: the stage pass 1 resumes at (-1: the group was finished in pass 0)
     for (int pass = 0; pass < 2 && rc == 0; pass++) {
     for (int g = 0; g < G && rc == 0; g++) {
+      if (pass == 1 && resume[g] < 0) continue;
       const int b0 = (int)((i64)sN * g / G), b1 = (int)((i64)sN * (g + 1) / G), cnt = b1 - b0;
       cudaStream_t q = (G > 1) ? W.side[g] : mainStream;
       if (pass == 0 && G > 1) CUDA_TRY(cudaStreamWaitEvent(q, W.sideEv[KZG_DEC_MAXG], 0));
@@ -1139,11 +1140,12 @@ static int64_t decompress_impl(const uint8_t* d_in, int64_t nBytes, const uint8_
           rc = run_transform_stage(sub, fn[i], i, false, xs, dScratch + (size_t)b0 * xs.perBlock, dHash + (size_t)b0 * xs.hashInts, dAux + (size_t)b0 * xs.aux32, flags);
           if (rc < 0) break;
         }
-        if (rc >= 0 && pass == 1 && chkBytes) rc = kzg_xxh_launch(q, sub.dBlocks, cnt, 1);       // verify the decoded bytes (CIS:1348-1370)
+        // (a group with nothing left for pass 1 finishes in pass 0: its download overlaps the other groups' kernels from the start)
+        if (rc >= 0 && (pass == 1 || resume[g] < 0) && chkBytes) rc = kzg_xxh_launch(q, sub.dBlocks, cnt, 1);       // verify the decoded bytes (CIS:1348-1370)
       } while (0);
       W.stream = mainStream;
       if (rc < 0) break;
-      if (pass == 0) continue;
+      if (pass == 0 && resume[g] >= 0) continue;  // the rest of this group in pass 1
       if (h_out) {                                // every block but the stream's last is blockSize bytes; the last one follows below
         const int full = (s0 + b1 == nBlocks) ? cnt - 1 : cnt;
         if (full > 0) CUDA_TRY(cudaMemcpyAsync(h_out + (size_t)(s0 + b0) * blockSize, d_out + (size_t)(s0 + b0) * blockSize, (size_t)full * blockSize, cudaMemcpyDeviceToHost, q));
