@@ -1969,7 +1969,9 @@ int kzg_lz_forward2_launch(cudaStream_t s, KzgBlock* d_blocks, int nBlocks, cons
         groupRound[g]++;
         enqueue(g, groupRound[g]);
       }
-      if (!progressed) std::this_thread::yield();          // (rounds last milliseconds; a query costs microseconds)
+      // (rounds last milliseconds: between sweeps the thread sleeps instead of spinning through 32 driver calls — with one process per
+      //  GPU on an 8-GPU box the spinning ranks slowed each other's launches: LZ forward 32 -> 41 ms at N = 8)
+      if (!progressed) std::this_thread::sleep_for(std::chrono::microseconds(25));
     }
     // join: the groups' emit kernels still run; blocks left to the serial walker (never on the test corpora) are emitted after it
     for (int g = 0; g < G; g++) {
