@@ -1,4 +1,5 @@
-"""Build libkanzi_b200.so (nvcc, sm_100a) in-tree.  No torch dependency: a JVM loads this library."""
+"""Build libkanzi_b200.so (nvcc, sm_100a) in-tree.  No torch dependency: a JVM loads this library.
+KZG_A1_TIMING=1 in the environment compiles the clock64 phase probes of the ANS / ROLZ kernels in (developer aid: they printf per chunk)."""
 import os
 import subprocess
 import sys
