@@ -225,3 +225,71 @@ def test_srt_forward_agrees_with_the_oracle():
     for d in _cases():
         ok_ref, ref, _, _ = O.transform("SRT", d, dst_cap=len(d) + 1024)
         assert ok_ref == 1 and srt_forward(d) == ref
+
+
+# ---- FPAQ: K/entropy/FPAQEncoder.java:128-238 (64-bit Java longs: wrapping, `>>>` logical) -------------------------------------
+M64 = (1 << 64) - 1
+
+
+class _Bits:
+    def __init__(self):
+        self.v, self.n = 0, 0
+
+    def write(self, value, nbits):
+        self.v = (self.v << nbits) | (value & ((1 << nbits) - 1))
+        self.n += nbits
+
+    def varint(self, value):          # EntropyUtils.writeVarInt (K/entropy/EntropyUtils.java:259-276)
+        while value >= 128:
+            self.write(0x80 | (value & 0x7F), 8)
+            value >>= 7
+        self.write(value, 8)
+
+    def bytes(self):
+        pad = (-self.n) % 8
+        return (self.v << pad).to_bytes((self.n + pad) // 8, "big"), self.n
+
+
+def fpaq_encode(data, chunk=4 << 20):
+    TOP, M24_56, M0_24, M0_32, PSCALE = 0x00FFFFFFFFFFFFFF, 0x00FFFFFFFF000000, 0xFFFFFF, 0xFFFFFFFF, 65536
+    probs = [[PSCALE >> 1] * 256 for _ in range(4)]
+    low, high = 0, TOP
+    out = _Bits()
+    start, end = 0, len(data)
+    while start < end:
+        size = min(chunk, end - start)
+        sba = bytearray()
+        p = probs[0]
+        for i in range(start, start + size):
+            val = data[i]
+            bits = val + 256
+            for k in range(8):
+                bit = val & (0x80 >> k)
+                idx = 1 if k == 0 else bits >> (8 - k)
+                split = ((((high - low) & M64) >> 8) * p[idx] & M64) >> 8
+                if bit == 0:
+                    low = (low + split + 1) & M64
+                    p[idx] -= p[idx] >> 6
+                else:
+                    high = (low + split) & M64
+                    p[idx] -= (p[idx] - PSCALE + 64) >> 6
+                while ((low ^ high) & M24_56) == 0:
+                    sba += ((high >> 24) & 0xFFFFFFFF).to_bytes(4, "big")
+                    low = (low << 32) & M64
+                    high = ((high << 32) | M0_32) & M64
+            p = probs[val >> 6]
+        out.varint(len(sba))
+        for b in sba:
+            out.write(b, 8)
+        start += size
+        if start < end:
+            out.write(low | M0_24, 56)
+    out.write(low | M0_24, 56)          # dispose()
+    return out.bytes()
+
+
+def test_fpaq_encoder_agrees_with_the_oracle():
+    for d in _cases()[:12] + [bytes(3000), bytes([255]) * 2000]:
+        ref, nbits = O.entropy_encode("FPAQ", d)
+        got, gbits = fpaq_encode(d)
+        assert gbits == nbits and got == ref, (len(d), gbits, nbits)
