@@ -293,3 +293,212 @@ def test_fpaq_encoder_agrees_with_the_oracle():
         ref, nbits = O.entropy_encode("FPAQ", d)
         got, gbits = fpaq_encode(d)
         assert gbits == nbits and got == ref, (len(d), gbits, nbits)
+
+
+# ---- rANS order 0 / order 1: K/entropy/ANSRangeEncoder.java:171-449, Symbol.reset :473-496; EntropyUtils.encodeAlphabet :38-75,
+#      normalizeFrequencies :141-250 ---------------------------------------------------------------------------------------------------
+def _normalize(freqs, total, scale):
+    """in-place on freqs[0..255]; -> alphabet (list of symbols)"""
+    if total == 0:
+        return []
+    if total == scale:
+        return [i for i in range(256) if freqs[i] != 0]
+    alphabet, sum_scaled, sum_freq, idx_max = [], 0, 0, 0
+    for i in range(256):
+        f = freqs[i]
+        if f == 0:
+            continue
+        sf = f * scale
+        scaled = 1 if sf <= total else (sf + (total >> 1)) // total
+        alphabet.append(i)
+        sum_scaled += scaled
+        freqs[i] = scaled
+        sum_freq += f
+        if scaled > freqs[idx_max]:
+            idx_max = i
+        if sum_freq >= total:
+            break
+    if not alphabet:
+        return []
+    if len(alphabet) == 1:
+        freqs[alphabet[0]] = scale
+        return alphabet
+    if sum_scaled == scale:
+        return alphabet
+    delta = sum_scaled - scale
+    thr = freqs[idx_max] >> 4
+    if abs(delta) <= thr:
+        freqs[idx_max] -= delta
+        return alphabet
+    if delta < 0:
+        delta += thr
+        freqs[idx_max] += thr
+    else:
+        delta -= thr
+        freqs[idx_max] -= thr
+    inc = -1 if delta > 0 else 1
+    delta = abs(delta)
+    rnd = 0
+    while True:
+        rnd += 1
+        if not (rnd < 6 and delta > 0):
+            break
+        adjustments = 0
+        for idx in alphabet:
+            if freqs[idx] <= 2:
+                continue
+            freqs[idx] += inc
+            adjustments += 1
+            delta -= 1
+            if delta == 0:
+                break
+        if adjustments == 0:
+            break
+    freqs[idx_max] = max(freqs[idx_max] - delta, 1)
+    return alphabet
+
+
+def _encode_alphabet(out, alphabet):
+    n = len(alphabet)
+    if n == 0:
+        out.write(0, 1); out.write(1, 1)
+    elif n == 256:
+        out.write(0, 1); out.write(0, 1)
+    else:
+        out.write(1, 1)
+        masks = [0] * 32
+        for a in alphabet:
+            masks[a >> 3] |= 1 << (a & 7)
+        last = alphabet[-1] >> 3
+        out.write(last, 5)
+        for i in range(last + 1):
+            out.write(masks[i], 8)
+
+
+def _symbol(cum, freq, lr):
+    """-> (xMax, bias, cmplFreq, invShift, invFreq)"""
+    if freq >= 1 << lr:
+        freq = (1 << lr) - 1
+    x_max = ((32768 >> lr) << 16) * freq
+    cmpl = (1 << lr) - freq
+    if freq < 2:
+        return (x_max, cum + (1 << lr) - 1, cmpl, 32, 0xFFFFFFFF)
+    shift = 0
+    while freq > (1 << shift):
+        shift += 1
+    return (x_max, cum, cmpl, 32 + shift - 1, (((1 << (shift + 31)) + freq - 1) // freq) & 0xFFFFFFFF)
+
+
+def ans_encode(data, order):
+    lr = 12 if order == 0 else 11
+    chunk = 16384 if order == 0 else (4 << 20)
+    out = _Bits()
+    n = len(data)
+    if n <= 32:
+        for b in data:
+            out.write(b, 8)
+        return out.bytes()
+    nctx = 255 * order + 1
+    zero = (0, 0, 0, 0, 0)
+    symbols = [[zero] * 256 for _ in range(nctx)]            # `new Symbol()` per encode() call (:277-282)
+    start = 0
+    while start < n:
+        end = min(start + chunk, n)
+        freqs = [[0] * 257 for _ in range(nctx)]
+        if order == 0:
+            for b in data[start:end]:
+                freqs[0][b] += 1
+            freqs[0][256] = end - start
+        else:
+            quarter = (end - start) >> 2
+            spans = [(start, end)] if quarter == 0 else [(start + q * quarter, start + (q + 1) * quarter) for q in range(4)]
+            for a, z in spans:
+                prv = 0
+                for b in data[a:z]:
+                    freqs[prv][b] += 1
+                    freqs[prv][256] += 1
+                    prv = b
+        out.write(lr - 8, 3)
+        total_alpha = 0
+        for k in range(nctx):
+            f = freqs[k]
+            alphabet = _normalize(f, f[256], 1 << lr)
+            cum = 0
+            for s in alphabet:
+                symbols[k][s] = _symbol(cum, f[s], lr)
+                cum += f[s]
+            _encode_alphabet(out, alphabet)
+            if len(alphabet) > 1:
+                chk = 8 if len(alphabet) >= 64 else 6
+                llr = 3
+                while (1 << llr) <= lr:
+                    llr += 1
+                for i in range(1, len(alphabet), chk):
+                    endj = min(i + chk, len(alphabet))
+                    mx = max(f[alphabet[j]] - 1 for j in range(i, endj))
+                    log_max = 0
+                    while (1 << log_max) <= mx:
+                        log_max += 1
+                    out.write(log_max, llr)
+                    if log_max == 0:
+                        continue
+                    for j in range(i, endj):
+                        out.write(f[alphabet[j]] - 1, log_max)
+            total_alpha += len(alphabet)
+        if total_alpha <= 1 and order == 0:
+            start = end
+            continue
+        # encodeChunk (:337-407)
+        buf = bytearray()                   # bytes in the order they are written, i.e. from the END of Java's buffer backwards
+        end4 = start + ((end - start) & -4)
+        for i in range(end - 1, end4 - 1, -1):
+            buf.append(data[i])
+        st = [32768] * 4
+
+        def step(k, sym):
+            x_max, bias, cmpl, inv_shift, inv = sym
+            s = st[k]
+            if s >= x_max:
+                buf.append(s & 0xFF)
+                buf.append((s >> 8) & 0xFF)
+                s >>= 16
+            st[k] = s + bias + ((s * inv) >> inv_shift) * cmpl
+
+        if order == 0:
+            i = end4 - 1
+            while i > start:
+                for k in range(4):
+                    step(k, symbols[0][data[i - k]])
+                i -= 4
+        else:
+            quarter = (end4 - start) >> 2
+            idx = [start + (q + 1) * quarter - 2 for q in range(4)]
+            prv = [data[j + 1] if j + 1 >= 0 else 0 for j in idx]
+            while idx[0] >= start:
+                for k in range(4):
+                    cur = data[idx[k]]
+                    step(k, symbols[cur][prv[k]])
+                    prv[k] = cur
+                    idx[k] -= 1
+            for k in range(4):
+                step(k, symbols[0][prv[k]])
+        out.varint(len(buf))
+        for k in range(4):
+            out.write(st[k], 32)
+        for b in reversed(buf):
+            out.write(b, 8)
+        start = end
+    return out.bytes()
+
+
+@pytest.mark.parametrize("kind,order", [("ANS0", 0), ("ANS1", 1)])
+def test_ans_encoder_agrees_with_the_oracle(kind, order):
+    r = np.random.default_rng(9)
+    # (order 1 writes 256 context headers: inputs are sized so that the oracle wrapper's 2 n + 4 KiB output buffer holds them)
+    noise = bytes(r.integers(0, 256, 40000 if order == 0 else 200000, dtype=np.uint8))
+    cases = [c for c in _cases()[:10] if order == 0 or len(set(c)) <= 64] + [noise, bytes(20000), bytes([7]) * 33,
+             bytes(r.choice([65, 66, 67, 200], 50001).astype(np.uint8)), bytes(range(32)), bytes(r.choice([1, 2, 3], 35).astype(np.uint8))]
+    for d in cases:
+        ref, nbits = O.entropy_encode(kind, d)
+        got, gbits = ans_encode(d, order)
+        assert gbits == nbits and got == ref, (kind, len(d), gbits, nbits)
