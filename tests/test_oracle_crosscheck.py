@@ -502,3 +502,186 @@ def test_ans_encoder_agrees_with_the_oracle(kind, order):
         ref, nbits = O.entropy_encode(kind, d)
         got, gbits = ans_encode(d, order)
         assert gbits == nbits and got == ref, (kind, len(d), gbits, nbits)
+
+
+# ---- Huffman: K/entropy/HuffmanEncoder.java:103-493, HuffmanCommon.generateCanonicalCodes :71-111, ExpGolombEncoder (signed table) ----
+def _expgolomb_signed(val):
+    """-> (bits, nbits) as the reference's signed cache emits them (ExpGolombEncoder.java:52-70: emit & 0x1FF in emit >>> 9 bits)"""
+    if val == 0:
+        return 1, 1
+    a = abs(val)
+    lg = (a + 1).bit_length() - 1
+    return (1 << (lg + 1)) | (((a + 1 - (1 << lg)) << 1) | (1 if val < 0 else 0)), 2 * lg + 2
+
+
+def test_expgolomb_formula_matches_the_reference_table():
+    # entries of CACHE_VALUES[1] (signed), index = val & 0xFF
+    table = {1: 2052, 2: 2054, 3: 3080, 4: 3082, 7: 4112, 15: 5152, 255: 2053, 254: 2055, 253: 3081, 249: 4113}
+    for idx, emit in table.items():
+        val = idx if idx < 128 else idx - 256
+        bits, n = _expgolomb_signed(val)
+        assert (n << 9) | bits == emit, (idx, bits, n, emit)
+
+
+def _hf_phase1(data, n):
+    s = r = 0
+    for t in range(n - 1):
+        total = 0
+        for _ in range(2):
+            if s >= n or (r < t and data[r] < data[s]):
+                total += data[r]
+                data[r] = t
+                r += 1
+                continue
+            total += data[s]
+            if s > t:
+                data[s] = 0
+            s += 1
+        data[t] = total
+
+
+def _hf_phase2(data, n):
+    if n < 2:
+        return 0
+    level_top, depth, i, total_nodes = n - 2, 1, n, 2
+    while i > 0:
+        k = level_top
+        while k > 0 and data[k - 1] >= level_top:
+            k -= 1
+        internal = level_top - k
+        for _ in range(total_nodes - internal):
+            i -= 1
+            data[i] = depth
+        total_nodes = internal << 1
+        level_top = k
+        depth += 1
+    return depth - 1
+
+
+def _hf_code_lengths(sizes, ranks, count):
+    ranks[:count] = sorted(ranks[:count])
+    freqs = [0] * 256
+    for i in range(count):
+        freqs[i] = ranks[i] >> 8
+        ranks[i] &= 0xFF
+        if freqs[i] == 0:
+            return 0
+    _hf_phase1(freqs, count)
+    mx = _hf_phase2(freqs, count)
+    for i in range(count):
+        sizes[ranks[i]] = freqs[i]
+    return mx
+
+
+def _hf_limit(alphabet, freqs, sizes, ranks, count):
+    MAXL = 12
+    n = debt = 0
+    while sizes[ranks[n]] >= MAXL:
+        debt += sizes[ranks[n]] - MAXL
+        sizes[ranks[n]] = MAXL
+        n += 1
+    ll = [[] for _ in range(6)]
+    while n < count:
+        idx = MAXL - 1 - sizes[ranks[n]]
+        if idx >= 6 or debt < (1 << idx):
+            break
+        ll[idx].append(ranks[n])
+        n += 1
+    idx = 5
+    while debt > 0 and idx >= 0:
+        if not ll[idx] or debt < (1 << idx):
+            idx -= 1
+            continue
+        sizes[ll[idx].pop(0)] += 1
+        debt -= 1 << idx
+    idx = 0
+    while debt > 0 and idx < 6:
+        if not ll[idx]:
+            idx += 1
+            continue
+        sizes[ll[idx].pop(0)] += 1
+        debt -= 1 << idx
+    if debt > 0:
+        f = [freqs[alphabet[i]] for i in range(count)] + [0] * (256 - count)
+        total = sum(f)
+        _normalize(f, total, 16384 >> 3)        # (over the first `count` entries: the reference passes a count-long array)
+        for i in range(count):
+            freqs[alphabet[i]] = f[i]
+            ranks[i] = (f[i] << 8) | alphabet[i]
+        return _hf_code_lengths(sizes, ranks, count)
+    return MAXL
+
+
+def huffman_encode(data, chunk=16384):
+    out = _Bits()
+    n = len(data)
+    start = 0
+    while start < n:
+        size = min(chunk, n - start)
+        blk = data[start:start + size]
+        if size < 32:
+            for b in blk:
+                out.write(b, 8)
+            start += size
+            continue
+        freqs = [0] * 256
+        for b in blk:
+            freqs[b] += 1
+        alphabet = [i for i in range(256) if freqs[i] > 0]
+        count = len(alphabet)
+        codes, sizes = [0] * 256, [0] * 256
+        _encode_alphabet(out, alphabet)
+        if count == 1:
+            sizes[alphabet[0]] = 1
+        else:
+            ranks = [(freqs[a] << 8) | a for a in alphabet] + [0] * (256 - count)
+            mx = _hf_code_lengths(sizes, ranks, count)
+            assert mx != 0
+            if mx > 12:
+                mx = _hf_limit(alphabet, freqs, sizes, ranks, count)
+                assert mx != 0
+            if mx > 12:
+                for i, a in enumerate(alphabet):
+                    codes[a] = i
+                    sizes[a] = 8
+            else:
+                order = sorted(ranks[:count], key=lambda s: (sizes[s], s))
+                code, cur = 0, sizes[order[0]]
+                for s in order:
+                    code <<= sizes[s] - cur
+                    cur = sizes[s]
+                    codes[s] = code
+                    code += 1
+        prev = 2
+        for a in alphabet:
+            bits, nb = _expgolomb_signed(sizes[a] - prev)
+            out.write(bits, nb)
+            prev = sizes[a]
+        if count > 1:
+            frag = size // 4
+            parts = []
+            for j in range(4):
+                v, nb = 0, 0
+                for b in blk[j * frag:(j + 1) * frag]:
+                    v = (v << sizes[b]) | codes[b]
+                    nb += sizes[b]
+                parts.append((v, nb))
+            for _, nb in parts:
+                out.varint(nb)
+            for v, nb in parts:
+                out.write(v, nb)
+            for b in blk[4 * frag:]:
+                out.write(b, 8)
+        start += size
+    return out.bytes()
+
+
+def test_huffman_encoder_agrees_with_the_oracle():
+    import corpus
+    r = np.random.default_rng(11)
+    cases = _cases()[:12] + [bytes(r.integers(0, 256, 40000, dtype=np.uint8)), bytes(20000), bytes([7]) * 33, bytes(range(32)), bytes(range(40)),
+                             corpus.fibonacci_chunk(), corpus.fibonacci_chunk() + bytes(r.integers(0, 7, 5000, dtype=np.uint8))]
+    for d in cases:
+        ref, nbits = O.entropy_encode("HUFFMAN", d)
+        got, gbits = huffman_encode(d)
+        assert gbits == nbits and got == ref, (len(d), gbits, nbits)
