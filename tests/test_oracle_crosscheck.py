@@ -685,3 +685,207 @@ def test_huffman_encoder_agrees_with_the_oracle():
         ref, nbits = O.entropy_encode("HUFFMAN", d)
         got, gbits = huffman_encode(d)
         assert gbits == nbits and got == ref, (len(d), gbits, nbits)
+
+
+# ---- LZ / LZX forward: K/transform/LZCodec.java:299-597 (LZXCodec.forward), hash :904-911, emitLength :209-231, findMatch :271-287 ----
+def lzx_forward(src, extra=False, data_type_dna=False):
+    """-> (ok, out bytes) for a slice with index 0, dst capacity getMaxEncodedLength; None if the Java code would throw"""
+    count = len(src)
+    if count == 0:
+        return True, b""
+    if count < 24:
+        return False, b""
+    hlog = 19 if extra else 16
+    hashes = [0] * (1 << hlog)
+    min_buf = max(count // 5, 256)
+    mbuf, mlen, tk = bytearray(min_buf), bytearray(min_buf), bytearray(min_buf)
+    MAXD1, MAXD2, MAX_MATCH = (1 << 16) - 2, (1 << 24) - 2, 65535 + 254 + 4
+    src_end = count - 16 - 2
+    max_dist = MAXD1 if src_end < 4 * MAXD1 else MAXD2
+    mm = 6 if data_type_dna else 4
+    dst = bytearray(count + (16 if count <= 1024 else count // 64) + 2 + 64)
+    dst[12] = (0 if max_dist == MAXD1 else 1) | (((mm - 2) & 7) << 1)
+
+    def h(i):
+        v = int.from_bytes(src[i:i + 8], "little")
+        return (((v << 24) * 0x1E35A7BD) & M64) >> (64 - hlog)
+
+    def diff4(a, b):
+        return src[a:a + 4] != src[b:b + 4]
+
+    def find(a, ref, max_match):
+        best = 0
+        while best + 8 <= max_match:
+            x = int.from_bytes(src[a + best:a + best + 8], "little") ^ int.from_bytes(src[ref + best:ref + best + 8], "little")
+            if x != 0:
+                best += ((x & -x).bit_length() - 1) >> 3
+                break
+            best += 8
+        return best
+
+    def emit_len(buf, idx, length):
+        if length < 254:
+            buf[idx] = length
+            return idx + 1
+        if length < 65536 + 254:
+            length -= 254
+            buf[idx] = 254; buf[idx + 1] = (length >> 8) & 0xFF; buf[idx + 2] = length & 0xFF
+            return idx + 3
+        length -= 255
+        buf[idx] = 255; buf[idx + 1] = (length >> 16) & 0xFF; buf[idx + 2] = (length >> 8) & 0xFF; buf[idx + 3] = length & 0xFF
+        return idx + 4
+
+    si = anchor = 0
+    di = 13
+    m_idx = ml_idx = tk_idx = 0
+    repd = [count, count]
+    rep_idx = 0
+    src_inc = 0
+    try:
+        while si < src_end:
+            best = 0
+            h0 = h(si)
+            ref0 = hashes[h0]
+            hashes[h0] = si
+            si1 = si + 1
+            ref = si1 - repd[rep_idx]
+            min_ref = max(si - max_dist, 0)
+            if ref > min_ref and not diff4(ref, si1):
+                best = find(si1, ref, min(src_end - si1, MAX_MATCH))
+            else:
+                ref = si1 - repd[rep_idx ^ 1]
+                if ref > min_ref and not diff4(ref, si1):
+                    best = find(si1, ref, min(src_end - si1, MAX_MATCH))
+            if best < mm:
+                ref = ref0
+                if ref > min_ref and not diff4(ref, si):
+                    best = find(si, ref, min(src_end - si, MAX_MATCH))
+                if best < mm:
+                    si = si1 + (src_inc >> 6)
+                    src_inc += 1
+                    rep_idx = 0
+                    continue
+                if ref != si - repd[0] and ref != si - repd[1]:
+                    h1 = h(si1)
+                    ref1 = hashes[h1]
+                    hashes[h1] = si1
+                    if ref1 > min_ref + 1 and not diff4(ref1 + best - 3, si1 + best - 3):
+                        b1 = find(si1, ref1, min(src_end - si1, MAX_MATCH))
+                        if b1 >= best:
+                            ref, best, si = ref1, b1, si1
+                    if extra:
+                        si2 = si1 + 1
+                        h2 = h(si2)
+                        ref2 = hashes[h2]
+                        hashes[h2] = si2
+                        if ref2 > min_ref + 2 and not diff4(ref2 + best - 3, si2 + best - 3):
+                            b2 = find(si2, ref2, min(src_end - si2, MAX_MATCH))
+                            if b2 >= best:
+                                ref, best, si = ref2, b2, si2
+                while si > anchor and ref > min_ref and src[si - 1] == src[ref - 1]:
+                    best += 1
+                    ref -= 1
+                    si -= 1
+                if best > MAX_MATCH:
+                    ref += best - MAX_MATCH
+                    si += best - MAX_MATCH
+                    best = MAX_MATCH
+            else:
+                if best >= MAX_MATCH or src[si] != src[ref - 1]:
+                    si += 1
+                    hashes[h(si)] = si
+                else:
+                    best += 1
+                    ref -= 1
+            src_inc = 0
+            dist = si - ref
+            if dist == repd[0]:
+                token, th = 0x00, 3
+            elif dist == repd[1]:
+                token, th = 0x04, 3
+            else:
+                mbuf[m_idx] = (dist >> 16) & 0xFF
+                inc1 = 1 if dist >= 65536 else 0
+                m_idx += inc1
+                mbuf[m_idx] = (dist >> 8) & 0xFF
+                inc2 = 1 if dist >= 256 else 0
+                m_idx += inc2
+                mbuf[m_idx] = dist & 0xFF
+                m_idx += 1
+                token, th = (inc1 + inc2 + 1) << 3, 7
+            m_len = best - mm
+            if m_len >= th:
+                token += th
+                ml_idx = emit_len(mlen, ml_idx, m_len - th)
+            else:
+                token += m_len
+            repd[1] = repd[0]
+            repd[0] = dist
+            rep_idx = 1
+            lit = si - anchor
+            if lit == 0:
+                tk[tk_idx] = token
+                tk_idx += 1
+            else:
+                if lit >= 7:
+                    if lit >= (1 << 24):
+                        return False, b""
+                    tk[tk_idx] = (7 << 5) | token
+                    tk_idx += 1
+                    di = emit_len(dst, di, lit - 7)
+                else:
+                    tk[tk_idx] = (lit << 5) | token
+                    tk_idx += 1
+                dst[di:di + lit] = src[anchor:anchor + lit]
+                di += lit
+            if m_idx >= len(mbuf) - 8:
+                mbuf += bytearray((len(mbuf) * 3) // 2 - len(mbuf))
+                if ml_idx >= len(mlen) - 4:
+                    mlen += bytearray((len(mlen) * 3) // 2 - len(mlen))
+            anchor = si + best
+            while si + 4 < anchor:
+                si += 4
+                for k in (3, 2, 1, 0):
+                    hashes[h(si - k)] = si - k
+            si += 1
+            while si < anchor:
+                hashes[h(si)] = si
+                si += 1
+        lit = count - anchor
+        if di + lit + tk_idx + m_idx + ml_idx >= count:
+            return False, b""
+        if lit >= 7:
+            tk[tk_idx] = 7 << 5
+            tk_idx += 1
+            di = emit_len(dst, di, lit - 7)
+        else:
+            tk[tk_idx] = lit << 5
+            tk_idx += 1
+        dst[di:di + lit] = src[anchor:anchor + lit]
+        di += lit
+    except IndexError:
+        return None, b""            # Java: ArrayIndexOutOfBoundsException (tkBuf is never grown)
+    dst[0:4] = di.to_bytes(4, "little"); dst[4:8] = tk_idx.to_bytes(4, "little"); dst[8:12] = m_idx.to_bytes(4, "little")
+    out = bytes(dst[:di]) + bytes(tk[:tk_idx]) + bytes(mbuf[:m_idx]) + bytes(mlen[:ml_idx])
+    return len(out) <= count - count // 100, out
+
+
+@pytest.mark.parametrize("name,extra", [("LZ", False), ("LZX", True)])
+def test_lz_forward_agrees_with_the_oracle(name, extra):
+    import corpus
+    from kanzi_b200 import synth
+    r = np.random.default_rng(21)
+    cases = [synth.text(30000, 5).tobytes(), synth.exe_like(40000, 6).tobytes(), synth.records(25000, 7).tobytes(), (b"0123456789abcdef" * 7 + b"Z") * 300,
+             bytes(np.repeat(r.integers(0, 256, 900, dtype=np.uint8), r.integers(1, 60, 900))), corpus.sparse_with_repeats(60000, 14),
+             bytes(70000), synth.text(70000, 9).tobytes() + synth.text(70000, 9).tobytes(), bytes(r.integers(0, 256, 5000, dtype=np.uint8)), b"ab" * 20]
+    applied = 0
+    for d in cases:
+        cap = len(d) + len(d) // 64 + 1100
+        ok_ref, ref, _, _ = O.transform(name, d, dst_cap=cap, ctx=[7, max(len(d), 1024), len(d), 1, 0, 0])
+        ok, got = lzx_forward(d, extra)
+        assert ok is not None
+        assert int(ok) == ok_ref, (name, len(d), ok, ok_ref)
+        if ok:
+            applied += 1
+            assert got == ref, (name, len(d), len(got), len(ref))
+    assert applied >= 6
