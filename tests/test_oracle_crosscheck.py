@@ -390,14 +390,19 @@ def _symbol(cum, freq, lr):
 
 
 def ans_encode(data, order):
-    lr = 12 if order == 0 else 11
-    chunk = 16384 if order == 0 else (4 << 20)
     out = _Bits()
+    _ans_encode_into(out, data, order, 16384 if order == 0 else (4 << 20))
+    return out.bytes()
+
+
+def _ans_encode_into(out, data, order, chunk):
+    """One ANSRangeEncoder.encode() call on an open bitstream (the ROLZ codec makes several, with its own chunk size)."""
+    lr = 12 if order == 0 else 11
     n = len(data)
     if n <= 32:
         for b in data:
             out.write(b, 8)
-        return out.bytes()
+        return
     nctx = 255 * order + 1
     zero = (0, 0, 0, 0, 0)
     symbols = [[zero] * 256 for _ in range(nctx)]            # `new Symbol()` per encode() call (:277-282)
@@ -488,7 +493,6 @@ def ans_encode(data, order):
         for b in reversed(buf):
             out.write(b, 8)
         start = end
-    return out.bytes()
 
 
 @pytest.mark.parametrize("kind,order", [("ANS0", 0), ("ANS1", 1)])
@@ -889,3 +893,206 @@ def test_lz_forward_agrees_with_the_oracle(name, extra):
             applied += 1
             assert got == ref, (name, len(d), len(got), len(ref))
     assert applied >= 6
+
+
+# ---- BWT forward by definition: K/transform/BWT.java:186-187, DivSufSort.java:204-227 (output layout), :230-322 (primary indexes) ----
+def bwt_by_definition(d):
+    """Suffixes sorted naively (a suffix that is a prefix of another sorts first).  out[0] = last byte; rank i before suffix 0's rank
+    p -> out[i+1], after -> out[i].  indexes[k] = rank(suffix k*step)+1 for the chunk starts, indexes[0] = p+1."""
+    n = len(d)
+    sa = sorted(range(n), key=lambda i: d[i:])
+    rank = {s: i for i, s in enumerate(sa)}
+    p = rank[0]
+    out = bytearray(n)
+    out[0] = d[n - 1]
+    for i, s in enumerate(sa):
+        if i < p:
+            out[i + 1] = d[s - 1]
+        elif i > p:
+            out[i] = d[s - 1]
+    chunks = 1 if n < 256 else 8
+    st = n // chunks
+    step = st + 1 if st * chunks != n else st
+    idx = [0] * 8
+    for s in range(0, n, step):
+        idx[s // step] = rank[s] + 1
+    return bytes(out), idx
+
+
+def test_bwt_forward_matches_a_naive_suffix_sort():
+    import corpus
+    from kanzi_b200 import synth
+    r = np.random.default_rng(33)
+    cases = list(corpus.BWT_LITERALS) + [synth.text(3001, 4).tobytes(), bytes(r.integers(0, 4, 2048, dtype=np.uint8)), bytes(r.integers(0, 256, 255, dtype=np.uint8)),
+                                         bytes(r.integers(0, 256, 256, dtype=np.uint8)), b"abcab" * 400, bytes(1500), b"ba" * 700 + b"c", synth.records(4000, 8).tobytes()]
+    for d in cases:
+        if len(d) < 2:
+            continue
+        ok, out, pi = O.bwt_forward(d)
+        want, idx = bwt_by_definition(d)
+        assert ok == 1 and out == want, len(d)
+        assert pi[:len(idx)] == idx, (len(d), pi, idx)
+
+
+# ---- ROLZ forward (ROLZCodec1): K/transform/ROLZCodec.java:419-677, findMatch :365-416, emitLength :679-693, keys/hash :123-149 ----
+def _is_dna(d):   # Global.detectSimpleType's first rule (Global.java:556-566); the other types it can return leave ROLZ's parameters alone
+    return len(d) > 0 and sum(d.count(bytes([c])) for c in b"acgntuACGNTU") > len(d) - len(d) // 12
+
+
+def rolz_forward(src, log_checks=4):
+    """-> (ok, out) for ROLZCodec1 with a non-null context of undefined data type; ok None where the Java code would throw"""
+    M32, HASH, HMASK = 0xFFFFFFFF, 200002979, 0xFF000000
+    count = len(src)
+    if count == 0:
+        return True, b""
+    if count < 64:
+        return False, b""
+    src_end = count - 4
+    size_chunk = min(count, 16 << 20)
+    lit = bytearray(size_chunk + 64 if size_chunk <= 512 else size_chunk)
+    lenb, midx, tk = bytearray(size_chunk // 5), bytearray(size_chunk // 4), bytearray(size_chunk // 4)
+    counters = [0] * 65536
+    lit_order = 0 if count < (1 << 17) else 1
+    flags, mm, dt = lit_order, 3, 2
+    if _is_dna(src):
+        dt, mm, flags = 8, 7, flags | 4
+    flags |= log_checks << 4
+    out = bytearray(count.to_bytes(4, "big")) + bytes([flags])
+    checks = 1 << log_checks
+    mask = checks - 1
+
+    def key_at(i):
+        if mm == 3:
+            return src[i] | (src[i + 1] << 8)
+        return (((int.from_bytes(src[i:i + 8], "little") * HASH) & M64) >> 40) & 0xFFFF
+
+    def hash_at(i):
+        return ((((int.from_bytes(src[i:i + 4], "little") << 8) & M32) * HASH) & M32) & HMASK
+
+    def emit_len(n):
+        nonlocal nl
+        if n >= 1 << 7:
+            if n >= 1 << 14:
+                if n >= 1 << 21:
+                    lenb[nl] = 0x80 | (n >> 21) & 0xFF; nl += 1
+                lenb[nl] = (0x80 | (n >> 14)) & 0xFF; nl += 1
+            lenb[nl] = (0x80 | (n >> 7)) & 0xFF; nl += 1
+        lenb[nl] = n & 0x7F; nl += 1
+
+    start = 0
+    try:
+        while start < src_end:
+            nlit = nl = nm = nt = 0
+            matches = [0] * (65536 << log_checks)
+            end_chunk = min(start + size_chunk, src_end)
+            size_chunk = end_chunk - start
+            si = start
+
+            def find(pos, h32, counter, base):
+                best_len, best_idx = 0, -1
+                max_match = min(3 + 65535, end_chunk - pos) - 8
+                for i in range(counter, counter - checks, -1):
+                    ref = matches[base + (i & mask)]
+                    if (ref & HMASK) != h32:
+                        continue
+                    ref = (ref & 0xFFFFFF) + start
+                    if src[ref + best_len] != src[pos + best_len]:
+                        continue
+                    n = 0
+                    while n < max_match:
+                        x = int.from_bytes(src[ref + n:ref + n + 8], "little") ^ int.from_bytes(src[pos + n:pos + n + 8], "little")
+                        if x:
+                            n += ((x & -x).bit_length() - 1) >> 3
+                            break
+                        n += 8
+                    if n > best_len:
+                        best_idx, best_len = counter - i, n
+                return -1 if best_len < mm else (best_idx << 16) | (best_len - mm)
+
+            for _ in range(min(src_end - start, 8)):
+                lit[nlit] = src[si]; nlit += 1; si += 1
+            first_lit = si
+            src_inc = 0
+            while si < end_chunk:
+                key = key_at(si - dt)
+                base = key << log_checks
+                h32 = hash_at(si)
+                match = find(si, h32, counters[key], base)
+                counters[key] = (counters[key] + 1) & mask
+                matches[base + counters[key]] = h32 | (si - start)
+                if match == -1:
+                    si += 1 + (src_inc >> 6)
+                    src_inc += 1
+                    continue
+                key = key_at(si + 1 - dt)
+                base = key << log_checks
+                h32 = hash_at(si + 1)
+                match2 = find(si + 1, h32, counters[key], base)
+                if match2 >= 0 and (match2 & 0xFFFF) > (match & 0xFFFF):
+                    match = match2
+                    si += 1
+                    counters[key] = (counters[key] + 1) & mask
+                    matches[base + counters[key]] = h32 | (si - start)
+                lit_len = si - first_lit
+                token = (lit_len << 3) if lit_len < 31 else 0xF8
+                m_len = match & 0xFFFF
+                if m_len >= 7:
+                    tk[nt] = token | 7; nt += 1
+                    emit_len(m_len - 7)
+                else:
+                    tk[nt] = token | m_len; nt += 1
+                if lit_len >= 31:
+                    emit_len(lit_len - 31)
+                if nlit + lit_len > len(lit):
+                    raise IndexError
+                lit[nlit:nlit + lit_len] = src[first_lit:first_lit + lit_len]
+                nlit += lit_len
+                midx[nm] = (match >> 16) & 0xFF; nm += 1
+                si += m_len + mm
+                first_lit = si
+                src_inc = 0
+            lit_len = size_chunk - (first_lit - start)
+            if nt != 0:
+                tk[nt] = 0xF8 if lit_len >= 31 else (lit_len << 3); nt += 1
+            if lit_len >= 31:
+                emit_len(lit_len - 31)
+            if nlit + lit_len > len(lit):
+                raise IndexError
+            lit[nlit:nlit + lit_len] = src[first_lit:first_lit + lit_len]
+            nlit += lit_len
+            bits = _Bits()
+            for v in (nlit, nt, nl, nm):
+                bits.write(v, 32)
+            _ans_encode_into(bits, bytes(lit[:nlit]), lit_order, 16384 if lit_order == 0 else (4 << 20))
+            for part in (tk[:nt], lenb[:nl], midx[:nm]):
+                _ans_encode_into(bits, bytes(part), 0, 32768)
+            out += bits.bytes()[0]
+            start = end_chunk
+    except IndexError:
+        return None, b""
+    out += src[src_end:src_end + 4]
+    return True, bytes(out)
+
+
+def test_rolz_forward_agrees_with_the_oracle():
+    import corpus
+    from kanzi_b200 import synth
+    r = np.random.default_rng(27)
+    dna = bytes(np.frombuffer(b"ACGT", dtype=np.uint8)[r.integers(0, 4, 6000)])
+    dna = dna + dna[1000:3000] + dna[:2500]
+    cases = [synth.text(30000, 5).tobytes(), synth.exe_like(40000, 6).tobytes(), synth.records(25000, 7).tobytes(), (b"0123456789abcdef" * 7 + b"Z") * 300,
+             corpus.sparse_with_repeats(60000, 14), synth.text(70000, 9).tobytes() + synth.text(70000, 9).tobytes(), dna,
+             bytes(r.integers(0, 256, 5000, dtype=np.uint8)), b"ab" * 20, b"xyz" * 40]
+    applied = 0
+    for d in cases:
+        cap = max(len(d) + 64, 1024) + 1024
+        ok_ref, ref, _, _ = O.transform("ROLZ", d, dst_cap=cap, ctx=[7, max(len(d), 1024), len(d), 1, 0, 0])
+        ok, got = rolz_forward(d)
+        assert ok is not None
+        if ok and len(got) > cap:
+            ok = False
+        assert int(ok) == ok_ref, (len(d), ok, ok_ref)
+        if ok:
+            applied += 1
+            assert got == ref, (len(d), len(got), len(ref))
+    assert applied >= 7
