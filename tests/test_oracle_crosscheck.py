@@ -4,7 +4,10 @@ two restatements that were written separately and agree bit for bit are the next
 Java semantics reproduced here: `int` wraps at 32 bits, bytes are unsigned after `& 0xFF`.
   ZRLT  K/transform/ZRLT.java:54-136 (forward), 146-233 (inverse)
   SBRT  K/transform/SBRT.java:87-151 (forward), 154-214 (inverse); modes MTF = 1, RANK = 2, TIMESTAMP = 3
-  SRT   K/transform/SRT.java:73-168 (forward), 178-257 (inverse), preprocess :266-302, header :312-353"""
+  SRT   K/transform/SRT.java:73-168 (forward), 178-257 (inverse), preprocess :266-302, header :312-353
+Further down, each with its own citation: the FPAQ, ANS0/ANS1 and Huffman encoders, the LZ/LZX and ROLZ forward transforms, the BWT held
+against a naive suffix sort, and the block framing of CompressedOutputStream.  The decoders and inverses are covered through the
+oracle's own round trips (tests/test_oracle.py): an inverse that returns the input of a doubly-checked encoder is checked too."""
 import numpy as np
 import pytest
 import oracle_lib as O
@@ -1096,3 +1099,94 @@ def test_rolz_forward_agrees_with_the_oracle():
             applied += 1
             assert got == ref, (len(d), len(got), len(ref))
     assert applied >= 7
+
+
+# ---- block framing: K/io/CompressedOutputStream.java:677-1035 (encodeBlock), close :483-493 -------------------------------------
+def _mix32(c, h, v):
+    c ^= (h * (~v & 0xFFFFFFFF)) & 0xFFFFFFFF
+    c = ((c << 13) | (c >> 19)) & 0xFFFFFFFF
+    return (c * 5 + 0x52DCE729) & 0xFFFFFFFF
+
+
+def frame_blocks(data, transforms, entropy, bs, checksum, header_len):
+    """The stream after its header, built from the oracle's per-block transform sequence and entropy coder plus a restatement of the
+    block framing: mode byte, skip flags, post-transform length, header check byte, block checksum, raw fallback, length prefix."""
+    nfun = len(transforms)
+    out = _Bits()
+    for b0 in range(0, len(data), bs):
+        blk = data[b0:b0 + bs]
+        n = len(blk)
+        ck = None
+        if checksum == 32:
+            ck = (O.xxhash32(blk, 0x4B414E5A) & 0xFFFFFFFF, 32)
+        elif checksum == 64:
+            ck = (O.xxhash64(blk, 0x4B414E5A) & M64, 64)
+        mode = 0
+        if n <= 15:
+            post, skip, nf, ent = blk, 0x7F, 1, "NONE"      # a NONE sequence: its one function "applies" (Sequence.java:107), the unused slots stay set
+            mode |= 0x80
+        else:
+            post, skip = O.sequence_forward(transforms, blk, bs)
+            nf, ent = nfun, entropy
+        pl = len(post)
+        size = 1 if pl < 256 else ((pl.bit_length() - 1) >> 3) + 1
+        mode |= ((size - 1) & 3) << 5
+
+        def header(w, m, raw):
+            hs = skip
+            if raw:
+                w.write(m, 8)
+                if nf > 4:
+                    w.write(skip, 8)
+                else:
+                    hs = ((m << 4) | 0x0F) & 0xFF
+            elif (m & 0x80) or nf <= 4:
+                m |= skip >> 4
+                hs = 0 if (m & 0x80) else ((m << 4) | 0x0F) & 0xFF
+                w.write(m, 8)
+            else:
+                m |= 0x10
+                w.write(m, 8)
+                w.write(skip, 8)
+            w.write(pl, 8 * size)
+            at = w.n
+            w.write(0, 8)
+            if ck:
+                w.write(*ck)
+            return m, hs, at
+
+        w = _Bits()
+        mode2, hs, at = header(w, mode, False)
+        payload, nbits = O.entropy_encode(ent, post)
+        w.write(int.from_bytes(payload[:nbits // 8], "big"), 8 * (nbits // 8))
+        if nbits % 8:
+            w.write(payload[nbits // 8] >> (8 - nbits % 8), nbits % 8)
+        if not (mode2 & 0x80) and pl < ((w.n + 7) >> 3):
+            w = _Bits()
+            mode2, hs, at = header(w, mode2 | 0x80 | 0x10, True)
+            w.write(int.from_bytes(post, "big"), 8 * len(post))
+        written = w.n
+        c = (0x1E35A7BD * 0x01030507) & 0xFFFFFFFF
+        for v in (mode2 & 0xFF, hs & 0xFF, pl, written >> 32, written & 0xFFFFFFFF):
+            c = _mix32(c, 0x1E35A7BD, v)
+        body = w.v | ((((c >> 23) ^ (c >> 3)) & 0xFF) << (w.n - at - 8))
+        lw = 3 if written < 8 else ((written >> 3).bit_length() - 1) + 4
+        out.write(lw - 3, 5)
+        out.write(written, lw)
+        out.v = (out.v << written) | body
+        out.n += written
+    out.write(0, 5)
+    out.write(0, 3)
+    return out.bytes()[0]
+
+
+@pytest.mark.parametrize("transforms,entropy,bs,checksum", [(["LZ"], "HUFFMAN", 65536, 0), (["BWT", "RANK", "ZRLT"], "ANS0", 32768, 32), (["ROLZ"], "NONE", 65536, 64),
+                                                            (["NONE"], "FPAQ", 4096, 0), (["LZX"], "ANS1", 1 << 20, 32), (["LZ", "RANK", "ZRLT", "SRT", "MTFT"], "HUFFMAN", 16384, 0)])
+def test_block_framing_agrees_with_the_oracle(transforms, entropy, bs, checksum):
+    from kanzi_b200 import synth
+    r = np.random.default_rng(5)
+    data = synth.text(100000, 3).tobytes() + bytes(r.integers(0, 256, 70000, dtype=np.uint8)) + synth.records(40000 + 9, 4).tobytes()
+    for d in (data, data[:bs + 7], data[:12], data[100000:100000 + 2 * bs]):
+        ref = O.compress(d, transforms, entropy, bs, checksum=checksum)
+        hl = len(O.stream_header(transforms, entropy, bs, len(d)))
+        assert ref[hl:] == frame_blocks(d, transforms, entropy, bs, checksum, hl), (len(d), transforms)
