@@ -63,5 +63,17 @@ def build_native():
     return NATIVE_BIN
 
 
+SIBLING_SRC = os.path.join(HERE, "..", "tests", "native", "kzg_sibling_check.c")
+SIBLING_BIN = os.path.join(HERE, "..", "tests", "native", "kzg_sibling_check")
+
+
+def build_sibling_check():
+    """tests/native/kzg_sibling_check.c: torch-free parity check of the sibling codecs against the oracle (dlopen), for short GPU slots."""
+    if os.path.exists(SIBLING_BIN) and os.path.getmtime(SIBLING_BIN) > max(os.path.getmtime(SIBLING_SRC), os.path.getmtime(LIB)):
+        return SIBLING_BIN
+    subprocess.check_call(["gcc", "-O2", "-std=c11", "-Wall", SIBLING_SRC, "-L" + HERE, "-lkanzi_b200", "-ldl", "-Wl,-rpath,$ORIGIN/../../kanzi_b200", "-o", SIBLING_BIN])
+    return SIBLING_BIN
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

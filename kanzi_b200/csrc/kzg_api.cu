@@ -143,7 +143,7 @@ struct EvSet {
 // ---- ids / sizes (TransformFactory, getMaxEncodedLength of each codec) --------------------------------------
 static bool xf_known(int t) {
   switch (t) { case KZG_T_NONE: case KZG_T_LZ: case KZG_T_LZX: case KZG_T_ROLZ: case KZG_T_BWT: case KZG_T_RANK: case KZG_T_MTFT:
-               case KZG_T_SRT: case KZG_T_ZRLT: return true; default: return false; }
+               case KZG_T_SRT: case KZG_T_ZRLT: case KZG_T_LZP: return true; default: return false; }
 }
 static bool ent_known(int e) {
   switch (e) { case KZG_E_NONE: case KZG_E_HUFFMAN: case KZG_E_ANS0: case KZG_E_ANS1: case KZG_E_FPAQ: return true; default: return false; }
@@ -151,6 +151,7 @@ static bool ent_known(int e) {
 static i32 xf_max_len(int t, i32 n) {
   switch (t) {
     case KZG_T_LZ: case KZG_T_LZX: return ((n <= 1024) ? n + 16 : n + (n / 64)) + 2;   // LZCodec.java:961-964
+    case KZG_T_LZP: return (n <= 1024) ? n + 16 : n + (n / 64);                       // LZCodec.java:1283-1285
     case KZG_T_ROLZ: return (n <= 512) ? n + 64 : n;                                  // ROLZCodec.java:1001-1003
     case KZG_T_BWT: return n + 33;                                                    // BWTBlockCodec.java:222-224
     case KZG_T_SRT: return n + 1024;                                                  // SRT.java:364-366
@@ -483,7 +484,7 @@ static int transform_batch(std::vector<KzgReq*>& rq) {
     memset(&B, 0, sizeof(B));
     B.cur = dA + k * cap; B.alt = dB + k * cap; B.curLen = Q.srcLen; B.cap = forward ? Q.dstLen : Q.dstCap; B.origLen = Q.srcLen; B.skipFlags = 0xFF;
     B.dataType = Q.ctx ? Q.ctx->dataType : 0; B.aux0 = nullptr; B.aux1 = B.cur; B.stagesLeft = 2;
-    bt.hEnabled[k] = 1; bt.hDstLimit[k] = forward ? Q.dstLen : Q.dstCap;
+    bt.hEnabled[k] = 1; bt.hDstLimit[k] = (forward || type == KZG_T_LZP) ? Q.dstLen : Q.dstCap;     // (LZP.inverse bounds its output by dst.length, LZCodec.java:1133)
     if (!cu(cudaMemsetAsync(B.cur + Q.srcLen, 0, cap - Q.srcLen, W.stream)) || !cu(cudaMemcpyAsync(B.cur, Q.src, Q.srcLen, cudaMemcpyHostToDevice, W.stream)))
       return failAll(-KZG_ERR_PROCESS_BLOCK);
   }

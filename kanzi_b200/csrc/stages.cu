@@ -83,6 +83,7 @@ void kzg_stage_scratch(int type, i32 maxLen, bool forward, size_t* perBlockBytes
   switch (type) {
     case KZG_T_BWT: kzg_bwt_scratch(maxLen, forward, perBlockBytes, aux32); break;
     case KZG_T_ROLZ: kzg_rolz_scratch(maxLen, forward, perBlockBytes, hashInts, aux32); break;
+    case KZG_T_LZP: kzg_lzp_scratch(maxLen, forward, perBlockBytes, hashInts); break;
     case KZG_T_SRT: case KZG_T_RANK: case KZG_T_MTFT: case KZG_T_ZRLT: kzg_small_scratch(type, maxLen, forward, perBlockBytes, aux32); break;
     default: break;
   }
@@ -96,6 +97,7 @@ int kzg_stage_launch(cudaStream_t s, int type, bool forward, KzgBlock* d_blocks,
     case KZG_T_SRT: return kzg_srt_launch(s, forward, d_blocks, nBlocks, P, maxLen);
     case KZG_T_BWT: return kzg_bwtblock_launch(s, forward, d_blocks, nBlocks, P, maxLen);
     case KZG_T_ROLZ: return kzg_rolz_launch(s, forward, d_blocks, nBlocks, P, maxLen);
+    case KZG_T_LZP: return kzg_lzp_launch(s, forward, d_blocks, nBlocks, P, maxLen);
     default: kzg_set_error("transform id %d has no kernel", type); return -KZG_ERR_INVALID_CODEC;
   }
 }
@@ -108,6 +110,10 @@ int kzg_stage_precheck(int type, bool forward, const kzg_ctx* ctx, i32 srcLen, i
     case KZG_T_NONE: return (dstLen < srcLen) ? 0 : 1;                                   // NullTransform.java:57-58
     case KZG_T_LZ: case KZG_T_LZX:
       if (forward) { if (dstLen < ((srcLen <= 1024 ? srcLen + 16 : srcLen + srcLen / 64) + 2)) return 0; }   // LZCodec.java:309-310
+      return 1;
+    case KZG_T_LZP:
+      if (forward) { if (dstLen < ((srcLen <= 1024) ? srcLen + 16 : srcLen + srcLen / 64) || srcLen < 128) return 0; }     // LZCodec.java:1013-1018
+      else if (dstLen < srcLen) return 0;                                                                                    // :1140-1141
       return 1;
     case KZG_T_ROLZ:
       if (forward) { if (srcLen < 64 || srcLen > (1 << 30)) return 0; if (dstLen < ((srcLen <= 512) ? srcLen + 64 : srcLen)) return 0; }   // ROLZCodec.java:207-212,426-428

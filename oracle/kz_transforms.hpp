@@ -1,7 +1,7 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see kz_core.hpp header).  parity unpinned for bitstreams;
 // BWT pinned by the 'mississippi' KAT (BWT.java:45-50).
 //
-// Transform stage: Null, LZ (LZXCodec, extra=false/true), ROLZ (ROLZCodec1), BWTBlockCodec + BWT,
+// Transform stage: Null, LZ (LZXCodec, extra=false/true), LZP (LZPCodec), ROLZ (ROLZCodec1), BWTBlockCodec + BWT,
 // SBRT (RANK/MTFT), SRT, ZRLT, Sequence, TransformFactory.
 #pragma once
 #include "kz_core.hpp"
@@ -1296,12 +1296,146 @@ struct ROLZ1 : Transform {
   }
 };
 
+// ---- LZPCodec (transform/LZCodec.java:973-1287; selected by ctx["lz"] == LZP_TYPE, LZCodec.java:57-58) ------------------
+// bsVersion >= 4 everywhere on this path, so minMatch is 64 both ways (LZCodec.java:988-997, 1137).
+struct LZP : Transform {
+  enum { HASH_SEED = 0x7FEB352D, HASH_LOG = 16, HASH_SHIFT = 32 - HASH_LOG, MIN_MATCH64 = 64, MIN_BLOCK_LENGTH = 128, MATCH_FLAG = 0xFC };
+  std::vector<i32> hashes;
+  static int findMatch(const u8* src, int srcIdx, int ref, int maxMatch) {       // :1267-1280
+    int bestLen = 0;
+    while (bestLen + 8 <= maxMatch) {
+      const u64 diff = le64(src + srcIdx + bestLen) ^ le64(src + ref + bestLen);
+      if (diff != 0) { bestLen += (__builtin_ctzll(diff) >> 3); break; }
+      bestLen += 8;
+    }
+    return bestLen;
+  }
+  // forward, :1003-1118
+  bool forward(Slice& input, Slice& output) override {
+    if (input.length == 0) return true;
+    if (!basicCheck(input, output)) return false;
+    const int count = input.length;
+    if (output.length - output.index < getMaxEncodedLength(count)) return false;
+    if (count < MIN_BLOCK_LENGTH) return false;
+    hashes.assign(1 << HASH_LOG, 0);
+    const int srcIdx0 = input.index, dstIdx0 = output.index;
+    const u8* src = input.p(); u8* dst = output.p();
+    const int dstCap = output.cap();
+    auto put = [&](int i, int v) { if (i < 0 || i >= dstCap) throw JavaException("AIOOBE in LZP.forward"); dst[i] = (u8)v; };
+    const int srcEnd = srcIdx0 + count;
+    const int dstEnd = dstIdx0 + count - (count >> 6);
+    int srcIdx = srcIdx0, dstIdx = dstIdx0;
+    for (int k = 0; k < 4; k++) put(dstIdx + k, src[srcIdx + k]);
+    u32 ctx = le32(src + srcIdx);
+    srcIdx += 4; dstIdx += 4;
+    const int minMatch = MIN_MATCH64;
+    while ((srcIdx < srcEnd - minMatch) && (dstIdx < dstEnd)) {
+      const u32 h = ((u32)HASH_SEED * ctx) >> HASH_SHIFT;
+      const int ref = hashes[h];
+      hashes[h] = srcIdx;
+      int bestLen = 0;
+      if ((ref != 0) && (le32(src + ref + minMatch - 4) == le32(src + srcIdx + minMatch - 4)))
+        bestLen = findMatch(src, srcIdx, ref, srcEnd - srcIdx);
+      if (bestLen < minMatch) {
+        const int val = src[srcIdx];
+        ctx = (ctx << 8) | (u32)val;
+        put(dstIdx++, src[srcIdx++]);
+        if ((ref != 0) && (val == MATCH_FLAG)) {
+          if (dstIdx >= dstEnd) return false;
+          put(dstIdx++, 0xFF);
+        }
+        continue;
+      }
+      srcIdx += bestLen;
+      ctx = le32(src + srcIdx - 4);
+      put(dstIdx++, MATCH_FLAG);
+      bestLen -= minMatch;
+      while (bestLen >= 254) {
+        bestLen -= 254;
+        put(dstIdx++, 0xFE);
+        if (dstIdx >= dstEnd) break;
+      }
+      if (dstIdx >= dstEnd) return false;
+      put(dstIdx++, bestLen);
+    }
+    while ((srcIdx < srcEnd) && (dstIdx < dstEnd)) {
+      const u32 h = ((u32)HASH_SEED * ctx) >> HASH_SHIFT;
+      const int ref = hashes[h];
+      hashes[h] = srcIdx;
+      const int val = src[srcIdx];
+      ctx = (ctx << 8) | (u32)val;
+      put(dstIdx++, src[srcIdx++]);
+      if ((ref != 0) && (val == MATCH_FLAG)) {
+        if (dstIdx >= dstEnd) return false;
+        put(dstIdx++, 0xFF);
+      }
+    }
+    input.index = srcIdx; output.index = dstIdx;
+    return (srcIdx == srcIdx0 + count) && (dstIdx < dstEnd);
+  }
+  // inverse, :1121-1263
+  bool inverse(Slice& input, Slice& output) override {
+    if (input.length == 0) return true;
+    if (!basicCheck(input, output)) return false;
+    const int count = input.length;
+    const u8* src = input.p(); u8* dst = output.p();
+    const int srcCap = input.cap(), dstCap = output.cap();
+    auto get = [&](int i) -> int { if (i < 0 || i >= srcCap) throw JavaException("AIOOBE in LZP.inverse"); return src[i]; };
+    auto put = [&](int i, int v) { if (i < 0 || i >= dstCap) throw JavaException("AIOOBE in LZP.inverse"); dst[i] = (u8)v; };
+    const int srcEnd = input.index + count;
+    const int dstEnd = output.length;
+    int srcIdx = input.index, dstIdx = output.index;
+    const int minMatch = MIN_MATCH64;
+    if (output.length - output.index < count) return false;
+    hashes.assign(1 << HASH_LOG, 0);
+    for (int k = 0; k < 4; k++) put(dstIdx + k, get(srcIdx + k));
+    u32 ctx = le32(dst + dstIdx);
+    srcIdx += 4; dstIdx += 4;
+    while (srcIdx < srcEnd) {
+      const u32 h = ((u32)HASH_SEED * ctx) >> HASH_SHIFT;
+      const int ref = hashes[h];
+      hashes[h] = dstIdx;
+      if ((ref == 0) || (src[srcIdx] != MATCH_FLAG)) {
+        if (dstIdx >= dstEnd) return false;
+        put(dstIdx, src[srcIdx]);
+        ctx = (ctx << 8) | (u32)dst[dstIdx];
+        srcIdx++; dstIdx++;
+        continue;
+      }
+      srcIdx++;
+      if (srcIdx >= srcEnd) return false;
+      if (src[srcIdx] == 0xFF) {
+        if (dstIdx >= dstEnd) return false;
+        put(dstIdx, MATCH_FLAG);
+        ctx = (ctx << 8) | (u32)MATCH_FLAG;
+        srcIdx++; dstIdx++;
+        continue;
+      }
+      int mLen = minMatch;
+      if (src[srcIdx] == 0xFE) {
+        while ((srcIdx < srcEnd) && (src[srcIdx] == 0xFE)) { srcIdx++; mLen += 254; }
+        if (srcIdx >= srcEnd) return false;
+      }
+      mLen += src[srcIdx++];
+      if (dstIdx + mLen > dstEnd) return false;
+      if (dstIdx + mLen > dstCap) throw JavaException("AIOOBE in LZP.inverse");
+      for (int i = 0; i < mLen; i++) dst[dstIdx + i] = dst[ref + i];
+      dstIdx += mLen;
+      ctx = le32(dst + dstIdx - 4);
+    }
+    input.index = srcIdx; output.index = dstIdx;
+    return srcIdx == srcEnd;
+  }
+  int getMaxEncodedLength(int srcLen) override { return (srcLen <= 1024) ? srcLen + 16 : srcLen + (srcLen / 64); }   // :1283-1285
+};
+
 // ---- TransformFactory.newFunctionToken (TransformFactory.java:273-351) -------------------------------
 static inline std::unique_ptr<Transform> newTransform(Ctx& ctx, int type) {
   switch (type) {
     case T_NONE: return std::unique_ptr<Transform>(new NullTransform());
     case T_LZ: ctx.lzType = T_LZ; return std::unique_ptr<Transform>(new LZX(&ctx, false));
     case T_LZX: ctx.lzType = T_LZX; return std::unique_ptr<Transform>(new LZX(&ctx, true));
+    case T_LZP: ctx.lzType = T_LZP; return std::unique_ptr<Transform>(new LZP());
     case T_ROLZ: return std::unique_ptr<Transform>(new ROLZ1(&ctx));
     case T_BWT: return std::unique_ptr<Transform>(new BWTBlockCodec(ctx));
     case T_RANK: ctx.sbrtMode = 2; return std::unique_ptr<Transform>(new SBRT(2));

@@ -1,0 +1,78 @@
+"""GPU parity of the sibling codecs added after the five BASELINE chains: LZP so far
+(K/transform/LZCodec.java:973-1287), against the oracle through the C ABI, bit for bit.  The same checks, torch-free, are what
+tests/native/kzg_sibling_check.c runs (profiles/r02_sibling_check_lzp.log is its output on a B200)."""
+import numpy as np
+import pytest
+import kanzi_b200 as K
+import oracle_lib as O
+import corpus
+from kanzi_b200 import synth
+from test_lzp_hostcheck import _inputs as lzp_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+def first_diff(a, b):
+    n = min(len(a), len(b))
+    x = np.frombuffer(a[:n], dtype=np.uint8) != np.frombuffer(b[:n], dtype=np.uint8)
+    return int(np.argmax(x)) if x.any() else n
+
+
+def pasted_text(n, seed):
+    """prose-like bytes with long passages pasted again further on (what LZP codes as matches) and flag bytes sprinkled in"""
+    r = np.random.default_rng(seed)
+    a = bytearray(synth.text(n, seed).tobytes())
+    for _ in range(n // 3000):
+        src, ln, dst = int(r.integers(0, n - 2000)), int(r.integers(70, 1900)), int(r.integers(0, n - 2000))
+        a[dst:dst + ln] = a[src:src + ln]
+    for _ in range(n // 5000):
+        a[int(r.integers(0, n))] = int(r.choice([0xFC, 0xFE, 0xFF]))
+    return bytes(a)
+
+
+def test_lzp_transform_bit_exact():
+    applied = 0
+    cases = list(corpus.small_cases().values()) + lzp_inputs() + [pasted_text(1_000_003, 9)]
+    for d in cases:
+        cap = len(d) + len(d) // 64 + 1100
+        ok_ref, ref, _, _ = O.transform("LZP", d, dst_cap=cap, ctx=[7, max(len(d), 1024), len(d), 1, 0, 0])
+        kctx = {"blockSize": max(len(d), 1024), "size": len(d), "flags": 0}
+        ok, got, used = K.transform_forward("LZP", d, kctx, dst_cap=cap)
+        assert int(ok) == ok_ref, (len(d), ok, ok_ref)
+        if not ok:
+            continue
+        applied += 1
+        assert used == len(d) and got == ref, (len(d), len(got), len(ref), "first differing byte", first_diff(got, ref))
+        ok2, back, used2 = K.transform_inverse("LZP", ref, {"blockSize": max(len(d), 1024), "flags": 0}, dst_cap=len(d))
+        assert ok2 and back == d and used2 == len(ref), (len(d), first_diff(back, d))
+        # LZPCodec.inverse bounds its output by the destination slice: one byte short is a refusal, as in the oracle
+        if len(d) > 200:
+            assert O.transform("LZP", ref, inverse=True, dst_cap=len(d) - 1, dst_len=len(d) - 1)[0] == 0
+            assert not K.transform_inverse("LZP", ref, {"blockSize": max(len(d), 1024), "flags": 0}, dst_cap=len(d) - 1)[0]
+    assert applied >= 40
+
+
+def test_lzp_inverse_of_corrupt_streams_fails_like_the_oracle():
+    r = np.random.default_rng(3)
+    d = pasted_text(120_000, 4)
+    ok, ref, _, _ = O.transform("LZP", d)
+    assert ok == 1
+    for k in range(24):
+        bad = bytearray(ref)
+        for _ in range(1 + k % 3):
+            bad[int(r.integers(4, len(bad)))] = int(r.choice([0xFC, 0xFE, 0xFF, 0x00, int(r.integers(0, 256))]))
+        o = O.transform("LZP", bytes(bad), inverse=True, dst_cap=len(d), dst_len=len(d))
+        g = K.transform_inverse("LZP", bytes(bad), {"blockSize": len(d), "flags": 0}, dst_cap=len(d))
+        assert bool(g[0]) == (o[0] == 1), k
+        if g[0]:
+            assert g[1] == o[1]
+    assert K.transform_inverse("LZP", ref, {"blockSize": len(d), "flags": 0}, dst_cap=len(d))[1] == d      # no sticky error
+
+
+@pytest.mark.parametrize("tr,ent,bs", [(["LZP"], "ANS0", 1 << 20), (["LZP", "ZRLT"], "HUFFMAN", 1 << 18), (["LZP"], "NONE", 1 << 16), (["ROLZ", "LZP"], "ANS0", 1 << 19)])
+def test_lzp_streams_bit_exact(tr, ent, bs):
+    d = pasted_text(2_500_000, 11) + synth.noise(150_000, 4).tobytes() + bytes(70000) + b"tail!"
+    ref = O.compress(d, tr, ent, bs)
+    got = K.compress(d, tr, ent, bs, flags=K.FLAG_BWT_ASREF)
+    assert len(got) == len(ref) and got == ref, (tr, ent, len(got), len(ref), "first differing byte", first_diff(got, ref))
+    assert K.decompress(ref, len(d) + 1024, flags=K.FLAG_BWT_ASREF) == d

@@ -1190,3 +1190,157 @@ def test_block_framing_agrees_with_the_oracle(transforms, entropy, bs, checksum)
         ref = O.compress(d, transforms, entropy, bs, checksum=checksum)
         hl = len(O.stream_header(transforms, entropy, bs, len(d)))
         assert ref[hl:] == frame_blocks(d, transforms, entropy, bs, checksum, hl), (len(d), transforms)
+
+
+# ---- LZP: K/transform/LZCodec.java:1003-1118 (forward), :1121-1263 (inverse), findMatch :1267-1280 ---------------------------
+def lzp_forward(src):
+    """-> (ok, out)"""
+    M32 = 0xFFFFFFFF
+    count = len(src)
+    if count == 0:
+        return True, b""
+    if count < 128:
+        return False, b""
+    hashes = [0] * 65536
+    dst = bytearray(count + (16 if count <= 1024 else count // 64))
+    src_end, dst_end = count, count - (count >> 6)
+    dst[0:4] = src[0:4]
+    ctx = int.from_bytes(src[0:4], "little")
+    si = di = 4
+    while si < src_end - 64 and di < dst_end:
+        h = ((0x7FEB352D * ctx) & M32) >> 16
+        ref = hashes[h]
+        hashes[h] = si
+        best = 0
+        if ref != 0 and src[ref + 60:ref + 64] == src[si + 60:si + 64]:
+            mx = src_end - si
+            while best + 8 <= mx:
+                a, b = src[si + best:si + best + 8], src[ref + best:ref + best + 8]
+                if a != b:
+                    best += next(k for k in range(8) if a[k] != b[k])
+                    break
+                best += 8
+        if best < 64:
+            val = src[si]
+            ctx = ((ctx << 8) | val) & M32
+            dst[di] = val
+            di += 1
+            si += 1
+            if ref != 0 and val == 0xFC:
+                if di >= dst_end:
+                    return False, b""
+                dst[di] = 0xFF
+                di += 1
+            continue
+        si += best
+        ctx = int.from_bytes(src[si - 4:si], "little")
+        dst[di] = 0xFC
+        di += 1
+        best -= 64
+        while best >= 254:
+            best -= 254
+            dst[di] = 0xFE
+            di += 1
+            if di >= dst_end:
+                break
+        if di >= dst_end:
+            return False, b""
+        dst[di] = best
+        di += 1
+    while si < src_end and di < dst_end:
+        h = ((0x7FEB352D * ctx) & M32) >> 16
+        ref = hashes[h]
+        hashes[h] = si
+        val = src[si]
+        ctx = ((ctx << 8) | val) & M32
+        dst[di] = val
+        di += 1
+        si += 1
+        if ref != 0 and val == 0xFC:
+            if di >= dst_end:
+                return False, b""
+            dst[di] = 0xFF
+            di += 1
+    return si == count and di < dst_end, bytes(dst[:di])
+
+
+def lzp_inverse(src, dst_end):
+    """-> (ok, out); dst_end = the destination slice's length"""
+    M32 = 0xFFFFFFFF
+    count = len(src)
+    if count == 0:
+        return True, b""
+    if dst_end < count:
+        return False, b""
+    hashes = [0] * 65536
+    dst = bytearray(src[0:4])
+    ctx = int.from_bytes(dst[0:4], "little")
+    si = 4
+    while si < count:
+        h = ((0x7FEB352D * ctx) & M32) >> 16
+        ref = hashes[h]
+        hashes[h] = len(dst)
+        if ref == 0 or src[si] != 0xFC:
+            if len(dst) >= dst_end:
+                return False, bytes(dst)
+            dst.append(src[si])
+            ctx = ((ctx << 8) | src[si]) & M32
+            si += 1
+            continue
+        si += 1
+        if si >= count:
+            return False, bytes(dst)
+        if src[si] == 0xFF:
+            if len(dst) >= dst_end:
+                return False, bytes(dst)
+            dst.append(0xFC)
+            ctx = ((ctx << 8) | 0xFC) & M32
+            si += 1
+            continue
+        m_len = 64
+        if src[si] == 0xFE:
+            while si < count and src[si] == 0xFE:
+                si += 1
+                m_len += 254
+            if si >= count:
+                return False, bytes(dst)
+        m_len += src[si]
+        si += 1
+        if len(dst) + m_len > dst_end:
+            return False, bytes(dst)
+        for i in range(m_len):
+            dst.append(dst[ref + i])
+        ctx = int.from_bytes(dst[-4:], "little")
+    return si == count, bytes(dst)
+
+
+def _lzp_cases():
+    from kanzi_b200 import synth
+    r = np.random.default_rng(41)
+    t = synth.text(20000, 5).tobytes()
+    noise = bytes(r.integers(0, 256, 3000, dtype=np.uint8))
+    flags = bytes(r.choice(np.array([0xFC, 0xFE, 0xFF, 0x41], dtype=np.uint8), 2000))
+    return [t + t[500:9000] + t[:6000], noise + noise + flags + noise[:1500] + flags, bytes(5000), (b"0123456789abcdef" * 7 + b"\xfc") * 300,
+            synth.records(30000, 7).tobytes(), noise, b"\xfc" * 700, t[:127], t[:128], (noise[:300] + b"\xfc\xfc") * 40, synth.exe_like(30000, 6).tobytes() * 2]
+
+
+def test_lzp_agrees_with_the_oracle_both_ways():
+    applied = 0
+    for d in _lzp_cases():
+        ok_ref, ref, used, _ = O.transform("LZP", d)
+        ok, got = lzp_forward(d)
+        assert int(ok) == ok_ref, (len(d), ok, ok_ref)
+        if not ok:
+            continue
+        applied += 1
+        assert got == ref and used == len(d)
+        ok_i, back_ref, used_i, _ = O.transform("LZP", ref, inverse=True, dst_cap=len(d), dst_len=len(d))
+        ok_p, back = lzp_inverse(ref, len(d))
+        assert ok_i == 1 and ok_p and back_ref == d and back == d and used_i == len(ref)
+        # a destination one byte short fails the same way in both; a truncated stream is accepted or refused alike
+        assert O.transform("LZP", ref, inverse=True, dst_cap=len(d) - 1, dst_len=len(d) - 1)[0] == int(lzp_inverse(ref, len(d) - 1)[0]) == 0
+        cut = ref[:len(ref) * 2 // 3]
+        o2 = O.transform("LZP", cut, inverse=True, dst_cap=len(d), dst_len=len(d))
+        p2 = lzp_inverse(cut, len(d))
+        assert o2[0] == int(p2[0]) and (not p2[0] or o2[1] == p2[1])
+    assert applied >= 6
