@@ -21,7 +21,7 @@ extern "C" {
 /* ---- ids ------------------------------------------------------------------------------------ */
 /* transform ids: K/transform/TransformFactory.java:36-58 */
 enum {
-  KZG_T_NONE = 0, KZG_T_BWT = 1, KZG_T_LZ = 3, KZG_T_ZRLT = 6, KZG_T_MTFT = 7, KZG_T_RANK = 8,
+  KZG_T_NONE = 0, KZG_T_BWT = 1, KZG_T_LZ = 3, KZG_T_RLT = 5, KZG_T_ZRLT = 6, KZG_T_MTFT = 7, KZG_T_RANK = 8,
   KZG_T_ROLZ = 11, KZG_T_SRT = 13, KZG_T_LZP = 14, KZG_T_LZX = 16
 };
 /* entropy ids: K/entropy/EntropyCodecFactory.java:38-47 */
@@ -54,6 +54,9 @@ typedef struct kzg_ctx {
   int32_t flags;
 } kzg_ctx;
 #define KZG_FLAG_BWT_ASREF 1
+/* ctx.flags bits 8-11, per-block transform calls only: ctx["entropy"] as KZG_E_* id + 1 (0 = key absent, read as "NONE").  RLT.forward
+ * chooses its escape byte by it (K/transform/RLT.java:101-107); kzg_compress* passes the stream's entropy codec itself. */
+#define KZG_CTX_ENTROPY(e) ((((e) + 1) & 0xF) << 8)
 /* kzg_compress* only: per-block checksum of the original bytes, ctx["checksum"] = 32 / 64 (CompressedOutputStream.java:193-204,
  * 745-755): K/util/hash/XXHash32.java (the published XXH32) / XXHash64.java (Kanzi's variant), seed 0x4B414E5A.  kzg_decompress*
  * reads the kind from the stream header and verifies every block (-KZG_ERR_CRC_CHECK on a mismatch). */
@@ -77,7 +80,7 @@ int64_t kzg_launch_count(int reset);
  * Returns 1 = true, 0 = false (transform skipped / recoverable), < 0 = -KZG_ERR_*.
  * On return *srcUsed / *dstUsed are the slices' new indexes (bytes consumed / produced).
  * getMaxEncodedLength: BWTBlockCodec.java:222-224 (n+33), LZCodec.java:961-964 (LZ, LZX), :1283-1285 (LZP), ROLZCodec.java:1001-1003,
- * SBRT/ZRLT n, SRT.java:364-366 (n+1024). */
+ * SBRT/ZRLT n, SRT.java:364-366 (n+1024), RLT.java:355-357. */
 int kzg_transform_forward(int type, kzg_ctx* ctx, const uint8_t* src, int32_t srcLen, uint8_t* dst, int32_t dstLen,
                           int32_t dstCap, int32_t* srcUsed, int32_t* dstUsed);
 int kzg_transform_inverse(int type, kzg_ctx* ctx, const uint8_t* src, int32_t srcLen, uint8_t* dst, int32_t dstLen,

@@ -36,6 +36,20 @@ public final class GpuTransform implements ByteTransform {
       this.ctx[1] = (ctx == null) ? 0 : (Integer) ctx.getOrDefault("blockSize", 0);
       this.ctx[3] = (ctx == null) ? 1 : (Integer) ctx.getOrDefault("jobs", 1);
       this.ctx[5] = FLAG_BWT_ASREF;
+      // ctx["entropy"] for RLT's choice of escape byte (RLT.java:101-107): KZG_CTX_ENTROPY(id) = (id + 1) << 8, 0 = key absent
+      if ((ctx != null) && ctx.containsKey("entropy")) {
+         int id = 14;                               // a codec this library has no id for (CM, TPAQ ...): "not one of the four plain ones"
+         switch (String.valueOf(ctx.get("entropy")).toUpperCase()) {
+            case "NONE": id = 0; break;
+            case "HUFFMAN": id = 1; break;
+            case "FPAQ": id = 2; break;
+            case "RANGE": id = 4; break;
+            case "ANS0": id = 5; break;
+            case "ANS1": id = 8; break;
+            default: break;
+         }
+         this.ctx[5] |= ((id + 1) & 0xF) << 8;
+      }
    }
 
    static native int configure0(int device, int maxBatch, int windowMicros);

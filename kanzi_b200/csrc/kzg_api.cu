@@ -143,7 +143,7 @@ struct EvSet {
 // ---- ids / sizes (TransformFactory, getMaxEncodedLength of each codec) --------------------------------------
 static bool xf_known(int t) {
   switch (t) { case KZG_T_NONE: case KZG_T_LZ: case KZG_T_LZX: case KZG_T_ROLZ: case KZG_T_BWT: case KZG_T_RANK: case KZG_T_MTFT:
-               case KZG_T_SRT: case KZG_T_ZRLT: case KZG_T_LZP: return true; default: return false; }
+               case KZG_T_SRT: case KZG_T_ZRLT: case KZG_T_LZP: case KZG_T_RLT: return true; default: return false; }
 }
 static bool ent_known(int e) {
   switch (e) { case KZG_E_NONE: case KZG_E_HUFFMAN: case KZG_E_ANS0: case KZG_E_ANS1: case KZG_E_FPAQ: return true; default: return false; }
@@ -152,6 +152,7 @@ static i32 xf_max_len(int t, i32 n) {
   switch (t) {
     case KZG_T_LZ: case KZG_T_LZX: return ((n <= 1024) ? n + 16 : n + (n / 64)) + 2;   // LZCodec.java:961-964
     case KZG_T_LZP: return (n <= 1024) ? n + 16 : n + (n / 64);                       // LZCodec.java:1283-1285
+    case KZG_T_RLT: return (n <= 512) ? n + 32 : n;                                   // RLT.java:355-357
     case KZG_T_ROLZ: return (n <= 512) ? n + 64 : n;                                  // ROLZCodec.java:1001-1003
     case KZG_T_BWT: return n + 33;                                                    // BWTBlockCodec.java:222-224
     case KZG_T_SRT: return n + 1024;                                                  // SRT.java:364-366
@@ -225,7 +226,7 @@ static int run_transform_stage(Batch& bt, int type, int stage, bool forward, con
   KzgXfParams P;
   P.result = bt.dResult; P.enabled = bt.dEnabled; P.dstLimit = bt.dDstLimit;
   P.scratch = dScratch; P.scratchStride = (i64)xs.perBlock; P.tkStride = xs.tk; P.mStride = xs.m; P.mLenStride = xs.ml;
-  P.hashBuf = dHash; P.aux32 = dAux32; P.aux32Stride = (i64)xs.aux32; P.flags = flags;
+  P.hashBuf = dHash; P.aux32 = dAux32; P.aux32Stride = (i64)xs.aux32; P.flags = (type == KZG_T_RLT) ? flags : (flags & ~0xF00);   // bits 8-11: ctx["entropy"] + 1, RLT only
   const bool lazy = forward && stage == 0 && bt.lazyHost && (type == KZG_T_LZ || type == KZG_T_LZX);
   P.lazyHost = lazy ? bt.lazyHost : nullptr; P.lazyDev = bt.lazyDev; P.lazyN = bt.lazyN; P.lazyBlock = bt.lazyBlock;
   int r = 0;
@@ -482,9 +483,10 @@ static int transform_batch(std::vector<KzgReq*>& rq) {
     KzgReq& Q = *rq[live[k]];
     KzgBlock& B = bt.hBlocks[k];
     memset(&B, 0, sizeof(B));
-    B.cur = dA + k * cap; B.alt = dB + k * cap; B.curLen = Q.srcLen; B.cap = forward ? Q.dstLen : Q.dstCap; B.origLen = Q.srcLen; B.skipFlags = 0xFF;
+    B.cur = dA + k * cap; B.alt = dB + k * cap; B.curLen = Q.srcLen; B.cap = (forward && type != KZG_T_RLT) ? Q.dstLen : Q.dstCap; B.origLen = Q.srcLen; B.skipFlags = 0xFF;
     B.dataType = Q.ctx ? Q.ctx->dataType : 0; B.aux0 = nullptr; B.aux1 = B.cur; B.stagesLeft = 2;
-    bt.hEnabled[k] = 1; bt.hDstLimit[k] = (forward || type == KZG_T_LZP) ? Q.dstLen : Q.dstCap;     // (LZP.inverse bounds its output by dst.length, LZCodec.java:1133)
+    // dst.length of the slice, except where the codec looks at dst.array.length: every inverse but LZP's (LZCodec.java:1133) and RLT.forward (RLT.java:117)
+    bt.hEnabled[k] = 1; bt.hDstLimit[k] = ((forward && type != KZG_T_RLT) || type == KZG_T_LZP) ? Q.dstLen : Q.dstCap;
     if (!cu(cudaMemsetAsync(B.cur + Q.srcLen, 0, cap - Q.srcLen, W.stream)) || !cu(cudaMemcpyAsync(B.cur, Q.src, Q.srcLen, cudaMemcpyHostToDevice, W.stream)))
       return failAll(-KZG_ERR_PROCESS_BLOCK);
   }
@@ -892,7 +894,7 @@ static int64_t compress_impl(const uint8_t* d_in, int64_t n, const int32_t* tran
     // Sequence.forward: a NONE-only chain is a copy that always succeeds (NullTransform) -> skip bit 7 cleared
     for (int i = 0; i < nf; i++) {
       if (fn[i] == KZG_T_NONE) { r = kzg_null_forward_launch(W.stream, bt.dBlocks, cnt, bt.dEnabled, i); if (r < 0) return r; continue; }
-      r = run_transform_stage(bt, fn[i], i, true, xs, dScratch, dHash, dAux, flags); if (r < 0) return r;
+      r = run_transform_stage(bt, fn[i], i, true, xs, dScratch, dHash, dAux, (flags & ~0xF00) | KZG_CTX_ENTROPY(entropy)); if (r < 0) return r;
     }
     if (timing3) CUDA_TRY(cudaEventRecord(ev[1], W.stream));
     r = run_entropy_encode(bt, entropy, es, dHdr, dPay, dTab, dSegs); if (r < 0) return r;

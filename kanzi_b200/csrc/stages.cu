@@ -98,6 +98,7 @@ int kzg_stage_launch(cudaStream_t s, int type, bool forward, KzgBlock* d_blocks,
     case KZG_T_BWT: return kzg_bwtblock_launch(s, forward, d_blocks, nBlocks, P, maxLen);
     case KZG_T_ROLZ: return kzg_rolz_launch(s, forward, d_blocks, nBlocks, P, maxLen);
     case KZG_T_LZP: return kzg_lzp_launch(s, forward, d_blocks, nBlocks, P, maxLen);
+    case KZG_T_RLT: return kzg_rlt_launch(s, forward, d_blocks, nBlocks, P, maxLen);
     default: kzg_set_error("transform id %d has no kernel", type); return -KZG_ERR_INVALID_CODEC;
   }
 }
@@ -110,6 +111,9 @@ int kzg_stage_precheck(int type, bool forward, const kzg_ctx* ctx, i32 srcLen, i
     case KZG_T_NONE: return (dstLen < srcLen) ? 0 : 1;                                   // NullTransform.java:57-58
     case KZG_T_LZ: case KZG_T_LZX:
       if (forward) { if (dstLen < ((srcLen <= 1024 ? srcLen + 16 : srcLen + srcLen / 64) + 2)) return 0; }   // LZCodec.java:309-310
+      return 1;
+    case KZG_T_RLT:
+      if (forward && (srcLen < 16 || dstLen < ((srcLen <= 512) ? srcLen + 32 : srcLen))) return 0;                          // RLT.java:71-80
       return 1;
     case KZG_T_LZP:
       if (forward) { if (dstLen < ((srcLen <= 1024) ? srcLen + 16 : srcLen + srcLen / 64) || srcLen < 128) return 0; }     // LZCodec.java:1013-1018

@@ -46,7 +46,7 @@ int32_t kzo_entropy_decode(int type, const uint8_t* in, int64_t inBits, uint8_t*
 int kzo_transform(int type, int inverse, int32_t* ctxv, const uint8_t* src, int32_t srcLen, int32_t srcCap,
                   uint8_t* dst, int32_t dstLen, int32_t dstCap, int32_t* srcUsed, int32_t* dstUsed) {
   try {
-    Ctx ctx; ctx.bsVersion = ctxv[0]; ctx.blockSize = ctxv[1]; ctx.size = ctxv[2]; ctx.jobs = ctxv[3]; ctx.dataType = ctxv[4]; ctx.bwtBounds = ctxv[5];
+    Ctx ctx; ctx.bsVersion = ctxv[0]; ctx.blockSize = ctxv[1]; ctx.size = ctxv[2]; ctx.jobs = ctxv[3]; ctx.dataType = ctxv[4]; ctx.bwtBounds = ctxv[5] & 0xFF; ctx.entropyType = (ctxv[5] >> 8) & 0xFF;
     std::vector<u8> sv(src, src + srcCap), dv((size_t)dstCap, 0);
     Slice s(&sv, srcLen, 0), d(&dv, dstLen, 0);
     std::unique_ptr<Transform> t = newTransform(ctx, type);
@@ -67,7 +67,7 @@ int32_t kzo_transform_max_encoded_len(int type, int32_t n) {
 int32_t kzo_sequence_forward(const int32_t* ids, int nIds, int32_t blockSize, int bwtBounds, const uint8_t* src, int32_t n,
                              uint8_t* dst, int32_t dstCap, int32_t* skipFlags) {
   try {
-    Ctx ctx; ctx.blockSize = blockSize; ctx.size = n; ctx.bwtBounds = bwtBounds;
+    Ctx ctx; ctx.blockSize = blockSize; ctx.size = n; ctx.bwtBounds = bwtBounds & 0xFF; ctx.entropyType = (bwtBounds >> 8) & 0xFF;
     int idv[8]; for (int i = 0; i < nIds; i++) idv[i] = ids[i];
     Sequence seq(ctx, transformTypeOf(idv, nIds));
     EncodeBuffers eb(std::max(blockSize, n));

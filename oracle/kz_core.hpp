@@ -141,6 +141,7 @@ struct Ctx {
   i32 sbrtMode = 0;
   i32 rolzExtra = 0;             // transform string is ROLZX
   i32 bwtBounds = 0;             // 0 = "fixed" (ignore the BWT.java:152-156 clause), 1 = "asref" 
+  i32 entropyType = 0;           // ctx["entropy"] as an id (absent = "NONE"); RLT.forward reads it (RLT.java:101-107)
 };
 
 // transform ids (TransformFactory.java:36-112) and entropy ids (EntropyCodecFactory.java:38-74)

@@ -179,6 +179,7 @@ static inline void encodeBlock(BitWriter& obs, EncodeBuffers& eb, int blockLengt
   if (blockLength == 0) return;
   Slice& data = eb.data; Slice& buffer = eb.buffer;
   Ctx ctx; ctx.bsVersion = BITSTREAM_FORMAT_VERSION; ctx.blockSize = sp.blockSize; ctx.jobs = 1; ctx.bwtBounds = sp.bwtBounds;
+  ctx.entropyType = sp.entropyType;             // the stream's ctx["entropy"] (COS:147), also for copy blocks
   int mode = 0;
   u64 blockTransformType = sp.transformType; int blockEntropyType = sp.entropyType;
   if (blockLength <= SMALL_BLOCK_SIZE) { blockTransformType = 0; blockEntropyType = E_NONE; mode |= COPY_BLOCK_MASK; }

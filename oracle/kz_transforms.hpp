@@ -1296,6 +1296,179 @@ struct ROLZ1 : Transform {
   }
 };
 
+// ---- RLT (transform/RLT.java) ---------------------------------------------------------------------------------------------------
+struct RLT : Transform {
+  enum { RUN_LEN_ENCODE1 = 224, RUN_LEN_ENCODE2 = (255 - RUN_LEN_ENCODE1) << 8, RUN_THRESHOLD = 3,
+         MAX_RUN = 0xFFFF + RUN_LEN_ENCODE2 + RUN_THRESHOLD - 1, MAX_RUN4 = MAX_RUN - 4, DEFAULT_ESCAPE = 0xFB };
+  Ctx* ctx;
+  explicit RLT(Ctx* c) : ctx(c) {}
+  static int emitRunLength(u8* dst, int dstCap, int dstIdx, int run) {       // RLT.java:233-249
+    auto put = [&](int i, int v) { if (i < 0 || i >= dstCap) throw JavaException("AIOOBE in RLT.emitRunLength"); dst[i] = (u8)v; };
+    run -= RUN_THRESHOLD;
+    if (run >= RUN_LEN_ENCODE1) {
+      if (run < RUN_LEN_ENCODE2) { run -= RUN_LEN_ENCODE1; put(dstIdx++, RUN_LEN_ENCODE1 + (run >> 8)); }
+      else { run -= RUN_LEN_ENCODE2; put(dstIdx++, 0xFF); put(dstIdx++, run >> 8); }
+    }
+    put(dstIdx, run);
+    return dstIdx + 1;
+  }
+  // forward, RLT.java:62-231
+  bool forward(Slice& input, Slice& output) override {
+    if (input.length == 0) return true;
+    if (!basicCheck(input, output)) return false;
+    if (input.length < 16) return false;
+    if (input.arr == output.arr) return false;
+    const int count = input.length;
+    if (output.length - output.index < getMaxEncodedLength(count)) return false;
+    const u8* src = input.p(); u8* dst = output.p();
+    const int srcCap = input.cap(), dstCap = output.cap();
+    auto get = [&](int i) -> int { if (i < 0 || i >= srcCap) throw JavaException("AIOOBE in RLT.forward"); return src[i]; };
+    auto put = [&](int i, int v) { if (i < 0 || i >= dstCap) throw JavaException("AIOOBE in RLT.forward"); dst[i] = (u8)v; };
+    int dt = DT_UNDEFINED;
+    bool findBestEscape = true;
+    if (ctx != nullptr) {
+      dt = ctx->dataType;
+      if ((dt == DT_DNA) || (dt == DT_BASE64) || (dt == DT_UTF8)) return false;
+      const int e = ctx->entropyType;
+      if (e == E_NONE || e == E_ANS0 || e == E_HUFFMAN || e == E_RANGE) findBestEscape = false;
+    }
+    int escape = DEFAULT_ESCAPE;
+    int srcIdx = input.index, dstIdx = output.index;
+    const int srcEnd = srcIdx + count, srcEnd4 = srcEnd - 4;
+    const int dstEnd = dstCap;
+    if (findBestEscape) {
+      int freqs[257];
+      histogramOrder0(src, srcIdx, srcEnd, freqs, false);
+      if (dt == DT_UNDEFINED) {
+        dt = detectSimpleType(count, freqs);
+        if ((ctx != nullptr) && (dt != DT_UNDEFINED)) ctx->dataType = dt;
+        if ((dt == DT_DNA) || (dt == DT_BASE64) || (dt == DT_UTF8)) return false;
+      }
+      int minIdx = 0;
+      if (freqs[minIdx] > 0) {
+        for (int i = 1; i < 256; i++) {
+          if (freqs[i] < freqs[minIdx]) { minIdx = i; if (freqs[i] == 0) break; }
+        }
+      }
+      escape = minIdx;
+    }
+    bool res = true;
+    int run = 0;
+    int prev = get(srcIdx++);
+    put(dstIdx++, escape);
+    put(dstIdx++, prev);
+    if (prev == escape) put(dstIdx++, 0);
+    while (true) {
+      if (prev == get(srcIdx)) {
+        srcIdx++; run++;
+        if (prev == get(srcIdx)) {
+          srcIdx++; run++;
+          if (prev == get(srcIdx)) {
+            srcIdx++; run++;
+            if (prev == get(srcIdx)) {
+              srcIdx++; run++;
+              if ((run < MAX_RUN4) && (srcIdx < srcEnd4)) continue;
+            }
+          }
+        }
+      }
+      if (run > RUN_THRESHOLD) {
+        if (dstIdx + 6 >= dstEnd) { res = false; break; }
+        put(dstIdx++, prev);
+        if (prev == escape) put(dstIdx++, 0);
+        put(dstIdx++, escape);
+        dstIdx = emitRunLength(dst, dstCap, dstIdx, run);
+      } else if (prev != escape) {
+        if (dstIdx + run >= dstEnd) { res = false; break; }
+        while (run-- > 0) put(dstIdx++, prev);
+      } else {
+        if (dstIdx + 2 * run >= dstEnd) { res = false; break; }
+        while (run-- > 0) { put(dstIdx++, escape); put(dstIdx++, 0); }
+      }
+      prev = get(srcIdx);
+      srcIdx++;
+      run = 1;
+      if (srcIdx >= srcEnd4) break;
+    }
+    if (res) {
+      if (prev != escape) {
+        if (dstIdx + run < dstEnd) { while (run-- > 0) put(dstIdx++, prev); }
+      } else {
+        if (dstIdx + 2 * run < dstEnd) { while (run-- > 0) { put(dstIdx++, escape); put(dstIdx++, 0); } }
+      }
+      while ((srcIdx < srcEnd) && (dstIdx < dstEnd)) {
+        if (get(srcIdx) == escape) {
+          if (dstIdx + 2 >= dstEnd) { res = false; break; }
+          put(dstIdx++, escape); put(dstIdx++, 0);
+          srcIdx++;
+          continue;
+        }
+        put(dstIdx++, get(srcIdx++));
+      }
+      res &= (srcIdx == srcEnd);
+    }
+    res &= ((dstIdx - output.index) < (srcIdx - input.index));
+    input.index = srcIdx; output.index = dstIdx;
+    return res;
+  }
+  // inverse, RLT.java:252-352
+  bool inverse(Slice& input, Slice& output) override {
+    if (input.length == 0) return true;
+    if (!basicCheck(input, output)) return false;
+    if (input.arr == output.arr) return false;
+    const int count = input.length;
+    int srcIdx = input.index, dstIdx = output.index;
+    const u8* src = input.p(); u8* dst = output.p();
+    const int srcCap = input.cap(), dstCap = output.cap();
+    auto get = [&](int i) -> int { if (i < 0 || i >= srcCap) throw JavaException("AIOOBE in RLT.inverse"); return src[i]; };
+    auto put = [&](int i, int v) { if (i < 0 || i >= dstCap) throw JavaException("AIOOBE in RLT.inverse"); dst[i] = (u8)v; };
+    const int srcEnd = srcIdx + count;
+    const int dstEnd = dstCap;
+    bool res = true;
+    const int escape = get(srcIdx++);
+    if (get(srcIdx) == escape) {
+      srcIdx++;
+      if ((srcIdx < srcEnd) && (get(srcIdx) != 0)) return false;
+      put(dstIdx++, escape);
+      srcIdx++;
+    }
+    while (srcIdx < srcEnd) {
+      if (get(srcIdx) != escape) {
+        if (dstIdx >= dstEnd) break;
+        put(dstIdx++, get(srcIdx++));
+        continue;
+      }
+      srcIdx++;
+      if (srcIdx >= srcEnd) { res = false; break; }
+      if (dstIdx - 1 < 0) throw JavaException("AIOOBE in RLT.inverse");
+      const int val = dst[dstIdx - 1];
+      int run = get(srcIdx++);
+      if (run == 0) {
+        if (dstIdx >= dstEnd) break;
+        put(dstIdx++, escape);
+        continue;
+      }
+      if (run == 0xFF) {
+        if (srcIdx >= srcEnd - 1) { res = false; break; }
+        run = (get(srcIdx) << 8) | get(srcIdx + 1);
+        srcIdx += 2;
+        run += RUN_LEN_ENCODE2;
+      } else if (run >= RUN_LEN_ENCODE1) {
+        if (srcIdx >= srcEnd) { res = false; break; }
+        run = ((run - RUN_LEN_ENCODE1) << 8) | get(srcIdx++);
+        run += RUN_LEN_ENCODE1;
+      }
+      run += (RUN_THRESHOLD - 1);
+      if ((dstIdx + run > dstEnd) || (run > MAX_RUN)) { res = false; break; }
+      while (run-- > 0) put(dstIdx++, val);
+    }
+    res &= (srcIdx == srcEnd);
+    input.index = srcIdx; output.index = dstIdx;
+    return res;
+  }
+  int getMaxEncodedLength(int srcLen) override { return (srcLen <= 512) ? srcLen + 32 : srcLen; }        // RLT.java:355-357
+};
+
 // ---- LZPCodec (transform/LZCodec.java:973-1287; selected by ctx["lz"] == LZP_TYPE, LZCodec.java:57-58) ------------------
 // bsVersion >= 4 everywhere on this path, so minMatch is 64 both ways (LZCodec.java:988-997, 1137).
 struct LZP : Transform {
@@ -1436,6 +1609,7 @@ static inline std::unique_ptr<Transform> newTransform(Ctx& ctx, int type) {
     case T_LZ: ctx.lzType = T_LZ; return std::unique_ptr<Transform>(new LZX(&ctx, false));
     case T_LZX: ctx.lzType = T_LZX; return std::unique_ptr<Transform>(new LZX(&ctx, true));
     case T_LZP: ctx.lzType = T_LZP; return std::unique_ptr<Transform>(new LZP());
+    case T_RLT: return std::unique_ptr<Transform>(new RLT(&ctx));
     case T_ROLZ: return std::unique_ptr<Transform>(new ROLZ1(&ctx));
     case T_BWT: return std::unique_ptr<Transform>(new BWTBlockCodec(ctx));
     case T_RANK: ctx.sbrtMode = 2; return std::unique_ptr<Transform>(new SBRT(2));

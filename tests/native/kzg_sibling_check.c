@@ -1,7 +1,7 @@
 /*
  * kzg_sibling_check.c — TEST INFRASTRUCTURE: a torch-free parity check of the LZP stage on a real GPU, for when a box is only
  * available for a minute (no Python start-up): libkanzi_b200 (linked) against the oracle (dlopen of oracle/libkzoracle.so), on
- * word-salad text with long re-pasted passages, flag bytes sprinkled in.
+ * word-salad text with long re-pasted passages, flag bytes sprinkled in, and of the RLT stage on run-heavy bytes.
  *   A  per-block LZP forward vs the oracle's bytes, inverse of those bytes vs the input     (kzg_transform_forward / _inverse)
  *   B  whole streams through chains with LZP vs the oracle's stream, then kzg_decompress    (kzg_compress / kzg_decompress)
  *   C  the same for LZ&ANS0 and ROLZ&ANS0: the chains that existed before must still match
@@ -43,6 +43,50 @@ static void fill(uint8_t* p, size_t n) {
     for (int k = 0; k < vlen[w] && o < n; k++) p[o++] = (uint8_t)vocab[w][k];
     if (o < n) p[o++] = ' ';
   }
+}
+
+static void fill_runs(uint8_t* p, size_t n) {
+  size_t o = 0;
+  while (o < n) {
+    const uint32_t r = rnd();
+    const uint8_t v = (r & 7) == 0 ? 0xFB : ((r & 7) == 1 ? 0 : (uint8_t)(r >> 8));
+    size_t len = 1 + (r >> 16) % 12;
+    if ((r & 0x300) == 0) len = 200 + rnd() % 9000;
+    if ((r & 0x7F00) == 0) len = 60000 + rnd() % 30000;
+    for (size_t k = 0; k < len && o < n; k++) p[o++] = v;
+  }
+}
+
+/* RLT per-block: entropy id e decides the escape byte (ctx flags bits 8-11 on our side, ctxv[5] >> 8 on the oracle's) */
+static void check_rlt(const uint8_t* d, int32_t n, int e) {
+  char what[128], detail[256] = "";
+  const int32_t cap = n <= 512 ? n + 32 : n;
+  uint8_t* ref = (uint8_t*)calloc((size_t)cap + 64, 1); uint8_t* got = (uint8_t*)calloc((size_t)cap + 64, 1); uint8_t* back = (uint8_t*)calloc((size_t)n + 64, 1);
+  int32_t cv[6] = {7, n > 1024 ? n : 1024, n, 1, 0, e << 8}, su = 0, du = 0, gsu = 0, gdu = 0;
+  const int okRef = kzo_transform(KZG_T_RLT, 0, cv, d, n, n, ref, cap, cap, &su, &du);
+  kzg_ctx ctx = {7, n > 1024 ? n : 1024, n, 1, 0, KZG_CTX_ENTROPY(e)};
+  const int ok = kzg_transform_forward(KZG_T_RLT, &ctx, d, n, got, cap, cap, &gsu, &gdu);
+  snprintf(what, sizeof(what), "A RLT forward n=%d entropy=%d", n, e);
+  int good = (ok == okRef) && ctx.dataType == cv[4] && (!ok || (gdu == du && gsu == su && memcmp(got, ref, (size_t)du) == 0));
+  snprintf(detail, sizeof(detail), "(ok %d/%d, bytes %d/%d, type %d/%d) %s", ok, okRef, gdu, du, ctx.dataType, cv[4], good ? "" : kzg_last_error());
+  verdict(what, good, detail);
+  if (okRef == 1) {
+    int32_t isu = 0, idu = 0;
+    const int oki = kzg_transform_inverse(KZG_T_RLT, &ctx, ref, du, back, n, n, &isu, &idu);
+    snprintf(what, sizeof(what), "A RLT inverse n=%d", n);
+    good = (oki == 1) && idu == n && isu == du && memcmp(back, d, (size_t)n) == 0;
+    snprintf(detail, sizeof(detail), "(ok %d, bytes %d, used %d/%d) %s", oki, idu, isu, du, good ? "" : kzg_last_error());
+    verdict(what, good, detail);
+    /* one byte short: refused, unless the byte that does not fit is a literal escape at the very end (RLT.java:308-313 drops it and
+     * still reports success); whatever the oracle says */
+    int32_t cv2[6] = {7, n, n, 1, 0, 0}, osu = 0, odu = 0;
+    const int o2 = kzo_transform(KZG_T_RLT, 1, cv2, ref, du, du, got, n - 1, n - 1, &osu, &odu);
+    const int k2 = kzg_transform_inverse(KZG_T_RLT, &ctx, ref, du, back, n - 1, n - 1, &isu, &idu);
+    snprintf(what, sizeof(what), "A RLT inverse short dst n=%d", n);
+    snprintf(detail, sizeof(detail), "(%d/%d, bytes %d/%d)", k2, o2, idu, odu);
+    verdict(what, k2 == (o2 < 0 ? 0 : o2) && (k2 != 1 || (idu == odu && memcmp(back, got, (size_t)idu) == 0)), detail);
+  }
+  free(ref); free(got); free(back);
 }
 
 static void check_block(const uint8_t* d, int32_t n) {
@@ -120,6 +164,16 @@ int main(int argc, char** argv) {
   const int32_t sizes[] = {127, 128, 129, 200, 5000, 70001, 1 << 20, (3 << 20) + 77};
   for (unsigned i = 0; i < sizeof(sizes) / sizeof(sizes[0]); i++) check_block(d + ((size_t)sizes[i] + 60000 < N ? (i * 4099) % 50000 : 0), sizes[i]);
   { uint8_t* z = (uint8_t*)calloc(300000, 1); check_block(z, 300000); memset(z, 0xFC, 300000); check_block(z, 300000); free(z); }
+  uint8_t* rr = (uint8_t*)malloc(N + 64);
+  fill_runs(rr, N);
+  const int32_t rsizes[] = {15, 16, 600, 70001, 1 << 20};
+  for (unsigned i = 0; i < sizeof(rsizes) / sizeof(rsizes[0]); i++) { check_rlt(rr + i * 1234, rsizes[i], KZG_E_NONE); check_rlt(rr + i * 1234, rsizes[i], KZG_E_FPAQ); }
+  { uint8_t* z = (uint8_t*)malloc(40000); for (int i = 0; i < 40000; i++) z[i] = "ACGT"[(i * 7 + (i >> 3)) & 3]; check_rlt(z, 40000, KZG_E_ANS1); check_rlt(z, 40000, KZG_E_ANS0); free(z); }
+  const int32_t rlt[] = {KZG_T_RLT}, rltlzp[] = {KZG_T_RLT, KZG_T_LZP};
+  check_stream("B RLT&ANS0", rr, (int64_t)N, rlt, 1, KZG_E_ANS0, 1 << 18);
+  check_stream("B RLT&FPAQ", rr, (int64_t)N, rlt, 1, KZG_E_FPAQ, 1 << 20);
+  check_stream("B RLT+LZP&HUFFMAN", rr, (int64_t)1 << 21, rltlzp, 2, KZG_E_HUFFMAN, 1 << 19);
+  check_stream("B RLT&NONE text", d, 700001, rlt, 1, KZG_E_NONE, 1 << 16);
   const int32_t lzp[] = {KZG_T_LZP}, lzpz[] = {KZG_T_LZP, KZG_T_ZRLT}, lz[] = {KZG_T_LZ}, rolz[] = {KZG_T_ROLZ}, rl[] = {KZG_T_ROLZ, KZG_T_LZP};
   check_stream("B LZP&ANS0", d, (int64_t)N, lzp, 1, KZG_E_ANS0, 1 << 20);
   check_stream("B LZP+ZRLT&HUFFMAN", d, (int64_t)N, lzpz, 2, KZG_E_HUFFMAN, 1 << 18);

@@ -1344,3 +1344,210 @@ def test_lzp_agrees_with_the_oracle_both_ways():
         p2 = lzp_inverse(cut, len(d))
         assert o2[0] == int(p2[0]) and (not p2[0] or o2[1] == p2[1])
     assert applied >= 6
+
+
+# ---- RLT: K/transform/RLT.java:62-231 (forward), :233-249 (emitRunLength), :252-352 (inverse) --------------------------------
+def _detect_simple_type(count, f):   # Global.java:556-608 -> DataType ordinal (DNA 6, NUMERIC 4, BASE64 5, BIN 7, SMALL_ALPHABET 9, UNDEFINED 0)
+    if count == 0:
+        return 0
+    if sum(f[c] for c in b"acgntuACGNTU") > count - count // 12:
+        return 6
+    if sum(f[c] for c in b"0123456789+-*/=,.:; ") == count:
+        return 4
+    if (1 if f[0x3D] == 1 else 0) + sum(f[c] for c in b"ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/") == count:
+        return 5
+    n = sum(1 for x in f if x > 0)
+    return 7 if n == 256 else (9 if n <= 4 else 0)
+
+
+def rlt_forward(src, entropy="NONE", data_type=0, dst_end=None):
+    """-> (ok, out, data type after the call); dst_end = dst.array.length"""
+    count = len(src)
+    if count == 0:
+        return True, b"", data_type
+    if count < 16:
+        return False, b"", data_type
+    if dst_end is None:
+        dst_end = count + 32 if count <= 512 else count
+    if data_type in (6, 5, 8):
+        return False, b"", data_type
+    escape = 0xFB
+    if entropy not in ("NONE", "ANS0", "HUFFMAN", "RANGE"):
+        f = [0] * 256
+        for b in src:
+            f[b] += 1
+        if data_type == 0:
+            data_type = _detect_simple_type(count, f)
+            if data_type in (6, 5, 8):
+                return False, b"", data_type
+        m = 0
+        if f[0] > 0:
+            for i in range(1, 256):
+                if f[i] < f[m]:
+                    m = i
+                    if f[i] == 0:
+                        break
+        escape = m
+    dst = bytearray()
+    si, end4 = 0, count - 4
+    res, run = True, 0
+    prev = src[si]
+    si += 1
+    dst += bytes([escape, prev])
+    if prev == escape:
+        dst.append(0)
+    while True:
+        again = False
+        for _ in range(4):
+            if prev != src[si]:
+                break
+            si += 1
+            run += 1
+        else:
+            again = run < 73469 and si < end4
+        if again:
+            continue
+        if run > 3:
+            if len(dst) + 6 >= dst_end:
+                res = False
+                break
+            dst.append(prev)
+            if prev == escape:
+                dst.append(0)
+            dst.append(escape)
+            r = run - 3
+            if r >= 224:
+                if r < 7936:
+                    r -= 224
+                    dst.append(224 + (r >> 8))
+                else:
+                    r -= 7936
+                    dst += bytes([0xFF, (r >> 8) & 0xFF])
+            dst.append(r & 0xFF)
+        elif prev != escape:
+            if len(dst) + run >= dst_end:
+                res = False
+                break
+            dst += bytes([prev]) * run
+        else:
+            if len(dst) + 2 * run >= dst_end:
+                res = False
+                break
+            dst += bytes([escape, 0]) * run
+        prev = src[si]
+        si += 1
+        run = 1
+        if si >= end4:
+            break
+    if res:
+        if prev != escape:
+            if len(dst) + run < dst_end:
+                dst += bytes([prev]) * run
+        elif len(dst) + 2 * run < dst_end:
+            dst += bytes([escape, 0]) * run
+        while si < count and len(dst) < dst_end:
+            if src[si] == escape:
+                if len(dst) + 2 >= dst_end:
+                    res = False
+                    break
+                dst += bytes([escape, 0])
+                si += 1
+                continue
+            dst.append(src[si])
+            si += 1
+        res = res and si == count
+    res = res and len(dst) < si
+    return res, bytes(dst), data_type
+
+
+def rlt_inverse(src, dst_end):
+    """-> (ok, out); None for ok where the Java code would throw"""
+    count = len(src)
+    if count == 0:
+        return True, b""
+    try:
+        dst = bytearray()
+        si = 0
+        escape = src[si]
+        si += 1
+        if src[si] == escape:
+            si += 1
+            if si < count and src[si] != 0:
+                return False, b""
+            dst.append(escape)
+            si += 1
+        res = True
+        while si < count:
+            if src[si] != escape:
+                if len(dst) >= dst_end:
+                    break
+                dst.append(src[si])
+                si += 1
+                continue
+            si += 1
+            if si >= count:
+                res = False
+                break
+            val = dst[len(dst) - 1] if len(dst) > 0 else [][0]
+            run = src[si]
+            si += 1
+            if run == 0:
+                if len(dst) >= dst_end:
+                    break
+                dst.append(escape)
+                continue
+            if run == 0xFF:
+                if si >= count - 1:
+                    res = False
+                    break
+                run = ((src[si] << 8) | src[si + 1]) + 7936
+                si += 2
+            elif run >= 224:
+                if si >= count:
+                    res = False
+                    break
+                run = (((run - 224) << 8) | src[si]) + 224
+                si += 1
+            run += 2
+            if len(dst) + run > dst_end or run > 73473:
+                res = False
+                break
+            dst += bytes([val]) * run
+        return res and si == count, bytes(dst)
+    except IndexError:
+        return None, b""
+
+
+def _rlt_cases():
+    from kanzi_b200 import synth
+    r = np.random.default_rng(51)
+    runs = bytes(np.repeat(r.integers(0, 256, 4000, dtype=np.uint8), r.integers(1, 40, 4000)))
+    long_runs = bytes(np.repeat(r.integers(0, 6, 40, dtype=np.uint8), r.integers(1, 90000, 40)))
+    esc = bytes(np.repeat(r.choice(np.array([0xFB, 0xFB, 0, 7, 0xFF], dtype=np.uint8), 3000), r.integers(1, 9, 3000)))
+    return [runs, long_runs, esc, bytes(80000), b"\xfb" * 80000, bytes([0xFB]) + bytes(50), synth.text(30000, 3).tobytes(), synth.records(40000, 4).tobytes(),
+            b"ab" * 8, b"a" * 16, b"a" * 15, b"abcdefgh" * 40 + b"z" * 73480 + b"q" * 5 + b"y" * 300, b"y" * 7 + b"z" * (73473 + 3) + b"x",
+            bytes(r.integers(0, 2, 5000, dtype=np.uint8)), b"ACGT" * 3000 + b"A" * 900, b"0123456789" * 500 + b"7" * 99, runs[:517], runs[:511], runs[:512] + b"\x00" * 4]
+
+
+@pytest.mark.parametrize("entropy", ["NONE", "FPAQ"])
+def test_rlt_agrees_with_the_oracle_both_ways(entropy):
+    eid = {"NONE": 0, "FPAQ": 2}[entropy]
+    applied = 0
+    for d in _rlt_cases():
+        ok_ref, ref, used, cv = O.transform("RLT", d, ctx=[7, max(len(d), 1024), len(d), 1, 0, eid << 8])
+        ok, got, dt = rlt_forward(d, entropy)
+        assert int(ok) == ok_ref and dt == cv[4], (len(d), ok, ok_ref, dt, cv[4])
+        if not ok:
+            continue
+        applied += 1
+        assert got == ref and used == len(d), (len(d), len(got), len(ref))
+        for cap in (len(d), len(d) + 100, len(d) - 1):
+            o = O.transform("RLT", ref, inverse=True, dst_cap=cap, dst_len=cap)
+            p = rlt_inverse(ref, cap)
+            assert o[0] == (-1 if p[0] is None else int(p[0])) and (o[0] != 1 or o[1] == p[1]), (len(d), cap)
+        assert O.transform("RLT", ref, inverse=True, dst_cap=len(d), dst_len=len(d))[1] == d
+        for cut in (len(ref) // 2, len(ref) - 1, 3, 1):
+            o = O.transform("RLT", ref[:cut], inverse=True, dst_cap=len(d), dst_len=len(d))
+            p = rlt_inverse(ref[:cut], len(d))
+            assert o[0] == (-1 if p[0] is None else int(p[0])) and (o[0] != 1 or o[1] == p[1]), (len(d), "cut", cut)
+    assert applied >= 8

@@ -1,9 +1,9 @@
-"""The loops lane 0 of `lzp_kernel` runs (kanzi_b200/csrc/lzp_core.cuh: grouped table lookups, 8-byte probes and copies) are plain
-C++ when no CUDA compiler is looking; tests/native/lzp_hostcheck.cpp compiles that same header for the host and this file holds it
-against the oracle's LZPCodec restatement (K/transform/LZCodec.java:973-1287) on seeded inputs.  What it proves: the reordering the
+"""The loops lane 0 of `lzp_kernel` and `rlt_kernel` runs (kanzi_b200/csrc/lzp_core.cuh: grouped table lookups, 8-byte probes and copies;
+rlt_core.cuh) are plain C++ when no CUDA compiler is looking; tests/native/sibling_hostcheck.cpp compiles those same headers for the host
+and this file holds them against the oracle's restatements (K/transform/LZCodec.java:973-1287, K/transform/RLT.java) on seeded inputs.  What it proves: the reordering the
 device code does (four lookups at a time with in-group forwarding, literal-only table reads in the inverse) keeps the serial
 semantics.  What it cannot prove: anything about the launch, the scratch carve or device memory; that is `-m gpu` territory
-(tests/test_gpu_parity.py::test_lzp_*).  Test infrastructure only: the product library exports none of this."""
+(tests/test_gpu_siblings.py).  Test infrastructure only: the product library exports none of this."""
 import ctypes as C
 import os
 import subprocess
@@ -14,19 +14,21 @@ import pytest
 import oracle_lib as O
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = os.path.join(HERE, "native", "lzp_hostcheck.cpp")
-LIB = os.path.join(HERE, "native", "liblzp_hostcheck.so")
-CORE = os.path.join(HERE, "..", "kanzi_b200", "csrc", "lzp_core.cuh")
+SRC = os.path.join(HERE, "native", "sibling_hostcheck.cpp")
+LIB = os.path.join(HERE, "native", "libsibling_hostcheck.so")
+CORES = [os.path.join(HERE, "..", "kanzi_b200", "csrc", f) for f in ("lzp_core.cuh", "rlt_core.cuh")]
 u8p = C.POINTER(C.c_uint8)
 
 
 @pytest.fixture(scope="module")
 def host():
-    if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(SRC), os.path.getmtime(CORE)):
+    if not os.path.exists(LIB) or os.path.getmtime(LIB) < max([os.path.getmtime(SRC)] + [os.path.getmtime(c) for c in CORES]):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", SRC, "-o", LIB])
     L = C.CDLL(LIB)
     L.lzp_host_forward.argtypes = [u8p, C.c_int, u8p, C.POINTER(C.c_int)]
     L.lzp_host_inverse.argtypes = [u8p, C.c_int, u8p, C.c_int, C.POINTER(C.c_int)]
+    L.rlt_host_forward.argtypes = [u8p, C.c_int, u8p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.rlt_host_inverse.argtypes = [u8p, C.c_int, u8p, C.c_int, C.POINTER(C.c_int)]
     return L
 
 
@@ -135,5 +137,82 @@ def test_corrupt_streams_fail_alike(host):
         o = O.transform("LZP", bytes(bad), inverse=True, dst_cap=len(d), dst_len=len(d))
         h = _inv(host, bytes(bad), len(d))
         assert o[0] == h[0], k
+        if h[0]:
+            assert o[1] == h[1]
+
+
+# ---- RLT ------------------------------------------------------------------------------------------------------------------------
+def _rlt_fwd(L, d, dst_end, best, dt=0):
+    g = _Guarded(d)
+    dst = np.full(dst_end + 64, 0xA5, dtype=np.uint8)
+    n, t = C.c_int(0), C.c_int(dt)
+    ok = L.rlt_host_forward(g.ptr, len(d), dst.ctypes.data_as(u8p), dst_end, best, C.byref(t), C.byref(n))
+    assert (dst[dst_end:] == 0xA5).all()
+    return ok, dst[:n.value].tobytes(), t.value
+
+
+def _rlt_inv(L, s, dst_end):
+    g = _Guarded(s)
+    dst = np.full(dst_end + 64, 0xA5, dtype=np.uint8)
+    n = C.c_int(0)
+    ok = L.rlt_host_inverse(g.ptr, len(s), dst.ctypes.data_as(u8p), dst_end, C.byref(n))
+    assert (dst[dst_end:] == 0xA5).all()
+    return ok, dst[:n.value].tobytes()
+
+
+def rlt_inputs():
+    from test_oracle_crosscheck import _rlt_cases
+    r = np.random.default_rng(91)
+    out = list(_rlt_cases())
+    for k in range(60):                                               # seeded fuzz: run lengths around every coding threshold, escapes inside and at the ends
+        parts = []
+        for _ in range(int(r.integers(2, 40))):
+            v = int(r.choice([0xFB, 0, 1, 0xFF, int(r.integers(0, 256))]))
+            ln = int(r.choice([1, 2, 3, 4, 5, 226, 227, 228, 7938, 7939, 7940, int(r.integers(1, 300))]))
+            parts.append(bytes([v]) * ln)
+        d = b"".join(parts)
+        out.append(d if len(d) >= 16 else d + bytes(16))
+    return out
+
+
+@pytest.mark.parametrize("entropy,eid", [("NONE", 0), ("ANS1", 8)])
+def test_rlt_device_loops_on_the_host_match_the_oracle(host, entropy, eid):
+    applied = 0
+    best = 0 if entropy == "NONE" else 1
+    for d in rlt_inputs():
+        if len(d) < 16:
+            continue
+        cap = len(d) + 32 if len(d) <= 512 else len(d)
+        ok_ref, ref, _, cv = O.transform("RLT", d, ctx=[7, max(len(d), 1024), len(d), 1, 0, eid << 8])
+        ok, got, dt = _rlt_fwd(host, d, cap, best)
+        assert (ok, dt) == (ok_ref, cv[4]), (len(d), ok, ok_ref, dt, cv[4])
+        if not ok:
+            continue
+        applied += 1
+        assert got == ref, (len(d), len(got), len(ref))
+        assert _rlt_inv(host, ref, len(d)) == (1, d)
+        for cap2 in (len(d) - 1, len(d) + 77):
+            o = O.transform("RLT", ref, inverse=True, dst_cap=cap2, dst_len=cap2)
+            h = _rlt_inv(host, ref, cap2)
+            assert max(o[0], 0) == h[0] and (not h[0] or o[1] == h[1]), (len(d), cap2)
+        for cut in (len(ref) // 2, len(ref) - 1, 3, 2):
+            o = O.transform("RLT", ref[:cut], inverse=True, dst_cap=len(d), dst_len=len(d))
+            h = _rlt_inv(host, ref[:cut], len(d))
+            assert max(o[0], 0) == h[0] and (not h[0] or o[1] == h[1]), (len(d), "cut", cut)
+    assert applied >= 40
+
+
+def test_rlt_corrupt_streams_fail_alike(host):
+    r = np.random.default_rng(8)
+    d = rlt_inputs()[0]
+    ok, ref, _, _ = O.transform("RLT", d)
+    assert ok == 1
+    for k in range(60):
+        bad = bytearray(ref)
+        for _ in range(1 + k % 3):
+            bad[int(r.integers(0, len(bad)))] = int(r.choice([ref[0], 0xFF, 0xE0, 0x00, int(r.integers(0, 256))]))
+        o = O.transform("RLT", bytes(bad), inverse=True, dst_cap=len(d), dst_len=len(d))
+        h = _rlt_inv(host, bytes(bad), len(d))
+        assert max(o[0], 0) == h[0], k
         if h[0]:
             assert o[1] == h[1]
