@@ -22,7 +22,7 @@ extern "C" {
 /* transform ids: K/transform/TransformFactory.java:36-58 */
 enum {
   KZG_T_NONE = 0, KZG_T_BWT = 1, KZG_T_LZ = 3, KZG_T_RLT = 5, KZG_T_ZRLT = 6, KZG_T_MTFT = 7, KZG_T_RANK = 8,
-  KZG_T_ROLZ = 11, KZG_T_SRT = 13, KZG_T_LZP = 14, KZG_T_LZX = 16
+  KZG_T_ROLZ = 11, KZG_T_ROLZX = 12, KZG_T_SRT = 13, KZG_T_LZP = 14, KZG_T_LZX = 16
 };
 /* entropy ids: K/entropy/EntropyCodecFactory.java:38-47 */
 enum { KZG_E_NONE = 0, KZG_E_HUFFMAN = 1, KZG_E_FPAQ = 2, KZG_E_ANS0 = 5, KZG_E_ANS1 = 8 };
@@ -80,7 +80,7 @@ int64_t kzg_launch_count(int reset);
  * Returns 1 = true, 0 = false (transform skipped / recoverable), < 0 = -KZG_ERR_*.
  * On return *srcUsed / *dstUsed are the slices' new indexes (bytes consumed / produced).
  * getMaxEncodedLength: BWTBlockCodec.java:222-224 (n+33), LZCodec.java:961-964 (LZ, LZX), :1283-1285 (LZP), ROLZCodec.java:1001-1003,
- * SBRT/ZRLT n, SRT.java:364-366 (n+1024), RLT.java:355-357. */
+ * :1417-1421 (ROLZX), SBRT/ZRLT n, SRT.java:364-366 (n+1024), RLT.java:355-357. */
 int kzg_transform_forward(int type, kzg_ctx* ctx, const uint8_t* src, int32_t srcLen, uint8_t* dst, int32_t dstLen,
                           int32_t dstCap, int32_t* srcUsed, int32_t* dstUsed);
 int kzg_transform_inverse(int type, kzg_ctx* ctx, const uint8_t* src, int32_t srcLen, uint8_t* dst, int32_t dstLen,

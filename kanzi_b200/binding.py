@@ -8,7 +8,7 @@ LIB_PATH = os.path.join(_HERE, "libkanzi_b200.so")
 _LIB = None
 
 # ids: K/transform/TransformFactory.java:36-58, K/entropy/EntropyCodecFactory.java:38-47
-T = dict(NONE=0, BWT=1, LZ=3, ZRLT=6, MTFT=7, RANK=8, ROLZ=11, SRT=13, LZP=14, LZX=16, RLT=5)
+T = dict(NONE=0, BWT=1, LZ=3, ZRLT=6, MTFT=7, RANK=8, ROLZ=11, SRT=13, LZP=14, LZX=16, RLT=5, ROLZX=12)
 E = dict(NONE=0, HUFFMAN=1, FPAQ=2, ANS0=5, ANS1=8)
 DT = dict(UNDEFINED=0, TEXT=1, MULTIMEDIA=2, EXE=3, NUMERIC=4, BASE64=5, DNA=6, BIN=7, UTF8=8, SMALL_ALPHABET=9)
 FLAG_BWT_ASREF = 1

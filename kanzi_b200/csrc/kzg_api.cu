@@ -143,7 +143,7 @@ struct EvSet {
 // ---- ids / sizes (TransformFactory, getMaxEncodedLength of each codec) --------------------------------------
 static bool xf_known(int t) {
   switch (t) { case KZG_T_NONE: case KZG_T_LZ: case KZG_T_LZX: case KZG_T_ROLZ: case KZG_T_BWT: case KZG_T_RANK: case KZG_T_MTFT:
-               case KZG_T_SRT: case KZG_T_ZRLT: case KZG_T_LZP: case KZG_T_RLT: return true; default: return false; }
+               case KZG_T_SRT: case KZG_T_ZRLT: case KZG_T_LZP: case KZG_T_RLT: case KZG_T_ROLZX: return true; default: return false; }
 }
 static bool ent_known(int e) {
   switch (e) { case KZG_E_NONE: case KZG_E_HUFFMAN: case KZG_E_ANS0: case KZG_E_ANS1: case KZG_E_FPAQ: return true; default: return false; }
@@ -153,6 +153,7 @@ static i32 xf_max_len(int t, i32 n) {
     case KZG_T_LZ: case KZG_T_LZX: return ((n <= 1024) ? n + 16 : n + (n / 64)) + 2;   // LZCodec.java:961-964
     case KZG_T_LZP: return (n <= 1024) ? n + 16 : n + (n / 64);                       // LZCodec.java:1283-1285
     case KZG_T_RLT: return (n <= 512) ? n + 32 : n;                                   // RLT.java:355-357
+    case KZG_T_ROLZX: return (n <= 16384) ? n + 1024 : n + (n / 32);                  // ROLZCodec.java:1417-1421
     case KZG_T_ROLZ: return (n <= 512) ? n + 64 : n;                                  // ROLZCodec.java:1001-1003
     case KZG_T_BWT: return n + 33;                                                    // BWTBlockCodec.java:222-224
     case KZG_T_SRT: return n + 1024;                                                  // SRT.java:364-366
@@ -486,7 +487,7 @@ static int transform_batch(std::vector<KzgReq*>& rq) {
     B.cur = dA + k * cap; B.alt = dB + k * cap; B.curLen = Q.srcLen; B.cap = (forward && type != KZG_T_RLT) ? Q.dstLen : Q.dstCap; B.origLen = Q.srcLen; B.skipFlags = 0xFF;
     B.dataType = Q.ctx ? Q.ctx->dataType : 0; B.aux0 = nullptr; B.aux1 = B.cur; B.stagesLeft = 2;
     // dst.length of the slice, except where the codec looks at dst.array.length: every inverse but LZP's (LZCodec.java:1133) and RLT.forward (RLT.java:117)
-    bt.hEnabled[k] = 1; bt.hDstLimit[k] = ((forward && type != KZG_T_RLT) || type == KZG_T_LZP) ? Q.dstLen : Q.dstCap;
+    bt.hEnabled[k] = 1; bt.hDstLimit[k] = ((forward && type != KZG_T_RLT) || type == KZG_T_LZP || type == KZG_T_ROLZX) ? Q.dstLen : Q.dstCap;   // (ROLZX.inverse: szBlock > output.length, ROLZCodec.java:1306)
     if (!cu(cudaMemsetAsync(B.cur + Q.srcLen, 0, cap - Q.srcLen, W.stream)) || !cu(cudaMemcpyAsync(B.cur, Q.src, Q.srcLen, cudaMemcpyHostToDevice, W.stream)))
       return failAll(-KZG_ERR_PROCESS_BLOCK);
   }

@@ -12,5 +12,7 @@ int kzg_srt_launch(cudaStream_t s, bool forward, KzgBlock* d_blocks, int nBlocks
 int kzg_bwtblock_launch(cudaStream_t s, bool forward, KzgBlock* d_blocks, int nBlocks, const KzgXfParams& P, i32 maxLen);
 void kzg_lzp_scratch(i32 maxLen, bool forward, size_t* perBlockBytes, size_t* hashInts);
 int kzg_lzp_launch(cudaStream_t s, bool forward, KzgBlock* d_blocks, int nBlocks, const KzgXfParams& P, i32 maxLen);
+void kzg_rolzx_scratch(i32 maxLen, bool forward, size_t* perBlockBytes, size_t* hashInts);
+int kzg_rolzx_launch(cudaStream_t s, bool forward, KzgBlock* d_blocks, int nBlocks, const KzgXfParams& P, i32 maxLen);
 int kzg_rlt_launch(cudaStream_t s, bool forward, KzgBlock* d_blocks, int nBlocks, const KzgXfParams& P, i32 maxLen);
 int kzg_rolz_launch(cudaStream_t s, bool forward, KzgBlock* d_blocks, int nBlocks, const KzgXfParams& P, i32 maxLen);

@@ -84,6 +84,7 @@ void kzg_stage_scratch(int type, i32 maxLen, bool forward, size_t* perBlockBytes
     case KZG_T_BWT: kzg_bwt_scratch(maxLen, forward, perBlockBytes, aux32); break;
     case KZG_T_ROLZ: kzg_rolz_scratch(maxLen, forward, perBlockBytes, hashInts, aux32); break;
     case KZG_T_LZP: kzg_lzp_scratch(maxLen, forward, perBlockBytes, hashInts); break;
+    case KZG_T_ROLZX: kzg_rolzx_scratch(maxLen, forward, perBlockBytes, hashInts); break;
     case KZG_T_SRT: case KZG_T_RANK: case KZG_T_MTFT: case KZG_T_ZRLT: kzg_small_scratch(type, maxLen, forward, perBlockBytes, aux32); break;
     default: break;
   }
@@ -99,6 +100,7 @@ int kzg_stage_launch(cudaStream_t s, int type, bool forward, KzgBlock* d_blocks,
     case KZG_T_ROLZ: return kzg_rolz_launch(s, forward, d_blocks, nBlocks, P, maxLen);
     case KZG_T_LZP: return kzg_lzp_launch(s, forward, d_blocks, nBlocks, P, maxLen);
     case KZG_T_RLT: return kzg_rlt_launch(s, forward, d_blocks, nBlocks, P, maxLen);
+    case KZG_T_ROLZX: return kzg_rolzx_launch(s, forward, d_blocks, nBlocks, P, maxLen);
     default: kzg_set_error("transform id %d has no kernel", type); return -KZG_ERR_INVALID_CODEC;
   }
 }
@@ -111,6 +113,10 @@ int kzg_stage_precheck(int type, bool forward, const kzg_ctx* ctx, i32 srcLen, i
     case KZG_T_NONE: return (dstLen < srcLen) ? 0 : 1;                                   // NullTransform.java:57-58
     case KZG_T_LZ: case KZG_T_LZX:
       if (forward) { if (dstLen < ((srcLen <= 1024 ? srcLen + 16 : srcLen + srcLen / 64) + 2)) return 0; }   // LZCodec.java:309-310
+      return 1;
+    case KZG_T_ROLZX:
+      if (srcLen > (1 << 30)) return 0;                                                                                        // ROLZCodec.java:220-221, 252-253
+      if (forward && (srcLen < 64 || dstLen < ((srcLen <= 16384) ? srcLen + 1024 : srcLen + srcLen / 32))) return 0;           // :216-217, 1184-1185
       return 1;
     case KZG_T_RLT:
       if (forward && (srcLen < 16 || dstLen < ((srcLen <= 512) ? srcLen + 32 : srcLen))) return 0;                          // RLT.java:71-80

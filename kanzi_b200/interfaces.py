@@ -184,7 +184,7 @@ class EntropyDecoder:
 
 class TransformFactory:
     """K/transform/TransformFactory.java: name -> ByteTransform."""
-    NAMES = ("NONE", "BWT", "LZ", "LZX", "LZP", "RLT", "ROLZ", "RANK", "MTFT", "SRT", "ZRLT")
+    NAMES = ("NONE", "BWT", "LZ", "LZX", "LZP", "RLT", "ROLZ", "ROLZX", "RANK", "MTFT", "SRT", "ZRLT")
 
     @staticmethod
     def newFunction(ctx, name):

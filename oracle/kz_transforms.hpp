@@ -1296,6 +1296,248 @@ struct ROLZ1 : Transform {
   }
 };
 
+// ---- ROLZX = ROLZCodec2 (transform/ROLZCodec.java:1016-1428) with its binary arithmetic coder ROLZEncoder / ROLZDecoder
+// (:1431-1597, :1599-1770).  Selected here by the ROLZX id (the reference looks for "ROLZX" in ctx["transform"], :106-112).
+struct ROLZ2 : Transform {
+  enum { HASH_SIZE = 65536, CHUNK_SIZE = 16 * 1024 * 1024, MAX_BLOCK_SIZE = 1 << 30, MIN_BLOCK_SIZE = 64, MIN_MATCH3 = 3, MIN_MATCH7 = 7,
+         MAX_MATCH = 3 + 255, LOG_POS_CHECKS = 5, MATCH_FLAG = 0, LITERAL_FLAG = 1, LITERAL_CTX = 0, MATCH_CTX = 1 };
+  static constexpr u32 HASH_MASK = ~(u32)(CHUNK_SIZE - 1);
+  static constexpr u64 TOP = 0x00FFFFFFFFFFFFFFULL, MASK_0_56 = 0x00FFFFFFFFFFFFFFULL, MASK_0_32 = 0x00000000FFFFFFFFULL;
+  int logPosChecks = LOG_POS_CHECKS, maskChecks = 31, posChecks = 32, minMatch = 3;
+  std::vector<i32> counters, matches;
+  Ctx* ctx;
+  explicit ROLZ2(Ctx* c) : counters(1 << 16, 0), matches((size_t)HASH_SIZE << LOG_POS_CHECKS, 0), ctx(c) {}
+  int getMaxEncodedLength(int n) override { return (n <= 16384) ? n + 1024 : n + (n / 32); }     // :1417-1421
+
+  struct Coder {                       // the state ROLZEncoder and ROLZDecoder share
+    u64 low = 0, high = TOP, current = 0;
+    std::vector<i32> probs[2];
+    int logSizes[2];
+    int c1 = 1, cx = 0, pIdx = LITERAL_FLAG;
+    u8* arr; int cap; int* index;
+    Coder(int litLogSize, int mLogSize, u8* a, int cap_, int* idx) : arr(a), cap(cap_), index(idx) {
+      probs[MATCH_CTX].assign((size_t)256 << mLogSize, 0xFFFF >> 1);
+      probs[LITERAL_CTX].assign((size_t)256 << litLogSize, 0xFFFF >> 1);
+      logSizes[MATCH_CTX] = mLogSize; logSizes[LITERAL_CTX] = litLogSize;
+    }
+    void setContext(int n, u8 c) { pIdx = n; cx = (int)c << logSizes[pIdx]; }
+    void need(int k) const { if (*index < 0 || *index + k > cap) throw JavaException("AIOOBE in ROLZ coder"); }
+    // ROLZEncoder.encodeBit, :1553-1580
+    void encodeBit(int bit) {
+      i32& p = probs[pIdx][cx + c1];
+      const u64 split = (((high - low) >> 4) * (u64)((u32)p >> 4)) >> 8;
+      if (bit == 0) { low += (split + 1); p -= (p >> 5); c1 += c1; }
+      else { high = low + split; p -= (((p - 0xFFFF) >> 5) + 1); c1 += (c1 + 1); }
+      while (((low ^ high) >> 24) == 0) {
+        need(4);
+        put_be32(arr + *index, (u32)(high >> 32));
+        *index += 4;
+        low <<= 32;
+        high = (high << 32) | MASK_0_32;
+      }
+    }
+    void encodeBits(int val, int n) { c1 = 1; do { n--; encodeBit(val & (1 << n)); } while (n != 0); }        // :1526-1535
+    void encode9Bits(int val) { c1 = 1; for (int m = 0x100; m != 0; m >>= 1) encodeBit(val & m); }          // :1538-1550
+    void disposeEncoder() {                                                                                  // :1583-1590
+      need(8);
+      for (int i = 0; i < 8; i++) { arr[*index + i] = (u8)((i64)low >> 56); low <<= 8; }
+      *index += 8;
+    }
+    // ROLZDecoder: constructor :1625-1648, decodeBit :1733-1764
+    void initDecoder() {
+      need(8);
+      current = 0;
+      for (int i = 0; i < 8; i++) current = (current << 8) | (u64)arr[*index + i];
+      *index += 8;
+      pIdx = LITERAL_CTX;
+    }
+    int decodeBit() {
+      i32& p = probs[pIdx][cx + c1];
+      const u64 mid = low + ((((high - low) >> 4) * (u64)((u32)p >> 4)) >> 8);
+      int bit;
+      if ((i64)mid >= (i64)current) { bit = 1; high = mid; p -= (((p - 0xFFFF) >> 5) + 1); c1 += (c1 + 1); }
+      else { bit = 0; low = mid + 1; p -= (p >> 5); c1 += c1; }
+      while (((low ^ high) >> 24) == 0) {
+        low = (low << 32) & MASK_0_56;
+        high = ((high << 32) | MASK_0_32) & MASK_0_56;
+        need(4);
+        const u64 val = (u64)be32(arr + *index);
+        current = ((current << 32) | val) & MASK_0_56;
+        *index += 4;
+      }
+      return bit;
+    }
+    int decodeBits(int n) { c1 = 1; const int mask = (1 << n) - 1; do { decodeBit(); n--; } while (n != 0); return c1 & mask; }   // :1702-1715
+    int decode9Bits() { c1 = 1; for (int i = 0; i < 9; i++) decodeBit(); return c1 & 0x1FF; }                                   // :1718-1730
+  };
+
+  // findMatch, :1114-1173.  sba = (buf, length = endChunk, index = startChunk)
+  int findMatch(const u8* buf, int bufCap, int sbaLength, int sbaIndex, int pos, int key) {
+    const int base = key << logPosChecks;
+    const i32 hash32 = ROLZ1::hash(buf, pos);
+    const int counter = counters[key];
+    int bestLen = 0, bestIdx = -1;
+    const int maxMatch = std::min((int)MAX_MATCH, sbaLength - pos) - 8;
+    for (int i = counter; i > counter - posChecks; i--) {
+      i32 ref = matches[base + (i & maskChecks)];
+      if ((u32)(ref & (i32)HASH_MASK) != (u32)hash32) continue;
+      ref = (ref & ~(i32)HASH_MASK) + sbaIndex;
+      if (ref + bestLen >= bufCap || pos + bestLen >= bufCap) throw JavaException("AIOOBE in ROLZ2.findMatch");
+      if (buf[ref + bestLen] != buf[pos + bestLen]) continue;
+      int n = 0;
+      while (n < maxMatch) {
+        const u64 diff = le64(buf + ref + n) ^ le64(buf + pos + n);
+        if (diff != 0) { n += (__builtin_ctzll(diff) >> 3); break; }
+        n += 8;
+      }
+      if (n > bestLen) {
+        bestIdx = counter - i; bestLen = n;
+        if (bestLen == maxMatch) break;
+      }
+    }
+    counters[key] = (counters[key] + 1) & maskChecks;
+    matches[base + counters[key]] = hash32 | (pos - sbaIndex);
+    return (bestLen < minMatch) ? -1 : (bestIdx << 16) | (bestLen - minMatch);
+  }
+
+  // forward: outer guards ROLZCodec.java:207-237, then :1176-1294
+  bool forward(Slice& input, Slice& output) override {
+    if (input.length == 0) return true;
+    if (!basicCheck(input, output)) return false;
+    if (input.length < MIN_BLOCK_SIZE) return false;
+    if (input.arr == output.arr) return false;
+    if (input.length > MAX_BLOCK_SIZE) return false;
+    const int count = input.length;
+    if (output.length - output.index < getMaxEncodedLength(count)) return false;
+    const u8* src = input.p(); u8* dst = output.p();
+    const int srcEnd = input.index + count - 4;
+    put_be32(dst + output.index, (u32)count);
+    int sizeChunk = std::min(count, (int)CHUNK_SIZE);
+    int startChunk = input.index;
+    minMatch = MIN_MATCH3;
+    int delta = 2, flags = 0;
+    if (ctx != nullptr) {
+      int dtp = ctx->dataType;
+      if (dtp == DT_UNDEFINED) {
+        int freqs0[257];
+        histogramOrder0(src, 0, count, freqs0, false);
+        dtp = detectSimpleType(count, freqs0);
+        if (dtp != DT_UNDEFINED) ctx->dataType = dtp;
+      }
+      if (dtp == DT_EXE) { delta = 3; flags |= 8; }
+      else if (dtp == DT_DNA) { delta = 8; minMatch = MIN_MATCH7; flags |= 4; }
+    }
+    const int mm = minMatch, dt = delta;
+    dst[output.index + 4] = (u8)flags;
+    int sbaIndex = output.index + 5;
+    Coder re(9, logPosChecks, dst, output.cap(), &sbaIndex);
+    int srcIdx = input.index;
+    std::fill(counters.begin(), counters.end(), 0);
+    while (startChunk < srcEnd) {
+      std::fill(matches.begin(), matches.end(), 0);
+      const int endChunk = std::min(startChunk + sizeChunk, srcEnd);
+      srcIdx = startChunk;
+      const int n = std::min(srcEnd - startChunk, 8);
+      re.setContext(LITERAL_CTX, 0);
+      for (int j = 0; j < n; j++) { re.encode9Bits((LITERAL_FLAG << 8) | src[srcIdx]); srcIdx++; }
+      while (srcIdx < endChunk) {
+        re.setContext(LITERAL_CTX, src[srcIdx - 1]);
+        const int key = (mm == MIN_MATCH3) ? ROLZ1::getKey1(src, srcIdx - dt) : ROLZ1::getKey2(src, srcIdx - dt);
+        const int match = findMatch(src, input.cap(), endChunk, startChunk, srcIdx, key);
+        if (match < 0) { re.encode9Bits((LITERAL_FLAG << 8) | src[srcIdx]); srcIdx++; continue; }
+        const int matchLen = match & 0xFFFF;
+        re.encode9Bits((MATCH_FLAG << 8) | matchLen);
+        re.setContext(MATCH_CTX, src[srcIdx - 1]);
+        const int matchIdx = (int)((u32)match >> 16);
+        re.encodeBits(matchIdx, logPosChecks);
+        srcIdx += (matchLen + minMatch);
+      }
+      startChunk = endChunk;
+    }
+    for (int i = 0; i < 4; i++, srcIdx++) {
+      re.setContext(LITERAL_CTX, src[srcIdx - 1]);
+      re.encode9Bits((LITERAL_FLAG << 8) | src[srcIdx]);
+    }
+    re.disposeEncoder();
+    input.index = srcIdx;
+    output.index = sbaIndex;
+    return (input.index == srcEnd + 4);            // (the second clause, (output.index - sba1.index) < count, is 0 < count: always true)
+  }
+
+  // inverse: outer guards ROLZCodec.java:239-256, then :1296-1414
+  bool inverse(Slice& input, Slice& output) override {
+    if (input.length == 0) return true;
+    if (!basicCheck(input, output)) return false;
+    if (input.arr == output.arr) return false;
+    if (input.length > MAX_BLOCK_SIZE) return false;
+    const int count = input.length;
+    u8* src = input.p(); u8* dst = output.p();
+    const int srcCap = input.cap(), dstCap = output.cap();
+    const int srcEnd = input.index + count;
+    if (input.index + 5 > srcCap) throw JavaException("AIOOBE in ROLZ2.inverse");
+    const int szBlock = (int)be32(src + input.index);
+    if ((szBlock <= 0) || (szBlock > output.length)) return false;
+    const int dstEnd = output.index + szBlock;
+    int sizeChunk = std::min(szBlock, (int)CHUNK_SIZE);
+    int startChunk = output.index;
+    minMatch = MIN_MATCH3;
+    int delta = 2;
+    int srcIdx = input.index + 4;
+    const int flags = src[srcIdx++];
+    const int bsVersion = (ctx == nullptr) ? 6 : ctx->bsVersion;
+    if (bsVersion >= 4) {
+      if ((flags & 0x0E) == 8) delta = 3;
+      else if ((flags & 0x0E) == 4) { delta = 8; minMatch = MIN_MATCH7; }
+    } else if ((bsVersion >= 3) && (flags == 1)) minMatch = MIN_MATCH7;
+    const int mm = minMatch, dt = delta;
+    int sbaIndex = srcIdx;
+    Coder rd(9, logPosChecks, src, srcCap, &sbaIndex);
+    rd.initDecoder();
+    std::fill(counters.begin(), counters.end(), 0);
+    auto put = [&](int i, int v) { if (i < 0 || i >= dstCap) throw JavaException("AIOOBE in ROLZ2.inverse"); dst[i] = (u8)v; };
+    auto at = [&](int i) -> int { if (i < 0 || i >= dstCap) throw JavaException("AIOOBE in ROLZ2.inverse"); return dst[i]; };
+    while (startChunk < dstEnd) {
+      std::fill(matches.begin(), matches.end(), 0);
+      const int endChunk = (startChunk + sizeChunk < dstEnd) ? startChunk + sizeChunk : dstEnd;
+      int dstIdx = output.index;
+      const int n = (bsVersion < 3) ? 2 : std::min(dstEnd - startChunk, 8);
+      rd.setContext(LITERAL_CTX, 0);
+      for (int j = 0; j < n; j++) {
+        const int val1 = rd.decode9Bits();
+        if ((val1 >> 8) == MATCH_FLAG) { output.index = dstIdx; return false; }
+        put(dstIdx++, val1);
+      }
+      while (dstIdx < endChunk) {
+        const int savedIdx = dstIdx;
+        if (dstIdx - dt < 0 || dstIdx - dt + (mm == MIN_MATCH3 ? 2 : 8) > dstCap) throw JavaException("AIOOBE in ROLZ2.inverse");
+        const int key = (mm == MIN_MATCH3) ? ROLZ1::getKey1(dst, dstIdx - dt) : ROLZ1::getKey2(dst, dstIdx - dt);
+        const int base = key << logPosChecks;
+        rd.setContext(LITERAL_CTX, (u8)at(dstIdx - 1));
+        const int val = rd.decode9Bits();
+        if ((val >> 8) == LITERAL_FLAG) {
+          put(dstIdx++, val);
+        } else {
+          const int matchLen = val & 0xFF;
+          if (dstIdx + matchLen + 3 > dstEnd) { output.index = dstIdx; return false; }
+          rd.setContext(MATCH_CTX, (u8)at(dstIdx - 1));
+          const int matchIdx = rd.decodeBits(logPosChecks);
+          const int ref = output.index + matches[base + ((counters[key] - matchIdx) & maskChecks)];
+          const int len = matchLen + mm;
+          if (ref < 0 || dstIdx + len > dstCap) throw JavaException("AIOOBE in ROLZ2 emitCopy");
+          for (int k = 0; k < len; k++) dst[dstIdx + k] = dst[ref + k];
+          dstIdx += len;
+        }
+        counters[key] = (counters[key] + 1) & maskChecks;
+        matches[base + counters[key]] = savedIdx - output.index;
+      }
+      startChunk = endChunk;
+      output.index = dstIdx;
+    }
+    input.index = sbaIndex;
+    return input.index == srcEnd;
+  }
+};
+
 // ---- RLT (transform/RLT.java) ---------------------------------------------------------------------------------------------------
 struct RLT : Transform {
   enum { RUN_LEN_ENCODE1 = 224, RUN_LEN_ENCODE2 = (255 - RUN_LEN_ENCODE1) << 8, RUN_THRESHOLD = 3,
@@ -1611,6 +1853,7 @@ static inline std::unique_ptr<Transform> newTransform(Ctx& ctx, int type) {
     case T_LZP: ctx.lzType = T_LZP; return std::unique_ptr<Transform>(new LZP());
     case T_RLT: return std::unique_ptr<Transform>(new RLT(&ctx));
     case T_ROLZ: return std::unique_ptr<Transform>(new ROLZ1(&ctx));
+    case T_ROLZX: ctx.rolzExtra = 1; return std::unique_ptr<Transform>(new ROLZ2(&ctx));
     case T_BWT: return std::unique_ptr<Transform>(new BWTBlockCodec(ctx));
     case T_RANK: ctx.sbrtMode = 2; return std::unique_ptr<Transform>(new SBRT(2));
     case T_MTFT: ctx.sbrtMode = 1; return std::unique_ptr<Transform>(new SBRT(1));

@@ -1,7 +1,7 @@
 /*
  * kzg_sibling_check.c — TEST INFRASTRUCTURE: a torch-free parity check of the LZP stage on a real GPU, for when a box is only
  * available for a minute (no Python start-up): libkanzi_b200 (linked) against the oracle (dlopen of oracle/libkzoracle.so), on
- * word-salad text with long re-pasted passages, flag bytes sprinkled in, and of the RLT stage on run-heavy bytes.
+ * word-salad text with long re-pasted passages, flag bytes sprinkled in, of the RLT stage on run-heavy bytes and of ROLZX on both.
  *   A  per-block LZP forward vs the oracle's bytes, inverse of those bytes vs the input     (kzg_transform_forward / _inverse)
  *   B  whole streams through chains with LZP vs the oracle's stream, then kzg_decompress    (kzg_compress / kzg_decompress)
  *   C  the same for LZ&ANS0 and ROLZ&ANS0: the chains that existed before must still match
@@ -55,6 +55,46 @@ static void fill_runs(uint8_t* p, size_t n) {
     if ((r & 0x7F00) == 0) len = 60000 + rnd() % 30000;
     for (size_t k = 0; k < len && o < n; k++) p[o++] = v;
   }
+}
+
+/* ROLZX per-block: forward bytes and data type against the oracle, inverse of the oracle's bytes, a destination one byte short */
+static void check_rolzx(const uint8_t* d, int32_t n, const char* tag) {
+  char what[128], detail[256] = "";
+  const int32_t cap = n <= 16384 ? n + 1024 : n + n / 32;
+  uint8_t* ref = (uint8_t*)calloc((size_t)cap + 64, 1); uint8_t* got = (uint8_t*)calloc((size_t)cap + 64, 1); uint8_t* back = (uint8_t*)calloc((size_t)n + 64, 1);
+  int32_t cv[6] = {7, n > 1024 ? n : 1024, n, 1, 0, 0}, su = 0, du = 0, gsu = 0, gdu = 0;
+  const int okRef = kzo_transform(KZG_T_ROLZX, 0, cv, d, n, n, ref, cap, cap, &su, &du);
+  kzg_ctx ctx = {7, n > 1024 ? n : 1024, n, 1, 0, 0};
+  double t0 = now();
+  const int ok = kzg_transform_forward(KZG_T_ROLZX, &ctx, d, n, got, cap, cap, &gsu, &gdu);
+  const double tf = now() - t0;
+  snprintf(what, sizeof(what), "A ROLZX forward %s n=%d", tag, n);
+  int good = (ok == okRef) && ctx.dataType == cv[4] && (!ok || (gdu == du && gsu == su && memcmp(got, ref, (size_t)du) == 0));
+  snprintf(detail, sizeof(detail), "(ok %d/%d, bytes %d/%d, type %d/%d, %.1f ms) %s", ok, okRef, gdu, du, ctx.dataType, cv[4], 1e3 * tf, good ? "" : kzg_last_error());
+  verdict(what, good, detail);
+  if (okRef == 1) {
+    int32_t isu = 0, idu = 0;
+    t0 = now();
+    const int oki = kzg_transform_inverse(KZG_T_ROLZX, &ctx, ref, du, back, n, n, &isu, &idu);
+    const double ti = now() - t0;
+    snprintf(what, sizeof(what), "A ROLZX inverse %s n=%d", tag, n);
+    good = (oki == 1) && idu == n && isu == du && memcmp(back, d, (size_t)n) == 0;
+    snprintf(detail, sizeof(detail), "(ok %d, bytes %d, used %d/%d, %.1f ms) %s", oki, idu, isu, du, 1e3 * ti, good ? "" : kzg_last_error());
+    verdict(what, good, detail);
+    const int k2 = kzg_transform_inverse(KZG_T_ROLZX, &ctx, ref, du, back, n - 1, n - 1, &isu, &idu);
+    snprintf(what, sizeof(what), "A ROLZX inverse short dst %s n=%d", tag, n);
+    snprintf(detail, sizeof(detail), "(%d)", k2);
+    verdict(what, k2 == 0, detail);
+    if (du > 40) {                                          /* a truncated stream: refused by both */
+      int32_t cv2[6] = {7, n, n, 1, 0, 0}, osu = 0, odu = 0;
+      const int o3 = kzo_transform(KZG_T_ROLZX, 1, cv2, ref, du / 2, du / 2, got, n, n, &osu, &odu);
+      const int k3 = kzg_transform_inverse(KZG_T_ROLZX, &ctx, ref, du / 2, back, n, n, &isu, &idu);
+      snprintf(what, sizeof(what), "A ROLZX inverse truncated %s n=%d", tag, n);
+      snprintf(detail, sizeof(detail), "(%d/%d)", k3, o3);
+      verdict(what, k3 == (o3 < 0 ? 0 : o3), detail);
+    }
+  }
+  free(ref); free(got); free(back);
 }
 
 /* RLT per-block: entropy id e decides the escape byte (ctx flags bits 8-11 on our side, ctxv[5] >> 8 on the oracle's) */
@@ -174,6 +214,17 @@ int main(int argc, char** argv) {
   check_stream("B RLT&FPAQ", rr, (int64_t)N, rlt, 1, KZG_E_FPAQ, 1 << 20);
   check_stream("B RLT+LZP&HUFFMAN", rr, (int64_t)1 << 21, rltlzp, 2, KZG_E_HUFFMAN, 1 << 19);
   check_stream("B RLT&NONE text", d, 700001, rlt, 1, KZG_E_NONE, 1 << 16);
+  const int32_t xsizes[] = {63, 64, 5000, 70001, 1 << 20};
+  for (unsigned i = 0; i < sizeof(xsizes) / sizeof(xsizes[0]); i++) check_rolzx(d + i * 777, xsizes[i], "text");
+  check_rolzx(rr, 300000, "runs");
+  { uint8_t* z = (uint8_t*)malloc(60000); for (int i = 0; i < 60000; i++) z[i] = "ACGT"[(rnd() >> 3) & 3]; memcpy(z + 30000, z + 1000, 20000); check_rolzx(z, 60000, "dna"); free(z); }
+  { const int32_t big = (17 << 20) + 4321; uint8_t* z = (uint8_t*)calloc((size_t)big + 64, 1);                /* two 16 MiB chunks: mostly zeros, a short passage every 64 KiB */
+    for (int32_t o = 0; o + 64 < big; o += 65536) memcpy(z + o, d + (o >> 10), 48);
+    check_rolzx(z, big, "two chunks"); free(z); }
+  const int32_t rx[] = {KZG_T_ROLZX}, rxz[] = {KZG_T_RLT, KZG_T_ROLZX};
+  check_stream("B ROLZX&NONE", d, (int64_t)N, rx, 1, KZG_E_NONE, 1 << 18);
+  check_stream("B ROLZX&ANS0", d, (int64_t)1 << 21, rx, 1, KZG_E_ANS0, 1 << 20);
+  check_stream("B RLT+ROLZX&HUFFMAN", rr, (int64_t)1 << 21, rxz, 2, KZG_E_HUFFMAN, 1 << 19);
   const int32_t lzp[] = {KZG_T_LZP}, lzpz[] = {KZG_T_LZP, KZG_T_ZRLT}, lz[] = {KZG_T_LZ}, rolz[] = {KZG_T_ROLZ}, rl[] = {KZG_T_ROLZ, KZG_T_LZP};
   check_stream("B LZP&ANS0", d, (int64_t)N, lzp, 1, KZG_E_ANS0, 1 << 20);
   check_stream("B LZP+ZRLT&HUFFMAN", d, (int64_t)N, lzpz, 2, KZG_E_HUFFMAN, 1 << 18);

@@ -1,5 +1,5 @@
-"""GPU parity of the sibling codecs added after the five BASELINE chains: LZP (K/transform/LZCodec.java:973-1287)
-and RLT (K/transform/RLT.java), against the oracle through the C ABI, bit for bit.  The same checks, torch-free, are what
+"""GPU parity of the sibling codecs added after the five BASELINE chains: LZP (K/transform/LZCodec.java:973-1287),
+RLT (K/transform/RLT.java) and ROLZX (K/transform/ROLZCodec.java:1016-1770), against the oracle through the C ABI, bit for bit.  The same checks, torch-free, are what
 tests/native/kzg_sibling_check.c runs (profiles/r02_sibling_check.log is its output on a B200)."""
 import numpy as np
 import pytest
@@ -133,6 +133,69 @@ def runs_input(n, seed):
 @pytest.mark.parametrize("tr,ent,bs", [(["RLT"], "ANS0", 1 << 18), (["RLT"], "FPAQ", 1 << 20), (["RLT", "LZP"], "HUFFMAN", 1 << 19), (["RLT"], "NONE", 1 << 16)])
 def test_rlt_streams_bit_exact(tr, ent, bs):
     d = runs_input(2_000_000, 5) + synth.text(300_000, 3).tobytes() + bytes(70000) + b"tail!"
+    ref = O.compress(d, tr, ent, bs)
+    got = K.compress(d, tr, ent, bs, flags=K.FLAG_BWT_ASREF)
+    assert len(got) == len(ref) and got == ref, (tr, ent, len(got), len(ref), "first differing byte", first_diff(got, ref))
+    assert K.decompress(ref, len(d) + 1024, flags=K.FLAG_BWT_ASREF) == d
+
+
+# ---- ROLZX = ROLZCodec2 (K/transform/ROLZCodec.java:1016-1428) --------------------------------------------------------------------
+from test_sibling_hostcheck import rolzx_inputs
+
+
+def test_rolzx_transform_bit_exact():
+    applied = 0
+    for d in rolzx_inputs():
+        ok_ref, ref, _, cv = O.transform("ROLZX", d)
+        kctx = {"blockSize": max(len(d), 1024), "size": len(d), "flags": 0}
+        ok, got, used = K.transform_forward("ROLZX", d, kctx)
+        assert int(ok) == ok_ref and kctx["dataType"] == cv[4], (len(d), ok, ok_ref, kctx["dataType"], cv[4])
+        if not ok:
+            continue
+        applied += 1
+        assert used == len(d) and got == ref, (len(d), len(got), len(ref), "first differing byte", first_diff(got, ref))
+        ok2, back, used2 = K.transform_inverse("ROLZX", ref, {"blockSize": max(len(d), 1024), "flags": 0}, dst_cap=len(d))
+        assert ok2 and back == d and used2 == len(ref), (len(d), first_diff(back, d))
+        assert not K.transform_inverse("ROLZX", ref, {"blockSize": max(len(d), 1024), "flags": 0}, dst_cap=len(d) - 1)[0]
+        assert not K.transform_inverse("ROLZX", ref[:len(ref) // 2], {"blockSize": max(len(d), 1024), "flags": 0}, dst_cap=len(d))[0]
+    assert applied >= 35
+
+
+def test_rolzx_inverse_of_corrupt_streams_fails_like_the_oracle():
+    r = np.random.default_rng(12)
+    d = synth.text(40000, 2).tobytes()
+    ok, ref, _, _ = O.transform("ROLZX", d)
+    assert ok == 1
+    for k in range(24):
+        bad = bytearray(ref)
+        for _ in range(1 + k % 3):
+            bad[int(r.integers(5 if k % 4 else 0, len(bad)))] ^= 1 << int(r.integers(0, 8))
+        o = O.transform("ROLZX", bytes(bad), inverse=True, dst_cap=len(d), dst_len=len(d))
+        g = K.transform_inverse("ROLZX", bytes(bad), {"blockSize": len(d), "flags": 0}, dst_cap=len(d))
+        assert bool(g[0]) == (o[0] == 1), k
+        if g[0]:
+            assert g[1] == o[1]
+    assert K.transform_inverse("ROLZX", ref, {"blockSize": len(d), "flags": 0}, dst_cap=len(d))[1] == d
+
+
+def test_rolzx_block_of_two_chunks():
+    """a block over 16 MiB: the ring table is cleared between the chunks, the coder and the counters carry over (ROLZCodec.java:1235-1283)"""
+    n = (17 << 20) + 4321
+    a = np.zeros(n, dtype=np.uint8)
+    t = np.frombuffer(synth.text(20000, 6).tobytes(), dtype=np.uint8)
+    for o in range(0, n - 64, 65536):
+        a[o:o + 48] = t[(o >> 10) % 19000:(o >> 10) % 19000 + 48]
+    d = a.tobytes()
+    ok_ref, ref, _, _ = O.transform("ROLZX", d)
+    ok, got, used = K.transform_forward("ROLZX", d, {"blockSize": n, "size": n, "flags": 0})
+    assert ok_ref == 1 and ok and got == ref and used == n
+    ok2, back, _ = K.transform_inverse("ROLZX", ref, {"blockSize": n, "flags": 0}, dst_cap=n)
+    assert ok2 and back == d
+
+
+@pytest.mark.parametrize("tr,ent,bs", [(["ROLZX"], "NONE", 1 << 18), (["ROLZX"], "ANS0", 1 << 20), (["RLT", "ROLZX"], "HUFFMAN", 1 << 19)])
+def test_rolzx_streams_bit_exact(tr, ent, bs):
+    d = (runs_input(1_500_000, 5) if "RLT" in tr else b"") + pasted_text(1_500_000, 11) + bytes(70000) + b"tail!"
     ref = O.compress(d, tr, ent, bs)
     got = K.compress(d, tr, ent, bs, flags=K.FLAG_BWT_ASREF)
     assert len(got) == len(ref) and got == ref, (tr, ent, len(got), len(ref), "first differing byte", first_diff(got, ref))

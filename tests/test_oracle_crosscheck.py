@@ -1551,3 +1551,262 @@ def test_rlt_agrees_with_the_oracle_both_ways(entropy):
             p = rlt_inverse(ref[:cut], len(d))
             assert o[0] == (-1 if p[0] is None else int(p[0])) and (o[0] != 1 or o[1] == p[1]), (len(d), "cut", cut)
     assert applied >= 8
+
+
+# ---- ROLZX: K/transform/ROLZCodec.java:1176-1294 (ROLZCodec2.forward), :1114-1173 (findMatch), :1296-1414 (inverse),
+#      ROLZEncoder :1431-1597, ROLZDecoder :1599-1770 ---------------------------------------------------------------------------------
+class _RolzCoder:
+    """the adaptive binary arithmetic coder; Java `long` arithmetic = 64-bit wrap, kept with explicit masks"""
+    def __init__(self, buf, index, decode):
+        self.low, self.high = 0, 0x00FFFFFFFFFFFFFF
+        self.probs = [[0xFFFF >> 1] * (256 << 9), [0xFFFF >> 1] * (256 << 5)]      # LITERAL_CTX = 0 (9 bits), MATCH_CTX = 1 (logPosChecks = 5)
+        self.shift = (9, 5)
+        self.buf, self.index = buf, index
+        self.c1, self.ctx, self.p = 1, 0, self.probs[0]
+        if decode:
+            self.current = int.from_bytes(bytes(buf[index:index + 8]).ljust(8, b"\0"), "big")
+            if index + 8 > len(buf):
+                raise IndexError
+            self.index += 8
+
+    def set_context(self, n, byte):
+        self.p = self.probs[n]
+        self.ctx = byte << self.shift[n]
+
+    def encode_bit(self, bit):
+        i = self.ctx + self.c1
+        pr = self.p[i]
+        split = ((((self.high - self.low) & M64) >> 4) * (pr >> 4) & M64) >> 8
+        if bit == 0:
+            self.low = (self.low + split + 1) & M64
+            self.p[i] = pr - (pr >> 5)
+            self.c1 += self.c1
+        else:
+            self.high = (self.low + split) & M64
+            self.p[i] = pr - (((pr - 0xFFFF) >> 5) + 1)
+            self.c1 += self.c1 + 1
+        while ((self.low ^ self.high) >> 24) == 0:
+            self.buf[self.index:self.index + 4] = ((self.high >> 32) & 0xFFFFFFFF).to_bytes(4, "big")
+            self.index += 4
+            self.low = (self.low << 32) & M64
+            self.high = ((self.high << 32) | 0xFFFFFFFF) & M64
+
+    def encode(self, val, nbits):
+        self.c1 = 1
+        for k in range(nbits - 1, -1, -1):
+            self.encode_bit(val & (1 << k))
+
+    def finish(self):
+        self.buf[self.index:self.index + 8] = self.low.to_bytes(8, "big")
+        self.index += 8
+
+    def decode_bit(self):
+        i = self.ctx + self.c1
+        pr = self.p[i]
+        mid = (self.low + (((((self.high - self.low) & M64) >> 4) * (pr >> 4) & M64) >> 8)) & M64
+        signed = lambda v: v - (1 << 64) if v >> 63 else v
+        if signed(mid) >= signed(self.current):
+            self.high = mid
+            self.p[i] = pr - (((pr - 0xFFFF) >> 5) + 1)
+            self.c1 += self.c1 + 1
+        else:
+            self.low = (mid + 1) & M64
+            self.p[i] = pr - (pr >> 5)
+            self.c1 += self.c1
+        while ((self.low ^ self.high) >> 24) == 0:
+            self.low = (self.low << 32) & 0x00FFFFFFFFFFFFFF
+            self.high = ((self.high << 32) | 0xFFFFFFFF) & 0x00FFFFFFFFFFFFFF
+            if self.index + 4 > len(self.buf):
+                raise IndexError
+            self.current = ((self.current << 32) | int.from_bytes(self.buf[self.index:self.index + 4], "big")) & 0x00FFFFFFFFFFFFFF
+            self.index += 4
+
+    def decode(self, nbits):
+        self.c1 = 1
+        for _ in range(nbits):
+            self.decode_bit()
+        return self.c1 & ((1 << nbits) - 1)
+
+
+def _rolz_key(buf, i, mm):
+    if mm == 3:
+        return buf[i] | (buf[i + 1] << 8)
+    return (((int.from_bytes(buf[i:i + 8], "little") * 200002979) & M64) >> 40) & 0xFFFF
+
+
+def rolzx_forward(src, data_type=0):
+    """-> (ok, out, data type after the call) for a non-null ctx; ok None where the Java code would throw"""
+    M32, HMASK = 0xFFFFFFFF, 0xFF000000
+    count = len(src)
+    if count == 0:
+        return True, b"", data_type
+    if count < 64:
+        return False, b"", data_type
+    src_end = count - 4
+    dst = bytearray(count + 1024 if count <= 16384 else count + count // 32)
+    dst[0:4] = count.to_bytes(4, "big")
+    if data_type == 0:
+        f = [0] * 256
+        for b in src:
+            f[b] += 1
+        data_type = _detect_simple_type(count, f)
+    mm, dt, flags = 3, 2, 0
+    if data_type == 3:
+        dt, flags = 3, 8
+    elif data_type == 6:
+        dt, mm, flags = 8, 7, 4
+    dst[4] = flags
+    re = _RolzCoder(dst, 5, False)
+    counters = [0] * 65536
+    size_chunk = min(count, 16 << 20)
+    start = 0
+    si = 0
+    try:
+        while start < src_end:
+            matches = [0] * (65536 << 5)
+            end_chunk = min(start + size_chunk, src_end)
+            si = start
+            re.set_context(0, 0)
+            for _ in range(min(src_end - start, 8)):
+                re.encode((1 << 8) | src[si], 9)
+                si += 1
+            while si < end_chunk:
+                re.set_context(0, src[si - 1])
+                key = _rolz_key(src, si - dt, mm)
+                base = key << 5
+                h32 = ((((int.from_bytes(src[si:si + 4], "little") << 8) & M32) * 200002979) & M32) & HMASK
+                counter = counters[key]
+                best_len, best_idx = 0, -1
+                max_match = min(3 + 255, end_chunk - si) - 8
+                for i in range(counter, counter - 32, -1):
+                    ref = matches[base + (i & 31)]
+                    if (ref & HMASK) != h32:
+                        continue
+                    ref = (ref & 0xFFFFFF) + start
+                    if src[ref + best_len] != src[si + best_len]:
+                        continue
+                    n = 0
+                    while n < max_match:
+                        x = int.from_bytes(src[ref + n:ref + n + 8], "little") ^ int.from_bytes(src[si + n:si + n + 8], "little")
+                        if x:
+                            n += ((x & -x).bit_length() - 1) >> 3
+                            break
+                        n += 8
+                    if n > best_len:
+                        best_idx, best_len = counter - i, n
+                        if best_len == max_match:
+                            break
+                counters[key] = (counters[key] + 1) & 31
+                matches[base + counters[key]] = h32 | (si - start)
+                if best_len < mm:
+                    re.encode((1 << 8) | src[si], 9)
+                    si += 1
+                    continue
+                re.encode(best_len - mm, 9)                     # MATCH_FLAG = 0 in bit 8
+                re.set_context(1, src[si - 1])
+                re.encode(best_idx, 5)
+                si += best_len
+            start = end_chunk
+        for _ in range(4):
+            re.set_context(0, src[si - 1])
+            re.encode((1 << 8) | src[si], 9)
+            si += 1
+        re.finish()
+        if re.index > len(dst):
+            return None, b"", data_type
+    except IndexError:
+        return None, b"", data_type
+    return si == src_end + 4, bytes(dst[:re.index]), data_type
+
+
+def rolzx_inverse(src, dst_len):
+    """-> (ok, out); ok None where the Java code would throw.  dst_len = dst slice length = array length here"""
+    count = len(src)
+    if count == 0:
+        return True, b""
+    try:
+        if count < 5:
+            raise IndexError
+        sz = int.from_bytes(src[0:4], "big")
+        if sz >= 1 << 31:
+            sz -= 1 << 32
+        if sz <= 0 or sz > dst_len:
+            return False, b""
+        flags = src[4]
+        mm, dt = 3, 2
+        if (flags & 0x0E) == 8:
+            dt = 3
+        elif (flags & 0x0E) == 4:
+            dt, mm = 8, 7
+        rd = _RolzCoder(src, 5, True)
+        counters = [0] * 65536
+        dst = bytearray()
+        size_chunk = min(sz, 16 << 20)
+        start = 0
+        while start < sz:
+            matches = [0] * (65536 << 5)
+            end_chunk = min(start + size_chunk, sz)
+            base0 = len(dst)                                      # output.index
+            rd.set_context(0, 0)
+            for _ in range(min(sz - start, 8)):
+                v = rd.decode(9)
+                if (v >> 8) == 0:
+                    return False, bytes(dst)
+                dst.append(v & 0xFF)
+            while len(dst) < end_chunk:
+                saved = len(dst)
+                if saved - dt < 0:
+                    raise IndexError
+                key = _rolz_key(bytes(dst[saved - dt:saved - dt + 8]).ljust(8, b"\0"), 0, mm)
+                base = key << 5
+                rd.set_context(0, dst[-1])
+                v = rd.decode(9)
+                if (v >> 8) == 1:
+                    dst.append(v & 0xFF)
+                else:
+                    m_len = v & 0xFF
+                    if len(dst) + m_len + 3 > sz:
+                        return False, bytes(dst)
+                    rd.set_context(1, dst[-1])
+                    m_idx = rd.decode(5)
+                    ref = base0 + matches[base + ((counters[key] - m_idx) & 31)]
+                    if len(dst) + m_len + mm > dst_len:
+                        raise IndexError
+                    for k in range(m_len + mm):
+                        dst.append(dst[ref + k])
+                counters[key] = (counters[key] + 1) & 31
+                matches[base + counters[key]] = saved - base0
+            start = end_chunk
+        return rd.index == count, bytes(dst)
+    except IndexError:
+        return None, b""
+
+
+def _rolzx_cases():
+    from kanzi_b200 import synth
+    r = np.random.default_rng(61)
+    dna = bytes(np.frombuffer(b"ACGT", dtype=np.uint8)[r.integers(0, 4, 3000)])
+    return [synth.text(12000, 5).tobytes(), synth.exe_like(15000, 6).tobytes(), synth.records(10000, 7).tobytes(), (b"0123456789abcdef" * 7 + b"Z") * 120,
+            bytes(20000), dna + dna[500:2500] + dna[:900], bytes(r.integers(0, 256, 3000, dtype=np.uint8)), b"ab" * 32, b"xyz" * 21, b"q" * 63,
+            bytes(r.integers(0, 3, 5000, dtype=np.uint8))]
+
+
+def test_rolzx_agrees_with_the_oracle_both_ways():
+    applied = 0
+    for d in _rolzx_cases():
+        ok_ref, ref, used, cv = O.transform("ROLZX", d)
+        ok, got, dt = rolzx_forward(d)
+        assert ok is not None and int(ok) == ok_ref and dt == cv[4], (len(d), ok, ok_ref, dt, cv[4])
+        if not ok:
+            continue
+        applied += 1
+        assert got == ref and used == len(d), (len(d), len(got), len(ref))
+        o = O.transform("ROLZX", ref, inverse=True, dst_cap=len(d), dst_len=len(d))
+        p = rolzx_inverse(ref, len(d))
+        assert o[0] == 1 and p[0] is True and o[1] == d and p[1] == d and o[2] == len(ref)
+        assert O.transform("ROLZX", ref, inverse=True, dst_cap=len(d) - 1, dst_len=len(d) - 1)[0] == 0 and rolzx_inverse(ref, len(d) - 1)[0] is False
+        for cut in (len(ref) // 2, len(ref) - 4):
+            o = O.transform("ROLZX", ref[:cut], inverse=True, dst_cap=len(d), dst_len=len(d))
+            p = rolzx_inverse(ref[:cut], len(d))
+            assert o[0] == (-1 if p[0] is None else int(p[0])), (len(d), cut, o[0], p[0])
+    assert applied >= 8

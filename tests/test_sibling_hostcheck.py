@@ -16,7 +16,7 @@ import oracle_lib as O
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "native", "sibling_hostcheck.cpp")
 LIB = os.path.join(HERE, "native", "libsibling_hostcheck.so")
-CORES = [os.path.join(HERE, "..", "kanzi_b200", "csrc", f) for f in ("lzp_core.cuh", "rlt_core.cuh")]
+CORES = [os.path.join(HERE, "..", "kanzi_b200", "csrc", f) for f in ("lzp_core.cuh", "rlt_core.cuh", "rolzx_core.cuh")]
 u8p = C.POINTER(C.c_uint8)
 
 
@@ -29,6 +29,8 @@ def host():
     L.lzp_host_inverse.argtypes = [u8p, C.c_int, u8p, C.c_int, C.POINTER(C.c_int)]
     L.rlt_host_forward.argtypes = [u8p, C.c_int, u8p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.rlt_host_inverse.argtypes = [u8p, C.c_int, u8p, C.c_int, C.POINTER(C.c_int)]
+    L.rolzx_host_forward.argtypes = [u8p, C.c_int, u8p, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    L.rolzx_host_inverse.argtypes = [u8p, C.c_int, u8p, C.c_int, C.POINTER(C.c_int)]
     return L
 
 
@@ -213,6 +215,84 @@ def test_rlt_corrupt_streams_fail_alike(host):
             bad[int(r.integers(0, len(bad)))] = int(r.choice([ref[0], 0xFF, 0xE0, 0x00, int(r.integers(0, 256))]))
         o = O.transform("RLT", bytes(bad), inverse=True, dst_cap=len(d), dst_len=len(d))
         h = _rlt_inv(host, bytes(bad), len(d))
+        assert max(o[0], 0) == h[0], k
+        if h[0]:
+            assert o[1] == h[1]
+
+
+# ---- ROLZX ----------------------------------------------------------------------------------------------------------------------
+def rolzx_inputs():
+    from kanzi_b200 import synth
+    from test_oracle_crosscheck import _rolzx_cases
+    r = np.random.default_rng(71)
+    t = synth.text(300_000, 8).tobytes()
+    out = list(_rolzx_cases()) + [t, t[:70000] + t[1000:40000], synth.exe_like(200_000, 3).tobytes(), synth.records(150_000, 5).tobytes(), bytes(100_000),
+                                  bytes(r.integers(0, 256, 50_000, dtype=np.uint8)), (b"ACGTTGCA" * 9 + b"N") * 800, t[:64], t[:65], t[:71], t[:72], t[:73]]
+    for k in range(25):
+        n = int(r.integers(64, 20000))
+        base = bytearray(r.integers(0, int(r.choice([2, 4, 16, 256])), n, dtype=np.uint8).tobytes())
+        for _ in range(int(r.integers(0, 20))):
+            a, ln, b = int(r.integers(0, n)), int(r.integers(3, 400)), int(r.integers(0, n))
+            seg = bytes(base[a:a + ln])
+            base[b:b + len(seg)] = seg
+        out.append(bytes(base[:n]))
+    return out
+
+
+def _rolzx_fwd(L, d, dt):
+    g = _Guarded(d)
+    cap = len(d) + 1024 if len(d) <= 16384 else len(d) + len(d) // 32
+    dst = np.full(cap + 64, 0xA5, dtype=np.uint8)
+    n = C.c_int(0)
+    ok = L.rolzx_host_forward(g.ptr, len(d), dst.ctypes.data_as(u8p), cap, dt, C.byref(n))
+    assert (dst[cap:] == 0xA5).all()
+    return ok, dst[:n.value].tobytes()
+
+
+def _rolzx_inv(L, s, dst_len):
+    g = _Guarded(s)
+    dst = np.full(dst_len + 64, 0xA5, dtype=np.uint8)
+    n = C.c_int(0)
+    ok = L.rolzx_host_inverse(g.ptr, len(s), dst.ctypes.data_as(u8p), dst_len, C.byref(n))
+    assert (dst[dst_len:] == 0xA5).all()
+    return ok, dst[:n.value].tobytes()
+
+
+def test_rolzx_device_loops_on_the_host_match_the_oracle(host):
+    applied = 0
+    for d in rolzx_inputs():
+        ok_ref, ref, _, cv = O.transform("ROLZX", d)
+        if len(d) < 64:
+            assert ok_ref == 0
+            continue
+        ok, got = _rolzx_fwd(host, d, cv[4])                      # (the kernel's histogram step decides the type; here the oracle's answer)
+        assert ok == ok_ref, (len(d), ok, ok_ref)
+        if ok != 1:
+            continue
+        applied += 1
+        assert got == ref, (len(d), len(got), len(ref))
+        assert _rolzx_inv(host, ref, len(d)) == (1, d)
+        assert _rolzx_inv(host, ref, len(d) + 500) == (1, d)
+        assert _rolzx_inv(host, ref, len(d) - 1)[0] == 0
+        for cut in (len(ref) // 2, len(ref) - 4, 13):
+            o = O.transform("ROLZX", ref[:cut], inverse=True, dst_cap=len(d), dst_len=len(d))
+            h = _rolzx_inv(host, ref[:cut], len(d))
+            assert max(o[0], 0) == h[0], (len(d), cut)
+    assert applied >= 35
+
+
+def test_rolzx_corrupt_streams_fail_alike(host):
+    from kanzi_b200 import synth
+    r = np.random.default_rng(12)
+    d = synth.text(40000, 2).tobytes()
+    ok, ref, _, _ = O.transform("ROLZX", d)
+    assert ok == 1
+    for k in range(40):
+        bad = bytearray(ref)
+        for _ in range(1 + k % 3):
+            bad[int(r.integers(5 if k % 4 else 0, len(bad)))] ^= 1 << int(r.integers(0, 8))
+        o = O.transform("ROLZX", bytes(bad), inverse=True, dst_cap=len(d), dst_len=len(d))
+        h = _rolzx_inv(host, bytes(bad), len(d))
         assert max(o[0], 0) == h[0], k
         if h[0]:
             assert o[1] == h[1]
