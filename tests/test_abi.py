@@ -47,6 +47,15 @@ def test_max_encoded_len_matches_reference_formulas():
         assert K.transform_max_encoded_len("SRT", n) == n + 1024
         for t in ("RANK", "MTFT", "ZRLT", "NONE"):
             assert K.transform_max_encoded_len(t, n) == n
+    # the sibling codecs: LZCodec.java:1283-1285 (LZP), RLT.java:355-357, ROLZCodec.java:1417-1421 (ROLZX); and the oracle agrees on all of them
+    import oracle_lib as O
+    for n in (1, 100, 512, 513, 1024, 1025, 16384, 16385, 65536, 4 << 20):
+        assert K.transform_max_encoded_len("LZP", n) == (n + 16 if n <= 1024 else n + n // 64)
+        assert K.transform_max_encoded_len("RLT", n) == (n + 32 if n <= 512 else n)
+        assert K.transform_max_encoded_len("ROLZX", n) == (n + 1024 if n <= 16384 else n + n // 32)
+        for t in K.T:
+            assert K.transform_max_encoded_len(t, n) == O.lib().kzo_transform_max_encoded_len(O.T[t], n), (t, n)
+    assert K.transform_max_encoded_len(2, 100) < 0          # BWTS: an id the library has no kernel for is refused, not guessed
 
 
 def test_host_bitstreams_roundtrip():
