@@ -421,11 +421,11 @@ const char* kzg_profile_json(void) {
 void* kzg_stream(void) { if (ws_init() < 0) return nullptr; return (void*)W.stream; }
 int32_t kzg_transform_max_encoded_len(int type, int32_t n) { return xf_known(type) ? xf_max_len(type, n) : -KZG_ERR_INVALID_CODEC; }
 // Worst case of any supported chain: a block whose entropy stage does not pay is stored as a "transformed copy"
-// (COS:926-973) = its transform output (at most Sequence.getMaxEncodedLength: LZ n + n/64 + 2, BWT + 33, SRT + 1024) plus a
+// (COS:926-973) = its transform output (at most Sequence.getMaxEncodedLength: ROLZX n + n/32, LZ n + n/64 + 2, BWT + 33, SRT + 1024) plus a
 // record header (5 + 32 bits of length, mode, skip flags, 4 length bytes, checksum).
 int64_t kzg_compress_bound(int64_t n, int32_t blockSize) {
   const i64 nb = (n + blockSize - 1) / std::max(blockSize, 1) + 1;
-  return n + n / 64 + nb * (2 + 33 + 1024 + 16) + 64;
+  return n + n / 32 + nb * (2 + 33 + 1024 + 16) + 64;
 }
 
 // ---- per-block calls: ByteTransform.forward / inverse, EntropyEncoder.encode, EntropyDecoder.decode -----------------------

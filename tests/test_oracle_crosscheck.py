@@ -1810,3 +1810,14 @@ def test_rolzx_agrees_with_the_oracle_both_ways():
             p = rolzx_inverse(ref[:cut], len(d))
             assert o[0] == (-1 if p[0] is None else int(p[0])), (len(d), cut, o[0], p[0])
     assert applied >= 8
+
+
+def test_rolzx_on_incompressible_data_overruns_its_buffer_in_both():
+    """Random bytes cost ROLZX's literal coder about nine bits each (256 x 512 adaptive cells never settle on 20 000 samples), more than
+    the n + n/32 bytes getMaxEncodedLength grants (ROLZCodec.java:1417-1421): the reference's writeInt32 then throws
+    ArrayIndexOutOfBoundsException and EncodingTask reports "Error in block" (COS:1042-1045).  Oracle and restatement both say so."""
+    d = bytes(np.random.default_rng(1).integers(0, 256, 20000, dtype=np.uint8))
+    assert O.transform("ROLZX", d)[0] == -1
+    assert rolzx_forward(d)[0] is None
+    with pytest.raises(RuntimeError):
+        O.compress(d, ["ROLZX"], "NONE", 65536)
