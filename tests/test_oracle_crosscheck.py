@@ -1586,6 +1586,8 @@ class _RolzCoder:
             self.p[i] = pr - (((pr - 0xFFFF) >> 5) + 1)
             self.c1 += self.c1 + 1
         while ((self.low ^ self.high) >> 24) == 0:
+            if self.index + 4 > len(self.buf):
+                raise IndexError                                      # Java: ArrayIndexOutOfBoundsException in writeInt32
             self.buf[self.index:self.index + 4] = ((self.high >> 32) & 0xFFFFFFFF).to_bytes(4, "big")
             self.index += 4
             self.low = (self.low << 32) & M64
@@ -1597,6 +1599,8 @@ class _RolzCoder:
             self.encode_bit(val & (1 << k))
 
     def finish(self):
+        if self.index + 8 > len(self.buf):
+            raise IndexError
         self.buf[self.index:self.index + 8] = self.low.to_bytes(8, "big")
         self.index += 8
 
