@@ -1008,6 +1008,173 @@ struct Decoder {
 }  // namespace fpaq
 
 // =================================================================================================
+// RangeEncoder / RangeDecoder (entropy/RangeEncoder.java, RangeDecoder.java): order-0 range coder, 32 KiB chunks, each with its
+// own statistics; 28 bits leave the coder at a time.  Not on the CUDA path yet: here so that the checker is
+// ready and ctx["entropy"] = "RANGE" means something to RLT.
+// =================================================================================================
+namespace range {
+static constexpr u64 TOP_RANGE = 0x0FFFFFFFFFFFFFFFULL, BOTTOM_RANGE = 0x000000000000FFFFULL, RANGE_MASK = 0x0FFFFFFF00000000ULL;
+enum { DEFAULT_CHUNK_SIZE = 1 << 15, DEFAULT_LOG_RANGE = 12 };
+
+struct Encoder {
+  BitWriter& bs; int chunkSize, logRange;
+  u64 low = 0, rng = TOP_RANGE; int shift = 0;
+  int alphabet[256], freqs[257]; u64 cumFreqs[257];
+  explicit Encoder(BitWriter& b, int chunkSize_ = DEFAULT_CHUNK_SIZE, int logRange_ = DEFAULT_LOG_RANGE) : bs(b), chunkSize(chunkSize_), logRange(logRange_) {}
+  // encodeHeader, RangeEncoder.java:182-219
+  bool encodeHeader(int alphabetSize, int lr) {
+    const int encoded = encodeAlphabet(bs, alphabet, 256, alphabetSize);
+    if (encoded < 0) return false;
+    if (encoded == 0) return true;
+    bs.writeBits((u64)(lr - 8), 3);
+    const int chkSize = (alphabetSize >= 64) ? 8 : 6;
+    int llr = 3;
+    while ((1 << llr) <= lr) llr++;
+    for (int i = 1; i < alphabetSize; i += chkSize) {
+      int max = freqs[alphabet[i]] - 1, logMax = 0;
+      const int endj = (i + chkSize < alphabetSize) ? i + chkSize : alphabetSize;
+      for (int j = i + 1; j < endj; j++) if (freqs[alphabet[j]] - 1 > max) max = freqs[alphabet[j]] - 1;
+      while ((1 << logMax) <= max) logMax++;
+      bs.writeBits((u64)logMax, llr);
+      if (logMax == 0) continue;
+      for (int j = i; j < endj; j++) bs.writeBits((u64)(freqs[alphabet[j]] - 1), logMax);
+    }
+    return true;
+  }
+  // updateFrequencies + rebuildStatistics, :160-176, :298-301
+  int rebuildStatistics(const u8* block, int start, int end, int lr) {
+    histogramOrder0(block, start, end, freqs, false);
+    const int alphabetSize = normalizeFrequencies(freqs, alphabet, 256, end - start, 1 << lr);
+    if (alphabetSize > 0) { cumFreqs[0] = 0; for (int i = 0; i < 256; i++) cumFreqs[i + 1] = cumFreqs[i] + (u64)freqs[i]; }
+    encodeHeader(alphabetSize, lr);
+    return alphabetSize;
+  }
+  // encodeByte, :270-295 (Java longs: 64-bit wrap-around, `range > BOTTOM_RANGE` compares signed)
+  void encodeByte(u8 b) {
+    const u64 cumFreq = cumFreqs[b], freq = cumFreqs[b + 1] - cumFreq;
+    rng >>= shift;
+    low += cumFreq * rng;
+    rng *= freq;
+    while (true) {
+      if (((low ^ (low + rng)) & RANGE_MASK) != 0) {
+        if ((i64)rng > (i64)BOTTOM_RANGE) break;
+        rng = (0 - low) & BOTTOM_RANGE;
+      }
+      bs.writeBits(low >> 32, 28);
+      rng <<= 28;
+      low <<= 28;
+    }
+  }
+  // encode, :223-266
+  int encode(const u8* block, int blkptr, int count) {
+    if (count == 0) return 0;
+    const int end = blkptr + count;
+    int startChunk = blkptr;
+    while (startChunk < end) {
+      const int endChunk = (startChunk + chunkSize < end) ? startChunk + chunkSize : end;
+      rng = TOP_RANGE; low = 0;
+      int lr = logRange;
+      while ((lr > 8) && ((1 << lr) > endChunk - startChunk)) lr--;
+      if (rebuildStatistics(block, startChunk, endChunk, lr) <= 1) { startChunk = endChunk; continue; }
+      shift = lr;
+      for (int i = startChunk; i < endChunk; i++) encodeByte(block[i]);
+      bs.writeBits(low, 60);
+      startChunk = endChunk;
+    }
+    return count;
+  }
+};
+
+struct Decoder {
+  BitReader& bs; int chunkSize;
+  u64 code = 0, low = 0, rng = TOP_RANGE; int shift = 0;
+  int alphabet[256], freqs[256]; u64 cumFreqs[257];
+  std::vector<short> f2s;
+  explicit Decoder(BitReader& b, int chunkSize_ = DEFAULT_CHUNK_SIZE) : bs(b), chunkSize(chunkSize_) {}
+  // decodeHeader, RangeDecoder.java:131-207
+  int decodeHeader() {
+    const int alphabetSize = decodeAlphabet(bs, alphabet);
+    if (alphabetSize == 0) return 0;
+    if (alphabetSize != 256) for (int i = 0; i < 256; i++) freqs[i] = 0;
+    const int logRange = (int)(8 + bs.readBits(3));
+    if ((logRange < 8) || (logRange > 15)) throw BitStreamError("Invalid bitstream: range");
+    const int scale = 1 << logRange;
+    shift = logRange;
+    int sum = 0;
+    const int chkSize = (alphabetSize >= 64) ? 8 : 6;
+    int llr = 3;
+    while ((1 << llr) <= logRange) llr++;
+    for (int i = 1; i < alphabetSize; i += chkSize) {
+      const int logMax = (int)bs.readBits(llr);
+      if ((1 << logMax) > scale) throw BitStreamError("Invalid bitstream: incorrect frequency size");
+      const int endj = (i + chkSize < alphabetSize) ? i + chkSize : alphabetSize;
+      for (int j = i; j < endj; j++) {
+        const int freq = (logMax == 0) ? 1 : (int)(1 + bs.readBits(logMax));
+        if ((freq <= 0) || (freq >= scale)) throw BitStreamError("Invalid bitstream: incorrect frequency");
+        freqs[alphabet[j]] = freq;
+        sum += freq;
+      }
+    }
+    if (scale <= sum) throw BitStreamError("Invalid bitstream: incorrect frequency");
+    freqs[alphabet[0]] = scale - sum;
+    cumFreqs[0] = 0;
+    if ((int)f2s.size() < scale) f2s.assign(scale, 0);
+    for (int i = 0; i < 256; i++) {
+      cumFreqs[i + 1] = cumFreqs[i] + (u64)freqs[i];
+      const int base = (int)cumFreqs[i];
+      for (int j = freqs[i] - 1; j >= 0; j--) {
+        if (base + j >= (int)f2s.size()) throw JavaException("AIOOBE in RangeDecoder.decodeHeader");
+        f2s[base + j] = (short)i;
+      }
+    }
+    return alphabetSize;
+  }
+  // decodeByte, :252-278 (the division is Java's signed long division)
+  u8 decodeByte() {
+    rng >>= shift;
+    if (rng == 0) throw JavaException("ArithmeticException in RangeDecoder.decodeByte");
+    const int count = (int)((i64)(code - low) / (i64)rng);
+    if (count < 0 || count >= (int)f2s.size()) throw JavaException("AIOOBE in RangeDecoder.decodeByte");
+    const int symbol = f2s[count];
+    const u64 cumFreq = cumFreqs[symbol], freq = cumFreqs[symbol + 1] - cumFreq;
+    low += cumFreq * rng;
+    rng *= freq;
+    while (true) {
+      if (((low ^ (low + rng)) & RANGE_MASK) != 0) {
+        if ((i64)rng > (i64)BOTTOM_RANGE) break;
+        rng = (0 - low) & BOTTOM_RANGE;
+      }
+      code = (code << 28) | bs.readBits(28);
+      rng <<= 28;
+      low <<= 28;
+    }
+    return (u8)symbol;
+  }
+  // decode, :210-249
+  int decode(u8* block, int blkptr, int count) {
+    if (count == 0) return 0;
+    const int end = blkptr + count;
+    int startChunk = blkptr;
+    while (startChunk < end) {
+      const int endChunk = (startChunk + chunkSize < end) ? startChunk + chunkSize : end;
+      const int alphabetSize = decodeHeader();
+      if (alphabetSize == 0) return startChunk - blkptr;
+      if (alphabetSize == 1) {
+        for (int i = startChunk; i < endChunk; i++) block[i] = (u8)alphabet[0];
+        startChunk = endChunk;
+        continue;
+      }
+      rng = TOP_RANGE; low = 0;
+      code = bs.readBits(60);
+      for (int i = startChunk; i < endChunk; i++) block[i] = decodeByte();
+      startChunk = endChunk;
+    }
+    return count;
+  }
+};
+}  // namespace range
+
+// =================================================================================================
 // EntropyCodecFactory.newEncoder/newDecoder (EntropyCodecFactory.java:113-203) + the host's
 // encode-then-dispose sequence (CompressedOutputStream.java:907-916)
 // =================================================================================================
@@ -1018,6 +1185,7 @@ static inline int entropyEncode(int type, BitWriter& bs, const u8* block, int co
     case E_ANS0: { ans::Encoder e(bs, 0); return e.encode(block, 0, count); }
     case E_ANS1: { ans::Encoder e(bs, 1); return e.encode(block, 0, count); }
     case E_FPAQ: { fpaq::Encoder e(bs); int r = e.encode(block, 0, count); e.dispose(); return r; }
+    case E_RANGE: { range::Encoder e(bs); return e.encode(block, 0, count); }
     default: throw JavaException("Unknown entropy codec type");
   }
 }
@@ -1028,6 +1196,7 @@ static inline int entropyDecode(int type, BitReader& bs, u8* block, int count) {
     case E_ANS0: { ans::Decoder d(bs, 0); return d.decode(block, 0, count); }
     case E_ANS1: { ans::Decoder d(bs, 1); return d.decode(block, 0, count); }
     case E_FPAQ: { fpaq::Decoder d(bs); return d.decode(block, 0, count); }
+    case E_RANGE: { range::Decoder d(bs); return d.decode(block, 0, count); }
     default: throw JavaException("Unsupported entropy codec type");
   }
 }

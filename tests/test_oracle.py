@@ -57,7 +57,7 @@ def test_expgolomb_kat():   # ExpGolombEncoder.java:53,69-70: +1 -> 0100, -1 -> 
 CASES = corpus.small_cases()
 
 
-@pytest.mark.parametrize("ent", ["NONE", "HUFFMAN", "ANS0", "ANS1", "FPAQ"])
+@pytest.mark.parametrize("ent", ["NONE", "HUFFMAN", "ANS0", "ANS1", "FPAQ", "RANGE"])
 def test_entropy_roundtrip(ent):
     for name, d in list(CASES.items()) + [(f"lit{i}", x) for i, x in enumerate(corpus.ENTROPY_LITERALS)] + [("fib", corpus.fibonacci_chunk())]:
         pay, bits = O.entropy_encode(ent, d)

@@ -1825,3 +1825,76 @@ def test_rolzx_on_incompressible_data_overruns_its_buffer_in_both():
     assert rolzx_forward(d)[0] is None
     with pytest.raises(RuntimeError):
         O.compress(d, ["ROLZX"], "NONE", 65536)
+
+
+# ---- RANGE: K/entropy/RangeEncoder.java:160-301 (not on the CUDA path; the oracle carries it for RLT's ctx["entropy"] and for what comes next)
+def range_encode(data, chunk=1 << 15, log_range=12):
+    TOP, BOTTOM, MASK = 0x0FFFFFFFFFFFFFFF, 0xFFFF, 0x0FFFFFFF00000000
+    out = _Bits()
+    n = len(data)
+    start = 0
+    signed = lambda v: v - (1 << 64) if v >> 63 else v
+    while start < n:
+        end = min(start + chunk, n)
+        rng, low = TOP, 0
+        lr = log_range
+        while lr > 8 and (1 << lr) > end - start:
+            lr -= 1
+        f = [0] * 257
+        for b in data[start:end]:
+            f[b] += 1
+        alphabet = _normalize(f, end - start, 1 << lr)
+        _encode_alphabet(out, alphabet)
+        if len(alphabet) > 0:
+            out.write(lr - 8, 3)
+            chk = 8 if len(alphabet) >= 64 else 6
+            llr = 3
+            while (1 << llr) <= lr:
+                llr += 1
+            for i in range(1, len(alphabet), chk):
+                endj = min(i + chk, len(alphabet))
+                mx = max(f[alphabet[j]] - 1 for j in range(i, endj))
+                log_max = 0
+                while (1 << log_max) <= mx:
+                    log_max += 1
+                out.write(log_max, llr)
+                if log_max == 0:
+                    continue
+                for j in range(i, endj):
+                    out.write(f[alphabet[j]] - 1, log_max)
+        if len(alphabet) <= 1:
+            start = end
+            continue
+        cum = [0] * 257
+        for i in range(256):
+            cum[i + 1] = cum[i] + f[i]
+        for b in data[start:end]:
+            rng >>= lr
+            low = (low + cum[b] * rng) & M64
+            rng = (rng * (cum[b + 1] - cum[b])) & M64
+            while True:
+                if ((low ^ ((low + rng) & M64)) & MASK) != 0:
+                    if signed(rng) > BOTTOM:
+                        break
+                    rng = (-low) & BOTTOM
+                out.write(low >> 32, 28)
+                rng = (rng << 28) & M64
+                low = (low << 28) & M64
+        out.write(low, 60)
+        start = end
+    return out.bytes()
+
+
+def test_range_encoder_agrees_with_the_oracle():
+    import corpus
+    from kanzi_b200 import synth
+    r = np.random.default_rng(13)
+    cases = [synth.text(70000, 3).tobytes(), synth.exe_like(40000, 4).tobytes(), bytes(50000), bytes(r.integers(0, 256, 33000, dtype=np.uint8)),
+             bytes(r.integers(0, 2, 9000, dtype=np.uint8)), b"abc" * 11, b"x", bytes(r.integers(0, 70, 300, dtype=np.uint8)), corpus.fibonacci_chunk()[:40000],
+             bytes(r.integers(0, 256, 1 << 15, dtype=np.uint8)) + b"tail"]
+    for d in cases:
+        ref, ref_bits = O.entropy_encode("RANGE", d)
+        got, bits = range_encode(d)
+        assert bits == ref_bits and got == ref, (len(d), bits, ref_bits)
+        out, rr, used = O.entropy_decode("RANGE", ref, ref_bits, len(d))
+        assert rr == len(d) and out == d and used == ref_bits
