@@ -60,6 +60,20 @@ def text(n, seed=1, nwords=50000, zipf_s=1.1):
     return _emit_words(rng, n, chars, offs, lens, zipf_s, extra=punct)
 
 
+def pasted(n, seed=1):
+    """Text in which long passages (70-1900 bytes) come back further on and the bytes 0xFC / 0xFE / 0xFF turn up here and there: what LZP
+    (matches of 64+ bytes behind a 4-byte context, escape byte 0xFC) has something to do on."""
+    rng = np.random.default_rng(seed + 977)
+    a = text(n, seed).copy()
+    for _ in range(n // 3000):
+        src, ln, dst = int(rng.integers(0, max(n - 2000, 1))), int(rng.integers(70, 1900)), int(rng.integers(0, max(n - 2000, 1)))
+        seg = a[src:src + ln].copy()
+        a[dst:dst + len(seg)] = seg[:len(a[dst:dst + len(seg)])]
+    for _ in range(n // 5000):
+        a[int(rng.integers(0, n))] = int(rng.choice([0xFC, 0xFE, 0xFF]))
+    return a
+
+
 def ascii_markov(n, seed=1):
     """cfg1 input: printable ASCII with an English-like skew."""
     return text(n, seed, nwords=8000, zipf_s=1.0)

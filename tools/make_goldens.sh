@@ -45,6 +45,13 @@ text_bwt_srt_zrlt_fpaq|text|262144|15|BWT+SRT+ZRLT|FPAQ|131072
 noise_lz_ans0|noise|200000|16|LZ|ANS0|65536
 cfg2_first_blocks|silesia_like|16777216|2|LZ|ANS0|4194304
 cfg3_first_block|enwik_like|8388608|3|BWT+RANK+ZRLT|ANS1|8388608
+pasted_lzp_ans0|pasted|400000|17|LZP|ANS0|131072
+pasted_lzp_zrlt_huffman|pasted|300000|18|LZP+ZRLT|HUFFMAN|65536
+mixed_rlt_fpaq|mixed_entropy|300000|19|RLT|FPAQ|131072
+records_rlt_ans0|records|300000|20|RLT|ANS0|65536
+text_rolzx_none|text|300000|21|ROLZX|NONE|131072
+exe_rolzx_ans0|exe_like|300000|22|ROLZX|ANS0|262144
+text_none_range|text|200000|23|NONE|RANGE|65536
 CASES
 echo ']}' >> "$MAN"
 echo "wrote $MAN; commit tests/golden/ and run: python -m pytest tests/test_golden.py -q"
