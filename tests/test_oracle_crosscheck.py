@@ -1898,3 +1898,137 @@ def test_range_encoder_agrees_with_the_oracle():
         assert bits == ref_bits and got == ref, (len(d), bits, ref_bits)
         out, rr, used = O.entropy_decode("RANGE", ref, ref_bits, len(d))
         assert rr == len(d) and out == d and used == ref_bits
+
+
+# ---- LZ / LZX inverse: K/transform/LZCodec.java:605-756 (inverseV6), readLength :241-258 ---------------------------------------------
+def lz_inverse(src, dst_end):
+    """-> (ok, out); ok None where the Java code would throw.  dst_end = dst.array.length"""
+    count = len(src)
+    if count == 0:
+        return True, b""
+    if count < 13:
+        return False, b""
+    le = lambda i: int.from_bytes(src[i:i + 4], "little", signed=True)
+    tk_len, m_idx_len, m_len_len = le(0), le(4), le(8)
+    if tk_len < 0 or m_idx_len < 0 or m_len_len < 0:
+        return False, b""
+    if tk_len < 13 or tk_len > count or m_idx_len > count - tk_len or m_len_len > count - tk_len - m_idx_len:
+        return False, b""
+    tk = tk_len
+    m_idx = tk + m_idx_len
+    m_len_idx = m_idx + m_len_len
+    src_end, lit_end = tk - 13, tk
+    max_dist = (1 << 16) - 2 if (src[12] & 1) == 0 else (1 << 24) - 2
+    min_match = ((src[12] >> 1) & 7) + 2
+    si = 13
+    dst = bytearray(dst_end)
+    di = 0
+    repd0 = repd1 = count
+
+    def read_length(i):
+        res = src[i]
+        i += 1
+        if res < 254:
+            return res, i
+        if res == 254:
+            return res + (src[i] << 8) + src[i + 1], i + 2
+        return res + (src[i] << 16) + (src[i + 1] << 8) + src[i + 2], i + 3
+
+    try:
+        while True:
+            token = src[tk]
+            tk += 1
+            if token >= 32:
+                if token >= 0xE0:
+                    ln, si = read_length(si)
+                    lit = 7 + ln
+                else:
+                    lit = token >> 5
+                if lit > dst_end - di or lit > lit_end - si:
+                    return False, bytes(dst[:di])
+                if si + lit < src_end:                            # emitLiterals (:945-950): eight bytes at a time, up to 7 past the run on both sides
+                    padded = (lit + 7) & ~7
+                    if si + padded > len(src) or di + padded > dst_end:
+                        raise IndexError
+                elif si + lit > len(src):
+                    raise IndexError
+                dst[di:di + lit] = src[si:si + lit]
+                si += lit
+                di += lit
+                if si >= src_end:
+                    break
+            f = token & 0x18
+            if f == 0:
+                ml = token & 3
+                if ml == 3:
+                    ln, m_len_idx = read_length(m_len_idx)
+                    ml += min_match + ln
+                else:
+                    ml += min_match
+                dist = repd0 if (token & 4) == 0 else repd1
+            else:
+                ml = token & 7
+                if ml == 7:
+                    ln, m_len_idx = read_length(m_len_idx)
+                    ml += min_match + ln
+                else:
+                    ml += min_match
+                dist = src[m_idx]
+                m_idx += 1
+                if f == 0x18:
+                    dist = (dist << 16) | (src[m_idx] << 8) | src[m_idx + 1]
+                    m_idx += 2
+                elif f == 0x10:
+                    dist = (dist << 8) | src[m_idx]
+                    m_idx += 1
+            repd1, repd0 = repd0, dist
+            m_end = di + ml
+            ref = di - dist
+            if ref < 0 or dist > max_dist or m_end > dst_end:
+                return False, bytes(dst[:di])
+            if dist >= 16:
+                while True:                                       # sixteen bytes at a time, past mEnd if need be (the array must hold them)
+                    if di + 16 > dst_end:
+                        raise IndexError
+                    dst[di:di + 16] = dst[ref:ref + 16]
+                    ref += 16
+                    di += 16
+                    if di >= m_end:
+                        break
+            else:
+                for i in range(ml):
+                    dst[di + i] = dst[ref + i]
+            di = m_end
+    except IndexError:
+        return None, b""
+    return si == src_end + 13, bytes(dst[:di])
+
+
+@pytest.mark.parametrize("name", ["LZ", "LZX"])
+def test_lz_inverse_agrees_with_the_oracle(name):
+    import corpus
+    from kanzi_b200 import synth
+    r = np.random.default_rng(23)
+    cases = [synth.text(30000, 5).tobytes(), synth.exe_like(40000, 6).tobytes(), synth.records(25000, 7).tobytes(), (b"0123456789abcdef" * 7 + b"Z") * 300,
+             corpus.sparse_with_repeats(60000, 14), bytes(70000), synth.text(70000, 9).tobytes() * 2, b"ACGT" * 4000 + b"TTGACA" * 900]
+    done = 0
+    for d in cases:
+        ok, enc, _, _ = O.transform(name, d, dst_cap=len(d) + len(d) // 64 + 1100, ctx=[7, max(len(d), 1024), len(d), 1, 0, 0])
+        if ok != 1:
+            continue
+        done += 1
+        for cap in (len(d) + 16, len(d) + 1000, len(d), len(d) - 1):      # (the 16-byte copies want slack after the last match)
+            o = O.transform(name, enc, inverse=True, dst_cap=cap, dst_len=cap, ctx=[7, max(len(d), 1024), len(d), 1, 0, 0])
+            p = lz_inverse(enc, cap)
+            assert o[0] == (-1 if p[0] is None else int(p[0])), (name, len(d), cap, o[0], p[0])
+            if o[0] == 1:
+                assert o[1] == p[1] == d
+        for k in range(12):                                        # damaged streams: refused or accepted alike, same bytes when accepted
+            bad = bytearray(enc)
+            bad[int(r.integers(0, len(bad)))] ^= 1 << int(r.integers(0, 8))
+            o = O.transform(name, bytes(bad), inverse=True, dst_cap=len(d) + 16, dst_len=len(d) + 16, ctx=[7, max(len(d), 1024), len(d), 1, 0, 0])
+            p = lz_inverse(bytes(bad), len(d) + 16)
+            assert o[0] == (-1 if p[0] is None else int(p[0])), (name, len(d), "flip", k, o[0], p[0])
+            if o[0] == 1:
+                assert o[1] == p[1]
+    assert done >= 6
