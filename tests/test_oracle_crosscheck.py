@@ -2032,3 +2032,176 @@ def test_lz_inverse_agrees_with_the_oracle(name):
             if o[0] == 1:
                 assert o[1] == p[1]
     assert done >= 6
+
+
+# ---- rANS decoder: K/entropy/ANSRangeDecoder.java:148-196 (decode), :257-331 (decodeChunkV2), :333-408 (decodeHeader); bsVersion >= 4 ----
+class _BitsIn:
+    def __init__(self, data, nbits):
+        self.v = int.from_bytes(data, "big")
+        self.total = 8 * len(data)
+        self.nbits, self.pos = nbits, 0
+
+    def read(self, n):
+        if n == 0:
+            return 0
+        if self.pos + n > ((self.nbits + 7) & ~7):
+            raise EOFError
+        r = (self.v >> (self.total - self.pos - n)) & ((1 << n) - 1)
+        self.pos += n
+        return r
+
+    def varint(self):          # EntropyUtils.readVarInt (K/entropy/EntropyUtils.java:284-300)
+        value = self.read(8)
+        res = value & 0x7F
+        shift = 7
+        while value >= 128 and shift <= 28:
+            value = self.read(8)
+            res |= (value & 0x7F) << shift
+            shift += 7
+        return res
+
+
+def _decode_alphabet(b):       # EntropyUtils.decodeAlphabet (:86-122)
+    if b.read(1) == 0:
+        return [] if b.read(1) == 1 else list(range(256))
+    last = b.read(5)
+    out = []
+    for i in range(last + 1):
+        m = b.read(8)
+        out += [(i << 3) + j for j in range(8) if m & (1 << j)]
+    return out
+
+
+def ans_decode(payload, nbits, n, order):
+    """-> (return value, bytes, bits consumed); a BitStreamException / index error of the Java code shows as return value None"""
+    b = _BitsIn(payload, nbits)
+    out = bytearray(n)
+    if n <= 32:
+        for i in range(n):
+            out[i] = b.read(8)
+        return n, bytes(out), b.pos
+    dim = 255 * order + 1
+    chunk = 16384 << (8 * order)
+    freqs = [[0] * 256 for _ in range(dim)]
+    f2s = [[] for _ in range(dim)]
+    sym = [[(0, 0)] * 256 for _ in range(dim)]                   # (cumFreq, freq)
+    start = 0
+    try:
+        while start < n:
+            end = min(start + chunk, n)
+            lr = 8 + b.read(3)
+            scale = 1 << lr
+            total_alpha = 0
+            alphabet = []
+            for k in range(dim):
+                alphabet = _decode_alphabet(b)
+                if not alphabet:
+                    continue
+                llr = 3
+                while (1 << llr) <= lr:
+                    llr += 1
+                f = freqs[k]
+                if len(alphabet) != 256:
+                    for i in range(256):
+                        f[i] = 0
+                if len(f2s[k]) < scale:
+                    f2s[k] = [0] * scale
+                chk = 8 if len(alphabet) >= 64 else 6
+                s = 0
+                for i in range(1, len(alphabet), chk):
+                    log_max = b.read(llr)
+                    if (1 << log_max) > scale:
+                        return None, b"", b.pos
+                    for j in range(i, min(i + chk, len(alphabet))):
+                        fr = 1 if log_max == 0 else 1 + b.read(log_max)
+                        if fr <= 0 or fr >= scale:
+                            return None, b"", b.pos
+                        f[alphabet[j]] = fr
+                        s += fr
+                if scale <= s:
+                    return None, b"", b.pos
+                f[alphabet[0]] = scale - s
+                s = 0
+                for i in range(256):
+                    if f[i] == 0:
+                        continue
+                    f2s[k][s:s + f[i]] = [i] * f[i]
+                    sym[k][i] = (s, scale - 1 if f[i] >= scale else f[i])      # Symbol.reset (:576-579) "mirrors the encoder"
+                    s += f[i]
+                total_alpha += len(alphabet)
+            if total_alpha == 0:
+                return start, bytes(out), b.pos
+            if order == 0 and total_alpha == 1:
+                out[start:end] = bytes([alphabet[0]]) * (end - start)
+                start = end
+                continue
+            sz = b.varint()
+            if sz >= 1 << 27:
+                break
+            st = [b.read(32) for _ in range(4)]                  # st0 .. st3
+            buf = bytearray(max(2 * (end - start), 256))
+            for i in range(sz):
+                v = b.read(8)
+                if i >= len(buf):
+                    raise IndexError
+                buf[i] = v
+            pos = 0
+            mask = scale - 1
+
+            def step(k, ctx):
+                nonlocal pos
+                cur = f2s[ctx][st[k] & mask]
+                cum, fr = sym[ctx][cur]
+                x = (fr * (st[k] >> lr) + (st[k] & mask) - cum) & 0xFFFFFFFF
+                if x >= 1 << 31:
+                    x -= 1 << 32                                  # Java int: the comparison below is signed
+                if x < (1 << 15):
+                    x = ((x << 8) | buf[pos]) & 0xFFFFFFFF
+                    x = ((x << 8) | buf[pos + 1]) & 0xFFFFFFFF
+                    pos += 2
+                st[k] = x & 0xFFFFFFFF
+                return cur
+
+            end4 = start + ((end - start) & -4)
+            if order == 0:
+                for i in range(start, end4, 4):
+                    for j, k in enumerate((3, 2, 1, 0)):
+                        out[i + j] = step(k, 0)
+            else:
+                quarter = (end4 - start) >> 2
+                prv = [0, 0, 0, 0]
+                for i in range(quarter):
+                    for k in (3, 2, 1, 0):
+                        cur = step(k, prv[k])
+                        out[start + k * quarter + i] = cur
+                        prv[k] = cur
+            for i in range(end4, end):
+                out[i] = buf[pos]
+                pos += 1
+            if pos != sz:
+                break
+            start = end
+    except (EOFError, IndexError):
+        return None, b"", b.pos
+    return n, bytes(out), b.pos
+
+
+@pytest.mark.parametrize("kind,order", [("ANS0", 0), ("ANS1", 1)])
+def test_ans_decoder_agrees_with_the_oracle(kind, order):
+    from kanzi_b200 import synth
+    r = np.random.default_rng(29)
+    cases = [synth.text(40000, 3).tobytes(), synth.exe_like(30000, 4).tobytes(), bytes(20000), bytes(r.integers(0, 256, 17000, dtype=np.uint8)),
+             bytes(r.integers(0, 2, 9000, dtype=np.uint8)), b"abc" * 11, b"x" * 33, b"hello", bytes(r.integers(0, 70, 300, dtype=np.uint8)), b"ab" * 8200 + b"xyz"]
+    for d in cases:
+        enc, bits = O.entropy_encode(kind, d)
+        o = O.entropy_decode(kind, enc, bits, len(d))
+        p = ans_decode(enc, bits, len(d), order)
+        assert o[1] == len(d) and o[0] == d and p[0] == len(d) and p[1] == d and p[2] == o[2] == bits, (kind, len(d))
+        for k in range(10):                                        # damaged payloads: same verdict, same bytes, same position
+            bad = bytearray(enc)
+            bad[int(r.integers(0, len(bad)))] ^= 1 << int(r.integers(0, 8))
+            o = O.entropy_decode(kind, bytes(bad), bits, len(d))
+            p = ans_decode(bytes(bad), bits, len(d), order)
+            assert o[1] == (-1 if p[0] is None else p[0]), (kind, len(d), "flip", k, o[1], p[0])
+            if p[0] is not None:
+                assert o[0][:max(p[0], 0)] == p[1][:max(p[0], 0)] or p[0] == len(d)
