@@ -2205,3 +2205,78 @@ def test_ans_decoder_agrees_with_the_oracle(kind, order):
             assert o[1] == (-1 if p[0] is None else p[0]), (kind, len(d), "flip", k, o[1], p[0])
             if p[0] is not None:
                 assert o[0][:max(p[0], 0)] == p[1][:max(p[0], 0)] or p[0] == len(d)
+
+
+# ---- FPAQ decoder: K/entropy/FPAQDecoder.java:88-176 (decode), :201-222 (decodeBitV2), :225-238 (read); bsVersion >= 4 -------------
+def fpaq_decode(payload, nbits, n, chunk=4 << 20):
+    """-> (return value, bytes, bits consumed); None as return value where the bitstream runs out (Java: BitStreamException)"""
+    TOP = 0x00FFFFFFFFFFFFFF
+    b = _BitsIn(payload, nbits)
+    out = bytearray(n)
+    if n == 0:
+        return 0, b"", 0
+    low, high = 0, TOP
+    probs = [[65536 >> 1] * 256 for _ in range(4)]
+    p = probs[0]
+    start = 0
+    try:
+        while start < n:
+            sz = b.varint()
+            if sz >= 2 * n:
+                return 0, bytes(out), b.pos
+            current = b.read(56)
+            buf = bytes(b.read(8) for _ in range(sz)) + bytes(max(sz + (sz >> 2), 1024) - sz)
+            idx = 0
+            end = start + min(chunk, n - start)
+            p = probs[0]
+            for i in range(start, end):
+                ctx = 1
+                for _ in range(8):
+                    split = ((((high - low) >> 8) * p[ctx]) >> 8) + low
+                    if split >= current:
+                        high = split
+                        p[ctx] -= (p[ctx] - 65536 + 64) >> 6
+                        ctx = (ctx << 1) + 1
+                    else:
+                        low = split + 1
+                        p[ctx] -= p[ctx] >> 6
+                        ctx <<= 1
+                    while ((low ^ high) & 0x00FFFFFFFF000000) == 0:
+                        low = (low << 32) & TOP
+                        high = ((high << 32) | 0xFFFFFFFF) & TOP
+                        if idx + 4 > sz:
+                            current = (current << 32) & TOP
+                            idx = sz + 1
+                        else:
+                            current = ((current << 32) | int.from_bytes(buf[idx:idx + 4], "big")) & TOP
+                            idx += 4
+                out[i] = ctx & 0xFF
+                if idx > sz:
+                    return 0, bytes(out), b.pos
+                p = probs[(ctx & 0xFF) >> 6]
+            start = end
+    except EOFError:
+        return None, b"", b.pos
+    return n, bytes(out), b.pos
+
+
+def test_fpaq_decoder_agrees_with_the_oracle():
+    from kanzi_b200 import synth
+    r = np.random.default_rng(31)
+    cases = [synth.text(30000, 3).tobytes(), synth.exe_like(20000, 4).tobytes(), bytes(9000), bytes(r.integers(0, 256, 7000, dtype=np.uint8)), b"a", b"hello world" * 3]
+    for d in cases:
+        enc, bits = O.entropy_encode("FPAQ", d)
+        o = O.entropy_decode("FPAQ", enc, bits, len(d))
+        p = fpaq_decode(enc, bits, len(d))
+        assert o[1] == len(d) and o[0] == d and p[0] == len(d) and p[1] == d and p[2] == o[2] == bits, len(d)
+        for k in range(8):
+            bad = bytearray(enc)
+            bad[int(r.integers(0, len(bad)))] ^= 1 << int(r.integers(0, 8))
+            o = O.entropy_decode("FPAQ", bytes(bad), bits, len(d))
+            p = fpaq_decode(bytes(bad), bits, len(d))
+            assert o[1] == (-1 if p[0] is None else p[0]), (len(d), "flip", k, o[1], p[0])
+            if p[0] == len(d):
+                assert o[0] == p[1]
+    # two chunks: probabilities and the interval carry over, `current` is read afresh (a small chunk size stands in for 4 MiB)
+    d = synth.text(5000, 9).tobytes()
+    assert fpaq_decode(*fpaq_encode(d, chunk=2048), len(d), chunk=2048)[1] == d
