@@ -2280,3 +2280,77 @@ def test_fpaq_decoder_agrees_with_the_oracle():
     # two chunks: probabilities and the interval carry over, `current` is read afresh (a small chunk size stands in for 4 MiB)
     d = synth.text(5000, 9).tobytes()
     assert fpaq_decode(*fpaq_encode(d, chunk=2048), len(d), chunk=2048)[1] == d
+
+
+# ---- Huffman decoder, by definition: stream layout of K/entropy/HuffmanDecoder.java:262-294 (decodeV6), :110-148 (readLengths),
+#      :297-360 (decodeChunk: four fragment bit strings, then the bytes that do not fill a fragment); canonical codes as the encoder's.
+#      The reference decodes through a 12-bit table and a 56-bit window; on a well-formed stream a bit-by-bit prefix decoder must give
+#      the same bytes and end at the same bit, which is what this checks (damaged streams are the GPU tests' business).
+def huffman_decode(payload, nbits, n, chunk=16384):
+    b = _BitsIn(payload, nbits)
+    out = bytearray(n)
+    start = 0
+    while start < n:
+        size = min(chunk, n - start)
+        if size < 32:
+            for i in range(size):
+                out[start + i] = b.read(8)
+            start += size
+            continue
+        alphabet = _decode_alphabet(b)
+        assert alphabet
+        sizes = {}
+        cur = 2
+        for s in alphabet:
+            if b.read(1) == 0:                                   # ExpGolombDecoder.decodeByte, signed (:41-56)
+                lg = 1
+                while b.read(1) == 0:
+                    lg += 1
+                res = b.read(lg + 1)
+                sgn = res & 1
+                res = (res >> 1) + (1 << lg) - 1
+                cur += -res if sgn else res
+            assert 0 < cur <= 12
+            sizes[s] = cur
+        if len(alphabet) == 1:
+            out[start:start + size] = bytes([alphabet[0]]) * size
+            start += size
+            continue
+        order = sorted(alphabet, key=lambda s: (sizes[s], s))
+        table = {}
+        code, cs = 0, sizes[order[0]]
+        for s in order:
+            code <<= sizes[s] - cs
+            cs = sizes[s]
+            table[(cs, code)] = s
+            code += 1
+        frag_bits = [b.varint() for _ in range(4)]
+        frag = size // 4
+        for k in range(4):
+            fb = _BitsIn(bytes((b.read(8) if 8 * i + 8 <= frag_bits[k] else b.read(frag_bits[k] - 8 * i) << (8 - (frag_bits[k] - 8 * i)))
+                               for i in range((frag_bits[k] + 7) // 8)), frag_bits[k])
+            for i in range(frag):
+                ln, code = 0, 0
+                while (ln, code) not in table:
+                    code = (code << 1) | fb.read(1)
+                    ln += 1
+                    assert ln <= 12
+                out[start + k * frag + i] = table[(ln, code)]
+            assert fb.pos == frag_bits[k]
+        for i in range(4 * frag, size):
+            out[start + i] = b.read(8)
+        start += size
+    return bytes(out), b.pos
+
+
+def test_huffman_decoder_by_definition_agrees_with_the_oracle():
+    from kanzi_b200 import synth
+    r = np.random.default_rng(37)
+    cases = [synth.text(40000, 3).tobytes(), synth.exe_like(33001, 4).tobytes(), bytes(20000), bytes(r.integers(0, 256, 17003, dtype=np.uint8)),
+             bytes(r.integers(0, 2, 9000, dtype=np.uint8)), b"abc" * 11, b"x" * 31, b"hello", bytes(r.integers(0, 70, 300, dtype=np.uint8)),
+             synth.skewed(50000, 5, 3.0).tobytes(), synth.text(16384 + 31, 8).tobytes(), synth.text(16384 + 32, 8).tobytes()]
+    for d in cases:
+        enc, bits = O.entropy_encode("HUFFMAN", d)
+        o = O.entropy_decode("HUFFMAN", enc, bits, len(d))
+        got, used = huffman_decode(enc, bits, len(d))
+        assert o[1] == len(d) and o[0] == d and got == d and used == o[2] == bits, len(d)
