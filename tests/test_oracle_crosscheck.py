@@ -2354,3 +2354,82 @@ def test_huffman_decoder_by_definition_agrees_with_the_oracle():
         o = O.entropy_decode("HUFFMAN", enc, bits, len(d))
         got, used = huffman_decode(enc, bits, len(d))
         assert o[1] == len(d) and o[0] == d and got == d and used == o[2] == bits, len(d)
+
+
+# ---- SRT inverse: K/transform/SRT.java:178-257, decodeHeader :335-353 ----------------------------------------------------------
+def srt_inverse(src, dst_len):
+    """-> (ok, out); ok None where the Java code would throw (an index past the input array)"""
+    if len(src) == 0:
+        return True, b""
+    try:
+        k = 0
+        freqs = []
+        for _ in range(256):
+            val = src[k]
+            k += 1
+            res, shift = val & 0x7F, 7
+            while val >= 128:
+                val = src[k]
+                k += 1
+                res |= (val & 0x7F) << shift
+                if shift > 21:
+                    break
+                shift += 7
+            res &= 0xFFFFFFFF
+            freqs.append(res - (1 << 32) if res >> 31 else res)
+        count = len(src) - k
+        if count > dst_len:
+            return False, b""
+        symbols = _srt_order(freqs)
+        n_sym = len(symbols)
+        buckets, ends, r2s = [0] * 256, [0] * 256, [0] * 256
+        pos = 0
+        for c in symbols:
+            if k + pos < 0 or k + pos >= len(src):
+                return False, b""
+            r2s[src[k + pos]] = c
+            buckets[c] = pos + 1
+            pos += freqs[c]
+            ends[c] = pos
+        c = r2s[0]
+        out = bytearray(max(count, 0))
+        for i in range(count):
+            out[i] = c
+            if buckets[c] < ends[c]:
+                r = src[k + buckets[c]]
+                buckets[c] += 1
+                if r == 0:
+                    continue
+                r2s[0:r] = r2s[1:r + 1]
+                r2s[r] = c
+                c = r2s[0]
+            else:
+                if n_sym == 1:
+                    continue
+                n_sym -= 1
+                r2s[0:n_sym] = r2s[1:n_sym + 1]
+                c = r2s[0]
+        return True, bytes(out)
+    except IndexError:
+        return None, b""
+
+
+def test_srt_inverse_agrees_with_the_oracle():
+    r = np.random.default_rng(43)
+    for d in _cases():
+        if len(d) == 0:
+            continue
+        ok, enc, _, _ = O.transform("SRT", d)
+        assert ok == 1
+        o = O.transform("SRT", enc, inverse=True, dst_cap=len(d), dst_len=len(d))
+        p = srt_inverse(enc, len(d))
+        assert o[0] == 1 and p[0] is True and o[1] == p[1] == d, len(d)
+        assert O.transform("SRT", enc, inverse=True, dst_cap=len(d) - 1, dst_len=len(d) - 1)[0] == int(srt_inverse(enc, len(d) - 1)[0]) == 0
+        for k in range(6):                                        # damaged ranks / header bytes: same verdict, same bytes
+            bad = bytearray(enc)
+            bad[int(r.integers(0, len(bad)))] = int(r.integers(0, 256))
+            o = O.transform("SRT", bytes(bad), inverse=True, dst_cap=len(d) + 300, dst_len=len(d) + 300)
+            p = srt_inverse(bytes(bad), len(d) + 300)
+            assert o[0] == (-1 if p[0] is None else int(p[0])), (len(d), k, o[0], p[0])
+            if o[0] == 1:
+                assert o[1] == p[1]
