@@ -2072,16 +2072,17 @@ def _decode_alphabet(b):       # EntropyUtils.decodeAlphabet (:86-122)
     return out
 
 
-def ans_decode(payload, nbits, n, order):
-    """-> (return value, bytes, bits consumed); a BitStreamException / index error of the Java code shows as return value None"""
-    b = _BitsIn(payload, nbits)
+def ans_decode(payload, nbits, n, order, chunk=None, b=None):
+    """-> (return value, bytes, bits consumed); a BitStreamException / index error of the Java code shows as return value None.
+    `b`: an open bit reader to continue from (the ROLZ codec decodes several arrays from one stream, with its own chunk size)."""
+    b = _BitsIn(payload, nbits) if b is None else b
     out = bytearray(n)
     if n <= 32:
         for i in range(n):
             out[i] = b.read(8)
         return n, bytes(out), b.pos
     dim = 255 * order + 1
-    chunk = 16384 << (8 * order)
+    chunk = (16384 if chunk is None else chunk) << (8 * order)
     freqs = [[0] * 256 for _ in range(dim)]
     f2s = [[] for _ in range(dim)]
     sym = [[(0, 0)] * 256 for _ in range(dim)]                   # (cumFreq, freq)
@@ -2433,3 +2434,155 @@ def test_srt_inverse_agrees_with_the_oracle():
             assert o[0] == (-1 if p[0] is None else int(p[0])), (len(d), k, o[0], p[0])
             if o[0] == 1:
                 assert o[1] == p[1]
+
+
+# ---- ROLZ inverse (ROLZCodec1): K/transform/ROLZCodec.java:696-960, readLength :962-980, emitCopy :162-180 --------------------------
+def rolz_inverse(src, dst_len):
+    """-> (ok, out); ok None where the Java code would throw.  bsVersion >= 4; dst_len = dst slice length = array length"""
+    count = len(src)
+    if count == 0:
+        return True, b""
+    try:
+        sz = int.from_bytes(src[0:4], "big", signed=True) - 4
+        if sz <= 0 or sz > dst_len:
+            return False, b""
+        size_chunk = min(sz, 16 << 20)
+        lit_cap, len_cap, idx_cap, tk_cap = size_chunk, size_chunk // 5 + 4, size_chunk // 4, size_chunk // 4
+        counters = [0] * 65536
+        flags = src[4]
+        lit_order = flags & 1
+        mm, dt = 3, 2
+        log_checks = flags >> 4
+        if log_checks < 2 or log_checks > 8:
+            return False, b""
+        mask = (1 << log_checks) - 1
+        sel = flags & 0x0E
+        if sel == 2:
+            mm, dt = 4, 8
+        elif sel == 4:
+            mm, dt = 7, 8
+        elif sel == 8:
+            dt = 3
+        dst = bytearray()
+        si = 5
+        start = 0
+        while start < sz:
+            matches = [0] * (65536 << log_checks)
+            end_chunk = min(start + size_chunk, sz)
+            size_chunk = end_chunk - start
+            base0 = len(dst)                                      # output.index
+            b = _BitsIn(src[si:], 8 * (count - si))
+            lit_len, tk_len, m_len_len, m_idx_len = (b.read(32) for _ in range(4))
+            if any(v >= 1 << 31 for v in (lit_len, tk_len, m_len_len, m_idx_len)):
+                return False, bytes(dst)
+            if lit_len > lit_cap or tk_len > tk_cap or m_len_len > len_cap - 4 or m_idx_len > idx_cap:
+                return False, bytes(dst)
+            if lit_len < min(size_chunk, 8) or lit_len > size_chunk or (tk_len == 0 and m_idx_len != 0) or (tk_len > 0 and m_idx_len + 1 != tk_len):
+                return False, bytes(dst)
+            r = ans_decode(None, 0, lit_len, lit_order, b=b)
+            if r[0] is None:
+                return None, b""
+            lit = r[1]
+            parts = []
+            for n in (tk_len, m_len_len, m_idx_len):
+                r = ans_decode(None, 0, n, 0, chunk=32768, b=b)
+                if r[0] is None:
+                    return None, b""
+                parts.append(r[1])
+            tk, lens, midx = parts
+            lens = lens + bytes(4)
+            si += (b.pos + 7) >> 3
+            if tk_len == 0:
+                if lit_len != size_chunk:
+                    return False, bytes(dst)
+                dst += lit[:size_chunk]
+                start = end_chunk
+                continue
+            li = ti = ni = mi = 0
+
+            def read_length():
+                nonlocal ni
+                nxt = lens[ni]; ni += 1
+                length = nxt & 0x7F
+                for _ in range(3):
+                    if not nxt & 0x80:
+                        break
+                    nxt = lens[ni]; ni += 1
+                    length = (length << 7) | (nxt & 0x7F)
+                return length
+
+            for _ in range(min(sz - len(dst), 8)):
+                dst.append(lit[li]); li += 1
+            while len(dst) < end_chunk:
+                token = tk[ti]; ti += 1
+                match_len = token & 7
+                if match_len == 7:
+                    if ni >= m_len_len:
+                        return False, bytes(dst)
+                    match_len = read_length() + 7
+                if token < 0xF8:
+                    ll = token >> 3
+                else:
+                    if ni >= m_len_len:
+                        return False, bytes(dst)
+                    ll = read_length() + 31
+                if ll > 0:
+                    n0 = len(dst) - base0
+                    if li + ll > len(lit) or len(dst) + ll > dst_len:
+                        raise IndexError
+                    dst += lit[li:li + ll]
+                    j, src_inc = 0, 0
+                    while j < ll:
+                        key = _rolz_key(bytes(dst[base0 + n0 + j - dt:base0 + n0 + j - dt + 8]).ljust(8, b"\0"), 0, mm if mm == 3 else 7)
+                        counters[key] = (counters[key] + 1) & mask
+                        matches[(key << log_checks) + counters[key]] = n0 + j
+                        j += src_inc >> 6
+                        src_inc += 1
+                        j += 1
+                    li += ll
+                    if len(dst) >= end_chunk:
+                        if len(dst) == end_chunk:
+                            break
+                        return False, bytes(dst)
+                if len(dst) + match_len + mm > sz:
+                    return False, bytes(dst)
+                p0 = len(dst)
+                key = _rolz_key(bytes(dst[p0 - dt:p0 - dt + 8]).ljust(8, b"\0"), 0, mm if mm == 3 else 7)
+                base = key << log_checks
+                m_idx = midx[mi]; mi += 1
+                ref = base0 + matches[base + ((counters[key] - m_idx) & mask)]
+                for k in range(match_len + mm):
+                    dst.append(dst[ref + k])
+                counters[key] = (counters[key] + 1) & mask
+                matches[base + counters[key]] = p0 - base0
+            if ti != tk_len or mi != m_idx_len or li != lit_len or ni != m_len_len:
+                return False, bytes(dst)
+            start = end_chunk
+        if len(dst) + 4 > dst_len or count - si != 4:
+            return False, bytes(dst)
+        dst += src[si:si + 4]
+        return True, bytes(dst)
+    except (IndexError, EOFError):
+        return None, b""
+
+
+def test_rolz_inverse_agrees_with_the_oracle():
+    import corpus
+    from kanzi_b200 import synth
+    r = np.random.default_rng(47)
+    dna = bytes(np.frombuffer(b"ACGT", dtype=np.uint8)[r.integers(0, 4, 6000)])
+    cases = [synth.text(30000, 5).tobytes(), synth.exe_like(40000, 6).tobytes(), synth.records(25000, 7).tobytes(), (b"0123456789abcdef" * 7 + b"Z") * 300,
+             corpus.sparse_with_repeats(60000, 14), synth.text(70000, 9).tobytes() * 2, dna + dna[1000:3000] + dna[:2500], bytes(r.integers(0, 256, 5000, dtype=np.uint8)), b"xyz" * 40]
+    done = 0
+    for d in cases:
+        ok, enc, _, _ = O.transform("ROLZ", d, dst_cap=max(len(d) + 64, 1024) + 1024, ctx=[7, max(len(d), 1024), len(d), 1, 0, 0])
+        if ok != 1:
+            continue
+        done += 1
+        for cap in (len(d), len(d) + 100, len(d) - 1):
+            o = O.transform("ROLZ", enc, inverse=True, dst_cap=cap, dst_len=cap, ctx=[7, max(len(d), 1024), len(d), 1, 0, 0])
+            p = rolz_inverse(enc, cap)
+            assert o[0] == (-1 if p[0] is None else int(p[0])), (len(d), cap, o[0], p[0])
+            if o[0] == 1:
+                assert o[1] == p[1] == d
+    assert done >= 7
