@@ -5,9 +5,11 @@ Java semantics reproduced here: `int` wraps at 32 bits, bytes are unsigned after
   ZRLT  K/transform/ZRLT.java:54-136 (forward), 146-233 (inverse)
   SBRT  K/transform/SBRT.java:87-151 (forward), 154-214 (inverse); modes MTF = 1, RANK = 2, TIMESTAMP = 3
   SRT   K/transform/SRT.java:73-168 (forward), 178-257 (inverse), preprocess :266-302, header :312-353
-Further down, each with its own citation: the FPAQ, ANS0/ANS1 and Huffman encoders, the LZ/LZX and ROLZ forward transforms, the BWT held
-against a naive suffix sort, and the block framing of CompressedOutputStream.  The decoders and inverses are covered through the
-oracle's own round trips (tests/test_oracle.py): an inverse that returns the input of a doubly-checked encoder is checked too."""
+Further down, each with its own citation: the FPAQ, ANS0/ANS1, Huffman and RANGE encoders, the LZ/LZX and ROLZ forward transforms, the BWT
+held against a naive suffix sort, the block framing of CompressedOutputStream, the sibling codecs LZP, RLT and ROLZX both ways, and the
+decode side: LZ/LZX, ROLZ and SRT inverses, the rANS and FPAQ decoders, Huffman by a bit-by-bit prefix decoder.  The BWT inverses are
+covered through the oracle's round trips (tests/test_oracle.py): an inverse that returns the input of a doubly-checked forward is
+checked too."""
 import numpy as np
 import pytest
 import oracle_lib as O
