@@ -7,7 +7,8 @@ Java semantics reproduced here: `int` wraps at 32 bits, bytes are unsigned after
   SRT   K/transform/SRT.java:73-168 (forward), 178-257 (inverse), preprocess :266-302, header :312-353
 Further down, each with its own citation: the FPAQ, ANS0/ANS1, Huffman and RANGE encoders, the LZ/LZX and ROLZ forward transforms, the BWT
 held against a naive suffix sort, the block framing of CompressedOutputStream, the sibling codecs LZP, RLT and ROLZX both ways, and the
-decode side: LZ/LZX, ROLZ and SRT inverses, the rANS and FPAQ decoders, Huffman by a bit-by-bit prefix decoder.  The BWT inverses are
+decode side: LZ/LZX, ROLZ and SRT inverses, the rANS and FPAQ decoders, Huffman by a bit-by-bit prefix decoder, whole streams parsed the
+way CompressedInputStream parses them.  The BWT inverses are
 covered through the oracle's round trips (tests/test_oracle.py): an inverse that returns the input of a doubly-checked forward is
 checked too."""
 import numpy as np
@@ -2588,3 +2589,106 @@ def test_rolz_inverse_agrees_with_the_oracle():
             if o[0] == 1:
                 assert o[1] == p[1] == d
     assert done >= 7
+
+
+# ---- stream parsing: K/io/CompressedInputStream.java:359-475 (readHeader, version 7), :1025-1095 (readBlockHeader),
+#      :1113-1340 (decodeBlock), Sequence.inverse K/transform/Sequence.java:137-207 -------------------------------------------------
+def parse_and_decode_stream(stream, bwt_bounds=1):
+    """A .knz walked the way CompressedInputStream does, with the oracle's codecs as black boxes for the payloads: header fields and
+    check, per block the length prefix, mode byte, skip flags, length bytes, header check byte, block checksum, entropy stage or copy,
+    inverse transforms in reverse order under the skip flags.  -> (decoded bytes, header dict)"""
+    names = {v: k for k, v in O.T.items()}
+    enames = {v: k for k, v in O.E.items()}
+    b = _BitsIn(stream, 8 * len(stream))
+    H = 0x1E35A7BD
+    assert b.read(32) == 0x4B414E5A
+    version = b.read(4)
+    assert version == 7
+    chk = b.read(2)
+    assert chk != 3
+    entropy = b.read(5)
+    ttype = b.read(48)
+    block_size = b.read(28) << 4
+    sz_mask = b.read(2)
+    out_size = b.read(16 * sz_mask) if sz_mask else 0
+    b.read(15)
+    crc = b.read(24)
+    c = (H * ((0x01030507 * version) & 0xFFFFFFFF)) & 0xFFFFFFFF
+    for v in [chk, entropy, ttype >> 32, ttype & 0xFFFFFFFF, block_size] + ([out_size >> 32, out_size & 0xFFFFFFFF] if sz_mask else []):
+        c = _mix32(c, H, v)
+    assert crc == ((c >> 23) ^ (c >> 3)) & 0xFFFFFF
+    slots = [(ttype >> (42 - 6 * i)) & 63 for i in range(8)]
+    nbtr = max(sum(1 for t in slots if t != 0), 1)
+    fns = [t for i, t in enumerate(slots[:nbtr]) if t != 0 or i == 0]          # TransformFactory.newFunction (:240-264)
+    out = bytearray()
+    while True:
+        lr = b.read(5) + 3
+        read = b.read(lr)
+        if read == 0:
+            break
+        # the record's bits as bytes of their own: Java copies them into data.array before it parses them
+        recv = (b.v >> (b.total - b.pos - read)) & ((1 << read) - 1)
+        b.pos += read
+        rb = (recv << ((-read) % 8)).to_bytes((read + 7) // 8, "big")
+        r = _BitsIn(rb, read)
+        mode = r.read(8)
+        copy = (mode & 0x80) != 0
+        has_skip, transformed_copy, skip = False, False, 0
+        if copy:
+            if mode & 0x10:
+                transformed_copy = True
+                if len(fns) > 4:
+                    has_skip = True
+                else:
+                    skip = ((mode << 4) | 0x0F) & 0xFF
+        elif mode & 0x10:
+            has_skip = True
+        else:
+            skip = ((mode << 4) | 0x0F) & 0xFF
+        if has_skip:
+            skip = r.read(8)
+        data_size = 1 + ((mode >> 5) & 3)
+        pre = 0
+        for _ in range(data_size):
+            pre = (pre << 8) | r.read(8)
+        check = r.read(8)
+        c = (H * 0x01030507) & 0xFFFFFFFF
+        for v in (mode, skip, pre, read >> 32, read & 0xFFFFFFFF):
+            c = _mix32(c, H, v)
+        assert check == ((c >> 23) ^ (c >> 3)) & 0xFF
+        assert 0 < pre <= min(max(block_size + block_size // 2, 2048), 1 << 30)
+        cks = r.read(32) if chk == 1 else (r.read(64) if chk == 2 else None)
+        raw_copy = copy and not transformed_copy
+        ent = "NONE" if (raw_copy or transformed_copy) else enames[entropy]
+        payload = rb[r.pos // 8:]
+        assert r.pos % 8 == 0
+        cur, ret, _ = O.entropy_decode(ent, payload, read - r.pos, pre)
+        assert ret == pre
+        if not raw_copy and skip != 0xFF:
+            for i in range(len(fns) - 1, -1, -1):
+                if skip & (1 << (7 - i)):
+                    continue
+                cap = max(block_size, len(cur)) + 1024
+                ok, cur, _, _ = O.transform(names[fns[i]], cur, inverse=True, dst_cap=cap, dst_len=cap, src_cap=len(cur) + 16, ctx=[7, block_size, len(cur), 1, 0, bwt_bounds])
+                assert ok == 1, (names[fns[i]], i)
+        if chk == 1:
+            assert cks == O.xxhash32(cur, 0x4B414E5A) & 0xFFFFFFFF
+        elif chk == 2:
+            assert cks == O.xxhash64(cur, 0x4B414E5A) & M64
+        out += cur
+    return bytes(out), dict(entropy=entropy, transforms=fns, block_size=block_size, out_size=out_size, checksum=chk)
+
+
+@pytest.mark.parametrize("transforms,entropy,bs,checksum", [(["LZ"], "HUFFMAN", 65536, 0), (["BWT", "RANK", "ZRLT"], "ANS0", 32768, 32), (["ROLZ"], "NONE", 65536, 64),
+                                                            (["NONE"], "FPAQ", 4096, 0), (["LZX"], "ANS1", 1 << 20, 32), (["LZ", "RANK", "ZRLT", "SRT", "MTFT"], "HUFFMAN", 16384, 0),
+                                                            (["LZP", "ZRLT"], "ANS0", 65536, 0), (["RLT", "ROLZX"], "RANGE", 131072, 64)])
+def test_stream_parsing_agrees_with_the_oracle(transforms, entropy, bs, checksum):
+    from kanzi_b200 import synth
+    r = np.random.default_rng(5)
+    data = synth.pasted(100000, 3).tobytes() + bytes(r.integers(0, 256, 70000, dtype=np.uint8)) + synth.records(40000 + 9, 4).tobytes() + bytes(30000)
+    for d in (data, data[:bs + 7], data[:12]):
+        knz = O.compress(d, transforms, entropy, bs, checksum=checksum)
+        got, hdr = parse_and_decode_stream(knz)
+        assert got == d == O.decompress(knz, len(d) + 64)
+        assert hdr["block_size"] == bs and hdr["out_size"] == len(d) and hdr["checksum"] == {0: 0, 32: 1, 64: 2}[checksum]
+        assert hdr["transforms"] == [O.T[t] for t in transforms if t != "NONE"] or transforms == ["NONE"]
