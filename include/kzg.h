@@ -115,7 +115,8 @@ int64_t kzg_coalescing_stats(int64_t* batches);
  * consume (COS:236-313,733-1054; CIS:359-515,1025-1378) for `nTransforms` chained ids + one entropy id,
  * with every block of the input in flight at once on the calling thread's device.  Host buffers.
  * kzg_compress: returns the .knz byte length (<0 on error).  kzg_decompress: returns decoded bytes.
- * flags: KZG_FLAG_BWT_ASREF | KZG_FLAG_XXH32 / KZG_FLAG_XXH64.
+ * flags: KZG_FLAG_BWT_ASREF | KZG_FLAG_XXH32 / KZG_FLAG_XXH64.  KZG_T_NONE entries of `transforms` are dropped before anything else, as
+ * TransformFactory.getType drops the NONE tokens of a "-t A+NONE+B" list (K/transform/TransformFactory.java:140-153).
  * Capacities: kzg_compress needs outCap >= kzg_compress_bound(n, blockSize) to be sure of success (a smaller buffer
  * fails with -KZG_ERR_WRITE_FILE only if the stream really does not fit).  kzg_decompress needs outCap >= the decoded size
  * and never writes beyond `out + outCap`: every block but the last decodes to blockSize bytes, the last to what is left

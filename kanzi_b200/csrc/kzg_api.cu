@@ -789,9 +789,13 @@ static int64_t compress_impl(const uint8_t* d_in, int64_t n, const int32_t* tran
   if (blockSize > (1 << 30) || blockSize < 1024 || (blockSize & -16) != blockSize) return -KZG_ERR_BLOCK_SIZE;    // COS:165-174
   for (int i = 0; i < nTransforms; i++) if (!xf_known(transforms[i])) return -KZG_ERR_INVALID_CODEC;
   int r = ws_init(); if (r < 0) return r;
-  int fn[8]; const int nf = seq_functions(transforms, nTransforms, fn);
+  // TransformFactory.getType (:140-153) drops the NONE tokens of a "-t A+NONE+B" list before the type is formed; the Sequence and the
+  // stream header only ever see the compacted list
+  i32 tc[8]; int nc = 0;
+  for (int i = 0; i < nTransforms; i++) if (transforms[i] != KZG_T_NONE) tc[nc++] = transforms[i];
+  int fn[8]; const int nf = seq_functions(tc, nc, fn);
   u64 transformType = 0;
-  for (int i = 0; i < nTransforms && i < 8; i++) transformType |= ((u64)transforms[i] << (42 - 6 * i));
+  for (int i = 0; i < nc; i++) transformType |= ((u64)tc[i] << (42 - 6 * i));
   W.lastRecBits.clear();
   const int nBlocks = (int)((n + blockSize - 1) / blockSize);
   const i32 maxBlock = (i32)std::min<i64>(n, blockSize);

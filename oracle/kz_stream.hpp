@@ -58,9 +58,9 @@ static inline bool isExecutable(i32 m) {
 }  // namespace magic
 
 // TransformFactory.getType (TransformFactory.java:132-164): first transform in the top 6-bit slot
-static inline u64 transformTypeOf(const int* ids, int n) {
+static inline u64 transformTypeOf(const int* ids, int n) {      // TransformFactory.getType (:140-153): NONE tokens are skipped
   u64 res = 0; int shift = 42;
-  for (int i = 0; i < n && i < 8; i++) { res |= ((u64)ids[i] << shift); shift -= 6; }
+  for (int i = 0; i < n && i < 8; i++) { if (ids[i] == T_NONE) continue; res |= ((u64)ids[i] << shift); shift -= 6; }
   return res;
 }
 

@@ -200,3 +200,13 @@ def test_rolzx_streams_bit_exact(tr, ent, bs):
     got = K.compress(d, tr, ent, bs, flags=K.FLAG_BWT_ASREF)
     assert len(got) == len(ref) and got == ref, (tr, ent, len(got), len(ref), "first differing byte", first_diff(got, ref))
     assert K.decompress(ref, len(d) + 1024, flags=K.FLAG_BWT_ASREF) == d
+
+
+def test_none_tokens_are_dropped_from_a_transform_list():
+    """TransformFactory.getType (K/transform/TransformFactory.java:140-153) skips NONE tokens: the stream of "-t NONE+LZ" is the stream of "-t LZ"."""
+    d = pasted_text(600_000, 21)
+    ref = O.compress(d, ["LZ"], "ANS0", 1 << 18)
+    assert O.compress(d, ["NONE", "LZ"], "ANS0", 1 << 18) == ref
+    assert K.compress(d, ["NONE", "LZ"], "ANS0", 1 << 18, flags=K.FLAG_BWT_ASREF) == ref
+    assert K.compress(d, ["LZ", "NONE"], "ANS0", 1 << 18, flags=K.FLAG_BWT_ASREF) == ref
+    assert K.decompress(ref, len(d) + 1024, flags=K.FLAG_BWT_ASREF) == d

@@ -168,3 +168,11 @@ def test_checksummed_streams_round_trip_and_detect_corruption():
         bad[len(bad) // 2] ^= 0x04
         with pytest.raises(RuntimeError):
             O.decompress(bytes(bad), len(d) + 64)
+
+
+def test_none_tokens_are_dropped_from_a_transform_list():
+    # TransformFactory.getType (K/transform/TransformFactory.java:140-153): "-t BWT+NONE+RANK+ZRLT" is the type of "BWT+RANK+ZRLT"
+    d = corpus.small_cases()["text64k"]
+    assert O.compress(d, ["BWT", "NONE", "RANK", "ZRLT"], "ANS1", 32768, bwt_bounds=0) == O.compress(d, ["BWT", "RANK", "ZRLT"], "ANS1", 32768, bwt_bounds=0)
+    assert O.compress(d, ["NONE", "LZ"], "ANS0", 32768) == O.compress(d, ["LZ"], "ANS0", 32768)
+    assert O.stream_header(["NONE", "NONE"], "HUFFMAN", 65536, 100) == O.stream_header(["NONE"], "HUFFMAN", 65536, 100)
