@@ -1538,6 +1538,114 @@ struct ROLZ2 : Transform {
   }
 };
 
+// ---- BWTS (transform/BWTS.java): the bijective Burrows-Wheeler transform (Scott), no primary index.  Not on the CUDA path
+// (SURVEY §8f rank 3); here so that the checker is ready.  Suffix array from the oracle's own SA-IS (any correct suffix sort will do).
+struct BWTS : Transform {
+  enum { MAX_BLOCK_SIZE = 1024 * 1024 * 1024 };
+  static bool guards(const Slice& src, const Slice& dst) {                  // BWTS.java:63-83
+    if ((src.index < 0) || (dst.index < 0) || (src.length < 0) || (dst.length <= 0) || (src.index > src.length) || (dst.index > dst.length) ||
+        ((i64)src.index + src.length > src.cap()) || ((i64)dst.index + dst.length > dst.cap())) return false;
+    if (src.arr == dst.arr) return false;
+    const int count = src.length;
+    if ((count > src.length - src.index) || (count > dst.length - dst.index)) return false;
+    if (count > MAX_BLOCK_SIZE) return false;
+    if (dst.index + count > dst.cap()) return false;
+    return true;
+  }
+  // moveLyndonWordHead, :163-197
+  static int moveLyndonWordHead(std::vector<int>& sa, std::vector<int>& isa, const u8* data, int count, int start, int size, int rank) {
+    const int end = start + size;
+    while (rank + 1 < count) {
+      const int nextStart0 = sa[rank + 1];
+      if (nextStart0 <= end) break;
+      int nextStart = nextStart0, k = 0;
+      while ((k < size) && (nextStart < count) && (data[start + k] == data[nextStart])) { k++; nextStart++; }
+      if ((k == size) && (nextStart >= count)) throw JavaException("AIOOBE in BWTS.moveLyndonWordHead");
+      if ((k == size) && (rank < isa[nextStart])) break;
+      if ((k < size) && (nextStart < count) && (data[start + k] < data[nextStart])) break;
+      sa[rank] = nextStart0;
+      isa[nextStart0] = rank;
+      rank++;
+    }
+    sa[rank] = start;
+    isa[start] = rank;
+    return rank;
+  }
+  // forward, :60-160
+  bool forward(Slice& src, Slice& dst) override {
+    if (src.length == 0) return true;
+    if (!guards(src, dst)) return false;
+    const int count = src.length;
+    const u8* input = src.p() + src.index; u8* output = dst.p() + dst.index;
+    if (count < 2) { output[0] = input[0]; src.index++; dst.index++; return true; }
+    std::vector<int> sa, isa((size_t)count, 0);                  // (Java: int[count] each; an index of `count` throws there and here)
+    sais::suffixArray(input, count, sa);
+    for (int i = 0; i < count; i++) isa[sa[i]] = i;
+    int min = isa[0], idxMin = 0;
+    for (int i = 1; (i < count) && (min > 0); i++) {
+      if (isa[i] >= min) continue;
+      int refRank = moveLyndonWordHead(sa, isa, input, count, idxMin, i - idxMin, min);
+      for (int j = i - 1; j > idxMin; j--) {
+        int testRank = isa[j];
+        const int startRank = testRank;
+        while (testRank < count - 1) {
+          const int nextRankStart = sa[testRank + 1];
+          if ((j > nextRankStart) || (input[j] != input[nextRankStart])) break;
+          if (nextRankStart + 1 >= count) throw JavaException("AIOOBE in BWTS.forward");
+          if (refRank < isa[nextRankStart + 1]) break;
+          sa[testRank] = nextRankStart;
+          isa[nextRankStart] = testRank;
+          testRank++;
+        }
+        sa[testRank] = j;
+        isa[j] = testRank;
+        refRank = testRank;
+        if (startRank == testRank) break;
+      }
+      min = isa[i];
+      idxMin = i;
+    }
+    min = count;
+    auto before = [&](int i) -> u8 { if (i < 1) throw JavaException("AIOOBE in BWTS.forward"); return input[i - 1]; };   // input[srcIdx - 1 + i]
+    for (int i = 0; i < count; i++) {
+      if (isa[i] >= min) { output[isa[i]] = before(i); continue; }
+      if (min < count) output[min] = before(i);
+      min = isa[i];
+    }
+    output[0] = input[count - 1];
+    src.index += count; dst.index += count;
+    return true;
+  }
+  // inverse, :200-262
+  bool inverse(Slice& src, Slice& dst) override {
+    if (src.length == 0) return true;
+    if (!guards(src, dst)) return false;
+    const int count = src.length;
+    const u8* input = src.p() + src.index; u8* output = dst.p() + dst.index;
+    if (count < 2) { output[0] = input[0]; src.index++; dst.index++; return true; }
+    int buckets[256] = {0};
+    std::vector<int> lf((size_t)count, 0);
+    for (int i = 0; i < count; i++) buckets[input[i]]++;
+    for (int i = 0, sum = 0; i < 256; i++) { sum += buckets[i]; buckets[i] = sum - buckets[i]; }
+    for (int i = 0; i < count; i++) lf[i] = buckets[input[i]]++;
+    for (int i = 0, j = count - 1; j >= 0; i++) {
+      if (i >= count) throw JavaException("AIOOBE in BWTS.inverse");
+      if (lf[i] < 0) continue;
+      int p = i;
+      do {
+        output[j] = input[p];
+        j--;
+        const int t = lf[p];
+        lf[p] = -1;
+        p = t;
+      } while (lf[p] >= 0);
+    }
+    src.index += count; dst.index += count;
+    return true;
+  }
+  int getMaxEncodedLength(int n) override { return n; }
+};
+
 // ---- RLT (transform/RLT.java) ---------------------------------------------------------------------------------------------------
 struct RLT : Transform {
   enum { RUN_LEN_ENCODE1 = 224, RUN_LEN_ENCODE2 = (255 - RUN_LEN_ENCODE1) << 8, RUN_THRESHOLD = 3,
@@ -1852,6 +1960,7 @@ static inline std::unique_ptr<Transform> newTransform(Ctx& ctx, int type) {
     case T_LZX: ctx.lzType = T_LZX; return std::unique_ptr<Transform>(new LZX(&ctx, true));
     case T_LZP: ctx.lzType = T_LZP; return std::unique_ptr<Transform>(new LZP());
     case T_RLT: return std::unique_ptr<Transform>(new RLT(&ctx));
+    case T_BWTS: return std::unique_ptr<Transform>(new BWTS());
     case T_ROLZ: return std::unique_ptr<Transform>(new ROLZ1(&ctx));
     case T_ROLZX: ctx.rolzExtra = 1; return std::unique_ptr<Transform>(new ROLZ2(&ctx));
     case T_BWT: return std::unique_ptr<Transform>(new BWTBlockCodec(ctx));

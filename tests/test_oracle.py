@@ -65,7 +65,7 @@ def test_entropy_roundtrip(ent):
         assert r == len(d) and out == d and used == bits, (ent, name)
 
 
-@pytest.mark.parametrize("tr", ["LZ", "LZX", "ROLZ", "ZRLT", "RANK", "MTFT", "SRT", "BWT", "LZP", "RLT", "ROLZX"])
+@pytest.mark.parametrize("tr", ["LZ", "LZX", "ROLZ", "ZRLT", "RANK", "MTFT", "SRT", "BWT", "LZP", "RLT", "ROLZX", "BWTS"])
 def test_transform_roundtrip(tr):
     applied = 0
     for name, d in CASES.items():

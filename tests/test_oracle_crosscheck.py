@@ -2692,3 +2692,44 @@ def test_stream_parsing_agrees_with_the_oracle(transforms, entropy, bs, checksum
         assert got == d == O.decompress(knz, len(d) + 64)
         assert hdr["block_size"] == bs and hdr["out_size"] == len(d) and hdr["checksum"] == {0: 0, 32: 1, 64: 2}[checksum]
         assert hdr["transforms"] == [O.T[t] for t in transforms if t != "NONE"] or transforms == ["NONE"]
+
+
+# ---- BWTS by definition (K/transform/BWTS.java:60-160; Gil & Scott's bijective BWT): factor the input into Lyndon words, sort every rotation of
+#      every factor by its infinite repetition, emit the byte before each rotation's start.  Not on the CUDA path; the oracle carries it.
+def bwts_by_definition(d):
+    n = len(d)
+    factors = []
+    i = 0
+    while i < n:                                                   # Duval
+        j, k = i + 1, i
+        while j < n and d[k] <= d[j]:
+            k = i if d[k] < d[j] else k + 1
+            j += 1
+        while i <= k:
+            factors.append(d[i:i + j - k])
+            i += j - k
+    rots = []
+    for w in factors:
+        for r in range(len(w)):
+            rots.append((w[r:] + w[:r], w[r - 1]))
+    from functools import cmp_to_key
+
+    def cmp(a, b):
+        u, v = a[0], b[0]
+        m = len(u) + len(v)
+        x, y = (u * (m // len(u) + 1))[:m], (v * (m // len(v) + 1))[:m]
+        return (x > y) - (x < y)
+
+    return bytes(last for _, last in sorted(rots, key=cmp_to_key(cmp)))
+
+
+def test_bwts_matches_its_definition():
+    from kanzi_b200 import synth
+    r = np.random.default_rng(53)
+    cases = [b"banana", b"mississippi", b"abracadabra", b"aaaaaa", b"ab", b"ba", b"cba", b"abcabcabc", b"zyxzyxzy", synth.text(1500, 2).tobytes(),
+             bytes(r.integers(0, 3, 900, dtype=np.uint8)), bytes(r.integers(0, 256, 1200, dtype=np.uint8)), bytes(100), b"ab" * 300 + b"a"]
+    for d in cases:
+        ok, out, _, _ = O.transform("BWTS", d)
+        assert ok == 1 and out == bwts_by_definition(d), (len(d), out[:20])
+        assert O.transform("BWTS", out, inverse=True, dst_cap=len(d), dst_len=len(d))[:2] == (1, d)
+    assert O.transform("BWTS", b"banana")[1] == b"annbaa"             # the textbook example

@@ -52,6 +52,7 @@ records_rlt_ans0|records|300000|20|RLT|ANS0|65536
 text_rolzx_none|text|300000|21|ROLZX|NONE|131072
 exe_rolzx_ans0|exe_like|300000|22|ROLZX|ANS0|262144
 text_none_range|text|200000|23|NONE|RANGE|65536
+text_bwts_rank_zrlt_ans0|text|262144|24|BWTS+RANK+ZRLT|ANS0|131072
 CASES
 echo ']}' >> "$MAN"
 echo "wrote $MAN; commit tests/golden/ and run: python -m pytest tests/test_golden.py -q"
